@@ -553,7 +553,24 @@ int orc_roi(const OrcInfo *o, const int16_t crop[4], int *x0, int *y0, int *w, i
 
 /* Assemble the caller-visible output. dst[c]/dst_pitch[c] follow RocJpegImage;
  * a channel with a null pointer or zero pitch is skipped
- * (src/rocjpeg_decoder.cpp:373). Only the valid bytes of each row are written. */
+ * (src/rocjpeg_decoder.cpp:373). Only the valid bytes of each row are written.
+ *
+ * Region of interest. Without a crop rectangle every format follows the
+ * reference byte for byte. With one:
+ *   - NATIVE is a raw copy of the VCN surface at the reference's byte offsets
+ *     (CopyChannel, decoder.cpp:376-389): top*pitch + left, chroma rows from
+ *     top>>1 for 4:2:0 / 4:4:0, left*2 for packed YUYV;
+ *   - Y, YUV_PLANAR, RGB and RGB_PLANAR are the geometric crop of the
+ *     full-picture result: out(x, y) = full(left + x, top + y), chroma sample
+ *     ((left+x)>>sx, (top+y)>>sy); planar chroma starts at (left>>sx, top>>sy)
+ *     and is (W>>sx) x (H>>sy). For even left/top this is what the reference
+ *     computes for 4:2:2 / 4:2:0 / 4:0:0. It deliberately does NOT reproduce
+ *     three reference defects, which read the wrong samples (or out of
+ *     bounds): RGB from 4:4:4 adds the ROI offset to the chroma planes twice
+ *     (decoder.cpp:464-466 with hip_kernels.cpp:66-68), RGB from 4:4:0 offsets
+ *     chroma by `top` instead of `top>>1` rows (decoder.cpp:468-470), and an
+ *     odd `left` swaps U and V for 4:2:0 / mis-phases YUYV (decoder.cpp:456-461).
+ */
 int orc_convert(const OrcInfo *o, const uint8_t *planes, int fmt, const int16_t crop[4],
                 uint8_t *dst[4], const uint32_t dst_pitch[4]) {
     Surf s;
@@ -572,59 +589,55 @@ int orc_convert(const OrcInfo *o, const uint8_t *planes, int fmt, const int16_t 
     int roi = orc_roi(o, crop, &x0, &y0, &W, &H);
     if (roi < 0) return ORC_INVALID;
     int css = o->css;
+    int sx = (css == CSS_422 || css == CSS_420) ? 1 : 0;   /* chroma shift, horizontal */
+    int sy = (css == CSS_440 || css == CSS_420) ? 1 : 0;   /* chroma shift, vertical */
 #define CH_OK(c) (dst[c] != NULL && dst_pitch[c] != 0)
     switch (fmt) {
-    case FMT_NATIVE:
-    case FMT_YUV_PLANAR:
-    case FMT_Y: {
-        /* luma: decoder.cpp:149, :593, :629-633 (YUYV: even bytes from 2*left) */
-        if (CH_OK(0) && !(fmt == FMT_NATIVE && css == CSS_422))
+    case FMT_NATIVE: {
+        if (css == CSS_422) {
+            /* packed YUYV, byte offset top*pitch + 2*left (decoder.cpp:384-388) */
+            if (CH_OK(0))
+                for (int y = 0; y < H; y++)
+                    for (int j = 0; j < 2 * W; j++)
+                        dst[0][(size_t)y * dst_pitch[0] + j] = yuyv_at(&s, y0 + y, 2 * x0 + j);
+            break;
+        }
+        if (CH_OK(0))
             for (int y = 0; y < H; y++)
                 for (int x = 0; x < W; x++) dst[0][(size_t)y * dst_pitch[0] + x] = pl_at(&s, 0, x0 + x, y0 + y);
-        if (fmt == FMT_Y || css == CSS_400) break;
         if (css == CSS_444 || css == CSS_440) {
-            /* decoder.cpp:157-158, :600-601 with CopyChannel's roi rule :376-389 */
-            int ch = (css == CSS_440) ? (H >> 1) : H;
-            int cy0 = (css == CSS_440) ? (y0 >> 1) : y0;
+            /* decoder.cpp:157-158 with CopyChannel's roi rule :376-389 */
+            int ch = H >> sy, cy0 = y0 >> sy;
             for (int c = 1; c < 3; c++)
                 if (CH_OK(c))
                     for (int y = 0; y < ch; y++)
                         for (int x = 0; x < W; x++)
                             dst[c][(size_t)y * dst_pitch[c] + x] = pl_at(&s, c, x0 + x, cy0 + y);
-        } else if (css == CSS_422) {
-            if (fmt == FMT_NATIVE) {
-                /* packed YUYV, byte offset top*pitch + 2*left (decoder.cpp:384-388) */
-                if (CH_OK(0))
-                    for (int y = 0; y < H; y++)
-                        for (int j = 0; j < 2 * W; j++)
-                            dst[0][(size_t)y * dst_pitch[0] + j] = yuyv_at(&s, y0 + y, 2 * x0 + j);
-            } else {
-                /* ConvertPackedYUYVToPlanarYUV (hip_kernels.cpp:2186-2233); U and V
-                 * both use pitch[1] (decoder.cpp:589-590) */
-                for (int y = 0; y < H; y++)
-                    for (int k = 0; k < (W >> 1); k++) {
-                        if (CH_OK(1)) dst[1][(size_t)y * dst_pitch[1] + k] = yuyv_at(&s, y0 + y, 2 * x0 + 4 * k + 1);
-                        if (dst[2] != NULL && dst_pitch[1] != 0)
-                            dst[2][(size_t)y * dst_pitch[1] + k] = yuyv_at(&s, y0 + y, 2 * x0 + 4 * k + 3);
-                    }
-            }
         } else if (css == CSS_420) {
-            int ch = H >> 1, cy0 = y0 >> 1;
-            if (fmt == FMT_NATIVE) {
-                /* interleaved UV rows, byte offset (top>>1)*pitch + left (decoder.cpp:380-388) */
-                if (CH_OK(1))
-                    for (int y = 0; y < ch; y++)
-                        for (int j = 0; j < W; j++)
-                            dst[1][(size_t)y * dst_pitch[1] + j] = nv12uv_at(&s, cy0 + y, x0 + j);
-            } else {
-                /* ConvertInterleavedUVToPlanarUV(W>>1, H>>1, pitch[1]) (decoder.cpp:596-597) */
-                for (int y = 0; y < ch; y++)
-                    for (int k = 0; k < (W >> 1); k++) {
-                        if (CH_OK(1)) dst[1][(size_t)y * dst_pitch[1] + k] = nv12uv_at(&s, cy0 + y, x0 + 2 * k);
-                        if (dst[2] != NULL && dst_pitch[1] != 0)
-                            dst[2][(size_t)y * dst_pitch[1] + k] = nv12uv_at(&s, cy0 + y, x0 + 2 * k + 1);
-                    }
-            }
+            /* interleaved UV rows, byte offset (top>>1)*pitch + left (decoder.cpp:380-388) */
+            if (CH_OK(1))
+                for (int y = 0; y < (H >> 1); y++)
+                    for (int j = 0; j < W; j++)
+                        dst[1][(size_t)y * dst_pitch[1] + j] = nv12uv_at(&s, (y0 >> 1) + y, x0 + j);
+        }
+        break;
+    }
+    case FMT_YUV_PLANAR:
+    case FMT_Y: {
+        if (CH_OK(0))
+            for (int y = 0; y < H; y++)
+                for (int x = 0; x < W; x++) dst[0][(size_t)y * dst_pitch[0] + x] = pl_at(&s, 0, x0 + x, y0 + y);
+        if (fmt == FMT_Y || css == CSS_400) break;
+        /* chroma at the coded resolution. 4:4:4 / 4:4:0 honour each channel's own
+         * pitch (CopyChannel, decoder.cpp:600-601); 4:2:2 / 4:2:0 write U and V
+         * with pitch[1] (decoder.cpp:589-590, 596-597). */
+        int cw = W >> sx, ch = H >> sy, cx0 = x0 >> sx, cy0 = y0 >> sy;
+        for (int c = 1; c < 3; c++) {
+            uint32_t pitch = (sx == 0) ? dst_pitch[c] : dst_pitch[1];
+            if (dst[c] == NULL || pitch == 0) continue;
+            for (int y = 0; y < ch; y++)
+                for (int x = 0; x < cw; x++)
+                    dst[c][(size_t)y * pitch + x] = pl_at(&s, c, cx0 + x, cy0 + y);
         }
         break;
     }
@@ -634,30 +647,14 @@ int orc_convert(const OrcInfo *o, const uint8_t *planes, int fmt, const int16_t 
         if (fmt == FMT_RGB_PLANAR && (!dst[0] || !dst[1] || !dst[2] || !dst_pitch[0])) break;
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++) {
-                uint8_t yy = pl_at(&s, 0, x0 + x, y0 + y), uu = 128, vv = 128, r, g, b;
-                switch (css) {
-                case CSS_444: /* decoder.cpp:464-466: same offset for all planes */
-                    uu = pl_at(&s, 1, x0 + x, y0 + y);
-                    vv = pl_at(&s, 2, x0 + x, y0 + y);
-                    break;
-                case CSS_440: /* decoder.cpp:468-470: chroma ROI offset is NOT applied */
-                    uu = pl_at(&s, 1, x, y >> 1);
-                    vv = pl_at(&s, 2, x, y >> 1);
-                    break;
-                case CSS_422: /* decoder.cpp:458-461,472-474; hip_kernels.cpp:947-954 */
-                    uu = yuyv_at(&s, y0 + y, 2 * x0 + 4 * (x >> 1) + 1);
-                    vv = yuyv_at(&s, y0 + y, 2 * x0 + 4 * (x >> 1) + 3);
-                    break;
-                case CSS_420: /* decoder.cpp:456-457,476-479; hip_kernels.cpp:1389-1429 */
-                    uu = nv12uv_at(&s, (y0 >> 1) + (y >> 1), x0 + 2 * (x >> 1));
-                    vv = nv12uv_at(&s, (y0 >> 1) + (y >> 1), x0 + 2 * (x >> 1) + 1);
-                    break;
-                default:
-                    break;
-                }
+                int X = x0 + x, Y = y0 + y;
+                uint8_t yy = pl_at(&s, 0, X, Y), r, g, b;
                 if (css == CSS_400) {
                     r = g = b = yy; /* hip_kernels.cpp:1915-1927 */
                 } else {
+                    /* nearest-neighbour chroma: hip_kernels.cpp:76-89 (444), :585-617 (440),
+                     * :947-954 (422), :1389-1429 (420) */
+                    uint8_t uu = pl_at(&s, 1, X >> sx, Y >> sy), vv = pl_at(&s, 2, X >> sx, Y >> sy);
                     rgb_from_yuv(yy, uu, vv, &r, &g, &b);
                 }
                 if (fmt == FMT_RGB) {
