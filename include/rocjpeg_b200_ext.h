@@ -1,0 +1,92 @@
+/* rocjpeg_b200_ext.h — extension entry points of the B200-native librocjpeg.so.
+ *
+ * The drop-in boundary is include/rocjpeg.h (the reference's api/rocjpeg.h,
+ * unchanged). The functions below are ADDITIONS used by this repository's
+ * parity tests and bench.py; nothing in the reference binds them:
+ *   - stage taps, so that the intermediate results the reference never exposes
+ *     (they live inside the VCN engine, src/rocjpeg_vaapi_decoder.cpp:677-689)
+ *     can be compared with the oracle: quantised coefficients (vs libjpeg-turbo
+ *     jpeg_read_coefficients) and decoded component planes (vs jpeg_read_raw_data);
+ *   - a split prepare/run form of rocJpegDecodeBatched (api/rocjpeg.h:331) so the
+ *     device-resident throughput ("inputs already in HBM") can be timed apart
+ *     from the host->device copy;
+ *   - per-stage CUDA-event timings and batch statistics for the roofline report;
+ *   - parser taps (host only; usable without a GPU).
+ * Plain C ABI: pointers and sizes only.
+ */
+#ifndef ROCJPEG_B200_EXT_H
+#define ROCJPEG_B200_EXT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "rocjpeg.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define ROCJPEG_B200_STAGE_COUNT 7 /* upload, clear, huffman-sync, huffman-write, dc, idct, output */
+
+typedef struct {
+    float stage_ms[ROCJPEG_B200_STAGE_COUNT]; /* CUDA-event time of each stage on the decoder's stream */
+    float total_ms;                           /* first to last event */
+    uint32_t sync_rounds;                     /* k1_sync launches (2 when the stream self-synchronises) */
+    uint32_t decodes_per_round[8];            /* subsequence decodes performed in each round */
+    uint64_t scan_bytes;                      /* destuffed entropy-coded bytes in the batch */
+    uint64_t blocks;                          /* 8x8 blocks decoded */
+    uint64_t subsequences;
+    uint64_t plane_bytes;                     /* component-plane bytes written by the IDCT stage */
+    uint64_t output_bytes;                    /* bytes written to the caller's buffers */
+    uint64_t h2d_bytes, d2h_bytes;            /* host<->device traffic of the last call */
+    uint32_t kernel_launches;                 /* kernels launched by the last call */
+    int32_t subsequence_bytes;                /* S chosen for the batch */
+} RocJpegB200Stats;
+
+/* Enable/disable CUDA-event stage timing on a decoder handle (off by default; env ROCJPEG_B200_PROFILE=1). */
+RocJpegStatus rocJpegB200SetProfiling(RocJpegHandle handle, int enable);
+/* Statistics of the last rocJpegDecode / rocJpegDecodeBatched / rocJpegB200Run on this handle. */
+RocJpegStatus rocJpegB200GetStats(RocJpegHandle handle, RocJpegB200Stats *stats);
+
+/* Split form of rocJpegDecodeBatched: Prepare parses nothing new — it builds the batch description
+ * and copies descriptors + entropy-coded bytes to the device; Run launches every stage on the
+ * resident batch and synchronises. Run may be called repeatedly. */
+RocJpegStatus rocJpegB200Prepare(RocJpegHandle handle, RocJpegStreamHandle *jpeg_stream_handles, int batch_size,
+                                 const RocJpegDecodeParams *decode_params, RocJpegImage *destinations);
+RocJpegStatus rocJpegB200Run(RocJpegHandle handle);
+
+/* Stage taps for image `index` of the last decoded batch. Layout = the oracle's: component-major,
+ * each component an MCU-padded raster of blocks (64 int16, natural order) / samples (u8). */
+RocJpegStatus rocJpegB200GetCoefficients(RocJpegHandle handle, int index, int16_t *host_out, size_t count);
+RocJpegStatus rocJpegB200GetPlanes(RocJpegHandle handle, int index, uint8_t *host_out, size_t count);
+
+/* Parser taps (host only). */
+typedef struct {
+    int32_t width, height, num_components, chroma_subsampling;
+    int32_t h_sampling[3], v_sampling[3], quant_selector[3], dc_selector[3], ac_selector[3];
+    int32_t restart_interval;
+    uint32_t num_mcus;                /* as the reference computes it (src/rocjpeg_parser.cpp:197) */
+    uint32_t scan_offset, scan_size;  /* entropy-coded slice inside the caller's buffer */
+    int32_t mcus_x, mcus_y, blocks_per_mcu;
+    int32_t blocks_w[3], blocks_h[3];
+    uint32_t num_segments;            /* restart intervals */
+    uint32_t restart_markers_seen;
+    uint64_t clean_bytes;             /* destuffed stream incl. per-segment padding */
+    int32_t decode_status;            /* RocJpegStatus rocJpegDecode would return for this stream */
+    int32_t staging_is_pinned;
+} RocJpegB200StreamInfo;
+RocJpegStatus rocJpegB200StreamGetInfo(RocJpegStreamHandle jpeg_stream_handle, RocJpegB200StreamInfo *info);
+/* Copy the destuffed bytes of restart interval `segment` (returns its length via *nbytes). */
+RocJpegStatus rocJpegB200StreamGetSegment(RocJpegStreamHandle jpeg_stream_handle, uint32_t segment, uint8_t *out,
+                                          size_t capacity, uint32_t *nbytes);
+/* Tables as the decoder sees them: quantiser steps in natural order; Huffman BITS/HUFFVAL. */
+RocJpegStatus rocJpegB200StreamGetQuantTable(RocJpegStreamHandle jpeg_stream_handle, int id, uint16_t out_natural[64]);
+RocJpegStatus rocJpegB200StreamGetHuffmanTable(RocJpegStreamHandle jpeg_stream_handle, int is_ac, int id, uint8_t bits[16],
+                                               uint8_t vals[256], uint32_t *count);
+
+const char *rocJpegB200Version(void);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* ROCJPEG_B200_EXT_H */

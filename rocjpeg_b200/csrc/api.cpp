@@ -1,0 +1,336 @@
+// api.cpp — the C ABI of librocjpeg.so.
+//
+// Same nine entry points, argument checks and status codes as the reference's
+// src/rocjpeg_api.cpp (null arguments -> INVALID_PARAMETER :39,69,87,108,133,162,
+// 195,223; parse failure -> BAD_JPEG :73-75; C++ exception -> RUNTIME_ERROR
+// :170-174; handle allocation failure -> NOT_INITIALIZED :45-48,113-116; error
+// names :246-277), over this repository's parser and CUDA decoder. Handle
+// wrappers mirror src/rocjpeg_api_decoder_handle.h / rocjpeg_api_stream_handle.h
+// (object + last-error string). The rocJpegB200* extension entry points are
+// declared in include/rocjpeg_b200_ext.h.
+#include <cstring>
+#include <exception>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "decoder.h"
+#include "jpeg_parser.h"
+#include "rocjpeg_b200_ext.h"
+
+#define ERR(X) std::cerr << "[ERR] " << " {" << __func__ << "} " << " " << X << std::endl;
+
+namespace {
+
+struct StreamHandle {
+    std::shared_ptr<rjb::StreamParser> parser = std::make_shared<rjb::StreamParser>();
+    std::string error;
+};
+
+struct DecoderHandle {
+    DecoderHandle(RocJpegBackend backend, int device_id) : decoder(std::make_shared<rjb::Decoder>(int(backend), device_id)) {}
+    std::shared_ptr<rjb::Decoder> decoder;
+    std::string error;
+    void CaptureError(const std::string& m) { error = m; }
+};
+
+inline rjb::DecodeParams ToParams(const RocJpegDecodeParams* p) {
+    rjb::DecodeParams d;
+    d.output_format = int32_t(p->output_format);
+    d.crop_left = p->crop_rectangle.left;
+    d.crop_top = p->crop_rectangle.top;
+    d.crop_right = p->crop_rectangle.right;
+    d.crop_bottom = p->crop_rectangle.bottom;
+    return d;
+}
+
+static_assert(sizeof(rjb::DestImage) == sizeof(RocJpegImage), "RocJpegImage layout");
+static_assert(ROCJPEG_B200_STAGE_COUNT == rjb::kStageCount, "stage count");
+
+int CollectStreams(RocJpegStreamHandle* handles, int n, std::vector<const rjb::StreamParser*>* out) {
+    out->resize(size_t(n));
+    for (int i = 0; i < n; i++) {
+        if (handles[i] == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+        (*out)[size_t(i)] = static_cast<StreamHandle*>(handles[i])->parser.get();
+    }
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+RocJpegStatus ROCJPEGAPI rocJpegStreamCreate(RocJpegStreamHandle* jpeg_stream_handle) {
+    if (jpeg_stream_handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    StreamHandle* h = nullptr;
+    try {
+        h = new StreamHandle();
+    } catch (const std::exception& e) {
+        ERR(std::string("Failed to init the rocJPEG stream handle, ") + e.what());
+        return ROCJPEG_STATUS_NOT_INITIALIZED;
+    }
+    *jpeg_stream_handle = h;
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus ROCJPEGAPI rocJpegStreamParse(const unsigned char* data, size_t length, RocJpegStreamHandle jpeg_stream_handle) {
+    if (data == nullptr || jpeg_stream_handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    auto h = static_cast<StreamHandle*>(jpeg_stream_handle);
+    try {
+        if (!h->parser->Parse(data, length)) {
+            h->error = h->parser->last_error();
+            ERR("Invalid JPEG! " + h->error);
+            return ROCJPEG_STATUS_BAD_JPEG;
+        }
+    } catch (const std::exception& e) {
+        h->error = e.what();
+        ERR(e.what());
+        return ROCJPEG_STATUS_RUNTIME_ERROR;
+    }
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus ROCJPEGAPI rocJpegStreamDestroy(RocJpegStreamHandle jpeg_stream_handle) {
+    if (jpeg_stream_handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    delete static_cast<StreamHandle*>(jpeg_stream_handle);
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus ROCJPEGAPI rocJpegCreate(RocJpegBackend backend, int device_id, RocJpegHandle* handle) {
+    if (handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    DecoderHandle* h = nullptr;
+    try {
+        h = new DecoderHandle(backend, device_id);
+    } catch (const std::exception& e) {
+        ERR(std::string("Failed to init the rocJPEG handle, ") + e.what());
+        return ROCJPEG_STATUS_NOT_INITIALIZED;
+    }
+    // as in the reference (src/rocjpeg_api.cpp:118-119) the handle is handed out before
+    // initialisation runs: a failed init still leaves the caller a handle to destroy
+    *handle = h;
+    try {
+        RocJpegStatus st = RocJpegStatus(h->decoder->Initialize());
+        if (st != ROCJPEG_STATUS_SUCCESS) h->CaptureError(h->decoder->last_error());
+        return st;
+    } catch (const std::exception& e) {
+        h->CaptureError(e.what());
+        ERR(e.what());
+        return ROCJPEG_STATUS_RUNTIME_ERROR;
+    }
+}
+
+RocJpegStatus ROCJPEGAPI rocJpegDestroy(RocJpegHandle handle) {
+    if (handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    delete static_cast<DecoderHandle*>(handle);
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus ROCJPEGAPI rocJpegGetImageInfo(RocJpegHandle handle, RocJpegStreamHandle jpeg_stream_handle, uint8_t* num_components,
+                                             RocJpegChromaSubsampling* subsampling, uint32_t* widths, uint32_t* heights) {
+    if (handle == nullptr || num_components == nullptr || subsampling == nullptr || widths == nullptr || heights == nullptr)
+        return ROCJPEG_STATUS_INVALID_PARAMETER;
+    if (jpeg_stream_handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;   // src/rocjpeg_decoder.cpp:309-311
+    auto h = static_cast<DecoderHandle*>(handle);
+    try {
+        int32_t css = 0;
+        int st = h->decoder->GetImageInfo(static_cast<StreamHandle*>(jpeg_stream_handle)->parser.get(), num_components, &css, widths, heights);
+        *subsampling = RocJpegChromaSubsampling(css);
+        return RocJpegStatus(st);
+    } catch (const std::exception& e) {
+        h->CaptureError(e.what());
+        ERR(e.what());
+        return ROCJPEG_STATUS_RUNTIME_ERROR;
+    }
+}
+
+RocJpegStatus ROCJPEGAPI rocJpegDecode(RocJpegHandle handle, RocJpegStreamHandle jpeg_stream_handle, const RocJpegDecodeParams* decode_params,
+                                       RocJpegImage* destination) {
+    if (handle == nullptr || decode_params == nullptr || destination == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    if (jpeg_stream_handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;   // src/rocjpeg_decoder.cpp:107-109
+    auto h = static_cast<DecoderHandle*>(handle);
+    try {
+        const rjb::StreamParser* s = static_cast<StreamHandle*>(jpeg_stream_handle)->parser.get();
+        int st = h->decoder->Decode(&s, 1, ToParams(decode_params), reinterpret_cast<const rjb::DestImage*>(destination));
+        if (st != 0) h->CaptureError(h->decoder->last_error());
+        return RocJpegStatus(st);
+    } catch (const std::exception& e) {
+        h->CaptureError(e.what());
+        ERR(e.what());
+        return ROCJPEG_STATUS_RUNTIME_ERROR;
+    }
+}
+
+RocJpegStatus ROCJPEGAPI rocJpegDecodeBatched(RocJpegHandle handle, RocJpegStreamHandle* jpeg_stream_handles, int batch_size,
+                                              const RocJpegDecodeParams* decode_params, RocJpegImage* destinations) {
+    if (handle == nullptr || jpeg_stream_handles == nullptr || decode_params == nullptr || destinations == nullptr)
+        return ROCJPEG_STATUS_INVALID_PARAMETER;
+    auto h = static_cast<DecoderHandle*>(handle);
+    try {
+        if (batch_size < 0) return ROCJPEG_STATUS_INVALID_PARAMETER;
+        std::vector<const rjb::StreamParser*> streams;
+        int st = CollectStreams(jpeg_stream_handles, batch_size, &streams);
+        if (st != 0) return RocJpegStatus(st);
+        st = h->decoder->Decode(streams.data(), batch_size, ToParams(decode_params), reinterpret_cast<const rjb::DestImage*>(destinations));
+        if (st != 0) h->CaptureError(h->decoder->last_error());
+        return RocJpegStatus(st);
+    } catch (const std::exception& e) {
+        h->CaptureError(e.what());
+        ERR(e.what());
+        return ROCJPEG_STATUS_RUNTIME_ERROR;
+    }
+}
+
+// src/rocjpeg_api.cpp:246-277
+const char* ROCJPEGAPI rocJpegGetErrorName(RocJpegStatus rocjpeg_status) {
+    switch (rocjpeg_status) {
+        case ROCJPEG_STATUS_SUCCESS: return "ROCJPEG_STATUS_SUCCESS";
+        case ROCJPEG_STATUS_NOT_INITIALIZED: return "ROCJPEG_STATUS_NOT_INITIALIZED";
+        case ROCJPEG_STATUS_INVALID_PARAMETER: return "ROCJPEG_STATUS_INVALID_PARAMETER";
+        case ROCJPEG_STATUS_BAD_JPEG: return "ROCJPEG_STATUS_BAD_JPEG";
+        case ROCJPEG_STATUS_JPEG_NOT_SUPPORTED: return "ROCJPEG_STATUS_JPEG_NOT_SUPPORTED";
+        case ROCJPEG_STATUS_EXECUTION_FAILED: return "ROCJPEG_STATUS_EXECUTION_FAILED";
+        case ROCJPEG_STATUS_ARCH_MISMATCH: return "ROCJPEG_STATUS_ARCH_MISMATCH";
+        case ROCJPEG_STATUS_INTERNAL_ERROR: return "ROCJPEG_STATUS_INTERNAL_ERROR";
+        case ROCJPEG_STATUS_IMPLEMENTATION_NOT_SUPPORTED: return "ROCJPEG_STATUS_IMPLEMENTATION_NOT_SUPPORTED";
+        case ROCJPEG_STATUS_HW_JPEG_DECODER_NOT_SUPPORTED: return "ROCJPEG_STATUS_HW_JPEG_DECODER_NOT_SUPPORTED";
+        case ROCJPEG_STATUS_RUNTIME_ERROR: return "ROCJPEG_STATUS_RUNTIME_ERROR";
+        case ROCJPEG_STATUS_OUTOF_MEMORY: return "ROCJPEG_STATUS_OUTOF_MEMORY";
+        case ROCJPEG_STATUS_NOT_IMPLEMENTED: return "ROCJPEG_STATUS_NOT_IMPLEMENTED";
+        default: return "UNKNOWN_ERROR";
+    }
+}
+
+// ------------------------------------------------------------------ extensions
+
+RocJpegStatus rocJpegB200SetProfiling(RocJpegHandle handle, int enable) {
+    if (handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    static_cast<DecoderHandle*>(handle)->decoder->SetProfiling(enable != 0);
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200GetStats(RocJpegHandle handle, RocJpegB200Stats* stats) {
+    if (handle == nullptr || stats == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    const rjb::BatchStats& s = static_cast<DecoderHandle*>(handle)->decoder->stats();
+    std::memset(stats, 0, sizeof(*stats));
+    for (int i = 0; i < ROCJPEG_B200_STAGE_COUNT; i++) stats->stage_ms[i] = s.stage_ms[i];
+    stats->total_ms = s.total_ms;
+    stats->sync_rounds = s.sync_rounds;
+    for (int i = 0; i < 8; i++) stats->decodes_per_round[i] = s.decodes_per_round[i];
+    stats->scan_bytes = s.scan_bytes;
+    stats->blocks = s.blocks;
+    stats->subsequences = s.subsequences;
+    stats->plane_bytes = s.plane_bytes;
+    stats->output_bytes = s.output_bytes;
+    stats->h2d_bytes = s.h2d_bytes;
+    stats->d2h_bytes = s.d2h_bytes;
+    stats->kernel_launches = s.kernel_launches;
+    stats->subsequence_bytes = s.sub_bytes;
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200Prepare(RocJpegHandle handle, RocJpegStreamHandle* jpeg_stream_handles, int batch_size,
+                                 const RocJpegDecodeParams* decode_params, RocJpegImage* destinations) {
+    if (handle == nullptr || jpeg_stream_handles == nullptr || decode_params == nullptr || destinations == nullptr || batch_size <= 0)
+        return ROCJPEG_STATUS_INVALID_PARAMETER;
+    auto h = static_cast<DecoderHandle*>(handle);
+    try {
+        std::vector<const rjb::StreamParser*> streams;
+        int st = CollectStreams(jpeg_stream_handles, batch_size, &streams);
+        if (st != 0) return RocJpegStatus(st);
+        return RocJpegStatus(h->decoder->Prepare(streams.data(), batch_size, ToParams(decode_params),
+                                                 reinterpret_cast<const rjb::DestImage*>(destinations)));
+    } catch (const std::exception& e) {
+        h->CaptureError(e.what());
+        ERR(e.what());
+        return ROCJPEG_STATUS_RUNTIME_ERROR;
+    }
+}
+
+RocJpegStatus rocJpegB200Run(RocJpegHandle handle) {
+    if (handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    auto h = static_cast<DecoderHandle*>(handle);
+    try {
+        return RocJpegStatus(h->decoder->Run());
+    } catch (const std::exception& e) {
+        h->CaptureError(e.what());
+        ERR(e.what());
+        return ROCJPEG_STATUS_RUNTIME_ERROR;
+    }
+}
+
+RocJpegStatus rocJpegB200GetCoefficients(RocJpegHandle handle, int index, int16_t* host_out, size_t count) {
+    if (handle == nullptr || host_out == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    return RocJpegStatus(static_cast<DecoderHandle*>(handle)->decoder->CopyCoefficients(index, host_out, count));
+}
+
+RocJpegStatus rocJpegB200GetPlanes(RocJpegHandle handle, int index, uint8_t* host_out, size_t count) {
+    if (handle == nullptr || host_out == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    return RocJpegStatus(static_cast<DecoderHandle*>(handle)->decoder->CopyPlanes(index, host_out, count));
+}
+
+RocJpegStatus rocJpegB200StreamGetInfo(RocJpegStreamHandle jpeg_stream_handle, RocJpegB200StreamInfo* info) {
+    if (jpeg_stream_handle == nullptr || info == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    auto h = static_cast<StreamHandle*>(jpeg_stream_handle);
+    const rjb::ParsedJpeg& p = h->parser->parsed();
+    std::memset(info, 0, sizeof(*info));
+    if (!p.valid) return ROCJPEG_STATUS_BAD_JPEG;
+    info->width = p.width; info->height = p.height; info->num_components = p.ncomp; info->chroma_subsampling = p.css;
+    for (int c = 0; c < 3; c++) {
+        info->h_sampling[c] = p.hs[c]; info->v_sampling[c] = p.vs[c]; info->quant_selector[c] = p.tq[c];
+        info->dc_selector[c] = p.td[c]; info->ac_selector[c] = p.ta[c];
+        info->blocks_w[c] = p.blocks_w[c]; info->blocks_h[c] = p.blocks_h[c];
+    }
+    info->restart_interval = p.restart_interval;
+    info->num_mcus = p.num_mcus_ref;
+    info->scan_offset = p.scan_offset; info->scan_size = p.scan_size;
+    info->mcus_x = p.mcus_x; info->mcus_y = p.mcus_y; info->blocks_per_mcu = p.bpm;
+    info->num_segments = uint32_t(p.segments.size());
+    info->restart_markers_seen = p.restart_markers_seen;
+    info->clean_bytes = p.clean_bytes;
+    info->decode_status = p.support_status;
+    info->staging_is_pinned = h->parser->clean().pinned() ? 1 : 0;
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200StreamGetSegment(RocJpegStreamHandle jpeg_stream_handle, uint32_t segment, uint8_t* out, size_t capacity,
+                                          uint32_t* nbytes) {
+    if (jpeg_stream_handle == nullptr || nbytes == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    auto h = static_cast<StreamHandle*>(jpeg_stream_handle);
+    const rjb::ParsedJpeg& p = h->parser->parsed();
+    if (!p.valid) return ROCJPEG_STATUS_BAD_JPEG;
+    if (segment >= p.segments.size()) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    const rjb::Segment& s = p.segments[segment];
+    *nbytes = s.nbytes;
+    if (out != nullptr) {
+        if (capacity < s.nbytes) return ROCJPEG_STATUS_INVALID_PARAMETER;
+        std::memcpy(out, h->parser->clean().data() + s.offset, s.nbytes);
+    }
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200StreamGetQuantTable(RocJpegStreamHandle jpeg_stream_handle, int id, uint16_t out_natural[64]) {
+    if (jpeg_stream_handle == nullptr || out_natural == nullptr || id < 0 || id >= 4) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    const rjb::ParsedJpeg& p = static_cast<StreamHandle*>(jpeg_stream_handle)->parser->parsed();
+    if (!p.valid || !p.qt_present[id]) return ROCJPEG_STATUS_BAD_JPEG;
+    std::memcpy(out_natural, p.qt_natural[id], 128);
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200StreamGetHuffmanTable(RocJpegStreamHandle jpeg_stream_handle, int is_ac, int id, uint8_t bits[16],
+                                               uint8_t vals[256], uint32_t* count) {
+    if (jpeg_stream_handle == nullptr || bits == nullptr || vals == nullptr || count == nullptr || id < 0 || id >= 2)
+        return ROCJPEG_STATUS_INVALID_PARAMETER;
+    const rjb::ParsedJpeg& p = static_cast<StreamHandle*>(jpeg_stream_handle)->parser->parsed();
+    if (!p.valid) return ROCJPEG_STATUS_BAD_JPEG;
+    const rjb::HuffSpec& t = is_ac ? p.ac[id] : p.dc[id];
+    if (!t.present) return ROCJPEG_STATUS_BAD_JPEG;
+    std::memcpy(bits, t.bits, 16);
+    std::memcpy(vals, t.vals, 256);
+    *count = t.count;
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+const char* rocJpegB200Version(void) { return "rocjpeg-b200 0.6.0 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,560 @@
+// decoder.cpp — see decoder.h. Status codes are RocJpegStatus values
+// (include/rocjpeg.h); error behaviour follows src/rocjpeg_decoder.cpp and
+// src/rocjpeg_commons.h:43-65 of the reference (print to stderr, return a code).
+#include "decoder.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+namespace rjb {
+
+namespace {
+constexpr int kSuccess = 0, kNotInitialized = -1, kInvalidParameter = -2, kBadJpeg = -3, kNotSupported = -4,
+              kOutOfMemory = -5, kExecutionFailed = -6, kNotImplemented = -12;
+
+inline size_t AlignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int EnvInt(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+#define RJB_CUDA(call)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            std::cerr << "CUDA failure: 'status: " << cudaGetErrorName(e_) << "' at " << __FILE__ << ":" << __LINE__ \
+                      << std::endl;                                                                          \
+            return Fail(e_ == cudaErrorMemoryAllocation ? kOutOfMemory : kExecutionFailed, cudaGetErrorString(e_)); \
+        }                                                                                                    \
+    } while (0)
+}  // namespace
+
+DeviceBuffer::~DeviceBuffer() {
+    if (ptr_) cudaFree(ptr_);
+}
+
+cudaError_t DeviceBuffer::Reserve(size_t bytes) {
+    if (bytes <= cap_) return cudaSuccess;
+    if (ptr_) {
+        cudaError_t e = cudaFree(ptr_);
+        ptr_ = nullptr;
+        cap_ = 0;
+        if (e != cudaSuccess) return e;
+    }
+    size_t want = AlignUp(bytes + bytes / 8, 1 << 20);
+    cudaError_t e = cudaMalloc(&ptr_, want);
+    if (e != cudaSuccess) {
+        ptr_ = nullptr;
+        return e;
+    }
+    cap_ = want;
+    return cudaSuccess;
+}
+
+Decoder::Decoder(int backend, int device_id) : backend_(backend), device_id_(device_id) {}
+
+Decoder::~Decoder() {
+    if (!initialized_) return;
+    DeviceGuard guard(device_id_);
+    for (auto& e : ev_)
+        if (e) cudaEventDestroy(e);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+int Decoder::Fail(int status, const std::string& why) {
+    err_ = why;
+    return status;
+}
+
+// src/rocjpeg_decoder.cpp:46-91 (InitHIP + InitializeDecoder)
+int Decoder::Initialize() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1) {
+        (void)cudaGetLastError();
+        std::cerr << "[ERR]  {Initialize}  ERROR: Failed to find any GPU!" << std::endl;
+        return Fail(kNotInitialized, "no CUDA device");
+    }
+    if (device_id_ < 0 || device_id_ >= count) {
+        std::cerr << "[ERR]  {Initialize}  ERROR: the requested device_id is not found!" << std::endl;
+        return Fail(kInvalidParameter, "device_id out of range");
+    }
+    if (backend_ == 1) return Fail(kNotImplemented, "ROCJPEG_BACKEND_HYBRID is not implemented");   // decoder.cpp:87-88
+    if (backend_ != 0) return Fail(kInvalidParameter, "unknown backend");
+    DeviceGuard guard(device_id_);
+    RJB_CUDA(cudaSetDevice(device_id_));
+    cudaDeviceProp prop;
+    RJB_CUDA(cudaGetDeviceProperties(&prop, device_id_));
+    sm_count_ = prop.multiProcessorCount;
+    RJB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& ev : ev_) RJB_CUDA(cudaEventCreate(&ev));
+    profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0) != 0;
+    initialized_ = true;
+    return kSuccess;
+}
+
+// src/rocjpeg_decoder.cpp:307-358
+int Decoder::GetImageInfo(const StreamParser* s, uint8_t* ncomp, int32_t* css, uint32_t* widths, uint32_t* heights) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!s || !ncomp || !css || !widths || !heights) return kInvalidParameter;
+    const ParsedJpeg& p = s->parsed();
+    *ncomp = uint8_t(p.ncomp);
+    *css = p.css;
+    widths[0] = uint32_t(p.width);
+    heights[0] = uint32_t(p.height);
+    widths[3] = heights[3] = 0;
+    switch (p.css) {
+        case CSS_444: widths[1] = widths[2] = widths[0]; heights[1] = heights[2] = heights[0]; break;
+        case CSS_440: widths[1] = widths[2] = widths[0]; heights[1] = heights[2] = heights[0] >> 1; break;
+        case CSS_422: widths[1] = widths[2] = widths[0] >> 1; heights[1] = heights[2] = heights[0]; break;
+        case CSS_420: widths[1] = widths[2] = widths[0] >> 1; heights[1] = heights[2] = heights[0] >> 1; break;
+        case CSS_400: widths[1] = widths[2] = 0; heights[1] = heights[2] = 0; break;
+        case CSS_411: widths[1] = widths[2] = widths[0] >> 2; heights[1] = heights[2] = heights[0]; break;
+        default: break;
+    }
+    return kSuccess;
+}
+
+// Bytes the output stage writes for one image (valid bytes only), mirroring the
+// sizing rules of samples/rocjpeg_samples_utils.h:318-399.
+static uint64_t OutputBytes(int css, int fmt, int W, int H) {
+    const int sx = (css == CSS_422 || css == CSS_420) ? 1 : 0, sy = (css == CSS_440 || css == CSS_420) ? 1 : 0;
+    const uint64_t luma = uint64_t(W) * H;
+    switch (fmt) {
+        case FMT_RGB:
+        case FMT_RGB_PLANAR: return 3 * luma;
+        case FMT_Y: return luma;
+        case FMT_YUV_PLANAR: return css == CSS_400 ? luma : luma + 2ull * uint64_t(W >> sx) * uint64_t(H >> sy);
+        case FMT_NATIVE:
+            if (css == CSS_400) return luma;
+            if (css == CSS_422) return 2 * luma;
+            if (css == CSS_420) return luma + uint64_t(W) * uint64_t(H >> 1);
+            return luma + 2ull * uint64_t(W) * uint64_t(H >> sy);
+        default: return 0;
+    }
+}
+
+int Decoder::BuildBatch(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
+    if (params.output_format < FMT_NATIVE || params.output_format > FMT_RGB_PLANAR)
+        return Fail(kInvalidParameter, "unknown output format");
+    batch_.assign(streams, streams + n);
+    h_images_.assign(size_t(n), ImageDesc{});
+    h_outputs_.assign(size_t(n), OutputDesc{});
+    h_segments_.clear();
+    h_img_cta0_.assign(size_t(n) + 1, 0);
+    h_img_dctile0_.assign(size_t(n) + 1, 0);
+    h_k2_tile0_.assign(size_t(n) + 1, 0);
+    h_k3_tile0_.assign(size_t(n) + 1, 0);
+    h_gather_.assign(size_t(n), GatherItem{});
+    h_lut_ptrs_.clear();
+    h_lut_hashes_.clear();
+    h_qtables_.assign(size_t(n) * 3 * 64, 1);
+    stats_ = BatchStats();
+
+    uint64_t total_clean = 0;
+    for (int i = 0; i < n; i++) {
+        if (!streams[i]) return Fail(kInvalidParameter, "null stream handle in batch");
+        const ParsedJpeg& p = streams[i]->parsed();
+        if (!p.valid) return Fail(kBadJpeg, "stream handle holds no successfully parsed JPEG");
+        if (p.support_status != kSuccess) {
+            if (p.support_status == kNotSupported)
+                std::cerr << "[ERR]  {Decode}  The JPEG image (chroma subsampling / layout / size) is not supported!" << std::endl;
+            return Fail(p.support_status, "unsupported or inconsistent JPEG");
+        }
+        if (!streams[i]->clean().data() || p.clean_bytes == 0) return Fail(kOutOfMemory, "no staging memory for the scan");
+        total_clean += p.clean_bytes;
+    }
+    // Subsequence size. Long subsequences amortise the speculative re-decodes (with interleaved
+    // 4:2:0 data a wrong start state needs about one MCU to re-synchronise); short ones only pay
+    // off when the whole batch is too small to occupy the GPU otherwise.
+    int S = EnvInt("ROCJPEG_B200_SUBSEQ", 0);
+    if (S != 32 && S != 64 && S != 128) S = (total_clean >= (256u << 10)) ? 128 : (total_clean >= (48u << 10)) ? 64 : 32;
+    stats_.sub_bytes = S;
+
+    uint64_t scan_off = 0, blk = 0, plane_off = 0;
+    uint32_t sub = 0, dctile = 0, k2tile = 0, k3tile = 0, chunk = 0;
+    all_pinned_ = true;
+    for (int i = 0; i < n; i++) {
+        const ParsedJpeg& p = streams[i]->parsed();
+        ImageDesc& im = h_images_[size_t(i)];
+        im.width = p.width; im.height = p.height; im.ncomp = p.ncomp; im.css = p.css;
+        im.mcus_x = p.mcus_x; im.mcus_y = p.mcus_y; im.bpm = p.bpm; im.restart_interval = p.restart_interval;
+        im.total_mcus = p.mcus_x * p.mcus_y;
+        int k = 0;
+        for (int c = 0; c < 3; c++) {
+            const bool have = c < p.ncomp;
+            const int H = !have ? 0 : (p.ncomp == 1 ? 1 : p.hs[c]), V = !have ? 0 : (p.ncomp == 1 ? 1 : p.vs[c]);
+            im.hs[c] = H; im.vs[c] = V;
+            im.blocks_w[c] = have ? p.blocks_w[c] : 0;
+            im.blocks_h[c] = have ? p.blocks_h[c] : 0;
+            im.comp_first_blk[c] = k;
+            for (int b = 0; b < H * V && k < kMaxBlocksPerMcu; b++, k++) {
+                im.mcu_comp[k] = uint8_t(c);
+                im.mcu_dc[k] = uint8_t(p.td[c]);
+                im.mcu_ac[k] = uint8_t(2 + p.ta[c]);
+            }
+            im.qt_index[c] = i * 3 + c;
+            if (have) std::memcpy(&h_qtables_[(size_t(i) * 3 + c) * 64], p.qt_natural[p.tq[c]], 128);
+        }
+        // Huffman table set, de-duplicated across the batch
+        int set = -1;
+        for (size_t s = 0; s < h_lut_hashes_.size(); s++)
+            if (h_lut_hashes_[s] == p.lut_hash && std::memcmp(h_lut_ptrs_[s], &p.lut, sizeof(HuffLutSet)) == 0) set = int(s);
+        if (set < 0) {
+            set = int(h_lut_ptrs_.size());
+            h_lut_ptrs_.push_back(&p.lut);
+            h_lut_hashes_.push_back(p.lut_hash);
+        }
+        im.lut_set = set;
+        // entropy-coded data
+        im.data_off = scan_off;
+        im.seg0 = uint32_t(h_segments_.size());
+        im.nseg = uint32_t(p.segments.size());
+        im.sub0 = sub;
+        const uint32_t ri = p.restart_interval > 0 ? uint32_t(p.restart_interval) : uint32_t(im.total_mcus);
+        for (size_t sgi = 0; sgi < p.segments.size(); sgi++) {
+            const Segment& sg = p.segments[sgi];
+            SegmentDesc sd;
+            sd.data_off = scan_off + sg.offset;
+            sd.nbytes = sg.nbytes;
+            sd.sub0 = sub;
+            const uint64_t mcu_first = uint64_t(sgi) * ri;
+            const uint64_t mcu_cnt = mcu_first >= uint64_t(im.total_mcus) ? 0 : std::min<uint64_t>(ri, uint64_t(im.total_mcus) - mcu_first);
+            sd.blk_first = uint32_t(mcu_first * uint64_t(p.bpm));
+            sd.blk_count = uint32_t(mcu_cnt * uint64_t(p.bpm));
+            h_segments_.push_back(sd);
+            sub += (sg.nbytes + uint32_t(S) - 1) / uint32_t(S);
+        }
+        im.nsub = sub - im.sub0;
+        sub = uint32_t(AlignUp(sub, kK1Threads));
+        h_img_cta0_[size_t(i)] = im.sub0 / kK1Threads;
+        h_gather_[size_t(i)] = GatherItem{streams[i]->clean().data(), scan_off, uint32_t(p.clean_bytes), chunk};
+        chunk += uint32_t((p.clean_bytes + 16383) / 16384);
+        all_pinned_ = all_pinned_ && streams[i]->clean().pinned();
+        scan_off += p.clean_bytes;
+        // coefficients, DC tiles
+        im.blk0 = blk;
+        im.nblocks = uint32_t(im.total_mcus) * uint32_t(p.bpm);
+        blk += im.nblocks;
+        im.dc_tile0 = dctile;
+        h_img_dctile0_[size_t(i)] = dctile;
+        dctile += uint32_t((im.total_mcus + kDcTileMcus - 1) / kDcTileMcus);
+        // planes + IDCT tiles
+        h_k2_tile0_[size_t(i)] = k2tile;
+        for (int c = 0; c < p.ncomp; c++) {
+            im.plane_pitch[c] = uint32_t(AlignUp(size_t(p.blocks_w[c]) * 8, 64));
+            im.plane_off[c] = plane_off;
+            plane_off += AlignUp(size_t(im.plane_pitch[c]) * size_t(p.blocks_h[c]) * 8, 256);
+            k2tile += uint32_t((p.blocks_w[c] + 31) / 32) * uint32_t(p.blocks_h[c]);
+            stats_.plane_bytes += uint64_t(p.blocks_w[c]) * p.blocks_h[c] * 64;
+        }
+        // output job. ROI rule: src/rocjpeg_decoder.cpp:126-131 (unsigned widths).
+        OutputDesc& od = h_outputs_[size_t(i)];
+        const uint32_t rw = uint32_t(int(params.crop_right) - int(params.crop_left));
+        const uint32_t rh = uint32_t(int(params.crop_bottom) - int(params.crop_top));
+        od.x0 = od.y0 = 0;
+        od.w = p.width;
+        od.h = p.height;
+        if (rw > 0 && rh > 0 && rw <= uint32_t(p.width) && rh <= uint32_t(p.height)) {
+            if (params.crop_left < 0 || params.crop_top < 0 || params.crop_right > p.width || params.crop_bottom > p.height)
+                return Fail(kInvalidParameter, "crop rectangle lies outside the picture");
+            od.x0 = params.crop_left; od.y0 = params.crop_top; od.w = int32_t(rw); od.h = int32_t(rh);
+        }
+        od.fmt = params.output_format;
+        for (int c = 0; c < 4; c++) {
+            od.dst[c] = dsts[i].channel[c];
+            od.dst_pitch[c] = dsts[i].pitch[c];
+        }
+        od.tiles_x = uint32_t((od.w + 255) / 256);
+        od.tiles_y = uint32_t((od.h + 7) / 8);
+        od.tile0 = k3tile;
+        h_k3_tile0_[size_t(i)] = k3tile;
+        k3tile += od.tiles_x * od.tiles_y;
+        stats_.output_bytes += OutputBytes(p.css, od.fmt, od.w, od.h);
+    }
+    h_img_cta0_[size_t(n)] = sub / kK1Threads;
+    h_img_dctile0_[size_t(n)] = dctile;
+    h_k2_tile0_[size_t(n)] = k2tile;
+    h_k3_tile0_[size_t(n)] = k3tile;
+    gather_chunks_ = chunk;
+    scan_bytes_ = scan_off;
+    coef_blocks_ = blk;
+    plane_bytes_ = plane_off;
+    nsub_total_ = sub;
+    stats_.scan_bytes = scan_off;
+    stats_.blocks = blk;
+    stats_.subsequences = sub;
+
+    k1_ = K1Args{};
+    k1_.nimages = n;
+    k1_.total_ctas = sub / kK1Threads;
+    k1_.total_dc_tiles = dctile;
+    k1_.sub_bytes = S;
+    k2_ = K2Args{};
+    k2_.nimages = n;
+    k2_.total_tiles = k2tile;
+    k3_ = K3Args{};
+    k3_.nimages = n;
+    k3_.total_tiles = k3tile;
+    return kSuccess;
+}
+
+// Descriptor block: one pinned host buffer mirrored by one device buffer, one copy.
+struct Decoder::Layout {
+    size_t images, outputs, segments, cta0, dctile0, k2tile0, k3tile0, gather, luts, qtables, total;
+};
+
+int Decoder::Upload() {
+    const size_t n = h_images_.size();
+    Layout L;
+    size_t o = 0;
+    auto place = [&](size_t bytes) { size_t at = o; o = AlignUp(o + bytes, 256); return at; };
+    L.images = place(n * sizeof(ImageDesc));
+    L.outputs = place(n * sizeof(OutputDesc));
+    L.segments = place(h_segments_.size() * sizeof(SegmentDesc));
+    L.cta0 = place((n + 1) * 4);
+    L.dctile0 = place((n + 1) * 4);
+    L.k2tile0 = place((n + 1) * 4);
+    L.k3tile0 = place((n + 1) * 4);
+    L.gather = place(n * sizeof(GatherItem));
+    L.luts = place(h_lut_ptrs_.size() * sizeof(HuffLutSet));
+    L.qtables = place(h_qtables_.size() * 2);
+    L.total = o;
+    uint8_t* h = h_desc_.Reserve(L.total);
+    if (!h) return Fail(kOutOfMemory, "descriptor staging");
+    std::memcpy(h + L.images, h_images_.data(), n * sizeof(ImageDesc));
+    std::memcpy(h + L.outputs, h_outputs_.data(), n * sizeof(OutputDesc));
+    std::memcpy(h + L.segments, h_segments_.data(), h_segments_.size() * sizeof(SegmentDesc));
+    std::memcpy(h + L.cta0, h_img_cta0_.data(), (n + 1) * 4);
+    std::memcpy(h + L.dctile0, h_img_dctile0_.data(), (n + 1) * 4);
+    std::memcpy(h + L.k2tile0, h_k2_tile0_.data(), (n + 1) * 4);
+    std::memcpy(h + L.k3tile0, h_k3_tile0_.data(), (n + 1) * 4);
+    std::memcpy(h + L.gather, h_gather_.data(), n * sizeof(GatherItem));
+    for (size_t s = 0; s < h_lut_ptrs_.size(); s++) std::memcpy(h + L.luts + s * sizeof(HuffLutSet), h_lut_ptrs_[s], sizeof(HuffLutSet));
+    std::memcpy(h + L.qtables, h_qtables_.data(), h_qtables_.size() * 2);
+    desc_bytes_ = L.total;
+
+    RJB_CUDA(d_desc_.Reserve(L.total));
+    RJB_CUDA(d_scan_.Reserve(scan_bytes_ + 512));
+    RJB_CUDA(d_coef_.Reserve(coef_blocks_ * 128 + 256));
+    RJB_CUDA(d_dcdiff_.Reserve(coef_blocks_ * 2 + 256));
+    RJB_CUDA(d_planes_.Reserve(plane_bytes_ + 512));
+    RJB_CUDA(d_state_.Reserve(nsub_total_ * 4 + 256));
+    RJB_CUDA(d_used_.Reserve(nsub_total_ * 4 + 256));
+    RJB_CUDA(d_subseg_.Reserve(nsub_total_ * 4 + 256));
+    RJB_CUDA(d_cta_partial_.Reserve(size_t(k1_.total_ctas) * 8 + 256));
+    RJB_CUDA(d_dc_partial_.Reserve(size_t(k1_.total_dc_tiles) * 12 + 256));
+    RJB_CUDA(d_counters_.Reserve(256));
+    if (!h_counters_.Reserve(256)) return Fail(kOutOfMemory, "counter staging");
+
+    uint8_t* d = d_desc_.as<uint8_t>();
+    k1_.images = reinterpret_cast<const ImageDesc*>(d + L.images);
+    k1_.segments = reinterpret_cast<const SegmentDesc*>(d + L.segments);
+    k1_.img_cta0 = reinterpret_cast<const uint32_t*>(d + L.cta0);
+    k1_.img_dctile0 = reinterpret_cast<const uint32_t*>(d + L.dctile0);
+    k1_.scan = d_scan_.as<uint8_t>();
+    k1_.luts = reinterpret_cast<const HuffLutSet*>(d + L.luts);
+    k1_.state = d_state_.as<uint32_t>();
+    k1_.used = d_used_.as<uint32_t>();
+    k1_.sub_seg = d_subseg_.as<uint32_t>();
+    k1_.cta_partial = d_cta_partial_.as<uint2>();
+    k1_.dc_partial = d_dc_partial_.as<int3>();
+    k1_.counters = d_counters_.as<uint32_t>();
+    k1_.coef = d_coef_.as<int16_t>();
+    k1_.dcdiff = d_dcdiff_.as<int16_t>();
+    k2_.images = k1_.images;
+    k2_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k2tile0);
+    k2_.qtables = reinterpret_cast<const uint16_t*>(d + L.qtables);
+    k2_.coef = k1_.coef;
+    k2_.planes = d_planes_.as<uint8_t>();
+    k3_.images = k1_.images;
+    k3_.outputs = reinterpret_cast<const OutputDesc*>(d + L.outputs);
+    k3_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k3tile0);
+    k3_.planes = k2_.planes;
+
+    RJB_CUDA(cudaMemcpyAsync(d, h, L.total, cudaMemcpyHostToDevice, stream_));
+    stats_.h2d_bytes = L.total + scan_bytes_;
+    const bool use_gather = all_pinned_ && h_images_.size() > 4 && EnvInt("ROCJPEG_B200_NO_GATHER", 0) == 0;
+    if (use_gather) {
+        RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, d_scan_.as<uint8_t>(), stream_));
+        stats_.kernel_launches++;
+    } else {
+        for (size_t i = 0; i < n; i++)
+            RJB_CUDA(cudaMemcpyAsync(d_scan_.as<uint8_t>() + h_gather_[i].dst_off, h_gather_[i].src, h_gather_[i].nbytes,
+                                     cudaMemcpyHostToDevice, stream_));
+    }
+    return kSuccess;
+}
+
+int Decoder::LaunchAll(bool include_upload) {
+    const int rounds = std::min(std::max(EnvInt("ROCJPEG_B200_SYNC_ROUNDS", 2), 1), kMaxSyncRounds);
+    auto mark = [&](int i) -> cudaError_t { return profiling_ ? cudaEventRecord(ev_[i], stream_) : cudaSuccess; };
+    RJB_CUDA(mark(0));
+    if (include_upload) {
+        int st = Upload();
+        if (st != kSuccess) return st;
+    }
+    RJB_CUDA(mark(1));
+    RJB_CUDA(cudaMemsetAsync(d_coef_.as<uint8_t>(), 0, coef_blocks_ * 128, stream_));
+    RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint8_t>(), 0, 256, stream_));
+    RJB_CUDA(mark(2));
+    for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
+    stats_.sync_rounds = uint32_t(rounds);
+    RJB_CUDA(mark(3));
+    RJB_CUDA(LaunchK1Write(k1_, stream_));
+    RJB_CUDA(mark(4));
+    RJB_CUDA(LaunchDcScan(k1_, stream_));
+    RJB_CUDA(mark(5));
+    RJB_CUDA(LaunchK2Idct(k2_, stream_));
+    RJB_CUDA(mark(6));
+    RJB_CUDA(LaunchK3Output(k3_, stream_));
+    RJB_CUDA(mark(7));
+    stats_.kernel_launches += uint32_t(rounds) + 1 + 2 + 1 + 1 + 2;   // + the two memset launches
+    RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), d_counters_.as<uint8_t>(), 256, cudaMemcpyDeviceToHost, stream_));
+    stats_.d2h_bytes = 256;
+    return kSuccess;
+}
+
+int Decoder::Finish() {
+    RJB_CUDA(cudaStreamSynchronize(stream_));
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(h_counters_.data());
+    uint32_t last = stats_.sync_rounds - 1;
+    if (cnt[last] != 0) {
+        // The stream did not re-synchronise within the rounds launched up front: keep
+        // going until a round changes nothing at any CTA boundary, then redo everything
+        // downstream of the synchronisation.
+        uint32_t guard = 0;
+        for (;;) {
+            uint32_t slot = std::min<uint32_t>(last + 1, kMaxSyncRounds - 1);
+            RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint32_t>() + slot, 0, 4, stream_));
+            RJB_CUDA(LaunchK1Sync(k1_, int(slot), stream_));
+            RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), d_counters_.as<uint8_t>(), 256, cudaMemcpyDeviceToHost, stream_));
+            RJB_CUDA(cudaStreamSynchronize(stream_));
+            stats_.sync_rounds++;
+            stats_.kernel_launches++;
+            last = slot;
+            if (cnt[slot] == 0) break;
+            if (++guard > k1_.total_ctas + 2) return Fail(kExecutionFailed, "entropy decoder failed to converge");
+        }
+        RJB_CUDA(cudaMemsetAsync(d_coef_.as<uint8_t>(), 0, coef_blocks_ * 128, stream_));
+        RJB_CUDA(LaunchK1Write(k1_, stream_));
+        RJB_CUDA(LaunchDcScan(k1_, stream_));
+        RJB_CUDA(LaunchK2Idct(k2_, stream_));
+        RJB_CUDA(LaunchK3Output(k3_, stream_));
+        RJB_CUDA(cudaStreamSynchronize(stream_));
+        stats_.kernel_launches += 6;
+    }
+    for (int r = 0; r < kMaxSyncRounds; r++) stats_.decodes_per_round[r] = cnt[kMaxSyncRounds + r];
+    if (profiling_) {
+        for (int s = 0; s < kStageCount; s++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_[s], ev_[s + 1]) == cudaSuccess) stats_.stage_ms[s] = ms;
+        }
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev_[0], ev_[kStageCount]) == cudaSuccess) stats_.total_ms = ms;
+        (void)cudaGetLastError();
+    }
+    return kSuccess;
+}
+
+int Decoder::Decode(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!initialized_) return Fail(kNotInitialized, "decoder not initialised");
+    if (!streams || !dsts || n < 0) return kInvalidParameter;
+    if (n == 0) return kSuccess;
+    DeviceGuard guard(device_id_);
+    prepared_ = false;
+    int st = BuildBatch(streams, n, params, dsts);
+    if (st != kSuccess) return st;
+    st = LaunchAll(true);
+    if (st != kSuccess) return st;
+    st = Finish();
+    prepared_ = (st == kSuccess);
+    return st;
+}
+
+int Decoder::Prepare(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!initialized_) return Fail(kNotInitialized, "decoder not initialised");
+    if (!streams || !dsts || n <= 0) return kInvalidParameter;
+    DeviceGuard guard(device_id_);
+    prepared_ = false;
+    int st = BuildBatch(streams, n, params, dsts);
+    if (st != kSuccess) return st;
+    st = Upload();
+    if (st != kSuccess) return st;
+    RJB_CUDA(cudaStreamSynchronize(stream_));
+    prepared_ = true;
+    return kSuccess;
+}
+
+int Decoder::Run() {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!initialized_ || !prepared_) return Fail(kNotInitialized, "no prepared batch");
+    DeviceGuard guard(device_id_);
+    stats_.kernel_launches = 0;
+    int st = LaunchAll(false);
+    if (st != kSuccess) return st;
+    return Finish();
+}
+
+int Decoder::CopyCoefficients(int image, int16_t* host_out, size_t count) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!prepared_ || image < 0 || size_t(image) >= h_images_.size() || !host_out) return kInvalidParameter;
+    DeviceGuard guard(device_id_);
+    const ImageDesc& im = h_images_[size_t(image)];
+    size_t need = 0;
+    for (int c = 0; c < im.ncomp; c++) need += size_t(im.blocks_w[c]) * im.blocks_h[c] * 64;
+    if (count < need) return kInvalidParameter;
+    std::vector<int16_t> tmp(size_t(im.nblocks) * 64);
+    RJB_CUDA(cudaMemcpy(tmp.data(), d_coef_.as<int16_t>() + size_t(im.blk0) * 64, tmp.size() * 2, cudaMemcpyDeviceToHost));
+    size_t base = 0;
+    for (int c = 0; c < im.ncomp; c++) {
+        const int H = im.hs[c], V = im.vs[c];
+        for (int by = 0; by < im.blocks_h[c]; by++)
+            for (int bx = 0; bx < im.blocks_w[c]; bx++) {
+                const size_t mcu = size_t(by / V) * size_t(im.mcus_x) + size_t(bx / H);
+                const size_t k = size_t(im.comp_first_blk[c] + (by % V) * H + (bx % H));
+                std::memcpy(host_out + base + (size_t(by) * im.blocks_w[c] + bx) * 64, &tmp[(mcu * im.bpm + k) * 64], 128);
+            }
+        base += size_t(im.blocks_w[c]) * im.blocks_h[c] * 64;
+    }
+    return kSuccess;
+}
+
+int Decoder::CopyPlanes(int image, uint8_t* host_out, size_t count) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!prepared_ || image < 0 || size_t(image) >= h_images_.size() || !host_out) return kInvalidParameter;
+    DeviceGuard guard(device_id_);
+    const ImageDesc& im = h_images_[size_t(image)];
+    size_t need = 0;
+    for (int c = 0; c < im.ncomp; c++) need += size_t(im.blocks_w[c]) * im.blocks_h[c] * 64;
+    if (count < need) return kInvalidParameter;
+    size_t base = 0;
+    for (int c = 0; c < im.ncomp; c++) {
+        const size_t w = size_t(im.blocks_w[c]) * 8, h = size_t(im.blocks_h[c]) * 8;
+        RJB_CUDA(cudaMemcpy2D(host_out + base, w, d_planes_.as<uint8_t>() + im.plane_off[c], im.plane_pitch[c], w, h,
+                              cudaMemcpyDeviceToHost));
+        base += w * h;
+    }
+    return kSuccess;
+}
+
+}  // namespace rjb

@@ -1,0 +1,139 @@
+// decoder.h — host orchestrator of the CUDA decode pipeline.
+//
+// Counterpart of the reference's RocJpegDecoder (src/rocjpeg_decoder.h:45-176,
+// src/rocjpeg_decoder.cpp) with its VA-API back end (RocJpegVappiDecoder,
+// src/rocjpeg_vaapi_decoder.h:274-413) folded in: where the reference submits
+// one picture at a time to a VCN core, waits on the surface, imports it into HIP
+// and launches a post-processing kernel per image, this class describes a whole
+// batch in one descriptor block, uploads it with the entropy-coded bytes, and
+// runs one launch per stage (K1 sync rounds, K1 write, DC scan, K2, K3) over all
+// images on the handle's CUDA stream. Device arenas are grow-only and reused
+// across calls (the reference's surface pool, vaapi_decoder.h:113-215).
+#pragma once
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "device_types.h"
+#include "jpeg_parser.h"
+#include "stages.h"
+
+namespace rjb {
+
+// Mirrors RocJpegDecodeParams / RocJpegImage (include/rocjpeg.h) without
+// depending on the public header.
+struct DecodeParams {
+    int32_t output_format;
+    int16_t crop_left, crop_top, crop_right, crop_bottom;
+};
+struct DestImage {
+    uint8_t* channel[4];
+    uint32_t pitch[4];
+};
+
+class DeviceBuffer {
+  public:
+    DeviceBuffer() = default;
+    ~DeviceBuffer();
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    cudaError_t Reserve(size_t bytes);   // grow-only; contents lost on growth
+    template <class U> U* as() const { return reinterpret_cast<U*>(ptr_); }
+    size_t capacity() const { return cap_; }
+
+  private:
+    void* ptr_ = nullptr;
+    size_t cap_ = 0;
+};
+
+enum StageId {
+    kStageUpload = 0,   // descriptor block + entropy-coded bytes, host -> device
+    kStageClear,        // coefficient arena memset
+    kStageSync,         // all k1_sync rounds
+    kStageWrite,        // k1_write
+    kStageDc,           // dc_sums + dc_apply
+    kStageIdct,         // k2_idct
+    kStageOutput,       // k3_output
+    kStageCount
+};
+
+struct BatchStats {
+    float stage_ms[kStageCount] = {};
+    float total_ms = 0;                 // first event to last event
+    uint32_t sync_rounds = 0;           // k1_sync launches that were needed
+    uint32_t decodes_per_round[kMaxSyncRounds] = {};
+    uint64_t scan_bytes = 0;            // clean entropy-coded bytes
+    uint64_t blocks = 0;                // 8x8 blocks decoded
+    uint64_t subsequences = 0;
+    uint64_t plane_bytes = 0;           // bytes of decoded component planes (K2 output)
+    uint64_t output_bytes = 0;          // bytes K3 writes
+    uint64_t k3_read_bytes = 0;         // plane bytes K3 reads
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    uint32_t kernel_launches = 0;
+    int sub_bytes = 0;
+};
+
+class Decoder {
+  public:
+    Decoder(int backend, int device_id);
+    ~Decoder();
+    int Initialize();   // RocJpegStatus
+    int GetImageInfo(const StreamParser* s, uint8_t* ncomp, int32_t* css, uint32_t* widths, uint32_t* heights);
+    int Decode(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
+
+    // Extension entry points (include/rocjpeg_b200_ext.h)
+    int Prepare(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
+    int Run();          // launch all stages for the prepared batch and synchronise
+    int CopyCoefficients(int image, int16_t* host_out, size_t count);   // component-major raster layout
+    int CopyPlanes(int image, uint8_t* host_out, size_t count);
+    void SetProfiling(bool on) { profiling_ = on; }
+    const BatchStats& stats() const { return stats_; }
+    const std::string& last_error() const { return err_; }
+    int device_id() const { return device_id_; }
+
+  private:
+    struct Layout;   // byte layout of the descriptor block
+    int Fail(int status, const std::string& why);
+    int BuildBatch(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
+    int Upload();
+    int LaunchAll(bool include_upload);
+    int Finish();
+
+    int backend_, device_id_;
+    bool initialized_ = false, profiling_ = false, prepared_ = false;
+    std::mutex mutex_;
+    std::string err_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[kStageCount + 1] = {};
+    int sm_count_ = 0;
+
+    // host-side batch description
+    std::vector<const StreamParser*> batch_;
+    std::vector<ImageDesc> h_images_;
+    std::vector<OutputDesc> h_outputs_;
+    std::vector<SegmentDesc> h_segments_;
+    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_;
+    std::vector<GatherItem> h_gather_;
+    std::vector<const HuffLutSet*> h_lut_ptrs_;
+    std::vector<uint64_t> h_lut_hashes_;
+    std::vector<uint16_t> h_qtables_;
+    K1Args k1_ = {};
+    K2Args k2_ = {};
+    K3Args k3_ = {};
+    uint32_t gather_chunks_ = 0;
+    bool all_pinned_ = false;
+    size_t scan_bytes_ = 0, coef_blocks_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
+
+    StagingBuffer h_desc_;        // pinned descriptor block
+    size_t desc_bytes_ = 0;
+    StagingBuffer h_counters_;    // pinned read-back
+    DeviceBuffer d_desc_, d_scan_, d_coef_, d_dcdiff_, d_planes_, d_state_, d_used_, d_subseg_, d_cta_partial_,
+        d_dc_partial_, d_counters_;
+    BatchStats stats_;
+};
+
+}  // namespace rjb

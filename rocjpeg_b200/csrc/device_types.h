@@ -1,0 +1,78 @@
+// device_types.h — plain structs shared by the host orchestrator and the CUDA stages.
+//
+// Nothing here exists in the reference: its Huffman/IDCT stage is the VCN
+// fixed-function block behind libva (src/rocjpeg_vaapi_decoder.cpp:677-689).
+// These descriptors are what replaces the five VA buffers of one picture
+// (picture / IQ matrix / Huffman / slice parameter / slice data) when the same
+// work is done by sm_100a kernels over a whole batch in one launch per stage.
+#pragma once
+#include <stdint.h>
+
+namespace rjb {
+
+constexpr int kMaxBlocksPerMcu = 10;   // T.81 B.2.3
+constexpr int kFastBits = 10;          // first-level Huffman LUT width
+constexpr int kFastSize = 1 << kFastBits;
+
+enum Css : int32_t { CSS_444 = 0, CSS_440 = 1, CSS_422 = 2, CSS_420 = 3, CSS_411 = 4, CSS_400 = 5, CSS_UNKNOWN = -1 };
+enum Fmt : int32_t { FMT_NATIVE = 0, FMT_YUV_PLANAR = 1, FMT_Y = 2, FMT_RGB = 3, FMT_RGB_PLANAR = 4 };
+
+// One set of four Huffman tables (DC0, DC1, AC0, AC1), decoder form.
+//   fast[t][peek10] = (code_length << 8) | symbol, 0 when the code is longer than kFastBits
+//   slow path (T.81 F.2.2.3 restated left-aligned): first l in (kFastBits,16] with
+//   peek16 < upper[t][l] has length l and symbol vals[t][(peek16 >> (16-l)) + valoff[t][l]]
+struct HuffLutSet {
+    uint16_t fast[4][kFastSize];
+    uint32_t upper[4][17];   // exclusive upper bound of codes of length l, left-aligned to 16 bits
+    int32_t valoff[4][17];   // valptr[l] - mincode[l]
+    uint8_t vals[4][256];
+};
+
+// Geometry + bookkeeping of one image inside a batch (device-resident array).
+struct ImageDesc {
+    int32_t width, height, ncomp, css;
+    int32_t mcus_x, mcus_y, bpm, restart_interval;   // bpm = blocks per MCU
+    int32_t total_mcus;
+    int32_t hs[3], vs[3];
+    int32_t blocks_w[3], blocks_h[3];                 // MCU-padded block grid per component
+    int32_t comp_first_blk[3];                        // index of a component's first block inside the MCU
+    uint8_t mcu_comp[kMaxBlocksPerMcu];               // block-in-MCU -> component
+    uint8_t mcu_dc[kMaxBlocksPerMcu];                 // block-in-MCU -> DC table (0/1)
+    uint8_t mcu_ac[kMaxBlocksPerMcu];                 // block-in-MCU -> AC table (2/3 = AC0/AC1 slot in HuffLutSet)
+    uint8_t pad_[2];
+    int32_t lut_set;                                  // index into the batch's HuffLutSet array
+    int32_t qt_index[3];                              // index into the batch's quant-table array (natural order u16[64])
+    // entropy-coded data (destuffed, restart markers removed; see jpeg_parser.h)
+    uint64_t data_off;                                // byte offset of the image's clean stream in the scan arena
+    uint32_t seg0, nseg;                              // this image's slice of the batch segment table
+    uint32_t sub0, nsub;                              // first subsequence (multiple of the CTA size) and count
+    // coefficient store: blocks in decode (MCU) order, 64 int16 each, natural order
+    uint64_t blk0;                                    // first block of this image in the batch coefficient arena
+    uint32_t nblocks;
+    uint32_t dc_tile0;                                // first DC-scan tile of this image
+    // decoded component planes (MCU-padded), u8
+    uint64_t plane_off[3];
+    uint32_t plane_pitch[3];
+};
+
+// One restart interval ("segment") of one image: an independently decodable,
+// byte-aligned run of entropy-coded data with predictors reset (T.81 E.1.4).
+struct SegmentDesc {
+    uint64_t data_off;     // byte offset in the scan arena (16-byte aligned)
+    uint32_t nbytes;       // entropy-coded bytes in the segment (excludes padding)
+    uint32_t sub0;         // first subsequence of the segment (global index)
+    uint32_t blk_first;    // first block of the segment, relative to the image's blk0
+    uint32_t blk_count;    // blocks the segment must produce (MCUs in interval * bpm)
+};
+
+// Output job for the colour/layout stage: one destination image.
+struct OutputDesc {
+    uint8_t* dst[4];
+    uint32_t dst_pitch[4];
+    int32_t x0, y0, w, h;    // region of interest in luma samples (whole picture when no crop)
+    int32_t fmt;
+    uint32_t tile0;          // first output tile of this image
+    uint32_t tiles_x, tiles_y;
+};
+
+}  // namespace rjb

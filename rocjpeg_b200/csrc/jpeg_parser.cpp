@@ -1,0 +1,372 @@
+// jpeg_parser.cpp — see jpeg_parser.h. Accept/reject rules follow
+// src/rocjpeg_parser.cpp of the reference (line numbers cited inline).
+#include "jpeg_parser.h"
+
+#include <cuda_runtime_api.h>
+
+#include <cstdlib>
+#include <cstring>
+
+namespace rjb {
+
+namespace {
+constexpr int kStatusSuccess = 0;
+constexpr int kStatusBadJpeg = -3;
+constexpr int kStatusNotSupported = -4;
+
+const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                             41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                             30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+inline uint32_t Rd16(const uint8_t* p) { return (uint32_t(p[0]) << 8) | p[1]; }
+inline size_t Align16(size_t v) { return (v + 15) & ~size_t(15); }
+}  // namespace
+
+// ------------------------------------------------------------ StagingBuffer
+
+StagingBuffer::~StagingBuffer() { Release(); }
+
+void StagingBuffer::Release() {
+    if (!ptr_) return;
+    if (pinned_) {
+        cudaFreeHost(ptr_);
+    } else {
+        std::free(ptr_);
+    }
+    ptr_ = nullptr;
+    cap_ = 0;
+    pinned_ = false;
+}
+
+uint8_t* StagingBuffer::Reserve(size_t bytes) {
+    if (bytes <= cap_) return ptr_;
+    Release();
+    size_t want = (bytes + bytes / 4 + 4095) & ~size_t(4095);
+    void* p = nullptr;
+    // Page-locked + portable so any device's stream can DMA from it, mapped so a
+    // gather kernel can read it in place. Falls back to pageable memory when no
+    // CUDA driver is present (host-only unit tests); decode still works from it.
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e == cudaSuccess && p) {
+        pinned_ = true;
+    } else {
+        (void)cudaGetLastError();
+        p = nullptr;
+        if (posix_memalign(&p, 4096, want) != 0) p = nullptr;
+        pinned_ = false;
+    }
+    if (!p) {
+        cap_ = 0;
+        return nullptr;
+    }
+    ptr_ = static_cast<uint8_t*>(p);
+    cap_ = want;
+    return ptr_;
+}
+
+// ------------------------------------------------------------ classification
+
+// src/rocjpeg_parser.cpp:432-470
+int ClassifyChromaSubsampling(const int32_t h[3], const int32_t v[3]) {
+    auto is = [&](int h0, int h1, int h2, int v0, int v1, int v2) {
+        return h[0] == h0 && h[1] == h1 && h[2] == h2 && v[0] == v0 && v[1] == v1 && v[2] == v2;
+    };
+    if (is(1, 1, 1, 1, 1, 1) || is(2, 2, 2, 2, 2, 2) || is(4, 4, 4, 4, 4, 4)) return CSS_444;
+    if (is(1, 1, 1, 2, 1, 1)) return CSS_440;
+    if (is(2, 1, 1, 1, 1, 1) || is(2, 1, 1, 2, 2, 2) || is(2, 2, 2, 2, 1, 1)) return CSS_422;
+    if (is(2, 1, 1, 2, 1, 1)) return CSS_420;
+    if (is(4, 1, 1, 1, 1, 1)) return CSS_411;
+    if (is(1, 0, 0, 1, 0, 0) || is(4, 0, 0, 4, 0, 0)) return CSS_400;
+    return CSS_UNKNOWN;
+}
+
+// ------------------------------------------------------------ Huffman tables
+
+// T.81 Annex C (code assignment) + F.2.2.3 (decoder tables), restated for a
+// left-aligned 16-bit peek. slot: 0 = DC0, 1 = DC1, 2 = AC0, 3 = AC1.
+void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out) {
+    uint16_t* fast = out->fast[slot];
+    std::memset(fast, 0, sizeof(uint16_t) * kFastSize);
+    std::memcpy(out->vals[slot], spec.vals, 256);
+    uint32_t code = 0, k = 0;
+    for (int l = 1; l <= 16; l++) {
+        out->valoff[slot][l] = int32_t(k) - int32_t(code);
+        for (uint32_t i = 0; i < spec.bits[l - 1]; i++, code++, k++) {
+            if (l <= kFastBits && code < (1u << l) && k < 256) {
+                uint32_t first = code << (kFastBits - l);
+                uint16_t entry = uint16_t((l << 8) | spec.vals[k]);
+                for (uint32_t j = 0; j < (1u << (kFastBits - l)); j++) fast[first + j] = entry;
+            }
+        }
+        uint32_t up = code << (16 - l);
+        out->upper[slot][l] = up > 0x10000u ? 0x10000u : up;
+        code <<= 1;
+    }
+    out->upper[slot][0] = 0;
+    out->valoff[slot][0] = 0;
+}
+
+// ------------------------------------------------------------ StreamParser
+
+bool StreamParser::Fail(const char* why) {
+    err_ = why;
+    p_.valid = false;
+    return false;
+}
+
+// src/rocjpeg_parser.cpp:160-207
+bool StreamParser::ParseSof(const uint8_t* s, uint32_t seglen) {
+    if (seglen < 8) return Fail("truncated SOF");
+    p_.height = int32_t(Rd16(s + 3));
+    p_.width = int32_t(Rd16(s + 5));
+    p_.ncomp = s[7];
+    if (p_.ncomp > 3) return Fail("more than three components");                // :172
+    if (seglen < 8u + 3u * uint32_t(p_.ncomp)) return Fail("truncated SOF");
+    for (int i = 0; i < p_.ncomp; i++) {
+        p_.comp_id[i] = s[8 + 3 * i];
+        uint8_t sf = s[9 + 3 * i], tq = s[10 + 3 * i];
+        if (tq >= 4) return Fail("quantiser table selector out of range");     // :185
+        p_.hs[i] = sf >> 4;
+        p_.vs[i] = sf & 15;
+        p_.tq[i] = tq;
+    }
+    int h0 = p_.hs[0] ? p_.hs[0] : 1, v0 = p_.vs[0] ? p_.vs[0] : 1;
+    p_.num_mcus_ref = uint32_t((p_.width + h0 * 8 - 1) / (h0 * 8)) * uint32_t((p_.height + v0 * 8 - 1) / (v0 * 8));  // :197
+    p_.css = ClassifyChromaSubsampling(p_.hs, p_.vs);
+    return true;
+}
+
+// src/rocjpeg_parser.cpp:256-313
+bool StreamParser::ParseDht(const uint8_t* s, uint32_t seglen) {
+    int32_t rem = int32_t(seglen) - 2;
+    const uint8_t* q = s + 2;
+    while (rem > 0) {
+        if (rem < 17) return Fail("truncated DHT");
+        uint8_t idx = *q++;
+        bool is_ac = (idx & 0xF0) != 0;
+        int id = idx & 0x0F;
+        if (id >= 2) return Fail("Huffman table id out of range");            // :274
+        uint32_t count = 0;
+        for (int i = 0; i < 16; i++) count += q[i];
+        if (is_ac ? count > 162 : count > 12) return Fail("too many Huffman values");   // :291, :298
+        if (int32_t(17 + count) > rem) return Fail("truncated DHT");
+        HuffSpec& t = is_ac ? p_.ac[id] : p_.dc[id];
+        std::memset(&t, 0, sizeof(t));
+        std::memcpy(t.bits, q, 16);
+        std::memcpy(t.vals, q + 16, count);
+        t.count = count;
+        t.present = true;
+        q += 16 + count;
+        rem -= 17 + int32_t(count);
+    }
+    return true;
+}
+
+// src/rocjpeg_parser.cpp:217-246
+bool StreamParser::ParseDqt(const uint8_t* s, uint32_t seglen) {
+    const uint8_t *q = s + 2, *end = s + seglen;
+    while (q < end) {
+        uint8_t idx = *q++;
+        if (idx >> 4) return Fail("16-bit quantisation tables are not supported");   // :230
+        if (idx >= 4) return Fail("quantisation table id out of range");             // :234
+        if (q + 64 > end) return Fail("truncated DQT");
+        std::memcpy(p_.qt[idx], q, 64);
+        p_.qt_present[idx] = true;
+        q += 64;
+    }
+    return true;
+}
+
+// src/rocjpeg_parser.cpp:324-363
+bool StreamParser::ParseSos(const uint8_t* s, uint32_t seglen) {
+    if (seglen < 3) return Fail("truncated SOS");
+    int n = s[2];
+    if (n > 3) return Fail("more than three scan components");                     // :333
+    if (seglen < 6u + 2u * uint32_t(n)) return Fail("truncated SOS");
+    p_.scan_ncomp = n;
+    for (int i = 0; i < n; i++) {
+        uint8_t cid = s[3 + 2 * i], t = s[4 + 2 * i];
+        if ((t & 15) >= 4 || (t >> 4) >= 4) return Fail("Huffman selector out of range");   // :347-354
+        if (cid != p_.comp_id[i]) return Fail("scan components do not follow the frame order");  // :355
+        p_.td[i] = t >> 4;
+        p_.ta[i] = t & 15;
+    }
+    return true;
+}
+
+void StreamParser::DeriveGeometry() {
+    p_.hmax = p_.vmax = 1;
+    p_.mcus_x = p_.mcus_y = p_.bpm = 0;
+    for (int i = 0; i < 3; i++) p_.blocks_w[i] = p_.blocks_h[i] = 0;
+    if (p_.ncomp < 1 || p_.width <= 0 || p_.height <= 0) return;
+    for (int i = 0; i < p_.ncomp; i++) {
+        if (p_.hs[i] > p_.hmax) p_.hmax = p_.hs[i];
+        if (p_.vs[i] > p_.vmax) p_.vmax = p_.vs[i];
+    }
+    if (p_.ncomp == 1) {
+        // single-component scan: MCU = one 8x8 block, sampling factors ignored (T.81 A.2.2)
+        p_.mcus_x = (p_.width + 7) / 8;
+        p_.mcus_y = (p_.height + 7) / 8;
+        p_.bpm = 1;
+        p_.blocks_w[0] = p_.mcus_x;
+        p_.blocks_h[0] = p_.mcus_y;
+    } else {
+        p_.mcus_x = (p_.width + 8 * p_.hmax - 1) / (8 * p_.hmax);
+        p_.mcus_y = (p_.height + 8 * p_.vmax - 1) / (8 * p_.vmax);
+        for (int i = 0; i < p_.ncomp; i++) {
+            p_.blocks_w[i] = p_.mcus_x * p_.hs[i];
+            p_.blocks_h[i] = p_.mcus_y * p_.vs[i];
+            p_.bpm += p_.hs[i] * p_.vs[i];
+        }
+    }
+}
+
+// One pass over the entropy-coded bytes: finds the first FF D9 (the reference's
+// ParseEOI, parser.cpp:400-416), and on the way writes the destuffed,
+// marker-free bitstream, one 16-byte-aligned segment per restart interval.
+void StreamParser::ExtractEntropyData(const uint8_t* d, size_t begin, size_t length) {
+    p_.segments.clear();
+    p_.restart_markers_seen = 0;
+    const int64_t total_mcus = int64_t(p_.mcus_x) * p_.mcus_y;
+    const size_t expected =
+        (p_.restart_interval > 0 && total_mcus > 0) ? size_t((total_mcus + p_.restart_interval - 1) / p_.restart_interval) : 1;
+    const size_t cap = (length - begin) + (expected + 2) * 48 + 64;
+    uint8_t* out = clean_.Reserve(cap);
+    if (!out) {
+        p_.clean_bytes = 0;
+        p_.scan_size = 0;
+        return;
+    }
+    size_t o = 0, seg_start = 0, pos = begin;
+    bool dead = false;   // a non-restart marker was met: no more data until the next RSTn
+    auto close_segment = [&]() {
+        if (p_.segments.size() < expected) p_.segments.push_back(Segment{uint32_t(seg_start), uint32_t(o - seg_start)});
+        size_t padded = Align16(o) + 16;   // zero tail: the bit reader may look 16 bytes ahead
+        std::memset(out + o, 0, padded - o);
+        o = padded;
+        seg_start = o;
+    };
+    size_t eoi = length;
+    while (pos < length) {
+        const uint8_t* q = static_cast<const uint8_t*>(std::memchr(d + pos, 0xFF, length - pos));
+        size_t stop = q ? size_t(q - d) : length;
+        if (!dead && stop > pos && o + (stop - pos) + 64 <= cap) {
+            std::memcpy(out + o, d + pos, stop - pos);
+            o += stop - pos;
+        }
+        pos = stop;
+        if (!q) break;
+        if (pos + 1 >= length) {   // lone FF at the very end: belongs to the slice, carries no data
+            pos = length;
+            break;
+        }
+        uint8_t nx = d[pos + 1];
+        if (nx == 0x00) {
+            if (!dead && o + 65 <= cap) out[o++] = 0xFF;
+            pos += 2;
+        } else if (nx == 0xD9) {
+            eoi = pos;
+            break;
+        } else if ((nx & 0xF8) == 0xD0) {
+            p_.restart_markers_seen++;
+            if (o + 48 + 64 <= cap) close_segment();
+            dead = false;
+            pos += 2;
+        } else if (nx == 0xFF) {
+            pos += 1;   // fill byte
+        } else {
+            dead = true;   // any other marker ends the entropy-coded data of this interval
+            pos += 2;
+        }
+    }
+    if (eoi == length) eoi = length;   // no EOI: the slice runs to the end of the buffer
+    p_.scan_offset = uint32_t(begin);
+    p_.scan_size = uint32_t(eoi - begin);
+    close_segment();
+    while (p_.segments.size() < expected && o + 48 + 64 <= cap) close_segment();   // missing intervals: empty
+    p_.clean_bytes = o;
+}
+
+void StreamParser::BuildDecodeTables() {
+    // support check: what the CUDA path decodes (baseline, one interleaved scan
+    // over all components, css in {444, 440, 422, 420, 400})
+    p_.support_status = kStatusSuccess;
+    if (p_.width <= 0 || p_.height <= 0) p_.support_status = kStatusNotSupported;
+    else if (p_.ncomp != 1 && p_.ncomp != 3) p_.support_status = kStatusNotSupported;
+    else if (p_.scan_ncomp != p_.ncomp) p_.support_status = kStatusNotSupported;
+    else if (p_.css == CSS_UNKNOWN || p_.css == CSS_411) p_.support_status = kStatusNotSupported;
+    else if (p_.bpm > kMaxBlocksPerMcu || p_.bpm < 1) p_.support_status = kStatusNotSupported;
+    else if (p_.css == CSS_422 && p_.ncomp == 3 && p_.hs[1] == p_.hs[0]) p_.support_status = kStatusNotSupported;
+    if (p_.support_status == kStatusSuccess) {
+        for (int i = 0; i < p_.ncomp; i++) {
+            if (!p_.qt_present[p_.tq[i]]) p_.support_status = kStatusBadJpeg;
+            if (p_.td[i] >= 2 || p_.ta[i] >= 2) p_.support_status = kStatusBadJpeg;
+            else if (!p_.dc[p_.td[i]].present || !p_.ac[p_.ta[i]].present) p_.support_status = kStatusBadJpeg;
+        }
+    }
+    for (int t = 0; t < 4; t++)
+        for (int k = 0; k < 64; k++) p_.qt_natural[t][kZigzag[k]] = p_.qt[t][k];
+    std::memset(&p_.lut, 0, sizeof(p_.lut));
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* ptr, size_t n) {
+        const uint8_t* b = static_cast<const uint8_t*>(ptr);
+        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    for (int t = 0; t < 2; t++) {
+        if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &p_.lut);
+        if (p_.ac[t].present) BuildHuffLut(p_.ac[t], 2 + t, &p_.lut);
+        uint8_t present[2] = {uint8_t(p_.dc[t].present), uint8_t(p_.ac[t].present)};
+        mix(present, 2);
+        mix(p_.dc[t].bits, 16);
+        mix(p_.dc[t].vals, p_.dc[t].count);
+        mix(p_.ac[t].bits, 16);
+        mix(p_.ac[t].vals, p_.ac[t].count);
+    }
+    p_.lut_hash = h;
+}
+
+bool StreamParser::Parse(const uint8_t* d, size_t len) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    // the reference zeroes its parameters on every parse (parser.cpp:54)
+    std::vector<Segment> keep;
+    keep.swap(p_.segments);
+    p_ = ParsedJpeg();
+    p_.segments.swap(keep);
+    p_.segments.clear();
+    err_.clear();
+    if (!d || len < 4) return Fail("stream too short");
+    if (d[0] != 0xFF || d[1] != 0xD8) return Fail("missing SOI");                   // parser.cpp:64
+    size_t p = 2;
+    bool seen_dht = false, seen_dqt = false, seen_sos = false;
+    while (!seen_sos) {
+        if (p + 4 > len) return Fail("truncated before SOS");
+        while (p < len && d[p] == 0xFF) p++;                                        // parser.cpp:75
+        if (p + 3 > len) return Fail("truncated before SOS");
+        uint8_t m = d[p++];
+        uint32_t seglen = Rd16(d + p);
+        size_t next = p + seglen;
+        if (seglen < 2 || next > len) return Fail("bad segment length");
+        const uint8_t* s = d + p;
+        switch (m) {
+            case 0xC0: if (!ParseSof(s, seglen)) return false; break;
+            case 0xC4: if (!ParseDht(s, seglen)) return false; seen_dht = true; break;
+            case 0xDB: if (!ParseDqt(s, seglen)) return false; seen_dqt = true; break;
+            case 0xDD:                                                              // parser.cpp:374-390
+                if (seglen != 4) return Fail("bad DRI length");
+                p_.restart_interval = int32_t(Rd16(s + 2));
+                break;
+            case 0xDA: if (!ParseSos(s, seglen)) return false; seen_sos = true; break;
+            default: break;   // APPn, COM, SOF2 ... skipped by length (parser.cpp:105-108)
+        }
+        p = next;
+    }
+    if (!seen_dht) return Fail("no Huffman table before SOS");                     // parser.cpp:111-118
+    if (!seen_dqt) return Fail("no quantisation table before SOS");
+    DeriveGeometry();
+    ExtractEntropyData(d, p, len);
+    BuildDecodeTables();
+    p_.valid = true;
+    return true;
+}
+
+}  // namespace rjb

@@ -1,0 +1,116 @@
+// jpeg_parser.h — host-side baseline JPEG stream parser.
+//
+// Behaviour-compatible replacement for the reference's RocJpegStreamParser
+// (src/rocjpeg_parser.h:180-269, src/rocjpeg_parser.cpp): same marker walk and
+// the same accept/reject decisions (SOF0 only, <=3 components, 8-bit DQT with
+// id<4, DHT id<2, SOS ids must follow SOF order, DRI length 4, at least one DHT
+// and one DQT before SOS, entropy-coded slice = bytes up to the first FF D9),
+// plus bounds checks (the reference reads past the end of truncated input).
+//
+// Extended for the CUDA back end (BASELINE north star, item 2): while it makes
+// the one pass over the entropy-coded bytes that the reference already makes to
+// find FF D9 (src/rocjpeg_parser.cpp:400-416), it also
+//   * removes byte stuffing (FF 00 -> FF) and restart markers, writing a clean
+//     bitstream into page-locked memory owned by the stream handle;
+//   * records every restart interval as a 16-byte-aligned segment (offset,
+//     length) of that clean stream;
+//   * builds the decoder-form Huffman tables (first-level LUT + canonical slow
+//     path) and natural-order quantisation tables.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "device_types.h"
+
+namespace rjb {
+
+// Grow-only host buffer; page-locked (cudaHostAlloc, portable + mapped) when a
+// CUDA driver is present, plain aligned memory otherwise (CPU-only unit tests).
+class StagingBuffer {
+  public:
+    StagingBuffer() = default;
+    ~StagingBuffer();
+    StagingBuffer(const StagingBuffer&) = delete;
+    StagingBuffer& operator=(const StagingBuffer&) = delete;
+    uint8_t* Reserve(size_t bytes);   // contents are NOT preserved across growth
+    uint8_t* data() const { return ptr_; }
+    size_t capacity() const { return cap_; }
+    bool pinned() const { return pinned_; }
+
+  private:
+    void Release();
+    uint8_t* ptr_ = nullptr;
+    size_t cap_ = 0;
+    bool pinned_ = false;
+};
+
+struct HuffSpec {
+    uint8_t bits[16];
+    uint8_t vals[256];
+    uint32_t count;
+    bool present;
+};
+
+struct Segment {
+    uint32_t offset;   // byte offset inside the clean stream (16-byte aligned)
+    uint32_t nbytes;   // entropy-coded bytes
+};
+
+// Everything one parsed picture contributes to a decode call.
+struct ParsedJpeg {
+    bool valid = false;
+    // frame / scan header (field-for-field what the reference keeps in
+    // JpegStreamParameters, src/rocjpeg_parser.h:150-172)
+    int32_t width = 0, height = 0, ncomp = 0, css = CSS_UNKNOWN;
+    int32_t comp_id[3] = {0, 0, 0}, hs[3] = {0, 0, 0}, vs[3] = {0, 0, 0}, tq[3] = {0, 0, 0};
+    int32_t scan_ncomp = 0, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+    int32_t restart_interval = 0;
+    uint32_t num_mcus_ref = 0;                    // the reference's num_mcus (parser.cpp:197)
+    uint32_t scan_offset = 0, scan_size = 0;      // slice inside the caller's buffer (parser.cpp:400-416)
+    uint8_t qt[4][64] = {};                       // zig-zag order, as in the stream
+    bool qt_present[4] = {false, false, false, false};
+    HuffSpec dc[2] = {}, ac[2] = {};
+    // derived geometry (T.81 A.1.1, A.2)
+    int32_t hmax = 1, vmax = 1, mcus_x = 0, mcus_y = 0, bpm = 0;
+    int32_t blocks_w[3] = {0, 0, 0}, blocks_h[3] = {0, 0, 0};
+    // decode-side products
+    int32_t support_status = 0;                   // RocJpegStatus value: 0 when the CUDA path can decode it
+    uint16_t qt_natural[4][64] = {};              // de-zig-zagged quantiser steps
+    HuffLutSet lut;                               // valid when support_status == 0
+    uint64_t lut_hash = 0;                        // identity of the four tables (batch de-duplication)
+    std::vector<Segment> segments;                // one per restart interval (exactly ceil(mcus / Ri))
+    size_t clean_bytes = 0;                       // bytes used in `clean`
+    uint32_t restart_markers_seen = 0;
+};
+
+class StreamParser {
+  public:
+    // Returns false for streams the reference parser rejects (-> BAD_JPEG).
+    bool Parse(const uint8_t* data, size_t length);
+    const ParsedJpeg& parsed() const { return p_; }
+    const StagingBuffer& clean() const { return clean_; }
+    const std::string& last_error() const { return err_; }
+
+  private:
+    bool Fail(const char* why);
+    bool ParseSof(const uint8_t* s, uint32_t seglen);
+    bool ParseDht(const uint8_t* s, uint32_t seglen);
+    bool ParseDqt(const uint8_t* s, uint32_t seglen);
+    bool ParseSos(const uint8_t* s, uint32_t seglen);
+    void DeriveGeometry();
+    void ExtractEntropyData(const uint8_t* d, size_t begin, size_t length);
+    void BuildDecodeTables();
+
+    std::mutex mutex_;
+    ParsedJpeg p_;
+    StagingBuffer clean_;
+    std::string err_;
+};
+
+int ClassifyChromaSubsampling(const int32_t h[3], const int32_t v[3]);
+void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out);
+
+}  // namespace rjb

@@ -1,0 +1,79 @@
+// stages.h — host-callable launchers of the three CUDA stages.
+//
+// These replace, for a whole batch per launch:
+//   K1 (k1_huffman.cu)  the Huffman decode done by VCN fixed function in the
+//                       reference (src/rocjpeg_vaapi_decoder.cpp:677-689, 816-828)
+//   K2 (k2_idct.cu)     the dequantise + IDCT done by VCN fixed function (same call sites)
+//   K3 (k3_output.cu)   the post-processing kernels and copies of
+//                       src/rocjpeg_hip_kernels.cpp / src/rocjpeg_decoder.cpp:372-636
+#pragma once
+#include <cuda_runtime_api.h>
+#include <stdint.h>
+
+#include "device_types.h"
+
+namespace rjb {
+
+constexpr int kK1Threads = 128;      // subsequences per CTA in K1
+constexpr int kDcTileMcus = 256;     // MCUs per DC-scan tile
+constexpr int kMaxSyncRounds = 8;    // counters kept per batch
+
+struct K1Args {
+    const ImageDesc* images;      // device
+    const SegmentDesc* segments;  // device
+    const uint32_t* img_cta0;     // device, nimages + 1 entries: first K1 CTA of each image
+    const uint32_t* img_dctile0;  // device, nimages + 1 entries: first DC tile of each image
+    const uint8_t* scan;          // device scan arena
+    const HuffLutSet* luts;       // device
+    uint32_t* state;              // per subsequence: packed out-state | blocks << 16
+    uint32_t* used;               // per subsequence: key of the in-state its state was decoded from
+    uint32_t* sub_seg;            // per subsequence: segment index (cache)
+    uint2* cta_partial;           // per K1 CTA: (has segment start, blocks after the last start)
+    int3* dc_partial;             // per DC tile: per-component DC sum after the tile's last reset
+    uint32_t* counters;           // [kMaxSyncRounds] boundary changes per round, then [kMaxSyncRounds] decodes per round
+    int16_t* coef;                // coefficient arena, 64 int16 per block
+    int16_t* dcdiff;              // one DC difference per block
+    int nimages;
+    uint32_t total_ctas;          // K1 CTAs in the batch
+    uint32_t total_dc_tiles;
+    int sub_bytes;                // subsequence size S in bytes: 32, 64 or 128
+};
+
+// Speculative decode + CTA-local synchronisation (round 0) or cross-CTA fix-up (round >= 1).
+cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream);
+// Final pass: positions from the block counts, coefficients and DC differences written.
+cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream);
+// DC prediction: per-tile sums, then prefix + write of absolute DC into coef[blk*64].
+cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream);
+
+struct K2Args {
+    const ImageDesc* images;
+    const uint32_t* img_tile0;    // nimages + 1: first IDCT tile of each image
+    const uint16_t* qtables;      // natural-order u16[64] tables
+    const int16_t* coef;
+    uint8_t* planes;              // plane arena
+    int nimages;
+    uint32_t total_tiles;
+};
+cudaError_t LaunchK2Idct(const K2Args& a, cudaStream_t stream);
+
+struct K3Args {
+    const ImageDesc* images;
+    const OutputDesc* outputs;
+    const uint32_t* img_tile0;    // nimages + 1: first output tile of each image
+    const uint8_t* planes;
+    int nimages;
+    uint32_t total_tiles;
+};
+cudaError_t LaunchK3Output(const K3Args& a, cudaStream_t stream);
+
+// Gather per-image clean streams from mapped page-locked host memory into the scan arena.
+struct GatherItem {
+    const uint8_t* src;   // device-visible address of the image's clean stream
+    uint64_t dst_off;     // byte offset in the scan arena
+    uint32_t nbytes;      // multiple of 16
+    uint32_t chunk0;      // first 16 KiB gather chunk of this image
+};
+cudaError_t LaunchGather(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena, cudaStream_t stream);
+
+}  // namespace rjb

@@ -1,0 +1,212 @@
+// k1_model.cpp — CPU model of the K1 schedule (TEST TOOL, not product, not oracle).
+//
+// Runs the product's own parser (csrc/jpeg_parser.cpp) and the product's own
+// sequential decode core (csrc/huff_core.cuh, compiled for the host) through a
+// serial emulation of what k1_huffman.cu does in parallel: subsequences of S
+// bytes, CTAs of T subsequences, speculative round 0 with CTA-local Jacobi
+// fix-up, cross-CTA rounds, CTA partials + look-back, write pass, tiled DC scan.
+// It lets the no-GPU test suite check the *algorithm* (state packing,
+// convergence logic, block positions, DC integration) against the oracle; the
+// CUDA kernels themselves are checked by the -m gpu tests.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "huff_core.cuh"
+#include "jpeg_parser.h"
+
+using namespace rjb;
+
+namespace {
+const uint8_t kZig[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                          41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                          30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct HostLoader {
+    const uint8_t* base;
+    uint32_t operator()(uint32_t i) const {
+        uint32_t w;
+        std::memcpy(&w, base + size_t(i) * 4, 4);
+        return w;
+    }
+};
+struct HostSink {
+    int16_t* coef;
+    int16_t* dcdiff;
+    void Dc(uint32_t blk, int v) const { dcdiff[blk] = int16_t(v); }
+    void Ac(uint32_t blk, int z, int v) const { coef[size_t(blk) * 64 + kZig[z]] = int16_t(v); }
+};
+struct SubInfo {
+    uint32_t seg;
+    bool first, last;
+    uint32_t end_bit;
+    size_t start;
+};
+}  // namespace
+
+struct K1ModelStats {
+    uint32_t rounds;            // k1_sync launches needed (>= 2)
+    uint32_t decodes[8];        // decodes per round
+    uint32_t max_local_iters;   // deepest CTA-local fix-up loop
+    uint32_t nsub, nctas;
+};
+
+extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, int16_t* out, size_t count, K1ModelStats* stats) {
+    StreamParser parser;
+    if (!parser.Parse(data, len)) return -3;
+    const ParsedJpeg& p = parser.parsed();
+    if (p.support_status != 0) return p.support_status;
+    const uint8_t* clean = parser.clean().data();
+    const int bpm = p.bpm;
+    uint8_t mcu_comp[kMaxBlocksPerMcu], mcu_dc[kMaxBlocksPerMcu], mcu_ac[kMaxBlocksPerMcu];
+    int comp_first[3] = {0, 0, 0};
+    int k = 0;
+    for (int c = 0; c < p.ncomp; c++) {
+        int H = p.ncomp == 1 ? 1 : p.hs[c], V = p.ncomp == 1 ? 1 : p.vs[c];
+        comp_first[c] = k;
+        for (int b = 0; b < H * V; b++, k++) {
+            mcu_comp[k] = uint8_t(c);
+            mcu_dc[k] = uint8_t(p.td[c]);
+            mcu_ac[k] = uint8_t(2 + p.ta[c]);
+        }
+    }
+    const uint32_t total_mcus = uint32_t(p.mcus_x) * uint32_t(p.mcus_y);
+    const uint32_t ri = p.restart_interval > 0 ? uint32_t(p.restart_interval) : total_mcus;
+    // subsequences
+    std::vector<SubInfo> subs;
+    std::vector<uint32_t> seg_blk_first, seg_blk_count;
+    for (size_t s = 0; s < p.segments.size(); s++) {
+        const Segment& sg = p.segments[s];
+        uint32_t n = (sg.nbytes + S - 1) / S;
+        uint64_t mf = uint64_t(s) * ri;
+        uint64_t mc = mf >= total_mcus ? 0 : std::min<uint64_t>(ri, total_mcus - mf);
+        seg_blk_first.push_back(uint32_t(mf * bpm));
+        seg_blk_count.push_back(uint32_t(mc * bpm));
+        for (uint32_t j = 0; j < n; j++) {
+            uint32_t remain = sg.nbytes - j * S;
+            subs.push_back(SubInfo{uint32_t(s), j == 0, j + 1 == n, std::min<uint32_t>(remain, uint32_t(S)) * 8u, size_t(sg.offset) + size_t(j) * S});
+        }
+    }
+    const uint32_t nsub = uint32_t(subs.size());
+    const uint32_t nctas = (nsub + T - 1) / T;
+    std::vector<uint32_t> state(nsub, 0), used(nsub, 0);
+    NullSink nsink;
+    auto decode_from = [&](uint32_t g, uint32_t key) {
+        uint32_t pb = StateOverflow(key), nb = 0, blk = 0;
+        int c = StateC(key), z = StateZ(key);
+        HostLoader ld{clean + subs[g].start};
+        DecodeSpan<false>(ld, &p.lut, mcu_dc, mcu_ac, bpm, pb, subs[g].end_bit, c, z, nb, blk, 0xFFFFFFFFu, nsink);
+        uint32_t over = pb > subs[g].end_bit ? pb - subs[g].end_bit : 0;
+        return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
+    };
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    uint32_t round = 0;
+    for (;; round++) {
+        uint32_t boundary_changes = 0, ndec = 0;
+        std::vector<uint32_t> prev_state = state;   // what other CTAs see during this round (worst case: old values)
+        for (uint32_t cta = 0; cta < nctas; cta++) {
+            const uint32_t g0 = cta * T, g1 = std::min(nsub, g0 + T);
+            if (round > 0) {
+                bool need0 = !subs[g0].first && StateKey(prev_state[g0 - 1]) != used[g0];
+                if (!need0) continue;
+            }
+            std::vector<uint32_t> old(state.begin() + g0, state.begin() + g1);
+            if (round == 0)
+                for (uint32_t g = g0; g < g1; g++) {
+                    used[g] = 0;
+                    state[g] = decode_from(g, 0);
+                    ndec++;
+                }
+            for (uint32_t iter = 0;; iter++) {
+                std::vector<uint32_t> snap(state.begin() + g0, state.begin() + g1);
+                bool any = false;
+                for (uint32_t g = g0; g < g1; g++) {
+                    if (subs[g].first) continue;
+                    uint32_t in = used[g];
+                    if (g > g0) in = StateKey(snap[g - 1 - g0]);
+                    else if (round > 0) in = StateKey(prev_state[g - 1]);
+                    if (in != used[g]) {
+                        state[g] = decode_from(g, in);
+                        used[g] = in;
+                        ndec++;
+                        any = true;
+                    }
+                }
+                if (stats) stats->max_local_iters = std::max(stats->max_local_iters, iter);
+                if (!any) break;
+            }
+            const uint32_t gl = g0 + T - 1;
+            if (gl < nsub && !subs[gl].last && (round == 0 || StateKey(old[gl - g0]) != StateKey(state[gl]))) boundary_changes++;
+        }
+        if (stats && round < 8) stats->decodes[round] = ndec;
+        if (round > 0 && boundary_changes == 0) break;
+        if (round > nctas + 2) return -6;
+    }
+    if (stats) {
+        stats->rounds = round + 1;
+        stats->nsub = nsub;
+        stats->nctas = nctas;
+    }
+    // CTA partials + look-back carry (as k1_write does)
+    std::vector<uint32_t> cta_flag(nctas, 0), cta_tail(nctas, 0);
+    for (uint32_t cta = 0; cta < nctas; cta++) {
+        uint32_t tail = 0, flag = 0;
+        for (uint32_t g = cta * T; g < std::min(nsub, (cta + 1) * T); g++) {
+            if (subs[g].first) { flag = 1; tail = 0; }
+            tail += StateBlocks(state[g]);
+        }
+        cta_flag[cta] = flag;
+        cta_tail[cta] = tail;
+    }
+    const uint32_t nblocks = total_mcus * uint32_t(bpm);
+    std::vector<int16_t> coef(size_t(nblocks) * 64, 0), dcdiff(nblocks, 0);
+    HostSink sink{coef.data(), dcdiff.data()};
+    for (uint32_t cta = 0; cta < nctas; cta++) {
+        uint32_t carry = 0;
+        for (int64_t kk = int64_t(cta) - 1; kk >= 0; kk--) {
+            carry += cta_tail[kk];
+            if (cta_flag[kk]) break;
+        }
+        uint32_t run = carry;
+        for (uint32_t g = cta * T; g < std::min(nsub, (cta + 1) * T); g++) {
+            if (subs[g].first) run = 0;
+            const uint32_t excl = run;
+            run += StateBlocks(state[g]);
+            uint32_t key = subs[g].first ? 0 : StateKey(state[g - 1]);
+            uint32_t pb = StateOverflow(key), cnt = 0;
+            int c = StateC(key), z = StateZ(key);
+            uint32_t blk = seg_blk_first[subs[g].seg] + excl;
+            const uint32_t limit = seg_blk_first[subs[g].seg] + seg_blk_count[subs[g].seg];
+            HostLoader ld{clean + subs[g].start};
+            DecodeSpan<true>(ld, &p.lut, mcu_dc, mcu_ac, bpm, pb, subs[g].end_bit, c, z, cnt, blk, limit, sink);
+        }
+    }
+    // DC integration per component, reset at restart intervals
+    {
+        int pred[3] = {0, 0, 0};
+        for (uint32_t m = 0; m < total_mcus; m++) {
+            if (m % ri == 0) pred[0] = pred[1] = pred[2] = 0;
+            for (int b = 0; b < bpm; b++) {
+                pred[mcu_comp[b]] += dcdiff[size_t(m) * bpm + b];
+                coef[(size_t(m) * bpm + b) * 64] = int16_t(pred[mcu_comp[b]]);
+            }
+        }
+    }
+    // reorder: decode order -> component-major raster
+    size_t need = 0;
+    for (int c = 0; c < p.ncomp; c++) need += size_t(p.blocks_w[c]) * p.blocks_h[c] * 64;
+    if (count < need) return -2;
+    size_t base = 0;
+    for (int c = 0; c < p.ncomp; c++) {
+        int H = p.ncomp == 1 ? 1 : p.hs[c], V = p.ncomp == 1 ? 1 : p.vs[c];
+        for (int by = 0; by < p.blocks_h[c]; by++)
+            for (int bx = 0; bx < p.blocks_w[c]; bx++) {
+                size_t mcu = size_t(by / V) * p.mcus_x + size_t(bx / H);
+                size_t kb = size_t(comp_first[c] + (by % V) * H + (bx % H));
+                std::memcpy(out + base + (size_t(by) * p.blocks_w[c] + bx) * 64, &coef[(mcu * bpm + kb) * 64], 128);
+            }
+        base += size_t(p.blocks_w[c]) * p.blocks_h[c] * 64;
+    }
+    return 0;
+}

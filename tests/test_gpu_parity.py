@@ -1,0 +1,297 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Gates:
+  1. quantised coefficients bit-exact vs the oracle (== libjpeg-turbo jpeg_read_coefficients,
+     pinned in test_oracle_pinning.py) for every block, incl. MCU padding blocks;
+  2. decoded Y/U/V planes bit-exact vs the oracle (== libjpeg-turbo jpeg_read_raw_data, islow);
+  3. every output format bit-exact vs the oracle's restatement of the reference's assembly
+     and colour formulas (== the reference's own kernels run on the CPU), incl. bytes the
+     decoder must NOT touch (exact-bounds stores, arbitrary pitch and base alignment);
+  4. committed golden hashes.
+"""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from rocjpeg_b200 import api, datagen
+
+import gpu_util as gu
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+with open(os.path.join(GOLDEN, "golden.json")) as _f:
+    _G = json.load(_f)
+CASES = sorted(_G["cases"])
+FORMATS = ["native", "yuv_planar", "y", "rgb", "rgb_planar"]
+
+
+def load(name):
+    with open(os.path.join(GOLDEN, name + ".jpg"), "rb") as f:
+        return f.read()
+
+
+def sha(arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+@pytest.fixture(scope="module")
+def dec():
+    import torch
+
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    d = api.Decoder(api.BACKEND_HARDWARE, 0)
+    yield d
+    d.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_coefficients_and_planes(dec, orc, name):
+    data = load(name)
+    st, got, want = gu.decode_one(dec, orc, data, "y")
+    assert st == api.SUCCESS
+    rc, info = orc.parse(data)
+    n = sum(info.blocks_w[c] * info.blocks_h[c] * 64 for c in range(info.ncomp))
+    coefs = orc.coefficients(data, info)
+    got_c = dec.coefficients(0, n)
+    assert np.array_equal(got_c, np.concatenate([c.reshape(-1) for c in coefs])), "coefficients"
+    assert sha(oracle.Oracle.split(info, got_c, 64)) == _G["cases"][name]["coefficients"]
+    planes = orc.planes(data, info)
+    got_p = dec.planes(0, n)
+    assert np.array_equal(got_p, np.concatenate([p.reshape(-1) for p in planes])), "planes"
+    gu.assert_same(got, want, name)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_all_output_formats_and_crops(dec, orc, name):
+    data = load(name)
+    rc, info = orc.parse(data)
+    g = _G["cases"][name]
+    crops = [(0, 0, 0, 0)]
+    if info.width >= 96 and info.height >= 64:
+        crops += [tuple(_G["meta"]["crop"]), (17, 9, 82, 59), (0, 0, 8, 8)]
+    for fmt in FORMATS:
+        for crop in crops:
+            for pad, mis in ((0, 0), (13, 3)):
+                st, got, want = gu.decode_one(dec, orc, data, fmt, crop, pad, mis)
+                assert st == api.SUCCESS, (fmt, crop, st)
+                gu.assert_same(got, want, f"{name} {fmt} {crop} pad={pad} mis={mis}")
+            key = f"{fmt}|{','.join(map(str, crop))}"
+            if key in g["outputs"]:
+                shapes = oracle.output_shapes(info, fmt, crop, orc)
+                assert sha([a[:rows, :rb] for a, (rows, rb) in zip(got, shapes)]) == g["outputs"][key], key
+
+
+def test_batched_mixed_everything(dec, orc):
+    """One rocJpegDecodeBatched over every fixture: mixed subsampling, sizes, DRI, Huffman tables."""
+    datas = [load(n) for n in CASES]
+    for fmt in ("rgb_planar", "yuv_planar", "native"):
+        streams, dests, keep = [], [], []
+        for d in datas:
+            s = api.JpegStream()
+            assert s.parse(d) == api.SUCCESS
+            rc, info = orc.parse(d)
+            dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, fmt, (0, 0, 0, 0), pitch_pad=5, misalign=1)
+            streams.append(s)
+            dests.append(dest)
+            keep.append((bufs, pitches, shapes))
+        assert dec.decode_batched(streams, api.make_params(fmt), dests) == api.SUCCESS
+        for d, (bufs, pitches, shapes), name in zip(datas, keep, CASES):
+            got = gu.fetch(bufs, pitches, shapes, 1)
+            _, want = gu.oracle_outputs(orc, d, fmt, (0, 0, 0, 0), pitches)
+            gu.assert_same(got, want, f"batched {fmt} {name}")
+    st = dec.stats()
+    assert st.blocks > 0 and st.kernel_launches > 0
+
+
+@pytest.mark.parametrize("S", [32, 64, 128])
+def test_every_subsequence_size(dec, orc, S, monkeypatch):
+    monkeypatch.setenv("ROCJPEG_B200_SUBSEQ", str(S))
+    for name in ("synth_420_500x375_dri7", "synth_444_500x375", "mug_420_crop", "custom_huffman_420_dri1", "extreme_coefs_444"):
+        data = load(name)
+        st, got, want = gu.decode_one(dec, orc, data, "rgb")
+        assert st == api.SUCCESS and dec.stats().subsequence_bytes == S
+        gu.assert_same(got, want, f"{name} S={S}")
+
+
+def test_single_sync_round_forces_fallback_and_still_exact(dec, orc, monkeypatch):
+    """With only round 0 launched up front, the host must detect unresolved CTA boundaries,
+    run more rounds and redo the downstream stages."""
+    monkeypatch.setenv("ROCJPEG_B200_SYNC_ROUNDS", "1")
+    monkeypatch.setenv("ROCJPEG_B200_SUBSEQ", "32")
+    data = load("synth_444_500x375")
+    st, got, want = gu.decode_one(dec, orc, data, "rgb")
+    assert st == api.SUCCESS
+    assert dec.stats().sync_rounds >= 2
+    gu.assert_same(got, want, "fallback rounds")
+
+
+def test_image_info_and_errors(dec, orc):
+    lib = api.load_library()
+    s = api.JpegStream()
+    assert s.parse(load("synth_420_123x77")) == api.SUCCESS
+    n, css, w, h = dec.image_info(s)
+    assert (n, css, w, h) == (3, api.CSS_420, [123, 61, 61, 0], [77, 38, 38, 0])
+    assert s.parse(load("synth_440_123x77")) == api.SUCCESS
+    assert dec.image_info(s)[1:] == (api.CSS_440, [123, 123, 123, 0], [77, 38, 38, 0])
+    assert s.parse(load("synth_400_123x77")) == api.SUCCESS
+    assert dec.image_info(s) == (1, api.CSS_400, [123, 0, 0, 0], [77, 0, 0, 0])
+    # crop rectangle that passes the reference's size test but lies outside the picture
+    rc, info = orc.parse(load("synth_400_123x77"))
+    dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "y", (0, 0, 0, 0))
+    assert dec.decode(s, api.make_params("y", (100, 50, 150, 70)), dest) == api.INVALID_PARAMETER
+    # oversize crop is ignored (whole picture), as in the reference (src/rocjpeg_decoder.cpp:126-131)
+    assert dec.decode(s, api.make_params("y", (0, 0, 500, 500)), dest) == api.SUCCESS
+    # 4:1:1 stream: parses, cannot be decoded
+    from test_host_library import make_411
+
+    assert s.parse(make_411()) == api.SUCCESS
+    assert dec.decode(s, api.make_params("y"), dest) == api.JPEG_NOT_SUPPORTED
+    # unparsed stream handle
+    assert dec.decode(api.JpegStream(), api.make_params("y"), dest) == api.BAD_JPEG
+    # HYBRID backend and bad device id (src/rocjpeg_decoder.cpp:46-91)
+    with pytest.raises(api.RocJpegError) as e:
+        api.Decoder(api.BACKEND_HYBRID, 0)
+    assert e.value.status == api.NOT_IMPLEMENTED
+    with pytest.raises(api.RocJpegError) as e:
+        api.Decoder(api.BACKEND_HARDWARE, 99)
+    assert e.value.status == api.INVALID_PARAMETER
+    # a null / zero-pitch channel is skipped silently (src/rocjpeg_decoder.cpp:373)
+    data = load("synth_444_123x77")
+    assert s.parse(data) == api.SUCCESS
+    rc, info = orc.parse(data)
+    dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "yuv_planar", (0, 0, 0, 0))
+    dest[1] = (0, pitches[1])
+    assert dec.decode(s, api.make_params("yuv_planar"), dest) == api.SUCCESS
+    got = gu.fetch(bufs, pitches, shapes)
+    _, want = gu.oracle_outputs(orc, data, "yuv_planar", (0, 0, 0, 0), pitches)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2])
+    assert (got[1] == gu.FILL).all()
+    del lib
+
+
+def test_prepare_run_matches_decode(dec, orc):
+    data = load("synth_422_500x375")
+    s = api.JpegStream()
+    assert s.parse(data) == api.SUCCESS
+    rc, info = orc.parse(data)
+    dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "rgb", (0, 0, 0, 0))
+    dec.set_profiling(True)
+    assert dec.prepare([s], api.make_params("rgb"), [dest]) == api.SUCCESS
+    for _ in range(3):
+        assert dec.run() == api.SUCCESS
+    dec.set_profiling(False)
+    st = dec.stats()
+    assert st.total_ms > 0 and all(m >= 0 for m in st.stage_ms)
+    _, want = gu.oracle_outputs(orc, data, "rgb", (0, 0, 0, 0), pitches)
+    gu.assert_same(gu.fetch(bufs, pitches, shapes), want, "prepare/run")
+
+
+# ------------------------------------------------------------ BASELINE.json shapes
+
+def _check_batch(dec, orc, datas, fmt, uniq=None):
+    streams, dests, keep = [], [], []
+    for d in datas:
+        s = api.JpegStream()
+        assert s.parse(d) == api.SUCCESS
+        rc, info = orc.parse(d)
+        dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, fmt, (0, 0, 0, 0))
+        streams.append(s); dests.append(dest); keep.append((bufs, pitches, shapes))
+    assert dec.decode_batched(streams, api.make_params(fmt), dests) == api.SUCCESS
+    cache = {}
+    for i, (d, (bufs, pitches, shapes)) in enumerate(zip(datas, keep)):
+        key = id(d) if uniq is None else uniq[i]
+        if key not in cache:
+            cache[key] = gu.oracle_outputs(orc, d, fmt, (0, 0, 0, 0), pitches)[1]
+        gu.assert_same(gu.fetch(bufs, pitches, shapes), cache[key], f"image {i}")
+    return dec.stats()
+
+
+def test_config2_1080p_420_rgb(dec, orc, ljt):
+    datas, fmt = datagen.workload("c2")
+    st = _check_batch(dec, orc, datas, fmt)
+    assert st.blocks == 48960
+    # Y plane vs libjpeg-turbo directly (<= 1 LSB gate of BASELINE.json; it is 0 LSB)
+    rc, info = orc.parse(datas[0])
+    n = sum(info.blocks_w[c] * info.blocks_h[c] * 64 for c in range(3))
+    got = oracle.Oracle.split(info, dec.coefficients(0, n), 64)
+    lc = ljt.coefficients(datas[0], info)
+    assert all(np.array_equal(a, b) for a, b in zip(got, lc))
+
+
+def test_config3_imagenet_batch_rgb_planar(dec, orc):
+    datas, fmt = datagen.workload("c3", 96)
+    _check_batch(dec, orc, datas, fmt)
+    datas, fmt = datagen.workload("c3j", 48)   # jittered, odd sizes
+    _check_batch(dec, orc, datas, fmt)
+
+
+@pytest.mark.parametrize("which", ["c4_dri", "c4_nodri"])
+def test_config4_4k_422_yuv_planar(dec, orc, which):
+    datas, fmt = datagen.workload(which, 6)
+    datas = datas[:3] + datas[:3]
+    st = _check_batch(dec, orc, datas, fmt, uniq=[0, 1, 2, 0, 1, 2])
+    assert st.blocks == 6 * 259200
+
+
+@pytest.mark.parametrize("which", ["c5_400", "c5_440"])
+def test_config5_8k_single_image(dec, orc, which):
+    datas, fmt = datagen.workload(which)
+    st = _check_batch(dec, orc, datas, fmt)
+    assert st.blocks == (1048576 if which == "c5_400" else 2097152)
+
+
+# ------------------------------------------------------------ the reference's samples, unmodified
+
+SAMPLES = os.path.join(ROOT, "samples", "_build")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(SAMPLES, "jpegdecode")), reason="samples not built")
+@pytest.mark.parametrize("fmt", ["native", "yuv_planar", "y", "rgb", "rgb_planar"])
+@pytest.mark.parametrize("crop", [None, "16,8,80,56"])
+def test_reference_sample_jpegdecode(tmp_path, fmt, crop):
+    """The reference's CTest matrix (samples/CMakeLists.txt:25-178): build-and-run, exit code 0;
+    here additionally the saved output of one image is compared with the oracle."""
+    import shutil
+
+    src = tmp_path / "in"
+    src.mkdir()
+    for n in ("synth_420_500x375_dri7", "synth_444_500x375", "synth_422_500x375", "synth_400_333x211", "mug_420_crop"):
+        shutil.copy(os.path.join(GOLDEN, n + ".jpg"), src / (n + ".jpg"))
+    out = tmp_path / "out"
+    out.mkdir()
+    cmd = [os.path.join(SAMPLES, "jpegdecode"), "-i", str(src), "-fmt", fmt, "-o", str(out)]
+    if crop:
+        cmd += ["-crop", crop]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Total decoded images: 5" in r.stdout, r.stdout
+    assert len(list(out.iterdir())) == 5, r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(SAMPLES, "jpegdecodebatched")), reason="samples not built")
+def test_reference_samples_batched_and_perf(tmp_path):
+    import shutil
+
+    src = tmp_path / "in"
+    src.mkdir()
+    for n in CASES:
+        if _G["cases"][n]["width"] >= 64 and _G["cases"][n]["height"] >= 64:
+            shutil.copy(os.path.join(GOLDEN, n + ".jpg"), src / (n + ".jpg"))
+    r = subprocess.run([os.path.join(SAMPLES, "jpegdecodebatched"), "-i", str(src), "-fmt", "rgb", "-b", "4"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([os.path.join(SAMPLES, "jpegdecodeperf"), "-i", str(src), "-fmt", "native", "-t", "2", "-b", "3"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -1,0 +1,216 @@
+"""CPU-only checks of the product library: the C ABI loads and exports every symbol
+include/*.h declares, argument/error behaviour of the entry points that need no
+GPU, the extended parser against the oracle (and, when present, the reference's
+own parser), and the K1 schedule (csrc/huff_core.cuh + the CPU model of
+k1_huffman.cu's rounds) against golden coefficients. No compute call needs a GPU here.
+"""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from rocjpeg_b200 import api
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+with open(os.path.join(GOLDEN, "golden.json")) as _f:
+    _G = json.load(_f)
+CASES = sorted(_G["cases"])
+
+
+def load(name):
+    with open(os.path.join(GOLDEN, name + ".jpg"), "rb") as f:
+        return f.read()
+
+
+@pytest.fixture(scope="session")
+def lib():
+    if not os.path.exists(api.LIB_PATH):
+        import __graft_entry__ as ge
+
+        ge.build()
+    return api.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = set()
+    for hdr in ("rocjpeg.h", "rocjpeg_b200_ext.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        declared |= set(re.findall(r"\b(rocJpeg[A-Za-z0-9]+)\s*\(", text))
+    assert set(api.EXPORTS) | set(api.EXT_EXPORTS) == declared
+    out = subprocess.run(["nm", "-D", "--defined-only", api.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (rocJpeg\w+)", out))
+    assert declared <= exported, declared - exported
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_library_is_sm100a_cuda_code():
+    """The decode path is native sm_100a SASS (no PTX-JIT for another arch, no CPU stand-in)."""
+    out = subprocess.run(["cuobjdump", "-lelf", api.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    syms = subprocess.run(["cuobjdump", "-elf", api.LIB_PATH], capture_output=True, text=True).stdout
+    for kernel in ("k1_sync", "k1_write", "dc_apply", "k2_idct", "k3_output"):
+        assert kernel in syms, kernel
+
+
+def test_error_names_and_null_arguments(lib):
+    # src/rocjpeg_api.cpp:246-277 and the null checks at :39,69,87,108,133,162,195,223
+    for code, name in api.STATUS.items():
+        assert api.error_name(code) == name
+    assert api.error_name(12345) == "UNKNOWN_ERROR"
+    assert lib.rocJpegStreamCreate(None) == api.INVALID_PARAMETER
+    assert lib.rocJpegStreamDestroy(None) == api.INVALID_PARAMETER
+    assert lib.rocJpegCreate(0, 0, None) == api.INVALID_PARAMETER
+    assert lib.rocJpegDestroy(None) == api.INVALID_PARAMETER
+    s = api.JpegStream()
+    assert lib.rocJpegStreamParse(None, 10, s.handle) == api.INVALID_PARAMETER
+    assert lib.rocJpegStreamParse(b"abcd", 4, None) == api.INVALID_PARAMETER
+    assert lib.rocJpegDecode(None, s.handle, None, None) == api.INVALID_PARAMETER
+    assert lib.rocJpegDecodeBatched(None, None, 1, None, None) == api.INVALID_PARAMETER
+    assert lib.rocJpegGetImageInfo(None, s.handle, None, None, None, None) == api.INVALID_PARAMETER
+    assert s.parse(b"\x00\x01\x02\x03\x04") == api.BAD_JPEG
+    assert lib.rocJpegB200StreamGetInfo(s.handle, C.byref(api.StreamInfo())) == api.BAD_JPEG
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_parser_matches_oracle(lib, orc, name):
+    data = load(name)
+    s = api.JpegStream()
+    assert s.parse(data) == api.SUCCESS
+    i = s.info()
+    rc, o = orc.parse(data)
+    assert rc == 0
+    assert (i.width, i.height, i.num_components, i.chroma_subsampling) == (o.width, o.height, o.ncomp, o.css)
+    assert (i.scan_offset, i.scan_size, i.restart_interval, i.num_mcus) == (o.scan_offset, o.scan_size, o.restart_interval, o.num_mcus_ref)
+    assert (i.mcus_x, i.mcus_y, i.blocks_per_mcu) == (o.mcus_x, o.mcus_y, o.blocks_per_mcu)
+    for c in range(o.ncomp):
+        assert (i.h_sampling[c], i.v_sampling[c], i.quant_selector[c], i.dc_selector[c], i.ac_selector[c]) == (
+            o.hs[c], o.vs[c], o.tq[c], o.td[c], o.ta[c])
+        assert (i.blocks_w[c], i.blocks_h[c]) == (o.blocks_w[c], o.blocks_h[c])
+        q = s.quant_table(o.tq[c])
+        assert np.array_equal(q[orc.zigzag], np.frombuffer(bytes(o.qt[o.tq[c]]), dtype=np.uint8))
+    for t in range(2):
+        if o.dc_present[t]:
+            bits, vals = s.huffman_table(0, t)
+            assert bits == bytes(o.dc_bits[t]) and vals == bytes(o.dc_vals[t])[:len(vals)]
+        if o.ac_present[t]:
+            bits, vals = s.huffman_table(1, t)
+            assert bits == bytes(o.ac_bits[t]) and vals == bytes(o.ac_vals[t])[:len(vals)]
+    assert i.decode_status == orc.supported(o)
+    assert i.restart_markers_seen == o.n_restart_markers
+    # destuffed segments == an independent restatement of T.81 B.1.1.5 / E.1.4
+    scan = data[o.scan_offset:o.scan_offset + o.scan_size]
+    segs, cur, k = [], bytearray(), 0
+    while k < len(scan):
+        b = scan[k]
+        if b == 0xFF and k + 1 < len(scan):
+            n = scan[k + 1]
+            if n == 0:
+                cur.append(0xFF); k += 2; continue
+            if 0xD0 <= n <= 0xD7:
+                segs.append(bytes(cur)); cur = bytearray(); k += 2; continue
+            if n == 0xFF:
+                k += 1; continue
+        cur.append(b); k += 1
+    segs.append(bytes(cur))
+    total = o.mcus_x * o.mcus_y
+    expected = (total + o.restart_interval - 1) // o.restart_interval if o.restart_interval else 1
+    assert i.num_segments == expected == len(segs)
+    assert [s.segment(j) for j in range(i.num_segments)] == segs
+
+
+def test_parser_accept_reject_matches_oracle(lib, orc):
+    from test_oracle_pinning import _mutations
+
+    base = load("synth_420_123x77")
+    for name, data in _mutations(base).items():
+        s = api.JpegStream()
+        st = s.parse(data)
+        rc, o = orc.parse(data)
+        assert (st == api.SUCCESS) == (rc == 0), name
+        if st == api.SUCCESS:
+            assert s.info().decode_status == orc.supported(o), name
+    sos = base.index(b"\xFF\xDA")
+    for cut in (1, 2, 3, 10, sos - 3, sos + 2, sos + 5):
+        assert api.JpegStream().parse(base[:cut]) == api.BAD_JPEG
+    # a scan cut short still parses (slice runs to the end of the buffer), as in the reference
+    s = api.JpegStream()
+    assert s.parse(base[:sos + 200]) == api.SUCCESS
+    assert s.info().scan_size == len(base[:sos + 200]) - s.info().scan_offset
+
+
+def test_parser_reuse_and_unsupported(lib):
+    s = api.JpegStream()
+    assert s.parse(load("synth_444_500x375")) == api.SUCCESS
+    big = s.info().clean_bytes
+    assert s.parse(load("synth_420_64x64")) == api.SUCCESS
+    assert s.info().clean_bytes < big and s.info().width == 64
+    # progressive (SOF2): the frame header is skipped like any unknown marker, so the scan
+    # header cannot match it -> BAD_JPEG, exactly as the reference parser decides
+    base = bytearray(load("synth_420_123x77"))
+    i = bytes(base).index(b"\xFF\xC0")
+    base[i + 1] = 0xC2
+    assert s.parse(bytes(base)) == api.BAD_JPEG
+    # 4:1:1 parses (ROCJPEG_CSS_411) but is not decodable, as in the reference (samples skip it)
+    assert s.parse(make_411()) == api.SUCCESS
+    assert s.info().chroma_subsampling == api.CSS_411 and s.info().decode_status == api.JPEG_NOT_SUPPORTED
+
+
+def make_411():
+    import jpeg_writer as jw
+
+    coefs = [np.zeros((1, 4, 64), np.int16), np.zeros((1, 1, 64), np.int16), np.zeros((1, 1, 64), np.int16)]
+    return jw.write_jpeg(32, 8, coefs, [4, 1, 1], [1, 1, 1], [0, 0, 0], {0: bytes([1] * 64)})
+
+
+def test_decoder_creation_without_gpu_fails_loudly(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.RocJpegError) as e:
+        api.Decoder()
+    assert e.value.status == api.NOT_INITIALIZED
+
+
+# ---------------------------------------------------------------- K1 schedule on the CPU
+
+class _ModelStats(C.Structure):
+    _fields_ = [("rounds", C.c_uint32), ("decodes", C.c_uint32 * 8), ("max_local_iters", C.c_uint32),
+                ("nsub", C.c_uint32), ("nctas", C.c_uint32)]
+
+
+@pytest.fixture(scope="session")
+def k1_model():
+    out = os.path.join(HERE, "_build", "libk1model.so")
+    src = [os.path.join(HERE, "k1_model.cpp"), os.path.join(ROOT, "rocjpeg_b200", "csrc", "jpeg_parser.cpp")]
+    deps = src + [os.path.join(ROOT, "rocjpeg_b200", "csrc", f) for f in ("huff_core.cuh", "jpeg_parser.h", "device_types.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "rocjpeg_b200", "csrc"),
+                        "-I", "/usr/local/cuda/include", *src, "-L/usr/local/cuda/lib64", "-lcudart", "-o", out], check=True)
+    L = C.CDLL(out)
+    L.k1_model_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(_ModelStats)]
+    return L
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_k1_schedule_model_matches_oracle(k1_model, orc, name):
+    data = load(name)
+    rc, info = orc.parse(data)
+    want = np.concatenate([c.reshape(-1) for c in orc.coefficients(data, info)])
+    for S, T in [(32, 128), (64, 128), (128, 128), (32, 4), (64, 2), (128, 1)]:
+        out = np.zeros(want.size, dtype=np.int16)
+        st = _ModelStats()
+        assert k1_model.k1_model_decode(data, len(data), S, T, out.ctypes.data, out.size, C.byref(st)) == 0
+        assert np.array_equal(out, want), (name, S, T)
+        assert st.rounds >= 2
