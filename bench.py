@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — decoded MP/s and images/s of rocJpegDecodeBatched on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+
+A "step" is one rocJpegDecodeBatched pass over one batch of synthetic JPEGs (seeded, encoded
+here at quality 90 — rocjpeg_b200/datagen.py). Default workload = BASELINE.json configs[2]
+("c3": 256 ImageNet-shaped 500x375 images, mixed 4:4:4/4:2:2/4:2:0, -> RGB_PLANAR), the
+configuration the metric "rocJpegDecodeBatched at 1/2/4/8 B200" is quoted on; the other
+configs are selectable with --workload (c2, c3j, c4_dri, c4_nodri, c5_400, c5_440).
+
+Our arm prints ONE JSON line:
+  value        device-resident throughput: batch already in HBM (rocJpegB200Prepare), each step
+               = rocJpegB200Run (every kernel of the path), CUDA events on the decoder's stream
+  e2e          the same metric through rocJpegDecodeBatched itself: HOST JPEG buffers in, the
+               host->device copy of descriptors + entropy-coded bytes and the device->host
+               read-back of the decoder's status counters inside the timed region (wall clock
+               around the synchronous call, as the reference's samples time it). Pixels stay in
+               device memory: that is the API's contract (api/rocjpeg.h:104-107).
+  roofline     the dominant kernel stage (by device time) against the measured HBM peak
+  cpu_baseline multithreaded libjpeg-turbo (Pillow's 3.1.4.1) decoding the identical files on
+               this box's host cores — the baseline BASELINE.json prescribes, because the
+               reference has no CPU decode path (src/rocjpeg_decoder.cpp:87-88)
+`--impl reference` times that CPU baseline alone and prints it in the same shape.
+Multi-GPU: one process per GPU (torchrun), every rank decodes its own full batch (weak
+scaling, images are independent — no data-path collective); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decoded_MP_per_s_rocJpegDecodeBatched"
+UNIT = "MP/s"
+WORKLOAD_DESC = {
+    "c2": "single 1920x1080 4:2:0 q90 baseline JPEG, no DRI -> RGB (BASELINE configs[1])",
+    "c3": "256 x 500x375 q90 baseline JPEGs, 4:4:4/4:2:2/4:2:0 round-robin, no DRI -> RGB_PLANAR (BASELINE configs[2])",
+    "c3j": "256 jittered-size (300-640 x 224-500) q90 JPEGs, mixed subsampling -> RGB_PLANAR",
+    "c4_dri": "64 x 3840x2160 4:2:2 q90, DRI = one MCU row -> YUV_PLANAR (BASELINE configs[3])",
+    "c4_nodri": "64 x 3840x2160 4:2:2 q90, no restart markers -> YUV_PLANAR (BASELINE configs[3])",
+    "c5_400": "single 8192x8192 4:0:0 q90, no DRI -> Y (BASELINE configs[4])",
+    "c5_440": "single 8192x8192 4:4:0 q90, no DRI -> NATIVE (BASELINE configs[4])",
+}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, n):
+    from rocjpeg_b200 import datagen
+
+    datas, fmt = datagen.workload(name, n)
+    return datas, fmt
+
+
+def pixels_of(datas):
+    import oracle  # header parse only, for width/height of the inputs
+
+    orc = oracle.Oracle()
+    tot, dims = 0, []
+    for d in datas:
+        rc, i = orc.parse(d)
+        tot += i.width * i.height
+        dims.append((i.width, i.height, oracle.CSS[i.css]))
+    return tot, dims
+
+
+def run_cpu_baseline(datas, fmt, budget_s=12.0, threads=None):
+    """Multithreaded libjpeg-turbo (default islow decode) of the same files, in host memory.
+    Returns (MP/s, images/s, threads, description of the sample)."""
+    import numpy as np
+
+    import oracle
+
+    ljt = oracle.LibJpegTurbo()
+    orc = oracle.Oracle()
+    threads = threads or os.cpu_count() or 1
+    mode = {"rgb": 0, "rgb_planar": 0, "y": 1, "yuv_planar": 2, "native": 2}[fmt]
+    outs, pitches, mp = [], [], 0
+    uniq = {}
+    for d in datas:
+        rc, i = orc.parse(d)
+        mp += i.width * i.height
+        if mode == 0:
+            outs.append(np.empty((i.height, i.width * 3), np.uint8)); pitches.append(i.width * 3)
+        elif mode == 1:
+            outs.append(np.empty((i.height, i.width), np.uint8)); pitches.append(i.width)
+        else:
+            n = sum(i.blocks_w[c] * i.blocks_h[c] * 64 for c in range(i.ncomp))
+            outs.append(np.empty(n, np.uint8)); pitches.append(0)
+    ljt.decode_batch(datas, outs, pitches, mode, threads)   # warm-up pass
+    passes, t0 = 0, time.perf_counter()
+    while True:
+        ljt.decode_batch(datas, outs, pitches, mode, threads)
+        passes += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or passes >= 200:
+            break
+    sample = f"{passes} passes over the full batch ({len(datas)} images, {mp / 1e6:.1f} MP) with {threads} host threads, " \
+             f"libjpeg-turbo {os.path.basename(ljt.path)} default decode -> " \
+             f"{'RGB' if mode == 0 else 'Y' if mode == 1 else 'raw YCbCr planes'} in host memory"
+    return mp * passes / el / 1e6, len(datas) * passes / el, threads, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--batch", type=int, default=0, help="override the number of images")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": f"{args.workload}: {WORKLOAD_DESC[args.workload]}", "per_gpu_batch": None,
+              "output_format": None, "l2": "256 MiB device buffer written between timed steps (L2 flush)",
+              "parallelism": f"{world} independent replicas, one process per GPU, no collective" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        # The reference cannot run without an AMD VCN engine and has no CPU path; the CPU arm is
+        # the baseline BASELINE.json prescribes. Rank 0 alone runs it.
+        if rank != 0:
+            return
+        datas, fmt = build_workload(args.workload, args.batch or None)
+        config["per_gpu_batch"], config["output_format"] = len(datas), fmt
+        per = max(2.0, min(args.cpu_budget, 60.0 / max(args.steps + args.warmup, 1)))
+        for _ in range(min(args.warmup, 1)):
+            run_cpu_baseline(datas, fmt, 0.5)
+        t0 = time.perf_counter()
+        mps, ips, threads, sample = run_cpu_baseline(datas, fmt, per * 3)
+        line = {"impl": "reference", "metric": METRIC, "value": round(mps, 2), "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * len(datas) / ips, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (libjpeg-turbo islow)",
+                "data": "synthetic", "config": config, "images_per_s": round(ips, 1),
+                "cpu_baseline": {"value": round(mps, 2), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                 "host_cpus": os.cpu_count()},
+                "e2e": {"value": round(mps, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 2)}
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    from rocjpeg_b200 import api
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: rocjpeg_b200 has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    datas, fmt = build_workload(args.workload, args.batch or None)
+    total_px, dims = pixels_of(datas)
+    config["per_gpu_batch"], config["output_format"] = len(datas), fmt
+    config["scan_bytes_per_batch"] = sum(len(d) for d in datas)
+
+    dec = api.Decoder(api.BACKEND_HARDWARE, local_rank)
+    streams = []
+    t0 = time.perf_counter()
+    for d in datas:
+        s = api.JpegStream()
+        assert s.parse(d) == api.SUCCESS
+        streams.append(s)
+    first_parse_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for s, d in zip(streams, datas):
+        assert s.parse(d) == api.SUCCESS
+    parse_s = time.perf_counter() - t0
+    dests, keep = [], []
+    for (w, h, css) in dims:
+        chans = api.output_channel_shapes(css, fmt, w, h)
+        pitches = [rb for (_, rb) in chans]
+        if fmt == "yuv_planar" and css in ("422", "420"):
+            pitches[2] = pitches[1]
+        bufs = [torch.empty(rows * p + 64, dtype=torch.uint8, device="cuda") for (rows, _), p in zip(chans, pitches)]
+        keep.append(bufs)
+        dests.append([(b.data_ptr(), p) for b, p in zip(bufs, pitches)])
+    params = api.make_params(fmt)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def l2_flush():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm (value) -------------------------------------------------
+    dec.set_profiling(True)
+    assert dec.prepare(streams, params, dests) == api.SUCCESS
+    for _ in range(args.warmup):
+        assert dec.run() == api.SUCCESS
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    step_ms, stage_ms, launches = [], [0.0] * len(api.STAGES), 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        l2_flush()
+        assert dec.run() == api.SUCCESS
+        st = dec.stats()
+        step_ms.append(st.total_ms)
+        launches += st.kernel_launches
+        for i in range(len(api.STAGES)):
+            stage_ms[i] += st.stage_ms[i]
+    barrier()
+    resident_wall = time.perf_counter() - wall0
+    stage_ms = [m / args.steps for m in stage_ms]
+    resident_ms = sum(step_ms) / len(step_ms)
+    stats = dec.stats()
+
+    # ---- end-to-end arm (e2e): the public call, host buffers in ------------------------
+    for _ in range(args.warmup):
+        assert dec.decode_batched(streams, params, dests) == api.SUCCESS
+    barrier()
+    e2e_s, e2e_launches = [], 0
+    for _ in range(args.steps):
+        l2_flush()
+        t0 = time.perf_counter()
+        rc = dec.decode_batched(streams, params, dests)
+        e2e_s.append(time.perf_counter() - t0)
+        assert rc == api.SUCCESS
+        e2e_launches += dec.stats().kernel_launches
+    barrier()
+    e2e_stats = dec.stats()
+    e2e_ms = 1e3 * sum(e2e_s) / len(e2e_s)
+    # parse + decode (the reference's samples leave parsing outside their timer; reported for honesty)
+    pd_s = []
+    for _ in range(max(3, args.steps // 4)):
+        l2_flush()
+        t0 = time.perf_counter()
+        for s, d in zip(streams, datas):
+            s.parse(d)
+        dec.decode_batched(streams, params, dests)
+        pd_s.append(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    dec.set_profiling(False)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([resident_ms, e2e_ms, 1e3 * sum(pd_s) / len(pd_s)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        resident_ms, e2e_ms, pd_ms = [float(x) for x in t.tolist()]
+    else:
+        pd_ms = 1e3 * sum(pd_s) / len(pd_s)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    mp_total = total_px * world / 1e6
+    images_total = len(datas) * world
+    value = mp_total / (resident_ms / 1e3)
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes per stage (DESIGN.md section 5 / SURVEY.md section 8d)
+    blocks, scan = stats.blocks, stats.scan_bytes
+    k3_read = stats.plane_bytes
+    stage_bytes = {
+        "clear": blocks * 128,                                  # coefficient arena zeroed
+        "huffman_sync": scan * 2,                               # ~2 speculative decodes of every byte, no output
+        "huffman_write": scan + blocks * 130,                   # scan read + int16 coefficients + DC diff written
+        "dc": blocks * 2 * 2 + blocks * 2,                      # diffs read twice, absolute DC written
+        "idct": blocks * 192,                                   # 128 B read + 64 B written per block
+        "output": k3_read + stats.output_bytes,                 # planes read at coded resolution + pixels written
+    }
+    stages = {}
+    for i, name in enumerate(api.STAGES):
+        ms = stage_ms[i]
+        b = stage_bytes.get(name)
+        stages[name] = {"ms": round(ms, 4), "GB_s": round(b / ms / 1e6, 1) if b and ms > 0 else None}
+    dom = max((n for n in stage_bytes), key=lambda n: stages[n]["ms"])
+    dom_ms = stages[dom]["ms"]
+    achieved = stage_bytes[dom] / dom_ms / 1e6 if dom_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(resident_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 / int16 coefficients / int32 IDCT / fp32 colour", "data": "synthetic", "config": config,
+        "images_per_s": round(images_total / (resident_ms / 1e3), 1),
+        "e2e": {"value": round(mp_total / (e2e_ms / 1e3), 1), "unit": UNIT, "images_per_s": round(images_total / (e2e_ms / 1e3), 1),
+                "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": int(e2e_stats.h2d_bytes), "d2h_bytes_per_step": int(e2e_stats.d2h_bytes),
+                "note": "rocJpegDecodeBatched wall clock; JPEG bytes in pinned host staging, pixels left in device memory as the API specifies"},
+        "e2e_with_parse": {"value": round(mp_total / (pd_ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(pd_ms, 3),
+                           "parse_ms_per_batch": round(parse_s * 1e3, 3), "first_parse_ms": round(first_parse_s * 1e3, 3)},
+        "gpu_launches": int(launches + e2e_launches),
+        "launches_per_step": int(stats.kernel_launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(stage_bytes[dom]), "launch_ms": dom_ms},
+        "stages": stages,
+        "k1": {"subsequence_bytes": stats.subsequence_bytes, "subsequences": int(stats.subsequences), "sync_rounds": stats.sync_rounds,
+               "decodes_per_round": [int(x) for x in stats.decodes_per_round[:stats.sync_rounds]],
+               "compressed_GB_s_all_k1": round(scan / ((stage_ms[2] + stage_ms[3]) or 1e-9) / 1e6, 2)},
+        "clocks": clocks, "resident_wall_s": round(resident_wall, 3),
+    }
+    if not args.no_cpu_baseline:
+        mps, ips, threads, sample = run_cpu_baseline(datas, fmt, args.cpu_budget)
+        line["cpu_baseline"] = {"value": round(mps, 2), "unit": UNIT, "images_per_s": round(ips, 1), "cores": threads, "kind": "port",
+                                "sample": sample, "host_cpus": os.cpu_count()}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

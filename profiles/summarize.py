@@ -1,0 +1,65 @@
+"""Turn ncu outputs brought back in gpurun_out/ into the small, tracked summaries under profiles/.
+
+  python profiles/summarize.py <tag> <launches.csv> [<report.ncu-rep>]
+
+Writes profiles/<tag>_launches.md (per-kernel launch count, mean duration, share of the step) and,
+when a full report is given, profiles/<tag>_kernels.md (DRAM bytes, throughput %, issue %, stalls).
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+tag, launches = sys.argv[1], sys.argv[2]
+rep = sys.argv[3] if len(sys.argv) > 3 else None
+rows = list(csv.reader(open(launches)))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+hdr, data = rows[hi], rows[hi + 1:]
+ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+agg = collections.OrderedDict()
+for r in data:
+    if len(r) <= vi:
+        continue
+    v = float(r[vi].replace(",", ""))
+    v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
+    agg.setdefault(r[ki].split("(")[0].replace("rjb::<unnamed>::", "").replace("void ", ""), []).append(v)
+tot = sum(sum(v) for v in agg.values())
+with open(f"profiles/{tag}_launches.md", "w") as f:
+    f.write(f"# {tag}: ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n\n")
+    f.write("| kernel | launches | mean us | share |\n|---|---|---|---|\n")
+    for k, v in agg.items():
+        f.write(f"| {k[:60]} | {len(v)} | {sum(v) / len(v):.1f} | {100 * sum(v) / tot:.1f}% |\n")
+if rep:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h, u, d = rr[0], rr[1], rr[2:]
+    cols = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "us"), ("launch__grid_size", "grid"),
+            ("launch__registers_per_thread", "regs"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+            ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ %"),
+            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+            ("smsp__inst_executed.sum", "warp inst"),
+            ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"),
+            ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st long_sb"),
+            ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "st short_sb"),
+            ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st barrier"),
+            ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem conflicts")]
+    idx = [(h.index(c), n) for c, n in cols if c in h]
+    with open(f"profiles/{tag}_kernels.md", "w") as f:
+        f.write(f"# {tag}: ncu --set full --clock-control none, one row per captured launch\n\n")
+        f.write("| " + " | ".join(n for _, n in idx) + " |\n|" + "---|" * len(idx) + "\n")
+        for r in d:
+            cells = []
+            for i, n in idx:
+                v = r[i]
+                if n == "kernel":
+                    v = v.split("(")[0].replace("unnamed>::", "").replace("void ", "")
+                else:
+                    try:
+                        v = f"{float(v.replace(',', '')):.4g} {u[i]}".replace(" inst", "").replace(" register/thread", "")
+                    except ValueError:
+                        pass
+                cells.append(v)
+            f.write("| " + " | ".join(cells) + " |\n")
+print("ok")
