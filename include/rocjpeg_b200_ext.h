@@ -41,6 +41,7 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;            /* host<->device traffic of the last call */
     uint32_t kernel_launches;                 /* kernels launched by the last call */
     int32_t subsequence_bytes;                /* S chosen for the batch */
+    int32_t lanes;                            /* pipeline lanes (streams) the batch was split over */
 } RocJpegB200Stats;
 
 /* Enable/disable CUDA-event stage timing on a decoder handle (off by default; env ROCJPEG_B200_PROFILE=1). */

@@ -57,7 +57,7 @@ class Stats(C.Structure):
         ("decodes_per_round", C.c_uint32 * 8), ("scan_bytes", C.c_uint64), ("blocks", C.c_uint64),
         ("subsequences", C.c_uint64), ("plane_bytes", C.c_uint64), ("output_bytes", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
-        ("subsequence_bytes", C.c_int32),
+        ("subsequence_bytes", C.c_int32), ("lanes", C.c_int32),
     ]
 
 
@@ -253,10 +253,15 @@ class Decoder:
         img = self._images([dest])
         return self.lib.rocJpegDecode(self.handle, stream.handle, C.byref(params), img)
 
-    def decode_batched(self, streams, params: RocJpegDecodeParams, dests) -> int:
+    def make_batch(self, streams, dests):
+        """Pre-built argument arrays for decode_batched (what a C caller already holds), so a
+        timed region around the call measures the library, not ctypes marshalling."""
         hs = (C.c_void_p * len(streams))(*[s.handle for s in streams])
-        imgs = self._images(dests)
-        return self.lib.rocJpegDecodeBatched(self.handle, hs, len(streams), C.byref(params), imgs)
+        return (hs, self._images(dests), len(streams), list(streams))
+
+    def decode_batched(self, streams, params: RocJpegDecodeParams, dests=None) -> int:
+        hs, imgs, n, _ = streams if dests is None else self.make_batch(streams, dests)
+        return self.lib.rocJpegDecodeBatched(self.handle, hs, n, C.byref(params), imgs)
 
     # ---- extension taps -------------------------------------------------
     def prepare(self, streams, params, dests) -> int:

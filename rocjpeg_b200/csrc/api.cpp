@@ -226,6 +226,7 @@ RocJpegStatus rocJpegB200GetStats(RocJpegHandle handle, RocJpegB200Stats* stats)
     stats->d2h_bytes = s.d2h_bytes;
     stats->kernel_launches = s.kernel_launches;
     stats->subsequence_bytes = s.sub_bytes;
+    stats->lanes = s.lanes;
     return ROCJPEG_STATUS_SUCCESS;
 }
 

@@ -68,14 +68,38 @@ cudaError_t DeviceBuffer::Reserve(size_t bytes) {
     return cudaSuccess;
 }
 
-Decoder::Decoder(int backend, int device_id) : backend_(backend), device_id_(device_id) {}
-
-Decoder::~Decoder() {
-    if (!initialized_) return;
-    DeviceGuard guard(device_id_);
+Lane::~Lane() {
+    if (!created_) return;
     for (auto& e : ev_)
         if (e) cudaEventDestroy(e);
+    if (ev_uploaded_) cudaEventDestroy(ev_uploaded_);
     if (stream_) cudaStreamDestroy(stream_);
+}
+
+int Lane::Fail(int status, const std::string& why) {
+    err_ = why;
+    return status;
+}
+
+int Lane::Create(int /*device_id*/, int sm_count) {
+    if (created_) return kSuccess;
+    sm_count_ = sm_count;
+    RJB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& ev : ev_) RJB_CUDA(cudaEventCreate(&ev));
+    RJB_CUDA(cudaEventCreateWithFlags(&ev_uploaded_, cudaEventDisableTiming));
+    created_ = true;
+    return kSuccess;
+}
+
+int Lane::Sync() {
+    RJB_CUDA(cudaStreamSynchronize(stream_));
+    return kSuccess;
+}
+
+Decoder::Decoder(int backend, int device_id) : backend_(backend), device_id_(device_id) {}
+
+Decoder::~Decoder() {   // lanes release their own streams, events and arenas
+    if (upload_stream_) cudaStreamDestroy(upload_stream_);
 }
 
 int Decoder::Fail(int status, const std::string& why) {
@@ -103,8 +127,9 @@ int Decoder::Initialize() {
     cudaDeviceProp prop;
     RJB_CUDA(cudaGetDeviceProperties(&prop, device_id_));
     sm_count_ = prop.multiProcessorCount;
-    RJB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    for (auto& ev : ev_) RJB_CUDA(cudaEventCreate(&ev));
+    int st = lanes_[0].Create(device_id_, sm_count_);
+    if (st != kSuccess) return Fail(st, lanes_[0].last_error());
+    RJB_CUDA(cudaStreamCreateWithFlags(&upload_stream_, cudaStreamNonBlocking));
     profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0) != 0;
     initialized_ = true;
     return kSuccess;
@@ -151,10 +176,9 @@ static uint64_t OutputBytes(int css, int fmt, int W, int H) {
     }
 }
 
-int Decoder::BuildBatch(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
+int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
     if (params.output_format < FMT_NATIVE || params.output_format > FMT_RGB_PLANAR)
         return Fail(kInvalidParameter, "unknown output format");
-    batch_.assign(streams, streams + n);
     h_images_.assign(size_t(n), ImageDesc{});
     h_outputs_.assign(size_t(n), OutputDesc{});
     h_segments_.clear();
@@ -174,8 +198,6 @@ int Decoder::BuildBatch(const StreamParser* const* streams, int n, const DecodeP
         const ParsedJpeg& p = streams[i]->parsed();
         if (!p.valid) return Fail(kBadJpeg, "stream handle holds no successfully parsed JPEG");
         if (p.support_status != kSuccess) {
-            if (p.support_status == kNotSupported)
-                std::cerr << "[ERR]  {Decode}  The JPEG image (chroma subsampling / layout / size) is not supported!" << std::endl;
             return Fail(p.support_status, "unsupported or inconsistent JPEG");
         }
         if (!streams[i]->clean().data() || p.clean_bytes == 0) return Fail(kOutOfMemory, "no staging memory for the scan");
@@ -188,6 +210,7 @@ int Decoder::BuildBatch(const StreamParser* const* streams, int n, const DecodeP
     if (S != 32 && S != 64 && S != 128) S = (total_clean >= (256u << 10)) ? 128 : (total_clean >= (48u << 10)) ? 64 : 32;
     stats_.sub_bytes = S;
 
+    needs_clear_ = false;
     uint64_t scan_off = 0, blk = 0, plane_off = 0;
     uint32_t sub = 0, dctile = 0, k2tile = 0, k3tile = 0, chunk = 0;
     all_pinned_ = true;
@@ -216,10 +239,10 @@ int Decoder::BuildBatch(const StreamParser* const* streams, int n, const DecodeP
         // Huffman table set, de-duplicated across the batch
         int set = -1;
         for (size_t s = 0; s < h_lut_hashes_.size(); s++)
-            if (h_lut_hashes_[s] == p.lut_hash && std::memcmp(h_lut_ptrs_[s], &p.lut, sizeof(HuffLutSet)) == 0) set = int(s);
+            if (h_lut_hashes_[s] == p.lut_hash && std::memcmp(h_lut_ptrs_[s], &streams[i]->lut(), sizeof(HuffLutSet)) == 0) set = int(s);
         if (set < 0) {
             set = int(h_lut_ptrs_.size());
-            h_lut_ptrs_.push_back(&p.lut);
+            h_lut_ptrs_.push_back(&streams[i]->lut());
             h_lut_hashes_.push_back(p.lut_hash);
         }
         im.lut_set = set;
@@ -240,6 +263,7 @@ int Decoder::BuildBatch(const StreamParser* const* streams, int n, const DecodeP
             sd.blk_first = uint32_t(mcu_first * uint64_t(p.bpm));
             sd.blk_count = uint32_t(mcu_cnt * uint64_t(p.bpm));
             h_segments_.push_back(sd);
+            if (sd.nbytes == 0 && sd.blk_count != 0) needs_clear_ = true;   // a restart interval with no data at all
             sub += (sg.nbytes + uint32_t(S) - 1) / uint32_t(S);
         }
         im.nsub = sub - im.sub0;
@@ -317,11 +341,12 @@ int Decoder::BuildBatch(const StreamParser* const* streams, int n, const DecodeP
 }
 
 // Descriptor block: one pinned host buffer mirrored by one device buffer, one copy.
-struct Decoder::Layout {
+struct Lane::Layout {
     size_t images, outputs, segments, cta0, dctile0, k2tile0, k3tile0, gather, luts, qtables, total;
 };
 
-int Decoder::Upload() {
+int Lane::Upload(cudaStream_t up) {
+    if (up == nullptr) up = stream_;
     const size_t n = h_images_.size();
     Layout L;
     size_t o = 0;
@@ -383,36 +408,49 @@ int Decoder::Upload() {
     k2_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k2tile0);
     k2_.qtables = reinterpret_cast<const uint16_t*>(d + L.qtables);
     k2_.coef = k1_.coef;
+    k2_.dc = k1_.dcdiff;
     k2_.planes = d_planes_.as<uint8_t>();
     k3_.images = k1_.images;
     k3_.outputs = reinterpret_cast<const OutputDesc*>(d + L.outputs);
     k3_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k3tile0);
     k3_.planes = k2_.planes;
 
-    RJB_CUDA(cudaMemcpyAsync(d, h, L.total, cudaMemcpyHostToDevice, stream_));
+    // Uploads of all lanes go through ONE stream, in lane order: the first chunk gets the whole
+    // PCIe link and its kernels start while the next chunks are still in flight.
+    RJB_CUDA(cudaMemcpyAsync(d, h, L.total, cudaMemcpyHostToDevice, up));
     stats_.h2d_bytes = L.total + scan_bytes_;
     const bool use_gather = all_pinned_ && h_images_.size() > 4 && EnvInt("ROCJPEG_B200_NO_GATHER", 0) == 0;
     if (use_gather) {
-        RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, d_scan_.as<uint8_t>(), stream_));
+        RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, d_scan_.as<uint8_t>(), up));
         stats_.kernel_launches++;
     } else {
         for (size_t i = 0; i < n; i++)
             RJB_CUDA(cudaMemcpyAsync(d_scan_.as<uint8_t>() + h_gather_[i].dst_off, h_gather_[i].src, h_gather_[i].nbytes,
-                                     cudaMemcpyHostToDevice, stream_));
+                                     cudaMemcpyHostToDevice, up));
+    }
+    if (up != stream_) {
+        RJB_CUDA(cudaEventRecord(ev_uploaded_, up));
+        RJB_CUDA(cudaStreamWaitEvent(stream_, ev_uploaded_, 0));
     }
     return kSuccess;
 }
 
-int Decoder::LaunchAll(bool include_upload) {
+int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up) {
     const int rounds = std::min(std::max(EnvInt("ROCJPEG_B200_SYNC_ROUNDS", 2), 1), kMaxSyncRounds);
     auto mark = [&](int i) -> cudaError_t { return profiling_ ? cudaEventRecord(ev_[i], stream_) : cudaSuccess; };
+    stats_.kernel_launches = 0;
     RJB_CUDA(mark(0));
     if (include_upload) {
-        int st = Upload();
+        int st = Upload(up);
         if (st != kSuccess) return st;
     }
     RJB_CUDA(mark(1));
-    RJB_CUDA(cudaMemsetAsync(d_coef_.as<uint8_t>(), 0, coef_blocks_ * 128, stream_));
+    // the coefficient arena is NOT cleared: k1_write stores every block as a whole line
+    // (except for damaged streams with restart intervals that carry no data at all)
+    if (needs_clear_) {
+        RJB_CUDA(cudaMemsetAsync(d_coef_.as<uint8_t>(), 0, coef_blocks_ * 128, stream_));
+        RJB_CUDA(cudaMemsetAsync(d_dcdiff_.as<uint8_t>(), 0, coef_blocks_ * 2, stream_));
+    }
     RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint8_t>(), 0, 256, stream_));
     RJB_CUDA(mark(2));
     for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
@@ -426,13 +464,13 @@ int Decoder::LaunchAll(bool include_upload) {
     RJB_CUDA(mark(6));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + 1 + 2 + 1 + 1 + 2;   // + the two memset launches
+    stats_.kernel_launches += uint32_t(rounds) + 1 + 2 + 1 + 1 + 1;   // + the counter memset
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), d_counters_.as<uint8_t>(), 256, cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256;
     return kSuccess;
 }
 
-int Decoder::Finish() {
+int Lane::Finish(bool profiling_) {
     RJB_CUDA(cudaStreamSynchronize(stream_));
     const uint32_t* cnt = reinterpret_cast<const uint32_t*>(h_counters_.data());
     uint32_t last = stats_.sync_rounds - 1;
@@ -453,13 +491,12 @@ int Decoder::Finish() {
             if (cnt[slot] == 0) break;
             if (++guard > k1_.total_ctas + 2) return Fail(kExecutionFailed, "entropy decoder failed to converge");
         }
-        RJB_CUDA(cudaMemsetAsync(d_coef_.as<uint8_t>(), 0, coef_blocks_ * 128, stream_));
         RJB_CUDA(LaunchK1Write(k1_, stream_));
         RJB_CUDA(LaunchDcScan(k1_, stream_));
         RJB_CUDA(LaunchK2Idct(k2_, stream_));
         RJB_CUDA(LaunchK3Output(k3_, stream_));
         RJB_CUDA(cudaStreamSynchronize(stream_));
-        stats_.kernel_launches += 6;
+        stats_.kernel_launches += 5;
     }
     for (int r = 0; r < kMaxSyncRounds; r++) stats_.decodes_per_round[r] = cnt[kMaxSyncRounds + r];
     if (profiling_) {
@@ -474,6 +511,95 @@ int Decoder::Finish() {
     return kSuccess;
 }
 
+// Contiguous split of the batch into chunks of similar entropy-coded size, one per lane.
+int Decoder::Split(const StreamParser* const* streams, int n) {
+    uint64_t total = 0;
+    for (int i = 0; i < n; i++) total += streams[i] ? streams[i]->parsed().clean_bytes : 0;
+    int want = EnvInt("ROCJPEG_B200_LANES", 0);
+    if (want <= 0) want = int(std::min<uint64_t>(kMaxLanes, total / (2u << 20)));   // about 2 MiB of scan per chunk at least
+    want = std::max(1, std::min(std::min(want, kMaxLanes), n));
+    uint64_t acc = 0;
+    int lane = 0;
+    chunk_first_[0] = 0;
+    for (int i = 0; i < n && lane + 1 < want; i++) {
+        acc += streams[i] ? streams[i]->parsed().clean_bytes : 0;
+        if (acc * uint64_t(want) >= total * uint64_t(lane + 1) && i + 1 < n) chunk_first_[++lane] = i + 1;
+    }
+    active_lanes_ = lane + 1;
+    chunk_first_[active_lanes_] = n;
+    return active_lanes_;
+}
+
+int Decoder::BuildAll(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, bool launch) {
+    // validate the whole batch before anything is launched: an error leaves every destination untouched
+    for (int i = 0; i < n; i++) {
+        if (!streams[i]) return Fail(kInvalidParameter, "null stream handle in batch");
+        const ParsedJpeg& p = streams[i]->parsed();
+        if (!p.valid) return Fail(kBadJpeg, "stream handle holds no successfully parsed JPEG");
+        if (p.support_status != kSuccess) {
+            if (p.support_status == kNotSupported)
+                std::cerr << "[ERR]  {Decode}  The JPEG image (chroma subsampling / layout / size) is not supported!" << std::endl;
+            return Fail(p.support_status, "unsupported or inconsistent JPEG");
+        }
+        const uint32_t rw = uint32_t(int(params.crop_right) - int(params.crop_left));
+        const uint32_t rh = uint32_t(int(params.crop_bottom) - int(params.crop_top));
+        if (rw > 0 && rh > 0 && rw <= uint32_t(p.width) && rh <= uint32_t(p.height) &&
+            (params.crop_left < 0 || params.crop_top < 0 || params.crop_right > p.width || params.crop_bottom > p.height))
+            return Fail(kInvalidParameter, "crop rectangle lies outside the picture");
+    }
+    if (params.output_format < FMT_NATIVE || params.output_format > FMT_RGB_PLANAR)
+        return Fail(kInvalidParameter, "unknown output format");
+    Split(streams, n);
+    for (int l = 0; l < active_lanes_; l++) {
+        Lane& lane = lanes_[l];
+        int st = lane.Create(device_id_, sm_count_);
+        const int first = chunk_first_[l], cnt = chunk_first_[l + 1] - first;
+        if (st == kSuccess) st = lane.Build(streams + first, cnt, params, dsts + first);
+        if (st == kSuccess) st = launch ? lane.LaunchAll(true, profiling_, upload_stream_) : lane.Upload(upload_stream_);
+        if (st != kSuccess) {
+            for (int k = 0; k < l; k++) lanes_[k].Sync();   // do not leave work in flight behind an error
+            return Fail(st, lane.last_error());
+        }
+    }
+    return kSuccess;
+}
+
+int Decoder::FinishAll() {
+    int status = kSuccess;
+    for (int l = 0; l < active_lanes_; l++) {
+        int st = lanes_[l].Finish(profiling_);
+        if (st != kSuccess && status == kSuccess) status = Fail(st, lanes_[l].last_error());
+    }
+    Aggregate();
+    return status;
+}
+
+void Decoder::Aggregate() {
+    stats_ = BatchStats();
+    stats_.lanes = active_lanes_;
+    for (int l = 0; l < active_lanes_; l++) {
+        const BatchStats& s = lanes_[l].stats();
+        for (int i = 0; i < kStageCount; i++) stats_.stage_ms[i] += s.stage_ms[i];
+        stats_.sync_rounds = std::max(stats_.sync_rounds, s.sync_rounds);
+        for (int r = 0; r < kMaxSyncRounds; r++) stats_.decodes_per_round[r] += s.decodes_per_round[r];
+        stats_.scan_bytes += s.scan_bytes;
+        stats_.blocks += s.blocks;
+        stats_.subsequences += s.subsequences;
+        stats_.plane_bytes += s.plane_bytes;
+        stats_.output_bytes += s.output_bytes;
+        stats_.h2d_bytes += s.h2d_bytes;
+        stats_.d2h_bytes += s.d2h_bytes;
+        stats_.kernel_launches += s.kernel_launches;
+        stats_.sub_bytes = std::max(stats_.sub_bytes, s.sub_bytes);
+        if (profiling_) {   // wall time on the device: first event of the first lane to the last event of any lane
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, lanes_[0].first_event(), lanes_[l].last_event()) == cudaSuccess)
+                stats_.total_ms = std::max(stats_.total_ms, ms);
+            (void)cudaGetLastError();
+        }
+    }
+}
+
 int Decoder::Decode(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
     std::lock_guard<std::mutex> lock(mutex_);
     if (!initialized_) return Fail(kNotInitialized, "decoder not initialised");
@@ -481,11 +607,9 @@ int Decoder::Decode(const StreamParser* const* streams, int n, const DecodeParam
     if (n == 0) return kSuccess;
     DeviceGuard guard(device_id_);
     prepared_ = false;
-    int st = BuildBatch(streams, n, params, dsts);
+    int st = BuildAll(streams, n, params, dsts, true);
     if (st != kSuccess) return st;
-    st = LaunchAll(true);
-    if (st != kSuccess) return st;
-    st = Finish();
+    st = FinishAll();
     prepared_ = (st == kSuccess);
     return st;
 }
@@ -496,11 +620,12 @@ int Decoder::Prepare(const StreamParser* const* streams, int n, const DecodePara
     if (!streams || !dsts || n <= 0) return kInvalidParameter;
     DeviceGuard guard(device_id_);
     prepared_ = false;
-    int st = BuildBatch(streams, n, params, dsts);
+    int st = BuildAll(streams, n, params, dsts, false);
     if (st != kSuccess) return st;
-    st = Upload();
-    if (st != kSuccess) return st;
-    RJB_CUDA(cudaStreamSynchronize(stream_));
+    for (int l = 0; l < active_lanes_; l++) {
+        st = lanes_[l].Sync();
+        if (st != kSuccess) return Fail(st, lanes_[l].last_error());
+    }
     prepared_ = true;
     return kSuccess;
 }
@@ -509,22 +634,41 @@ int Decoder::Run() {
     std::lock_guard<std::mutex> lock(mutex_);
     if (!initialized_ || !prepared_) return Fail(kNotInitialized, "no prepared batch");
     DeviceGuard guard(device_id_);
-    stats_.kernel_launches = 0;
-    int st = LaunchAll(false);
-    if (st != kSuccess) return st;
-    return Finish();
+    for (int l = 0; l < active_lanes_; l++) {
+        int st = lanes_[l].LaunchAll(false, profiling_, nullptr);
+        if (st != kSuccess) return Fail(st, lanes_[l].last_error());
+    }
+    return FinishAll();
 }
 
 int Decoder::CopyCoefficients(int image, int16_t* host_out, size_t count) {
     std::lock_guard<std::mutex> lock(mutex_);
-    if (!prepared_ || image < 0 || size_t(image) >= h_images_.size() || !host_out) return kInvalidParameter;
+    if (!prepared_ || image < 0 || image >= chunk_first_[active_lanes_] || !host_out) return kInvalidParameter;
     DeviceGuard guard(device_id_);
+    int l = 0;
+    while (image >= chunk_first_[l + 1]) l++;
+    return lanes_[l].CopyCoefficients(image - chunk_first_[l], host_out, count);
+}
+
+int Decoder::CopyPlanes(int image, uint8_t* host_out, size_t count) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!prepared_ || image < 0 || image >= chunk_first_[active_lanes_] || !host_out) return kInvalidParameter;
+    DeviceGuard guard(device_id_);
+    int l = 0;
+    while (image >= chunk_first_[l + 1]) l++;
+    return lanes_[l].CopyPlanes(image - chunk_first_[l], host_out, count);
+}
+
+int Lane::CopyCoefficients(int image, int16_t* host_out, size_t count) {
+    if (image < 0 || size_t(image) >= h_images_.size() || !host_out) return kInvalidParameter;
     const ImageDesc& im = h_images_[size_t(image)];
     size_t need = 0;
     for (int c = 0; c < im.ncomp; c++) need += size_t(im.blocks_w[c]) * im.blocks_h[c] * 64;
     if (count < need) return kInvalidParameter;
-    std::vector<int16_t> tmp(size_t(im.nblocks) * 64);
+    std::vector<int16_t> tmp(size_t(im.nblocks) * 64), dc(im.nblocks);
     RJB_CUDA(cudaMemcpy(tmp.data(), d_coef_.as<int16_t>() + size_t(im.blk0) * 64, tmp.size() * 2, cudaMemcpyDeviceToHost));
+    RJB_CUDA(cudaMemcpy(dc.data(), d_dcdiff_.as<int16_t>() + im.blk0, dc.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < dc.size(); b++) tmp[b * 64] = dc[b];   // DC lives in the compact per-block array
     size_t base = 0;
     for (int c = 0; c < im.ncomp; c++) {
         const int H = im.hs[c], V = im.vs[c];
@@ -539,10 +683,8 @@ int Decoder::CopyCoefficients(int image, int16_t* host_out, size_t count) {
     return kSuccess;
 }
 
-int Decoder::CopyPlanes(int image, uint8_t* host_out, size_t count) {
-    std::lock_guard<std::mutex> lock(mutex_);
-    if (!prepared_ || image < 0 || size_t(image) >= h_images_.size() || !host_out) return kInvalidParameter;
-    DeviceGuard guard(device_id_);
+int Lane::CopyPlanes(int image, uint8_t* host_out, size_t count) {
+    if (image < 0 || size_t(image) >= h_images_.size() || !host_out) return kInvalidParameter;
     const ImageDesc& im = h_images_[size_t(image)];
     size_t need = 0;
     for (int c = 0; c < im.ncomp; c++) need += size_t(im.blocks_w[c]) * im.blocks_h[c] * 64;

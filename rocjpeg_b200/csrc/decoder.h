@@ -52,7 +52,7 @@ class DeviceBuffer {
 
 enum StageId {
     kStageUpload = 0,   // descriptor block + entropy-coded bytes, host -> device
-    kStageClear,        // coefficient arena memset
+    kStageClear,        // counter reset (the coefficient arena is cleared only for damaged streams)
     kStageSync,         // all k1_sync rounds
     kStageWrite,        // k1_write
     kStageDc,           // dc_sums + dc_apply
@@ -75,7 +75,69 @@ struct BatchStats {
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
     uint32_t kernel_launches = 0;
     int sub_bytes = 0;
+    int lanes = 0;                      // pipeline lanes (chunks) the batch was split over
 };
+
+// One pipeline lane: a CUDA stream, its device arenas and the description of the
+// (sub-)batch it is decoding. A decode call splits its batch over up to kMaxLanes lanes so
+// that the upload of one chunk overlaps the kernels of another and the latency-bound tails
+// of the entropy stage overlap across chunks.
+class Lane {
+  public:
+    Lane() = default;
+    ~Lane();
+    Lane(const Lane&) = delete;
+    Lane& operator=(const Lane&) = delete;
+    int Create(int device_id, int sm_count);
+    int Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
+    int Upload(cudaStream_t upload_stream);   // nullptr: use the lane's own stream
+    int LaunchAll(bool include_upload, bool profiling, cudaStream_t upload_stream);
+    int Finish(bool profiling);
+    int Sync();
+    int CopyCoefficients(int image, int16_t* host_out, size_t count);
+    int CopyPlanes(int image, uint8_t* host_out, size_t count);
+    const BatchStats& stats() const { return stats_; }
+    const std::string& last_error() const { return err_; }
+    cudaEvent_t first_event() const { return ev_[0]; }
+    cudaEvent_t last_event() const { return ev_[kStageCount]; }
+    int num_images() const { return int(h_images_.size()); }
+
+  private:
+    struct Layout;   // byte layout of the descriptor block
+    int Fail(int status, const std::string& why);
+
+    bool created_ = false;
+    std::string err_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[kStageCount + 1] = {};
+    cudaEvent_t ev_uploaded_ = nullptr;
+    int sm_count_ = 0;
+
+    // host-side batch description
+    std::vector<ImageDesc> h_images_;
+    std::vector<OutputDesc> h_outputs_;
+    std::vector<SegmentDesc> h_segments_;
+    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_;
+    std::vector<GatherItem> h_gather_;
+    std::vector<const HuffLutSet*> h_lut_ptrs_;
+    std::vector<uint64_t> h_lut_hashes_;
+    std::vector<uint16_t> h_qtables_;
+    K1Args k1_ = {};
+    K2Args k2_ = {};
+    K3Args k3_ = {};
+    uint32_t gather_chunks_ = 0;
+    bool all_pinned_ = false, needs_clear_ = false;
+    size_t scan_bytes_ = 0, coef_blocks_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
+
+    StagingBuffer h_desc_;        // pinned descriptor block
+    size_t desc_bytes_ = 0;
+    StagingBuffer h_counters_;    // pinned read-back
+    DeviceBuffer d_desc_, d_scan_, d_coef_, d_dcdiff_, d_planes_, d_state_, d_used_, d_subseg_, d_cta_partial_,
+        d_dc_partial_, d_counters_;
+    BatchStats stats_;
+};
+
+constexpr int kMaxLanes = 4;
 
 class Decoder {
   public:
@@ -96,43 +158,21 @@ class Decoder {
     int device_id() const { return device_id_; }
 
   private:
-    struct Layout;   // byte layout of the descriptor block
     int Fail(int status, const std::string& why);
-    int BuildBatch(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
-    int Upload();
-    int LaunchAll(bool include_upload);
-    int Finish();
+    int Split(const StreamParser* const* streams, int n);
+    int BuildAll(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, bool launch);
+    int FinishAll();
+    void Aggregate();
 
     int backend_, device_id_;
     bool initialized_ = false, profiling_ = false, prepared_ = false;
     std::mutex mutex_;
     std::string err_;
-    cudaStream_t stream_ = nullptr;
-    cudaEvent_t ev_[kStageCount + 1] = {};
     int sm_count_ = 0;
-
-    // host-side batch description
-    std::vector<const StreamParser*> batch_;
-    std::vector<ImageDesc> h_images_;
-    std::vector<OutputDesc> h_outputs_;
-    std::vector<SegmentDesc> h_segments_;
-    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_;
-    std::vector<GatherItem> h_gather_;
-    std::vector<const HuffLutSet*> h_lut_ptrs_;
-    std::vector<uint64_t> h_lut_hashes_;
-    std::vector<uint16_t> h_qtables_;
-    K1Args k1_ = {};
-    K2Args k2_ = {};
-    K3Args k3_ = {};
-    uint32_t gather_chunks_ = 0;
-    bool all_pinned_ = false;
-    size_t scan_bytes_ = 0, coef_blocks_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
-
-    StagingBuffer h_desc_;        // pinned descriptor block
-    size_t desc_bytes_ = 0;
-    StagingBuffer h_counters_;    // pinned read-back
-    DeviceBuffer d_desc_, d_scan_, d_coef_, d_dcdiff_, d_planes_, d_state_, d_used_, d_subseg_, d_cta_partial_,
-        d_dc_partial_, d_counters_;
+    Lane lanes_[kMaxLanes];
+    cudaStream_t upload_stream_ = nullptr;   // all host->device traffic, serialised in lane order
+    int active_lanes_ = 0;
+    int chunk_first_[kMaxLanes + 1] = {};   // image range of each lane's chunk
     BatchStats stats_;
 };
 

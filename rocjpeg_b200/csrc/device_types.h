@@ -18,7 +18,8 @@ enum Css : int32_t { CSS_444 = 0, CSS_440 = 1, CSS_422 = 2, CSS_420 = 3, CSS_411
 enum Fmt : int32_t { FMT_NATIVE = 0, FMT_YUV_PLANAR = 1, FMT_Y = 2, FMT_RGB = 3, FMT_RGB_PLANAR = 4 };
 
 // One set of four Huffman tables (DC0, DC1, AC0, AC1), decoder form.
-//   fast[t][peek10] = (code_length << 8) | symbol, 0 when the code is longer than kFastBits
+//   fast[t][peek10] = packed symbol entry (huff_core.cuh: MakeEntry), 0 when the code is
+//   longer than kFastBits
 //   slow path (T.81 F.2.2.3 restated left-aligned): first l in (kFastBits,16] with
 //   peek16 < upper[t][l] has length l and symbol vals[t][(peek16 >> (16-l)) + valoff[t][l]]
 struct HuffLutSet {

@@ -54,73 +54,133 @@ RJB_HD uint32_t ByteSwap32(uint32_t w) {
 struct NullSink {
     RJB_HD void Dc(uint32_t, int) const {}
     RJB_HD void Ac(uint32_t, int, int) const {}
+    RJB_HD void EndBlock(uint32_t) const {}
 };
 
-// Decode symbols that START in [p, end_bit). Words come from `load(i)`: the i-th
-// little-endian 32-bit word counted from the subsequence's first byte (the
-// backing store is zero-padded at least 16 bytes past end_bit).
+// First-level table entry (HuffLutSet::fast) and the value SlowEntry() returns (16 bits):
+//   bits 0..4   code length + SSSS = bits the whole symbol consumes (1..31); entry 0 = not in the fast table
+//   bits 5..8   SSSS  number of magnitude bits that follow the code
+//   bits 9..15  how far the symbol advances the zig-zag index: 1 for a DC symbol, RRRR + 1 for
+//               an AC coefficient or ZRL (15 + 1), 64 for end-of-block (so "z += advance; z >= 64"
+//               is the only block-end test)
+RJB_HD uint32_t MakeEntry(uint32_t len, uint32_t sym, bool is_ac) {
+    const uint32_t s = sym & 15u;
+    const uint32_t adv = !is_ac ? 1u : (sym == 0 ? 64u : (sym >> 4) + 1u);
+    return (len + s) | (s << 5) | (adv << 9);
+}
+RJB_HD uint32_t EntryBits(uint32_t e) { return e & 31u; }
+RJB_HD uint32_t EntrySize(uint32_t e) { return (e >> 5) & 15u; }
+RJB_HD int EntryAdvance(uint32_t e) { return int(e >> 9); }
+
+// Codes longer than kFastBits (or invalid ones: 16 bits consumed, symbol 0 — T.81 leaves
+// this undefined; the oracle does the same).
+RJB_HD uint32_t SlowEntry(const HuffLutSet* lut, uint32_t tab, uint32_t v16) {
+    for (int l = kFastBits + 1; l <= 16; l++) {
+        if (v16 < lut->upper[tab][l])
+            return MakeEntry(uint32_t(l), lut->vals[tab][(int32_t(v16 >> (16 - l)) + lut->valoff[tab][l]) & 255], tab >= 2);
+    }
+    return MakeEntry(16, 0, tab >= 2);
+}
+
+RJB_HD uint32_t FunnelLeft(uint32_t hi, uint32_t lo, uint32_t k) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, k);
+#else
+    k &= 31u;
+    return k ? (hi << k) | (lo >> (32 - k)) : hi;
+#endif
+}
+
+// Which Huffman tables block c of the MCU uses, as two bit masks (bit c = table id 0/1), so a
+// block change costs ALU work only. Offsets index HuffLutSet::fast as one flat array.
+struct TableSel {
+    uint32_t dc_mask, ac_mask;
+};
+RJB_HD uint32_t DcOffset(TableSel t, int c) { return ((t.dc_mask >> c) & 1u) * uint32_t(kFastSize); }
+RJB_HD uint32_t AcOffset(TableSel t, int c) { return (2u + ((t.ac_mask >> c) & 1u)) * uint32_t(kFastSize); }
+RJB_HD TableSel MakeTableSel(const uint8_t* mcu_dc, const uint8_t* mcu_ac, int bpm) {
+    TableSel t{0u, 0u};
+    for (int c = 0; c < bpm; c++) {
+        t.dc_mask |= uint32_t(mcu_dc[c] & 1u) << c;
+        t.ac_mask |= uint32_t(mcu_ac[c] & 1u) << c;   // slots 2/3 -> bit 0
+    }
+    return t;
+}
+
+// Three-word window over the big-endian stream: w0/w1 hold the bits being decoded, w2 is
+// fetched one word ahead so the load never sits on the symbol-to-symbol dependency chain.
+struct BitWindow {
+    uint32_t w0, w1, w2, wi;
+    template <class Loader>
+    RJB_HD void Init(const Loader& load, uint32_t p) {
+        wi = p >> 5;
+        w0 = load(wi);
+        w1 = load(wi + 1);
+        w2 = load(wi + 2);
+    }
+    RJB_HD uint32_t Peek(uint32_t p) const { return FunnelLeft(w0, w1, p); }   // next 32 bits (shift taken mod 32)
+    template <class Loader>
+    RJB_HD void Advance(const Loader& load, uint32_t p_new) {   // a symbol is at most 31 bits: one word at most
+        if ((p_new >> 5) != wi) {
+            wi++;
+            w0 = w1;
+            w1 = w2;
+            w2 = load(wi + 2);
+        }
+    }
+};
+
+RJB_HD uint32_t LookupSymbol(const HuffLutSet* lut, uint32_t tab_off, uint32_t win) {
+    const uint16_t* fast = &lut->fast[0][0];
+    uint32_t e = fast[tab_off + (win >> (32 - kFastBits))];
+    if (e == 0) e = SlowEntry(lut, tab_off >> kFastBits, win >> 16);
+    return e;
+}
+
+// RECEIVE + EXTEND (T.81 F.2.2.1) for an entry `e` whose symbol starts at the top of `win`.
+RJB_HD int SymbolValue(uint32_t e, uint32_t win) {
+    const uint32_t s = EntrySize(e), tot = EntryBits(e);
+    if (s == 0) return 0;
+    const uint32_t extra = (win << (tot - s)) >> (32 - s);
+    return (extra < (1u << (s - 1))) ? int(extra) - int((1u << s) - 1u) : int(extra);
+}
+
+// Decode symbols that START in [p, end_bit). `load(i)` returns the i-th 32-bit word of the
+// subsequence in BIG-endian order (bit 31 = first bit of the stream); the backing store is
+// zero-padded at least 16 bytes past end_bit.
 //   WRITE = false: only the state is tracked (speculation / synchronisation).
-//   WRITE = true : coefficients go to `sink`; stops early at blk_limit.
+//   WRITE = true : coefficients go to `sink` (Dc / Ac per symbol, EndBlock when a block
+//                  completes); stops early at blk_limit. (The CUDA write pass uses its own
+//                  warp-synchronous loop over the same primitives; this form serves the host model.)
 // On return p >= end_bit (or the block limit was reached); c, z, nb, blk updated.
 template <bool WRITE, class Loader, class Sink>
-RJB_HD void DecodeSpan(const Loader& load, const HuffLutSet* lut, const uint8_t* mcu_dc, const uint8_t* mcu_ac, int bpm,
-                       uint32_t& p, uint32_t end_bit, int& c, int& z, uint32_t& nb, uint32_t& blk, uint32_t blk_limit,
-                       Sink& sink) {
+RJB_HD void DecodeSpan(const Loader& load, const HuffLutSet* lut, TableSel sel, int bpm, uint32_t& p, uint32_t end_bit, int& c,
+                       int& z, uint32_t& nb, uint32_t& blk, uint32_t blk_limit, Sink& sink) {
     if (p >= end_bit) return;
-    uint32_t wi = p >> 5;
-    uint64_t bb = uint64_t(ByteSwap32(load(wi))) << (32 + (p & 31u));
-    int bc = 32 - int(p & 31u);
-    wi++;
+    BitWindow bw;
+    bw.Init(load, p);
+    uint32_t dc_off = DcOffset(sel, c), ac_off = AcOffset(sel, c);
     while (p < end_bit) {
         if (WRITE && blk >= blk_limit) break;
-        if (bc <= 32) {
-            bb |= uint64_t(ByteSwap32(load(wi))) << (32 - bc);
-            bc += 32;
-            wi++;
+        const uint32_t win = bw.Peek(p);
+        const uint32_t e = LookupSymbol(lut, (z == 0) ? dc_off : ac_off, win);
+        const int adv = EntryAdvance(e);
+        if (WRITE) {
+            const int val = SymbolValue(e, win);
+            if (z == 0) sink.Dc(blk, val);
+            else if (EntrySize(e) && z + adv <= 64) sink.Ac(blk, z + adv - 1, val);
         }
-        const int tab = (z == 0) ? mcu_dc[c] : mcu_ac[c];
-        const uint32_t v16 = uint32_t(bb >> 48);
-        uint32_t e = lut->fast[tab][v16 >> (16 - kFastBits)];
-        uint32_t len = e >> 8, sym = e & 0xFFu;
-        if (len == 0) {   // code longer than the first-level table (or invalid)
-            len = 16;
-            sym = 0;
-            for (int l = kFastBits + 1; l <= 16; l++) {
-                if (v16 < lut->upper[tab][l]) {
-                    len = uint32_t(l);
-                    sym = lut->vals[tab][(int32_t(v16 >> (16 - l)) + lut->valoff[tab][l]) & 255];
-                    break;
-                }
-            }
-        }
-        bb <<= len;
-        const uint32_t s = sym & 15u;
-        int val = 0;
-        if (s) {   // RECEIVE + EXTEND (T.81 F.2.2.1)
-            const uint32_t extra = uint32_t(bb >> (64 - s));
-            bb <<= s;
-            val = (extra < (1u << (s - 1))) ? int(extra) - int((1u << s) - 1u) : int(extra);
-        }
-        bc -= int(len + s);
-        p += len + s;
-        if (z == 0) {
-            if (WRITE) sink.Dc(blk, val);
-            z = 1;
-        } else {
-            const uint32_t r = sym >> 4;
-            if (s == 0) {
-                z = (r == 15) ? z + 16 : 64;   // ZRL / EOB
-            } else {
-                z += int(r);
-                if (WRITE && z < 64) sink.Ac(blk, z, val);
-                z++;
-            }
-        }
+        z += adv;                                              // EOB advances by 64, ZRL by 16
+        p += EntryBits(e);
+        bw.Advance(load, p);
         if (z >= 64) {
+            if (WRITE) sink.EndBlock(blk);
             z = 0;
             nb++;
             blk++;
             c = (c + 1 == bpm) ? 0 : c + 1;
+            dc_off = DcOffset(sel, c);
+            ac_off = AcOffset(sel, c);
         }
     }
 }

@@ -1,6 +1,7 @@
 // jpeg_parser.cpp — see jpeg_parser.h. Accept/reject rules follow
 // src/rocjpeg_parser.cpp of the reference (line numbers cited inline).
 #include "jpeg_parser.h"
+#include "huff_core.cuh"
 
 #include <cuda_runtime_api.h>
 
@@ -88,13 +89,14 @@ void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out) {
     uint16_t* fast = out->fast[slot];
     std::memset(fast, 0, sizeof(uint16_t) * kFastSize);
     std::memcpy(out->vals[slot], spec.vals, 256);
+    const bool is_ac = slot >= 2;
     uint32_t code = 0, k = 0;
     for (int l = 1; l <= 16; l++) {
         out->valoff[slot][l] = int32_t(k) - int32_t(code);
         for (uint32_t i = 0; i < spec.bits[l - 1]; i++, code++, k++) {
             if (l <= kFastBits && code < (1u << l) && k < 256) {
-                uint32_t first = code << (kFastBits - l);
-                uint16_t entry = uint16_t((l << 8) | spec.vals[k]);
+                const uint32_t first = code << (kFastBits - l);
+                const uint16_t entry = uint16_t(MakeEntry(uint32_t(l), spec.vals[k], is_ac));
                 for (uint32_t j = 0; j < (1u << (kFastBits - l)); j++) fast[first + j] = entry;
             }
         }
@@ -306,15 +308,14 @@ void StreamParser::BuildDecodeTables() {
     }
     for (int t = 0; t < 4; t++)
         for (int k = 0; k < 64; k++) p_.qt_natural[t][kZigzag[k]] = p_.qt[t][k];
-    std::memset(&p_.lut, 0, sizeof(p_.lut));
+    // Identity of the four Huffman tables. Streams parsed through the same handle very often
+    // repeat the previous tables (the standard ones): the decoder-form LUTs are then kept.
     uint64_t h = 1469598103934665603ull;
     auto mix = [&](const void* ptr, size_t n) {
         const uint8_t* b = static_cast<const uint8_t*>(ptr);
         for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
     };
     for (int t = 0; t < 2; t++) {
-        if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &p_.lut);
-        if (p_.ac[t].present) BuildHuffLut(p_.ac[t], 2 + t, &p_.lut);
         uint8_t present[2] = {uint8_t(p_.dc[t].present), uint8_t(p_.ac[t].present)};
         mix(present, 2);
         mix(p_.dc[t].bits, 16);
@@ -323,6 +324,19 @@ void StreamParser::BuildDecodeTables() {
         mix(p_.ac[t].vals, p_.ac[t].count);
     }
     p_.lut_hash = h;
+    const bool same = lut_valid_ && h == lut_spec_hash_ && std::memcmp(lut_spec_dc_, p_.dc, sizeof(p_.dc)) == 0 &&
+                      std::memcmp(lut_spec_ac_, p_.ac, sizeof(p_.ac)) == 0;
+    if (!same) {
+        std::memset(&lut_, 0, sizeof(lut_));
+        for (int t = 0; t < 2; t++) {
+            if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &lut_);
+            if (p_.ac[t].present) BuildHuffLut(p_.ac[t], 2 + t, &lut_);
+        }
+        std::memcpy(lut_spec_dc_, p_.dc, sizeof(p_.dc));
+        std::memcpy(lut_spec_ac_, p_.ac, sizeof(p_.ac));
+        lut_spec_hash_ = h;
+        lut_valid_ = true;
+    }
 }
 
 bool StreamParser::Parse(const uint8_t* d, size_t len) {

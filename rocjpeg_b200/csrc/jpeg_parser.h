@@ -79,8 +79,7 @@ struct ParsedJpeg {
     // decode-side products
     int32_t support_status = 0;                   // RocJpegStatus value: 0 when the CUDA path can decode it
     uint16_t qt_natural[4][64] = {};              // de-zig-zagged quantiser steps
-    HuffLutSet lut;                               // valid when support_status == 0
-    uint64_t lut_hash = 0;                        // identity of the four tables (batch de-duplication)
+    uint64_t lut_hash = 0;                        // identity of the four Huffman tables (batch de-duplication)
     std::vector<Segment> segments;                // one per restart interval (exactly ceil(mcus / Ri))
     size_t clean_bytes = 0;                       // bytes used in `clean`
     uint32_t restart_markers_seen = 0;
@@ -92,6 +91,7 @@ class StreamParser {
     bool Parse(const uint8_t* data, size_t length);
     const ParsedJpeg& parsed() const { return p_; }
     const StagingBuffer& clean() const { return clean_; }
+    const HuffLutSet& lut() const { return lut_; }   // decoder-form tables of the last parsed stream
     const std::string& last_error() const { return err_; }
 
   private:
@@ -106,6 +106,10 @@ class StreamParser {
 
     std::mutex mutex_;
     ParsedJpeg p_;
+    HuffLutSet lut_ = {};             // kept across parses while the DHT content does not change
+    HuffSpec lut_spec_dc_[2] = {}, lut_spec_ac_[2] = {};
+    uint64_t lut_spec_hash_ = 0;
+    bool lut_valid_ = false;
     StagingBuffer clean_;
     std::string err_;
 };

@@ -27,10 +27,12 @@
 //                     (correctness never depends on the stream synchronising).
 //   k1_write          block positions = segmented prefix sums of the per-thread
 //                     block counts (CTA scan + look-back over CTA partials), then
-//                     the final decode writes int16 coefficients (natural order)
-//                     and one DC difference per block.
+//                     the final decode assembles each block in shared memory and
+//                     stores it as one whole 128-byte line of int16 coefficients
+//                     (natural order), plus one DC difference per block.
 //   dc_sums/dc_apply  per-component, per-restart-interval prefix sum of the DC
-//                     differences; absolute DC stored into coefficient 0.
+//                     differences; the absolute DC replaces the difference in the
+//                     compact per-block DC array that K2 reads.
 #include <cuda_runtime.h>
 
 #include "huff_core.cuh"
@@ -62,19 +64,18 @@ struct SmemLoader {
     const uint32_t* base;
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return base[i]; }
 };
-struct GlobalLoader {
-    const uint32_t* base;
-    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(base + i); }
-};
-
-struct CoefSink {
-    int16_t* coef;     // image base: coef + blk0 * 64
-    int16_t* dcdiff;   // image base
-    __device__ __forceinline__ void Dc(uint32_t blk, int v) const { dcdiff[blk] = int16_t(v); }
-    __device__ __forceinline__ void Ac(uint32_t blk, int z, int v) const {
-        coef[size_t(blk) * 64 + c_zigzag[z]] = int16_t(v);
+// Write pass: words of the thread's own slot come from shared memory; past it (finishing an
+// owned block beyond the subsequence) they come straight from the scan arena.
+struct SlotOrGlobalLoader {
+    const uint32_t* slot;
+    const uint32_t* gbase;
+    uint32_t slot_words;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        return i < slot_words ? slot[i] : ByteSwap32(__ldg(gbase + i));
     }
 };
+
+constexpr int kBlkBufBytes = 144;   // 128 B block + 16: 16-byte aligned rows, quarter-warps conflict-free
 
 // Per-thread description of its subsequence.
 struct Sub {
@@ -132,7 +133,14 @@ struct K1Smem {
     uint64_t start[T];
     uint32_t state[T];
     uint8_t mcu_dc[16], mcu_ac[16];
+    uint8_t zigzag[64];
     uint32_t scratch[40];
+};
+
+template <int S>
+struct K1WriteSmem {
+    K1Smem<S> k;
+    __align__(16) unsigned char blkbuf[T * kBlkBufBytes];
 };
 
 template <int S>
@@ -149,6 +157,7 @@ __device__ __forceinline__ void StageCta(K1Smem<S>& sm, const K1Args& a, const I
         sm.mcu_dc[tid] = tid < kMaxBlocksPerMcu ? im.mcu_dc[tid] : 0;
         sm.mcu_ac[tid] = tid < kMaxBlocksPerMcu ? im.mcu_ac[tid] : 2;
     }
+    if (tid < 64) sm.zigzag[tid] = c_zigzag[tid];
     __syncthreads();
     constexpr int V = K1Smem<S>::kSlotVecs;
     for (int idx = tid; idx < T * V; idx += T) {
@@ -157,7 +166,8 @@ __device__ __forceinline__ void StageCta(K1Smem<S>& sm, const K1Args& a, const I
         if (st == ~0ull) continue;
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.scan + st) + v);
         uint32_t* w = sm.words + slot * K1Smem<S>::kSlotStride + v * 4;
-        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+        // stored big-endian: bit 31 of a word is the first bit of the stream (huff_core.cuh)
+        w[0] = ByteSwap32(q.x); w[1] = ByteSwap32(q.y); w[2] = ByteSwap32(q.z); w[3] = ByteSwap32(q.w);
     }
     __syncthreads();
 }
@@ -191,10 +201,12 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     const SmemLoader loader{sm.words + tid * K1Smem<S>::kSlotStride};
     NullSink sink;
 
+    const TableSel sel = MakeTableSel(sm.mcu_dc, sm.mcu_ac, im.bpm);
+    const int bpm = im.bpm;
     auto decode_from = [&](uint32_t key) {
         uint32_t p = StateOverflow(key), nb = 0, blk = 0;
         int c = StateC(key), z = StateZ(key);
-        DecodeSpan<false>(loader, &sm.lut, sm.mcu_dc, sm.mcu_ac, im.bpm, p, me.end_bit, c, z, nb, blk, 0xFFFFFFFFu, sink);
+        DecodeSpan<false>(loader, &sm.lut, sel, bpm, p, me.end_bit, c, z, nb, blk, 0xFFFFFFFFu, sink);
         const uint32_t over = p > me.end_bit ? p - me.end_bit : 0;
         return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
     };
@@ -250,13 +262,19 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
 template <int S>
 __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw);
+    K1WriteSmem<S>& wsm = *reinterpret_cast<K1WriteSmem<S>*>(smem_raw);
+    K1Smem<S>& sm = wsm.k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t cta = blockIdx.x;
     const uint32_t img = UpperIndex(a.img_cta0, uint32_t(a.nimages), cta);
     const ImageDesc& im = a.images[img];
     const uint32_t g = cta * T + tid;
     const Sub me = Locate<S>(a, im, g, true);
+    {   // zero this thread's block buffer (only ever touched by its owner)
+        uint4* zb = reinterpret_cast<uint4*>(wsm.blkbuf + tid * kBlkBufBytes);
+#pragma unroll
+        for (int i = 0; i < kBlkBufBytes / 16; i++) zb[i] = make_uint4(0, 0, 0, 0);
+    }
     StageCta<S>(sm, a, im, me);
 
     const uint32_t st = me.active ? a.state[g] : 0;
@@ -310,17 +328,96 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const uint32_t incl = v + add;
     const uint32_t excl = (me.active && me.first) ? 0u : incl - nb;
 
-    if (!me.active) return;
-    const SegmentDesc sd = a.segments[me.seg];
+    // ---- final decode. Every block is assembled in this thread's shared-memory buffer and
+    // leaves as eight 128-bit stores (whole 128-byte lines: the coefficient arena needs no
+    // clearing and sees no partial-sector read-modify-write). A block belongs to the thread that
+    // decodes its DC symbol: that thread keeps decoding past the end of its subsequence until the
+    // block is complete; a thread that starts inside a block stays silent (`live` false) until
+    // the first block boundary. The warp runs "decode to the next block end" / "flush" in
+    // lock-step so the 24-instruction flush is not replayed for every divergent lane.
+    SegmentDesc sd = {};
+    if (me.active) sd = a.segments[me.seg];
     uint32_t key = 0;
-    if (!me.first) key = StateKey(a.state[g - 1]);
-    uint32_t p = StateOverflow(key), cnt = 0;
+    if (me.active && !me.first) key = StateKey(a.state[g - 1]);
+    uint32_t p = StateOverflow(key);
     int c = StateC(key), z = StateZ(key);
     uint32_t blk = sd.blk_first + excl;
     const uint32_t limit = sd.blk_first + sd.blk_count;
-    CoefSink sink{a.coef + size_t(im.blk0) * 64, a.dcdiff + im.blk0};
-    const SmemLoader loader{sm.words + tid * K1Smem<S>::kSlotStride};
-    DecodeSpan<true>(loader, &sm.lut, sm.mcu_dc, sm.mcu_ac, im.bpm, p, me.end_bit, c, z, cnt, blk, limit, sink);
+    const uint32_t seg_end_bit = me.active ? (sd.nbytes - uint32_t(me.start - sd.data_off)) * 8u : 0u;
+    int16_t* coef = a.coef + size_t(im.blk0) * 64;
+    int16_t* dcdiff = a.dcdiff + im.blk0;
+    int16_t* buf = reinterpret_cast<int16_t*>(wsm.blkbuf + tid * kBlkBufBytes);
+    const TableSel sel = MakeTableSel(sm.mcu_dc, sm.mcu_ac, im.bpm);
+    const int bpm = im.bpm;
+    const SlotOrGlobalLoader loader{sm.words + tid * K1Smem<S>::kSlotStride,
+                                    reinterpret_cast<const uint32_t*>(a.scan + (me.active ? me.start : 0)),
+                                    uint32_t(K1Smem<S>::kSlotWords)};
+    auto flush = [&](uint32_t b) {
+        uint4* src = reinterpret_cast<uint4*>(buf);
+        uint4* dst = reinterpret_cast<uint4*>(coef + size_t(b) * 64);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            dst[i] = src[i];
+            src[i] = make_uint4(0, 0, 0, 0);
+        }
+    };
+    bool live = (z == 0);
+    bool finishing = false;                 // past the subsequence, completing an owned block
+    uint32_t stop = me.end_bit;
+    bool done = !me.active || p >= stop || blk >= limit;
+    BitWindow bw;
+    bw.Init(loader, done ? 0u : p);
+    uint32_t dc_off = DcOffset(sel, c), ac_off = AcOffset(sel, c);
+    for (;;) {
+        bool ended = false;
+        while (!done && !ended) {
+            const uint32_t win = bw.Peek(p);
+            const uint32_t e = LookupSymbol(&sm.lut, (z == 0) ? dc_off : ac_off, win);
+            const int adv = EntryAdvance(e);
+            if (live) {
+                const int val = SymbolValue(e, win);
+                if (z == 0) dcdiff[blk] = int16_t(val);
+                else if (EntrySize(e) && z + adv <= 64) buf[sm.zigzag[z + adv - 1]] = int16_t(val);
+            }
+            z += adv;
+            p += EntryBits(e);
+            bw.Advance(loader, p);
+            if (z >= 64) {
+                ended = true;
+            } else if (p >= stop) {
+                if (!finishing && live && p < seg_end_bit) {
+                    finishing = true;       // own the unfinished block: follow it into the next subsequence(s)
+                    stop = seg_end_bit;
+                } else {
+                    done = true;
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, ended)) break;
+        if (ended) {
+            if (live) flush(blk);
+            live = true;
+            z = 0;
+            blk++;
+            c = (c + 1 == bpm) ? 0 : c + 1;
+            dc_off = DcOffset(sel, c);
+            ac_off = AcOffset(sel, c);
+            if (finishing || p >= stop || blk >= limit) done = true;
+        }
+    }
+    // Damaged / truncated data only: when the interval's data ends under this thread's hands,
+    // what the interval still owes is written as zero blocks (the arena is never cleared, so
+    // every block must be stored by someone).
+    if (me.active && live && (me.last || p >= seg_end_bit) && blk < limit) {
+        if (z != 0) {
+            flush(blk);
+            blk++;
+        }
+        for (; blk < limit; blk++) {
+            flush(blk);
+            dcdiff[blk] = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- DC prediction
@@ -442,44 +539,55 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
     // exclusive prefix = predictor values entering this MCU
     int pred[3] = {v0 + a0 - s[0], v1 + a1 - s[1], v2 + a2 - s[2]};
     if (reset_here) pred[0] = pred[1] = pred[2] = 0;
-    int16_t* out = a.coef + (size_t(im.blk0) + size_t(m) * im.bpm) * 64;
+    // absolute DC replaces the difference in the compact per-block array (K2 reads it from
+    // there: one coalesced 2-byte load per block instead of a scattered store per block here)
+    int16_t* out = a.dcdiff + im.blk0 + m * im.bpm;
     for (int k = 0; k < im.bpm; k++) {
         const int comp = im.mcu_comp[k];
         pred[comp] += diffs[k];
-        out[size_t(k) * 64] = int16_t(pred[comp]);
+        out[k] = int16_t(pred[comp]);
     }
 }
 
 // ---------------------------------------------------------------- gather
 
 constexpr int kGatherChunk = 16384;
+constexpr int kGatherCtas = 64;   // PCIe-bound: a few CTAs saturate the link; the rest of the GPU stays free
+                                  // for the kernels of the other pipeline lanes
 
-__global__ void __launch_bounds__(256) gather_scans(const GatherItem* items, int nitems, uint8_t* arena) {
+__global__ void __launch_bounds__(256) gather_scans(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena) {
     __shared__ int s_item;
-    if (threadIdx.x == 0) {
-        int lo = 0, hi = nitems;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (items[mid].chunk0 <= blockIdx.x) lo = mid; else hi = mid;
+    for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int lo = 0, hi = nitems;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (items[mid].chunk0 <= chunk) lo = mid; else hi = mid;
+            }
+            s_item = lo;
         }
-        s_item = lo;
+        __syncthreads();
+        const GatherItem it = items[s_item];
+        const uint32_t off = (chunk - it.chunk0) * kGatherChunk;
+        const uint32_t n = min(uint32_t(kGatherChunk), it.nbytes - off);
+        const uint4* src = reinterpret_cast<const uint4*>(it.src + off);
+        uint4* dst = reinterpret_cast<uint4*>(arena + it.dst_off + off);
+        for (uint32_t i = threadIdx.x; i < n / 16; i += blockDim.x) dst[i] = src[i];
     }
-    __syncthreads();
-    const GatherItem it = items[s_item];
-    const uint32_t off = (blockIdx.x - it.chunk0) * kGatherChunk;
-    const uint32_t n = min(uint32_t(kGatherChunk), it.nbytes - off);
-    const uint4* src = reinterpret_cast<const uint4*>(it.src + off);
-    uint4* dst = reinterpret_cast<uint4*>(arena + it.dst_off + off);
-    for (uint32_t i = threadIdx.x; i < n / 16; i += blockDim.x) dst[i] = src[i];
 }
 
 template <int S>
 cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream) {
-    // dynamic shared memory: stays below the 48 KiB default for every S, no opt-in needed
-    const size_t smem = sizeof(K1Smem<S>);
-    static_assert(sizeof(K1Smem<S>) <= 48 * 1024, "K1 shared memory exceeds the default limit");
-    if (round >= 0) k1_sync<S><<<a.total_ctas, T, smem, stream>>>(a, round);
-    else k1_write<S><<<a.total_ctas, T, smem, stream>>>(a);
+    if (round >= 0) {
+        static_assert(sizeof(K1Smem<S>) <= 48 * 1024, "k1_sync shared memory exceeds the default limit");
+        k1_sync<S><<<a.total_ctas, T, sizeof(K1Smem<S>), stream>>>(a, round);
+    } else {
+        // above the 48 KiB default for S = 128: opt in (per device; cheap, so done on every launch)
+        cudaError_t e = cudaFuncSetAttribute(k1_write<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(K1WriteSmem<S>)));
+        if (e != cudaSuccess) return e;
+        k1_write<S><<<a.total_ctas, T, sizeof(K1WriteSmem<S>), stream>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -514,7 +622,7 @@ cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream) {
 
 cudaError_t LaunchGather(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena, cudaStream_t stream) {
     if (total_chunks == 0) return cudaSuccess;
-    gather_scans<<<total_chunks, 256, 0, stream>>>(items, nitems, arena);
+    gather_scans<<<min(total_chunks, uint32_t(kGatherCtas)), 256, 0, stream>>>(items, nitems, total_chunks, arena);
     return cudaGetLastError();
 }
 

@@ -36,7 +36,8 @@ namespace {
 constexpr int kTileW = 256;   // luma samples per tile row (8 per lane)
 constexpr int kTileH = 8;     // rows per tile (one per warp)
 constexpr int kThreads = 256;
-constexpr int kRowBuf = 3 * kTileW + 32;
+constexpr int kChanBuf = kTileW + 32;      // one planar channel row + alignment phase
+constexpr int kRowBuf = 3 * kChanBuf;      // >= 3 * kTileW + 32 (packed RGB row)
 
 __device__ __forceinline__ uint32_t UpperIndexK3(const uint32_t* a, uint32_t n, uint32_t v) {
     uint32_t lo = 0, hi = n;
@@ -47,39 +48,39 @@ __device__ __forceinline__ uint32_t UpperIndexK3(const uint32_t* a, uint32_t n, 
     return lo;
 }
 
+// hipPack convention: saturating round-to-nearest-even float -> u8 (one F2I on sm_100a).
 __device__ __forceinline__ uint32_t PackU8(float f) {
-    return uint32_t(min(max(__float2int_rn(f), 0), 255));   // cvt.rni + saturate
+    uint32_t r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(f));
+    return r;
 }
+__device__ __forceinline__ uint32_t Pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+}
+__device__ __forceinline__ float ByteF(uint32_t w, int i) { return float((w >> (8 * i)) & 0xFFu); }
 
 // Write `n` bytes staged at buf[phase .. phase+n) to dst (dst & 15 == phase).
 __device__ __forceinline__ void FlushRow(const uint8_t* buf, int phase, uint8_t* dst, int n, int lane) {
-    __syncwarp();
     int head = (16 - phase) & 15;
     if (head > n) head = n;
-    for (int i = lane; i < head; i += 32) dst[i] = buf[phase + i];
+    if (lane < head) dst[lane] = buf[phase + lane];
     const int nvec = (n - head) >> 4;
     const uint4* s = reinterpret_cast<const uint4*>(buf + phase + head);
     uint4* d = reinterpret_cast<uint4*>(dst + head);
     for (int v = lane; v < nvec; v += 32) d[v] = s[v];
     const int done = head + (nvec << 4);
-    for (int i = done + lane; i < n; i += 32) dst[i] = buf[phase + i];
-    __syncwarp();
+    if (done + lane < n) dst[done + lane] = buf[phase + done + lane];
 }
 
-// Load 8 consecutive samples of a plane row starting at column x (any alignment).
-__device__ __forceinline__ void Load8(const uint8_t* row, int x, uint32_t (&v)[8]) {
+// Load 8 consecutive samples of a plane row starting at column x (any alignment) as two
+// little-endian words.
+__device__ __forceinline__ uint2 Load8(const uint8_t* row, int x) {
     const uint8_t* p = row + x;
-    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
-        const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) return __ldg(reinterpret_cast<const uint2*>(p));
+    uint32_t b[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            v[i] = (q.x >> (8 * i)) & 0xFFu;
-            v[i + 4] = (q.y >> (8 * i)) & 0xFFu;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __ldg(p + i);
-    }
+    for (int i = 0; i < 8; i++) b[i] = __ldg(p + i);
+    return make_uint2(Pack4(b[0], b[1], b[2], b[3]), Pack4(b[4], b[5], b[6], b[7]));
 }
 
 struct Planes {
@@ -87,18 +88,30 @@ struct Planes {
     uint32_t pitch[3];
 };
 
+// Stage `n` bytes produced 8 per lane (two words) at buf[phase + 8*lane ..): word stores when
+// the phase allows, byte stores otherwise and in the ragged last lane.
+__device__ __forceinline__ void Stage8(uint8_t* buf, int phase, int lane, int n, uint2 v) {
+    const int i0 = lane * 8;
+    if (i0 >= n) return;
+    uint8_t* o = buf + phase + i0;
+    if ((phase & 3) == 0 && i0 + 8 <= n) {
+        *reinterpret_cast<uint32_t*>(o) = v.x;
+        *reinterpret_cast<uint32_t*>(o + 4) = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i0 + i < n) o[i] = uint8_t(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 0xFFu);
+    }
+}
+
 // Copy `n` bytes of one plane row (columns x .. x+n) into the caller's row.
 __device__ __forceinline__ void CopyRow(uint8_t* buf, const uint8_t* src_row, int x, uint8_t* dst, int n, int lane) {
     const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
-    const int i0 = lane * 8;
-    if (i0 < n) {
-        uint32_t v[8];
-        Load8(src_row, x + i0, v);   // planes are MCU-padded: reading up to 7 samples past n stays inside the row
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (i0 + i < n) buf[phase + i0 + i] = uint8_t(v[i]);
-    }
+    // planes are MCU-padded (and the arena has slack): reading up to 7 samples past n is in bounds
+    if (lane * 8 < n) Stage8(buf, phase, lane, n, Load8(src_row, x + lane * 8));
+    __syncwarp();
     FlushRow(buf, phase, dst, n, lane);
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
@@ -133,37 +146,57 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
         if (fmt == FMT_RGB_PLANAR && (!od.dst[0] || !od.dst[1] || !od.dst[2] || od.dst_pitch[0] == 0)) return;
         const int Y = y0 + y;
         const int X = x0 + xt + lane * 8;    // first luma column of this lane
-        uint32_t r[8], g[8], b[8];
         const bool have = lane * 8 < nx;
+        uint2 R = make_uint2(0, 0), G = R, B = R;   // 8 packed bytes per channel
         if (have) {
-            uint32_t yy[8];
-            Load8(pl.p[0] + size_t(Y) * pl.pitch[0], X, yy);
+            const uint2 yy = Load8(pl.p[0] + size_t(Y) * pl.pitch[0], X);
             if (gray) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) r[i] = g[i] = b[i] = yy[i];
+                R = G = B = yy;   // hip_kernels.cpp:1915-1927
             } else {
                 const uint8_t* urow = pl.p[1] + size_t(Y >> sy) * pl.pitch[1];
                 const uint8_t* vrow = pl.p[2] + size_t(Y >> sy) * pl.pitch[2];
-                uint32_t uu[8], vv[8];
+                // chroma bytes per luma pixel (nearest neighbour): `pair` = the 4 bytes of uu.x/vv.x
+                // each serve two pixels (aligned 4:2:x fast path), otherwise one byte per pixel.
+                uint2 uu, vv;
+                const bool pair = (sx == 1) && ((X & 7) == 0);
                 if (sx == 0) {
-                    Load8(urow, X, uu);
-                    Load8(vrow, X, vv);
+                    uu = Load8(urow, X);
+                    vv = Load8(vrow, X);
+                } else if (pair) {
+                    uu = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(urow + (X >> 1))), 0);
+                    vv = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(vrow + (X >> 1))), 0);
                 } else {
-                    // nearest neighbour: luma column X+i uses chroma column (X+i)>>1
-                    const int cx = X >> 1;
+                    uint32_t ub[8], vb[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        const int k = ((X + i) >> 1) - cx;   // 0..4
-                        uu[i] = __ldg(urow + cx + k);
-                        vv[i] = __ldg(vrow + cx + k);
+                        ub[i] = __ldg(urow + ((X + i) >> 1));
+                        vb[i] = __ldg(vrow + ((X + i) >> 1));
                     }
+                    uu = make_uint2(Pack4(ub[0], ub[1], ub[2], ub[3]), Pack4(ub[4], ub[5], ub[6], ub[7]));
+                    vv = make_uint2(Pack4(vb[0], vb[1], vb[2], vb[3]), Pack4(vb[4], vb[5], vb[6], vb[7]));
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float fy = float(yy[i]), fu = float(uu[i]) - 128.0f, fv = float(vv[i]) - 128.0f;
-                    r[i] = PackU8(fmaf(1.5748f, fv, fy));
-                    g[i] = PackU8(fmaf(-0.4681f, fv, fmaf(-0.1873f, fu, fy)));
-                    b[i] = PackU8(fmaf(1.8556f, fu, fy));
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t yw = h ? yy.y : yy.x;
+                    uint32_t r[4], g[4], b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float fy = ByteF(yw, i);
+                        float fu, fv;
+                        if (pair) {
+                            fu = ByteF(uu.x, 2 * h + (i >> 1)) - 128.0f;
+                            fv = ByteF(vv.x, 2 * h + (i >> 1)) - 128.0f;
+                        } else {
+                            fu = ByteF(h ? uu.y : uu.x, i) - 128.0f;
+                            fv = ByteF(h ? vv.y : vv.x, i) - 128.0f;
+                        }
+                        r[i] = PackU8(fmaf(1.5748f, fv, fy));
+                        g[i] = PackU8(fmaf(-0.4681f, fv, fmaf(-0.1873f, fu, fy)));
+                        b[i] = PackU8(fmaf(1.8556f, fu, fy));
+                    }
+                    const uint32_t rw = Pack4(r[0], r[1], r[2], r[3]), gw = Pack4(g[0], g[1], g[2], g[3]),
+                                   bw = Pack4(b[0], b[1], b[2], b[3]);
+                    if (h) { R.y = rw; G.y = gw; B.y = bw; } else { R.x = rw; G.x = gw; B.x = bw; }
                 }
             }
         }
@@ -171,31 +204,40 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
             uint8_t* dst = od.dst[0] + size_t(y) * od.dst_pitch[0] + size_t(xt) * 3;
             const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
             if (have) {
-                uint8_t* o = buf + phase + lane * 24;
+                // interleave R,G,B bytes: 8 pixels -> 6 words
+                uint32_t w[6];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (lane * 8 + i < nx) {
-                        o[3 * i] = uint8_t(r[i]);
-                        o[3 * i + 1] = uint8_t(g[i]);
-                        o[3 * i + 2] = uint8_t(b[i]);
-                    }
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t r = h ? R.y : R.x, g = h ? G.y : G.x, b = h ? B.y : B.x;
+                    w[3 * h + 0] = __byte_perm(__byte_perm(r, g, 0x1040), b, 0x3410);   // r0 g0 b0 r1
+                    w[3 * h + 1] = __byte_perm(__byte_perm(g, b, 0x2051), r, 0x3610);   // g1 b1 r2 g2
+                    w[3 * h + 2] = __byte_perm(__byte_perm(b, r, 0x3702), g, 0x3720);   // b2 r3 g3 b3
+                }
+                uint8_t* o = buf + phase + lane * 24;
+                if ((phase & 3) == 0 && lane * 8 + 8 <= nx) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) reinterpret_cast<uint32_t*>(o)[k] = w[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 24; k++)
+                        if (lane * 8 + k / 3 < nx) o[k] = uint8_t((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
                 }
             }
+            __syncwarp();
             FlushRow(buf, phase, dst, nx * 3, lane);
         } else {
             // all three planes use pitch[0] (src/rocjpeg_decoder.cpp:526-544)
+            uint8_t* dst[3];
+            int phase[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                uint8_t* dst = od.dst[c] + size_t(y) * od.dst_pitch[0] + xt;
-                const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
-                if (have) {
-                    const uint32_t(&src)[8] = (c == 0) ? r : (c == 1) ? g : b;
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if (lane * 8 + i < nx) buf[phase + lane * 8 + i] = uint8_t(src[i]);
-                }
-                FlushRow(buf, phase, dst, nx, lane);
+                dst[c] = od.dst[c] + size_t(y) * od.dst_pitch[0] + xt;
+                phase[c] = int(reinterpret_cast<uintptr_t>(dst[c]) & 15);
+                Stage8(buf + c * kChanBuf, phase[c], lane, nx, c == 0 ? R : c == 1 ? G : B);
             }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 3; c++) FlushRow(buf + c * kChanBuf, phase[c], dst[c], nx, lane);
         }
         return;
     }
@@ -220,6 +262,7 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
             else v = (k & 2) ? __ldg(vrow + (k >> 2)) : __ldg(urow + (k >> 2));
             buf[phase + j] = v;
         }
+        __syncwarp();
         FlushRow(buf, phase, dst, n, lane);
         return;
     }
@@ -242,6 +285,7 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
                 const int k = x0 + xt + j;
                 buf[phase + j] = (k & 1) ? __ldg(vrow + (k >> 1)) : __ldg(urow + (k >> 1));
             }
+            __syncwarp();
             FlushRow(buf, phase, dst, nx, lane);
         }
         return;

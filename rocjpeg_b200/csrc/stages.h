@@ -32,7 +32,7 @@ struct K1Args {
     int3* dc_partial;             // per DC tile: per-component DC sum after the tile's last reset
     uint32_t* counters;           // [kMaxSyncRounds] boundary changes per round, then [kMaxSyncRounds] decodes per round
     int16_t* coef;                // coefficient arena, 64 int16 per block
-    int16_t* dcdiff;              // one DC difference per block
+    int16_t* dcdiff;              // one DC value per block: difference after k1_write, absolute after dc_apply
     int nimages;
     uint32_t total_ctas;          // K1 CTAs in the batch
     uint32_t total_dc_tiles;
@@ -43,14 +43,15 @@ struct K1Args {
 cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream);
 // Final pass: positions from the block counts, coefficients and DC differences written.
 cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream);
-// DC prediction: per-tile sums, then prefix + write of absolute DC into coef[blk*64].
+// DC prediction: per-tile sums, then prefix; absolute DC written over the per-block differences.
 cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream);
 
 struct K2Args {
     const ImageDesc* images;
     const uint32_t* img_tile0;    // nimages + 1: first IDCT tile of each image
     const uint16_t* qtables;      // natural-order u16[64] tables
-    const int16_t* coef;
+    const int16_t* coef;          // AC coefficients (coefficient 0 of every block is unused)
+    const int16_t* dc;            // absolute DC per block (decode order)
     uint8_t* planes;              // plane arena
     int nimages;
     uint32_t total_tiles;

@@ -28,14 +28,25 @@ struct HostLoader {
     uint32_t operator()(uint32_t i) const {
         uint32_t w;
         std::memcpy(&w, base + size_t(i) * 4, 4);
-        return w;
+        return ByteSwap32(w);   // the core reads big-endian words
     }
 };
+// Mirrors CoefSink in k1_huffman.cu: blocks assembled per thread and stored whole by their owner.
 struct HostSink {
     int16_t* coef;
     int16_t* dcdiff;
-    void Dc(uint32_t blk, int v) const { dcdiff[blk] = int16_t(v); }
-    void Ac(uint32_t blk, int z, int v) const { coef[size_t(blk) * 64 + kZig[z]] = int16_t(v); }
+    int16_t buf[64];
+    bool live;
+    void Dc(uint32_t blk, int v) { if (live) dcdiff[blk] = int16_t(v); }
+    void Ac(uint32_t, int z, int v) { if (live) buf[kZig[z]] = int16_t(v); }
+    void Flush(uint32_t blk) {
+        std::memcpy(coef + size_t(blk) * 64, buf, 128);
+        std::memset(buf, 0, 128);
+    }
+    void EndBlock(uint32_t blk) {
+        if (live) Flush(blk);
+        live = true;
+    }
 };
 struct SubInfo {
     uint32_t seg;
@@ -71,6 +82,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
             mcu_ac[k] = uint8_t(2 + p.ta[c]);
         }
     }
+    const TableSel sel = MakeTableSel(mcu_dc, mcu_ac, bpm);
     const uint32_t total_mcus = uint32_t(p.mcus_x) * uint32_t(p.mcus_y);
     const uint32_t ri = p.restart_interval > 0 ? uint32_t(p.restart_interval) : total_mcus;
     // subsequences
@@ -96,7 +108,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         uint32_t pb = StateOverflow(key), nb = 0, blk = 0;
         int c = StateC(key), z = StateZ(key);
         HostLoader ld{clean + subs[g].start};
-        DecodeSpan<false>(ld, &p.lut, mcu_dc, mcu_ac, bpm, pb, subs[g].end_bit, c, z, nb, blk, 0xFFFFFFFFu, nsink);
+        DecodeSpan<false>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, nb, blk, 0xFFFFFFFFu, nsink);
         uint32_t over = pb > subs[g].end_bit ? pb - subs[g].end_bit : 0;
         return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
     };
@@ -160,8 +172,8 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         cta_tail[cta] = tail;
     }
     const uint32_t nblocks = total_mcus * uint32_t(bpm);
-    std::vector<int16_t> coef(size_t(nblocks) * 64, 0), dcdiff(nblocks, 0);
-    HostSink sink{coef.data(), dcdiff.data()};
+    // the arena is NOT cleared on the device: start from garbage to prove every block gets stored
+    std::vector<int16_t> coef(size_t(nblocks) * 64, int16_t(0x7777)), dcdiff(nblocks, int16_t(0x7777));
     for (uint32_t cta = 0; cta < nctas; cta++) {
         uint32_t carry = 0;
         for (int64_t kk = int64_t(cta) - 1; kk >= 0; kk--) {
@@ -178,8 +190,17 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
             int c = StateC(key), z = StateZ(key);
             uint32_t blk = seg_blk_first[subs[g].seg] + excl;
             const uint32_t limit = seg_blk_first[subs[g].seg] + seg_blk_count[subs[g].seg];
+            HostSink sink{coef.data(), dcdiff.data(), {}, z == 0};
             HostLoader ld{clean + subs[g].start};
-            DecodeSpan<true>(ld, &p.lut, mcu_dc, mcu_ac, bpm, pb, subs[g].end_bit, c, z, cnt, blk, limit, sink);
+            DecodeSpan<true>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, cnt, blk, limit, sink);
+            const Segment& sg = p.segments[subs[g].seg];
+            const uint32_t seg_end_bit = (sg.nbytes - uint32_t(subs[g].start - sg.offset)) * 8u;
+            if (sink.live && z != 0 && blk < limit && pb < seg_end_bit)
+                DecodeSpan<true>(ld, &parser.lut(), sel, bpm, pb, seg_end_bit, c, z, cnt, blk, blk + 1, sink);
+            if (sink.live && (subs[g].last || pb >= seg_end_bit) && blk < limit) {
+                if (z != 0) { sink.Flush(blk); blk++; }
+                for (; blk < limit; blk++) { sink.Flush(blk); dcdiff[blk] = 0; }
+            }
         }
     }
     // DC integration per component, reset at restart intervals
