@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank decodes a full batch; strong: one batch sharded over the ranks by scan bytes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -203,11 +205,13 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: rocjpeg_b200 has no CPU fallback"
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
+    from rocjpeg_b200 import dist as rdist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rdist.init("nccl", torch.device("cuda", local_rank))
     datas, fmt = build_workload(args.workload, args.batch or None)
+    if args.scaling == "strong" and world > 1:
+        mine = rdist.shard_by_cost([len(d) for d in datas], world)[rank]
+        datas = [datas[i] for i in mine]
     total_px, dims = pixels_of(datas)
     config["per_gpu_batch"], config["output_format"] = len(datas), fmt
     config["scan_bytes_per_batch"] = sum(len(d) for d in datas)
@@ -243,7 +247,7 @@ def main():
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            rdist.barrier()
             torch.cuda.synchronize()
 
     # ---- device-resident arm (value) -------------------------------------------------
@@ -299,20 +303,14 @@ def main():
     dec.set_profiling(False)
 
     # max over ranks
-    if world > 1:
-        t = torch.tensor([resident_ms, e2e_ms, 1e3 * sum(pd_s) / len(pd_s)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        resident_ms, e2e_ms, pd_ms = [float(x) for x in t.tolist()]
-    else:
-        pd_ms = 1e3 * sum(pd_s) / len(pd_s)
+    resident_ms, e2e_ms, pd_ms = rdist.max_over_ranks([resident_ms, e2e_ms, 1e3 * sum(pd_s) / len(pd_s)], "cuda")
+    px_all, n_all = rdist.sum_over_ranks([total_px, len(datas)], "cuda")
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        rdist.finalize()
         return
 
-    mp_total = total_px * world / 1e6
-    images_total = len(datas) * world
+    mp_total = px_all / 1e6
+    images_total = int(n_all)
     value = mp_total / (resident_ms / 1e3)
     peak, peak_src = measured_peaks()
     # algorithmic bytes per stage (DESIGN.md section 5 / SURVEY.md section 8d)
@@ -335,7 +333,7 @@ def main():
     achieved = stage_bytes[dom] / dom_ms / 1e6 if dom_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(resident_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(resident_ms, 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u8 / int16 coefficients / int32 IDCT / fp32 colour", "data": "synthetic", "config": config,
         "images_per_s": round(images_total / (resident_ms / 1e3), 1),
         "e2e": {"value": round(mp_total / (e2e_ms / 1e3), 1), "unit": UNIT, "images_per_s": round(images_total / (e2e_ms / 1e3), 1),
@@ -359,9 +357,7 @@ def main():
         line["cpu_baseline"] = {"value": round(mps, 2), "unit": UNIT, "images_per_s": round(ips, 1), "cores": threads, "kind": "port",
                                 "sample": sample, "host_cpus": os.cpu_count()}
     print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    rdist.finalize()
 
 
 if __name__ == "__main__":

@@ -306,8 +306,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             od.dst[c] = dsts[i].channel[c];
             od.dst_pitch[c] = dsts[i].pitch[c];
         }
-        od.tiles_x = uint32_t((od.w + 255) / 256);
-        od.tiles_y = uint32_t((od.h + 7) / 8);
+        od.tiles_x = uint32_t((od.w + kK3TileW - 1) / kK3TileW);
+        od.tiles_y = uint32_t((od.h + kK3TileH - 1) / kK3TileH);
         od.tile0 = k3tile;
         h_k3_tile0_[size_t(i)] = k3tile;
         k3tile += od.tiles_x * od.tiles_y;

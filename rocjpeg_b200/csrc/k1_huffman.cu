@@ -75,7 +75,69 @@ struct SlotOrGlobalLoader {
     }
 };
 
-constexpr int kBlkBufBytes = 144;   // 128 B block + 16: 16-byte aligned rows, quarter-warps conflict-free
+// ---- lean shared-memory primitives for the two hot loops ---------------------------------
+// Both K1 loops are instruction-issue bound (profiles/r01b_*), so they are written against raw
+// 32-bit shared-memory addresses: no generic-address arithmetic, no window registers to rotate
+// (two extra LDS per symbol cost latency, which the other warps hide, but no issue slots for
+// bookkeeping), table select and bit position as the only loop-carried scalars.
+__device__ __forceinline__ uint32_t SharedAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t Lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t Lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t Lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void Sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// Next 32 bits of the stream at bit position p of the slot at shared address `slot`.
+__device__ __forceinline__ uint32_t PeekBits(uint32_t slot, uint32_t p) {
+    const uint32_t a = slot + ((p >> 5) << 2);
+    return __funnelshift_l(Lds32(a + 4), Lds32(a), p);
+}
+// Byte offsets of the Huffman tables of block c inside HuffLutSet::fast.
+__device__ __forceinline__ uint32_t DcBytes(TableSel t, int c) { return ((t.dc_mask >> c) & 1u) << (kFastBits + 1); }
+__device__ __forceinline__ uint32_t AcBytes(TableSel t, int c) { return (2u + ((t.ac_mask >> c) & 1u)) << (kFastBits + 1); }
+
+// Count-only decode of one subsequence from state `key` (speculation / synchronisation):
+// returns the packed end state and block count.
+__device__ __forceinline__ uint32_t DecodeCount(uint32_t slot, uint32_t lut_sa, const HuffLutSet* lut, TableSel sel, int bpm,
+                                                uint32_t key, uint32_t end_bit) {
+    uint32_t p = StateOverflow(key), nb = 0;
+    int c = StateC(key), z = StateZ(key);
+    uint32_t dc_off = DcBytes(sel, c), ac_off = AcBytes(sel, c);
+    uint32_t off = (z == 0) ? dc_off : ac_off;
+    while (p < end_bit) {
+        const uint32_t win = PeekBits(slot, p);
+        uint32_t e = Lds16(lut_sa + off + ((win >> (31 - kFastBits)) & (2u * kFastSize - 2u)));
+        if (e == 0) e = SlowEntry(lut, off >> (kFastBits + 1), win >> 16);
+        p += EntryBits(e);
+        z += EntryAdvance(e);
+        off = ac_off;
+        if (z >= 64) {
+            z = 0;
+            nb++;
+            c = (c + 1 == bpm) ? 0 : c + 1;
+            dc_off = DcBytes(sel, c);
+            ac_off = AcBytes(sel, c);
+            off = dc_off;
+        }
+    }
+    const uint32_t over = p > end_bit ? p - end_bit : 0;
+    return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
+}
+
+constexpr int kBlkBufBytes = 144;    // one staged block: 128 B + 16 (keeps 16-byte alignment)
+constexpr int kLaneBufBytes = 2 * kBlkBufBytes + 8;   // two blocks per lane; 74-word lane stride spreads the banks
+constexpr int kFlushEvery = 8;       // symbols decoded per lane between two cooperative flushes
 
 // Per-thread description of its subsequence.
 struct Sub {
@@ -132,6 +194,9 @@ struct K1Smem {
     uint32_t words[T * kSlotStride];
     uint64_t start[T];
     uint32_t state[T];
+    uint32_t used[T];
+    uint32_t endbit[T];
+    uint32_t queue[T];
     uint8_t mcu_dc[16], mcu_ac[16];
     uint8_t zigzag[64];
     uint32_t scratch[40];
@@ -140,7 +205,7 @@ struct K1Smem {
 template <int S>
 struct K1WriteSmem {
     K1Smem<S> k;
-    __align__(16) unsigned char blkbuf[T * kBlkBufBytes];
+    __align__(16) unsigned char blkbuf[T * kLaneBufBytes];
 };
 
 template <int S>
@@ -198,44 +263,63 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
         }
     }
     StageCta<S>(sm, a, im, me);
-    const SmemLoader loader{sm.words + tid * K1Smem<S>::kSlotStride};
-    NullSink sink;
-
     const TableSel sel = MakeTableSel(sm.mcu_dc, sm.mcu_ac, im.bpm);
     const int bpm = im.bpm;
-    auto decode_from = [&](uint32_t key) {
-        uint32_t p = StateOverflow(key), nb = 0, blk = 0;
-        int c = StateC(key), z = StateZ(key);
-        DecodeSpan<false>(loader, &sm.lut, sel, bpm, p, me.end_bit, c, z, nb, blk, 0xFFFFFFFFu, sink);
-        const uint32_t over = p > me.end_bit ? p - me.end_bit : 0;
-        return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
+    const uint32_t slots_sa = SharedAddr(sm.words);
+    const uint32_t lut_sa = SharedAddr(&sm.lut.fast[0][0]);
+    auto decode = [&](uint32_t sub, uint32_t key) {
+        return DecodeCount(slots_sa + sub * uint32_t(K1Smem<S>::kSlotStride * 4), lut_sa, &sm.lut, sel, bpm, key, sm.endbit[sub]);
     };
 
     uint32_t ndecodes = 0;
+    sm.endbit[tid] = me.end_bit;
+    if (tid == 0) sm.scratch[0] = 0;   // work-queue length
+    __syncthreads();
     if (round == 0 && me.active) {
         // guess for a mid-segment start: aligned on a symbol, first block of an MCU, DC next
         my_used = 0;
-        out = decode_from(0);
+        out = decode(uint32_t(tid), 0);
         ndecodes++;
     }
     sm.state[tid] = out;
-    // CTA-local fix-up: re-decode while the predecessor's end state is not the state used.
+    sm.used[tid] = my_used;
+    // state entering the CTA (snapshot: the neighbouring CTA may still be changing it; a change is
+    // caught by the boundary counter and the next round)
+    uint32_t in0 = my_used;
+    if (round > 0 && tid == 0 && me.active && !me.first) in0 = StateKey(a.state[g - 1]);
+    const bool can_redo = me.active && !me.first;
+    const int lane = tid & 31;
+    // CTA-local fix-up: re-decode while the predecessor's end state is not the state used. The
+    // subsequences that need it are compacted into a queue so that the re-decodes occupy as few
+    // warps as possible (a warp with one busy lane costs as many issue slots as a full one).
     for (int iter = 0; iter < T + 1; iter++) {
         __syncthreads();
-        uint32_t in = my_used;
-        if (me.active && !me.first) {
-            if (tid > 0) in = StateKey(sm.state[tid - 1]);
-            else if (round > 0) in = StateKey(a.state[g - 1]);
-        }
-        const int need = me.active && !me.first && in != my_used;
-        if (!__syncthreads_or(need)) break;
-        if (need) {
-            out = decode_from(in);
-            my_used = in;
-            sm.state[tid] = out;
+        const uint32_t in = (tid > 0) ? StateKey(sm.state[tid - 1]) : in0;
+        const bool need = can_redo && in != sm.used[tid];
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, need);
+        uint32_t base = 0;
+        if (lane == 0 && mask) base = atomicAdd(&sm.scratch[0], uint32_t(__popc(mask)));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (need) sm.queue[base + __popc(mask & ((1u << lane) - 1u))] = (in << 16) | uint32_t(tid);
+        __syncthreads();
+        const uint32_t n = sm.scratch[0];
+        if (n == 0) break;
+        uint32_t item = 0, res = 0;
+        if (uint32_t(tid) < n) {
+            item = sm.queue[tid];
+            res = decode(item & 0xFFFFu, item >> 16);
             ndecodes++;
         }
+        __syncthreads();
+        if (uint32_t(tid) < n) {
+            sm.state[item & 0xFFFFu] = res;
+            sm.used[item & 0xFFFFu] = item >> 16;
+        }
+        if (tid == 0) sm.scratch[0] = 0;
     }
+    __syncthreads();
+    out = sm.state[tid];
+    my_used = sm.used[tid];
     if (me.active) {
         a.state[g] = out;
         a.used[g] = my_used;
@@ -270,10 +354,9 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const ImageDesc& im = a.images[img];
     const uint32_t g = cta * T + tid;
     const Sub me = Locate<S>(a, im, g, true);
-    {   // zero this thread's block buffer (only ever touched by its owner)
-        uint4* zb = reinterpret_cast<uint4*>(wsm.blkbuf + tid * kBlkBufBytes);
-#pragma unroll
-        for (int i = 0; i < kBlkBufBytes / 16; i++) zb[i] = make_uint4(0, 0, 0, 0);
+    {   // zero the block buffers
+        uint32_t* zb = reinterpret_cast<uint32_t*>(wsm.blkbuf);
+        for (int i = tid; i < T * kLaneBufBytes / 4; i += T) zb[i] = 0;
     }
     StageCta<S>(sm, a, im, me);
 
@@ -328,13 +411,17 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const uint32_t incl = v + add;
     const uint32_t excl = (me.active && me.first) ? 0u : incl - nb;
 
-    // ---- final decode. Every block is assembled in this thread's shared-memory buffer and
-    // leaves as eight 128-bit stores (whole 128-byte lines: the coefficient arena needs no
-    // clearing and sees no partial-sector read-modify-write). A block belongs to the thread that
-    // decodes its DC symbol: that thread keeps decoding past the end of its subsequence until the
-    // block is complete; a thread that starts inside a block stays silent (`live` false) until
-    // the first block boundary. The warp runs "decode to the next block end" / "flush" in
-    // lock-step so the 24-instruction flush is not replayed for every divergent lane.
+    // ---- final decode. Every block is assembled in shared memory and leaves as one whole
+    // 128-byte line (the coefficient arena needs no clearing and sees no partial-sector
+    // read-modify-write). A block belongs to the thread that decodes its DC symbol: that thread
+    // keeps decoding past the end of its subsequence until the block is complete; a thread that
+    // starts inside a block stays silent (`live` false) until the first block boundary.
+    //
+    // The warp advances in lock-step, one symbol per lane per step, so all 32 lanes execute the
+    // same instruction stream. Each lane owns two block buffers: a finished block is parked
+    // (`pending`) while the lane continues in the other buffer; every kFlushEvery steps the
+    // warp stores all parked blocks cooperatively — 32 lanes x 4 bytes = one coalesced line per
+    // block. A lane that finishes a second block before the rendezvous simply waits for it.
     SegmentDesc sd = {};
     if (me.active) sd = a.segments[me.seg];
     uint32_t key = 0;
@@ -346,75 +433,108 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const uint32_t seg_end_bit = me.active ? (sd.nbytes - uint32_t(me.start - sd.data_off)) * 8u : 0u;
     int16_t* coef = a.coef + size_t(im.blk0) * 64;
     int16_t* dcdiff = a.dcdiff + im.blk0;
-    int16_t* buf = reinterpret_cast<int16_t*>(wsm.blkbuf + tid * kBlkBufBytes);
+    unsigned char* mybufs = wsm.blkbuf + tid * kLaneBufBytes;
     const TableSel sel = MakeTableSel(sm.mcu_dc, sm.mcu_ac, im.bpm);
     const int bpm = im.bpm;
-    const SlotOrGlobalLoader loader{sm.words + tid * K1Smem<S>::kSlotStride,
-                                    reinterpret_cast<const uint32_t*>(a.scan + (me.active ? me.start : 0)),
-                                    uint32_t(K1Smem<S>::kSlotWords)};
-    auto flush = [&](uint32_t b) {
-        uint4* src = reinterpret_cast<uint4*>(buf);
-        uint4* dst = reinterpret_cast<uint4*>(coef + size_t(b) * 64);
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            dst[i] = src[i];
-            src[i] = make_uint4(0, 0, 0, 0);
-        }
-    };
+    const uint32_t slot_sa = SharedAddr(sm.words + tid * K1Smem<S>::kSlotStride);
+    const uint32_t lut_sa = SharedAddr(&sm.lut.fast[0][0]);
+    const uint32_t zz_sa = SharedAddr(sm.zigzag);
+    const uint32_t bufs_sa = SharedAddr(mybufs);
+    const uint32_t* gwords = reinterpret_cast<const uint32_t*>(a.scan + (me.active ? me.start : 0));
     bool live = (z == 0);
     bool finishing = false;                 // past the subsequence, completing an owned block
     uint32_t stop = me.end_bit;
     bool done = !me.active || p >= stop || blk >= limit;
-    BitWindow bw;
-    bw.Init(loader, done ? 0u : p);
-    uint32_t dc_off = DcOffset(sel, c), ac_off = AcOffset(sel, c);
+    uint32_t cur_sa = bufs_sa;              // buffer being filled
+    bool pending = false;                   // the other buffer holds a finished block
+    uint32_t pend_blk = 0;
+    uint32_t pend_sa = 0;
+    uint32_t dc_off = DcBytes(sel, c), ac_off = AcBytes(sel, c);
+    uint32_t off = (z == 0) ? dc_off : ac_off;
     for (;;) {
-        bool ended = false;
-        while (!done && !ended) {
-            const uint32_t win = bw.Peek(p);
-            const uint32_t e = LookupSymbol(&sm.lut, (z == 0) ? dc_off : ac_off, win);
-            const int adv = EntryAdvance(e);
-            if (live) {
-                const int val = SymbolValue(e, win);
-                if (z == 0) dcdiff[blk] = int16_t(val);
-                else if (EntrySize(e) && z + adv <= 64) buf[sm.zigzag[z + adv - 1]] = int16_t(val);
-            }
-            z += adv;
-            p += EntryBits(e);
-            bw.Advance(loader, p);
-            if (z >= 64) {
-                ended = true;
-            } else if (p >= stop) {
-                if (!finishing && live && p < seg_end_bit) {
-                    finishing = true;       // own the unfinished block: follow it into the next subsequence(s)
-                    stop = seg_end_bit;
-                } else {
-                    done = true;
+#pragma unroll 1
+        for (int step = 0; step < kFlushEvery; step++) {
+            if (!done && z < 64) {
+                const uint32_t wi = p >> 5;
+                uint32_t w0, w1;
+                if (wi + 1 < uint32_t(K1Smem<S>::kSlotWords)) {
+                    w0 = Lds32(slot_sa + (wi << 2));
+                    w1 = Lds32(slot_sa + (wi << 2) + 4);
+                } else {   // finishing an owned block beyond the staged slot: straight from the arena
+                    w0 = ByteSwap32(__ldg(gwords + wi));
+                    w1 = ByteSwap32(__ldg(gwords + wi + 1));
+                }
+                const uint32_t win = __funnelshift_l(w1, w0, p);
+                uint32_t e = Lds16(lut_sa + off + ((win >> (31 - kFastBits)) & (2u * kFastSize - 2u)));
+                if (e == 0) e = SlowEntry(&sm.lut, off >> (kFastBits + 1), win >> 16);
+                const uint32_t sz = EntrySize(e), bits = EntryBits(e);
+                // RECEIVE + EXTEND (T.81 F.2.2.1): magnitude bits moved to the top of t
+                const uint32_t t = win << (bits - sz);
+                const uint32_t extra = __funnelshift_rc(t, 0u, 32u - sz);
+                const int val = int(extra) - ((int(t) < 0) ? 0 : int((1u << sz) - 1u));
+                const int z_old = z;
+                z += EntryAdvance(e);
+                p += bits;
+                if (live) {
+                    if (z_old == 0) dcdiff[blk] = int16_t(val);
+                    else if (sz != 0 && z <= 64) Sts16(cur_sa + 2u * Lds8(zz_sa + uint32_t(z) - 1u), uint32_t(val));
+                }
+                off = ac_off;
+                if (z < 64 && p >= stop) {
+                    if (!finishing && live && p < seg_end_bit) {
+                        finishing = true;   // own the unfinished block: follow it into the next subsequence(s)
+                        stop = seg_end_bit;
+                    } else {
+                        done = true;
+                    }
                 }
             }
+            if (!done && z >= 64 && !(live && pending)) {   // block complete and a buffer is free
+                if (live) {
+                    pending = true;
+                    pend_blk = blk;
+                    pend_sa = cur_sa;
+                    cur_sa = bufs_sa + (cur_sa == bufs_sa ? uint32_t(kBlkBufBytes) : 0u);
+                }
+                live = true;
+                z = 0;
+                blk++;
+                c = (c + 1 == bpm) ? 0 : c + 1;
+                dc_off = DcBytes(sel, c);
+                ac_off = AcBytes(sel, c);
+                off = dc_off;
+                if (finishing || p >= stop || blk >= limit) done = true;
+            }
         }
-        if (!__any_sync(0xFFFFFFFFu, ended)) break;
-        if (ended) {
-            if (live) flush(blk);
-            live = true;
-            z = 0;
-            blk++;
-            c = (c + 1 == bpm) ? 0 : c + 1;
-            dc_off = DcOffset(sel, c);
-            ac_off = AcOffset(sel, c);
-            if (finishing || p >= stop || blk >= limit) done = true;
+        // rendezvous: store every parked block, one coalesced 128-byte line each
+        __syncwarp();
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, pending);
+        while (m) {
+            const int L = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t b = __shfl_sync(0xFFFFFFFFu, pend_blk, L);
+            const uint32_t src = __shfl_sync(0xFFFFFFFFu, pend_sa, L) + 4u * uint32_t(lane);
+            const uint32_t v = Lds32(src);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(src), "r"(0u) : "memory");
+            reinterpret_cast<uint32_t*>(coef + size_t(b) * 64)[lane] = v;
         }
+        pending = false;
+        __syncwarp();
+        if (!__any_sync(0xFFFFFFFFu, !done)) break;
     }
     // Damaged / truncated data only: when the interval's data ends under this thread's hands,
     // what the interval still owes is written as zero blocks (the arena is never cleared, so
     // every block must be stored by someone).
     if (me.active && live && (me.last || p >= seg_end_bit) && blk < limit) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(mybufs + (cur_sa - bufs_sa));
         if (z != 0) {
-            flush(blk);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(coef + size_t(blk) * 64);
+            for (int i = 0; i < 32; i++) dst[i] = src[i];
             blk++;
         }
         for (; blk < limit; blk++) {
-            flush(blk);
+            uint4* dst = reinterpret_cast<uint4*>(coef + size_t(blk) * 64);
+            for (int i = 0; i < 8; i++) dst[i] = make_uint4(0, 0, 0, 0);
             dcdiff[blk] = 0;
         }
     }

@@ -28,8 +28,18 @@ constexpr int kBlocksPerTile = 32;
 constexpr int kThreads = kBlocksPerTile * 8;
 constexpr int kTilesPerCta = 4;
 
+// Everything the 256 threads of a CTA need about one tile (32 adjacent blocks of one block row
+// of one component), resolved once per tile by one thread.
 struct TileInfo {
-    int comp, by, bx0;   // comp < 0: no work
+    const int16_t* coef;     // image coefficient base (coef + blk0 * 64)
+    const int16_t* dc;       // image DC base
+    const uint16_t* qt;      // natural-order quantiser table of the component
+    uint8_t* out;            // plane address of (row by*8, column 0)
+    uint32_t pitch;
+    uint32_t row_mcu;        // (by / V) * mcus_x
+    uint32_t k_row;          // comp_first_blk + (by % V) * H
+    int32_t bx0, nbx;        // first block column of the tile, block columns of the component (<0: no work)
+    int32_t hshift, hmask, bpm;
 };
 
 __device__ __forceinline__ uint32_t UpperIndexK2(const uint32_t* a, uint32_t n, uint32_t v) {
@@ -79,52 +89,56 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
     // row-wise and the column-wise access of a warp hit 32 distinct banks.
     __shared__ int ws[kBlocksPerTile * 72];
     __shared__ TileInfo s_tile[kTilesPerCta];
-    __shared__ uint32_t s_img[kTilesPerCta];
     const int tid = threadIdx.x;
     if (tid < kTilesPerCta) {
         // tile -> (image, component, block row, first block column); one search per tile, four
-        // lanes in parallel, no division anywhere else in the kernel
+        // lanes in parallel; sampling factors are powers of two, so no division in the hot part
         const uint32_t tile = blockIdx.x * kTilesPerCta + tid;
-        TileInfo ti{-1, 0, 0};
-        uint32_t img = 0;
+        TileInfo ti = {};
+        ti.nbx = -1;
         if (tile < a.total_tiles) {
-            img = UpperIndexK2(a.img_tile0, uint32_t(a.nimages), tile);
+            const uint32_t img = UpperIndexK2(a.img_tile0, uint32_t(a.nimages), tile);
             const ImageDesc& im = a.images[img];
             uint32_t t = tile - a.img_tile0[img];
             for (int comp = 0; comp < im.ncomp; comp++) {
                 const uint32_t tiles_x = (uint32_t(im.blocks_w[comp]) + kBlocksPerTile - 1) / kBlocksPerTile;
                 const uint32_t n = tiles_x * uint32_t(im.blocks_h[comp]);
                 if (t < n) {
-                    ti.comp = comp;
-                    ti.by = int(t / tiles_x);
+                    const int by = int(t / tiles_x);
+                    const int H = im.hs[comp], V = im.vs[comp];
+                    const int hs = __ffs(H) - 1, vs = __ffs(V) - 1;
+                    ti.coef = a.coef + size_t(im.blk0) * 64;
+                    ti.dc = a.dc + im.blk0;
+                    ti.qt = a.qtables + size_t(im.qt_index[comp]) * 64;
+                    ti.pitch = im.plane_pitch[comp];
+                    ti.out = a.planes + im.plane_off[comp] + size_t(by) * 8 * ti.pitch;
+                    ti.row_mcu = uint32_t(by >> vs) * uint32_t(im.mcus_x);
+                    ti.k_row = uint32_t(im.comp_first_blk[comp] + ((by & (V - 1)) << hs));
                     ti.bx0 = int(t % tiles_x) * kBlocksPerTile;
+                    ti.nbx = im.blocks_w[comp];
+                    ti.hshift = hs;
+                    ti.hmask = H - 1;
+                    ti.bpm = im.bpm;
                     break;
                 }
                 t -= n;
             }
         }
         s_tile[tid] = ti;
-        s_img[tid] = img;
     }
     __syncthreads();
     const int b = tid >> 3, j = tid & 7;
     int* my = ws + b * 72;
 #pragma unroll 1
     for (int it = 0; it < kTilesPerCta; it++) {
-        const TileInfo ti = s_tile[it];
-        if (ti.comp < 0) break;
-        const ImageDesc& im = a.images[s_img[it]];
-        const int comp = ti.comp, by = ti.by, bx = ti.bx0 + b;
-        const bool valid = bx < im.blocks_w[comp];
+        const TileInfo& ti = s_tile[it];
+        if (ti.nbx < 0) break;
+        const int bx = ti.bx0 + b;
+        const bool valid = bx < ti.nbx;
         if (valid) {
-            // sampling factors are 1 or 2 on every supported layout (T.81 allows up to 4: __ffs keeps it exact)
-            const int H = im.hs[comp], V = im.vs[comp];
-            const int hs = __ffs(H) - 1, vs = __ffs(V) - 1;
-            const uint32_t mcu = uint32_t(by >> vs) * uint32_t(im.mcus_x) + uint32_t(bx >> hs);
-            const uint32_t k = uint32_t(im.comp_first_blk[comp] + ((by & (V - 1)) << hs) + (bx & (H - 1)));
-            const size_t blk = size_t(im.blk0) + size_t(mcu) * im.bpm + k;
-            const uint4 cq = __ldg(reinterpret_cast<const uint4*>(a.coef + blk * 64) + j);
-            const uint4 qq = __ldg(reinterpret_cast<const uint4*>(a.qtables + size_t(im.qt_index[comp]) * 64) + j);
+            const size_t blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
+            const uint4 cq = __ldg(reinterpret_cast<const uint4*>(ti.coef + blk * 64) + j);
+            const uint4 qq = __ldg(reinterpret_cast<const uint4*>(ti.qt) + j);
             const uint32_t cw[4] = {cq.x, cq.y, cq.z, cq.w}, qw[4] = {qq.x, qq.y, qq.z, qq.w};
             int* row = my + j * 9;
 #pragma unroll
@@ -132,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
                 row[2 * w] = int(int16_t(cw[w] & 0xFFFFu)) * int(qw[w] & 0xFFFFu);
                 row[2 * w + 1] = (int(cw[w]) >> 16) * int(qw[w] >> 16);
             }
-            if (j == 0) row[0] = int(__ldg(a.dc + blk)) * int(qw[0] & 0xFFFFu);   // DC comes from the compact array
+            if (j == 0) row[0] = int(__ldg(ti.dc + blk)) * int(qw[0] & 0xFFFFu);   // DC comes from the compact array
         }
         __syncwarp();
         int in[8], out[8];
@@ -148,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
 #pragma unroll
             for (int c = 0; c < 8; c++) in[c] = my[j * 9 + c];   // row j
             Islow8<18>(in, out, (1 << 17) + (128 << 18));
-            uint8_t* dst = a.planes + im.plane_off[comp] + size_t(by * 8 + j) * im.plane_pitch[comp] + size_t(bx) * 8;
+            uint8_t* dst = ti.out + size_t(j) * ti.pitch + size_t(bx) * 8;
             *reinterpret_cast<uint2*>(dst) = make_uint2(PackSat4(out[0], out[1], out[2], out[3]), PackSat4(out[4], out[5], out[6], out[7]));
         }
         __syncwarp();

@@ -33,9 +33,10 @@
 namespace rjb {
 namespace {
 
-constexpr int kTileW = 256;   // luma samples per tile row (8 per lane)
-constexpr int kTileH = 8;     // rows per tile (one per warp)
-constexpr int kThreads = 256;
+constexpr int kTileW = kK3TileW;   // luma samples per tile row (8 per lane)
+constexpr int kTileH = kK3TileH;   // rows per tile: each of the 8 warps walks kTileH / 8 of them
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
 constexpr int kChanBuf = kTileW + 32;      // one planar channel row + alignment phase
 constexpr int kRowBuf = 3 * kChanBuf;      // >= 3 * kTileW + 32 (packed RGB row)
 
@@ -114,130 +115,158 @@ __device__ __forceinline__ void CopyRow(uint8_t* buf, const uint8_t* src_row, in
     __syncwarp();
 }
 
+// Everything a CTA needs to know about its tile, resolved once by thread 0 (the kernel was
+// dominated by per-thread setup when each warp did a single row: profiles/r01b_*).
+struct K3Job {
+    const uint8_t* p[3];
+    uint32_t pitch[3];
+    uint8_t* dst[4];
+    uint32_t dpitch[4];
+    int W, H, x0, y0, css, fmt, xt, nx, ty;
+};
+
+// One output row segment of RGB / RGB_PLANAR (nx pixels starting at column xt of row y).
+__device__ __forceinline__ void RowRgb(const K3Job& j, int sx, int sy, bool gray, uint8_t* buf, int y, int lane) {
+    const int nx = j.nx, xt = j.xt;
+    const int Y = j.y0 + y;
+    const int X = j.x0 + xt + lane * 8;    // first luma column of this lane
+    const bool have = lane * 8 < nx;
+    uint2 R = make_uint2(0, 0), G = R, B = R;   // 8 packed bytes per channel
+    if (have) {
+        const uint2 yy = Load8(j.p[0] + size_t(Y) * j.pitch[0], X);
+        if (gray) {
+            R = G = B = yy;   // hip_kernels.cpp:1915-1927
+        } else {
+            const uint8_t* urow = j.p[1] + size_t(Y >> sy) * j.pitch[1];
+            const uint8_t* vrow = j.p[2] + size_t(Y >> sy) * j.pitch[2];
+            // chroma bytes per luma pixel (nearest neighbour): `pair` = the 4 bytes of uu.x/vv.x
+            // each serve two pixels (aligned 4:2:x fast path), otherwise one byte per pixel.
+            uint2 uu, vv;
+            const bool pair = (sx == 1) && ((X & 7) == 0);
+            if (sx == 0) {
+                uu = Load8(urow, X);
+                vv = Load8(vrow, X);
+            } else if (pair) {
+                uu = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(urow + (X >> 1))), 0);
+                vv = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(vrow + (X >> 1))), 0);
+            } else {
+                uint32_t ub[8], vb[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    ub[i] = __ldg(urow + ((X + i) >> 1));
+                    vb[i] = __ldg(vrow + ((X + i) >> 1));
+                }
+                uu = make_uint2(Pack4(ub[0], ub[1], ub[2], ub[3]), Pack4(ub[4], ub[5], ub[6], ub[7]));
+                vv = make_uint2(Pack4(vb[0], vb[1], vb[2], vb[3]), Pack4(vb[4], vb[5], vb[6], vb[7]));
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t yw = h ? yy.y : yy.x;
+                uint32_t r[4], g[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float fy = ByteF(yw, i);
+                    float fu, fv;
+                    if (pair) {
+                        fu = ByteF(uu.x, 2 * h + (i >> 1)) - 128.0f;
+                        fv = ByteF(vv.x, 2 * h + (i >> 1)) - 128.0f;
+                    } else {
+                        fu = ByteF(h ? uu.y : uu.x, i) - 128.0f;
+                        fv = ByteF(h ? vv.y : vv.x, i) - 128.0f;
+                    }
+                    r[i] = PackU8(fmaf(1.5748f, fv, fy));
+                    g[i] = PackU8(fmaf(-0.4681f, fv, fmaf(-0.1873f, fu, fy)));
+                    b[i] = PackU8(fmaf(1.8556f, fu, fy));
+                }
+                const uint32_t rw = Pack4(r[0], r[1], r[2], r[3]), gw = Pack4(g[0], g[1], g[2], g[3]),
+                               bw = Pack4(b[0], b[1], b[2], b[3]);
+                if (h) { R.y = rw; G.y = gw; B.y = bw; } else { R.x = rw; G.x = gw; B.x = bw; }
+            }
+        }
+    }
+    if (j.fmt == FMT_RGB) {
+        uint8_t* dst = j.dst[0] + size_t(y) * j.dpitch[0] + size_t(xt) * 3;
+        const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
+        if (have) {
+            // interleave R,G,B bytes: 8 pixels -> 6 words
+            uint32_t w[6];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t r = h ? R.y : R.x, g = h ? G.y : G.x, b = h ? B.y : B.x;
+                w[3 * h + 0] = __byte_perm(__byte_perm(r, g, 0x1040), b, 0x3410);   // r0 g0 b0 r1
+                w[3 * h + 1] = __byte_perm(__byte_perm(g, b, 0x2051), r, 0x3610);   // g1 b1 r2 g2
+                w[3 * h + 2] = __byte_perm(__byte_perm(b, r, 0x3702), g, 0x3720);   // b2 r3 g3 b3
+            }
+            uint8_t* o = buf + phase + lane * 24;
+            if ((phase & 3) == 0 && lane * 8 + 8 <= nx) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) reinterpret_cast<uint32_t*>(o)[k] = w[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 24; k++)
+                    if (lane * 8 + k / 3 < nx) o[k] = uint8_t((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+            }
+        }
+        __syncwarp();
+        FlushRow(buf, phase, dst, nx * 3, lane);
+    } else {
+        // all three planes use pitch[0] (src/rocjpeg_decoder.cpp:526-544)
+        uint8_t* dst[3];
+        int phase[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            dst[c] = j.dst[c] + size_t(y) * j.dpitch[0] + xt;
+            phase[c] = int(reinterpret_cast<uintptr_t>(dst[c]) & 15);
+            Stage8(buf + c * kChanBuf, phase[c], lane, nx, c == 0 ? R : c == 1 ? G : B);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 3; c++) FlushRow(buf + c * kChanBuf, phase[c], dst[c], nx, lane);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
-    __shared__ __align__(16) uint8_t s_buf[kTileH][kRowBuf];
-    __shared__ uint32_t s_img;
+    __shared__ __align__(16) uint8_t s_buf[kWarps][kRowBuf];
+    __shared__ K3Job s_job;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_img = UpperIndexK3(a.img_tile0, uint32_t(a.nimages), blockIdx.x);
+    if (tid == 0) {
+        const uint32_t img = UpperIndexK3(a.img_tile0, uint32_t(a.nimages), blockIdx.x);
+        const ImageDesc& im = a.images[img];
+        const OutputDesc& od = a.outputs[img];
+        const uint32_t t = blockIdx.x - a.img_tile0[img];
+        K3Job j;
+        for (int c = 0; c < 3; c++) {
+            j.p[c] = a.planes + im.plane_off[c < im.ncomp ? c : 0];
+            j.pitch[c] = im.plane_pitch[c < im.ncomp ? c : 0];
+        }
+        for (int c = 0; c < 4; c++) {
+            j.dst[c] = od.dst[c];
+            j.dpitch[c] = od.dst_pitch[c];
+        }
+        j.W = od.w; j.H = od.h; j.x0 = od.x0; j.y0 = od.y0; j.css = im.css; j.fmt = od.fmt;
+        j.xt = int(t % od.tiles_x) * kTileW;
+        j.ty = int(t / od.tiles_x);
+        j.nx = min(kTileW, od.w - j.xt);
+        s_job = j;
+    }
     __syncthreads();
-    const ImageDesc& im = a.images[s_img];
-    const OutputDesc& od = a.outputs[s_img];
-    const uint32_t t = blockIdx.x - a.img_tile0[s_img];
-    const int tx = int(t % od.tiles_x), ty = int(t / od.tiles_x);
-    const int W = od.w, H = od.h, x0 = od.x0, y0 = od.y0;
-    const int css = im.css, fmt = od.fmt;
+    const K3Job& j = s_job;
+    const int W = j.W, H = j.H, x0 = j.x0, y0 = j.y0, css = j.css, fmt = j.fmt;
     const int sx = (css == CSS_422 || css == CSS_420) ? 1 : 0;
     const int sy = (css == CSS_440 || css == CSS_420) ? 1 : 0;
     const bool gray = (css == CSS_400);
-    Planes pl;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        pl.p[c] = a.planes + im.plane_off[c < im.ncomp ? c : 0];
-        pl.pitch[c] = im.plane_pitch[c < im.ncomp ? c : 0];
-    }
     uint8_t* buf = s_buf[warp];
-    const int xt = tx * kTileW;              // first output column of the tile
-    const int y = ty * kTileH + warp;        // output row of this warp
-    const int nx = min(kTileW, W - xt);      // output columns in this tile
+    const int xt = j.xt, nx = j.nx, ty = j.ty;
+    if (nx <= 0) return;
 
     if (fmt == FMT_RGB || fmt == FMT_RGB_PLANAR) {
-        if (y >= H || nx <= 0) return;
-        if (fmt == FMT_RGB && (od.dst[0] == nullptr || od.dst_pitch[0] == 0)) return;
-        if (fmt == FMT_RGB_PLANAR && (!od.dst[0] || !od.dst[1] || !od.dst[2] || od.dst_pitch[0] == 0)) return;
-        const int Y = y0 + y;
-        const int X = x0 + xt + lane * 8;    // first luma column of this lane
-        const bool have = lane * 8 < nx;
-        uint2 R = make_uint2(0, 0), G = R, B = R;   // 8 packed bytes per channel
-        if (have) {
-            const uint2 yy = Load8(pl.p[0] + size_t(Y) * pl.pitch[0], X);
-            if (gray) {
-                R = G = B = yy;   // hip_kernels.cpp:1915-1927
-            } else {
-                const uint8_t* urow = pl.p[1] + size_t(Y >> sy) * pl.pitch[1];
-                const uint8_t* vrow = pl.p[2] + size_t(Y >> sy) * pl.pitch[2];
-                // chroma bytes per luma pixel (nearest neighbour): `pair` = the 4 bytes of uu.x/vv.x
-                // each serve two pixels (aligned 4:2:x fast path), otherwise one byte per pixel.
-                uint2 uu, vv;
-                const bool pair = (sx == 1) && ((X & 7) == 0);
-                if (sx == 0) {
-                    uu = Load8(urow, X);
-                    vv = Load8(vrow, X);
-                } else if (pair) {
-                    uu = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(urow + (X >> 1))), 0);
-                    vv = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(vrow + (X >> 1))), 0);
-                } else {
-                    uint32_t ub[8], vb[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        ub[i] = __ldg(urow + ((X + i) >> 1));
-                        vb[i] = __ldg(vrow + ((X + i) >> 1));
-                    }
-                    uu = make_uint2(Pack4(ub[0], ub[1], ub[2], ub[3]), Pack4(ub[4], ub[5], ub[6], ub[7]));
-                    vv = make_uint2(Pack4(vb[0], vb[1], vb[2], vb[3]), Pack4(vb[4], vb[5], vb[6], vb[7]));
-                }
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t yw = h ? yy.y : yy.x;
-                    uint32_t r[4], g[4], b[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const float fy = ByteF(yw, i);
-                        float fu, fv;
-                        if (pair) {
-                            fu = ByteF(uu.x, 2 * h + (i >> 1)) - 128.0f;
-                            fv = ByteF(vv.x, 2 * h + (i >> 1)) - 128.0f;
-                        } else {
-                            fu = ByteF(h ? uu.y : uu.x, i) - 128.0f;
-                            fv = ByteF(h ? vv.y : vv.x, i) - 128.0f;
-                        }
-                        r[i] = PackU8(fmaf(1.5748f, fv, fy));
-                        g[i] = PackU8(fmaf(-0.4681f, fv, fmaf(-0.1873f, fu, fy)));
-                        b[i] = PackU8(fmaf(1.8556f, fu, fy));
-                    }
-                    const uint32_t rw = Pack4(r[0], r[1], r[2], r[3]), gw = Pack4(g[0], g[1], g[2], g[3]),
-                                   bw = Pack4(b[0], b[1], b[2], b[3]);
-                    if (h) { R.y = rw; G.y = gw; B.y = bw; } else { R.x = rw; G.x = gw; B.x = bw; }
-                }
-            }
-        }
-        if (fmt == FMT_RGB) {
-            uint8_t* dst = od.dst[0] + size_t(y) * od.dst_pitch[0] + size_t(xt) * 3;
-            const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
-            if (have) {
-                // interleave R,G,B bytes: 8 pixels -> 6 words
-                uint32_t w[6];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t r = h ? R.y : R.x, g = h ? G.y : G.x, b = h ? B.y : B.x;
-                    w[3 * h + 0] = __byte_perm(__byte_perm(r, g, 0x1040), b, 0x3410);   // r0 g0 b0 r1
-                    w[3 * h + 1] = __byte_perm(__byte_perm(g, b, 0x2051), r, 0x3610);   // g1 b1 r2 g2
-                    w[3 * h + 2] = __byte_perm(__byte_perm(b, r, 0x3702), g, 0x3720);   // b2 r3 g3 b3
-                }
-                uint8_t* o = buf + phase + lane * 24;
-                if ((phase & 3) == 0 && lane * 8 + 8 <= nx) {
-#pragma unroll
-                    for (int k = 0; k < 6; k++) reinterpret_cast<uint32_t*>(o)[k] = w[k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 24; k++)
-                        if (lane * 8 + k / 3 < nx) o[k] = uint8_t((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
-                }
-            }
-            __syncwarp();
-            FlushRow(buf, phase, dst, nx * 3, lane);
-        } else {
-            // all three planes use pitch[0] (src/rocjpeg_decoder.cpp:526-544)
-            uint8_t* dst[3];
-            int phase[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                dst[c] = od.dst[c] + size_t(y) * od.dst_pitch[0] + xt;
-                phase[c] = int(reinterpret_cast<uintptr_t>(dst[c]) & 15);
-                Stage8(buf + c * kChanBuf, phase[c], lane, nx, c == 0 ? R : c == 1 ? G : B);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < 3; c++) FlushRow(buf + c * kChanBuf, phase[c], dst[c], nx, lane);
+        if (fmt == FMT_RGB && (j.dst[0] == nullptr || j.dpitch[0] == 0)) return;
+        if (fmt == FMT_RGB_PLANAR && (!j.dst[0] || !j.dst[1] || !j.dst[2] || j.dpitch[0] == 0)) return;
+        for (int r = warp; r < kTileH; r += kWarps) {
+            const int y = ty * kTileH + r;
+            if (y >= H) break;
+            RowRgb(j, sx, sy, gray, buf, y, lane);
         }
         return;
     }
@@ -247,46 +276,58 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
     if (native && css == CSS_422) {
         // packed YUYV: byte k of the surface row is Y[k>>1] (k even), U[k>>2] (k%4==1), V[k>>2] (k%4==3);
         // the caller's row starts at surface byte 2*left (src/rocjpeg_decoder.cpp:384-388)
-        if (y >= H || nx <= 0 || od.dst[0] == nullptr || od.dst_pitch[0] == 0) return;
-        const int Y = y0 + y;
-        uint8_t* dst = od.dst[0] + size_t(y) * od.dst_pitch[0] + size_t(xt) * 2;
-        const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
-        const uint8_t* yrow = pl.p[0] + size_t(Y) * pl.pitch[0];
-        const uint8_t* urow = pl.p[1] + size_t(Y) * pl.pitch[1];
-        const uint8_t* vrow = pl.p[2] + size_t(Y) * pl.pitch[2];
-        const int n = nx * 2;
-        for (int j = lane; j < n; j += 32) {
-            const int k = 2 * (x0 + xt) + j;
-            uint8_t v;
-            if ((k & 1) == 0) v = __ldg(yrow + (k >> 1));
-            else v = (k & 2) ? __ldg(vrow + (k >> 2)) : __ldg(urow + (k >> 2));
-            buf[phase + j] = v;
+        if (j.dst[0] == nullptr || j.dpitch[0] == 0) return;
+        for (int r = warp; r < kTileH; r += kWarps) {
+            const int y = ty * kTileH + r;
+            if (y >= H) break;
+            const int Y = y0 + y;
+            uint8_t* dst = j.dst[0] + size_t(y) * j.dpitch[0] + size_t(xt) * 2;
+            const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
+            const uint8_t* yrow = j.p[0] + size_t(Y) * j.pitch[0];
+            const uint8_t* urow = j.p[1] + size_t(Y) * j.pitch[1];
+            const uint8_t* vrow = j.p[2] + size_t(Y) * j.pitch[2];
+            const int n = nx * 2;
+            for (int b = lane; b < n; b += 32) {
+                const int k = 2 * (x0 + xt) + b;
+                uint8_t v;
+                if ((k & 1) == 0) v = __ldg(yrow + (k >> 1));
+                else v = (k & 2) ? __ldg(vrow + (k >> 2)) : __ldg(urow + (k >> 2));
+                buf[phase + b] = v;
+            }
+            __syncwarp();
+            FlushRow(buf, phase, dst, n, lane);
+            __syncwarp();
         }
-        __syncwarp();
-        FlushRow(buf, phase, dst, n, lane);
         return;
     }
     // luma (every remaining format writes channel 0 = Y)
-    if (y < H && nx > 0 && od.dst[0] != nullptr && od.dst_pitch[0] != 0) {
-        CopyRow(buf, pl.p[0] + size_t(y0 + y) * pl.pitch[0], x0 + xt, od.dst[0] + size_t(y) * od.dst_pitch[0] + xt, nx, lane);
+    if (j.dst[0] != nullptr && j.dpitch[0] != 0) {
+        for (int r = warp; r < kTileH; r += kWarps) {
+            const int y = ty * kTileH + r;
+            if (y >= H) break;
+            CopyRow(buf, j.p[0] + size_t(y0 + y) * j.pitch[0], x0 + xt, j.dst[0] + size_t(y) * j.dpitch[0] + xt, nx, lane);
+        }
     }
     if (fmt == FMT_Y || gray) return;
     if (native && css == CSS_420) {
         // interleaved UV rows: surface byte k is U[k>>1] (k even) / V[k>>1] (k odd); the caller's row
         // starts at surface byte `left` of chroma row top>>1 (src/rocjpeg_decoder.cpp:380-388)
+        if (j.dst[1] == nullptr || j.dpitch[1] == 0) return;
         const int rows = H >> 1;
-        const int cy = ty * (kTileH / 2) + warp;
-        if (warp < kTileH / 2 && cy < rows && nx > 0 && od.dst[1] != nullptr && od.dst_pitch[1] != 0) {
-            uint8_t* dst = od.dst[1] + size_t(cy) * od.dst_pitch[1] + xt;
+        for (int r = warp; r < kTileH / 2; r += kWarps) {
+            const int cy = ty * (kTileH / 2) + r;
+            if (cy >= rows) break;
+            uint8_t* dst = j.dst[1] + size_t(cy) * j.dpitch[1] + xt;
             const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
-            const uint8_t* urow = pl.p[1] + size_t((y0 >> 1) + cy) * pl.pitch[1];
-            const uint8_t* vrow = pl.p[2] + size_t((y0 >> 1) + cy) * pl.pitch[2];
-            for (int j = lane; j < nx; j += 32) {
-                const int k = x0 + xt + j;
-                buf[phase + j] = (k & 1) ? __ldg(vrow + (k >> 1)) : __ldg(urow + (k >> 1));
+            const uint8_t* urow = j.p[1] + size_t((y0 >> 1) + cy) * j.pitch[1];
+            const uint8_t* vrow = j.p[2] + size_t((y0 >> 1) + cy) * j.pitch[2];
+            for (int b = lane; b < nx; b += 32) {
+                const int k = x0 + xt + b;
+                buf[phase + b] = (k & 1) ? __ldg(vrow + (k >> 1)) : __ldg(urow + (k >> 1));
             }
             __syncwarp();
             FlushRow(buf, phase, dst, nx, lane);
+            __syncwarp();
         }
         return;
     }
@@ -295,15 +336,15 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
     // (src/rocjpeg_decoder.cpp:589-590, 596-597, 600-601).
     const int cw = W >> sx, ch = H >> sy;
     const int rows_per_tile = kTileH >> sy, cols_per_tile = kTileW >> sx;
-    const int cxt = tx * cols_per_tile;
+    const int cxt = (xt >> sx);
     const int cn = min(cols_per_tile, cw - cxt);
-    for (int task = warp; task < 2 * rows_per_tile; task += kTileH) {
-        const int c = 1 + task / rows_per_tile;
-        const int cy = ty * rows_per_tile + task % rows_per_tile;
-        const uint32_t pitch = (sx == 0) ? od.dst_pitch[c] : od.dst_pitch[1];
-        if (cy >= ch || cn <= 0 || od.dst[c] == nullptr || pitch == 0) continue;
-        CopyRow(buf, pl.p[c] + size_t((y0 >> sy) + cy) * pl.pitch[c], (x0 >> sx) + cxt,
-                od.dst[c] + size_t(cy) * pitch + cxt, cn, lane);
+    if (cn <= 0) return;
+    for (int task = warp; task < 2 * rows_per_tile; task += kWarps) {
+        const int c = 1 + (task >= rows_per_tile ? 1 : 0);
+        const int cy = ty * rows_per_tile + (task >= rows_per_tile ? task - rows_per_tile : task);
+        const uint32_t pitch = (sx == 0) ? j.dpitch[c] : j.dpitch[1];
+        if (cy >= ch || j.dst[c] == nullptr || pitch == 0) continue;
+        CopyRow(buf, j.p[c] + size_t((y0 >> sy) + cy) * j.pitch[c], (x0 >> sx) + cxt, j.dst[c] + size_t(cy) * pitch + cxt, cn, lane);
     }
 }
 

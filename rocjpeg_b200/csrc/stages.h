@@ -17,6 +17,8 @@ namespace rjb {
 constexpr int kK1Threads = 128;      // subsequences per CTA in K1
 constexpr int kDcTileMcus = 256;     // MCUs per DC-scan tile
 constexpr int kMaxSyncRounds = 8;    // counters kept per batch
+constexpr int kK3TileW = 256;        // output tile of the colour/layout stage, in luma samples
+constexpr int kK3TileH = 32;
 
 struct K1Args {
     const ImageDesc* images;      // device
