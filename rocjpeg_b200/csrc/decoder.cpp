@@ -211,7 +211,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     stats_.sub_bytes = S;
 
     needs_clear_ = false;
-    uint64_t scan_off = 0, blk = 0, plane_off = 0;
+    uint64_t scan_off = 0, blk = 0, plane_off = 0, ent = 0;
     uint32_t sub = 0, dctile = 0, k2tile = 0, k3tile = 0, chunk = 0;
     all_pinned_ = true;
     for (int i = 0; i < n; i++) {
@@ -277,6 +277,11 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         im.blk0 = blk;
         im.nblocks = uint32_t(im.total_mcus) * uint32_t(p.bpm);
         blk += im.nblocks;
+        // entry arena: every entry consumes at least min_entry_bits of the scan, and a block holds at most 64
+        im.ent0 = ent;
+        // (+3 padding entries per subsequence: every thread's run is rounded up to whole 16-byte stores)
+        im.ent_cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 3 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
+        ent += (uint64_t(im.ent_cap) + 63) & ~uint64_t(63);
         im.dc_tile0 = dctile;
         h_img_dctile0_[size_t(i)] = dctile;
         dctile += uint32_t((im.total_mcus + kDcTileMcus - 1) / kDcTileMcus);
@@ -320,6 +325,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     gather_chunks_ = chunk;
     scan_bytes_ = scan_off;
     coef_blocks_ = blk;
+    entry_count_ = ent;
     plane_bytes_ = plane_off;
     nsub_total_ = sub;
     stats_.scan_bytes = scan_off;
@@ -378,7 +384,10 @@ int Lane::Upload(cudaStream_t up) {
 
     RJB_CUDA(d_desc_.Reserve(L.total));
     RJB_CUDA(d_scan_.Reserve(scan_bytes_ + 512));
-    RJB_CUDA(d_coef_.Reserve(coef_blocks_ * 128 + 256));
+    RJB_CUDA(d_entries_.Reserve(entry_count_ * 4 + 256));
+    RJB_CUDA(d_blkent_.Reserve(coef_blocks_ * 8 + 256));
+    RJB_CUDA(d_nnz_.Reserve(nsub_total_ * 4 + 256));
+    RJB_CUDA(d_cta_entries_.Reserve(size_t(k1_.total_ctas) * 4 + 256));
     RJB_CUDA(d_dcdiff_.Reserve(coef_blocks_ * 2 + 256));
     RJB_CUDA(d_planes_.Reserve(plane_bytes_ + 512));
     RJB_CUDA(d_state_.Reserve(nsub_total_ * 4 + 256));
@@ -402,12 +411,16 @@ int Lane::Upload(cudaStream_t up) {
     k1_.cta_partial = d_cta_partial_.as<uint2>();
     k1_.dc_partial = d_dc_partial_.as<int3>();
     k1_.counters = d_counters_.as<uint32_t>();
-    k1_.coef = d_coef_.as<int16_t>();
+    k1_.entries = d_entries_.as<uint32_t>();
+    k1_.blk_ent = d_blkent_.as<uint32_t>();
+    k1_.nnz = d_nnz_.as<uint32_t>();
+    k1_.cta_entries = d_cta_entries_.as<uint32_t>();
     k1_.dcdiff = d_dcdiff_.as<int16_t>();
     k2_.images = k1_.images;
     k2_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k2tile0);
     k2_.qtables = reinterpret_cast<const uint16_t*>(d + L.qtables);
-    k2_.coef = k1_.coef;
+    k2_.entries = k1_.entries;
+    k2_.blk_ent = k1_.blk_ent;
     k2_.dc = k1_.dcdiff;
     k2_.planes = d_planes_.as<uint8_t>();
     k3_.images = k1_.images;
@@ -445,12 +458,10 @@ int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up) {
         if (st != kSuccess) return st;
     }
     RJB_CUDA(mark(1));
-    // the coefficient arena is NOT cleared: k1_write stores every block as a whole line
-    // (except for damaged streams with restart intervals that carry no data at all)
-    if (needs_clear_) {
-        RJB_CUDA(cudaMemsetAsync(d_coef_.as<uint8_t>(), 0, coef_blocks_ * 128, stream_));
-        RJB_CUDA(cudaMemsetAsync(d_dcdiff_.as<uint8_t>(), 0, coef_blocks_ * 2, stream_));
-    }
+    // Per-block entry indices start as "never decoded" (4 bytes per block; the entry arena itself is
+    // never cleared): blocks a damaged stream does not reach then decode as zero.
+    RJB_CUDA(cudaMemsetAsync(d_blkent_.as<uint8_t>(), 0xFF, coef_blocks_ * 8, stream_));
+    if (needs_clear_) RJB_CUDA(cudaMemsetAsync(d_dcdiff_.as<uint8_t>(), 0, coef_blocks_ * 2, stream_));
     RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint8_t>(), 0, 256, stream_));
     RJB_CUDA(mark(2));
     for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
@@ -464,7 +475,7 @@ int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up) {
     RJB_CUDA(mark(6));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + 1 + 2 + 1 + 1 + 1;   // + the counter memset
+    stats_.kernel_launches += uint32_t(rounds) + 1 + 2 + 1 + 1 + 2;   // + the two memsets
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), d_counters_.as<uint8_t>(), 256, cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256;
     return kSuccess;
@@ -491,6 +502,7 @@ int Lane::Finish(bool profiling_) {
             if (cnt[slot] == 0) break;
             if (++guard > k1_.total_ctas + 2) return Fail(kExecutionFailed, "entropy decoder failed to converge");
         }
+        RJB_CUDA(cudaMemsetAsync(d_blkent_.as<uint8_t>(), 0xFF, coef_blocks_ * 8, stream_));
         RJB_CUDA(LaunchK1Write(k1_, stream_));
         RJB_CUDA(LaunchDcScan(k1_, stream_));
         RJB_CUDA(LaunchK2Idct(k2_, stream_));
@@ -665,10 +677,21 @@ int Lane::CopyCoefficients(int image, int16_t* host_out, size_t count) {
     size_t need = 0;
     for (int c = 0; c < im.ncomp; c++) need += size_t(im.blocks_w[c]) * im.blocks_h[c] * 64;
     if (count < need) return kInvalidParameter;
-    std::vector<int16_t> tmp(size_t(im.nblocks) * 64), dc(im.nblocks);
-    RJB_CUDA(cudaMemcpy(tmp.data(), d_coef_.as<int16_t>() + size_t(im.blk0) * 64, tmp.size() * 2, cudaMemcpyDeviceToHost));
+    // densify the sparse stream on the host: decode-order blocks of 64 int16, natural order
+    static const uint8_t kZz[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    std::vector<int16_t> tmp(size_t(im.nblocks) * 64, 0), dc(im.nblocks);
+    std::vector<uint32_t> be(size_t(im.nblocks) * 2), ents(im.ent_cap);
+    RJB_CUDA(cudaMemcpy(be.data(), d_blkent_.as<uint32_t>() + 2 * im.blk0, be.size() * 4, cudaMemcpyDeviceToHost));
+    RJB_CUDA(cudaMemcpy(ents.data(), d_entries_.as<uint32_t>() + im.ent0, ents.size() * 4, cudaMemcpyDeviceToHost));
     RJB_CUDA(cudaMemcpy(dc.data(), d_dcdiff_.as<int16_t>() + im.blk0, dc.size() * 2, cudaMemcpyDeviceToHost));
-    for (size_t b = 0; b < dc.size(); b++) tmp[b * 64] = dc[b];   // DC lives in the compact per-block array
+    for (size_t b = 0; b < dc.size(); b++) {
+        uint32_t e0 = be[2 * b], e1 = be[2 * b + 1];
+        if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > im.ent_cap) e0 = e1 = 0;
+        for (uint32_t k = e0; k < e1; k++) tmp[b * 64 + kZz[(ents[k] >> 16) & 63u]] = int16_t(ents[k] & 0xFFFFu);
+        tmp[b * 64] = dc[b];   // integrated DC lives in the compact per-block array
+    }
     size_t base = 0;
     for (int c = 0; c < im.ncomp; c++) {
         const int H = im.hs[c], V = im.vs[c];

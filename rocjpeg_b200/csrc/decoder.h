@@ -127,12 +127,12 @@ class Lane {
     K3Args k3_ = {};
     uint32_t gather_chunks_ = 0;
     bool all_pinned_ = false, needs_clear_ = false;
-    size_t scan_bytes_ = 0, coef_blocks_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
+    size_t scan_bytes_ = 0, coef_blocks_ = 0, entry_count_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
 
     StagingBuffer h_desc_;        // pinned descriptor block
     size_t desc_bytes_ = 0;
     StagingBuffer h_counters_;    // pinned read-back
-    DeviceBuffer d_desc_, d_scan_, d_coef_, d_dcdiff_, d_planes_, d_state_, d_used_, d_subseg_, d_cta_partial_,
+    DeviceBuffer d_desc_, d_scan_, d_entries_, d_blkent_, d_nnz_, d_cta_entries_, d_dcdiff_, d_planes_, d_state_, d_used_, d_subseg_, d_cta_partial_,
         d_dc_partial_, d_counters_;
     BatchStats stats_;
 };

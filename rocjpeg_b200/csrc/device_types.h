@@ -47,10 +47,14 @@ struct ImageDesc {
     uint64_t data_off;                                // byte offset of the image's clean stream in the scan arena
     uint32_t seg0, nseg;                              // this image's slice of the batch segment table
     uint32_t sub0, nsub;                              // first subsequence (multiple of the CTA size) and count
-    // coefficient store: blocks in decode (MCU) order, 64 int16 each, natural order
-    uint64_t blk0;                                    // first block of this image in the batch coefficient arena
+    // coefficient store: a sparse stream of (zig-zag position, int16 value) entries in decode
+    // order plus, per block, the index of its first entry; DC kept in a compact per-block array
+    uint64_t blk0;                                    // first block of this image in the per-block arrays
+    uint64_t ent0;                                    // first entry of this image in the entry arena
+    uint32_t ent_cap;                                 // entries reserved for this image (upper bound from the scan size)
     uint32_t nblocks;
     uint32_t dc_tile0;                                // first DC-scan tile of this image
+    uint32_t pad2_;
     // decoded component planes (MCU-padded), u8
     uint64_t plane_off[3];
     uint32_t plane_pitch[3];

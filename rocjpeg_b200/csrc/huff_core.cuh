@@ -53,9 +53,15 @@ RJB_HD uint32_t ByteSwap32(uint32_t w) {
 
 struct NullSink {
     RJB_HD void Dc(uint32_t, int) const {}
-    RJB_HD void Ac(uint32_t, int, int) const {}
+    RJB_HD void Entry(int, int) const {}
     RJB_HD void EndBlock(uint32_t) const {}
 };
+
+// Coefficient entry of the sparse coefficient stream K1 writes and K2 expands: one 32-bit word
+// per symbol that carries magnitude bits (every non-zero AC coefficient; DC symbols with a
+// non-zero difference too, which K2 ignores in favour of the integrated DC).
+//   bits 0..15  quantised value, int16;   bits 16..21  zig-zag position 0..63
+RJB_HD uint32_t MakeCoefEntry(int pos, int val) { return (uint32_t(val) & 0xFFFFu) | (uint32_t(pos) << 16); }
 
 // First-level table entry (HuffLutSet::fast) and the value SlowEntry() returns (16 bits):
 //   bits 0..4   code length + SSSS = bits the whole symbol consumes (1..31); entry 0 = not in the fast table
@@ -149,13 +155,15 @@ RJB_HD int SymbolValue(uint32_t e, uint32_t win) {
 // subsequence in BIG-endian order (bit 31 = first bit of the stream); the backing store is
 // zero-padded at least 16 bytes past end_bit.
 //   WRITE = false: only the state is tracked (speculation / synchronisation).
-//   WRITE = true : coefficients go to `sink` (Dc / Ac per symbol, EndBlock when a block
-//                  completes); stops early at blk_limit. (The CUDA write pass uses its own
-//                  warp-synchronous loop over the same primitives; this form serves the host model.)
-// On return p >= end_bit (or the block limit was reached); c, z, nb, blk updated.
+//   WRITE = true : `sink` receives Dc(blk, diff) for every DC symbol, Entry(pos, val) for every
+//                  symbol with magnitude bits, EndBlock(blk) when a block completes; stops early
+//                  at blk_limit. (The CUDA kernels run their own lean loops over the same
+//                  primitives; this form serves the host model.)
+// On return p >= end_bit (or the block limit was reached); c, z, nb (blocks completed), nnz
+// (entries produced), blk updated.
 template <bool WRITE, class Loader, class Sink>
 RJB_HD void DecodeSpan(const Loader& load, const HuffLutSet* lut, TableSel sel, int bpm, uint32_t& p, uint32_t end_bit, int& c,
-                       int& z, uint32_t& nb, uint32_t& blk, uint32_t blk_limit, Sink& sink) {
+                       int& z, uint32_t& nb, uint32_t& nnz, uint32_t& blk, uint32_t blk_limit, Sink& sink) {
     if (p >= end_bit) return;
     BitWindow bw;
     bw.Init(load, p);
@@ -165,11 +173,11 @@ RJB_HD void DecodeSpan(const Loader& load, const HuffLutSet* lut, TableSel sel, 
         const uint32_t win = bw.Peek(p);
         const uint32_t e = LookupSymbol(lut, (z == 0) ? dc_off : ac_off, win);
         const int adv = EntryAdvance(e);
-        if (WRITE) {
-            const int val = SymbolValue(e, win);
-            if (z == 0) sink.Dc(blk, val);
-            else if (EntrySize(e) && z + adv <= 64) sink.Ac(blk, z + adv - 1, val);
+        if (EntrySize(e)) {
+            nnz++;
+            if (WRITE) sink.Entry((z + adv - 1) & 63, SymbolValue(e, win));
         }
+        if (WRITE && z == 0) sink.Dc(blk, SymbolValue(e, win));
         z += adv;                                              // EOB advances by 64, ZRL by 16
         p += EntryBits(e);
         bw.Advance(load, p);

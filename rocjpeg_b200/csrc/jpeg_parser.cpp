@@ -324,6 +324,21 @@ void StreamParser::BuildDecodeTables() {
         mix(p_.ac[t].vals, p_.ac[t].count);
     }
     p_.lut_hash = h;
+    // Shortest symbol that carries magnitude bits: code length + SSSS. Bounds how many
+    // coefficient entries a scan of a given size can produce.
+    uint32_t min_bits = 32;
+    for (int t = 0; t < 2; t++)
+        for (int is_ac = 0; is_ac < 2; is_ac++) {
+            const HuffSpec& sp = is_ac ? p_.ac[t] : p_.dc[t];
+            if (!sp.present) continue;
+            uint32_t k = 0;
+            for (uint32_t l = 1; l <= 16; l++)
+                for (uint32_t i = 0; i < sp.bits[l - 1] && k < 256; i++, k++) {
+                    const uint32_t sz = sp.vals[k] & 15u;
+                    if (sz && l + sz < min_bits) min_bits = l + sz;
+                }
+        }
+    p_.min_entry_bits = min_bits < 2 ? 2 : (min_bits > 31 ? 2 : min_bits);
     const bool same = lut_valid_ && h == lut_spec_hash_ && std::memcmp(lut_spec_dc_, p_.dc, sizeof(p_.dc)) == 0 &&
                       std::memcmp(lut_spec_ac_, p_.ac, sizeof(p_.ac)) == 0;
     if (!same) {

@@ -80,6 +80,7 @@ struct ParsedJpeg {
     int32_t support_status = 0;                   // RocJpegStatus value: 0 when the CUDA path can decode it
     uint16_t qt_natural[4][64] = {};              // de-zig-zagged quantiser steps
     uint64_t lut_hash = 0;                        // identity of the four Huffman tables (batch de-duplication)
+    uint32_t min_entry_bits = 2;                  // fewest bits a symbol with magnitude bits can take (bounds the entry count)
     std::vector<Segment> segments;                // one per restart interval (exactly ceil(mcus / Ri))
     size_t clean_bytes = 0;                       // bytes used in `clean`
     uint32_t restart_markers_seen = 0;

@@ -26,24 +26,23 @@
 //                     the last round; a non-zero value triggers more rounds
 //                     (correctness never depends on the stream synchronising).
 //   k1_write          block positions = segmented prefix sums of the per-thread
-//                     block counts (CTA scan + look-back over CTA partials), then
-//                     the final decode assembles each block in shared memory and
-//                     stores it as one whole 128-byte line of int16 coefficients
-//                     (natural order), plus one DC difference per block.
+//                     block counts, entry offsets = prefix sums of the per-thread
+//                     entry counts (CTA scan + look-back over CTA partials); the
+//                     final decode then writes the image's sparse coefficient stream
+//                     (one 32-bit (position, int16 value) entry per non-zero
+//                     coefficient), the index of every block's first entry, and one
+//                     DC difference per block.
 //   dc_sums/dc_apply  per-component, per-restart-interval prefix sum of the DC
 //                     differences; the absolute DC replaces the difference in the
 //                     compact per-block DC array that K2 reads.
 #include <cuda_runtime.h>
 
+#include <cstddef>
+
 #include "huff_core.cuh"
 #include "stages.h"
 
 namespace rjb {
-
-__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
-                                     12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
-                                     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
-                                     58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 namespace {
 
@@ -64,17 +63,6 @@ struct SmemLoader {
     const uint32_t* base;
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return base[i]; }
 };
-// Write pass: words of the thread's own slot come from shared memory; past it (finishing an
-// owned block beyond the subsequence) they come straight from the scan arena.
-struct SlotOrGlobalLoader {
-    const uint32_t* slot;
-    const uint32_t* gbase;
-    uint32_t slot_words;
-    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
-        return i < slot_words ? slot[i] : ByteSwap32(__ldg(gbase + i));
-    }
-};
-
 // ---- lean shared-memory primitives for the two hot loops ---------------------------------
 // Both K1 loops are instruction-issue bound (profiles/r01b_*), so they are written against raw
 // 32-bit shared-memory addresses: no generic-address arithmetic, no window registers to rotate
@@ -98,6 +86,23 @@ __device__ __forceinline__ uint32_t Lds8(uint32_t a) {
 }
 __device__ __forceinline__ void Sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// Codes longer than the first-level table, without a search loop and without generic loads: the six
+// length thresholds are fetched at once, the code length is a count of comparisons
+// (huff_core.cuh: SlowEntry is the same computation written as a loop, for the host model).
+// With 32 lanes per warp some lane takes this path in roughly every second step, so its latency
+// is paid by the whole warp.
+__device__ __forceinline__ uint32_t SlowEntryShared(uint32_t lutset_sa, uint32_t tab, uint32_t v16) {
+    const uint32_t up = lutset_sa + uint32_t(offsetof(HuffLutSet, upper)) + tab * 68u + 4u * (kFastBits + 1);
+    static_assert(kFastBits == 10, "six lengths (11..16) are searched");
+    const uint32_t u11 = Lds32(up), u12 = Lds32(up + 4), u13 = Lds32(up + 8), u14 = Lds32(up + 12), u15 = Lds32(up + 16),
+                   u16 = Lds32(up + 20);
+    const uint32_t len = 11u + (v16 >= u11) + (v16 >= u12) + (v16 >= u13) + (v16 >= u14) + (v16 >= u15);
+    if (v16 >= u16) return MakeEntry(16, 0, tab >= 2);   // invalid code: 16 bits consumed, symbol 0
+    const int32_t voff = int32_t(Lds32(lutset_sa + uint32_t(offsetof(HuffLutSet, valoff)) + tab * 68u + 4u * len));
+    const uint32_t sym = Lds8(lutset_sa + uint32_t(offsetof(HuffLutSet, vals)) + tab * 256u + (uint32_t(int32_t(v16 >> (16u - len)) + voff) & 255u));
+    return MakeEntry(len, sym, tab >= 2);
+}
+
 // Next 32 bits of the stream at bit position p of the slot at shared address `slot`.
 __device__ __forceinline__ uint32_t PeekBits(uint32_t slot, uint32_t p) {
     const uint32_t a = slot + ((p >> 5) << 2);
@@ -108,19 +113,20 @@ __device__ __forceinline__ uint32_t DcBytes(TableSel t, int c) { return ((t.dc_m
 __device__ __forceinline__ uint32_t AcBytes(TableSel t, int c) { return (2u + ((t.ac_mask >> c) & 1u)) << (kFastBits + 1); }
 
 // Count-only decode of one subsequence from state `key` (speculation / synchronisation):
-// returns the packed end state and block count.
-__device__ __forceinline__ uint32_t DecodeCount(uint32_t slot, uint32_t lut_sa, const HuffLutSet* lut, TableSel sel, int bpm,
-                                                uint32_t key, uint32_t end_bit) {
-    uint32_t p = StateOverflow(key), nb = 0;
+// returns the packed end state + block count, and the number of coefficient entries in *nnz.
+__device__ __forceinline__ uint32_t DecodeCount(uint32_t slot, uint32_t lut_sa, TableSel sel, int bpm, uint32_t key,
+                                                uint32_t end_bit, uint32_t* nnz_out) {
+    uint32_t p = StateOverflow(key), nb = 0, nnz = 0;
     int c = StateC(key), z = StateZ(key);
     uint32_t dc_off = DcBytes(sel, c), ac_off = AcBytes(sel, c);
     uint32_t off = (z == 0) ? dc_off : ac_off;
     while (p < end_bit) {
         const uint32_t win = PeekBits(slot, p);
         uint32_t e = Lds16(lut_sa + off + ((win >> (31 - kFastBits)) & (2u * kFastSize - 2u)));
-        if (e == 0) e = SlowEntry(lut, off >> (kFastBits + 1), win >> 16);
+        if (e == 0) e = SlowEntryShared(lut_sa, off >> (kFastBits + 1), win >> 16);
         p += EntryBits(e);
         z += EntryAdvance(e);
+        nnz += (e & (15u << 5)) ? 1u : 0u;
         off = ac_off;
         if (z >= 64) {
             z = 0;
@@ -131,13 +137,10 @@ __device__ __forceinline__ uint32_t DecodeCount(uint32_t slot, uint32_t lut_sa, 
             off = dc_off;
         }
     }
+    *nnz_out = (nnz + 3u) & ~3u;   // a thread's run of the entry stream is padded to whole 16-byte stores
     const uint32_t over = p > end_bit ? p - end_bit : 0;
     return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
 }
-
-constexpr int kBlkBufBytes = 144;    // one staged block: 128 B + 16 (keeps 16-byte alignment)
-constexpr int kLaneBufBytes = 2 * kBlkBufBytes + 8;   // two blocks per lane; 74-word lane stride spreads the banks
-constexpr int kFlushEvery = 8;       // symbols decoded per lane between two cooperative flushes
 
 // Per-thread description of its subsequence.
 struct Sub {
@@ -195,17 +198,11 @@ struct K1Smem {
     uint64_t start[T];
     uint32_t state[T];
     uint32_t used[T];
+    uint32_t nnz[T];
     uint32_t endbit[T];
     uint32_t queue[T];
     uint8_t mcu_dc[16], mcu_ac[16];
-    uint8_t zigzag[64];
     uint32_t scratch[40];
-};
-
-template <int S>
-struct K1WriteSmem {
-    K1Smem<S> k;
-    __align__(16) unsigned char blkbuf[T * kLaneBufBytes];
 };
 
 template <int S>
@@ -222,7 +219,6 @@ __device__ __forceinline__ void StageCta(K1Smem<S>& sm, const K1Args& a, const I
         sm.mcu_dc[tid] = tid < kMaxBlocksPerMcu ? im.mcu_dc[tid] : 0;
         sm.mcu_ac[tid] = tid < kMaxBlocksPerMcu ? im.mcu_ac[tid] : 2;
     }
-    if (tid < 64) sm.zigzag[tid] = c_zigzag[tid];
     __syncthreads();
     constexpr int V = K1Smem<S>::kSlotVecs;
     for (int idx = tid; idx < T * V; idx += T) {
@@ -267,12 +263,16 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     const int bpm = im.bpm;
     const uint32_t slots_sa = SharedAddr(sm.words);
     const uint32_t lut_sa = SharedAddr(&sm.lut.fast[0][0]);
-    auto decode = [&](uint32_t sub, uint32_t key) {
-        return DecodeCount(slots_sa + sub * uint32_t(K1Smem<S>::kSlotStride * 4), lut_sa, &sm.lut, sel, bpm, key, sm.endbit[sub]);
+    auto decode = [&](uint32_t sub, uint32_t key) {   // result state returned, entry count left in sm.nnz[sub]
+        uint32_t n;
+        const uint32_t st = DecodeCount(slots_sa + sub * uint32_t(K1Smem<S>::kSlotStride * 4), lut_sa, sel, bpm, key, sm.endbit[sub], &n);
+        sm.nnz[sub] = n;
+        return st;
     };
 
     uint32_t ndecodes = 0;
     sm.endbit[tid] = me.end_bit;
+    sm.nnz[tid] = (round > 0 && me.active) ? a.nnz[g] : 0u;
     if (tid == 0) sm.scratch[0] = 0;   // work-queue length
     __syncthreads();
     if (round == 0 && me.active) {
@@ -320,9 +320,11 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     __syncthreads();
     out = sm.state[tid];
     my_used = sm.used[tid];
+    const uint32_t my_nnz = sm.nnz[tid];
     if (me.active) {
         a.state[g] = out;
         a.used[g] = my_used;
+        a.nnz[g] = my_nnz;
     }
     // A change of the state handed to the next CTA means that CTA must look again.
     const bool hands_over = me.active && !me.last && (tid == T - 1);
@@ -339,6 +341,12 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     if (me.active && (last_first == 0 || uint32_t(tid) + 1u >= last_first)) atomicAdd(&red[1], StateBlocks(out));
     __syncthreads();
     if (tid == 0) a.cta_partial[cta] = make_uint2(last_first != 0 ? 1u : 0u, red[1]);
+    // entries produced by the CTA (plain sum: entry offsets run through the whole image)
+    if (tid == 0) red[2] = 0;
+    __syncthreads();
+    if (me.active && my_nnz) atomicAdd(&red[2], my_nnz);
+    __syncthreads();
+    if (tid == 0) a.cta_entries[cta] = red[2];
 }
 
 // ---------------------------------------------------------------- k1_write
@@ -346,197 +354,149 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
 template <int S>
 __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K1WriteSmem<S>& wsm = *reinterpret_cast<K1WriteSmem<S>*>(smem_raw);
-    K1Smem<S>& sm = wsm.k;
+    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t cta = blockIdx.x;
     const uint32_t img = UpperIndex(a.img_cta0, uint32_t(a.nimages), cta);
     const ImageDesc& im = a.images[img];
     const uint32_t g = cta * T + tid;
     const Sub me = Locate<S>(a, im, g, true);
-    {   // zero the block buffers
-        uint32_t* zb = reinterpret_cast<uint32_t*>(wsm.blkbuf);
-        for (int i = tid; i < T * kLaneBufBytes / 4; i += T) zb[i] = 0;
-    }
     StageCta<S>(sm, a, im, me);
 
     const uint32_t st = me.active ? a.state[g] : 0;
     const uint32_t nb = StateBlocks(st);
-    // inclusive segmented scan of nb over the CTA (a segment start resets the sum)
-    uint32_t v = nb;
+    const uint32_t my_nnz = me.active ? a.nnz[g] : 0;
+    // Two scans over the CTA: block positions (segmented: a segment start resets the count) and
+    // entry offsets (plain, they run through the whole image).
+    uint32_t v = nb, e = my_nnz;
     uint32_t f = (me.active && me.first) ? 1u : 0u;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t pv = __shfl_up_sync(0xFFFFFFFFu, v, d);
         const uint32_t pf = __shfl_up_sync(0xFFFFFFFFu, f, d);
+        const uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, e, d);
         if (lane >= d) {
             if (!f) v += pv;
             f |= pf;
+            e += pe;
         }
     }
-    uint32_t* wsum = sm.scratch;        // [4] warp totals (value of the open segment at warp end)
-    uint32_t* wflag = sm.scratch + 4;   // [4] warp contains a start
-    uint32_t* carry_s = sm.scratch + 8; // look-back result
-    if (lane == 31) { wsum[warp] = v; wflag[warp] = f; }
-    // look-back over previous CTAs of the same image (warp 0), in parallel with the scan above
+    uint32_t* wsum = sm.scratch;          // [4] warp totals (value of the open segment at warp end)
+    uint32_t* wflag = sm.scratch + 4;     // [4] warp contains a start
+    uint32_t* wents = sm.scratch + 8;     // [4] warp entry totals
+    uint32_t* carry_s = sm.scratch + 12;  // [2] look-back results: blocks, entries
+    if (lane == 31) { wsum[warp] = v; wflag[warp] = f; wents[warp] = e; }
+    // look-back over previous CTAs of the same image (warp 0)
     if (warp == 0) {
-        uint32_t carry = 0;
+        uint32_t carry = 0, ecarry = 0;
         const uint32_t first_cta = a.img_cta0[img];
-        int64_t k = int64_t(cta) - 1;
         bool done = false;
-        while (!done && k >= int64_t(first_cta)) {
+        for (int64_t k = int64_t(cta) - 1; k >= int64_t(first_cta); k -= 32) {
             const int64_t idx = k - lane;
             uint2 part = make_uint2(0u, 0u);
-            if (idx >= int64_t(first_cta)) part = a.cta_partial[idx];
-            const uint32_t flagged = __ballot_sync(0xFFFFFFFFu, part.x != 0);
-            const int stop = flagged ? __ffs(flagged) - 1 : 31;   // nearest CTA (smallest lane) holding a start
-            uint32_t contrib = (lane <= stop) ? part.y : 0u;
+            uint32_t ents = 0;
+            if (idx >= int64_t(first_cta)) {
+                part = a.cta_partial[idx];
+                ents = a.cta_entries[idx];
+            }
+            if (!done) {
+                const uint32_t flagged = __ballot_sync(0xFFFFFFFFu, part.x != 0);
+                const int stop = flagged ? __ffs(flagged) - 1 : 31;   // nearest CTA (smallest lane) holding a start
+                uint32_t contrib = (lane <= stop) ? part.y : 0u;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, d);
-            carry += contrib;
-            done = flagged != 0;
-            k -= 32;
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, d);
+                carry += contrib;
+                done = flagged != 0;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) ents += __shfl_xor_sync(0xFFFFFFFFu, ents, d);
+            ecarry += ents;
         }
-        if (lane == 0) carry_s[0] = carry;
+        if (lane == 0) { carry_s[0] = carry; carry_s[1] = ecarry; }
     }
     __syncthreads();
-    // add the totals of earlier warps while the segment is still open
-    uint32_t add = 0;
+    uint32_t add = 0, eadd = carry_s[1];
     bool open = (f == 0);   // no segment start at or before this thread inside its warp
-    for (int w = warp - 1; w >= 0 && open; w--) {
-        add += wsum[w];
-        if (wflag[w]) open = false;
+    for (int w = warp - 1; w >= 0; w--) {
+        eadd += wents[w];
+        if (open) {
+            add += wsum[w];
+            if (wflag[w]) open = false;
+        }
     }
     if (open) add += carry_s[0];
-    const uint32_t incl = v + add;
-    const uint32_t excl = (me.active && me.first) ? 0u : incl - nb;
+    const uint32_t excl = (me.active && me.first) ? 0u : v + add - nb;
+    uint32_t n = e + eadd - my_nnz;   // this thread's first entry, relative to the image
 
-    // ---- final decode. Every block is assembled in shared memory and leaves as one whole
-    // 128-byte line (the coefficient arena needs no clearing and sees no partial-sector
-    // read-modify-write). A block belongs to the thread that decodes its DC symbol: that thread
-    // keeps decoding past the end of its subsequence until the block is complete; a thread that
-    // starts inside a block stays silent (`live` false) until the first block boundary.
-    //
-    // The warp advances in lock-step, one symbol per lane per step, so all 32 lanes execute the
-    // same instruction stream. Each lane owns two block buffers: a finished block is parked
-    // (`pending`) while the lane continues in the other buffer; every kFlushEvery steps the
-    // warp stores all parked blocks cooperatively — 32 lanes x 4 bytes = one coalesced line per
-    // block. A lane that finishes a second block before the rendezvous simply waits for it.
-    SegmentDesc sd = {};
-    if (me.active) sd = a.segments[me.seg];
+    if (!me.active) return;
+    // ---- final decode: every symbol with magnitude bits becomes one 32-bit entry of the
+    // image's coefficient stream, written at its final position (each thread owns a contiguous
+    // run of the stream, so consecutive stores of a lane fill whole sectors in L2); every block
+    // end records where the next block's entries begin; DC differences go to the compact
+    // per-block array. No clearing, no read-modify-write, no ownership hand-over: a thread
+    // decodes exactly the symbols that start inside its subsequence, as in the counting passes.
+    const SegmentDesc sd = a.segments[me.seg];
     uint32_t key = 0;
-    if (me.active && !me.first) key = StateKey(a.state[g - 1]);
+    if (!me.first) key = StateKey(a.state[g - 1]);
     uint32_t p = StateOverflow(key);
     int c = StateC(key), z = StateZ(key);
     uint32_t blk = sd.blk_first + excl;
     const uint32_t limit = sd.blk_first + sd.blk_count;
-    const uint32_t seg_end_bit = me.active ? (sd.nbytes - uint32_t(me.start - sd.data_off)) * 8u : 0u;
-    int16_t* coef = a.coef + size_t(im.blk0) * 64;
+    uint32_t* entries = a.entries + im.ent0;
+    uint32_t* blk_ent = a.blk_ent + 2 * im.blk0;      // (first, end) entry index of every block
     int16_t* dcdiff = a.dcdiff + im.blk0;
-    unsigned char* mybufs = wsm.blkbuf + tid * kLaneBufBytes;
+    const uint32_t ent_cap = im.ent_cap;
     const TableSel sel = MakeTableSel(sm.mcu_dc, sm.mcu_ac, im.bpm);
     const int bpm = im.bpm;
     const uint32_t slot_sa = SharedAddr(sm.words + tid * K1Smem<S>::kSlotStride);
     const uint32_t lut_sa = SharedAddr(&sm.lut.fast[0][0]);
-    const uint32_t zz_sa = SharedAddr(sm.zigzag);
-    const uint32_t bufs_sa = SharedAddr(mybufs);
-    const uint32_t* gwords = reinterpret_cast<const uint32_t*>(a.scan + (me.active ? me.start : 0));
-    bool live = (z == 0);
-    bool finishing = false;                 // past the subsequence, completing an owned block
-    uint32_t stop = me.end_bit;
-    bool done = !me.active || p >= stop || blk >= limit;
-    uint32_t cur_sa = bufs_sa;              // buffer being filled
-    bool pending = false;                   // the other buffer holds a finished block
-    uint32_t pend_blk = 0;
-    uint32_t pend_sa = 0;
+    const uint32_t end_bit = me.end_bit;
+    if (me.first && blk < limit) blk_ent[2 * blk] = n;   // a restart interval's first block starts at this thread's first entry
     uint32_t dc_off = DcBytes(sel, c), ac_off = AcBytes(sel, c);
     uint32_t off = (z == 0) ? dc_off : ac_off;
-    for (;;) {
-#pragma unroll 1
-        for (int step = 0; step < kFlushEvery; step++) {
-            if (!done && z < 64) {
-                const uint32_t wi = p >> 5;
-                uint32_t w0, w1;
-                if (wi + 1 < uint32_t(K1Smem<S>::kSlotWords)) {
-                    w0 = Lds32(slot_sa + (wi << 2));
-                    w1 = Lds32(slot_sa + (wi << 2) + 4);
-                } else {   // finishing an owned block beyond the staged slot: straight from the arena
-                    w0 = ByteSwap32(__ldg(gwords + wi));
-                    w1 = ByteSwap32(__ldg(gwords + wi + 1));
-                }
-                const uint32_t win = __funnelshift_l(w1, w0, p);
-                uint32_t e = Lds16(lut_sa + off + ((win >> (31 - kFastBits)) & (2u * kFastSize - 2u)));
-                if (e == 0) e = SlowEntry(&sm.lut, off >> (kFastBits + 1), win >> 16);
-                const uint32_t sz = EntrySize(e), bits = EntryBits(e);
-                // RECEIVE + EXTEND (T.81 F.2.2.1): magnitude bits moved to the top of t
-                const uint32_t t = win << (bits - sz);
-                const uint32_t extra = __funnelshift_rc(t, 0u, 32u - sz);
-                const int val = int(extra) - ((int(t) < 0) ? 0 : int((1u << sz) - 1u));
-                const int z_old = z;
-                z += EntryAdvance(e);
-                p += bits;
-                if (live) {
-                    if (z_old == 0) dcdiff[blk] = int16_t(val);
-                    else if (sz != 0 && z <= 64) Sts16(cur_sa + 2u * Lds8(zz_sa + uint32_t(z) - 1u), uint32_t(val));
-                }
-                off = ac_off;
-                if (z < 64 && p >= stop) {
-                    if (!finishing && live && p < seg_end_bit) {
-                        finishing = true;   // own the unfinished block: follow it into the next subsequence(s)
-                        stop = seg_end_bit;
-                    } else {
-                        done = true;
-                    }
-                }
-            }
-            if (!done && z >= 64 && !(live && pending)) {   // block complete and a buffer is free
-                if (live) {
-                    pending = true;
-                    pend_blk = blk;
-                    pend_sa = cur_sa;
-                    cur_sa = bufs_sa + (cur_sa == bufs_sa ? uint32_t(kBlkBufBytes) : 0u);
-                }
-                live = true;
-                z = 0;
-                blk++;
-                c = (c + 1 == bpm) ? 0 : c + 1;
-                dc_off = DcBytes(sel, c);
-                ac_off = AcBytes(sel, c);
-                off = dc_off;
-                if (finishing || p >= stop || blk >= limit) done = true;
+    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0, cnt = 0;   // pending entries of the current 16-byte group
+    while (p < end_bit && blk < limit) {
+        const uint32_t win = PeekBits(slot_sa, p);
+        uint32_t en = Lds16(lut_sa + off + ((win >> (31 - kFastBits)) & (2u * kFastSize - 2u)));
+        if (en == 0) en = SlowEntryShared(lut_sa, off >> (kFastBits + 1), win >> 16);
+        const uint32_t sz = EntrySize(en), bits = EntryBits(en);
+        // RECEIVE + EXTEND (T.81 F.2.2.1): magnitude bits moved to the top of t
+        const uint32_t t = win << (bits - sz);
+        const uint32_t extra = __funnelshift_rc(t, 0u, 32u - sz);
+        const int val = int(extra) - ((int(t) < 0) ? 0 : int((1u << sz) - 1u));
+        if (z == 0) dcdiff[blk] = int16_t(val);
+        z += EntryAdvance(en);
+        p += bits;
+        if (sz != 0) {
+            // four entries are collected in registers (oldest in q0) and leave as one 128-bit store:
+            // scattered 4-byte stores were throttling the L1 store path (profiles/r01c_*)
+            q0 = q1; q1 = q2; q2 = q3;
+            q3 = MakeCoefEntry((z - 1) & 63, val);
+            if (++cnt == 4) {
+                if (n + 4 <= ent_cap) *reinterpret_cast<uint4*>(entries + n) = make_uint4(q0, q1, q2, q3);
+                n += 4;
+                cnt = 0;
             }
         }
-        // rendezvous: store every parked block, one coalesced 128-byte line each
-        __syncwarp();
-        uint32_t m = __ballot_sync(0xFFFFFFFFu, pending);
-        while (m) {
-            const int L = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t b = __shfl_sync(0xFFFFFFFFu, pend_blk, L);
-            const uint32_t src = __shfl_sync(0xFFFFFFFFu, pend_sa, L) + 4u * uint32_t(lane);
-            const uint32_t v = Lds32(src);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(src), "r"(0u) : "memory");
-            reinterpret_cast<uint32_t*>(coef + size_t(b) * 64)[lane] = v;
-        }
-        pending = false;
-        __syncwarp();
-        if (!__any_sync(0xFFFFFFFFu, !done)) break;
-    }
-    // Damaged / truncated data only: when the interval's data ends under this thread's hands,
-    // what the interval still owes is written as zero blocks (the arena is never cleared, so
-    // every block must be stored by someone).
-    if (me.active && live && (me.last || p >= seg_end_bit) && blk < limit) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(mybufs + (cur_sa - bufs_sa));
-        if (z != 0) {
-            uint32_t* dst = reinterpret_cast<uint32_t*>(coef + size_t(blk) * 64);
-            for (int i = 0; i < 32; i++) dst[i] = src[i];
+        off = ac_off;
+        if (z >= 64) {
+            z = 0;
             blk++;
+            // [first, end) of the finished block's entries, and the first entry of the next block of the
+            // interval (across a restart boundary the next interval's first thread records its own
+            // start: the counting pass may have taken the padding bits that end an interval for one
+            // more symbol, so that thread's entries can begin one slot further on)
+            blk_ent[2 * (blk - 1) + 1] = n + cnt;
+            if (blk < limit) blk_ent[2 * blk] = n + cnt;
+            c = (c + 1 == bpm) ? 0 : c + 1;
+            dc_off = DcBytes(sel, c);
+            ac_off = AcBytes(sel, c);
+            off = dc_off;
         }
-        for (; blk < limit; blk++) {
-            uint4* dst = reinterpret_cast<uint4*>(coef + size_t(blk) * 64);
-            for (int i = 0; i < 8; i++) dst[i] = make_uint4(0, 0, 0, 0);
-            dcdiff[blk] = 0;
-        }
+    }
+    if (cnt) {   // last, partial group: padded with zero entries (position 0, which K2 overwrites with the DC anyway)
+        for (; cnt < 4; cnt++) { q0 = q1; q1 = q2; q2 = q3; q3 = 0; }
+        if (n + 4 <= ent_cap) *reinterpret_cast<uint4*>(entries + n) = make_uint4(q0, q1, q2, q3);
     }
 }
 
@@ -699,15 +659,9 @@ __global__ void __launch_bounds__(256) gather_scans(const GatherItem* items, int
 
 template <int S>
 cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream) {
-    if (round >= 0) {
-        static_assert(sizeof(K1Smem<S>) <= 48 * 1024, "k1_sync shared memory exceeds the default limit");
-        k1_sync<S><<<a.total_ctas, T, sizeof(K1Smem<S>), stream>>>(a, round);
-    } else {
-        // above the 48 KiB default for S = 128: opt in (per device; cheap, so done on every launch)
-        cudaError_t e = cudaFuncSetAttribute(k1_write<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(K1WriteSmem<S>)));
-        if (e != cudaSuccess) return e;
-        k1_write<S><<<a.total_ctas, T, sizeof(K1WriteSmem<S>), stream>>>(a);
-    }
+    static_assert(sizeof(K1Smem<S>) <= 48 * 1024, "K1 shared memory exceeds the default limit");
+    if (round >= 0) k1_sync<S><<<a.total_ctas, T, sizeof(K1Smem<S>), stream>>>(a, round);
+    else k1_write<S><<<a.total_ctas, T, sizeof(K1Smem<S>), stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -8,9 +8,10 @@
 // jpeg_idct_islow on encoder-produced data (the zero-column shortcuts in
 // libjpeg are arithmetically identical to the general path, so none are taken).
 //
-// HBM-bound integer work on CUDA cores: 128 B read + 64 B written per block
-// (+2 B of DC from the compact per-block array). Mapping: 8 threads per block
-// (one 16-byte coefficient row each -> coalesced 128 B per block), 32
+// Input is K1's sparse coefficient stream: per block the index of its first entry, then one
+// 32-bit (zig-zag position, int16 value) entry per non-zero coefficient, plus the integrated DC
+// from the compact per-block array; the 8 threads of a block scatter the entries (dequantised)
+// into a zeroed shared-memory workspace. Mapping: 8 threads per block, 32
 // horizontally adjacent blocks of one component per tile, kTilesPerCta tiles per
 // CTA, transposes through padded shared memory (bank-conflict free), one 8-byte
 // store per thread = full 32-byte sectors per block row. The kernel was
@@ -24,6 +25,11 @@
 namespace rjb {
 namespace {
 
+__constant__ uint8_t c_zigzag_k2[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                                        12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                                        35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                                        58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
 constexpr int kBlocksPerTile = 32;
 constexpr int kThreads = kBlocksPerTile * 8;
 constexpr int kTilesPerCta = 4;
@@ -31,8 +37,10 @@ constexpr int kTilesPerCta = 4;
 // Everything the 256 threads of a CTA need about one tile (32 adjacent blocks of one block row
 // of one component), resolved once per tile by one thread.
 struct TileInfo {
-    const int16_t* coef;     // image coefficient base (coef + blk0 * 64)
+    const uint32_t* entries; // image's coefficient entries
+    const uint2* blk_ent;    // image's per-block (first, end) entry index
     const int16_t* dc;       // image DC base
+    uint32_t ent_cap;
     const uint16_t* qt;      // natural-order quantiser table of the component
     uint8_t* out;            // plane address of (row by*8, column 0)
     uint32_t pitch;
@@ -89,7 +97,9 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
     // row-wise and the column-wise access of a warp hit 32 distinct banks.
     __shared__ int ws[kBlocksPerTile * 72];
     __shared__ TileInfo s_tile[kTilesPerCta];
+    __shared__ uint8_t s_zigzag[64];
     const int tid = threadIdx.x;
+    if (tid < 64) s_zigzag[tid] = c_zigzag_k2[tid];
     if (tid < kTilesPerCta) {
         // tile -> (image, component, block row, first block column); one search per tile, four
         // lanes in parallel; sampling factors are powers of two, so no division in the hot part
@@ -107,7 +117,9 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
                     const int by = int(t / tiles_x);
                     const int H = im.hs[comp], V = im.vs[comp];
                     const int hs = __ffs(H) - 1, vs = __ffs(V) - 1;
-                    ti.coef = a.coef + size_t(im.blk0) * 64;
+                    ti.entries = a.entries + im.ent0;
+                    ti.blk_ent = reinterpret_cast<const uint2*>(a.blk_ent) + im.blk0;
+                    ti.ent_cap = im.ent_cap;
                     ti.dc = a.dc + im.blk0;
                     ti.qt = a.qtables + size_t(im.qt_index[comp]) * 64;
                     ti.pitch = im.plane_pitch[comp];
@@ -135,19 +147,27 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
         if (ti.nbx < 0) break;
         const int bx = ti.bx0 + b;
         const bool valid = bx < ti.nbx;
+        // expand the block's sparse entries into the zeroed workspace, dequantising on the way
+        size_t blk = 0;
+        uint32_t e0 = 0, e1 = 0;
         if (valid) {
-            const size_t blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
-            const uint4 cq = __ldg(reinterpret_cast<const uint4*>(ti.coef + blk * 64) + j);
-            const uint4 qq = __ldg(reinterpret_cast<const uint4*>(ti.qt) + j);
-            const uint32_t cw[4] = {cq.x, cq.y, cq.z, cq.w}, qw[4] = {qq.x, qq.y, qq.z, qq.w};
+            blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
             int* row = my + j * 9;
 #pragma unroll
-            for (int w = 0; w < 4; w++) {
-                row[2 * w] = int(int16_t(cw[w] & 0xFFFFu)) * int(qw[w] & 0xFFFFu);
-                row[2 * w + 1] = (int(cw[w]) >> 16) * int(qw[w] >> 16);
-            }
-            if (j == 0) row[0] = int(__ldg(ti.dc + blk)) * int(qw[0] & 0xFFFFu);   // DC comes from the compact array
+            for (int w = 0; w < 8; w++) row[w] = 0;
+            const uint2 range = __ldg(ti.blk_ent + blk);
+            e0 = range.x;
+            e1 = range.y;
+            if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > ti.ent_cap) e1 = e0 = 0;   // never decoded
         }
+        __syncwarp();
+        for (uint32_t k = e0 + uint32_t(j); k < e1; k += 8) {
+            const uint32_t en = __ldg(ti.entries + k);
+            const int nat = s_zigzag[(en >> 16) & 63u];
+            my[(nat >> 3) * 9 + (nat & 7)] = int(int16_t(en & 0xFFFFu)) * int(__ldg(ti.qt + nat));
+        }
+        __syncwarp();
+        if (valid && j == 0) my[0] = int(__ldg(ti.dc + blk)) * int(__ldg(ti.qt));   // integrated DC replaces any DC-difference entry
         __syncwarp();
         int in[8], out[8];
         if (valid) {

@@ -19,6 +19,7 @@ constexpr int kDcTileMcus = 256;     // MCUs per DC-scan tile
 constexpr int kMaxSyncRounds = 8;    // counters kept per batch
 constexpr int kK3TileW = 256;        // output tile of the colour/layout stage, in luma samples
 constexpr int kK3TileH = 32;
+constexpr uint32_t kNoEntry = 0xFFFFFFFFu;   // blk_ent value of a block no thread reached (damaged streams)
 
 struct K1Args {
     const ImageDesc* images;      // device
@@ -30,10 +31,13 @@ struct K1Args {
     uint32_t* state;              // per subsequence: packed out-state | blocks << 16
     uint32_t* used;               // per subsequence: key of the in-state its state was decoded from
     uint32_t* sub_seg;            // per subsequence: segment index (cache)
+    uint32_t* nnz;                // per subsequence: coefficient entries it produces
     uint2* cta_partial;           // per K1 CTA: (has segment start, blocks after the last start)
+    uint32_t* cta_entries;        // per K1 CTA: coefficient entries of the CTA's subsequences
     int3* dc_partial;             // per DC tile: per-component DC sum after the tile's last reset
     uint32_t* counters;           // [kMaxSyncRounds] boundary changes per round, then [kMaxSyncRounds] decodes per round
-    int16_t* coef;                // coefficient arena, 64 int16 per block
+    uint32_t* entries;            // coefficient entry arena (huff_core.cuh: MakeCoefEntry), decode order
+    uint32_t* blk_ent;            // per block: (first, end) index of its entries, relative to the image's stream
     int16_t* dcdiff;              // one DC value per block: difference after k1_write, absolute after dc_apply
     int nimages;
     uint32_t total_ctas;          // K1 CTAs in the batch
@@ -52,7 +56,8 @@ struct K2Args {
     const ImageDesc* images;
     const uint32_t* img_tile0;    // nimages + 1: first IDCT tile of each image
     const uint16_t* qtables;      // natural-order u16[64] tables
-    const int16_t* coef;          // AC coefficients (coefficient 0 of every block is unused)
+    const uint32_t* entries;      // coefficient entries
+    const uint32_t* blk_ent;      // (first, end) entry index of every block (image-relative), kNoEntry when never decoded
     const int16_t* dc;            // absolute DC per block (decode order)
     uint8_t* planes;              // plane arena
     int nimages;

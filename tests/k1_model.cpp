@@ -31,21 +31,22 @@ struct HostLoader {
         return ByteSwap32(w);   // the core reads big-endian words
     }
 };
-// Mirrors CoefSink in k1_huffman.cu: blocks assembled per thread and stored whole by their owner.
+// Mirrors k1_write in k1_huffman.cu: a sparse entry stream per image + per-block first-entry index.
 struct HostSink {
-    int16_t* coef;
+    uint32_t* entries;
+    uint32_t* blk_ent;
     int16_t* dcdiff;
-    int16_t buf[64];
-    bool live;
-    void Dc(uint32_t blk, int v) { if (live) dcdiff[blk] = int16_t(v); }
-    void Ac(uint32_t, int z, int v) { if (live) buf[kZig[z]] = int16_t(v); }
-    void Flush(uint32_t blk) {
-        std::memcpy(coef + size_t(blk) * 64, buf, 128);
-        std::memset(buf, 0, 128);
+    uint32_t n;          // next entry index
+    uint32_t cap;
+    void Dc(uint32_t blk, int v) { dcdiff[blk] = int16_t(v); }
+    void Entry(int pos, int v) {
+        if (n < cap) entries[n] = MakeCoefEntry(pos, v);
+        n++;
     }
+    uint32_t limit, nblocks;
     void EndBlock(uint32_t blk) {
-        if (live) Flush(blk);
-        live = true;
+        blk_ent[2 * blk + 1] = n;
+        if (blk + 1 < limit) blk_ent[2 * (blk + 1)] = n;
     }
 };
 struct SubInfo {
@@ -102,13 +103,14 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     }
     const uint32_t nsub = uint32_t(subs.size());
     const uint32_t nctas = (nsub + T - 1) / T;
-    std::vector<uint32_t> state(nsub, 0), used(nsub, 0);
+    std::vector<uint32_t> state(nsub, 0), used(nsub, 0), nnzv(nsub, 0);
     NullSink nsink;
     auto decode_from = [&](uint32_t g, uint32_t key) {
-        uint32_t pb = StateOverflow(key), nb = 0, blk = 0;
+        uint32_t pb = StateOverflow(key), nb = 0, blk = 0, nnz = 0;
         int c = StateC(key), z = StateZ(key);
         HostLoader ld{clean + subs[g].start};
-        DecodeSpan<false>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, nb, blk, 0xFFFFFFFFu, nsink);
+        DecodeSpan<false>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, nb, nnz, blk, 0xFFFFFFFFu, nsink);
+        nnzv[g] = (nnz + 3u) & ~3u;   // runs are padded to whole 16-byte stores
         uint32_t over = pb > subs[g].end_bit ? pb - subs[g].end_bit : 0;
         return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
     };
@@ -172,8 +174,12 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         cta_tail[cta] = tail;
     }
     const uint32_t nblocks = total_mcus * uint32_t(bpm);
-    // the arena is NOT cleared on the device: start from garbage to prove every block gets stored
-    std::vector<int16_t> coef(size_t(nblocks) * 64, int16_t(0x7777)), dcdiff(nblocks, int16_t(0x7777));
+    // the entry arena is NOT cleared on the device: start from garbage; per-block indices start
+    // as "never decoded"
+    const uint32_t cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 3 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
+    std::vector<uint32_t> entries(cap, 0x77777777u), blk_ent(size_t(nblocks) * 2, 0xFFFFFFFFu);
+    std::vector<int16_t> dcdiff(nblocks, int16_t(0x7777));
+    uint32_t ent_run = 0;
     for (uint32_t cta = 0; cta < nctas; cta++) {
         uint32_t carry = 0;
         for (int64_t kk = int64_t(cta) - 1; kk >= 0; kk--) {
@@ -185,23 +191,29 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
             if (subs[g].first) run = 0;
             const uint32_t excl = run;
             run += StateBlocks(state[g]);
+            const uint32_t n0 = ent_run;
+            ent_run += nnzv[g];
             uint32_t key = subs[g].first ? 0 : StateKey(state[g - 1]);
-            uint32_t pb = StateOverflow(key), cnt = 0;
+            uint32_t pb = StateOverflow(key), cnt = 0, nnz = 0;
             int c = StateC(key), z = StateZ(key);
             uint32_t blk = seg_blk_first[subs[g].seg] + excl;
             const uint32_t limit = seg_blk_first[subs[g].seg] + seg_blk_count[subs[g].seg];
-            HostSink sink{coef.data(), dcdiff.data(), {}, z == 0};
+            HostSink sink{entries.data(), blk_ent.data(), dcdiff.data(), n0, cap, limit, nblocks};
+            if (subs[g].first && blk < limit) blk_ent[2 * blk] = n0;
             HostLoader ld{clean + subs[g].start};
-            DecodeSpan<true>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, cnt, blk, limit, sink);
-            const Segment& sg = p.segments[subs[g].seg];
-            const uint32_t seg_end_bit = (sg.nbytes - uint32_t(subs[g].start - sg.offset)) * 8u;
-            if (sink.live && z != 0 && blk < limit && pb < seg_end_bit)
-                DecodeSpan<true>(ld, &parser.lut(), sel, bpm, pb, seg_end_bit, c, z, cnt, blk, blk + 1, sink);
-            if (sink.live && (subs[g].last || pb >= seg_end_bit) && blk < limit) {
-                if (z != 0) { sink.Flush(blk); blk++; }
-                for (; blk < limit; blk++) { sink.Flush(blk); dcdiff[blk] = 0; }
-            }
+            DecodeSpan<true>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, cnt, nnz, blk, limit, sink);
+            // counting pass and write pass must agree (the last thread of an interval may have counted padding)
+            const uint32_t used_n = (sink.n - n0 + 3u) & ~3u;
+            if (subs[g].last ? used_n > nnzv[g] : used_n != nnzv[g]) return -7;
+            for (uint32_t k2 = sink.n; k2 < n0 + used_n && k2 < cap; k2++) entries[k2] = 0;   // zero padding entries
         }
+    }
+    // densify (what K2 / the coefficient tap do)
+    std::vector<int16_t> coef(size_t(nblocks) * 64, 0);
+    for (uint32_t b = 0; b < nblocks; b++) {
+        uint32_t e0 = blk_ent[2 * b], e1 = blk_ent[2 * b + 1];
+        if (e0 == 0xFFFFFFFFu || e1 == 0xFFFFFFFFu || e1 < e0 || e1 - e0 > 128u || e1 > cap) return -8;
+        for (uint32_t k2 = e0; k2 < e1; k2++) coef[size_t(b) * 64 + kZig[(entries[k2] >> 16) & 63u]] = int16_t(entries[k2] & 0xFFFFu);
     }
     // DC integration per component, reset at restart intervals
     {
