@@ -58,44 +58,90 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled from a thread every
+    couple of milliseconds (the timed region of the default run is tens of milliseconds, shorter
+    than one `nvidia-smi -lms` period); nvidia-smi is the fallback when NVML cannot be loaded."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
-        self.proc = None
+        self.sm, self.reasons, self.mx = [], set(), 0
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
 
-    def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+    def _nvml_loop(self):
+        import pynvml as nv
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        self.source = "nvml"
+        self.ready.set()
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(f[0]))
-                mx = max(mx, float(f[1]))
-                for n, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.source = "nvidia-smi"
+        self.ready.set()
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                f = [x.strip() for x in out.split(",")]
+                self.sm.append(float(f[0]))
+                self.mx = max(self.mx, float(f[1]))
+                for n, v in zip(self.NAMES, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                time.sleep(0.05)
+
+    def _loop(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
+
+    def start(self):
+        self.ready = threading.Event()
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+        self.ready.wait(20)
+        self.sm.clear()   # keep only samples taken after start() returned
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(15)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx or None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
+
+
+def measured_traffic(workload, stage):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a stage's kernel from the
+    committed `ncu --set full` capture of this workload (profiles/traffic.json, written by
+    profiles/summarize.py); None when no capture of that workload/kernel has been committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(workload, {}).get(stage)
+    except Exception:
+        return None
 
 
 def build_workload(name, n):
@@ -344,7 +390,7 @@ def main():
         "gpu_launches": int(launches + e2e_launches),
         "launches_per_step": int(stats.kernel_launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(stage_bytes[dom]), "launch_ms": dom_ms},
         "stages": stages,
         "k1": {"lanes": stats.lanes, "subsequence_bytes": stats.subsequence_bytes, "subsequences": int(stats.subsequences), "sync_rounds": stats.sync_rounds,

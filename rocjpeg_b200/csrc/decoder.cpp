@@ -3,6 +3,8 @@
 // src/rocjpeg_commons.h:43-65 of the reference (print to stderr, return a code).
 #include "decoder.h"
 
+#include "huff_core.cuh"
+
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -212,7 +214,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
 
     needs_clear_ = false;
     uint64_t scan_off = 0, blk = 0, plane_off = 0, ent = 0;
-    uint32_t sub = 0, dctile = 0, k2tile = 0, k3tile = 0, chunk = 0;
+    uint32_t sub = 0, dctile = 0, k2tile = 0, k3tile = 0, chunk = 0, max_pairs = 1, max_sub = 0;
     all_pinned_ = true;
     for (int i = 0; i < n; i++) {
         const ParsedJpeg& p = streams[i]->parsed();
@@ -228,10 +230,22 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             im.blocks_w[c] = have ? p.blocks_w[c] : 0;
             im.blocks_h[c] = have ? p.blocks_h[c] : 0;
             im.comp_first_blk[c] = k;
+            // (DC table, AC table) pair of the component: K1 keeps each pair's two tables back to back
+            int pair = -1;
+            if (have) {
+                for (int q = 0; q < im.npairs; q++)
+                    if (im.pair_dc[q] == p.td[c] && im.pair_ac[q] == 2 + p.ta[c]) pair = q;
+                if (pair < 0) {
+                    pair = im.npairs++;
+                    im.pair_dc[pair] = uint8_t(p.td[c]);
+                    im.pair_ac[pair] = uint8_t(2 + p.ta[c]);
+                }
+            }
             for (int b = 0; b < H * V && k < kMaxBlocksPerMcu; b++, k++) {
                 im.mcu_comp[k] = uint8_t(c);
                 im.mcu_dc[k] = uint8_t(p.td[c]);
                 im.mcu_ac[k] = uint8_t(2 + p.ta[c]);
+                im.mcu_pair[k] = uint8_t(pair);
             }
             im.qt_index[c] = i * 3 + c;
             if (have) std::memcpy(&h_qtables_[(size_t(i) * 3 + c) * 64], p.qt_natural[p.tq[c]], 128);
@@ -246,6 +260,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             h_lut_hashes_.push_back(p.lut_hash);
         }
         im.lut_set = set;
+        max_pairs = std::max(max_pairs, uint32_t(im.npairs));
+        max_sub = std::max(max_sub, (streams[i]->lut().sub_used + 3u) & ~3u);
         // entropy-coded data
         im.data_off = scan_off;
         im.seg0 = uint32_t(h_segments_.size());
@@ -263,12 +279,12 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             sd.blk_first = uint32_t(mcu_first * uint64_t(p.bpm));
             sd.blk_count = uint32_t(mcu_cnt * uint64_t(p.bpm));
             h_segments_.push_back(sd);
-            if (sd.nbytes == 0 && sd.blk_count != 0) needs_clear_ = true;   // a restart interval with no data at all
+            if (sd.nbytes == 0 && sd.blk_count != 0) needs_clear_ = true;   // a restart interval with no data at all (its records keep the 0xFF fill)
             sub += (sg.nbytes + uint32_t(S) - 1) / uint32_t(S);
         }
         im.nsub = sub - im.sub0;
-        sub = uint32_t(AlignUp(sub, kK1Threads));
-        h_img_cta0_[size_t(i)] = im.sub0 / kK1Threads;
+        sub = uint32_t(AlignUp(sub, kK1Owned));
+        h_img_cta0_[size_t(i)] = im.sub0 / kK1Owned;
         h_gather_[size_t(i)] = GatherItem{streams[i]->clean().data(), scan_off, uint32_t(p.clean_bytes), chunk};
         chunk += uint32_t((p.clean_bytes + 16383) / 16384);
         all_pinned_ = all_pinned_ && streams[i]->clean().pinned();
@@ -318,7 +334,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         k3tile += od.tiles_x * od.tiles_y;
         stats_.output_bytes += OutputBytes(p.css, od.fmt, od.w, od.h);
     }
-    h_img_cta0_[size_t(n)] = sub / kK1Threads;
+    h_img_cta0_[size_t(n)] = sub / kK1Owned;
     h_img_dctile0_[size_t(n)] = dctile;
     h_k2_tile0_[size_t(n)] = k2tile;
     h_k3_tile0_[size_t(n)] = k3tile;
@@ -334,7 +350,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
 
     k1_ = K1Args{};
     k1_.nimages = n;
-    k1_.total_ctas = sub / kK1Threads;
+    k1_.total_ctas = sub / kK1Owned;
+    k1_.lut_smem_bytes = max_pairs * 2u * uint32_t(kFastSize) * 4u + max_sub * 4u;
     k1_.total_dc_tiles = dctile;
     k1_.sub_bytes = S;
     k2_ = K2Args{};
@@ -385,10 +402,9 @@ int Lane::Upload(cudaStream_t up) {
     RJB_CUDA(d_desc_.Reserve(L.total));
     RJB_CUDA(d_scan_.Reserve(scan_bytes_ + 512));
     RJB_CUDA(d_entries_.Reserve(entry_count_ * 4 + 256));
-    RJB_CUDA(d_blkent_.Reserve(coef_blocks_ * 8 + 256));
+    RJB_CUDA(d_blkrec_.Reserve(coef_blocks_ * sizeof(BlockRec) + 256));
     RJB_CUDA(d_nnz_.Reserve(nsub_total_ * 4 + 256));
     RJB_CUDA(d_cta_entries_.Reserve(size_t(k1_.total_ctas) * 4 + 256));
-    RJB_CUDA(d_dcdiff_.Reserve(coef_blocks_ * 2 + 256));
     RJB_CUDA(d_planes_.Reserve(plane_bytes_ + 512));
     RJB_CUDA(d_state_.Reserve(nsub_total_ * 4 + 256));
     RJB_CUDA(d_used_.Reserve(nsub_total_ * 4 + 256));
@@ -412,16 +428,14 @@ int Lane::Upload(cudaStream_t up) {
     k1_.dc_partial = d_dc_partial_.as<int3>();
     k1_.counters = d_counters_.as<uint32_t>();
     k1_.entries = d_entries_.as<uint32_t>();
-    k1_.blk_ent = d_blkent_.as<uint32_t>();
+    k1_.blk_rec = d_blkrec_.as<BlockRec>();
     k1_.nnz = d_nnz_.as<uint32_t>();
     k1_.cta_entries = d_cta_entries_.as<uint32_t>();
-    k1_.dcdiff = d_dcdiff_.as<int16_t>();
     k2_.images = k1_.images;
     k2_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k2tile0);
     k2_.qtables = reinterpret_cast<const uint16_t*>(d + L.qtables);
     k2_.entries = k1_.entries;
-    k2_.blk_ent = k1_.blk_ent;
-    k2_.dc = k1_.dcdiff;
+    k2_.blk_rec = k1_.blk_rec;
     k2_.planes = d_planes_.as<uint8_t>();
     k3_.images = k1_.images;
     k3_.outputs = reinterpret_cast<const OutputDesc*>(d + L.outputs);
@@ -458,10 +472,9 @@ int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up) {
         if (st != kSuccess) return st;
     }
     RJB_CUDA(mark(1));
-    // Per-block entry indices start as "never decoded" (4 bytes per block; the entry arena itself is
+    // Per-block records start as "never decoded" (8 bytes per block; the entry arena itself is
     // never cleared): blocks a damaged stream does not reach then decode as zero.
-    RJB_CUDA(cudaMemsetAsync(d_blkent_.as<uint8_t>(), 0xFF, coef_blocks_ * 8, stream_));
-    if (needs_clear_) RJB_CUDA(cudaMemsetAsync(d_dcdiff_.as<uint8_t>(), 0, coef_blocks_ * 2, stream_));
+    RJB_CUDA(cudaMemsetAsync(d_blkrec_.as<uint8_t>(), 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
     RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint8_t>(), 0, 256, stream_));
     RJB_CUDA(mark(2));
     for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
@@ -502,7 +515,7 @@ int Lane::Finish(bool profiling_) {
             if (cnt[slot] == 0) break;
             if (++guard > k1_.total_ctas + 2) return Fail(kExecutionFailed, "entropy decoder failed to converge");
         }
-        RJB_CUDA(cudaMemsetAsync(d_blkent_.as<uint8_t>(), 0xFF, coef_blocks_ * 8, stream_));
+        RJB_CUDA(cudaMemsetAsync(d_blkrec_.as<uint8_t>(), 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
         RJB_CUDA(LaunchK1Write(k1_, stream_));
         RJB_CUDA(LaunchDcScan(k1_, stream_));
         RJB_CUDA(LaunchK2Idct(k2_, stream_));
@@ -681,16 +694,16 @@ int Lane::CopyCoefficients(int image, int16_t* host_out, size_t count) {
     static const uint8_t kZz[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-    std::vector<int16_t> tmp(size_t(im.nblocks) * 64, 0), dc(im.nblocks);
-    std::vector<uint32_t> be(size_t(im.nblocks) * 2), ents(im.ent_cap);
-    RJB_CUDA(cudaMemcpy(be.data(), d_blkent_.as<uint32_t>() + 2 * im.blk0, be.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<int16_t> tmp(size_t(im.nblocks) * 64, 0);
+    std::vector<BlockRec> recs(im.nblocks);
+    std::vector<uint32_t> ents(im.ent_cap);
+    RJB_CUDA(cudaMemcpy(recs.data(), d_blkrec_.as<BlockRec>() + im.blk0, recs.size() * sizeof(BlockRec), cudaMemcpyDeviceToHost));
     RJB_CUDA(cudaMemcpy(ents.data(), d_entries_.as<uint32_t>() + im.ent0, ents.size() * 4, cudaMemcpyDeviceToHost));
-    RJB_CUDA(cudaMemcpy(dc.data(), d_dcdiff_.as<int16_t>() + im.blk0, dc.size() * 2, cudaMemcpyDeviceToHost));
-    for (size_t b = 0; b < dc.size(); b++) {
-        uint32_t e0 = be[2 * b], e1 = be[2 * b + 1];
+    for (size_t b = 0; b < recs.size(); b++) {
+        uint32_t e0 = b ? recs[b - 1].end : 0u, e1 = recs[b].end;   // a block's entries begin where its predecessor's end
         if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > im.ent_cap) e0 = e1 = 0;
-        for (uint32_t k = e0; k < e1; k++) tmp[b * 64 + kZz[(ents[k] >> 16) & 63u]] = int16_t(ents[k] & 0xFFFFu);
-        tmp[b * 64] = dc[b];   // integrated DC lives in the compact per-block array
+        for (uint32_t k = e0; k < e1; k++) tmp[b * 64 + kZz[CoefEntryPos(ents[k])]] = int16_t(ents[k] & 0xFFFFu);
+        tmp[b * 64] = recs[b].dc;   // integrated DC lives in the block's record
     }
     size_t base = 0;
     for (int c = 0; c < im.ncomp; c++) {

@@ -132,7 +132,7 @@ class Lane {
     StagingBuffer h_desc_;        // pinned descriptor block
     size_t desc_bytes_ = 0;
     StagingBuffer h_counters_;    // pinned read-back
-    DeviceBuffer d_desc_, d_scan_, d_entries_, d_blkent_, d_nnz_, d_cta_entries_, d_dcdiff_, d_planes_, d_state_, d_used_, d_subseg_, d_cta_partial_,
+    DeviceBuffer d_desc_, d_scan_, d_entries_, d_blkrec_, d_nnz_, d_cta_entries_, d_planes_, d_state_, d_used_, d_subseg_, d_cta_partial_,
         d_dc_partial_, d_counters_;
     BatchStats stats_;
 };

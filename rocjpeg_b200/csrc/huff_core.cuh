@@ -60,26 +60,44 @@ struct NullSink {
 // Coefficient entry of the sparse coefficient stream K1 writes and K2 expands: one 32-bit word
 // per symbol that carries magnitude bits (every non-zero AC coefficient; DC symbols with a
 // non-zero difference too, which K2 ignores in favour of the integrated DC).
-//   bits 0..15  quantised value, int16;   bits 16..21  zig-zag position 0..63
-RJB_HD uint32_t MakeCoefEntry(int pos, int val) { return (uint32_t(val) & 0xFFFFu) | (uint32_t(pos) << 16); }
+//   bits 0..15   quantised value, int16
+//   bits 16..21  zig-zag index AFTER the symbol = position + 1 (mod 64: 0 stands for position 63)
+//   bits 22..31  don't care (K1 leaves decoder state bits there)
+// kPadEntry fills the gaps between two threads' runs: value 0 at position 0, which K2
+// overwrites with the integrated DC.
+RJB_HD uint32_t MakeCoefEntry(int pos, int val) { return (uint32_t(val) & 0xFFFFu) | (uint32_t((pos + 1) & 63) << 16); }
+RJB_HD int CoefEntryPos(uint32_t en) { return int(((en >> 16) - 1u) & 63u); }
+constexpr uint32_t kPadEntry = 1u << 16;
 
-// First-level table entry (HuffLutSet::fast) and the value SlowEntry() returns (16 bits):
-//   bits 0..4   code length + SSSS = bits the whole symbol consumes (1..31); entry 0 = not in the fast table
-//   bits 5..8   SSSS  number of magnitude bits that follow the code
-//   bits 9..15  how far the symbol advances the zig-zag index: 1 for a DC symbol, RRRR + 1 for
-//               an AC coefficient or ZRL (15 + 1), 64 for end-of-block (so "z += advance; z >= 64"
-//               is the only block-end test)
+// Symbol entry of the two-level tables (HuffLutSet::fast / ::sub), 32 bits, laid out so that ONE
+// integer add advances the whole per-thread decoder state of k1_huffman.cu
+// (acc = bit position | entries produced << 11 | zig-zag index << 21):
+//   bits 0..4    code length + SSSS = bits the whole symbol consumes (1..31)
+//   bits 5..10   0 (bit 10 set = link, see below)
+//   bit  11      1 when the symbol carries magnitude bits (SSSS != 0): it produces a coefficient entry
+//   bits 21..27  how far the symbol advances the zig-zag index: 1 for a DC symbol, RRRR + 1 for an
+//                AC coefficient or ZRL (15 + 1), 64 for end-of-block (so "z += advance; z >= 64" is
+//                the only block-end test)
+//   bits 28..31  SSSS, number of magnitude bits that follow the code (adds harmlessly above z)
 RJB_HD uint32_t MakeEntry(uint32_t len, uint32_t sym, bool is_ac) {
     const uint32_t s = sym & 15u;
     const uint32_t adv = !is_ac ? 1u : (sym == 0 ? 64u : (sym >> 4) + 1u);
-    return (len + s) | (s << 5) | (adv << 9);
+    return (len + s) | (s ? (1u << 11) : 0u) | (adv << 21) | (s << 28);
 }
 RJB_HD uint32_t EntryBits(uint32_t e) { return e & 31u; }
-RJB_HD uint32_t EntrySize(uint32_t e) { return (e >> 5) & 15u; }
-RJB_HD int EntryAdvance(uint32_t e) { return int(e >> 9); }
+RJB_HD uint32_t EntrySize(uint32_t e) { return e >> 28; }
+RJB_HD int EntryAdvance(uint32_t e) { return int((e >> 21) & 127u); }
+// Link entry (first level only, code longer than kFastBits): bits 0..9 = 0, bit 10 = 1 (added to
+// the decoder state it raises the same "look closer" flag as the end of the subsequence does),
+// bits 11..14 = x, the number of index bits of the sub-table (1..16-kFastBits; 0 = resolve by the
+// canonical search), bits 16..31 = index of the sub-table's first entry in HuffLutSet::sub.
+RJB_HD uint32_t MakeLink(uint32_t x, uint32_t first) { return (1u << 10) | (x << 11) | (first << 16); }
+RJB_HD bool IsLink(uint32_t e) { return (e & (1u << 10)) != 0; }
+RJB_HD uint32_t LinkBits(uint32_t e) { return (e >> 11) & 15u; }
+RJB_HD uint32_t LinkFirst(uint32_t e) { return e >> 16; }
 
-// Codes longer than kFastBits (or invalid ones: 16 bits consumed, symbol 0 — T.81 leaves
-// this undefined; the oracle does the same).
+// Canonical search for codes longer than kFastBits (or invalid ones: 16 bits consumed, symbol 0 —
+// T.81 leaves this undefined; the oracle does the same).
 RJB_HD uint32_t SlowEntry(const HuffLutSet* lut, uint32_t tab, uint32_t v16) {
     for (int l = kFastBits + 1; l <= 16; l++) {
         if (v16 < lut->upper[tab][l])
@@ -97,13 +115,12 @@ RJB_HD uint32_t FunnelLeft(uint32_t hi, uint32_t lo, uint32_t k) {
 #endif
 }
 
-// Which Huffman tables block c of the MCU uses, as two bit masks (bit c = table id 0/1), so a
-// block change costs ALU work only. Offsets index HuffLutSet::fast as one flat array.
+// Which Huffman tables block c of the MCU uses, as two bit masks (bit c = table id 0/1).
 struct TableSel {
     uint32_t dc_mask, ac_mask;
 };
-RJB_HD uint32_t DcOffset(TableSel t, int c) { return ((t.dc_mask >> c) & 1u) * uint32_t(kFastSize); }
-RJB_HD uint32_t AcOffset(TableSel t, int c) { return (2u + ((t.ac_mask >> c) & 1u)) * uint32_t(kFastSize); }
+RJB_HD uint32_t DcTab(TableSel t, int c) { return (t.dc_mask >> c) & 1u; }
+RJB_HD uint32_t AcTab(TableSel t, int c) { return 2u + ((t.ac_mask >> c) & 1u); }
 RJB_HD TableSel MakeTableSel(const uint8_t* mcu_dc, const uint8_t* mcu_ac, int bpm) {
     TableSel t{0u, 0u};
     for (int c = 0; c < bpm; c++) {
@@ -136,10 +153,14 @@ struct BitWindow {
     }
 };
 
-RJB_HD uint32_t LookupSymbol(const HuffLutSet* lut, uint32_t tab_off, uint32_t win) {
-    const uint16_t* fast = &lut->fast[0][0];
-    uint32_t e = fast[tab_off + (win >> (32 - kFastBits))];
-    if (e == 0) e = SlowEntry(lut, tab_off >> kFastBits, win >> 16);
+// Two-level lookup of the symbol whose code starts at the top of `win` in table `tab` (0..3).
+RJB_HD uint32_t LookupSymbol(const HuffLutSet* lut, uint32_t tab, uint32_t win) {
+    uint32_t e = lut->fast[tab][win >> (32 - kFastBits)];
+    if (IsLink(e)) {
+        const uint32_t x = LinkBits(e);
+        if (x == 0) e = SlowEntry(lut, tab, win >> 16);
+        else e = lut->sub[LinkFirst(e) + ((win << kFastBits) >> (32u - x))];
+    }
     return e;
 }
 
@@ -167,11 +188,11 @@ RJB_HD void DecodeSpan(const Loader& load, const HuffLutSet* lut, TableSel sel, 
     if (p >= end_bit) return;
     BitWindow bw;
     bw.Init(load, p);
-    uint32_t dc_off = DcOffset(sel, c), ac_off = AcOffset(sel, c);
+    uint32_t dc_tab = DcTab(sel, c), ac_tab = AcTab(sel, c);
     while (p < end_bit) {
         if (WRITE && blk >= blk_limit) break;
         const uint32_t win = bw.Peek(p);
-        const uint32_t e = LookupSymbol(lut, (z == 0) ? dc_off : ac_off, win);
+        const uint32_t e = LookupSymbol(lut, (z == 0) ? dc_tab : ac_tab, win);
         const int adv = EntryAdvance(e);
         if (EntrySize(e)) {
             nnz++;
@@ -187,8 +208,8 @@ RJB_HD void DecodeSpan(const Loader& load, const HuffLutSet* lut, TableSel sel, 
             nb++;
             blk++;
             c = (c + 1 == bpm) ? 0 : c + 1;
-            dc_off = DcOffset(sel, c);
-            ac_off = AcOffset(sel, c);
+            dc_tab = DcTab(sel, c);
+            ac_tab = AcTab(sel, c);
         }
     }
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime_api.h>
 
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 namespace rjb {
@@ -83,21 +84,29 @@ int ClassifyChromaSubsampling(const int32_t h[3], const int32_t v[3]) {
 
 // ------------------------------------------------------------ Huffman tables
 
-// T.81 Annex C (code assignment) + F.2.2.3 (decoder tables), restated for a
-// left-aligned 16-bit peek. slot: 0 = DC0, 1 = DC1, 2 = AC0, 3 = AC1.
-void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out) {
-    uint16_t* fast = out->fast[slot];
-    std::memset(fast, 0, sizeof(uint16_t) * kFastSize);
-    std::memcpy(out->vals[slot], spec.vals, 256);
+// T.81 Annex C (code assignment) + F.2.2.3 (decoder tables), restated as a two-level lookup over
+// a left-aligned peek (device_types.h: HuffLutSet). slot: 0 = DC0, 1 = DC1, 2 = AC0, 3 = AC1.
+// Sub-tables are appended to out->sub (the caller zeroes the set before building its tables).
+void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out, uint32_t sub_cap) {
+    uint32_t* fast = out->fast[slot];
+    if (sub_cap > uint32_t(kSubCap)) sub_cap = uint32_t(kSubCap);
     const bool is_ac = slot >= 2;
+    const uint32_t invalid = MakeEntry(16, 0, is_ac);   // unassigned code: 16 bits consumed, symbol 0
+    for (int i = 0; i < kFastSize; i++) fast[i] = invalid;
+    std::memcpy(out->vals[slot], spec.vals, 256);
+    struct Long { uint32_t code, len, sym; };
+    std::vector<Long> longs;
     uint32_t code = 0, k = 0;
     for (int l = 1; l <= 16; l++) {
         out->valoff[slot][l] = int32_t(k) - int32_t(code);
         for (uint32_t i = 0; i < spec.bits[l - 1]; i++, code++, k++) {
-            if (l <= kFastBits && code < (1u << l) && k < 256) {
+            if (code >= (1u << l) || k >= 256) continue;   // over-subscribed DHT: the excess codes cannot occur
+            if (l <= kFastBits) {
                 const uint32_t first = code << (kFastBits - l);
-                const uint16_t entry = uint16_t(MakeEntry(uint32_t(l), spec.vals[k], is_ac));
+                const uint32_t entry = MakeEntry(uint32_t(l), spec.vals[k], is_ac);
                 for (uint32_t j = 0; j < (1u << (kFastBits - l)); j++) fast[first + j] = entry;
+            } else {
+                longs.push_back(Long{code, uint32_t(l), spec.vals[k]});
             }
         }
         uint32_t up = code << (16 - l);
@@ -106,6 +115,31 @@ void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out) {
     }
     out->upper[slot][0] = 0;
     out->valoff[slot][0] = 0;
+    // second level: one sub-table per first-level prefix that has longer codes under it, indexed by
+    // the next (longest code under the prefix - kFastBits) bits. Canonical codes are assigned in
+    // increasing order, so the codes of one prefix are contiguous in `longs`.
+    for (size_t i = 0; i < longs.size();) {
+        const uint32_t prefix = longs[i].code >> (longs[i].len - kFastBits);
+        size_t j = i;
+        uint32_t maxlen = 0;
+        while (j < longs.size() && (longs[j].code >> (longs[j].len - kFastBits)) == prefix) maxlen = std::max(maxlen, longs[j++].len);
+        const uint32_t x = maxlen - kFastBits, n = 1u << x;
+        if (out->sub_used + n > sub_cap) {
+            fast[prefix] = MakeLink(0, 0);   // arena exhausted: the canonical search resolves these codes
+        } else {
+            const uint32_t first = out->sub_used;
+            out->sub_used += n;
+            for (uint32_t t = 0; t < n; t++) out->sub[first + t] = invalid;
+            for (size_t q = i; q < j; q++) {
+                const uint32_t rest = longs[q].len - kFastBits;   // bits of the code below the prefix
+                const uint32_t low = (longs[q].code & ((1u << rest) - 1u)) << (x - rest);
+                const uint32_t entry = MakeEntry(longs[q].len, longs[q].sym, is_ac);
+                for (uint32_t t = 0; t < (1u << (x - rest)); t++) out->sub[first + low + t] = entry;
+            }
+            fast[prefix] = MakeLink(x, first);
+        }
+        i = j;
+    }
 }
 
 // ------------------------------------------------------------ StreamParser
@@ -343,9 +377,12 @@ void StreamParser::BuildDecodeTables() {
                       std::memcmp(lut_spec_ac_, p_.ac, sizeof(p_.ac)) == 0;
     if (!same) {
         std::memset(&lut_, 0, sizeof(lut_));
+        // debug knob: a smaller second-level arena forces long codes onto the canonical search
+        const char* cap_env = std::getenv("ROCJPEG_B200_SUBCAP");
+        const uint32_t cap = (cap_env && *cap_env) ? uint32_t(std::atoi(cap_env)) : uint32_t(kSubCap);
         for (int t = 0; t < 2; t++) {
-            if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &lut_);
-            if (p_.ac[t].present) BuildHuffLut(p_.ac[t], 2 + t, &lut_);
+            if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &lut_, cap);
+            if (p_.ac[t].present) BuildHuffLut(p_.ac[t], 2 + t, &lut_, cap);
         }
         std::memcpy(lut_spec_dc_, p_.dc, sizeof(p_.dc));
         std::memcpy(lut_spec_ac_, p_.ac, sizeof(p_.ac));

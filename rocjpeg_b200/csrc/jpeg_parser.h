@@ -116,6 +116,6 @@ class StreamParser {
 };
 
 int ClassifyChromaSubsampling(const int32_t h[3], const int32_t v[3]);
-void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out);
+void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out, uint32_t sub_cap = kSubCap);
 
 }  // namespace rjb

@@ -47,6 +47,8 @@ namespace rjb {
 namespace {
 
 constexpr int T = kK1Threads;
+constexpr int H = kK1Halo;
+constexpr int TO = kK1Owned;
 constexpr uint32_t kNoState = 0xFFFFFFFFu;
 
 // largest i in [0, n) with a[i] <= v (a is non-decreasing, a[0] <= v)
@@ -59,15 +61,7 @@ __device__ __forceinline__ uint32_t UpperIndex(const uint32_t* a, uint32_t n, ui
     return lo;
 }
 
-struct SmemLoader {
-    const uint32_t* base;
-    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return base[i]; }
-};
-// ---- lean shared-memory primitives for the two hot loops ---------------------------------
-// Both K1 loops are instruction-issue bound (profiles/r01b_*), so they are written against raw
-// 32-bit shared-memory addresses: no generic-address arithmetic, no window registers to rotate
-// (two extra LDS per symbol cost latency, which the other warps hide, but no issue slots for
-// bookkeeping), table select and bit position as the only loop-carried scalars.
+// ---- raw shared-memory primitives for the two hot loops ----------------------------------
 __device__ __forceinline__ uint32_t SharedAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t Lds32(uint32_t a) {
     uint32_t v;
@@ -79,67 +73,139 @@ __device__ __forceinline__ uint32_t Lds16(uint32_t a) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
-__device__ __forceinline__ uint32_t Lds8(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void Sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-// Codes longer than the first-level table, without a search loop and without generic loads: the six
-// length thresholds are fetched at once, the code length is a count of comparisons
-// (huff_core.cuh: SlowEntry is the same computation written as a loop, for the host model).
-// With 32 lanes per warp some lane takes this path in roughly every second step, so its latency
-// is paid by the whole warp.
-__device__ __forceinline__ uint32_t SlowEntryShared(uint32_t lutset_sa, uint32_t tab, uint32_t v16) {
-    const uint32_t up = lutset_sa + uint32_t(offsetof(HuffLutSet, upper)) + tab * 68u + 4u * (kFastBits + 1);
-    static_assert(kFastBits == 10, "six lengths (11..16) are searched");
-    const uint32_t u11 = Lds32(up), u12 = Lds32(up + 4), u13 = Lds32(up + 8), u14 = Lds32(up + 12), u15 = Lds32(up + 16),
-                   u16 = Lds32(up + 20);
-    const uint32_t len = 11u + (v16 >= u11) + (v16 >= u12) + (v16 >= u13) + (v16 >= u14) + (v16 >= u15);
-    if (v16 >= u16) return MakeEntry(16, 0, tab >= 2);   // invalid code: 16 bits consumed, symbol 0
-    const int32_t voff = int32_t(Lds32(lutset_sa + uint32_t(offsetof(HuffLutSet, valoff)) + tab * 68u + 4u * len));
-    const uint32_t sym = Lds8(lutset_sa + uint32_t(offsetof(HuffLutSet, vals)) + tab * 256u + (uint32_t(int32_t(v16 >> (16u - len)) + voff) & 255u));
-    return MakeEntry(len, sym, tab >= 2);
+// Decoder state of one thread packed so that adding a table entry (huff_core.cuh: MakeEntry)
+// advances all of it at once:
+//   bits 0..10   bit position inside the subsequence, biased by 1024 - (end of the subsequence
+//                rounded up to a whole 32-bit word): bit 10 comes on when the position passes
+//                that end (link entries use the same bit of a table entry as their mark).
+//   bits 11..20  coefficient entries produced so far
+//   bits 21..26  zig-zag index; bit 27 comes on with the symbol that ends a block
+//   bits 28..31  scratch (the SSSS fields of the entries pile up here and fall off the top)
+// Rounding the end up only matters for the last subsequence of a restart interval: the symbols
+// it may see past the true end lie in the interval's zero padding, change nothing downstream
+// (no hand-over; the write pass stops at the interval's last block and zero-fills what the
+// counting pass reserved for them).
+constexpr uint32_t kAccStop = 1u << 10;
+constexpr uint32_t kAccBlockEnd = 1u << 27;
+constexpr uint32_t kAccKeep = 0x001FFFFFu;   // cleared at a block end: zig-zag index, end flag, scratch
+constexpr uint32_t kAccZMask = 63u << 21;
+
+// Addresses (shared window) of everything the decode loops touch besides the thread's own slot.
+struct LutView {
+    uint32_t fast_sa;            // first pair's DC table; pair k at + k * 4096, its AC table 2048 further
+    uint32_t sub_sa;             // second-level arena
+    const HuffLutSet* set;       // global copy (canonical search for link entries with x = 0)
+    const uint8_t* pair_tab;     // shared: [2 * pair + is_ac] -> table index in the set
+};
+
+// A code longer than kFastBits: second-level lookup by the x bits that follow the first kFastBits.
+__device__ __forceinline__ uint32_t CanonicalSearch(const LutView& lv, uint32_t off, uint32_t win) {
+    return SlowEntry(lv.set, lv.pair_tab[(off - lv.fast_sa) >> 11], win >> 16);   // off = fast_sa + 4096 * pair + 2048 * is_ac
+}
+__device__ __forceinline__ uint32_t ResolveLink(const LutView& lv, uint32_t e, uint32_t off, uint32_t win) {
+    const uint32_t x = LinkBits(e);
+    if (x == 0) return CanonicalSearch(lv, off, win);
+    return Lds32(lv.sub_sa + ((LinkFirst(e) + ((win << kFastBits) >> (32u - x))) << 2));
 }
 
-// Next 32 bits of the stream at bit position p of the slot at shared address `slot`.
-__device__ __forceinline__ uint32_t PeekBits(uint32_t slot, uint32_t p) {
-    const uint32_t a = slot + ((p >> 5) << 2);
-    return __funnelshift_l(Lds32(a + 4), Lds32(a), p);
-}
-// Byte offsets of the Huffman tables of block c inside HuffLutSet::fast.
-__device__ __forceinline__ uint32_t DcBytes(TableSel t, int c) { return ((t.dc_mask >> c) & 1u) << (kFastBits + 1); }
-__device__ __forceinline__ uint32_t AcBytes(TableSel t, int c) { return (2u + ((t.ac_mask >> c) & 1u)) << (kFastBits + 1); }
+// One thread's decoder registers. The three per-symbol updates are written as predicated PTX so
+// that each costs a fixed, minimal number of issue slots: with 32 lanes per warp some lane
+// crosses a word boundary or ends a block in almost every step, so these paths are executed by
+// the warp every time whether written as branches or not (profiles/r01c_*).
+//   window    w0:w1 hold the 64 bits around the read position, w2 is fetched one word ahead, so
+//             the only shared-memory access on the symbol-to-symbol dependency chain is the
+//             table lookup;
+//   schedule  a pointer walking through the CTA's shared array of DC-table addresses, one entry
+//             per block from the start of an MCU on, repeated (the block-in-MCU counter is the
+//             pointer itself). A pair's AC table lies 2048 bytes after its DC table and DC tables
+//             start at addresses with bit 11 clear (checked in StageCta), so "the AC table of
+//             whatever table is current" is off | 2048.
+struct Lane {
+    uint32_t acc;              // packed state, see above
+    uint32_t w0, w1, w2, wp;   // wp = shared address of w2
+    uint32_t sp0, sp;          // shared address of the schedule entry of the first / current block
+    uint32_t next_dc;          // DC-table address of the next block, fetched one block ahead
+    uint32_t off;              // table the next symbol is looked up in
+
+    __device__ __forceinline__ void Init(uint32_t slot_sa, uint32_t sched_sa, uint32_t key, uint32_t end_bit) {
+        const uint32_t p = StateOverflow(key), end32 = (end_bit + 31u) & ~31u;
+        acc = (p + 1024u - end32) | (uint32_t(StateZ(key)) << 21);
+        wp = slot_sa + ((p >> 5) << 2);
+        w0 = Lds32(wp);
+        w1 = Lds32(wp + 4);
+        w2 = Lds32(wp + 8);
+        wp += 8;
+        sp0 = sp = sched_sa + 2u * uint32_t(StateC(key));
+        off = Lds16(sp) | (StateZ(key) ? 2048u : 0u);
+        next_dc = Lds16(sp + 2);
+    }
+    __device__ __forceinline__ uint32_t Peek() const { return __funnelshift_l(w1, w0, acc); }
+    __device__ __forceinline__ uint32_t Lookup(uint32_t win) const {
+        uint32_t a, e;
+        asm volatile("{\n\t.reg .b32 i;\n\tshr.u32 i, %2, 23;\n\tmad.lo.u32 %0, i, 4, %3;\n\tld.shared.u32 %1, [%0];\n\t}"
+                     : "=r"(a), "=r"(e) : "r"(win), "r"(off));
+        return e;
+    }
+    // acc <- nxt; window refill when the position entered the next word; block-end bookkeeping.
+#define RJB_K1_COMMIT_HEAD(NXT)                              \
+    "lop3.b32 t, %0, %" NXT ", 32, 0x28;\n\t"               \
+    "setp.ne.u32 pc, t, 0;\n\t"                             \
+    "and.b32 t, %" NXT ", 0x8000000;\n\t"                   \
+    "setp.ne.u32 pe, t, 0;\n\t"                             \
+    "@pc mov.b32 %1, %2;\n\t"                               \
+    "@pc mov.b32 %2, %3;\n\t"                               \
+    "@pc ld.shared.u32 %3, [%4+4];\n\t"                     \
+    "@pc add.u32 %4, %4, 4;\n\t"                            \
+    "mov.b32 %0, %" NXT ";\n\t"                             \
+    "or.b32 %7, %7, 2048;\n\t"                              \
+    "@pe and.b32 %0, %" NXT ", 0x1fffff;\n\t"               \
+    "@pe mov.b32 %7, %6;\n\t"                               \
+    "@pe ld.shared.u16 %6, [%5+4];\n\t"                     \
+    "@pe add.u32 %5, %5, 2;\n\t"
+    __device__ __forceinline__ void Commit(uint32_t nxt) {
+        asm volatile("{\n\t.reg .pred pc, pe;\n\t.reg .b32 t;\n\t" RJB_K1_COMMIT_HEAD("8") "}"
+                     : "+r"(acc), "+r"(w0), "+r"(w1), "+r"(w2), "+r"(wp), "+r"(sp), "+r"(next_dc), "+r"(off)
+                     : "r"(nxt));
+    }
+    // The same, and at a block end: the block's record gets `n` (entries so far = one past the
+    // block's last), the record pointer moves on; reaching the record of the restart interval's
+    // last block + 1 raises the stop bit (what follows in the subsequence is padding).
+    __device__ __forceinline__ void CommitWrite(uint32_t nxt, BlockRec*& rp, uint32_t n, uint32_t rp_stop) {
+        asm volatile("{\n\t.reg .pred pc, pe, pl;\n\t.reg .b32 t;\n\t" RJB_K1_COMMIT_HEAD("9")
+                     "@pe st.global.u32 [%8], %10;\n\t"
+                     "@pe add.u64 %8, %8, 8;\n\t"
+                     "cvt.u32.u64 t, %8;\n\t"
+                     "setp.eq.and.u32 pl, t, %11, pe;\n\t"
+                     "@pl or.b32 %0, %0, 0x400;\n\t"
+                     "}"
+                     : "+r"(acc), "+r"(w0), "+r"(w1), "+r"(w2), "+r"(wp), "+r"(sp), "+r"(next_dc), "+r"(off), "+l"(rp)
+                     : "r"(nxt), "r"(n), "r"(rp_stop)
+                     : "memory");
+    }
+#undef RJB_K1_COMMIT_HEAD
+    __device__ __forceinline__ uint32_t Blocks() const { return (sp - sp0) >> 1; }
+};
 
 // Count-only decode of one subsequence from state `key` (speculation / synchronisation):
-// returns the packed end state + block count, and the number of coefficient entries in *nnz.
-__device__ __forceinline__ uint32_t DecodeCount(uint32_t slot, uint32_t lut_sa, TableSel sel, int bpm, uint32_t key,
+// returns the packed end state + block count, the number of coefficient entries in *nnz_out.
+__device__ __forceinline__ uint32_t DecodeCount(uint32_t slot_sa, const LutView& lv, uint32_t sched_sa, int bpm, uint32_t key,
                                                 uint32_t end_bit, uint32_t* nnz_out) {
-    uint32_t p = StateOverflow(key), nb = 0, nnz = 0;
-    int c = StateC(key), z = StateZ(key);
-    uint32_t dc_off = DcBytes(sel, c), ac_off = AcBytes(sel, c);
-    uint32_t off = (z == 0) ? dc_off : ac_off;
-    while (p < end_bit) {
-        const uint32_t win = PeekBits(slot, p);
-        uint32_t e = Lds16(lut_sa + off + ((win >> (31 - kFastBits)) & (2u * kFastSize - 2u)));
-        if (e == 0) e = SlowEntryShared(lut_sa, off >> (kFastBits + 1), win >> 16);
-        p += EntryBits(e);
-        z += EntryAdvance(e);
-        nnz += (e & (15u << 5)) ? 1u : 0u;
-        off = ac_off;
-        if (z >= 64) {
-            z = 0;
-            nb++;
-            c = (c + 1 == bpm) ? 0 : c + 1;
-            dc_off = DcBytes(sel, c);
-            ac_off = AcBytes(sel, c);
-            off = dc_off;
+    Lane ln;
+    ln.Init(slot_sa, sched_sa, key, end_bit);
+    if (end_bit != 0) {
+        for (;;) {
+            const uint32_t win = ln.Peek();
+            uint32_t e = ln.Lookup(win);
+            if (IsLink(e)) e = ResolveLink(lv, e, ln.off, win);
+            ln.Commit(ln.acc + e);
+            if (ln.acc & kAccStop) break;
         }
     }
-    *nnz_out = (nnz + 3u) & ~3u;   // a thread's run of the entry stream is padded to whole 16-byte stores
-    const uint32_t over = p > end_bit ? p - end_bit : 0;
-    return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
+    const uint32_t nb = ln.Blocks(), acc = ln.acc;
+    *nnz_out = (((acc >> 11) & 0x3FFu) + 3u) & ~3u;   // a thread's run of the entry stream is padded to whole 16-byte stores
+    // bits consumed past the end (meaningful when the end is word-aligned, i.e. whenever a successor exists)
+    return PackState(acc & 63u, int((uint32_t(StateC(key)) + nb) % uint32_t(bpm)), int((acc >> 21) & 63u), nb > 0xFFFFu ? 0xFFFFu : nb);
 }
 
 // Per-thread description of its subsequence.
@@ -153,14 +219,15 @@ struct Sub {
 };
 
 template <int S>
-__device__ __forceinline__ Sub Locate(const K1Args& a, const ImageDesc& im, uint32_t g, bool use_cache) {
+__device__ __forceinline__ Sub Locate(const K1Args& a, const ImageDesc& im, int64_t gi, bool use_cache) {
     Sub s;
-    s.active = g < im.sub0 + im.nsub;
+    s.active = gi >= int64_t(im.sub0) && gi < int64_t(im.sub0) + int64_t(im.nsub);
     s.first = s.last = false;
     s.seg = 0;
     s.end_bit = 0;
     s.start = 0;
     if (!s.active) return s;
+    const uint32_t g = uint32_t(gi);
     uint32_t k;
     if (use_cache) {
         k = a.sub_seg[g];
@@ -172,7 +239,6 @@ __device__ __forceinline__ Sub Locate(const K1Args& a, const ImageDesc& im, uint
             if (__ldg(&a.segments[im.seg0 + mid].sub0) <= g) lo = mid; else hi = mid;
         }
         k = im.seg0 + lo;
-        a.sub_seg[g] = k;
     }
     const SegmentDesc sd = a.segments[k];
     const uint32_t j = g - sd.sub0;
@@ -187,13 +253,14 @@ __device__ __forceinline__ Sub Locate(const K1Args& a, const ImageDesc& im, uint
     return s;
 }
 
-// Shared-memory image of one CTA's working set.
+// Shared-memory image of one CTA's working set; the Huffman tables follow it (dynamic size:
+// 4 KiB per table pair the image uses + the second-level arena).
 template <int S>
 struct K1Smem {
     static constexpr int kSlotWords = (S + 16) / 4;      // subsequence + 16 bytes of look-ahead
     static constexpr int kSlotStride = kSlotWords + 1;   // odd stride: conflict-free when lanes read the same word index
     static constexpr int kSlotVecs = (S + 16) / 16;
-    HuffLutSet lut;
+    static constexpr int kSchedLen = S * 4 + 48;         // a block takes at least 2 bits: S*4 blocks + one MCU + prefetch
     uint32_t words[T * kSlotStride];
     uint64_t start[T];
     uint32_t state[T];
@@ -201,23 +268,44 @@ struct K1Smem {
     uint32_t nnz[T];
     uint32_t endbit[T];
     uint32_t queue[T];
-    uint8_t mcu_dc[16], mcu_ac[16];
+    uint16_t sched[kSchedLen];
+    uint8_t pair_tab[8];
     uint32_t scratch[40];
+    alignas(4096) uint32_t lut[4];   // [npairs][2][kFastSize] then the second-level arena (dynamic size)
 };
 
 template <int S>
-__device__ __forceinline__ void StageCta(K1Smem<S>& sm, const K1Args& a, const ImageDesc& im, const Sub& me) {
+__device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, const K1Args& a, const ImageDesc& im, const Sub& me) {
     const int tid = threadIdx.x;
+    // Lane forms "AC table of the current pair" as (table address | 2048): every pair's DC table must
+    // start at a shared-window address with bit 11 clear. The tables lie at a multiple of 4096 from
+    // the start of dynamic shared memory, which itself begins less than 2048 bytes into the window
+    // (0 or the 1 KiB the system reserves); anything else must fail loudly, not decode garbage.
+    if (tid == 0 && (SharedAddr(sm.lut) & 2048u) != 0) __trap();
     sm.start[tid] = me.active ? me.start : ~0ull;
-    // Huffman tables of this image
+    const HuffLutSet* set = a.luts + im.lut_set;
+    const int npairs = im.npairs;
+    // Huffman tables of this image: per (DC, AC) table pair the two first-level tables back to back
     {
-        const uint4* src = reinterpret_cast<const uint4*>(a.luts + im.lut_set);
-        uint4* dst = reinterpret_cast<uint4*>(&sm.lut);
-        for (int i = tid; i < int(sizeof(HuffLutSet) / 16); i += T) dst[i] = __ldg(src + i);
+        uint4* dst = reinterpret_cast<uint4*>(sm.lut);
+        constexpr int kVecsPerTable = kFastSize * 4 / 16;
+        for (int i = tid; i < npairs * 2 * kVecsPerTable; i += T) {
+            const int tsel = i / kVecsPerTable, v = i - tsel * kVecsPerTable;   // tsel = 2 * pair + is_ac
+            const int tab = (tsel & 1) ? im.pair_ac[tsel >> 1] : im.pair_dc[tsel >> 1];
+            dst[i] = __ldg(reinterpret_cast<const uint4*>(set->fast[tab]) + v);
+        }
+        uint4* sdst = dst + npairs * 2 * kVecsPerTable;
+        const int nsub_vecs = int((__ldg(&set->sub_used) + 3u) >> 2);
+        for (int i = tid; i < nsub_vecs; i += T) sdst[i] = __ldg(reinterpret_cast<const uint4*>(set->sub) + i);
     }
-    if (tid < 16) {
-        sm.mcu_dc[tid] = tid < kMaxBlocksPerMcu ? im.mcu_dc[tid] : 0;
-        sm.mcu_ac[tid] = tid < kMaxBlocksPerMcu ? im.mcu_ac[tid] : 2;
+    if (tid < 8) sm.pair_tab[tid] = tid < 2 * npairs ? ((tid & 1) ? im.pair_ac[tid >> 1] : im.pair_dc[tid >> 1]) : 0;
+    {
+        const int bpm = im.bpm;
+        int c = tid % bpm;
+        for (int j = tid; j < K1Smem<S>::kSchedLen; j += T) {
+            sm.sched[j] = uint16_t(SharedAddr(sm.lut) + (uint32_t(im.mcu_pair[c]) << 12));   // the window is < 64 KiB
+            c = (c + T) % bpm;
+        }
     }
     __syncthreads();
     constexpr int V = K1Smem<S>::kSlotVecs;
@@ -231,9 +319,21 @@ __device__ __forceinline__ void StageCta(K1Smem<S>& sm, const K1Args& a, const I
         w[0] = ByteSwap32(q.x); w[1] = ByteSwap32(q.y); w[2] = ByteSwap32(q.z); w[3] = ByteSwap32(q.w);
     }
     __syncthreads();
+    LutView lv;
+    lv.fast_sa = SharedAddr(sm.lut);
+    lv.sub_sa = lv.fast_sa + uint32_t(npairs) * 4096u;
+    lv.set = set;
+    lv.pair_tab = sm.pair_tab;
+    return lv;
 }
 
 // ---------------------------------------------------------------- k1_sync
+//
+// A CTA owns TO = T - H consecutive subsequences of one image; its first H threads re-decode the H
+// subsequences before them (the halo, owned by the previous CTA) so that the state entering the
+// first owned subsequence is, almost always, already the synchronised one in round 0. Nothing the
+// halo threads compute is stored; round >= 1 verifies every CTA boundary against the owner's
+// result and repairs the few that differ.
 
 template <int S>
 __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
@@ -243,14 +343,18 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     const uint32_t cta = blockIdx.x;
     const uint32_t img = UpperIndex(a.img_cta0, uint32_t(a.nimages), cta);
     const ImageDesc& im = a.images[img];
-    const uint32_t g = cta * T + tid;
-    const Sub me = Locate<S>(a, im, g, round > 0);
+    const int64_t gi = int64_t(cta) * TO + tid - H;
+    const uint32_t g = uint32_t(gi);
+    const bool owned = tid >= H;
+    Sub me = Locate<S>(a, im, gi, round > 0);
+    if (round > 0 && !owned) me.active = false;   // later rounds read the owner's state instead of a halo
+    if (round == 0 && owned && me.active) a.sub_seg[g] = me.seg;
 
     uint32_t my_used = 0, out = 0, old_out = kNoState;
     if (round > 0) {
         // Does anything entering this CTA differ from what it was decoded with?
         int need0 = 0;
-        if (tid == 0 && me.active && !me.first) need0 = (StateKey(a.state[g - 1]) != a.used[g]);
+        if (tid == H && me.active && !me.first) need0 = (StateKey(a.state[g - 1]) != a.used[g]);
         if (!__syncthreads_or(need0)) return;
         if (me.active) {
             my_used = a.used[g];
@@ -258,14 +362,13 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
             old_out = out;
         }
     }
-    StageCta<S>(sm, a, im, me);
-    const TableSel sel = MakeTableSel(sm.mcu_dc, sm.mcu_ac, im.bpm);
+    const LutView lv = StageCta<S>(sm, a, im, me);
     const int bpm = im.bpm;
     const uint32_t slots_sa = SharedAddr(sm.words);
-    const uint32_t lut_sa = SharedAddr(&sm.lut.fast[0][0]);
+    const uint32_t sched_sa = SharedAddr(sm.sched);
     auto decode = [&](uint32_t sub, uint32_t key) {   // result state returned, entry count left in sm.nnz[sub]
         uint32_t n;
-        const uint32_t st = DecodeCount(slots_sa + sub * uint32_t(K1Smem<S>::kSlotStride * 4), lut_sa, sel, bpm, key, sm.endbit[sub], &n);
+        const uint32_t st = DecodeCount(slots_sa + sub * uint32_t(K1Smem<S>::kSlotStride * 4), lv, sched_sa, bpm, key, sm.endbit[sub], &n);
         sm.nnz[sub] = n;
         return st;
     };
@@ -283,10 +386,12 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     }
     sm.state[tid] = out;
     sm.used[tid] = my_used;
-    // state entering the CTA (snapshot: the neighbouring CTA may still be changing it; a change is
-    // caught by the boundary counter and the next round)
+    // state entering the first active thread (later rounds: snapshot of the owner's result; the
+    // neighbouring CTA may still be changing it — a change is caught by the boundary counter and the
+    // next round)
     uint32_t in0 = my_used;
-    if (round > 0 && tid == 0 && me.active && !me.first) in0 = StateKey(a.state[g - 1]);
+    if (round > 0 && tid == H && me.active && !me.first) in0 = StateKey(a.state[g - 1]);
+    const bool has_pred = (round == 0) ? (tid > 0) : (tid > H);
     const bool can_redo = me.active && !me.first;
     const int lane = tid & 31;
     // CTA-local fix-up: re-decode while the predecessor's end state is not the state used. The
@@ -294,7 +399,9 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     // warps as possible (a warp with one busy lane costs as many issue slots as a full one).
     for (int iter = 0; iter < T + 1; iter++) {
         __syncthreads();
-        const uint32_t in = (tid > 0) ? StateKey(sm.state[tid - 1]) : in0;
+        // a predecessor slot that maps to no data (before the image's first subsequence) hands over
+        // nothing: such a thread is `first` and never re-decodes, so the value read is irrelevant
+        const uint32_t in = has_pred ? StateKey(sm.state[tid - 1]) : in0;
         const bool need = can_redo && in != sm.used[tid];
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, need);
         uint32_t base = 0;
@@ -321,13 +428,14 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     out = sm.state[tid];
     my_used = sm.used[tid];
     const uint32_t my_nnz = sm.nnz[tid];
-    if (me.active) {
+    const bool mine = owned && me.active;
+    if (mine) {
         a.state[g] = out;
         a.used[g] = my_used;
         a.nnz[g] = my_nnz;
     }
     // A change of the state handed to the next CTA means that CTA must look again.
-    const bool hands_over = me.active && !me.last && (tid == T - 1);
+    const bool hands_over = mine && !me.last && (tid == T - 1);
     if (hands_over && (old_out == kNoState || StateKey(old_out) != StateKey(out))) atomicAdd(&a.counters[round], 1u);
     if (ndecodes) atomicAdd(&a.counters[kMaxSyncRounds + round], ndecodes);
 
@@ -335,16 +443,16 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     uint32_t* red = sm.scratch;
     if (tid == 0) { red[0] = 0; red[1] = 0; }
     __syncthreads();
-    if (me.active && me.first) atomicMax(&red[0], uint32_t(tid) + 1u);
+    if (mine && me.first) atomicMax(&red[0], uint32_t(tid) + 1u);
     __syncthreads();
     const uint32_t last_first = red[0];   // 0 = none, else tid + 1
-    if (me.active && (last_first == 0 || uint32_t(tid) + 1u >= last_first)) atomicAdd(&red[1], StateBlocks(out));
+    if (mine && (last_first == 0 || uint32_t(tid) + 1u >= last_first)) atomicAdd(&red[1], StateBlocks(out));
     __syncthreads();
     if (tid == 0) a.cta_partial[cta] = make_uint2(last_first != 0 ? 1u : 0u, red[1]);
     // entries produced by the CTA (plain sum: entry offsets run through the whole image)
     if (tid == 0) red[2] = 0;
     __syncthreads();
-    if (me.active && my_nnz) atomicAdd(&red[2], my_nnz);
+    if (mine && my_nnz) atomicAdd(&red[2], my_nnz);
     __syncthreads();
     if (tid == 0) a.cta_entries[cta] = red[2];
 }
@@ -359,9 +467,11 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const uint32_t cta = blockIdx.x;
     const uint32_t img = UpperIndex(a.img_cta0, uint32_t(a.nimages), cta);
     const ImageDesc& im = a.images[img];
-    const uint32_t g = cta * T + tid;
-    const Sub me = Locate<S>(a, im, g, true);
-    StageCta<S>(sm, a, im, me);
+    const int64_t gi = int64_t(cta) * TO + tid - H;
+    const uint32_t g = uint32_t(gi);
+    Sub me = Locate<S>(a, im, gi, true);
+    if (tid < H) me.active = false;   // halo slots belong to the previous CTA
+    const LutView lv = StageCta<S>(sm, a, im, me);
 
     const uint32_t st = me.active ? a.state[g] : 0;
     const uint32_t nb = StateBlocks(st);
@@ -431,76 +541,88 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     if (!me.active) return;
     // ---- final decode: every symbol with magnitude bits becomes one 32-bit entry of the
     // image's coefficient stream, written at its final position (each thread owns a contiguous
-    // run of the stream, so consecutive stores of a lane fill whole sectors in L2); every block
-    // end records where the next block's entries begin; DC differences go to the compact
-    // per-block array. No clearing, no read-modify-write, no ownership hand-over: a thread
-    // decodes exactly the symbols that start inside its subsequence, as in the counting passes.
+    // run of the stream, four entries per 128-bit store); every block end records the index one
+    // past the block's last entry, every DC symbol its difference in the compact per-block array.
+    // A block's entries begin where the previous block's end (block 0: entry 0): what lies between
+    // two threads' runs or two restart intervals is zero padding (position 0, which K2 overwrites
+    // with the DC). No clearing, no read-modify-write, no ownership hand-over: a thread decodes
+    // exactly the symbols that start inside its subsequence, as in the counting passes.
     const SegmentDesc sd = a.segments[me.seg];
     uint32_t key = 0;
     if (!me.first) key = StateKey(a.state[g - 1]);
-    uint32_t p = StateOverflow(key);
-    int c = StateC(key), z = StateZ(key);
-    uint32_t blk = sd.blk_first + excl;
-    const uint32_t limit = sd.blk_first + sd.blk_count;
-    uint32_t* entries = a.entries + im.ent0;
-    uint32_t* blk_ent = a.blk_ent + 2 * im.blk0;      // (first, end) entry index of every block
-    int16_t* dcdiff = a.dcdiff + im.blk0;
-    const uint32_t ent_cap = im.ent_cap;
-    const TableSel sel = MakeTableSel(sm.mcu_dc, sm.mcu_ac, im.bpm);
-    const int bpm = im.bpm;
-    const uint32_t slot_sa = SharedAddr(sm.words + tid * K1Smem<S>::kSlotStride);
-    const uint32_t lut_sa = SharedAddr(&sm.lut.fast[0][0]);
-    const uint32_t end_bit = me.end_bit;
-    if (me.first && blk < limit) blk_ent[2 * blk] = n;   // a restart interval's first block starts at this thread's first entry
-    uint32_t dc_off = DcBytes(sel, c), ac_off = AcBytes(sel, c);
-    uint32_t off = (z == 0) ? dc_off : ac_off;
-    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0, cnt = 0;   // pending entries of the current 16-byte group
-    while (p < end_bit && blk < limit) {
-        const uint32_t win = PeekBits(slot_sa, p);
-        uint32_t en = Lds16(lut_sa + off + ((win >> (31 - kFastBits)) & (2u * kFastSize - 2u)));
-        if (en == 0) en = SlowEntryShared(lut_sa, off >> (kFastBits + 1), win >> 16);
-        const uint32_t sz = EntrySize(en), bits = EntryBits(en);
-        // RECEIVE + EXTEND (T.81 F.2.2.1): magnitude bits moved to the top of t
-        const uint32_t t = win << (bits - sz);
-        const uint32_t extra = __funnelshift_rc(t, 0u, 32u - sz);
-        const int val = int(extra) - ((int(t) < 0) ? 0 : int((1u << sz) - 1u));
-        if (z == 0) dcdiff[blk] = int16_t(val);
-        z += EntryAdvance(en);
-        p += bits;
-        if (sz != 0) {
-            // four entries are collected in registers (oldest in q0) and leave as one 128-bit store:
-            // scattered 4-byte stores were throttling the L1 store path (profiles/r01c_*)
-            q0 = q1; q1 = q2; q2 = q3;
-            q3 = MakeCoefEntry((z - 1) & 63, val);
-            if (++cnt == 4) {
-                if (n + 4 <= ent_cap) *reinterpret_cast<uint4*>(entries + n) = make_uint4(q0, q1, q2, q3);
-                n += 4;
-                cnt = 0;
-            }
-        }
-        off = ac_off;
-        if (z >= 64) {
-            z = 0;
-            blk++;
-            // [first, end) of the finished block's entries, and the first entry of the next block of the
-            // interval (across a restart boundary the next interval's first thread records its own
-            // start: the counting pass may have taken the padding bits that end an interval for one
-            // more symbol, so that thread's entries can begin one slot further on)
-            blk_ent[2 * (blk - 1) + 1] = n + cnt;
-            if (blk < limit) blk_ent[2 * blk] = n + cnt;
-            c = (c + 1 == bpm) ? 0 : c + 1;
-            dc_off = DcBytes(sel, c);
-            ac_off = AcBytes(sel, c);
-            off = dc_off;
+    const uint32_t blk0 = sd.blk_first + excl, limit = sd.blk_first + sd.blk_count;
+    // running pointers: the current block's record {end-of-entries index, DC} and the next 16-byte
+    // entry group of this thread's run; the run never leaves its reservation [n, n_end), the
+    // reservations never leave the image's arena
+    BlockRec* recs = a.blk_rec + im.blk0;
+    BlockRec* rp = recs + blk0;
+    const uint32_t rp_stop = uint32_t(reinterpret_cast<uintptr_t>(recs + limit));   // low word is enough: < 4 GiB of records
+    uint32_t* ep = a.entries + im.ent0 + n;
+    const uint32_t n_end = min(n + my_nnz, im.ent_cap & ~3u);
+    Lane ln;
+    ln.Init(SharedAddr(sm.words + tid * K1Smem<S>::kSlotStride), SharedAddr(sm.sched), key, me.end_bit);
+    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;   // the last four entries (oldest in q0): a group leaves as one 128-bit store
+    if (blk0 < limit && me.end_bit != 0) {
+        for (;;) {
+            const uint32_t win = ln.Peek();
+            uint32_t en = ln.Lookup(win);
+            if (IsLink(en)) en = ResolveLink(lv, en, ln.off, win);
+            const uint32_t nxt = ln.acc + en;
+            // RECEIVE + EXTEND (T.81 F.2.2.1) on the magnitude bits that follow the code; the DC
+            // difference goes to the block's record, every symbol with magnitude bits becomes an entry
+            // whose upper half is the zig-zag index AFTER the symbol (+ state bits K2 masks off)
+            asm volatile(
+                "{\n\t"
+                ".reg .pred pdc, pnz, pneg, pfl, pst;\n\t"
+                ".reg .b32 sz, bits, sh, t, rs, ex, m, v, zq;\n\t"
+                "shr.u32 sz, %7, 28;\n\t"
+                "and.b32 bits, %7, 31;\n\t"
+                "sub.u32 sh, bits, sz;\n\t"
+                "shl.b32 t, %8, sh;\n\t"
+                "sub.u32 rs, 32, sz;\n\t"
+                "shf.r.clamp.b32 ex, t, 0, rs;\n\t"
+                "bmsk.clamp.b32 m, 0, sz;\n\t"
+                "setp.lt.s32 pneg, t, 0;\n\t"
+                "selp.b32 m, 0, m, pneg;\n\t"
+                "sub.s32 v, ex, m;\n\t"
+                "and.b32 zq, %9, 0x7e00000;\n\t"
+                "setp.eq.u32 pdc, zq, 0;\n\t"
+                "@pdc st.global.u16 [%6+4], v;\n\t"
+                "setp.ne.u32 pnz, sz, 0;\n\t"
+                "shr.u32 zq, %10, 21;\n\t"
+                "@pnz mov.b32 %0, %1;\n\t"
+                "@pnz mov.b32 %1, %2;\n\t"
+                "@pnz mov.b32 %2, %3;\n\t"
+                "@pnz prmt.b32 %3, v, zq, 0x5410;\n\t"
+                "@pnz add.u32 %4, %4, 1;\n\t"
+                "and.b32 zq, %4, 3;\n\t"
+                "setp.eq.and.u32 pfl, zq, 0, pnz;\n\t"
+                "setp.le.and.u32 pst, %4, %11, pfl;\n\t"
+                "@pst st.global.v4.b32 [%5], {%0, %1, %2, %3};\n\t"
+                "@pfl add.u64 %5, %5, 16;\n\t"
+                "}"
+                : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(n), "+l"(ep)
+                : "l"(rp), "r"(en), "r"(win), "r"(ln.acc), "r"(nxt), "r"(n_end)
+                : "memory");
+            ln.CommitWrite(nxt, rp, n, rp_stop);
+            if (ln.acc & kAccStop) break;
         }
     }
-    if (cnt) {   // last, partial group: padded with zero entries (position 0, which K2 overwrites with the DC anyway)
-        for (; cnt < 4; cnt++) { q0 = q1; q1 = q2; q2 = q3; q3 = 0; }
-        if (n + 4 <= ent_cap) *reinterpret_cast<uint4*>(entries + n) = make_uint4(q0, q1, q2, q3);
+    if (n & 3u) {   // last, partial group: padded with entries for position 0, which K2 overwrites with the DC anyway
+        for (; n & 3u; n++) { q0 = q1; q1 = q2; q2 = q3; q3 = kPadEntry; }
+        if (n <= n_end) *reinterpret_cast<uint4*>(ep) = make_uint4(q0, q1, q2, q3);
+        ep += 4;
     }
+    // groups the counting pass reserved but this pass did not fill (symbols it saw in the padding
+    // after a restart interval's last block): pad them, the next block's range starts behind them
+    for (; n < n_end; n += 4, ep += 4) *reinterpret_cast<uint4*>(ep) = make_uint4(kPadEntry, kPadEntry, kPadEntry, kPadEntry);
 }
 
 // ---------------------------------------------------------------- DC prediction
+
+// DC difference of a block; 0 for a block no thread reached (damaged stream: the record still
+// holds the 0xFF fill)
+__device__ __forceinline__ int RecDc(const BlockRec& r) { return r.end == kNoEntry ? 0 : int(r.dc); }
 
 // Does MCU range [m0, m1) of an image contain a predictor reset? Returns the last one, or -1.
 __device__ __forceinline__ int64_t LastReset(int64_t m0, int64_t m1, int ri) {
@@ -524,8 +646,8 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_sums(K1Args a) {
     __syncthreads();
     int s[3] = {0, 0, 0};
     if (m < m1 && m >= reset) {
-        const int16_t* d = a.dcdiff + im.blk0 + m * im.bpm;
-        for (int k = 0; k < im.bpm; k++) s[im.mcu_comp[k]] += d[k];
+        const BlockRec* d = a.blk_rec + im.blk0 + m * im.bpm;
+        for (int k = 0; k < im.bpm; k++) s[im.mcu_comp[k]] += RecDc(d[k]);
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -557,9 +679,9 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
     int diffs[kMaxBlocksPerMcu];
     int s[3] = {0, 0, 0};
     if (active) {
-        const int16_t* d = a.dcdiff + im.blk0 + m * im.bpm;
+        const BlockRec* d = a.blk_rec + im.blk0 + m * im.bpm;
         for (int k = 0; k < im.bpm; k++) {
-            diffs[k] = d[k];
+            diffs[k] = RecDc(d[k]);
             s[im.mcu_comp[k]] += diffs[k];
         }
     }
@@ -619,13 +741,12 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
     // exclusive prefix = predictor values entering this MCU
     int pred[3] = {v0 + a0 - s[0], v1 + a1 - s[1], v2 + a2 - s[2]};
     if (reset_here) pred[0] = pred[1] = pred[2] = 0;
-    // absolute DC replaces the difference in the compact per-block array (K2 reads it from
-    // there: one coalesced 2-byte load per block instead of a scattered store per block here)
-    int16_t* out = a.dcdiff + im.blk0 + m * im.bpm;
+    // absolute DC replaces the difference in the block's record (K2 reads end index and DC together)
+    BlockRec* out = a.blk_rec + im.blk0 + m * im.bpm;
     for (int k = 0; k < im.bpm; k++) {
         const int comp = im.mcu_comp[k];
         pred[comp] += diffs[k];
-        out[k] = int16_t(pred[comp]);
+        out[k].dc = int16_t(pred[comp]);
     }
 }
 
@@ -659,9 +780,11 @@ __global__ void __launch_bounds__(256) gather_scans(const GatherItem* items, int
 
 template <int S>
 cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream) {
-    static_assert(sizeof(K1Smem<S>) <= 48 * 1024, "K1 shared memory exceeds the default limit");
-    if (round >= 0) k1_sync<S><<<a.total_ctas, T, sizeof(K1Smem<S>), stream>>>(a, round);
-    else k1_write<S><<<a.total_ctas, T, sizeof(K1Smem<S>), stream>>>(a);
+    static_assert(S <= 128, "the packed decoder state holds bit positions below 2048");
+    const size_t smem = offsetof(K1Smem<S>, lut) + a.lut_smem_bytes;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;   // 3 table pairs + the full second-level arena fit
+    if (round >= 0) k1_sync<S><<<a.total_ctas, T, smem, stream>>>(a, round);
+    else k1_write<S><<<a.total_ctas, T, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -8,7 +8,8 @@
 // jpeg_idct_islow on encoder-produced data (the zero-column shortcuts in
 // libjpeg are arithmetically identical to the general path, so none are taken).
 //
-// Input is K1's sparse coefficient stream: per block the index of its first entry, then one
+// Input is K1's sparse coefficient stream: per block the index one past its last entry (it begins
+// where the previous block of the image ends), one
 // 32-bit (zig-zag position, int16 value) entry per non-zero coefficient, plus the integrated DC
 // from the compact per-block array; the 8 threads of a block scatter the entries (dequantised)
 // into a zeroed shared-memory workspace. Mapping: 8 threads per block, 32
@@ -38,8 +39,7 @@ constexpr int kTilesPerCta = 4;
 // of one component), resolved once per tile by one thread.
 struct TileInfo {
     const uint32_t* entries; // image's coefficient entries
-    const uint2* blk_ent;    // image's per-block (first, end) entry index
-    const int16_t* dc;       // image DC base
+    const BlockRec* rec;     // image's per-block records (a block's entries begin where its predecessor's end)
     uint32_t ent_cap;
     const uint16_t* qt;      // natural-order quantiser table of the component
     uint8_t* out;            // plane address of (row by*8, column 0)
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
     __shared__ TileInfo s_tile[kTilesPerCta];
     __shared__ uint8_t s_zigzag[64];
     const int tid = threadIdx.x;
-    if (tid < 64) s_zigzag[tid] = c_zigzag_k2[tid];
+    if (tid < 64) s_zigzag[tid] = c_zigzag_k2[(tid + 63) & 63];   // entries carry position + 1 (huff_core.cuh)
     if (tid < kTilesPerCta) {
         // tile -> (image, component, block row, first block column); one search per tile, four
         // lanes in parallel; sampling factors are powers of two, so no division in the hot part
@@ -118,9 +118,8 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
                     const int H = im.hs[comp], V = im.vs[comp];
                     const int hs = __ffs(H) - 1, vs = __ffs(V) - 1;
                     ti.entries = a.entries + im.ent0;
-                    ti.blk_ent = reinterpret_cast<const uint2*>(a.blk_ent) + im.blk0;
+                    ti.rec = a.blk_rec + im.blk0;
                     ti.ent_cap = im.ent_cap;
-                    ti.dc = a.dc + im.blk0;
                     ti.qt = a.qtables + size_t(im.qt_index[comp]) * 64;
                     ti.pitch = im.plane_pitch[comp];
                     ti.out = a.planes + im.plane_off[comp] + size_t(by) * 8 * ti.pitch;
@@ -150,14 +149,16 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
         // expand the block's sparse entries into the zeroed workspace, dequantising on the way
         size_t blk = 0;
         uint32_t e0 = 0, e1 = 0;
+        int dc = 0;
         if (valid) {
             blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
             int* row = my + j * 9;
 #pragma unroll
             for (int w = 0; w < 8; w++) row[w] = 0;
-            const uint2 range = __ldg(ti.blk_ent + blk);
-            e0 = range.x;
-            e1 = range.y;
+            const uint2 r = __ldg(reinterpret_cast<const uint2*>(ti.rec + blk));
+            e0 = blk ? __ldg(&ti.rec[blk - 1].end) : 0u;
+            e1 = r.x;
+            dc = int(int16_t(r.y & 0xFFFFu));
             if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > ti.ent_cap) e1 = e0 = 0;   // never decoded
         }
         __syncwarp();
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
             my[(nat >> 3) * 9 + (nat & 7)] = int(int16_t(en & 0xFFFFu)) * int(__ldg(ti.qt + nat));
         }
         __syncwarp();
-        if (valid && j == 0) my[0] = int(__ldg(ti.dc + blk)) * int(__ldg(ti.qt));   // integrated DC replaces any DC-difference entry
+        if (valid && j == 0) my[0] = dc * int(__ldg(ti.qt));   // integrated DC replaces any DC-difference entry
         __syncwarp();
         int in[8], out[8];
         if (valid) {

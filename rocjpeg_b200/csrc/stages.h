@@ -14,12 +14,24 @@
 
 namespace rjb {
 
-constexpr int kK1Threads = 128;      // subsequences per CTA in K1
+constexpr int kK1Threads = 128;      // threads per CTA in K1, one subsequence each
+constexpr int kK1Halo = 2;           // leading threads that re-decode the previous CTA's last subsequences
+constexpr int kK1Owned = kK1Threads - kK1Halo;   // subsequences a K1 CTA owns
 constexpr int kDcTileMcus = 256;     // MCUs per DC-scan tile
 constexpr int kMaxSyncRounds = 8;    // counters kept per batch
 constexpr int kK3TileW = 256;        // output tile of the colour/layout stage, in luma samples
 constexpr int kK3TileH = 32;
-constexpr uint32_t kNoEntry = 0xFFFFFFFFu;   // blk_ent value of a block no thread reached (damaged streams)
+constexpr uint32_t kNoEntry = 0xFFFFFFFFu;   // BlockRec::end of a block no thread reached (damaged streams)
+
+// What K1 leaves per 8x8 block besides its coefficient entries (decode order, filled with 0xFF
+// before every decode): where its entries end — they begin where the previous block's end,
+// block 0 of an image at entry 0 — and its DC value: the difference after k1_write, the
+// integrated DC after dc_apply.
+struct BlockRec {
+    uint32_t end;   // index one past the block's last entry, relative to the image's stream
+    int16_t dc;
+    int16_t pad_;
+};
 
 struct K1Args {
     const ImageDesc* images;      // device
@@ -37,12 +49,12 @@ struct K1Args {
     int3* dc_partial;             // per DC tile: per-component DC sum after the tile's last reset
     uint32_t* counters;           // [kMaxSyncRounds] boundary changes per round, then [kMaxSyncRounds] decodes per round
     uint32_t* entries;            // coefficient entry arena (huff_core.cuh: MakeCoefEntry), decode order
-    uint32_t* blk_ent;            // per block: (first, end) index of its entries, relative to the image's stream
-    int16_t* dcdiff;              // one DC value per block: difference after k1_write, absolute after dc_apply
+    BlockRec* blk_rec;            // per block, decode order
     int nimages;
     uint32_t total_ctas;          // K1 CTAs in the batch
     uint32_t total_dc_tiles;
     int sub_bytes;                // subsequence size S in bytes: 32, 64 or 128
+    uint32_t lut_smem_bytes;      // shared memory for the Huffman tables: 4 KiB per table pair + the second-level arena (batch maximum)
 };
 
 // Speculative decode + CTA-local synchronisation (round 0) or cross-CTA fix-up (round >= 1).
@@ -57,8 +69,7 @@ struct K2Args {
     const uint32_t* img_tile0;    // nimages + 1: first IDCT tile of each image
     const uint16_t* qtables;      // natural-order u16[64] tables
     const uint32_t* entries;      // coefficient entries
-    const uint32_t* blk_ent;      // (first, end) entry index of every block (image-relative), kNoEntry when never decoded
-    const int16_t* dc;            // absolute DC per block (decode order)
+    const BlockRec* blk_rec;      // end-of-entries index + integrated DC of every block (decode order)
     uint8_t* planes;              // plane arena
     int nimages;
     uint32_t total_tiles;

@@ -31,10 +31,10 @@ struct HostLoader {
         return ByteSwap32(w);   // the core reads big-endian words
     }
 };
-// Mirrors k1_write in k1_huffman.cu: a sparse entry stream per image + per-block first-entry index.
+// Mirrors k1_write in k1_huffman.cu: a sparse entry stream per image + per-block end-of-entries index.
 struct HostSink {
     uint32_t* entries;
-    uint32_t* blk_ent;
+    uint32_t* blk_end;
     int16_t* dcdiff;
     uint32_t n;          // next entry index
     uint32_t cap;
@@ -43,11 +43,7 @@ struct HostSink {
         if (n < cap) entries[n] = MakeCoefEntry(pos, v);
         n++;
     }
-    uint32_t limit, nblocks;
-    void EndBlock(uint32_t blk) {
-        blk_ent[2 * blk + 1] = n;
-        if (blk + 1 < limit) blk_ent[2 * (blk + 1)] = n;
-    }
+    void EndBlock(uint32_t blk) { blk_end[blk] = n; }
 };
 struct SubInfo {
     uint32_t seg;
@@ -102,15 +98,17 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         }
     }
     const uint32_t nsub = uint32_t(subs.size());
+    // T = subsequences a CTA owns; its kK1Halo leading threads re-decode the subsequences before them
+    const uint32_t H = 2;
     const uint32_t nctas = (nsub + T - 1) / T;
     std::vector<uint32_t> state(nsub, 0), used(nsub, 0), nnzv(nsub, 0);
     NullSink nsink;
-    auto decode_from = [&](uint32_t g, uint32_t key) {
+    auto decode_from = [&](uint32_t g, uint32_t key, uint32_t* nnz_out) {
         uint32_t pb = StateOverflow(key), nb = 0, blk = 0, nnz = 0;
         int c = StateC(key), z = StateZ(key);
         HostLoader ld{clean + subs[g].start};
         DecodeSpan<false>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, nb, nnz, blk, 0xFFFFFFFFu, nsink);
-        nnzv[g] = (nnz + 3u) & ~3u;   // runs are padded to whole 16-byte stores
+        *nnz_out = (nnz + 3u) & ~3u;   // runs are padded to whole 16-byte stores
         uint32_t over = pb > subs[g].end_bit ? pb - subs[g].end_bit : 0;
         return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
     };
@@ -125,24 +123,31 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
                 bool need0 = !subs[g0].first && StateKey(prev_state[g0 - 1]) != used[g0];
                 if (!need0) continue;
             }
-            std::vector<uint32_t> old(state.begin() + g0, state.begin() + g1);
+            // local window: round 0 includes the halo, later rounds start at the first owned subsequence
+            const uint32_t lo = round == 0 ? (g0 >= H ? g0 - H : 0) : g0;
+            std::vector<uint32_t> lstate(g1 - lo), lused(g1 - lo), lnnz(g1 - lo);
+            for (uint32_t g = lo; g < g1; g++) {
+                lstate[g - lo] = round == 0 ? 0 : state[g];
+                lused[g - lo] = round == 0 ? 0 : used[g];
+                lnnz[g - lo] = round == 0 ? 0 : nnzv[g];
+            }
+            std::vector<uint32_t> old(lstate);
             if (round == 0)
-                for (uint32_t g = g0; g < g1; g++) {
-                    used[g] = 0;
-                    state[g] = decode_from(g, 0);
+                for (uint32_t g = lo; g < g1; g++) {
+                    lstate[g - lo] = decode_from(g, 0, &lnnz[g - lo]);
                     ndec++;
                 }
             for (uint32_t iter = 0;; iter++) {
-                std::vector<uint32_t> snap(state.begin() + g0, state.begin() + g1);
+                std::vector<uint32_t> snap(lstate);
                 bool any = false;
-                for (uint32_t g = g0; g < g1; g++) {
+                for (uint32_t g = lo; g < g1; g++) {
                     if (subs[g].first) continue;
-                    uint32_t in = used[g];
-                    if (g > g0) in = StateKey(snap[g - 1 - g0]);
+                    uint32_t in = lused[g - lo];
+                    if (g > lo) in = StateKey(snap[g - 1 - lo]);
                     else if (round > 0) in = StateKey(prev_state[g - 1]);
-                    if (in != used[g]) {
-                        state[g] = decode_from(g, in);
-                        used[g] = in;
+                    if (in != lused[g - lo]) {
+                        lstate[g - lo] = decode_from(g, in, &lnnz[g - lo]);
+                        lused[g - lo] = in;
                         ndec++;
                         any = true;
                     }
@@ -150,8 +155,13 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
                 if (stats) stats->max_local_iters = std::max(stats->max_local_iters, iter);
                 if (!any) break;
             }
+            for (uint32_t g = g0; g < g1; g++) {   // only owned results are stored
+                state[g] = lstate[g - lo];
+                used[g] = lused[g - lo];
+                nnzv[g] = lnnz[g - lo];
+            }
             const uint32_t gl = g0 + T - 1;
-            if (gl < nsub && !subs[gl].last && (round == 0 || StateKey(old[gl - g0]) != StateKey(state[gl]))) boundary_changes++;
+            if (gl < nsub && !subs[gl].last && (round == 0 || StateKey(old[gl - lo]) != StateKey(state[gl]))) boundary_changes++;
         }
         if (stats && round < 8) stats->decodes[round] = ndec;
         if (round > 0 && boundary_changes == 0) break;
@@ -177,7 +187,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     // the entry arena is NOT cleared on the device: start from garbage; per-block indices start
     // as "never decoded"
     const uint32_t cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 3 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
-    std::vector<uint32_t> entries(cap, 0x77777777u), blk_ent(size_t(nblocks) * 2, 0xFFFFFFFFu);
+    std::vector<uint32_t> entries(cap, 0x77777777u), blk_end(size_t(nblocks), 0xFFFFFFFFu);
     std::vector<int16_t> dcdiff(nblocks, int16_t(0x7777));
     uint32_t ent_run = 0;
     for (uint32_t cta = 0; cta < nctas; cta++) {
@@ -198,22 +208,22 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
             int c = StateC(key), z = StateZ(key);
             uint32_t blk = seg_blk_first[subs[g].seg] + excl;
             const uint32_t limit = seg_blk_first[subs[g].seg] + seg_blk_count[subs[g].seg];
-            HostSink sink{entries.data(), blk_ent.data(), dcdiff.data(), n0, cap, limit, nblocks};
-            if (subs[g].first && blk < limit) blk_ent[2 * blk] = n0;
+            HostSink sink{entries.data(), blk_end.data(), dcdiff.data(), n0, cap};
             HostLoader ld{clean + subs[g].start};
             DecodeSpan<true>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, cnt, nnz, blk, limit, sink);
             // counting pass and write pass must agree (the last thread of an interval may have counted padding)
             const uint32_t used_n = (sink.n - n0 + 3u) & ~3u;
             if (subs[g].last ? used_n > nnzv[g] : used_n != nnzv[g]) return -7;
-            for (uint32_t k2 = sink.n; k2 < n0 + used_n && k2 < cap; k2++) entries[k2] = 0;   // zero padding entries
+            // zero padding: the tail of the last group and the groups the counting pass reserved in vain
+            for (uint32_t k2 = sink.n; k2 < n0 + nnzv[g] && k2 < cap; k2++) entries[k2] = kPadEntry;
         }
     }
     // densify (what K2 / the coefficient tap do)
     std::vector<int16_t> coef(size_t(nblocks) * 64, 0);
     for (uint32_t b = 0; b < nblocks; b++) {
-        uint32_t e0 = blk_ent[2 * b], e1 = blk_ent[2 * b + 1];
+        uint32_t e0 = b ? blk_end[b - 1] : 0u, e1 = blk_end[b];   // a block begins where its predecessor ends
         if (e0 == 0xFFFFFFFFu || e1 == 0xFFFFFFFFu || e1 < e0 || e1 - e0 > 128u || e1 > cap) return -8;
-        for (uint32_t k2 = e0; k2 < e1; k2++) coef[size_t(b) * 64 + kZig[(entries[k2] >> 16) & 63u]] = int16_t(entries[k2] & 0xFFFFu);
+        for (uint32_t k2 = e0; k2 < e1; k2++) coef[size_t(b) * 64 + kZig[CoefEntryPos(entries[k2])]] = int16_t(entries[k2] & 0xFFFFu);
     }
     // DC integration per component, reset at restart intervals
     {
