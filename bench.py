@@ -210,6 +210,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inlib-devices", type=int, default=0,
+                    help="single process: shard each rocJpegDecodeBatched call over this many GPUs inside the library "
+                         "(ROCJPEG_B200_DEVICES), every destination on GPU 0; reported under e2e_inlib")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank decodes a full batch; strong: one batch sharded over the ranks by scan bytes")
     args = ap.parse_args()
@@ -321,6 +324,7 @@ def main():
     stats = dec.stats()
 
     # ---- end-to-end arm (e2e): the public call, host buffers in ------------------------
+    dec.set_profiling(False)                 # no stage events inside the timed call
     batch = dec.make_batch(streams, dests)   # the argument arrays a C caller holds ready
     for _ in range(args.warmup):
         assert dec.decode_batched(batch, params) == api.SUCCESS
@@ -347,6 +351,26 @@ def main():
         pd_s.append(time.perf_counter() - t0)
     clocks = sampler.stop()
     dec.set_profiling(False)
+    # optional: one process, the library shards the same call over several GPUs (destinations stay on this GPU)
+    inlib = None
+    if args.inlib_devices > 1 and world == 1:
+        os.environ["ROCJPEG_B200_DEVICES"] = str(args.inlib_devices)
+        decn = api.Decoder(api.BACKEND_HARDWARE, local_rank)
+        del os.environ["ROCJPEG_B200_DEVICES"]
+        for _ in range(args.warmup + 2):
+            assert decn.decode_batched(batch, params) == api.SUCCESS
+        ts = []
+        for _ in range(args.steps):
+            l2_flush()
+            t0 = time.perf_counter()
+            assert decn.decode_batched(batch, params) == api.SUCCESS
+            ts.append(time.perf_counter() - t0)
+        sn = decn.stats()
+        ms = 1e3 * sum(ts) / len(ts)
+        inlib = {"devices_requested": args.inlib_devices, "devices_used": int(sn.devices), "value": round(total_px / 1e6 / (ms / 1e3), 1),
+                 "unit": UNIT, "ms_per_step": round(ms, 4), "host_submit_ms": round(sn.host_submit_ms, 4),
+                 "host_wait_ms": round(sn.host_wait_ms, 4), "note": "one rocJpegDecodeBatched call sharded by the library, all destinations on GPU 0"}
+        decn.close()
 
     # max over ranks
     resident_ms, e2e_ms, pd_ms = rdist.max_over_ranks([resident_ms, e2e_ms, 1e3 * sum(pd_s) / len(pd_s)], "cuda")
@@ -397,7 +421,10 @@ def main():
                "decodes_per_round": [int(x) for x in stats.decodes_per_round[:stats.sync_rounds]],
                "compressed_GB_s_all_k1": round(scan / ((stage_ms[2] + stage_ms[3]) or 1e-9) / 1e6, 2)},
         "clocks": clocks, "resident_wall_s": round(resident_wall, 3),
+        "e2e_host": {"submit_ms": round(e2e_stats.host_submit_ms, 4), "wait_ms": round(e2e_stats.host_wait_ms, 4)},
     }
+    if inlib:
+        line["e2e_inlib"] = inlib
     if not args.no_cpu_baseline:
         mps, ips, threads, sample = run_cpu_baseline(datas, fmt, args.cpu_budget)
         line["cpu_baseline"] = {"value": round(mps, 2), "unit": UNIT, "images_per_s": round(ips, 1), "cores": threads, "kind": "port",

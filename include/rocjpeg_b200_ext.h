@@ -42,6 +42,9 @@ typedef struct {
     uint32_t kernel_launches;                 /* kernels launched by the last call */
     int32_t subsequence_bytes;                /* S chosen for the batch */
     int32_t lanes;                            /* pipeline lanes (streams) the batch was split over */
+    float host_submit_ms;                     /* host wall time of the last call spent describing the batch and enqueueing work */
+    float host_wait_ms;                       /* host wall time of the last call spent waiting for the device */
+    int32_t devices;                          /* GPUs the last call was sharded over (ROCJPEG_B200_DEVICES) */
 } RocJpegB200Stats;
 
 /* Enable/disable CUDA-event stage timing on a decoder handle (off by default; env ROCJPEG_B200_PROFILE=1). */
@@ -84,6 +87,16 @@ RocJpegStatus rocJpegB200StreamGetSegment(RocJpegStreamHandle jpeg_stream_handle
 RocJpegStatus rocJpegB200StreamGetQuantTable(RocJpegStreamHandle jpeg_stream_handle, int id, uint16_t out_natural[64]);
 RocJpegStatus rocJpegB200StreamGetHuffmanTable(RocJpegStreamHandle jpeg_stream_handle, int is_ac, int id, uint8_t bits[16],
                                                uint8_t vals[256], uint32_t *count);
+
+/* Multi-GPU sharding of rocJpegDecodeBatched (images are independent: no collective). With the
+ * environment variable ROCJPEG_B200_DEVICES=N (N > 1) set when rocJpegCreate runs, the handle also
+ * drives the N-1 devices after device_id; each batch is then split by the longest-processing-time
+ * rule over the devices, every device decodes its share concurrently and stores its pixels straight
+ * into the caller's buffers (peer access over NVLink), which must live on the handle's device.
+ * rocJpegB200PlanShards exposes the assignment rule (host only): cost[i] = entropy-coded bytes of
+ * image i, out_device[i] in [0, num_devices). rocJpegB200GetDeviceCount = devices the handle drives. */
+RocJpegStatus rocJpegB200PlanShards(const uint64_t *cost, int batch_size, int num_devices, int *out_device);
+RocJpegStatus rocJpegB200GetDeviceCount(RocJpegHandle handle, int *num_devices);
 
 const char *rocJpegB200Version(void);
 

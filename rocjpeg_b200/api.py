@@ -58,6 +58,7 @@ class Stats(C.Structure):
         ("subsequences", C.c_uint64), ("plane_bytes", C.c_uint64), ("output_bytes", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
         ("subsequence_bytes", C.c_int32), ("lanes", C.c_int32),
+        ("host_submit_ms", C.c_float), ("host_wait_ms", C.c_float), ("devices", C.c_int32),
     ]
 
 
@@ -82,6 +83,7 @@ EXT_EXPORTS = (
     "rocJpegB200SetProfiling", "rocJpegB200GetStats", "rocJpegB200Prepare", "rocJpegB200Run",
     "rocJpegB200GetCoefficients", "rocJpegB200GetPlanes", "rocJpegB200StreamGetInfo", "rocJpegB200StreamGetSegment",
     "rocJpegB200StreamGetQuantTable", "rocJpegB200StreamGetHuffmanTable", "rocJpegB200Version",
+    "rocJpegB200PlanShards", "rocJpegB200GetDeviceCount",
 )
 
 _lib = None
@@ -124,12 +126,24 @@ def load_library() -> C.CDLL:
     L.rocJpegB200StreamGetSegment.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_uint32)]
     L.rocJpegB200StreamGetQuantTable.argtypes = [vp, i32, vp]
     L.rocJpegB200StreamGetHuffmanTable.argtypes = [vp, i32, i32, vp, vp, C.POINTER(C.c_uint32)]
+    L.rocJpegB200PlanShards.argtypes = [vp, i32, i32, vp]
+    L.rocJpegB200GetDeviceCount.argtypes = [vp, C.POINTER(i32)]
     L.rocJpegB200Version.restype = C.c_char_p
     for name in EXPORTS + EXT_EXPORTS:
         if name not in ("rocJpegGetErrorName", "rocJpegB200Version"):
             getattr(L, name).restype = i32
     _lib = L
     return L
+
+
+def plan_shards(costs, num_devices: int):
+    """The longest-processing-time assignment rocJpegDecodeBatched uses when ROCJPEG_B200_DEVICES > 1."""
+    import numpy as np
+
+    c = np.ascontiguousarray(costs, dtype=np.uint64)
+    out = np.zeros(len(c), dtype=np.int32)
+    _check(load_library().rocJpegB200PlanShards(c.ctypes.data, len(c), num_devices, out.ctypes.data), "rocJpegB200PlanShards")
+    return out
 
 
 def error_name(status: int) -> str:
@@ -271,6 +285,11 @@ class Decoder:
 
     def run(self) -> int:
         return self.lib.rocJpegB200Run(self.handle)
+
+    def num_devices(self) -> int:
+        n = C.c_int()
+        _check(self.lib.rocJpegB200GetDeviceCount(self.handle, C.byref(n)), "rocJpegB200GetDeviceCount")
+        return n.value
 
     def set_profiling(self, on: bool):
         self.lib.rocJpegB200SetProfiling(self.handle, int(on))

@@ -227,6 +227,9 @@ RocJpegStatus rocJpegB200GetStats(RocJpegHandle handle, RocJpegB200Stats* stats)
     stats->kernel_launches = s.kernel_launches;
     stats->subsequence_bytes = s.sub_bytes;
     stats->lanes = s.lanes;
+    stats->host_submit_ms = s.host_submit_ms;
+    stats->host_wait_ms = s.host_wait_ms;
+    stats->devices = s.devices;
     return ROCJPEG_STATUS_SUCCESS;
 }
 
@@ -258,6 +261,18 @@ RocJpegStatus rocJpegB200Run(RocJpegHandle handle) {
         ERR(e.what());
         return ROCJPEG_STATUS_RUNTIME_ERROR;
     }
+}
+
+RocJpegStatus rocJpegB200PlanShards(const uint64_t* cost, int batch_size, int num_devices, int* out_device) {
+    if (cost == nullptr || out_device == nullptr || batch_size < 0 || num_devices < 1) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    rjb::PlanShards(cost, batch_size, num_devices, out_device);
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200GetDeviceCount(RocJpegHandle handle, int* num_devices) {
+    if (handle == nullptr || num_devices == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    *num_devices = static_cast<DecoderHandle*>(handle)->decoder->num_devices();
+    return ROCJPEG_STATUS_SUCCESS;
 }
 
 RocJpegStatus rocJpegB200GetCoefficients(RocJpegHandle handle, int index, int16_t* host_out, size_t count) {

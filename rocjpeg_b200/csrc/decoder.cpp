@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -134,7 +135,49 @@ int Decoder::Initialize() {
     RJB_CUDA(cudaStreamCreateWithFlags(&upload_stream_, cudaStreamNonBlocking));
     profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0) != 0;
     initialized_ = true;
+    // Multi-device sharding of rocJpegDecodeBatched (the C API has no way to ask for it, hence the
+    // environment variable): peers = the next devices after device_id, each reachable with peer
+    // access so that its output stage can store into buffers on this handle's device.
+    const int want = is_peer_ ? 1 : std::min(EnvInt("ROCJPEG_B200_DEVICES", 1), std::min(count, kMaxDevices));
+    for (int k = 1; k < want; k++) {
+        const int dev = (device_id_ + k) % count;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dev, device_id_) != cudaSuccess || !can) {
+            (void)cudaGetLastError();
+            std::cerr << "[WARN] rocjpeg_b200: device " << dev << " cannot access device " << device_id_ << " memory; not used for sharding" << std::endl;
+            continue;
+        }
+        std::unique_ptr<Decoder> peer(new Decoder(backend_, dev));
+        peer->is_peer_ = true;
+        if (peer->Initialize() != kSuccess) continue;
+        {
+            DeviceGuard pg(dev);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(device_id_, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+                (void)cudaGetLastError();
+                continue;
+            }
+            (void)cudaGetLastError();
+        }
+        peer->profiling_ = profiling_;
+        peers_.push_back(std::move(peer));
+    }
     return kSuccess;
+}
+
+void PlanShards(const uint64_t* cost, int n, int ndev, int* out_device) {
+    if (ndev < 1) ndev = 1;
+    std::vector<int> order(size_t(std::max(n, 0)));
+    for (int i = 0; i < n; i++) order[size_t(i)] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<uint64_t> load(size_t(ndev), 0);
+    for (int i : order) {
+        int best = 0;
+        for (int d = 1; d < ndev; d++)
+            if (load[size_t(d)] < load[size_t(best)]) best = d;
+        out_device[i] = best;
+        load[size_t(best)] += cost[i] + 1;   // +1: zero-cost images still spread out
+    }
 }
 
 // src/rocjpeg_decoder.cpp:307-358
@@ -190,6 +233,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     h_k3_tile0_.assign(size_t(n) + 1, 0);
     h_gather_.assign(size_t(n), GatherItem{});
     h_lut_ptrs_.clear();
+    h_lut_specs_.clear();
     h_lut_hashes_.clear();
     h_qtables_.assign(size_t(n) * 3 * 64, 1);
     stats_ = BatchStats();
@@ -253,10 +297,17 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         // Huffman table set, de-duplicated across the batch
         int set = -1;
         for (size_t s = 0; s < h_lut_hashes_.size(); s++)
-            if (h_lut_hashes_[s] == p.lut_hash && std::memcmp(h_lut_ptrs_[s], &streams[i]->lut(), sizeof(HuffLutSet)) == 0) set = int(s);
+            // same DHT content -> same decoder-form tables (they are a pure function of the four specs);
+            // comparing the 1 KiB of specs instead of the 14 KiB LUTs keeps this loop off the e2e profile
+            if (h_lut_hashes_[s] == p.lut_hash && std::memcmp(h_lut_specs_[s]->dc, p.dc, sizeof(p.dc)) == 0 &&
+                std::memcmp(h_lut_specs_[s]->ac, p.ac, sizeof(p.ac)) == 0) {
+                set = int(s);
+                break;
+            }
         if (set < 0) {
             set = int(h_lut_ptrs_.size());
             h_lut_ptrs_.push_back(&streams[i]->lut());
+            h_lut_specs_.push_back(&p);
             h_lut_hashes_.push_back(p.lut_hash);
         }
         im.lut_set = set;
@@ -630,13 +681,100 @@ int Decoder::Decode(const StreamParser* const* streams, int n, const DecodeParam
     if (!initialized_) return Fail(kNotInitialized, "decoder not initialised");
     if (!streams || !dsts || n < 0) return kInvalidParameter;
     if (n == 0) return kSuccess;
+    sharded_ = false;
+    if (!peers_.empty() && n >= 2) return DecodeSharded(streams, n, params, dsts);
     DeviceGuard guard(device_id_);
     prepared_ = false;
+    const auto t0 = std::chrono::steady_clock::now();
     int st = BuildAll(streams, n, params, dsts, true);
     if (st != kSuccess) return st;
+    const auto t1 = std::chrono::steady_clock::now();
     st = FinishAll();
+    const auto t2 = std::chrono::steady_clock::now();
+    stats_.host_submit_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+    stats_.host_wait_ms = std::chrono::duration<float, std::milli>(t2 - t1).count();
     prepared_ = (st == kSuccess);
     return st;
+}
+
+int Decoder::Submit(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
+    DeviceGuard guard(device_id_);
+    prepared_ = false;
+    return BuildAll(streams, n, params, dsts, true);
+}
+
+int Decoder::Wait() {
+    DeviceGuard guard(device_id_);
+    int st = FinishAll();
+    prepared_ = (st == kSuccess);
+    return st;
+}
+
+int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int ndev = 1 + int(peers_.size());
+    // validate first so that an error leaves every destination untouched on every device
+    std::vector<uint64_t> cost(static_cast<size_t>(n), 0);
+    for (int i = 0; i < n; i++) {
+        if (!streams[i]) return Fail(kInvalidParameter, "null stream handle in batch");
+        const ParsedJpeg& p = streams[i]->parsed();
+        if (!p.valid) return Fail(kBadJpeg, "stream handle holds no successfully parsed JPEG");
+        if (p.support_status != kSuccess) return Fail(p.support_status, "unsupported or inconsistent JPEG");
+        cost[size_t(i)] = p.clean_bytes;
+    }
+    shard_dev_.assign(size_t(n), 0);
+    shard_local_.assign(size_t(n), 0);
+    PlanShards(cost.data(), n, ndev, shard_dev_.data());
+    std::vector<std::vector<const StreamParser*>> sub_streams(static_cast<size_t>(ndev));
+    std::vector<std::vector<DestImage>> sub_dsts(static_cast<size_t>(ndev));
+    for (int i = 0; i < n; i++) {
+        const size_t d = size_t(shard_dev_[size_t(i)]);
+        shard_local_[size_t(i)] = int(sub_streams[d].size());
+        sub_streams[d].push_back(streams[i]);
+        sub_dsts[d].push_back(dsts[i]);
+    }
+    // enqueue everything on every device, then join: the devices run concurrently
+    int status = kSuccess;
+    std::vector<char> submitted(static_cast<size_t>(ndev), 0);
+    for (int d = 0; d < ndev && status == kSuccess; d++) {
+        if (sub_streams[size_t(d)].empty()) continue;
+        Decoder* dec = d == 0 ? this : peers_[size_t(d - 1)].get();
+        const int st = dec->Submit(sub_streams[size_t(d)].data(), int(sub_streams[size_t(d)].size()), params, sub_dsts[size_t(d)].data());
+        if (st != kSuccess) status = Fail(st, dec->last_error());
+        else submitted[size_t(d)] = 1;
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    BatchStats total;
+    total.devices = 0;
+    for (int d = 0; d < ndev; d++) {
+        if (!submitted[size_t(d)]) continue;
+        Decoder* dec = d == 0 ? this : peers_[size_t(d - 1)].get();
+        const int st = dec->Wait();
+        if (st != kSuccess && status == kSuccess) status = Fail(st, dec->last_error());
+        const BatchStats& s = dec->stats_;
+        for (int i = 0; i < kStageCount; i++) total.stage_ms[i] += s.stage_ms[i];
+        total.total_ms = std::max(total.total_ms, s.total_ms);
+        total.sync_rounds = std::max(total.sync_rounds, s.sync_rounds);
+        for (int r = 0; r < kMaxSyncRounds; r++) total.decodes_per_round[r] += s.decodes_per_round[r];
+        total.scan_bytes += s.scan_bytes;
+        total.blocks += s.blocks;
+        total.subsequences += s.subsequences;
+        total.plane_bytes += s.plane_bytes;
+        total.output_bytes += s.output_bytes;
+        total.h2d_bytes += s.h2d_bytes;
+        total.d2h_bytes += s.d2h_bytes;
+        total.kernel_launches += s.kernel_launches;
+        total.sub_bytes = std::max(total.sub_bytes, s.sub_bytes);
+        total.lanes += s.lanes;
+        total.devices++;
+    }
+    const auto t2 = std::chrono::steady_clock::now();
+    stats_ = total;
+    stats_.host_submit_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+    stats_.host_wait_ms = std::chrono::duration<float, std::milli>(t2 - t1).count();
+    sharded_ = (status == kSuccess);
+    if (status != kSuccess) prepared_ = false;
+    return status;
 }
 
 int Decoder::Prepare(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
@@ -668,6 +806,12 @@ int Decoder::Run() {
 
 int Decoder::CopyCoefficients(int image, int16_t* host_out, size_t count) {
     std::lock_guard<std::mutex> lock(mutex_);
+    if (sharded_) {
+        if (image < 0 || size_t(image) >= shard_dev_.size()) return kInvalidParameter;
+        const int d = shard_dev_[size_t(image)];
+        if (d > 0) return peers_[size_t(d - 1)]->CopyCoefficients(shard_local_[size_t(image)], host_out, count);
+        image = shard_local_[size_t(image)];
+    }
     if (!prepared_ || image < 0 || image >= chunk_first_[active_lanes_] || !host_out) return kInvalidParameter;
     DeviceGuard guard(device_id_);
     int l = 0;
@@ -677,6 +821,12 @@ int Decoder::CopyCoefficients(int image, int16_t* host_out, size_t count) {
 
 int Decoder::CopyPlanes(int image, uint8_t* host_out, size_t count) {
     std::lock_guard<std::mutex> lock(mutex_);
+    if (sharded_) {
+        if (image < 0 || size_t(image) >= shard_dev_.size()) return kInvalidParameter;
+        const int d = shard_dev_[size_t(image)];
+        if (d > 0) return peers_[size_t(d - 1)]->CopyPlanes(shard_local_[size_t(image)], host_out, count);
+        image = shard_local_[size_t(image)];
+    }
     if (!prepared_ || image < 0 || image >= chunk_first_[active_lanes_] || !host_out) return kInvalidParameter;
     DeviceGuard guard(device_id_);
     int l = 0;

@@ -76,6 +76,8 @@ struct BatchStats {
     uint32_t kernel_launches = 0;
     int sub_bytes = 0;
     int lanes = 0;                      // pipeline lanes (chunks) the batch was split over
+    float host_submit_ms = 0, host_wait_ms = 0;   // host wall time: describing + enqueueing / waiting for the device
+    int devices = 1;                    // GPUs the call was sharded over
 };
 
 // One pipeline lane: a CUDA stream, its device arenas and the description of the
@@ -120,6 +122,7 @@ class Lane {
     std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_;
     std::vector<GatherItem> h_gather_;
     std::vector<const HuffLutSet*> h_lut_ptrs_;
+    std::vector<const ParsedJpeg*> h_lut_specs_;
     std::vector<uint64_t> h_lut_hashes_;
     std::vector<uint16_t> h_qtables_;
     K1Args k1_ = {};
@@ -138,6 +141,13 @@ class Lane {
 };
 
 constexpr int kMaxLanes = 4;
+constexpr int kMaxDevices = 16;
+
+// Longest-processing-time-first assignment of `n` independent images (cost = entropy-coded bytes)
+// to `ndev` devices: images in decreasing cost order, each to the least loaded device. Images are
+// independent units (no exchange step), so this is the whole "parallelism
+// plan" of a sharded rocJpegDecodeBatched. out_device[i] in [0, ndev).
+void PlanShards(const uint64_t* cost, int n, int ndev, int* out_device);
 
 class Decoder {
   public:
@@ -156,8 +166,16 @@ class Decoder {
     const BatchStats& stats() const { return stats_; }
     const std::string& last_error() const { return err_; }
     int device_id() const { return device_id_; }
+    int num_devices() const { return 1 + int(peers_.size()); }
 
   private:
+    // Sharded form of Decode: the batch is split over this handle's device and its peers
+    // (ROCJPEG_B200_DEVICES), every device runs the whole pipeline on its share concurrently and
+    // writes its pixels straight into the caller's buffers (peer stores over NVLink when the
+    // buffer lives on another GPU). No collective: the join is one stream sync per device.
+    int DecodeSharded(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
+    int Submit(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);   // async part
+    int Wait();
     int Fail(int status, const std::string& why);
     int Split(const StreamParser* const* streams, int n);
     int BuildAll(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, bool launch);
@@ -174,6 +192,11 @@ class Decoder {
     int active_lanes_ = 0;
     int chunk_first_[kMaxLanes + 1] = {};   // image range of each lane's chunk
     BatchStats stats_;
+    // multi-device sharding
+    bool is_peer_ = false;                          // a peer never shards further
+    std::vector<std::unique_ptr<Decoder>> peers_;   // decoders on the other devices, owned by the handle's decoder
+    std::vector<int> shard_dev_, shard_local_;      // image -> (0 = this device, k = peers_[k-1]; index inside that device's share)
+    bool sharded_ = false;
 };
 
 }  // namespace rjb

@@ -295,3 +295,42 @@ def test_reference_samples_batched_and_perf(tmp_path):
     r = subprocess.run([os.path.join(SAMPLES, "jpegdecodeperf"), "-i", str(src), "-fmt", "native", "-t", "2", "-b", "3"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_batched_decode_sharded_over_two_devices(orc, monkeypatch):
+    """ROCJPEG_B200_DEVICES=2: one rocJpegDecodeBatched call split over two GPUs (no collective), every
+    destination on device 0, peers store through peer access. Bit-exact like the single-device path."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    monkeypatch.setenv("ROCJPEG_B200_DEVICES", "2")
+    torch.cuda.set_device(0)
+    d2 = api.Decoder(api.BACKEND_HARDWARE, 0)
+    try:
+        if d2.num_devices() < 2:
+            pytest.skip("no peer access between device 0 and 1")
+        names = [n for n in CASES] * 2
+        datas = [load(n) for n in names]
+        for fmt in ("rgb", "yuv_planar"):
+            streams, dests, keep = [], [], []
+            for d in datas:
+                s = api.JpegStream()
+                assert s.parse(d) == api.SUCCESS
+                rc, info = orc.parse(d)
+                dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, fmt, (0, 0, 0, 0))
+                streams.append(s); dests.append(dest); keep.append((bufs, pitches, shapes))
+            assert d2.decode_batched(streams, api.make_params(fmt), dests) == api.SUCCESS
+            st = d2.stats()
+            assert st.devices == 2
+            for k, d in enumerate(datas):
+                bufs, pitches, shapes = keep[k]
+                got = gu.fetch(bufs, pitches, shapes)
+                _, want = gu.oracle_outputs(orc, d, fmt, (0, 0, 0, 0), pitches)
+                gu.assert_same(got, want, f"sharded {names[k]} {fmt}")
+                rc, info = orc.parse(d)
+                n = sum(info.blocks_w[c] * info.blocks_h[c] * 64 for c in range(info.ncomp))
+                coefs = np.concatenate([c.reshape(-1) for c in orc.coefficients(d, info)])
+                assert np.array_equal(d2.coefficients(k, n), coefs), f"sharded {names[k]}: coefficients"
+    finally:
+        d2.close()

@@ -214,3 +214,27 @@ def test_k1_schedule_model_matches_oracle(k1_model, orc, name):
         assert k1_model.k1_model_decode(data, len(data), S, T, out.ctypes.data, out.size, C.byref(st)) == 0
         assert np.array_equal(out, want), (name, S, T)
         assert st.rounds >= 2
+
+
+# ---------------------------------------------------------------- multi-device plan (host only)
+
+def test_shard_plan_is_lpt_and_balanced():
+    rng = np.random.default_rng(3)
+    costs = rng.integers(1_000, 400_000, size=257).astype(np.uint64)
+    for ndev in (1, 2, 3, 4, 8):
+        dev = api.plan_shards(costs, ndev)
+        assert dev.min() >= 0 and dev.max() < ndev
+        loads = np.array([costs[dev == d].sum() for d in range(ndev)], dtype=np.float64)
+        # LPT guarantee: no device exceeds the mean by more than the largest single image
+        assert loads.max() - loads.mean() <= costs.max()
+        # reference implementation of the same rule
+        order = sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i))
+        load = [0] * ndev
+        want = [0] * len(costs)
+        for i in order:
+            d = min(range(ndev), key=lambda k: (load[k], k))
+            want[i] = d
+            load[d] += int(costs[i]) + 1
+        assert dev.tolist() == want
+    assert api.plan_shards([], 4).size == 0
+    assert api.plan_shards([5, 5, 5, 5], 2).tolist() == [0, 1, 0, 1]
