@@ -257,6 +257,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     stats_.sub_bytes = S;
 
     needs_clear_ = false;
+    any_direct_ = false;
+    const bool direct_ok = EnvInt("ROCJPEG_B200_NO_DIRECT", 0) == 0;
     uint64_t scan_off = 0, blk = 0, plane_off = 0, ent = 0;
     uint32_t sub = 0, dctile = 0, k2tile = 0, k3tile = 0, chunk = 0, max_pairs = 1, max_sub = 0;
     all_pinned_ = true;
@@ -378,8 +380,15 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             od.dst[c] = dsts[i].channel[c];
             od.dst_pitch[c] = dsts[i].pitch[c];
         }
-        od.tiles_x = uint32_t((od.w + kK3TileW - 1) / kK3TileW);
-        od.tiles_y = uint32_t((od.h + kK3TileH - 1) / kK3TileH);
+        // Planar formats without a crop need no output stage: the IDCT stage stores the planes straight
+        // into the caller's channels (4:2:2 / 4:2:0 NATIVE are interleaved surfaces and keep their tiles).
+        const bool whole = od.x0 == 0 && od.y0 == 0 && od.w == p.width && od.h == p.height;
+        const bool planar = od.fmt == FMT_Y || od.fmt == FMT_YUV_PLANAR ||
+                            (od.fmt == FMT_NATIVE && (p.css == CSS_444 || p.css == CSS_440 || p.css == CSS_400));
+        od.direct = (whole && planar && direct_ok) ? 1 : 0;
+        od.tiles_x = od.direct ? 0u : uint32_t((od.w + kK3TileW - 1) / kK3TileW);
+        od.tiles_y = od.direct ? 0u : uint32_t((od.h + kK3TileH - 1) / kK3TileH);
+        any_direct_ = any_direct_ || od.direct;
         od.tile0 = k3tile;
         h_k3_tile0_[size_t(i)] = k3tile;
         k3tile += od.tiles_x * od.tiles_y;
@@ -462,6 +471,8 @@ int Lane::Upload(cudaStream_t up) {
     RJB_CUDA(d_subseg_.Reserve(nsub_total_ * 4 + 256));
     RJB_CUDA(d_cta_partial_.Reserve(size_t(k1_.total_ctas) * 8 + 256));
     RJB_CUDA(d_dc_partial_.Reserve(size_t(k1_.total_dc_tiles) * 12 + 256));
+    RJB_CUDA(d_dc_carry_.Reserve(size_t(k1_.total_dc_tiles) * 12 + 256));
+    RJB_CUDA(d_cta_carry_.Reserve(size_t(k1_.total_ctas) * 8 + 256));
     RJB_CUDA(d_counters_.Reserve(256));
     if (!h_counters_.Reserve(256)) return Fail(kOutOfMemory, "counter staging");
 
@@ -477,12 +488,16 @@ int Lane::Upload(cudaStream_t up) {
     k1_.sub_seg = d_subseg_.as<uint32_t>();
     k1_.cta_partial = d_cta_partial_.as<uint2>();
     k1_.dc_partial = d_dc_partial_.as<int3>();
+    k1_.dc_carry = d_dc_carry_.as<int3>();
+    k1_.cta_carry = d_cta_carry_.as<uint2>();
     k1_.counters = d_counters_.as<uint32_t>();
     k1_.entries = d_entries_.as<uint32_t>();
     k1_.blk_rec = d_blkrec_.as<BlockRec>();
     k1_.nnz = d_nnz_.as<uint32_t>();
     k1_.cta_entries = d_cta_entries_.as<uint32_t>();
     k2_.images = k1_.images;
+    k2_.outputs = reinterpret_cast<const OutputDesc*>(d + L.outputs);
+    k2_.force_planes = 0;
     k2_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k2tile0);
     k2_.qtables = reinterpret_cast<const uint16_t*>(d + L.qtables);
     k2_.entries = k1_.entries;
@@ -539,7 +554,7 @@ int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up) {
     RJB_CUDA(mark(6));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + 1 + 2 + 1 + 1 + 2;   // + the two memsets
+    stats_.kernel_launches += uint32_t(rounds) + 2 + 3 + 1 + 1 + 2;   // sync rounds, scan + write, 3 DC kernels, IDCT, output, + the two memsets
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), d_counters_.as<uint8_t>(), 256, cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256;
     return kSuccess;
@@ -572,7 +587,7 @@ int Lane::Finish(bool profiling_) {
         RJB_CUDA(LaunchK2Idct(k2_, stream_));
         RJB_CUDA(LaunchK3Output(k3_, stream_));
         RJB_CUDA(cudaStreamSynchronize(stream_));
-        stats_.kernel_launches += 5;
+        stats_.kernel_launches += 7;
     }
     for (int r = 0; r < kMaxSyncRounds; r++) stats_.decodes_per_round[r] = cnt[kMaxSyncRounds + r];
     if (profiling_) {
@@ -875,6 +890,12 @@ int Lane::CopyPlanes(int image, uint8_t* host_out, size_t count) {
     size_t need = 0;
     for (int c = 0; c < im.ncomp; c++) need += size_t(im.blocks_w[c]) * im.blocks_h[c] * 64;
     if (count < need) return kInvalidParameter;
+    if (any_direct_) {   // the planes of this batch went straight to the caller: produce them in the arena for the tap
+        K2Args k2 = k2_;
+        k2.force_planes = 1;
+        RJB_CUDA(LaunchK2Idct(k2, stream_));
+        RJB_CUDA(cudaStreamSynchronize(stream_));
+    }
     size_t base = 0;
     for (int c = 0; c < im.ncomp; c++) {
         const size_t w = size_t(im.blocks_w[c]) * 8, h = size_t(im.blocks_h[c]) * 8;

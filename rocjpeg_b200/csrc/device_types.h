@@ -89,6 +89,8 @@ struct OutputDesc {
     int32_t fmt;
     uint32_t tile0;          // first output tile of this image
     uint32_t tiles_x, tiles_y;
+    int32_t direct;          // the IDCT stage stores this image's planes straight into dst (planar formats, no crop): no output tiles
+    int32_t pad_;
 };
 
 }  // namespace rjb

@@ -457,6 +457,67 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     if (tid == 0) a.cta_entries[cta] = red[2];
 }
 
+// ---------------------------------------------------------------- k1_scan
+//
+// One CTA per image: exclusive scan over the image's CTA partials, kScanThreads at a time. Block
+// positions are a segmented sum (a CTA holding a restart-interval start cuts the chain: its
+// partial already counts only the blocks after its last start), entry offsets a plain sum.
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads) k1_scan(K1Args a) {
+    __shared__ uint32_t s_v[kScanThreads / 32], s_f[kScanThreads / 32], s_e[kScanThreads / 32];
+    const uint32_t img = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c0 = a.img_cta0[img], c1 = a.img_cta0[img + 1];
+    uint32_t carry_b = 0, carry_e = 0;   // what enters the current chunk (same in every thread)
+    for (uint32_t base = c0; base < c1; base += kScanThreads) {
+        const uint32_t k = base + tid;
+        uint2 part = make_uint2(0u, 0u);
+        uint32_t ents = 0;
+        if (k < c1) {
+            part = a.cta_partial[k];
+            ents = a.cta_entries[k];
+        }
+        uint32_t f = part.x ? 1u : 0u, v = part.y, e = ents;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t pv = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            const uint32_t pf = __shfl_up_sync(0xFFFFFFFFu, f, d);
+            const uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, e, d);
+            if (lane >= d) {
+                if (!f) v += pv;
+                f |= pf;
+                e += pe;
+            }
+        }
+        __syncthreads();   // previous iteration's readers are done
+        if (lane == 31) { s_v[warp] = v; s_f[warp] = f; s_e[warp] = e; }
+        __syncthreads();
+        // what precedes this warp inside the chunk, then the chunk's own carry
+        uint32_t pre_v = 0, pre_f = 0, pre_e = 0;
+        for (int w = 0; w < warp; w++) {
+            pre_v = s_f[w] ? s_v[w] : pre_v + s_v[w];
+            pre_f |= s_f[w];
+            pre_e += s_e[w];
+        }
+        if (!pre_f) pre_v += carry_b;
+        pre_e += carry_e;
+        // inclusive -> exclusive inside the warp
+        uint32_t xv = __shfl_up_sync(0xFFFFFFFFu, v, 1), xf = __shfl_up_sync(0xFFFFFFFFu, f, 1), xe = __shfl_up_sync(0xFFFFFFFFu, e, 1);
+        if (lane == 0) { xv = 0; xf = 0; xe = 0; }
+        if (k < c1) a.cta_carry[k] = make_uint2(xf ? xv : xv + pre_v, xe + pre_e);
+        // carry into the next chunk = inclusive value at the chunk's last element
+        uint32_t tot_v = 0, tot_f = 0, tot_e = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) {
+            tot_v = s_f[w] ? s_v[w] : tot_v + s_v[w];
+            tot_f |= s_f[w];
+            tot_e += s_e[w];
+        }
+        carry_b = tot_f ? tot_v : tot_v + carry_b;
+        carry_e += tot_e;
+    }
+}
+
 // ---------------------------------------------------------------- k1_write
 
 template <int S>
@@ -496,33 +557,12 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     uint32_t* wents = sm.scratch + 8;     // [4] warp entry totals
     uint32_t* carry_s = sm.scratch + 12;  // [2] look-back results: blocks, entries
     if (lane == 31) { wsum[warp] = v; wflag[warp] = f; wents[warp] = e; }
-    // look-back over previous CTAs of the same image (warp 0)
-    if (warp == 0) {
-        uint32_t carry = 0, ecarry = 0;
-        const uint32_t first_cta = a.img_cta0[img];
-        bool done = false;
-        for (int64_t k = int64_t(cta) - 1; k >= int64_t(first_cta); k -= 32) {
-            const int64_t idx = k - lane;
-            uint2 part = make_uint2(0u, 0u);
-            uint32_t ents = 0;
-            if (idx >= int64_t(first_cta)) {
-                part = a.cta_partial[idx];
-                ents = a.cta_entries[idx];
-            }
-            if (!done) {
-                const uint32_t flagged = __ballot_sync(0xFFFFFFFFu, part.x != 0);
-                const int stop = flagged ? __ffs(flagged) - 1 : 31;   // nearest CTA (smallest lane) holding a start
-                uint32_t contrib = (lane <= stop) ? part.y : 0u;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, d);
-                carry += contrib;
-                done = flagged != 0;
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) ents += __shfl_xor_sync(0xFFFFFFFFu, ents, d);
-            ecarry += ents;
-        }
-        if (lane == 0) { carry_s[0] = carry; carry_s[1] = ecarry; }
+    // what enters this CTA from the previous CTAs of the image: k1_scan prepared it (a look-back here
+    // would re-read every earlier partial of the image, quadratic for the 8192x8192 pictures)
+    if (tid == 0) {
+        const uint2 cin = a.cta_carry[cta];
+        carry_s[0] = cin.x;
+        carry_s[1] = cin.y;
     }
     __syncthreads();
     uint32_t add = 0, eadd = carry_s[1];
@@ -660,6 +700,62 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_sums(K1Args a) {
     if (tid == 0) a.dc_partial[tile] = make_int3(red[0], red[1], red[2]);
 }
 
+// One CTA per image: exclusive segmented scan over the image's DC-tile sums (a tile that
+// contains a predictor reset cuts the chain; its sums already start at its last reset).
+__global__ void __launch_bounds__(kScanThreads) dc_scan(K1Args a) {
+    __shared__ int s_v[kScanThreads / 32][3];
+    __shared__ uint32_t s_f[kScanThreads / 32];
+    const uint32_t img = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ImageDesc& im = a.images[img];
+    const uint32_t t0 = a.img_dctile0[img], t1 = a.img_dctile0[img + 1];
+    const int ri = im.restart_interval;
+    int c0 = 0, c1 = 0, c2 = 0;   // predictors entering the current chunk
+    for (uint32_t base = t0; base < t1; base += kScanThreads) {
+        const uint32_t k = base + tid;
+        int3 part = make_int3(0, 0, 0);
+        uint32_t f = 0;
+        if (k < t1) {
+            part = a.dc_partial[k];
+            const int64_t m0 = int64_t(k - t0) * kDcTileMcus;
+            f = LastReset(m0, min(m0 + kDcTileMcus, int64_t(im.total_mcus)), ri) >= 0 ? 1u : 0u;
+        }
+        int v0 = part.x, v1 = part.y, v2 = part.z;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int p0 = __shfl_up_sync(0xFFFFFFFFu, v0, d);
+            const int p1 = __shfl_up_sync(0xFFFFFFFFu, v1, d);
+            const int p2 = __shfl_up_sync(0xFFFFFFFFu, v2, d);
+            const uint32_t pf = __shfl_up_sync(0xFFFFFFFFu, f, d);
+            if (lane >= d) {
+                if (!f) { v0 += p0; v1 += p1; v2 += p2; }
+                f |= pf;
+            }
+        }
+        __syncthreads();
+        if (lane == 31) { s_v[warp][0] = v0; s_v[warp][1] = v1; s_v[warp][2] = v2; s_f[warp] = f; }
+        __syncthreads();
+        int q0 = 0, q1 = 0, q2 = 0;
+        uint32_t qf = 0;
+        for (int w = 0; w < warp; w++) {
+            if (s_f[w]) { q0 = s_v[w][0]; q1 = s_v[w][1]; q2 = s_v[w][2]; } else { q0 += s_v[w][0]; q1 += s_v[w][1]; q2 += s_v[w][2]; }
+            qf |= s_f[w];
+        }
+        if (!qf) { q0 += c0; q1 += c1; q2 += c2; }
+        int x0 = __shfl_up_sync(0xFFFFFFFFu, v0, 1), x1 = __shfl_up_sync(0xFFFFFFFFu, v1, 1), x2 = __shfl_up_sync(0xFFFFFFFFu, v2, 1);
+        uint32_t xf = __shfl_up_sync(0xFFFFFFFFu, f, 1);
+        if (lane == 0) { x0 = x1 = x2 = 0; xf = 0; }
+        if (k < t1) a.dc_carry[k] = xf ? make_int3(x0, x1, x2) : make_int3(x0 + q0, x1 + q1, x2 + q2);
+        int w0 = 0, w1 = 0, w2 = 0;
+        uint32_t wf = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) {
+            if (s_f[w]) { w0 = s_v[w][0]; w1 = s_v[w][1]; w2 = s_v[w][2]; } else { w0 += s_v[w][0]; w1 += s_v[w][1]; w2 += s_v[w][2]; }
+            wf |= s_f[w];
+        }
+        if (wf) { c0 = w0; c1 = w1; c2 = w2; } else { c0 += w0; c1 += w1; c2 += w2; }
+    }
+}
+
 __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
     __shared__ int wsum[8][3];
     __shared__ int wflag[8];
@@ -700,34 +796,9 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
         }
     }
     if (lane == 31) { wsum[warp][0] = v0; wsum[warp][1] = v1; wsum[warp][2] = v2; wflag[warp] = int(f); }
-    if (warp == 0) {
-        // look-back over earlier tiles of the image until one that contains a reset (tile 0 always does)
-        int c0 = 0, c1 = 0, c2 = 0;
-        int64_t k = int64_t(tile) - 1;
-        bool done = (tile == tile_first);
-        while (!done && k >= int64_t(tile_first)) {
-            const int64_t idx = k - lane;
-            int3 part = make_int3(0, 0, 0);
-            bool has_reset = false;
-            if (idx >= int64_t(tile_first)) {
-                part = a.dc_partial[idx];
-                const int64_t t0 = (idx - tile_first) * kDcTileMcus;
-                has_reset = LastReset(t0, min(t0 + kDcTileMcus, int64_t(im.total_mcus)), ri) >= 0;
-            }
-            const uint32_t flagged = __ballot_sync(0xFFFFFFFFu, has_reset);
-            const int stop = flagged ? __ffs(flagged) - 1 : 31;
-            int q0 = lane <= stop ? part.x : 0, q1 = lane <= stop ? part.y : 0, q2 = lane <= stop ? part.z : 0;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                q0 += __shfl_xor_sync(0xFFFFFFFFu, q0, d);
-                q1 += __shfl_xor_sync(0xFFFFFFFFu, q1, d);
-                q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, d);
-            }
-            c0 += q0; c1 += q1; c2 += q2;
-            done = flagged != 0;
-            k -= 32;
-        }
-        if (lane == 0) { carry_s[0] = c0; carry_s[1] = c1; carry_s[2] = c2; }
+    if (tid == 0) {   // predictors entering the tile, prepared by dc_scan
+        const int3 cin = a.dc_carry[tile];
+        carry_s[0] = cin.x; carry_s[1] = cin.y; carry_s[2] = cin.z;
     }
     __syncthreads();
     bool open = (f == 0);
@@ -802,6 +873,7 @@ cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream) {
 
 cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream) {
     if (a.total_ctas == 0) return cudaSuccess;
+    k1_scan<<<a.nimages, kScanThreads, 0, stream>>>(a);
     switch (a.sub_bytes) {
         case 32: return SyncImpl<32>(a, -1, stream);
         case 64: return SyncImpl<64>(a, -1, stream);
@@ -813,6 +885,7 @@ cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream) {
 cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream) {
     if (a.total_dc_tiles == 0) return cudaSuccess;
     dc_sums<<<a.total_dc_tiles, kDcTileMcus, 0, stream>>>(a);
+    dc_scan<<<a.nimages, kScanThreads, 0, stream>>>(a);
     dc_apply<<<a.total_dc_tiles, kDcTileMcus, 0, stream>>>(a);
     return cudaGetLastError();
 }

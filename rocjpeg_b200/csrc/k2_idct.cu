@@ -46,8 +46,12 @@ struct TileInfo {
     uint32_t pitch;
     uint32_t row_mcu;        // (by / V) * mcus_x
     uint32_t k_row;          // comp_first_blk + (by % V) * H
-    int32_t bx0, nbx;        // first block column of the tile, block columns of the component (<0: no work)
+    int32_t bx0, nbx;        // first block column of the tile, block columns of the component (<0: no more tiles)
     int32_t hshift, hmask, bpm;
+    // direct mode (planar output formats without a crop): `out`/`pitch` address the caller's channel,
+    // stores are clipped to the component's visible size and follow the destination's alignment
+    int32_t direct;          // 0: plane arena; 1: caller's buffer; 2: nothing to store (channel skipped / not part of the format)
+    int32_t clip_w, clip_rows;
 };
 
 __device__ __forceinline__ uint32_t UpperIndexK2(const uint32_t* a, uint32_t n, uint32_t v) {
@@ -92,7 +96,82 @@ __device__ __forceinline__ uint32_t PackSat4(int v0, int v1, int v2, int v3) {
     return d;
 }
 
-__global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
+// tile -> (image, component, block row, first block column); sampling factors are powers of two,
+// so no division in the hot part
+__device__ __forceinline__ TileInfo ResolveTile(const K2Args& a, uint32_t tile) {
+    TileInfo ti = {};
+    ti.nbx = -1;
+    if (tile >= a.total_tiles) return ti;
+    const uint32_t img = UpperIndexK2(a.img_tile0, uint32_t(a.nimages), tile);
+    const ImageDesc& im = a.images[img];
+    uint32_t t = tile - a.img_tile0[img];
+    for (int comp = 0; comp < im.ncomp; comp++) {
+        const uint32_t tiles_x = (uint32_t(im.blocks_w[comp]) + kBlocksPerTile - 1) / kBlocksPerTile;
+        const uint32_t n = tiles_x * uint32_t(im.blocks_h[comp]);
+        if (t < n) {
+            const int by = int(t / tiles_x);
+            const int H = im.hs[comp], V = im.vs[comp];
+            const int hs = __ffs(H) - 1, vs = __ffs(V) - 1;
+            ti.entries = a.entries + im.ent0;
+            ti.rec = a.blk_rec + im.blk0;
+            ti.ent_cap = im.ent_cap;
+            ti.qt = a.qtables + size_t(im.qt_index[comp]) * 64;
+            ti.pitch = im.plane_pitch[comp];
+            ti.out = a.planes + im.plane_off[comp] + size_t(by) * 8 * ti.pitch;
+            ti.row_mcu = uint32_t(by >> vs) * uint32_t(im.mcus_x);
+            ti.k_row = uint32_t(im.comp_first_blk[comp] + ((by & (V - 1)) << hs));
+            ti.bx0 = int(t % tiles_x) * kBlocksPerTile;
+            ti.nbx = im.blocks_w[comp];
+            ti.hshift = hs;
+            ti.hmask = H - 1;
+            ti.bpm = im.bpm;
+            const OutputDesc& od = a.outputs[img];
+            if (od.direct && !a.force_planes) {
+                // channel, pitch and visible size of this component in the caller's layout
+                // (src/rocjpeg_decoder.cpp:576-636: planar chroma at the subsampled size, floor shifts;
+                // 4:2:2 / 4:2:0 use pitch[1] for both chroma planes, 4:4:4 / 4:4:0 each channel's own)
+                const int sx = (im.css == CSS_422 || im.css == CSS_420) ? 1 : 0;
+                const int sy = (im.css == CSS_440 || im.css == CSS_420) ? 1 : 0;
+                const uint32_t dpitch = comp == 0 ? od.dst_pitch[0] : (sx == 0 ? od.dst_pitch[comp] : od.dst_pitch[1]);
+                const int cw = comp == 0 ? im.width : (im.width >> sx), chh = comp == 0 ? im.height : (im.height >> sy);
+                const bool wanted = comp == 0 || od.fmt != FMT_Y;
+                if (!wanted || od.dst[comp] == nullptr || dpitch == 0 || by * 8 >= chh) {
+                    ti.direct = 2;
+                } else {
+                    ti.direct = 1;
+                    ti.pitch = dpitch;
+                    ti.out = od.dst[comp] + size_t(by) * 8 * dpitch;
+                    ti.clip_w = cw;
+                    ti.clip_rows = min(8, chh - by * 8);
+                }
+            }
+            break;
+        }
+        t -= n;
+    }
+    return ti;
+}
+
+// 8 samples of one block row into the caller's buffer: n = visible samples left in the row
+__device__ __forceinline__ void StoreClipped(uint8_t* dst, uint2 v, int n) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(dst);
+    if (n >= 8 && (al & 7) == 0) {
+        *reinterpret_cast<uint2*>(dst) = v;
+    } else if (n >= 8 && (al & 3) == 0) {
+        reinterpret_cast<uint32_t*>(dst)[0] = v.x;
+        reinterpret_cast<uint32_t*>(dst)[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < n) dst[i] = uint8_t(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 0xFFu);
+    }
+}
+
+// 8 CTAs of 256 threads per SM (32 registers): the stage is latency/issue bound and lost 11% when a
+// refactor let it grow to 40 registers. (A one-thread-per-block mapping — private shared-memory
+// column, no transposes, ~30% fewer instructions — was measured 22-28% SLOWER: 77 registers and
+// 33 KiB per CTA leave 24 warps per SM.)
+__global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
     // [block][row][col] with row stride 9 and block stride 72 words: both the
     // row-wise and the column-wise access of a warp hit 32 distinct banks.
     __shared__ int ws[kBlocksPerTile * 72];
@@ -100,43 +179,7 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
     __shared__ uint8_t s_zigzag[64];
     const int tid = threadIdx.x;
     if (tid < 64) s_zigzag[tid] = c_zigzag_k2[(tid + 63) & 63];   // entries carry position + 1 (huff_core.cuh)
-    if (tid < kTilesPerCta) {
-        // tile -> (image, component, block row, first block column); one search per tile, four
-        // lanes in parallel; sampling factors are powers of two, so no division in the hot part
-        const uint32_t tile = blockIdx.x * kTilesPerCta + tid;
-        TileInfo ti = {};
-        ti.nbx = -1;
-        if (tile < a.total_tiles) {
-            const uint32_t img = UpperIndexK2(a.img_tile0, uint32_t(a.nimages), tile);
-            const ImageDesc& im = a.images[img];
-            uint32_t t = tile - a.img_tile0[img];
-            for (int comp = 0; comp < im.ncomp; comp++) {
-                const uint32_t tiles_x = (uint32_t(im.blocks_w[comp]) + kBlocksPerTile - 1) / kBlocksPerTile;
-                const uint32_t n = tiles_x * uint32_t(im.blocks_h[comp]);
-                if (t < n) {
-                    const int by = int(t / tiles_x);
-                    const int H = im.hs[comp], V = im.vs[comp];
-                    const int hs = __ffs(H) - 1, vs = __ffs(V) - 1;
-                    ti.entries = a.entries + im.ent0;
-                    ti.rec = a.blk_rec + im.blk0;
-                    ti.ent_cap = im.ent_cap;
-                    ti.qt = a.qtables + size_t(im.qt_index[comp]) * 64;
-                    ti.pitch = im.plane_pitch[comp];
-                    ti.out = a.planes + im.plane_off[comp] + size_t(by) * 8 * ti.pitch;
-                    ti.row_mcu = uint32_t(by >> vs) * uint32_t(im.mcus_x);
-                    ti.k_row = uint32_t(im.comp_first_blk[comp] + ((by & (V - 1)) << hs));
-                    ti.bx0 = int(t % tiles_x) * kBlocksPerTile;
-                    ti.nbx = im.blocks_w[comp];
-                    ti.hshift = hs;
-                    ti.hmask = H - 1;
-                    ti.bpm = im.bpm;
-                    break;
-                }
-                t -= n;
-            }
-        }
-        s_tile[tid] = ti;
-    }
+    if (tid < kTilesPerCta) s_tile[tid] = ResolveTile(a, blockIdx.x * kTilesPerCta + tid);
     __syncthreads();
     const int b = tid >> 3, j = tid & 7;
     int* my = ws + b * 72;
@@ -144,6 +187,7 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
     for (int it = 0; it < kTilesPerCta; it++) {
         const TileInfo& ti = s_tile[it];
         if (ti.nbx < 0) break;
+        if (ti.direct == 2) continue;   // e.g. chroma of a colour picture decoded to ROCJPEG_OUTPUT_Y
         const int bx = ti.bx0 + b;
         const bool valid = bx < ti.nbx;
         // expand the block's sparse entries into the zeroed workspace, dequantising on the way
@@ -184,11 +228,17 @@ __global__ void __launch_bounds__(kThreads) k2_idct(K2Args a) {
             for (int c = 0; c < 8; c++) in[c] = my[j * 9 + c];   // row j
             Islow8<18>(in, out, (1 << 17) + (128 << 18));
             uint8_t* dst = ti.out + size_t(j) * ti.pitch + size_t(bx) * 8;
-            *reinterpret_cast<uint2*>(dst) = make_uint2(PackSat4(out[0], out[1], out[2], out[3]), PackSat4(out[4], out[5], out[6], out[7]));
+            const uint2 v = make_uint2(PackSat4(out[0], out[1], out[2], out[3]), PackSat4(out[4], out[5], out[6], out[7]));
+            if (!ti.direct) {
+                *reinterpret_cast<uint2*>(dst) = v;
+            } else if (j < ti.clip_rows) {
+                StoreClipped(dst, v, ti.clip_w - bx * 8);
+            }
         }
         __syncwarp();
     }
 }
+
 
 }  // namespace
 

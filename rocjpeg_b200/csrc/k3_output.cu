@@ -107,6 +107,27 @@ __device__ __forceinline__ void Stage8(uint8_t* buf, int phase, int lane, int n,
 
 // Copy `n` bytes of one plane row (columns x .. x+n) into the caller's row.
 __device__ __forceinline__ void CopyRow(uint8_t* buf, const uint8_t* src_row, int x, uint8_t* dst, int n, int lane) {
+    // fast case (warp-uniform): aligned plane loads, word-aligned destination -> registers only
+    if (((reinterpret_cast<uintptr_t>(src_row) + size_t(x)) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        const int m = n - lane * 8;
+        if (m > 0) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(src_row + x) + lane);
+            uint8_t* d = dst + lane * 8;
+            if (m >= 8) {
+                if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                    *reinterpret_cast<uint2*>(d) = v;
+                } else {
+                    reinterpret_cast<uint32_t*>(d)[0] = v.x;
+                    reinterpret_cast<uint32_t*>(d)[1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (i < m) d[i] = uint8_t(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 0xFFu);
+            }
+        }
+        return;
+    }
     const int phase = int(reinterpret_cast<uintptr_t>(dst) & 15);
     // planes are MCU-padded (and the arena has slack): reading up to 7 samples past n is in bounds
     if (lane * 8 < n) Stage8(buf, phase, lane, n, Load8(src_row, x + lane * 8));
@@ -226,6 +247,142 @@ __device__ __forceinline__ void RowRgb(const K3Job& j, int sx, int sy, bool gray
     __syncwarp();
 }
 
+// ---- fast RGB rows ------------------------------------------------------------------------
+// The general row routine above stages every row in shared memory so that any destination
+// alignment gets 128-bit stores; it costs ~65 instructions per pixel (profiles/r01c_*), four times
+// the arithmetic. When the tile's first plane column is a multiple of 8 (always, unless a crop
+// starts at an odd multiple) and the destination row is at least 4-byte aligned, a lane can load
+// its 8 samples per plane with one aligned load each, convert in registers and store words
+// directly: no staging, no per-byte work.
+
+// byte k of w as float, minus `bias`, exactly: the byte is dropped into the mantissa of 2^23
+__device__ __forceinline__ float ByteToFloat(uint32_t w, uint32_t sel, float magic) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - magic;
+}
+
+struct Rgb8 {
+    uint2 r, g, b;   // 8 packed bytes per channel
+};
+
+// 8 pixels: yy = 8 luma bytes; chroma bytes per pixel given by (uw, vw) words and the byte
+// selectors in csel (pixel i uses chroma byte csel[i] of the pair {lo, hi}).
+template <int SX>
+__device__ __forceinline__ Rgb8 Convert8(uint2 yy, uint2 uu, uint2 vv) {
+    constexpr float kY = 8388608.0f, kC = 8388608.0f + 128.0f;
+    float fu[8], fv[8];
+    if (SX == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            fu[i] = ByteToFloat(uu.x, 0x7650 + i, kC);
+            fu[4 + i] = ByteToFloat(uu.y, 0x7650 + i, kC);
+            fv[i] = ByteToFloat(vv.x, 0x7650 + i, kC);
+            fv[4 + i] = ByteToFloat(vv.y, 0x7650 + i, kC);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {   // chroma byte i serves pixels 2i and 2i+1
+            fu[2 * i] = fu[2 * i + 1] = ByteToFloat(uu.x, 0x7650 + i, kC);
+            fv[2 * i] = fv[2 * i + 1] = ByteToFloat(vv.x, 0x7650 + i, kC);
+        }
+    }
+    uint32_t r[8], g[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float fy = ByteToFloat(i < 4 ? yy.x : yy.y, 0x7650 + (i & 3), kY);
+        r[i] = PackU8(fmaf(1.5748f, fv[i], fy));
+        g[i] = PackU8(fmaf(-0.4681f, fv[i], fmaf(-0.1873f, fu[i], fy)));
+        b[i] = PackU8(fmaf(1.8556f, fu[i], fy));
+    }
+    Rgb8 o;
+    o.r = make_uint2(Pack4(r[0], r[1], r[2], r[3]), Pack4(r[4], r[5], r[6], r[7]));
+    o.g = make_uint2(Pack4(g[0], g[1], g[2], g[3]), Pack4(g[4], g[5], g[6], g[7]));
+    o.b = make_uint2(Pack4(b[0], b[1], b[2], b[3]), Pack4(b[4], b[5], b[6], b[7]));
+    return o;
+}
+
+__device__ __forceinline__ void StoreBytes(uint8_t* d, uint2 v, int n) {   // first n (< 8) bytes of v
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < n) d[i] = uint8_t(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 0xFFu);
+}
+__device__ __forceinline__ void Store8(uint8_t* d, uint2 v, bool al8) {   // d is 4-byte aligned at least
+    if (al8) {
+        *reinterpret_cast<uint2*>(d) = v;
+    } else {
+        reinterpret_cast<uint32_t*>(d)[0] = v.x;
+        reinterpret_cast<uint32_t*>(d)[1] = v.y;
+    }
+}
+
+// One output row segment (nx pixels from column xt of output row y), RGB or RGB_PLANAR.
+// Preconditions (checked by the caller, warp-uniform): (x0 + xt) % 8 == 0, destination row(s) 4-byte aligned.
+template <int SX>
+__device__ __forceinline__ void RowRgbFast(const K3Job& j, int sy, bool gray, int y, int lane) {
+    const int nx = j.nx, xt = j.xt;
+    const int n = nx - lane * 8;   // pixels this lane owns (may be <= 0 or < 8 at the right edge)
+    if (n <= 0) return;
+    const int Y = j.y0 + y;
+    const int X = j.x0 + xt + lane * 8;
+    const uint2 yy = __ldg(reinterpret_cast<const uint2*>(j.p[0] + size_t(Y) * j.pitch[0] + X));
+    Rgb8 o;
+    if (gray) {
+        o.r = o.g = o.b = yy;   // hip_kernels.cpp:1915-1927
+    } else {
+        const uint8_t* urow = j.p[1] + size_t(Y >> sy) * j.pitch[1];
+        const uint8_t* vrow = j.p[2] + size_t(Y >> sy) * j.pitch[2];
+        uint2 uu, vv;
+        if (SX == 0) {
+            uu = __ldg(reinterpret_cast<const uint2*>(urow + X));
+            vv = __ldg(reinterpret_cast<const uint2*>(vrow + X));
+        } else {
+            uu = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(urow + (X >> 1))), 0u);
+            vv = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(vrow + (X >> 1))), 0u);
+        }
+        o = Convert8<SX>(yy, uu, vv);
+    }
+    if (j.fmt == FMT_RGB) {
+        uint8_t* d = j.dst[0] + size_t(y) * j.dpitch[0] + size_t(xt + lane * 8) * 3;
+        // interleave R,G,B bytes: 8 pixels -> 6 words
+        uint32_t w[6];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t r = h ? o.r.y : o.r.x, g = h ? o.g.y : o.g.x, b = h ? o.b.y : o.b.x;
+            w[3 * h + 0] = __byte_perm(__byte_perm(r, g, 0x1040), b, 0x3410);   // r0 g0 b0 r1
+            w[3 * h + 1] = __byte_perm(__byte_perm(g, b, 0x2051), r, 0x3610);   // g1 b1 r2 g2
+            w[3 * h + 2] = __byte_perm(__byte_perm(b, r, 0x3702), g, 0x3720);   // b2 r3 g3 b3
+        }
+        if (n >= 8) {
+            if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) reinterpret_cast<uint2*>(d)[k] = make_uint2(w[2 * k], w[2 * k + 1]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) reinterpret_cast<uint32_t*>(d)[k] = w[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 24; k++)
+                if (k < 3 * n) d[k] = uint8_t((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+        }
+    } else {
+        // all three planes use pitch[0] (src/rocjpeg_decoder.cpp:526-544)
+        const size_t off = size_t(y) * j.dpitch[0] + size_t(xt + lane * 8);
+        uint8_t* d0 = j.dst[0] + off;
+        uint8_t* d1 = j.dst[1] + off;
+        uint8_t* d2 = j.dst[2] + off;
+        if (n >= 8) {
+            const bool al8 = ((reinterpret_cast<uintptr_t>(d0) | reinterpret_cast<uintptr_t>(d1) | reinterpret_cast<uintptr_t>(d2)) & 7) == 0;
+            Store8(d0, o.r, al8);
+            Store8(d1, o.g, al8);
+            Store8(d2, o.b, al8);
+        } else {
+            StoreBytes(d0, o.r, n);
+            StoreBytes(d1, o.g, n);
+            StoreBytes(d2, o.b, n);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
     __shared__ __align__(16) uint8_t s_buf[kWarps][kRowBuf];
     __shared__ K3Job s_job;
@@ -263,10 +420,20 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
     if (fmt == FMT_RGB || fmt == FMT_RGB_PLANAR) {
         if (fmt == FMT_RGB && (j.dst[0] == nullptr || j.dpitch[0] == 0)) return;
         if (fmt == FMT_RGB_PLANAR && (!j.dst[0] || !j.dst[1] || !j.dst[2] || j.dpitch[0] == 0)) return;
+        // fast rows need aligned plane loads and word-aligned destination rows (warp-uniform tests)
+        const bool src_ok = ((x0 + xt) & 7) == 0;
+        const uintptr_t bases = fmt == FMT_RGB ? reinterpret_cast<uintptr_t>(j.dst[0]) + size_t(xt) * 3
+                                               : (reinterpret_cast<uintptr_t>(j.dst[0]) | reinterpret_cast<uintptr_t>(j.dst[1]) |
+                                                  reinterpret_cast<uintptr_t>(j.dst[2])) + size_t(xt);
         for (int r = warp; r < kTileH; r += kWarps) {
             const int y = ty * kTileH + r;
             if (y >= H) break;
-            RowRgb(j, sx, sy, gray, buf, y, lane);
+            const bool dst_ok = ((bases | (size_t(y) * j.dpitch[0])) & 3) == 0;
+            if (src_ok && dst_ok) {
+                if (sx) RowRgbFast<1>(j, sy, gray, y, lane); else RowRgbFast<0>(j, sy, gray, y, lane);
+            } else {
+                RowRgb(j, sx, sy, gray, buf, y, lane);
+            }
         }
         return;
     }

@@ -46,7 +46,9 @@ struct K1Args {
     uint32_t* nnz;                // per subsequence: coefficient entries it produces
     uint2* cta_partial;           // per K1 CTA: (has segment start, blocks after the last start)
     uint32_t* cta_entries;        // per K1 CTA: coefficient entries of the CTA's subsequences
+    uint2* cta_carry;             // per K1 CTA: (blocks, entries) entering it from the image's earlier CTAs (k1_scan)
     int3* dc_partial;             // per DC tile: per-component DC sum after the tile's last reset
+    int3* dc_carry;               // per DC tile: predictors entering it (dc_scan)
     uint32_t* counters;           // [kMaxSyncRounds] boundary changes per round, then [kMaxSyncRounds] decodes per round
     uint32_t* entries;            // coefficient entry arena (huff_core.cuh: MakeCoefEntry), decode order
     BlockRec* blk_rec;            // per block, decode order
@@ -66,6 +68,8 @@ cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream);
 
 struct K2Args {
     const ImageDesc* images;
+    const OutputDesc* outputs;    // for images whose planes go straight to the caller's buffers (OutputDesc::direct)
+    int force_planes;             // 1: ignore `direct`, write the plane arena (stage tap)
     const uint32_t* img_tile0;    // nimages + 1: first IDCT tile of each image
     const uint16_t* qtables;      // natural-order u16[64] tables
     const uint32_t* entries;      // coefficient entries
