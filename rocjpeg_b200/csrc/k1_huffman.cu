@@ -253,16 +253,19 @@ __device__ __forceinline__ Sub Locate(const K1Args& a, const ImageDesc& im, int6
     return s;
 }
 
-// Shared-memory image of one CTA's working set; the Huffman tables follow it (dynamic size:
-// 4 KiB per table pair the image uses + the second-level arena).
+// Shared-memory image of one CTA's working set. Dynamic shared memory starts with the Huffman
+// tables (4 KiB per table pair the image uses + the second-level arena: K1Args::lut_smem_bytes,
+// the batch maximum), this struct follows. Every byte counts: at 32 KiB per CTA seven CTAs fit an
+// SM instead of six, and the two decode kernels are latency-bound (profiles/r01c_c3_kernels.md).
 template <int S>
 struct K1Smem {
-    static constexpr int kSlotWords = (S + 16) / 4;      // subsequence + 16 bytes of look-ahead
-    static constexpr int kSlotStride = kSlotWords + 1;   // odd stride: conflict-free when lanes read the same word index
-    static constexpr int kSlotVecs = (S + 16) / 16;
+    static constexpr int kSlotVecs = (S + 16) / 16;      // 16-byte vectors staged per subsequence
+    static constexpr int kSlotStride = S / 4 + 3;        // words kept: subsequence + 12 bytes of look-ahead (a symbol is at
+                                                         // most 31 bits, the window prefetches two words); the stride is odd:
+                                                         // conflict-free when lanes read the same word index
     static constexpr int kSchedLen = S * 4 + 48;         // a block takes at least 2 bits: S*4 blocks + one MCU + prefetch
-    uint32_t words[T * kSlotStride];
-    uint64_t start[T];
+    uint32_t words[T * kSlotStride + 1];                 // + the word the last slot's final vector spills
+    uint32_t start[T];                                   // byte offset of the subsequence from the image's data_off (~0: none)
     uint32_t state[T];
     uint32_t used[T];
     uint32_t nnz[T];
@@ -271,23 +274,22 @@ struct K1Smem {
     uint16_t sched[kSchedLen];
     uint8_t pair_tab[8];
     uint32_t scratch[40];
-    alignas(4096) uint32_t lut[4];   // [npairs][2][kFastSize] then the second-level arena (dynamic size)
 };
 
 template <int S>
-__device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, const K1Args& a, const ImageDesc& im, const Sub& me) {
+__device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, uint32_t* lut, const K1Args& a, const ImageDesc& im, const Sub& me) {
     const int tid = threadIdx.x;
     // Lane forms "AC table of the current pair" as (table address | 2048): every pair's DC table must
-    // start at a shared-window address with bit 11 clear. The tables lie at a multiple of 4096 from
+    // start at a shared-window address with bit 11 clear. The tables lie at multiples of 4096 from
     // the start of dynamic shared memory, which itself begins less than 2048 bytes into the window
     // (0 or the 1 KiB the system reserves); anything else must fail loudly, not decode garbage.
-    if (tid == 0 && (SharedAddr(sm.lut) & 2048u) != 0) __trap();
-    sm.start[tid] = me.active ? me.start : ~0ull;
+    if (tid == 0 && (SharedAddr(lut) & 2048u) != 0) __trap();
+    sm.start[tid] = me.active ? uint32_t(me.start - im.data_off) : ~0u;
     const HuffLutSet* set = a.luts + im.lut_set;
     const int npairs = im.npairs;
     // Huffman tables of this image: per (DC, AC) table pair the two first-level tables back to back
     {
-        uint4* dst = reinterpret_cast<uint4*>(sm.lut);
+        uint4* dst = reinterpret_cast<uint4*>(lut);
         constexpr int kVecsPerTable = kFastSize * 4 / 16;
         for (int i = tid; i < npairs * 2 * kVecsPerTable; i += T) {
             const int tsel = i / kVecsPerTable, v = i - tsel * kVecsPerTable;   // tsel = 2 * pair + is_ac
@@ -303,7 +305,7 @@ __device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, const K1Args& a, cons
         const int bpm = im.bpm;
         int c = tid % bpm;
         for (int j = tid; j < K1Smem<S>::kSchedLen; j += T) {
-            sm.sched[j] = uint16_t(SharedAddr(sm.lut) + (uint32_t(im.mcu_pair[c]) << 12));   // the window is < 64 KiB
+            sm.sched[j] = uint16_t(SharedAddr(lut) + (uint32_t(im.mcu_pair[c]) << 12));   // the window is < 64 KiB
             c = (c + T) % bpm;
         }
     }
@@ -311,16 +313,18 @@ __device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, const K1Args& a, cons
     constexpr int V = K1Smem<S>::kSlotVecs;
     for (int idx = tid; idx < T * V; idx += T) {
         const int slot = idx / V, v = idx - slot * V;
-        const uint64_t st = sm.start[slot];
-        if (st == ~0ull) continue;
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.scan + st) + v);
+        const uint32_t st = sm.start[slot];
+        if (st == ~0u) continue;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.scan + im.data_off + st) + v);
         uint32_t* w = sm.words + slot * K1Smem<S>::kSlotStride + v * 4;
-        // stored big-endian: bit 31 of a word is the first bit of the stream (huff_core.cuh)
-        w[0] = ByteSwap32(q.x); w[1] = ByteSwap32(q.y); w[2] = ByteSwap32(q.z); w[3] = ByteSwap32(q.w);
+        // stored big-endian: bit 31 of a word is the first bit of the stream (huff_core.cuh); the last
+        // vector's final word belongs to the next slot and is not kept
+        w[0] = ByteSwap32(q.x); w[1] = ByteSwap32(q.y); w[2] = ByteSwap32(q.z);
+        if (v != V - 1) w[3] = ByteSwap32(q.w);
     }
     __syncthreads();
     LutView lv;
-    lv.fast_sa = SharedAddr(sm.lut);
+    lv.fast_sa = SharedAddr(lut);
     lv.sub_sa = lv.fast_sa + uint32_t(npairs) * 4096u;
     lv.set = set;
     lv.pair_tab = sm.pair_tab;
@@ -338,7 +342,8 @@ __device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, const K1Args& a, cons
 template <int S>
 __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw);
+    uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
+    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
     const int tid = threadIdx.x;
     const uint32_t cta = blockIdx.x;
     const uint32_t img = UpperIndex(a.img_cta0, uint32_t(a.nimages), cta);
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
             old_out = out;
         }
     }
-    const LutView lv = StageCta<S>(sm, a, im, me);
+    const LutView lv = StageCta<S>(sm, lut, a, im, me);
     const int bpm = im.bpm;
     const uint32_t slots_sa = SharedAddr(sm.words);
     const uint32_t sched_sa = SharedAddr(sm.sched);
@@ -523,7 +528,8 @@ __global__ void __launch_bounds__(kScanThreads) k1_scan(K1Args a) {
 template <int S>
 __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw);
+    uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
+    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t cta = blockIdx.x;
     const uint32_t img = UpperIndex(a.img_cta0, uint32_t(a.nimages), cta);
@@ -532,7 +538,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const uint32_t g = uint32_t(gi);
     Sub me = Locate<S>(a, im, gi, true);
     if (tid < H) me.active = false;   // halo slots belong to the previous CTA
-    const LutView lv = StageCta<S>(sm, a, im, me);
+    const LutView lv = StageCta<S>(sm, lut, a, im, me);
 
     const uint32_t st = me.active ? a.state[g] : 0;
     const uint32_t nb = StateBlocks(st);
@@ -852,7 +858,7 @@ __global__ void __launch_bounds__(256) gather_scans(const GatherItem* items, int
 template <int S>
 cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream) {
     static_assert(S <= 128, "the packed decoder state holds bit positions below 2048");
-    const size_t smem = offsetof(K1Smem<S>, lut) + a.lut_smem_bytes;
+    const size_t smem = sizeof(K1Smem<S>) + a.lut_smem_bytes;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;   // 3 table pairs + the full second-level arena fit
     if (round >= 0) k1_sync<S><<<a.total_ctas, T, smem, stream>>>(a, round);
     else k1_write<S><<<a.total_ctas, T, smem, stream>>>(a);
