@@ -1,6 +1,9 @@
 """Turn ncu outputs brought back in gpurun_out/ into the small, tracked summaries under profiles/.
 
-  python profiles/summarize.py <tag> <launches.csv> [<report.ncu-rep>]
+  python profiles/summarize.py <tag> <launches.csv> [<report.ncu-rep> [<workload>]]
+
+With <workload> (bench.py --workload name) the DRAM bytes of one step's launches are also recorded per
+stage in profiles/traffic.json, which bench.py reports as roofline.traffic.
 
 Writes profiles/<tag>_launches.md (per-kernel launch count, mean duration, share of the step) and,
 when a full report is given, profiles/<tag>_kernels.md (DRAM bytes, throughput %, issue %, stalls).
@@ -62,4 +65,28 @@ if rep:
                         pass
                 cells.append(v)
             f.write("| " + " | ".join(cells) + " |\n")
+if rep and len(sys.argv) > 4:
+    import json
+    import os
+
+    stage_of = {"k1_sync": "huffman_sync", "k1_scan": "huffman_write", "k1_write": "huffman_write", "dc_sums": "dc", "dc_scan": "dc",
+                "dc_apply": "dc", "k2_idct": "idct", "k3_output": "output"}
+    ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_stage = {}
+    for r in d:   # launches in order: stop after the first complete step (k3_output or, without an output stage, the IDCT)
+        name = r[ki].split("(")[0].split("<")[0].replace("void ", "").split("::")[-1]
+        st = stage_of.get(name)
+        if st is None:
+            continue
+        b = float(r[ri].replace(",", "")) * scale.get(u[ri], 1.0) + float(r[wi].replace(",", "")) * scale.get(u[wi], 1.0)
+        per_stage[st] = per_stage.get(st, 0.0) + b
+        if name == "k3_output":
+            break
+    path = "profiles/traffic.json"
+    t = json.load(open(path)) if os.path.exists(path) else {}
+    t[sys.argv[4]] = {k: int(v) for k, v in per_stage.items()}
+    t.setdefault("_note", "dram__bytes_read.sum + dram__bytes_write.sum per stage of ONE step, from the ncu --set full capture named by "
+                          "the tag in profiles/<tag>_kernels.md (cold cache, one pipeline lane)")
+    json.dump(t, open(path, "w"), indent=1, sort_keys=True)
 print("ok")

@@ -125,6 +125,18 @@ def test_every_subsequence_size(dec, orc, S, monkeypatch):
         gu.assert_same(got, want, f"{name} S={S}")
 
 
+@pytest.mark.parametrize("cap", ["0", "64"])
+def test_long_codes_through_the_canonical_search(dec, orc, cap, monkeypatch):
+    """ROCJPEG_B200_SUBCAP shrinks the second-level table arena: long codes then take the canonical
+    search in global memory (the path pathological DHTs would take) and must decode identically."""
+    monkeypatch.setenv("ROCJPEG_B200_SUBCAP", cap)
+    for name in ("custom_huffman_420_dri1", "synth_444_500x375", "extreme_coefs_444"):
+        data = load(name)
+        st, got, want = gu.decode_one(dec, orc, data, "rgb")
+        assert st == api.SUCCESS
+        gu.assert_same(got, want, f"{name} subcap={cap}")
+
+
 def test_single_sync_round_forces_fallback_and_still_exact(dec, orc, monkeypatch):
     """With only round 0 launched up front, the host must detect unresolved CTA boundaries,
     run more rounds and redo the downstream stages."""

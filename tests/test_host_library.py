@@ -238,3 +238,18 @@ def test_shard_plan_is_lpt_and_balanced():
         assert dev.tolist() == want
     assert api.plan_shards([], 4).size == 0
     assert api.plan_shards([5, 5, 5, 5], 2).tolist() == [0, 1, 0, 1]
+
+
+@pytest.mark.parametrize("cap", ["0", "64"])
+def test_k1_model_with_exhausted_subtable_arena(k1_model, orc, cap, monkeypatch):
+    """Codes longer than the first-level table normally resolve through second-level sub-tables; when the
+    arena is exhausted (forced here) the canonical T.81 search must give the same symbols."""
+    monkeypatch.setenv("ROCJPEG_B200_SUBCAP", cap)
+    for name in ("custom_huffman_420_dri1", "synth_420_123x77", "extreme_coefs_444"):
+        data = load(name)
+        rc, info = orc.parse(data)
+        want = np.concatenate([c.reshape(-1) for c in orc.coefficients(data, info)])
+        out = np.zeros(want.size, dtype=np.int16)
+        st = _ModelStats()
+        assert k1_model.k1_model_decode(data, len(data), 128, 126, out.ctypes.data, out.size, C.byref(st)) == 0
+        assert np.array_equal(out, want), (name, cap)
