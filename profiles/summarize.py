@@ -73,16 +73,18 @@ if rep and len(sys.argv) > 4:
                 "dc_apply": "dc", "k2_idct": "idct", "k3_output": "output"}
     ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    per_stage = {}
-    for r in d:   # launches in order: stop after the first complete step (k3_output or, without an output stage, the IDCT)
+    per_stage, seen = {}, {}
+    per_step = {"k1_sync": 2}   # launches of a kernel in one step (default 1)
+    for r in d:   # launches in order: one step's worth, wherever in the step the capture window began
         name = r[ki].split("(")[0].split("<")[0].replace("void ", "").split("::")[-1]
         st = stage_of.get(name)
         if st is None:
             continue
+        if seen.get(name, 0) >= per_step.get(name, 1):
+            break
+        seen[name] = seen.get(name, 0) + 1
         b = float(r[ri].replace(",", "")) * scale.get(u[ri], 1.0) + float(r[wi].replace(",", "")) * scale.get(u[wi], 1.0)
         per_stage[st] = per_stage.get(st, 0.0) + b
-        if name == "k3_output":
-            break
     path = "profiles/traffic.json"
     t = json.load(open(path)) if os.path.exists(path) else {}
     t[sys.argv[4]] = {k: int(v) for k, v in per_stage.items()}

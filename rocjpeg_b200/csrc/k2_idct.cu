@@ -172,17 +172,31 @@ __device__ __forceinline__ void StoreClipped(uint8_t* dst, uint2 v, int n) {
 // column, no transposes, ~30% fewer instructions — was measured 22-28% SLOWER: 77 registers and
 // 33 KiB per CTA leave 24 warps per SM.)
 __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
-    // [block][row][col] with row stride 9 and block stride 72 words: both the
-    // row-wise and the column-wise access of a warp hit 32 distinct banks.
-    __shared__ int ws[kBlocksPerTile * 72];
+    // Workspace [block][row][col], row stride kRS = 12 words, block stride kBS = 104 words. A warp holds
+    // 4 blocks x 8 threads: column-wise, thread (b, j) touches word 104 b + 12 r + j -> bank 8 b + j + const,
+    // all 32 distinct; row-wise it moves its row as two 128-bit accesses whose bank groups 3 j mod 8 are
+    // distinct within each quarter-warp.
+    constexpr int kRS = 12, kBS = 104;
+    __shared__ __align__(16) int ws[kBlocksPerTile * kBS];
     __shared__ TileInfo s_tile[kTilesPerCta];
-    __shared__ uint8_t s_zigzag[64];
+    // per tile and zig-zag code of an entry: byte offset of the coefficient inside a block's workspace
+    // (low half) and its quantiser step (high half) - one shared load replaces the zig-zag lookup, the
+    // row/column split and the quantiser load
+    __shared__ uint32_t s_tab[kTilesPerCta][64];
     const int tid = threadIdx.x;
-    if (tid < 64) s_zigzag[tid] = c_zigzag_k2[(tid + 63) & 63];   // entries carry position + 1 (huff_core.cuh)
     if (tid < kTilesPerCta) s_tile[tid] = ResolveTile(a, blockIdx.x * kTilesPerCta + tid);
     __syncthreads();
+    {
+        const int t = tid >> 6, code = tid & 63;   // entries carry position + 1 (huff_core.cuh)
+        const TileInfo& ti = s_tile[t];
+        if (ti.nbx >= 0) {
+            const int nat = c_zigzag_k2[(code + 63) & 63];
+            s_tab[t][code] = uint32_t(((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(ti.qt + nat)) << 16);
+        }
+    }
+    __syncthreads();
     const int b = tid >> 3, j = tid & 7;
-    int* my = ws + b * 72;
+    int* my = ws + b * kBS;
 #pragma unroll 1
     for (int it = 0; it < kTilesPerCta; it++) {
         const TileInfo& ti = s_tile[it];
@@ -191,41 +205,46 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
         const int bx = ti.bx0 + b;
         const bool valid = bx < ti.nbx;
         // expand the block's sparse entries into the zeroed workspace, dequantising on the way
-        size_t blk = 0;
-        uint32_t e0 = 0, e1 = 0;
+        const uint32_t* ep = ti.entries;
+        uint32_t n = 0;
         int dc = 0;
         if (valid) {
-            blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
-            int* row = my + j * 9;
-#pragma unroll
-            for (int w = 0; w < 8; w++) row[w] = 0;
+            const size_t blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
+            int4* row = reinterpret_cast<int4*>(my + j * kRS);
+            row[0] = make_int4(0, 0, 0, 0);
+            row[1] = make_int4(0, 0, 0, 0);
             const uint2 r = __ldg(reinterpret_cast<const uint2*>(ti.rec + blk));
-            e0 = blk ? __ldg(&ti.rec[blk - 1].end) : 0u;
-            e1 = r.x;
+            uint32_t e0 = blk ? __ldg(&ti.rec[blk - 1].end) : 0u, e1 = r.x;
             dc = int(int16_t(r.y & 0xFFFFu));
             if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > ti.ent_cap) e1 = e0 = 0;   // never decoded
+            ep += e0 + uint32_t(j);
+            n = e1 - e0;
         }
         __syncwarp();
-        for (uint32_t k = e0 + uint32_t(j); k < e1; k += 8) {
-            const uint32_t en = __ldg(ti.entries + k);
-            const int nat = s_zigzag[(en >> 16) & 63u];
-            my[(nat >> 3) * 9 + (nat & 7)] = int(int16_t(en & 0xFFFFu)) * int(__ldg(ti.qt + nat));
+        const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(&s_tab[it][0]));
+        const uint32_t my_sa = uint32_t(__cvta_generic_to_shared(my));
+        for (uint32_t k = uint32_t(j); k < n; k += 8, ep += 8) {
+            const uint32_t en = __ldg(ep);
+            uint32_t t;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(tab_sa + ((en >> 14) & 0xFCu)));
+            const int v = int(int16_t(en & 0xFFFFu)) * int(t >> 16);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_sa + (t & 0xFFFFu)), "r"(v) : "memory");
         }
         __syncwarp();
-        if (valid && j == 0) my[0] = dc * int(__ldg(ti.qt));   // integrated DC replaces any DC-difference entry
+        if (valid && j == 0) my[0] = dc * int(s_tab[it][1] >> 16);   // integrated DC replaces any DC-difference entry
         __syncwarp();
         int in[8], out[8];
         if (valid) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) in[r] = my[r * 9 + j];   // column j
+            for (int r = 0; r < 8; r++) in[r] = my[r * kRS + j];   // column j
             Islow8<11>(in, out, 1 << 10);
 #pragma unroll
-            for (int r = 0; r < 8; r++) my[r * 9 + j] = out[r];
+            for (int r = 0; r < 8; r++) my[r * kRS + j] = out[r];
         }
         __syncwarp();
         if (valid) {
-#pragma unroll
-            for (int c = 0; c < 8; c++) in[c] = my[j * 9 + c];   // row j
+            const int4 lo = *reinterpret_cast<const int4*>(my + j * kRS), hi = *reinterpret_cast<const int4*>(my + j * kRS + 4);   // row j
+            in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
             Islow8<18>(in, out, (1 << 17) + (128 << 18));
             uint8_t* dst = ti.out + size_t(j) * ti.pitch + size_t(bx) * 8;
             const uint2 v = make_uint2(PackSat4(out[0], out[1], out[2], out[3]), PackSat4(out[4], out[5], out[6], out[7]));
@@ -238,7 +257,6 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
         __syncwarp();
     }
 }
-
 
 }  // namespace
 
