@@ -155,32 +155,39 @@ struct Lane {
     "setp.ne.u32 pe, t, 0;\n\t"                             \
     "@pc mov.b32 %1, %2;\n\t"                               \
     "@pc mov.b32 %2, %3;\n\t"                               \
-    "@pc ld.shared.u32 %3, [%4+4];\n\t"                     \
     "@pc add.u32 %4, %4, 4;\n\t"                            \
+    "@pc ld.shared.u32 %3, [%4];\n\t"                       \
     "mov.b32 %0, %" NXT ";\n\t"                             \
     "or.b32 %7, %7, 2048;\n\t"                              \
     "@pe and.b32 %0, %" NXT ", 0x1fffff;\n\t"               \
     "@pe mov.b32 %7, %6;\n\t"                               \
-    "@pe ld.shared.u16 %6, [%5+4];\n\t"                     \
-    "@pe add.u32 %5, %5, 2;\n\t"
+    "@pe add.u32 %5, %5, 2;\n\t"                            \
+    "@pe ld.shared.u16 %6, [%5+2];\n\t"
     __device__ __forceinline__ void Commit(uint32_t nxt) {
         asm volatile("{\n\t.reg .pred pc, pe;\n\t.reg .b32 t;\n\t" RJB_K1_COMMIT_HEAD("8") "}"
                      : "+r"(acc), "+r"(w0), "+r"(w1), "+r"(w2), "+r"(wp), "+r"(sp), "+r"(next_dc), "+r"(off)
                      : "r"(nxt));
     }
     // The same, and at a block end: the block's record gets `n` (entries so far = one past the
-    // block's last), the record pointer moves on; reaching the record of the restart interval's
+    // block's last) and, when this thread decoded the block's DC symbol (always, except for a first
+    // block that began in the previous subsequence), the DC difference in the same 8-byte store - one
+    // scattered store per block instead of two, the store path is the write pass's second bottleneck
+    // (profiles/r01d_*). The record pointer moves on; reaching the record of the restart interval's
     // last block + 1 raises the stop bit (what follows in the subsequence is padding).
-    __device__ __forceinline__ void CommitWrite(uint32_t nxt, BlockRec*& rp, uint32_t n, uint32_t rp_stop) {
-        asm volatile("{\n\t.reg .pred pc, pe, pl;\n\t.reg .b32 t;\n\t" RJB_K1_COMMIT_HEAD("9")
-                     "@pe st.global.u32 [%8], %10;\n\t"
+    __device__ __forceinline__ void CommitWrite(uint32_t nxt, BlockRec*& rp, uint32_t n, uint32_t rp_stop, int dcv, uint32_t& has_dc) {
+        asm volatile("{\n\t.reg .pred pc, pe, pl, pf, pn;\n\t.reg .b32 t;\n\t" RJB_K1_COMMIT_HEAD("10")
+                     "setp.ne.and.u32 pf, %9, 0, pe;\n\t"
+                     "setp.eq.and.u32 pn, %9, 0, pe;\n\t"
+                     "@pf st.global.v2.b32 [%8], {%11, %13};\n\t"
+                     "@pn st.global.u32 [%8], %11;\n\t"
+                     "@pe mov.b32 %9, 1;\n\t"
                      "@pe add.u64 %8, %8, 8;\n\t"
                      "cvt.u32.u64 t, %8;\n\t"
-                     "setp.eq.and.u32 pl, t, %11, pe;\n\t"
+                     "setp.eq.and.u32 pl, t, %12, pe;\n\t"
                      "@pl or.b32 %0, %0, 0x400;\n\t"
                      "}"
-                     : "+r"(acc), "+r"(w0), "+r"(w1), "+r"(w2), "+r"(wp), "+r"(sp), "+r"(next_dc), "+r"(off), "+l"(rp)
-                     : "r"(nxt), "r"(n), "r"(rp_stop)
+                     : "+r"(acc), "+r"(w0), "+r"(w1), "+r"(w2), "+r"(wp), "+r"(sp), "+r"(next_dc), "+r"(off), "+l"(rp), "+r"(has_dc)
+                     : "r"(nxt), "r"(n), "r"(rp_stop), "r"(dcv)
                      : "memory");
     }
 #undef RJB_K1_COMMIT_HEAD
@@ -608,6 +615,8 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     Lane ln;
     ln.Init(SharedAddr(sm.words + tid * K1Smem<S>::kSlotStride), SharedAddr(sm.sched), key, me.end_bit);
     uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;   // the last four entries (oldest in q0): a group leaves as one 128-bit store
+    int dcv = 0;                               // DC difference of the block in progress, when its DC symbol was ours
+    uint32_t has_dc = StateZ(key) == 0 ? 1u : 0u;
     if (blk0 < limit && me.end_bit != 0) {
         for (;;) {
             const uint32_t win = ln.Peek();
@@ -633,7 +642,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
                 "sub.s32 v, ex, m;\n\t"
                 "and.b32 zq, %9, 0x7e00000;\n\t"
                 "setp.eq.u32 pdc, zq, 0;\n\t"
-                "@pdc st.global.u16 [%6+4], v;\n\t"
+                "@pdc mov.b32 %6, v;\n\t"
                 "setp.ne.u32 pnz, sz, 0;\n\t"
                 "shr.u32 zq, %10, 21;\n\t"
                 "@pnz mov.b32 %0, %1;\n\t"
@@ -647,13 +656,15 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
                 "@pst st.global.v4.b32 [%5], {%0, %1, %2, %3};\n\t"
                 "@pfl add.u64 %5, %5, 16;\n\t"
                 "}"
-                : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(n), "+l"(ep)
-                : "l"(rp), "r"(en), "r"(win), "r"(ln.acc), "r"(nxt), "r"(n_end)
+                : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(n), "+l"(ep), "+r"(dcv)
+                : "r"(en), "r"(win), "r"(ln.acc), "r"(nxt), "r"(n_end)
                 : "memory");
-            ln.CommitWrite(nxt, rp, n, rp_stop);
+            ln.CommitWrite(nxt, rp, n, rp_stop, dcv, has_dc);
             if (ln.acc & kAccStop) break;
         }
     }
+    // a block still in progress whose DC symbol was ours: the thread that ends it stores only the end index
+    if (has_dc && (ln.acc & kAccZMask) != 0 && blk0 < limit && me.end_bit != 0) rp->dc = int16_t(dcv);
     if (n & 3u) {   // last, partial group: padded with entries for position 0, which K2 overwrites with the DC anyway
         for (; n & 3u; n++) { q0 = q1; q1 = q2; q2 = q3; q3 = kPadEntry; }
         if (n <= n_end) *reinterpret_cast<uint4*>(ep) = make_uint4(q0, q1, q2, q3);
