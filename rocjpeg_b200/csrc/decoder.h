@@ -12,10 +12,14 @@
 #pragma once
 #include <cuda_runtime_api.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_types.h"
@@ -80,6 +84,37 @@ struct BatchStats {
     int devices = 1;                    // GPUs the call was sharded over
 };
 
+// Helper threads of one decoder: the lanes of a call are described and enqueued in parallel (kernel
+// launches cost the host ~3 us each and a lane issues about fifteen), the caller's thread taking lane 0.
+// Workers sleep on a condition variable between calls.
+class SubmitPool {
+  public:
+    explicit SubmitPool(int workers);
+    ~SubmitPool();
+    SubmitPool(const SubmitPool&) = delete;
+    SubmitPool& operator=(const SubmitPool&) = delete;
+    // fn(0) on the calling thread, fn(1..n-1) on the workers; returns when all are done
+    void Run(int n, const std::function<void(int)>& fn);
+
+  private:
+    void Loop(int index);
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    uint64_t generation_ = 0;
+    int jobs_ = 0;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> pending_{0};
+    bool stop_ = false;
+};
+
+// Order in which concurrent lane submitters may enqueue on the shared upload stream (lane order: the
+// first chunk gets the whole PCIe link, its kernels start while the next chunks are still in flight).
+struct UploadTurn {
+    std::atomic<int>* turn = nullptr;   // null: single submitter, no ordering needed
+    int mine = 0;
+};
+
 // One pipeline lane: a CUDA stream, its device arenas and the description of the
 // (sub-)batch it is decoding. A decode call splits its batch over up to kMaxLanes lanes so
 // that the upload of one chunk overlaps the kernels of another and the latency-bound tails
@@ -92,8 +127,8 @@ class Lane {
     Lane& operator=(const Lane&) = delete;
     int Create(int device_id, int sm_count);
     int Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
-    int Upload(cudaStream_t upload_stream);   // nullptr: use the lane's own stream
-    int LaunchAll(bool include_upload, bool profiling, cudaStream_t upload_stream);
+    int Upload(cudaStream_t upload_stream, UploadTurn turn = UploadTurn());   // nullptr: use the lane's own stream
+    int LaunchAll(bool include_upload, bool profiling, cudaStream_t upload_stream, UploadTurn turn = UploadTurn());
     int Finish(bool profiling);
     int Sync();
     int CopyCoefficients(int image, int16_t* host_out, size_t count);
@@ -142,6 +177,8 @@ class Lane {
 
 constexpr int kMaxLanes = 4;
 constexpr int kMaxDevices = 16;
+
+
 
 // Longest-processing-time-first assignment of `n` independent images (cost = entropy-coded bytes)
 // to `ndev` devices: images in decreasing cost order, each to the least loaded device. Images are
@@ -193,6 +230,8 @@ class Decoder {
     int chunk_first_[kMaxLanes + 1] = {};   // image range of each lane's chunk
     BatchStats stats_;
     // multi-device sharding
+    std::unique_ptr<SubmitPool> pool_;              // lane submitters (ROCJPEG_B200_SUBMIT_THREADS=1)
+    std::unique_ptr<SubmitPool> shard_pool_;        // one submitter per peer device
     bool is_peer_ = false;                          // a peer never shards further
     std::vector<std::unique_ptr<Decoder>> peers_;   // decoders on the other devices, owned by the handle's decoder
     std::vector<int> shard_dev_, shard_local_;      // image -> (0 = this device, k = peers_[k-1]; index inside that device's share)
