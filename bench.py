@@ -300,6 +300,7 @@ def main():
             torch.cuda.synchronize()
 
     # ---- device-resident arm (value) -------------------------------------------------
+    lanes_env = os.environ.get("ROCJPEG_B200_LANES")
     dec.set_profiling(True)
     assert dec.prepare(streams, params, dests) == api.SUCCESS
     for _ in range(args.warmup):
@@ -307,7 +308,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    step_ms, stage_ms, launches = [], [0.0] * len(api.STAGES), 0
+    step_ms, launches = [], 0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         l2_flush()
@@ -315,13 +316,31 @@ def main():
         st = dec.stats()
         step_ms.append(st.total_ms)
         launches += st.kernel_launches
-        for i in range(len(api.STAGES)):
-            stage_ms[i] += st.stage_ms[i]
     barrier()
     resident_wall = time.perf_counter() - wall0
-    stage_ms = [m / args.steps for m in stage_ms]
     resident_ms = sum(step_ms) / len(step_ms)
     stats = dec.stats()
+    # per-stage device times for the roofline: the same resident batch on ONE pipeline lane, so that the
+    # stages do not overlap each other (with several lanes the per-stage event times of the lanes add up)
+    os.environ["ROCJPEG_B200_LANES"] = "1"
+    assert dec.prepare(streams, params, dests) == api.SUCCESS
+    for _ in range(3):
+        assert dec.run() == api.SUCCESS
+    stage_ms, prof_steps, one_lane_ms = [0.0] * len(api.STAGES), max(3, min(args.steps, 10)), 0.0
+    for _ in range(prof_steps):
+        l2_flush()
+        assert dec.run() == api.SUCCESS
+        st = dec.stats()
+        launches += st.kernel_launches
+        one_lane_ms += st.total_ms
+        for i in range(len(api.STAGES)):
+            stage_ms[i] += st.stage_ms[i]
+    stage_ms = [m / prof_steps for m in stage_ms]
+    one_lane_ms /= prof_steps
+    if lanes_env is None:
+        del os.environ["ROCJPEG_B200_LANES"]
+    else:
+        os.environ["ROCJPEG_B200_LANES"] = lanes_env
 
     # ---- end-to-end arm (e2e): the public call, host buffers in ------------------------
     dec.set_profiling(False)                 # no stage events inside the timed call
@@ -416,7 +435,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(stage_bytes[dom]), "launch_ms": dom_ms},
-        "stages": stages,
+        "stages": stages, "stages_note": "CUDA-event time per stage of the same resident batch on one pipeline lane "
+                                         f"(stages serialised; that step takes {round(one_lane_ms, 4)} ms)",
         "k1": {"lanes": stats.lanes, "subsequence_bytes": stats.subsequence_bytes, "subsequences": int(stats.subsequences), "sync_rounds": stats.sync_rounds,
                "decodes_per_round": [int(x) for x in stats.decodes_per_round[:stats.sync_rounds]],
                "compressed_GB_s_all_k1": round(scan / ((stage_ms[2] + stage_ms[3]) or 1e-9) / 1e6, 2)},

@@ -201,7 +201,11 @@ int Decoder::Initialize() {
     sm_count_ = prop.multiProcessorCount;
     int st = lanes_[0].Create(device_id_, sm_count_);
     if (st != kSuccess) return Fail(st, lanes_[0].last_error());
-    RJB_CUDA(cudaStreamCreateWithFlags(&upload_stream_, cudaStreamNonBlocking));
+    // the upload stream outranks the lanes' streams: the CTAs of the gather kernel (PCIe-bound, few) must
+    // not queue behind the thousands of CTAs of another lane's decode kernels
+    int prio_lo = 0, prio_hi = 0;
+    RJB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    RJB_CUDA(cudaStreamCreateWithPriority(&upload_stream_, cudaStreamNonBlocking, prio_hi));
     profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0) != 0;
     initialized_ = true;
     // Multi-device sharding of rocJpegDecodeBatched (the C API has no way to ask for it, hence the
@@ -583,7 +587,11 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     guard.Acquire();
     RJB_CUDA(cudaMemcpyAsync(d, h, L.total, cudaMemcpyHostToDevice, up));
     stats_.h2d_bytes = L.total + scan_bytes_;
-    const bool use_gather = all_pinned_ && h_images_.size() > 4 && EnvInt("ROCJPEG_B200_NO_GATHER", 0) == 0;
+    // Many small pictures: one gather kernel reading the parsers' mapped page-locked buffers (a copy call
+    // per picture would cost the host more than the transfer). Few large ones: plain copies, which run on
+    // the copy engine at full PCIe rate without occupying SMs.
+    const bool use_gather = all_pinned_ && h_images_.size() > 4 && scan_bytes_ / h_images_.size() < (256u << 10) &&
+                            EnvInt("ROCJPEG_B200_NO_GATHER", 0) == 0;
     if (use_gather) {
         RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, d_scan_.as<uint8_t>(), up));
         stats_.kernel_launches++;
