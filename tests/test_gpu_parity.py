@@ -149,6 +149,37 @@ def test_single_sync_round_forces_fallback_and_still_exact(dec, orc, monkeypatch
     gu.assert_same(got, want, "fallback rounds")
 
 
+def test_damaged_scans_do_not_break_the_decoder(dec, orc):
+    """Random byte damage inside the entropy-coded data (and truncation): whatever comes out, the call
+    must return, the device must stay healthy and the next clean decode must be bit-exact."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    clean = {n: load(n) for n in ("synth_420_500x375_dri7", "synth_444_500x375", "custom_huffman_420_dri1", "mug_422_crop_dri1")}
+    for trial in range(24):
+        name = sorted(clean)[trial % len(clean)]
+        data = bytearray(clean[name])
+        sos = data.rfind(b"\xff\xda")
+        lo, hi = sos + 14, len(data) - 2
+        if trial % 6 == 5:
+            data = data[:lo + int(rng.integers(1, hi - lo))] + b"\xff\xd9"     # truncated scan
+        else:
+            for _ in range(int(rng.integers(1, 24))):
+                data[int(rng.integers(lo, hi))] = int(rng.integers(0, 256))
+        data = bytes(data)
+        s = api.JpegStream()
+        if s.parse(data) != api.SUCCESS:
+            continue
+        n, css, w, h = dec.image_info(s)
+        buf = torch.zeros(w[0] * h[0] * 3 + 64, dtype=torch.uint8, device="cuda")
+        st = dec.decode(s, api.make_params("rgb"), [(buf.data_ptr(), w[0] * 3)])
+        assert st in (api.SUCCESS, api.BAD_JPEG, api.JPEG_NOT_SUPPORTED, api.INVALID_PARAMETER), (name, trial, st)
+        torch.cuda.synchronize()
+        st, got, want = gu.decode_one(dec, orc, clean[name], "rgb")
+        assert st == api.SUCCESS
+        gu.assert_same(got, want, f"clean decode after damaged {name} #{trial}")
+
+
 def test_image_info_and_errors(dec, orc):
     lib = api.load_library()
     s = api.JpegStream()
