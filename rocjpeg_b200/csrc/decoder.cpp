@@ -461,7 +461,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         od.direct = (whole && planar && direct_ok) ? 1 : 0;
         od.tiles_x = od.direct ? 0u : uint32_t((od.w + kK3TileW - 1) / kK3TileW);
         od.tiles_y = od.direct ? 0u : uint32_t((od.h + kK3TileH - 1) / kK3TileH);
-        any_direct_ = any_direct_ || od.direct;
+        any_direct_ = any_direct_ || od.direct || !whole;   // the plane arena is then incomplete: the tap re-runs the IDCT
         od.tile0 = k3tile;
         h_k3_tile0_[size_t(i)] = k3tile;
         k3tile += od.tiles_x * od.tiles_y;
@@ -689,12 +689,31 @@ int Decoder::Split(const StreamParser* const* streams, int n) {
     int want = EnvInt("ROCJPEG_B200_LANES", 0);
     if (want <= 0) want = int(std::min<uint64_t>(kMaxLanes, total / (2u << 20)));   // about 2 MiB of scan per chunk at least
     want = std::max(1, std::min(std::min(want, kMaxLanes), n));
+    // Chunk sizes as cumulative shares of the scan bytes. Equal shares by default; ROCJPEG_B200_SPLIT
+    // ("15,35,35,15": percentages, one per lane) makes the first chunk small so the device starts early and
+    // the last one small so the tail behind the final upload is short.
+    double cum[kMaxLanes + 1] = {0};
+    for (int l = 1; l <= want; l++) cum[l] = double(l) / want;
+    if (const char* sp = std::getenv("ROCJPEG_B200_SPLIT")) {
+        double w[kMaxLanes] = {0}, sum = 0;
+        int k = 0;
+        for (const char* q = sp; *q && k < want;) {
+            w[k] = std::max(0.0, std::atof(q));
+            sum += w[k++];
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        if (k == want && sum > 0) {
+            double run = 0;
+            for (int l = 0; l < want; l++) cum[l + 1] = (run += w[l]) / sum;
+        }
+    }
     uint64_t acc = 0;
     int lane = 0;
     chunk_first_[0] = 0;
     for (int i = 0; i < n && lane + 1 < want; i++) {
         acc += streams[i] ? streams[i]->parsed().clean_bytes : 0;
-        if (acc * uint64_t(want) >= total * uint64_t(lane + 1) && i + 1 < n) chunk_first_[++lane] = i + 1;
+        if (double(acc) >= double(total) * cum[lane + 1] && i + 1 < n) chunk_first_[++lane] = i + 1;
     }
     active_lanes_ = lane + 1;
     chunk_first_[active_lanes_] = n;

@@ -126,6 +126,15 @@ __device__ __forceinline__ TileInfo ResolveTile(const K2Args& a, uint32_t tile) 
             ti.hmask = H - 1;
             ti.bpm = im.bpm;
             const OutputDesc& od = a.outputs[img];
+            if (!od.direct && !a.force_planes && (od.x0 != 0 || od.y0 != 0 || od.w != im.width || od.h != im.height)) {
+                // Region of interest (src/rocjpeg_decoder.cpp:120-141): the output stage only reads the
+                // samples under the crop rectangle, so blocks outside it are not transformed at all.
+                const int sx = (comp != 0 && (im.css == CSS_422 || im.css == CSS_420)) ? 1 : 0;
+                const int sy = (comp != 0 && (im.css == CSS_440 || im.css == CSS_420)) ? 1 : 0;
+                const int bx_lo = (od.x0 >> sx) >> 3, bx_hi = ((od.x0 + od.w - 1) >> sx) >> 3;
+                const int by_lo = (od.y0 >> sy) >> 3, by_hi = ((od.y0 + od.h - 1) >> sy) >> 3;
+                if (by < by_lo || by > by_hi || ti.bx0 > bx_hi || ti.bx0 + kBlocksPerTile - 1 < bx_lo) ti.direct = 2;
+            }
             if (od.direct && !a.force_planes) {
                 // channel, pitch and visible size of this component in the caller's layout
                 // (src/rocjpeg_decoder.cpp:576-636: planar chroma at the subsampled size, floor shifts;
