@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -394,6 +395,20 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         im.nseg = uint32_t(p.segments.size());
         im.sub0 = sub;
         const uint32_t ri = p.restart_interval > 0 ? uint32_t(p.restart_interval) : uint32_t(im.total_mcus);
+        // Region of interest + restart markers: a restart interval is an independent unit (predictors
+        // reset), so the intervals whose MCU rows lie wholly outside the crop rectangle are not entropy-
+        // decoded at all (same ROI rule as below: src/rocjpeg_decoder.cpp:126-131).
+        int64_t roi_row_lo = 0, roi_row_hi = INT64_MAX;
+        {
+            const uint32_t cw = uint32_t(int(params.crop_right) - int(params.crop_left));
+            const uint32_t chh = uint32_t(int(params.crop_bottom) - int(params.crop_top));
+            if (p.restart_interval > 0 && cw > 0 && chh > 0 && cw <= uint32_t(p.width) && chh <= uint32_t(p.height) &&
+                params.crop_top >= 0 && params.crop_bottom <= p.height && im.mcus_y > 0) {
+                const int mcu_h = 8 * std::max(1, p.ncomp == 1 ? 1 : p.vmax);
+                roi_row_lo = params.crop_top / mcu_h;
+                roi_row_hi = (params.crop_bottom - 1) / mcu_h;
+            }
+        }
         for (size_t sgi = 0; sgi < p.segments.size(); sgi++) {
             const Segment& sg = p.segments[sgi];
             SegmentDesc sd;
@@ -402,11 +417,14 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             sd.sub0 = sub;
             const uint64_t mcu_first = uint64_t(sgi) * ri;
             const uint64_t mcu_cnt = mcu_first >= uint64_t(im.total_mcus) ? 0 : std::min<uint64_t>(ri, uint64_t(im.total_mcus) - mcu_first);
+            if (mcu_cnt > 0 && (int64_t((mcu_first + mcu_cnt - 1) / uint64_t(im.mcus_x)) < roi_row_lo ||
+                                int64_t(mcu_first / uint64_t(im.mcus_x)) > roi_row_hi))
+                sd.nbytes = 0;   // outside the region of interest: no subsequences, its blocks stay "never decoded"
             sd.blk_first = uint32_t(mcu_first * uint64_t(p.bpm));
             sd.blk_count = uint32_t(mcu_cnt * uint64_t(p.bpm));
             h_segments_.push_back(sd);
             if (sd.nbytes == 0 && sd.blk_count != 0) needs_clear_ = true;   // a restart interval with no data at all (its records keep the 0xFF fill)
-            sub += (sg.nbytes + uint32_t(S) - 1) / uint32_t(S);
+            sub += (sd.nbytes + uint32_t(S) - 1) / uint32_t(S);
         }
         im.nsub = sub - im.sub0;
         sub = uint32_t(AlignUp(sub, kK1Owned));

@@ -149,6 +149,23 @@ def test_single_sync_round_forces_fallback_and_still_exact(dec, orc, monkeypatch
     gu.assert_same(got, want, "fallback rounds")
 
 
+@pytest.mark.parametrize("css", ["420", "422", "444", "400"])
+def test_crop_with_restart_markers_skips_entropy_work(dec, orc, css):
+    """Region of interest on a picture with one restart interval per MCU row: intervals outside the crop
+    rectangle are not entropy-decoded, blocks outside it not transformed - and the crop is still exact."""
+    data = datagen.make_jpeg(640, 480, css, seed=21, restart_rows=1)
+    crop = (160, 120, 480, 360)
+    for fmt in ("rgb", "yuv_planar", "native"):
+        st, got, want = gu.decode_one(dec, orc, data, fmt, crop=crop)
+        assert st == api.SUCCESS
+        gu.assert_same(got, want, f"dri crop {css} {fmt}")
+    cropped = dec.stats().subsequences
+    st, got, want = gu.decode_one(dec, orc, data, "rgb")
+    assert st == api.SUCCESS
+    gu.assert_same(got, want, f"dri full {css}")
+    assert cropped < dec.stats().subsequences
+
+
 def test_damaged_scans_do_not_break_the_decoder(dec, orc):
     """Random byte damage inside the entropy-coded data (and truncation): whatever comes out, the call
     must return, the device must stay healthy and the next clean decode must be bit-exact."""
