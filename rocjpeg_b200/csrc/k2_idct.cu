@@ -275,4 +275,13 @@ cudaError_t LaunchK2Idct(const K2Args& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Forces the module holding this stage's kernels onto the device (CUDA loads lazily: the first launch
+// of every kernel would otherwise pay for it inside the first decode call).
+cudaError_t PreloadK2() {
+    cudaFuncAttributes at;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k2_idct);
+    return e;
+}
+
 }  // namespace rjb

@@ -523,4 +523,13 @@ cudaError_t LaunchK3Output(const K3Args& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Forces the module holding this stage's kernels onto the device (CUDA loads lazily: the first launch
+// of every kernel would otherwise pay for it inside the first decode call).
+cudaError_t PreloadK3() {
+    cudaFuncAttributes at;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k3_output);
+    return e;
+}
+
 }  // namespace rjb

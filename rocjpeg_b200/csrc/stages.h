@@ -97,6 +97,11 @@ struct GatherItem {
     uint32_t nbytes;      // multiple of 16
     uint32_t chunk0;      // first 16 KiB gather chunk of this image
 };
+// Load the stages' kernels now instead of at their first launch.
+cudaError_t PreloadK1();
+cudaError_t PreloadK2();
+cudaError_t PreloadK3();
+
 cudaError_t LaunchGather(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena, cudaStream_t stream);
 
 }  // namespace rjb
