@@ -47,7 +47,9 @@ typedef struct {
     int32_t devices;                          /* GPUs the last call was sharded over (ROCJPEG_B200_DEVICES) */
 } RocJpegB200Stats;
 
-/* Enable/disable CUDA-event stage timing on a decoder handle (off by default; env ROCJPEG_B200_PROFILE=1). */
+/* CUDA-event timing on a decoder handle: 0 off (default), 1 an event after every stage (stage_ms and total_ms;
+ * the events keep neighbouring stages from overlapping), 2 first and last event only (total_ms).
+ * Env ROCJPEG_B200_PROFILE sets the initial level. */
 RocJpegStatus rocJpegB200SetProfiling(RocJpegHandle handle, int enable);
 /* Statistics of the last rocJpegDecode / rocJpegDecodeBatched / rocJpegB200Run on this handle. */
 RocJpegStatus rocJpegB200GetStats(RocJpegHandle handle, RocJpegB200Stats *stats);

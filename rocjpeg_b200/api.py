@@ -291,8 +291,9 @@ class Decoder:
         _check(self.lib.rocJpegB200GetDeviceCount(self.handle, C.byref(n)), "rocJpegB200GetDeviceCount")
         return n.value
 
-    def set_profiling(self, on: bool):
-        self.lib.rocJpegB200SetProfiling(self.handle, int(on))
+    def set_profiling(self, level):
+        """0/False off, 1/True per-stage events, 2 first/last event only (total_ms)."""
+        self.lib.rocJpegB200SetProfiling(self.handle, int(level))
 
     def stats(self) -> Stats:
         s = Stats()

@@ -205,7 +205,7 @@ const char* ROCJPEGAPI rocJpegGetErrorName(RocJpegStatus rocjpeg_status) {
 
 RocJpegStatus rocJpegB200SetProfiling(RocJpegHandle handle, int enable) {
     if (handle == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
-    static_cast<DecoderHandle*>(handle)->decoder->SetProfiling(enable != 0);
+    static_cast<DecoderHandle*>(handle)->decoder->SetProfiling(enable);
     return ROCJPEG_STATUS_SUCCESS;
 }
 

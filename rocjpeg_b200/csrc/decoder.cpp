@@ -217,7 +217,7 @@ int Decoder::Initialize() {
     int prio_lo = 0, prio_hi = 0;
     RJB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     RJB_CUDA(cudaStreamCreateWithPriority(&upload_stream_, cudaStreamNonBlocking, prio_hi));
-    profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0) != 0;
+    profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0);
     // everything a first decode would otherwise pay for: kernel modules, the lanes' streams and events
     RJB_CUDA(PreloadK1());
     RJB_CUDA(PreloadK2());
@@ -645,9 +645,14 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     return kSuccess;
 }
 
-int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up, UploadTurn turn) {
+int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, UploadTurn turn) {
     const int rounds = std::min(std::max(EnvInt("ROCJPEG_B200_SYNC_ROUNDS", 2), 1), kMaxSyncRounds);
-    auto mark = [&](int i) -> cudaError_t { return profiling_ ? cudaEventRecord(ev_[i], stream_) : cudaSuccess; };
+    // profiling 1: an event after every stage (they sit between the kernels, so neighbouring stages no longer
+    // overlap through programmatic dependent launch); 2: only the first and the last event (total time)
+    auto mark = [&](int i) -> cudaError_t {
+        const bool want = profiling_ == 1 || (profiling_ == 2 && (i == 0 || i == kStageCount));
+        return want ? cudaEventRecord(ev_[i], stream_) : cudaSuccess;
+    };
     stats_.kernel_launches = 0;
     RJB_CUDA(mark(0));
     if (include_upload) {
@@ -677,7 +682,7 @@ int Lane::LaunchAll(bool include_upload, bool profiling_, cudaStream_t up, Uploa
     return kSuccess;
 }
 
-int Lane::Finish(bool profiling_) {
+int Lane::Finish(int profiling_) {
     RJB_CUDA(cudaStreamSynchronize(stream_));
     const uint32_t* cnt = reinterpret_cast<const uint32_t*>(h_counters_.data());
     uint32_t last = stats_.sync_rounds - 1;
@@ -708,7 +713,7 @@ int Lane::Finish(bool profiling_) {
     }
     for (int r = 0; r < kMaxSyncRounds; r++) stats_.decodes_per_round[r] = cnt[kMaxSyncRounds + r];
     if (profiling_) {
-        for (int s = 0; s < kStageCount; s++) {
+        for (int s = 0; s < kStageCount && profiling_ == 1; s++) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, ev_[s], ev_[s + 1]) == cudaSuccess) stats_.stage_ms[s] = ms;
         }

@@ -128,8 +128,8 @@ class Lane {
     int Create(int device_id, int sm_count);
     int Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
     int Upload(cudaStream_t upload_stream, UploadTurn turn = UploadTurn());   // nullptr: use the lane's own stream
-    int LaunchAll(bool include_upload, bool profiling, cudaStream_t upload_stream, UploadTurn turn = UploadTurn());
-    int Finish(bool profiling);
+    int LaunchAll(bool include_upload, int profiling, cudaStream_t upload_stream, UploadTurn turn = UploadTurn());
+    int Finish(int profiling);
     int Sync();
     int CopyCoefficients(int image, int16_t* host_out, size_t count);
     int CopyPlanes(int image, uint8_t* host_out, size_t count);
@@ -199,7 +199,7 @@ class Decoder {
     int Run();          // launch all stages for the prepared batch and synchronise
     int CopyCoefficients(int image, int16_t* host_out, size_t count);   // component-major raster layout
     int CopyPlanes(int image, uint8_t* host_out, size_t count);
-    void SetProfiling(bool on) { profiling_ = on; }
+    void SetProfiling(int level) { profiling_ = level; }   // 0 off, 1 per-stage events, 2 first/last event only
     const BatchStats& stats() const { return stats_; }
     const std::string& last_error() const { return err_; }
     int device_id() const { return device_id_; }
@@ -220,7 +220,8 @@ class Decoder {
     void Aggregate();
 
     int backend_, device_id_;
-    bool initialized_ = false, profiling_ = false, prepared_ = false;
+    bool initialized_ = false, prepared_ = false;
+    int profiling_ = 0;
     std::mutex mutex_;
     std::string err_;
     int sm_count_ = 0;

@@ -348,6 +348,7 @@ __device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, uint32_t* lut, const 
 
 template <int S>
 __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
+    PdlEntry();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
     K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
@@ -477,6 +478,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
 constexpr int kScanThreads = 256;
 
 __global__ void __launch_bounds__(kScanThreads) k1_scan(K1Args a) {
+    PdlEntry();
     __shared__ uint32_t s_v[kScanThreads / 32], s_f[kScanThreads / 32], s_e[kScanThreads / 32];
     const uint32_t img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -534,6 +536,7 @@ __global__ void __launch_bounds__(kScanThreads) k1_scan(K1Args a) {
 
 template <int S>
 __global__ void __launch_bounds__(T) k1_write(K1Args a) {
+    PdlEntry();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
     K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
@@ -690,6 +693,7 @@ __device__ __forceinline__ int64_t LastReset(int64_t m0, int64_t m1, int ri) {
 }
 
 __global__ void __launch_bounds__(kDcTileMcus) dc_sums(K1Args a) {
+    PdlEntry();
     __shared__ int red[3];
     const int tid = threadIdx.x;
     const uint32_t tile = blockIdx.x;
@@ -720,6 +724,7 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_sums(K1Args a) {
 // One CTA per image: exclusive segmented scan over the image's DC-tile sums (a tile that
 // contains a predictor reset cuts the chain; its sums already start at its last reset).
 __global__ void __launch_bounds__(kScanThreads) dc_scan(K1Args a) {
+    PdlEntry();
     __shared__ int s_v[kScanThreads / 32][3];
     __shared__ uint32_t s_f[kScanThreads / 32];
     const uint32_t img = blockIdx.x;
@@ -774,6 +779,7 @@ __global__ void __launch_bounds__(kScanThreads) dc_scan(K1Args a) {
 }
 
 __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
+    PdlEntry();
     __shared__ int wsum[8][3];
     __shared__ int wflag[8];
     __shared__ int carry_s[3];
@@ -845,6 +851,7 @@ constexpr int kGatherCtas = 64;   // PCIe-bound: a few CTAs saturate the link; t
                                   // for the kernels of the other pipeline lanes
 
 __global__ void __launch_bounds__(256) gather_scans(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena) {
+    PdlEntry();
     __shared__ int s_item;
     for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
         __syncthreads();
@@ -871,9 +878,8 @@ cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream) {
     static_assert(S <= 128, "the packed decoder state holds bit positions below 2048");
     const size_t smem = sizeof(K1Smem<S>) + a.lut_smem_bytes;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;   // 3 table pairs + the full second-level arena fit
-    if (round >= 0) k1_sync<S><<<a.total_ctas, T, smem, stream>>>(a, round);
-    else k1_write<S><<<a.total_ctas, T, smem, stream>>>(a);
-    return cudaGetLastError();
+    if (round >= 0) return LaunchPdl(k1_sync<S>, dim3(a.total_ctas), dim3(T), smem, stream, a, round);
+    return LaunchPdl(k1_write<S>, dim3(a.total_ctas), dim3(T), smem, stream, a);
 }
 
 }  // namespace
@@ -890,7 +896,10 @@ cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream) {
 
 cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream) {
     if (a.total_ctas == 0) return cudaSuccess;
-    k1_scan<<<a.nimages, kScanThreads, 0, stream>>>(a);
+    {
+        const cudaError_t e = LaunchPdl(k1_scan, dim3(a.nimages), dim3(kScanThreads), 0, stream, a);
+        if (e != cudaSuccess) return e;
+    }
     switch (a.sub_bytes) {
         case 32: return SyncImpl<32>(a, -1, stream);
         case 64: return SyncImpl<64>(a, -1, stream);
@@ -901,16 +910,15 @@ cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream) {
 
 cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream) {
     if (a.total_dc_tiles == 0) return cudaSuccess;
-    dc_sums<<<a.total_dc_tiles, kDcTileMcus, 0, stream>>>(a);
-    dc_scan<<<a.nimages, kScanThreads, 0, stream>>>(a);
-    dc_apply<<<a.total_dc_tiles, kDcTileMcus, 0, stream>>>(a);
-    return cudaGetLastError();
+    cudaError_t e = LaunchPdl(dc_sums, dim3(a.total_dc_tiles), dim3(kDcTileMcus), 0, stream, a);
+    if (e == cudaSuccess) e = LaunchPdl(dc_scan, dim3(a.nimages), dim3(kScanThreads), 0, stream, a);
+    if (e == cudaSuccess) e = LaunchPdl(dc_apply, dim3(a.total_dc_tiles), dim3(kDcTileMcus), 0, stream, a);
+    return e;
 }
 
 cudaError_t LaunchGather(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena, cudaStream_t stream) {
     if (total_chunks == 0) return cudaSuccess;
-    gather_scans<<<min(total_chunks, uint32_t(kGatherCtas)), 256, 0, stream>>>(items, nitems, total_chunks, arena);
-    return cudaGetLastError();
+    return LaunchPdl(gather_scans, dim3(min(total_chunks, uint32_t(kGatherCtas))), dim3(256), 0, stream, items, nitems, total_chunks, arena);
 }
 
 // Forces the module holding this stage's kernels onto the device (CUDA loads lazily: the first launch

@@ -181,6 +181,7 @@ __device__ __forceinline__ void StoreClipped(uint8_t* dst, uint2 v, int n) {
 // column, no transposes, ~30% fewer instructions — was measured 22-28% SLOWER: 77 registers and
 // 33 KiB per CTA leave 24 warps per SM.)
 __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
+    PdlEntry();
     // Workspace [block][row][col], row stride kRS = 12 words, block stride kBS = 104 words. A warp holds
     // 4 blocks x 8 threads: column-wise, thread (b, j) touches word 104 b + 12 r + j -> bank 8 b + j + const,
     // all 32 distinct; row-wise it moves its row as two 128-bit accesses whose bank groups 3 j mod 8 are
@@ -271,8 +272,7 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
 
 cudaError_t LaunchK2Idct(const K2Args& a, cudaStream_t stream) {
     if (a.total_tiles == 0) return cudaSuccess;
-    k2_idct<<<(a.total_tiles + kTilesPerCta - 1) / kTilesPerCta, kThreads, 0, stream>>>(a);
-    return cudaGetLastError();
+    return LaunchPdl(k2_idct, dim3((a.total_tiles + kTilesPerCta - 1) / kTilesPerCta), dim3(kThreads), 0, stream, a);
 }
 
 // Forces the module holding this stage's kernels onto the device (CUDA loads lazily: the first launch

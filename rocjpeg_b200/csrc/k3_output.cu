@@ -384,6 +384,7 @@ __device__ __forceinline__ void RowRgbFast(const K3Job& j, int sy, bool gray, in
 }
 
 __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
+    PdlEntry();
     __shared__ __align__(16) uint8_t s_buf[kWarps][kRowBuf];
     __shared__ K3Job s_job;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -519,8 +520,7 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
 
 cudaError_t LaunchK3Output(const K3Args& a, cudaStream_t stream) {
     if (a.total_tiles == 0) return cudaSuccess;
-    k3_output<<<a.total_tiles, kThreads, 0, stream>>>(a);
-    return cudaGetLastError();
+    return LaunchPdl(k3_output, dim3(a.total_tiles), dim3(kThreads), 0, stream, a);
 }
 
 // Forces the module holding this stage's kernels onto the device (CUDA loads lazily: the first launch
