@@ -58,8 +58,8 @@ struct ImageDesc {
     uint64_t data_off;                                // byte offset of the image's clean stream in the scan arena
     uint32_t seg0, nseg;                              // this image's slice of the batch segment table
     uint32_t sub0, nsub;                              // first subsequence (multiple of the CTA size) and count
-    // coefficient store: a sparse stream of (zig-zag position, int16 value) entries in decode
-    // order plus, per block, the index of its first entry; DC kept in a compact per-block array
+    // coefficient store: a sparse stream of (int16 value, zig-zag index) entries in decode order
+    // plus one record per block {where its entries end, DC} (stages.h: BlockRec)
     uint64_t blk0;                                    // first block of this image in the per-block arrays
     uint64_t ent0;                                    // first entry of this image in the entry arena
     uint32_t ent_cap;                                 // entries reserved for this image (upper bound from the scan size)

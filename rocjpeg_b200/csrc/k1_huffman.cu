@@ -9,8 +9,9 @@
 //   segment      = one restart interval (or the whole scan when DRI is absent):
 //                  byte-aligned start, known decoder state, known first block.
 //   subsequence  = S consecutive bytes of a segment (S = 32/64/128), one thread.
-//   CTA          = kK1Threads consecutive subsequences of ONE image; the image's
-//                  Huffman tables and the CTA's bytes are staged in shared memory.
+//   CTA          = kK1Threads threads on ONE image: kK1Owned consecutive subsequences
+//                  it owns + the kK1Halo before them (re-decoded, never stored); the
+//                  image's Huffman tables and the CTA's bytes are staged in shared memory.
 //
 // Schedule (self-synchronising parallel Huffman decoding)
 //   k1_sync round 0   every thread decodes its subsequence from a guessed state
@@ -18,23 +19,25 @@
 //                     its end state; then, inside the CTA, every thread whose
 //                     predecessor's end state differs from the state it started
 //                     from re-decodes, until nothing changes. Huffman streams
-//                     re-synchronise after a few symbols, so this is typically
-//                     two decodes per thread.
-//   k1_sync round r>0 repairs what crossed CTA boundaries (thread 0 of a CTA had
-//                     no predecessor state in round 0). A CTA whose incoming state
-//                     is unchanged exits at once. The host checks the counter of
-//                     the last round; a non-zero value triggers more rounds
+//                     re-synchronise within tens of bytes, so this is typically
+//                     two decodes per thread, and thanks to the halo the state
+//                     entering the CTA's first owned subsequence is almost always
+//                     final already.
+//   k1_sync round r>0 verifies every CTA boundary against the owner's result and
+//                     repairs the few that differ. A CTA whose incoming state is
+//                     unchanged exits at once. The host checks the counter of the
+//                     last round; a non-zero value triggers more rounds
 //                     (correctness never depends on the stream synchronising).
-//   k1_write          block positions = segmented prefix sums of the per-thread
-//                     block counts, entry offsets = prefix sums of the per-thread
-//                     entry counts (CTA scan + look-back over CTA partials); the
-//                     final decode then writes the image's sparse coefficient stream
-//                     (one 32-bit (position, int16 value) entry per non-zero
-//                     coefficient), the index of every block's first entry, and one
-//                     DC difference per block.
-//   dc_sums/dc_apply  per-component, per-restart-interval prefix sum of the DC
-//                     differences; the absolute DC replaces the difference in the
-//                     compact per-block DC array that K2 reads.
+//   k1_scan           per image: exclusive prefix of the CTAs' block counts
+//                     (segmented at restart intervals) and entry counts.
+//   k1_write          the final decode: the image's sparse coefficient stream (one
+//                     32-bit (int16 value, zig-zag index) entry per symbol with
+//                     magnitude bits, four per 128-bit store) and one 8-byte record
+//                     per block {where its entries end, DC difference}.
+//   dc_sums / dc_scan / dc_apply
+//                     per-component, per-restart-interval prefix sum of the DC
+//                     differences; the integrated DC replaces the difference in the
+//                     block's record, where K2 reads it.
 #include <cuda_runtime.h>
 
 #include <cstddef>
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     uint32_t* wsum = sm.scratch;          // [4] warp totals (value of the open segment at warp end)
     uint32_t* wflag = sm.scratch + 4;     // [4] warp contains a start
     uint32_t* wents = sm.scratch + 8;     // [4] warp entry totals
-    uint32_t* carry_s = sm.scratch + 12;  // [2] look-back results: blocks, entries
+    uint32_t* carry_s = sm.scratch + 12;  // [2] what enters the CTA: blocks, entries
     if (lane == 31) { wsum[warp] = v; wflag[warp] = f; wents[warp] = e; }
     // what enters this CTA from the previous CTAs of the image: k1_scan prepared it (a look-back here
     // would re-read every earlier partial of the image, quadratic for the 8192x8192 pictures)

@@ -4,7 +4,7 @@
 // sequential decode core (csrc/huff_core.cuh, compiled for the host) through a
 // serial emulation of what k1_huffman.cu does in parallel: subsequences of S
 // bytes, CTAs of T subsequences, speculative round 0 with CTA-local Jacobi
-// fix-up, cross-CTA rounds, CTA partials + look-back, write pass, tiled DC scan.
+// fix-up (with the CTA halo), cross-CTA rounds, CTA partials + prefix, write pass, DC scan.
 // It lets the no-GPU test suite check the *algorithm* (state packing,
 // convergence logic, block positions, DC integration) against the oracle; the
 // CUDA kernels themselves are checked by the -m gpu tests.
@@ -172,7 +172,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         stats->nsub = nsub;
         stats->nctas = nctas;
     }
-    // CTA partials + look-back carry (as k1_write does)
+    // CTA partials + carry (as k1_scan / k1_write do)
     std::vector<uint32_t> cta_flag(nctas, 0), cta_tail(nctas, 0);
     for (uint32_t cta = 0; cta < nctas; cta++) {
         uint32_t tail = 0, flag = 0;
