@@ -571,10 +571,12 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
             e += pe;
         }
     }
-    uint32_t* wsum = sm.scratch;          // [4] warp totals (value of the open segment at warp end)
-    uint32_t* wflag = sm.scratch + 4;     // [4] warp contains a start
-    uint32_t* wents = sm.scratch + 8;     // [4] warp entry totals
-    uint32_t* carry_s = sm.scratch + 12;  // [2] what enters the CTA: blocks, entries
+    constexpr int kW = T / 32;
+    static_assert(3 * kW + 2 <= 40, "scratch");
+    uint32_t* wsum = sm.scratch;               // [kW] warp totals (value of the open segment at warp end)
+    uint32_t* wflag = sm.scratch + kW;         // [kW] warp contains a start
+    uint32_t* wents = sm.scratch + 2 * kW;     // [kW] warp entry totals
+    uint32_t* carry_s = sm.scratch + 3 * kW;   // [2] what enters the CTA: blocks, entries
     if (lane == 31) { wsum[warp] = v; wflag[warp] = f; wents[warp] = e; }
     // what enters this CTA from the previous CTAs of the image: k1_scan prepared it (a look-back here
     // would re-read every earlier partial of the image, quadratic for the 8192x8192 pictures)
