@@ -152,14 +152,17 @@ def build_workload(name, n):
 
 
 def pixels_of(datas):
-    import oracle  # header parse only, for width/height of the inputs
+    """Total pixels and (width, height, subsampling) per picture, from the library's own parser."""
+    from rocjpeg_b200 import api
 
-    orc = oracle.Oracle()
     tot, dims = 0, []
+    s = api.JpegStream()
     for d in datas:
-        rc, i = orc.parse(d)
+        assert s.parse(d) == api.SUCCESS
+        i = s.info()
         tot += i.width * i.height
-        dims.append((i.width, i.height, oracle.CSS[i.css]))
+        dims.append((i.width, i.height, api.CSS_NAME[i.chroma_subsampling]))
+    s.close()
     return tot, dims
 
 
