@@ -348,7 +348,6 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     if (S != 32 && S != 64 && S != 128) S = (total_clean >= (256u << 10)) ? 128 : (total_clean >= (48u << 10)) ? 64 : 32;
     stats_.sub_bytes = S;
 
-    needs_clear_ = false;
     any_direct_ = false;
     needs_planes_ = false;
     const bool direct_ok = EnvInt("ROCJPEG_B200_NO_DIRECT", 0) == 0;
@@ -442,7 +441,6 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             sd.blk_first = uint32_t(mcu_first * uint64_t(p.bpm));
             sd.blk_count = uint32_t(mcu_cnt * uint64_t(p.bpm));
             h_segments_.push_back(sd);
-            if (sd.nbytes == 0 && sd.blk_count != 0) needs_clear_ = true;   // a restart interval with no data at all (its records keep the 0xFF fill)
             sub += (sd.nbytes + uint32_t(S) - 1) / uint32_t(S);
         }
         im.nsub = sub - im.sub0;

@@ -56,10 +56,10 @@ class DeviceBuffer {
 
 enum StageId {
     kStageUpload = 0,   // descriptor block + entropy-coded bytes, host -> device
-    kStageClear,        // counter reset (the coefficient arena is cleared only for damaged streams)
+    kStageClear,        // block records filled with "never decoded", counters reset
     kStageSync,         // all k1_sync rounds
-    kStageWrite,        // k1_write
-    kStageDc,           // dc_sums + dc_apply
+    kStageWrite,        // k1_scan + k1_write
+    kStageDc,           // dc_sums + dc_scan + dc_apply
     kStageIdct,         // k2_idct
     kStageOutput,       // k3_output
     kStageCount
@@ -75,7 +75,6 @@ struct BatchStats {
     uint64_t subsequences = 0;
     uint64_t plane_bytes = 0;           // bytes of decoded component planes (K2 output)
     uint64_t output_bytes = 0;          // bytes K3 writes
-    uint64_t k3_read_bytes = 0;         // plane bytes K3 reads
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
     uint32_t kernel_launches = 0;
     int sub_bytes = 0;
@@ -164,7 +163,7 @@ class Lane {
     K2Args k2_ = {};
     K3Args k3_ = {};
     uint32_t gather_chunks_ = 0;
-    bool all_pinned_ = false, needs_clear_ = false, any_direct_ = false, needs_planes_ = false;
+    bool all_pinned_ = false, any_direct_ = false, needs_planes_ = false;
     size_t scan_bytes_ = 0, coef_blocks_ = 0, entry_count_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
 
     StagingBuffer h_desc_;        // pinned descriptor block

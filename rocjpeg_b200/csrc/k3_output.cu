@@ -84,11 +84,6 @@ __device__ __forceinline__ uint2 Load8(const uint8_t* row, int x) {
     return make_uint2(Pack4(b[0], b[1], b[2], b[3]), Pack4(b[4], b[5], b[6], b[7]));
 }
 
-struct Planes {
-    const uint8_t* p[3];
-    uint32_t pitch[3];
-};
-
 // Stage `n` bytes produced 8 per lane (two words) at buf[phase + 8*lane ..): word stores when
 // the phase allows, byte stores otherwise and in the ragged last lane.
 __device__ __forceinline__ void Stage8(uint8_t* buf, int phase, int lane, int n, uint2 v) {
