@@ -33,7 +33,8 @@ __constant__ uint8_t c_zigzag_k2[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 
 
 constexpr int kBlocksPerTile = 32;
 constexpr int kThreads = kBlocksPerTile * 8;
-constexpr int kTilesPerCta = 4;
+constexpr int kTilesPerCta = 8;
+constexpr int kSearchCache = 1024;   // image tile prefix entries searched in shared memory
 
 // Everything the 256 threads of a CTA need about one tile (32 adjacent blocks of one block row
 // of one component), resolved once per tile by one thread.
@@ -54,11 +55,20 @@ struct TileInfo {
     int32_t clip_w, clip_rows;
 };
 
-__device__ __forceinline__ uint32_t UpperIndexK2(const uint32_t* a, uint32_t n, uint32_t v) {
+// largest i in [0, n) with a[i] <= v; the prefix array is searched in its shared-memory copy when it
+// fits (eight dependent global loads per tile were a fifth of the kernel: profiles/r01f_*)
+__device__ __forceinline__ uint32_t UpperIndexK2(const uint32_t* a, const uint32_t* cached, uint32_t n, uint32_t v) {
     uint32_t lo = 0, hi = n;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(a + mid) <= v) lo = mid; else hi = mid;
+    if (cached) {
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (cached[mid] <= v) lo = mid; else hi = mid;
+        }
+    } else {
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(a + mid) <= v) lo = mid; else hi = mid;
+        }
     }
     return lo;
 }
@@ -98,11 +108,11 @@ __device__ __forceinline__ uint32_t PackSat4(int v0, int v1, int v2, int v3) {
 
 // tile -> (image, component, block row, first block column); sampling factors are powers of two,
 // so no division in the hot part
-__device__ __forceinline__ TileInfo ResolveTile(const K2Args& a, uint32_t tile) {
+__device__ __forceinline__ TileInfo ResolveTile(const K2Args& a, const uint32_t* cached_tile0, uint32_t tile) {
     TileInfo ti = {};
     ti.nbx = -1;
     if (tile >= a.total_tiles) return ti;
-    const uint32_t img = UpperIndexK2(a.img_tile0, uint32_t(a.nimages), tile);
+    const uint32_t img = UpperIndexK2(a.img_tile0, cached_tile0, uint32_t(a.nimages), tile);
     const ImageDesc& im = a.images[img];
     uint32_t t = tile - a.img_tile0[img];
     for (int comp = 0; comp < im.ncomp; comp++) {
@@ -193,11 +203,17 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
     // (low half) and its quantiser step (high half) - one shared load replaces the zig-zag lookup, the
     // row/column split and the quantiser load
     __shared__ uint32_t s_tab[kTilesPerCta][64];
+    __shared__ uint32_t s_tile0[kSearchCache];
     const int tid = threadIdx.x;
-    if (tid < kTilesPerCta) s_tile[tid] = ResolveTile(a, blockIdx.x * kTilesPerCta + tid);
+    const bool cached = a.nimages <= kSearchCache;
+    if (cached) {
+        for (int i = tid; i < a.nimages; i += kThreads) s_tile0[i] = __ldg(a.img_tile0 + i);
+        __syncthreads();
+    }
+    if (tid < kTilesPerCta) s_tile[tid] = ResolveTile(a, cached ? s_tile0 : nullptr, blockIdx.x * kTilesPerCta + tid);
     __syncthreads();
-    {
-        const int t = tid >> 6, code = tid & 63;   // entries carry position + 1 (huff_core.cuh)
+    for (int idx = tid; idx < kTilesPerCta * 64; idx += kThreads) {
+        const int t = idx >> 6, code = idx & 63;   // entries carry position + 1 (huff_core.cuh)
         const TileInfo& ti = s_tile[t];
         if (ti.nbx >= 0) {
             const int nat = c_zigzag_k2[(code + 63) & 63];
@@ -233,13 +249,24 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
         __syncwarp();
         const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(&s_tab[it][0]));
         const uint32_t my_sa = uint32_t(__cvta_generic_to_shared(my));
-        for (uint32_t k = uint32_t(j); k < n; k += 8, ep += 8) {
-            const uint32_t en = __ldg(ep);
+        auto put = [&](uint32_t en) {
             uint32_t t;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(tab_sa + ((en >> 14) & 0xFCu)));
             const int v = int(int16_t(en & 0xFFFFu)) * int(t >> 16);
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_sa + (t & 0xFFFFu)), "r"(v) : "memory");
+        };
+        // four loads in flight per thread (32 entries per block) before the first is used: the loop was
+        // waiting on one global load after the other
+        {
+            const uint32_t k = uint32_t(j);
+            uint32_t e[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) e[u] = (k + 8u * u < n) ? __ldg(ep + 8 * u) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k + 8u * u < n) put(e[u]);
         }
+        for (uint32_t k = uint32_t(j) + 32u; k < n; k += 8) put(__ldg(ep + (k - uint32_t(j))));
         __syncwarp();
         if (valid && j == 0) my[0] = dc * int(s_tab[it][1] >> 16);   // integrated DC replaces any DC-difference entry
         __syncwarp();
