@@ -64,6 +64,23 @@ __device__ __forceinline__ uint32_t UpperIndex(const uint32_t* a, uint32_t n, ui
     return lo;
 }
 
+// The CTA -> image search of the two decode kernels: on a copy of the prefix array in shared memory (the
+// scan-word area, not yet in use) when it fits - one coalesced load instead of eight dependent ones.
+template <int CAP>
+__device__ __forceinline__ uint32_t ImageOfCta(const K1Args& a, uint32_t* scratch, uint32_t cta) {
+    const uint32_t n = uint32_t(a.nimages);
+    if (n > uint32_t(CAP)) return UpperIndex(a.img_cta0, n, cta);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) scratch[i] = __ldg(a.img_cta0 + i);
+    __syncthreads();
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (scratch[mid] <= cta) lo = mid; else hi = mid;
+    }
+    __syncthreads();   // the area is about to be overwritten with the scan words
+    return lo;
+}
+
 // ---- raw shared-memory primitives for the two hot loops ----------------------------------
 __device__ __forceinline__ uint32_t SharedAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t Lds32(uint32_t a) {
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
     const int tid = threadIdx.x;
     const uint32_t cta = blockIdx.x;
-    const uint32_t img = UpperIndex(a.img_cta0, uint32_t(a.nimages), cta);
+    const uint32_t img = ImageOfCta<T * K1Smem<S>::kSlotStride>(a, sm.words, cta);
     const ImageDesc& im = a.images[img];
     const int64_t gi = int64_t(cta) * TO + tid - H;
     const uint32_t g = uint32_t(gi);
@@ -545,7 +562,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t cta = blockIdx.x;
-    const uint32_t img = UpperIndex(a.img_cta0, uint32_t(a.nimages), cta);
+    const uint32_t img = ImageOfCta<T * K1Smem<S>::kSlotStride>(a, sm.words, cta);
     const ImageDesc& im = a.images[img];
     const int64_t gi = int64_t(cta) * TO + tid - H;
     const uint32_t g = uint32_t(gi);
