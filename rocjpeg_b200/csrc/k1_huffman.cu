@@ -303,58 +303,71 @@ struct K1Smem {
     uint32_t scratch[40];
 };
 
+// Huffman tables + block schedule of one image into shared memory (any CTA size; no barrier inside).
 template <int S>
-__device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, uint32_t* lut, const K1Args& a, const ImageDesc& im, const Sub& me) {
-    const int tid = threadIdx.x;
+__device__ __forceinline__ LutView StageTables(uint32_t* lut, uint16_t* sched, uint8_t* pair_tab, const K1Args& a, const ImageDesc& im) {
+    const int tid = threadIdx.x, nth = blockDim.x;
     // Lane forms "AC table of the current pair" as (table address | 2048): every pair's DC table must
     // start at a shared-window address with bit 11 clear. The tables lie at multiples of 4096 from
     // the start of dynamic shared memory, which itself begins less than 2048 bytes into the window
     // (0 or the 1 KiB the system reserves); anything else must fail loudly, not decode garbage.
     if (tid == 0 && (SharedAddr(lut) & 2048u) != 0) __trap();
-    sm.start[tid] = me.active ? uint32_t(me.start - im.data_off) : ~0u;
     const HuffLutSet* set = a.luts + im.lut_set;
     const int npairs = im.npairs;
-    // Huffman tables of this image: per (DC, AC) table pair the two first-level tables back to back
+    // per (DC, AC) table pair the two first-level tables back to back, then the second-level arena
     {
         uint4* dst = reinterpret_cast<uint4*>(lut);
         constexpr int kVecsPerTable = kFastSize * 4 / 16;
-        for (int i = tid; i < npairs * 2 * kVecsPerTable; i += T) {
+        for (int i = tid; i < npairs * 2 * kVecsPerTable; i += nth) {
             const int tsel = i / kVecsPerTable, v = i - tsel * kVecsPerTable;   // tsel = 2 * pair + is_ac
             const int tab = (tsel & 1) ? im.pair_ac[tsel >> 1] : im.pair_dc[tsel >> 1];
             dst[i] = __ldg(reinterpret_cast<const uint4*>(set->fast[tab]) + v);
         }
         uint4* sdst = dst + npairs * 2 * kVecsPerTable;
         const int nsub_vecs = int((__ldg(&set->sub_used) + 3u) >> 2);
-        for (int i = tid; i < nsub_vecs; i += T) sdst[i] = __ldg(reinterpret_cast<const uint4*>(set->sub) + i);
+        for (int i = tid; i < nsub_vecs; i += nth) sdst[i] = __ldg(reinterpret_cast<const uint4*>(set->sub) + i);
     }
-    if (tid < 8) sm.pair_tab[tid] = tid < 2 * npairs ? ((tid & 1) ? im.pair_ac[tid >> 1] : im.pair_dc[tid >> 1]) : 0;
+    if (tid < 8) pair_tab[tid] = tid < 2 * npairs ? ((tid & 1) ? im.pair_ac[tid >> 1] : im.pair_dc[tid >> 1]) : 0;
     {
         const int bpm = im.bpm;
         int c = tid % bpm;
-        for (int j = tid; j < K1Smem<S>::kSchedLen; j += T) {
-            sm.sched[j] = uint16_t(SharedAddr(lut) + (uint32_t(im.mcu_pair[c]) << 12));   // the window is < 64 KiB
-            c = (c + T) % bpm;
+        for (int j = tid; j < K1Smem<S>::kSchedLen; j += nth) {
+            sched[j] = uint16_t(SharedAddr(lut) + (uint32_t(im.mcu_pair[c]) << 12));   // the window is < 64 KiB
+            c = (c + nth) % bpm;
         }
     }
+    LutView lv;
+    lv.fast_sa = SharedAddr(lut);
+    lv.sub_sa = lv.fast_sa + uint32_t(npairs) * 4096u;
+    lv.set = set;
+    lv.pair_tab = pair_tab;
+    return lv;
+}
+
+// One subsequence's bytes into a slot of kSlotStride words, big-endian (bit 31 of a word is the first
+// bit of the stream, huff_core.cuh); the last vector's final word lies beyond the slot and is not kept.
+template <int S>
+__device__ __forceinline__ void StageSlotVec(uint32_t* slot, const uint8_t* src, int v) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + v);
+    uint32_t* w = slot + v * 4;
+    w[0] = ByteSwap32(q.x); w[1] = ByteSwap32(q.y); w[2] = ByteSwap32(q.z);
+    if (v != K1Smem<S>::kSlotVecs - 1) w[3] = ByteSwap32(q.w);
+}
+
+template <int S>
+__device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, uint32_t* lut, const K1Args& a, const ImageDesc& im, const Sub& me) {
+    const int tid = threadIdx.x;
+    sm.start[tid] = me.active ? uint32_t(me.start - im.data_off) : ~0u;
+    const LutView lv = StageTables<S>(lut, sm.sched, sm.pair_tab, a, im);
     __syncthreads();
     constexpr int V = K1Smem<S>::kSlotVecs;
     for (int idx = tid; idx < T * V; idx += T) {
         const int slot = idx / V, v = idx - slot * V;
         const uint32_t st = sm.start[slot];
         if (st == ~0u) continue;
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.scan + im.data_off + st) + v);
-        uint32_t* w = sm.words + slot * K1Smem<S>::kSlotStride + v * 4;
-        // stored big-endian: bit 31 of a word is the first bit of the stream (huff_core.cuh); the last
-        // vector's final word belongs to the next slot and is not kept
-        w[0] = ByteSwap32(q.x); w[1] = ByteSwap32(q.y); w[2] = ByteSwap32(q.z);
-        if (v != V - 1) w[3] = ByteSwap32(q.w);
+        StageSlotVec<S>(sm.words + slot * K1Smem<S>::kSlotStride, a.scan + im.data_off + st, v);
     }
     __syncthreads();
-    LutView lv;
-    lv.fast_sa = SharedAddr(lut);
-    lv.sub_sa = lv.fast_sa + uint32_t(npairs) * 4096u;
-    lv.set = set;
-    lv.pair_tab = sm.pair_tab;
     return lv;
 }
 
@@ -367,7 +380,7 @@ __device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, uint32_t* lut, const 
 // result and repairs the few that differ.
 
 template <int S>
-__global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
+__global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters) {
     PdlEntry();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
@@ -385,9 +398,10 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
 
     uint32_t my_used = 0, out = 0, old_out = kNoState;
     if (round > 0) {
-        // Does anything entering this CTA differ from what it was decoded with?
+        // Does any owned subsequence start from a state that is not its predecessor's end state (the CTA
+        // boundary after a neighbour changed, or - behind k1_fix - a chain it could not finish)?
         int need0 = 0;
-        if (tid == H && me.active && !me.first) need0 = (StateKey(a.state[g - 1]) != a.used[g]);
+        if (me.active && !me.first) need0 = (StateKey(a.state[g - 1]) != a.used[g]);
         if (!__syncthreads_or(need0)) return;
         if (me.active) {
             my_used = a.used[g];
@@ -430,7 +444,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round) {
     // CTA-local fix-up: re-decode while the predecessor's end state is not the state used. The
     // subsequences that need it are compacted into a queue so that the re-decodes occupy as few
     // warps as possible (a warp with one busy lane costs as many issue slots as a full one).
-    for (int iter = 0; iter < T + 1; iter++) {
+    for (int iter = 0; iter < max_iters; iter++) {
         __syncthreads();
         // a predecessor slot that maps to no data (before the image's first subsequence) hands over
         // nothing: such a thread is `first` and never re-decodes, so the value read is irrelevant
@@ -896,22 +910,23 @@ __global__ void __launch_bounds__(256) gather_scans(const GatherItem* items, int
 }
 
 template <int S>
-cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream) {
+cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream, int max_iters = T + 1) {
     static_assert(S <= 128, "the packed decoder state holds bit positions below 2048");
     const size_t smem = sizeof(K1Smem<S>) + a.lut_smem_bytes;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;   // 3 table pairs + the full second-level arena fit
-    if (round >= 0) return LaunchPdl(k1_sync<S>, dim3(a.total_ctas), dim3(T), smem, stream, a, round);
+    if (round >= 0) return LaunchPdl(k1_sync<S>, dim3(a.total_ctas), dim3(T), smem, stream, a, round, max_iters);
     return LaunchPdl(k1_write<S>, dim3(a.total_ctas), dim3(T), smem, stream, a);
 }
 
 }  // namespace
 
-cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream) {
+cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream, int max_iters) {
     if (a.total_ctas == 0) return cudaSuccess;
+    if (max_iters <= 0) max_iters = T + 1;
     switch (a.sub_bytes) {
-        case 32: return SyncImpl<32>(a, round, stream);
-        case 64: return SyncImpl<64>(a, round, stream);
-        case 128: return SyncImpl<128>(a, round, stream);
+        case 32: return SyncImpl<32>(a, round, stream, max_iters);
+        case 64: return SyncImpl<64>(a, round, stream, max_iters);
+        case 128: return SyncImpl<128>(a, round, stream, max_iters);
         default: return cudaErrorInvalidValue;
     }
 }

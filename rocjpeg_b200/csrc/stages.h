@@ -95,7 +95,8 @@ struct K1Args {
 };
 
 // Speculative decode + CTA-local synchronisation (round 0) or cross-CTA fix-up (round >= 1).
-cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream);
+// max_iters bounds the CTA-local fix-up loop (<= 0: until nothing changes).
+cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream, int max_iters = 0);
 // Final pass: positions from the block counts, coefficients and DC differences written.
 cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream);
 // DC prediction: per-tile sums, then prefix; absolute DC written over the per-block differences.
