@@ -456,8 +456,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         blk += im.nblocks;
         // entry arena: every entry consumes at least min_entry_bits of the scan, and a block holds at most 64
         im.ent0 = ent;
-        // (+3 padding entries per subsequence: every thread's run is rounded up to whole 16-byte stores)
-        im.ent_cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 3 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
+        // (+7 padding entries per subsequence: every thread's run is rounded up to whole 32-byte stores)
+        im.ent_cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 7 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
         ent += (uint64_t(im.ent_cap) + 63) & ~uint64_t(63);
         im.dc_tile0 = dctile;
         h_img_dctile0_[size_t(i)] = dctile;

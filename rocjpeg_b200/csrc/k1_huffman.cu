@@ -32,7 +32,7 @@
 //                     (segmented at restart intervals) and entry counts.
 //   k1_write          the final decode: the image's sparse coefficient stream (one
 //                     32-bit (int16 value, zig-zag index) entry per symbol with
-//                     magnitude bits, four per 128-bit store) and one 8-byte record
+//                     magnitude bits, eight per 256-bit store) and one 8-byte record
 //                     per block {where its entries end, DC difference}.
 //   dc_sums / dc_scan / dc_apply
 //                     per-component, per-restart-interval prefix sum of the DC
@@ -230,7 +230,7 @@ __device__ __forceinline__ uint32_t DecodeCount(uint32_t slot_sa, const LutView&
         }
     }
     const uint32_t nb = ln.Blocks(), acc = ln.acc;
-    *nnz_out = (((acc >> 11) & 0x3FFu) + 3u) & ~3u;   // a thread's run of the entry stream is padded to whole 16-byte stores
+    *nnz_out = (((acc >> 11) & 0x3FFu) + 7u) & ~7u;   // a thread's run of the entry stream is padded to whole 32-byte stores
     // bits consumed past the end (meaningful when the end is word-aligned, i.e. whenever a successor exists)
     return PackState(acc & 63u, int((uint32_t(StateC(key)) + nb) % uint32_t(bpm)), int((acc >> 21) & 63u), nb > 0xFFFFu ? 0xFFFFu : nb);
 }
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     if (!me.active) return;
     // ---- final decode: every symbol with magnitude bits becomes one 32-bit entry of the
     // image's coefficient stream, written at its final position (each thread owns a contiguous
-    // run of the stream, four entries per 128-bit store); every block end records the index one
+    // run of the stream, eight entries per 256-bit store); every block end records the index one
     // past the block's last entry, every DC symbol its difference in the compact per-block array.
     // A block's entries begin where the previous block's end (block 0: entry 0): what lies between
     // two threads' runs or two restart intervals is zero padding (position 0, which K2 overwrites
@@ -643,17 +643,21 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     uint32_t key = 0;
     if (!me.first) key = StateKey(a.state[g - 1]);
     const uint32_t blk0 = sd.blk_first + excl, limit = sd.blk_first + sd.blk_count;
-    // running pointers: the current block's record {end-of-entries index, DC} and the next 16-byte
+    // running pointers: the current block's record {end-of-entries index, DC} and the next 32-byte
     // entry group of this thread's run; the run never leaves its reservation [n, n_end), the
     // reservations never leave the image's arena
     BlockRec* recs = a.blk_rec + im.blk0;
     BlockRec* rp = recs + blk0;
     const uint32_t rp_stop = uint32_t(reinterpret_cast<uintptr_t>(recs + limit));   // low word is enough: < 4 GiB of records
     uint32_t* ep = a.entries + im.ent0 + n;
-    const uint32_t n_end = min(n + my_nnz, im.ent_cap & ~3u);
+    const uint32_t n_end = min(n + my_nnz, im.ent_cap & ~7u);
     Lane ln;
     ln.Init(SharedAddr(sm.words + tid * K1Smem<S>::kSlotStride), SharedAddr(sm.sched), key, me.end_bit);
-    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;   // the last four entries (oldest in q0): a group leaves as one 128-bit store
+    // The last four entries (oldest in q0) and, once four have gathered, the first half of the group of
+    // eight (h0..h3): a group leaves as ONE 256-bit store, a whole 32-byte sector. The store path is the
+    // write pass's second bottleneck (every lane writes its own run, so a store instruction is as many
+    // transactions as it has active lanes): half the stores of the 128-bit form (profiles/r01g_*).
+    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
     int dcv = 0;                               // DC difference of the block in progress, when its DC symbol was ours
     uint32_t has_dc = StateZ(key) == 0 ? 1u : 0u;
     if (blk0 < limit && me.end_bit != 0) {
@@ -667,35 +671,40 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
             // whose upper half is the zig-zag index AFTER the symbol (+ state bits K2 masks off)
             asm volatile(
                 "{\n\t"
-                ".reg .pred pdc, pnz, pneg, pfl, pst;\n\t"
+                ".reg .pred pdc, pnz, pneg, pfl, pst, phalf;\n\t"
                 ".reg .b32 sz, bits, sh, t, rs, ex, m, v, zq;\n\t"
-                "shr.u32 sz, %7, 28;\n\t"
-                "and.b32 bits, %7, 31;\n\t"
+                "shr.u32 sz, %11, 28;\n\t"
+                "and.b32 bits, %11, 31;\n\t"
                 "sub.u32 sh, bits, sz;\n\t"
-                "shl.b32 t, %8, sh;\n\t"
+                "shl.b32 t, %12, sh;\n\t"
                 "sub.u32 rs, 32, sz;\n\t"
                 "shf.r.clamp.b32 ex, t, 0, rs;\n\t"
                 "bmsk.clamp.b32 m, 0, sz;\n\t"
                 "setp.lt.s32 pneg, t, 0;\n\t"
                 "selp.b32 m, 0, m, pneg;\n\t"
                 "sub.s32 v, ex, m;\n\t"
-                "and.b32 zq, %9, 0x7e00000;\n\t"
+                "and.b32 zq, %13, 0x7e00000;\n\t"
                 "setp.eq.u32 pdc, zq, 0;\n\t"
                 "@pdc mov.b32 %6, v;\n\t"
                 "setp.ne.u32 pnz, sz, 0;\n\t"
-                "shr.u32 zq, %10, 21;\n\t"
+                "shr.u32 zq, %14, 21;\n\t"
                 "@pnz mov.b32 %0, %1;\n\t"
                 "@pnz mov.b32 %1, %2;\n\t"
                 "@pnz mov.b32 %2, %3;\n\t"
                 "@pnz prmt.b32 %3, v, zq, 0x5410;\n\t"
                 "@pnz add.u32 %4, %4, 1;\n\t"
-                "and.b32 zq, %4, 3;\n\t"
+                "and.b32 zq, %4, 7;\n\t"
+                "setp.eq.and.u32 phalf, zq, 4, pnz;\n\t"
                 "setp.eq.and.u32 pfl, zq, 0, pnz;\n\t"
-                "setp.le.and.u32 pst, %4, %11, pfl;\n\t"
-                "@pst st.global.v4.b32 [%5], {%0, %1, %2, %3};\n\t"
-                "@pfl add.u64 %5, %5, 16;\n\t"
+                "@phalf mov.b32 %7, %0;\n\t"
+                "@phalf mov.b32 %8, %1;\n\t"
+                "@phalf mov.b32 %9, %2;\n\t"
+                "@phalf mov.b32 %10, %3;\n\t"
+                "setp.le.and.u32 pst, %4, %15, pfl;\n\t"
+                "@pst st.global.v8.b32 [%5], {%7, %8, %9, %10, %0, %1, %2, %3};\n\t"
+                "@pfl add.u64 %5, %5, 32;\n\t"
                 "}"
-                : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(n), "+l"(ep), "+r"(dcv)
+                : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(n), "+l"(ep), "+r"(dcv), "+r"(h0), "+r"(h1), "+r"(h2), "+r"(h3)
                 : "r"(en), "r"(win), "r"(ln.acc), "r"(nxt), "r"(n_end)
                 : "memory");
             ln.CommitWrite(nxt, rp, n, rp_stop, dcv, has_dc);
@@ -704,14 +713,23 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     }
     // a block still in progress whose DC symbol was ours: the thread that ends it stores only the end index
     if (has_dc && (ln.acc & kAccZMask) != 0 && blk0 < limit && me.end_bit != 0) rp->dc = int16_t(dcv);
-    if (n & 3u) {   // last, partial group: padded with entries for position 0, which K2 overwrites with the DC anyway
-        for (; n & 3u; n++) { q0 = q1; q1 = q2; q2 = q3; q3 = kPadEntry; }
-        if (n <= n_end) *reinterpret_cast<uint4*>(ep) = make_uint4(q0, q1, q2, q3);
-        ep += 4;
+    if (n & 7u) {   // last, partial group: padded with entries for position 0, which K2 overwrites with the DC anyway
+        for (; n & 7u; n++) {
+            q0 = q1; q1 = q2; q2 = q3; q3 = kPadEntry;
+            if ((n & 7u) == 3u) { h0 = q0; h1 = q1; h2 = q2; h3 = q3; }   // this entry completed the first half
+        }
+        if (n <= n_end) {
+            reinterpret_cast<uint4*>(ep)[0] = make_uint4(h0, h1, h2, h3);
+            reinterpret_cast<uint4*>(ep)[1] = make_uint4(q0, q1, q2, q3);
+        }
+        ep += 8;
     }
     // groups the counting pass reserved but this pass did not fill (symbols it saw in the padding
     // after a restart interval's last block): pad them, the next block's range starts behind them
-    for (; n < n_end; n += 4, ep += 4) *reinterpret_cast<uint4*>(ep) = make_uint4(kPadEntry, kPadEntry, kPadEntry, kPadEntry);
+    for (; n < n_end; n += 8, ep += 8) {
+        reinterpret_cast<uint4*>(ep)[0] = make_uint4(kPadEntry, kPadEntry, kPadEntry, kPadEntry);
+        reinterpret_cast<uint4*>(ep)[1] = make_uint4(kPadEntry, kPadEntry, kPadEntry, kPadEntry);
+    }
 }
 
 // ---------------------------------------------------------------- DC prediction

@@ -108,7 +108,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         int c = StateC(key), z = StateZ(key);
         HostLoader ld{clean + subs[g].start};
         DecodeSpan<false>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, nb, nnz, blk, 0xFFFFFFFFu, nsink);
-        *nnz_out = (nnz + 3u) & ~3u;   // runs are padded to whole 16-byte stores
+        *nnz_out = (nnz + 7u) & ~7u;   // runs are padded to whole 32-byte stores
         uint32_t over = pb > subs[g].end_bit ? pb - subs[g].end_bit : 0;
         return PackState(over, c, z, nb > 0xFFFFu ? 0xFFFFu : nb);
     };
@@ -186,7 +186,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     const uint32_t nblocks = total_mcus * uint32_t(bpm);
     // the entry arena is NOT cleared on the device: start from garbage; per-block indices start
     // as "never decoded"
-    const uint32_t cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 3 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
+    const uint32_t cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 7 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
     std::vector<uint32_t> entries(cap, 0x77777777u), blk_end(size_t(nblocks), 0xFFFFFFFFu);
     std::vector<int16_t> dcdiff(nblocks, int16_t(0x7777));
     uint32_t ent_run = 0;
@@ -212,7 +212,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
             HostLoader ld{clean + subs[g].start};
             DecodeSpan<true>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, cnt, nnz, blk, limit, sink);
             // counting pass and write pass must agree (the last thread of an interval may have counted padding)
-            const uint32_t used_n = (sink.n - n0 + 3u) & ~3u;
+            const uint32_t used_n = (sink.n - n0 + 7u) & ~7u;
             if (subs[g].last ? used_n > nnzv[g] : used_n != nnzv[g]) return -7;
             // zero padding: the tail of the last group and the groups the counting pass reserved in vain
             for (uint32_t k2 = sink.n; k2 < n0 + nnzv[g] && k2 < cap; k2++) entries[k2] = kPadEntry;
