@@ -204,6 +204,10 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
     // row/column split and the quantiser load
     __shared__ uint32_t s_tab[kTilesPerCta][64];
     __shared__ uint32_t s_tile0[kSearchCache];
+    __shared__ uint32_t s_first[kTilesPerCta][kBlocksPerTile];   // first entry of every block of every tile
+    __shared__ uint16_t s_count[kTilesPerCta][kBlocksPerTile];   // its number of entries
+    __shared__ int16_t s_dc[kTilesPerCta][kBlocksPerTile];       // its integrated DC
+    static_assert(kTilesPerCta * kBlocksPerTile == kThreads, "one record fetch per thread");
     const int tid = threadIdx.x;
     const bool cached = a.nimages <= kSearchCache;
     if (cached) {
@@ -223,6 +227,29 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
     __syncthreads();
     const int b = tid >> 3, j = tid & 7;
     int* my = ws + b * kBS;
+    // Records of ALL the CTA's tiles first: every thread fetches the record pair of one (tile, block) -
+    // eight tiles x 32 blocks = 256 - so the tile loop below starts from shared memory instead of
+    // waiting for a dependent global load at the top of every tile (profiles/r01g_*).
+    {
+        const int t = tid >> 5, bb = tid & 31;
+        const TileInfo& ti = s_tile[t];
+        uint32_t e0 = 0, n = 0;
+        int dc = 0;
+        if (ti.nbx >= 0 && ti.direct != 2 && ti.bx0 + bb < ti.nbx) {
+            const int bx = ti.bx0 + bb;
+            const size_t blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
+            const uint2 r = __ldg(reinterpret_cast<const uint2*>(ti.rec + blk));
+            e0 = blk ? __ldg(&ti.rec[blk - 1].end) : 0u;
+            uint32_t e1 = r.x;
+            dc = int(int16_t(r.y & 0xFFFFu));
+            if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > ti.ent_cap) e1 = e0 = 0;   // never decoded
+            n = e1 - e0;
+        }
+        s_first[t][bb] = e0;
+        s_count[t][bb] = uint16_t(n);
+        s_dc[t][bb] = int16_t(dc);
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int it = 0; it < kTilesPerCta; it++) {
         const TileInfo& ti = s_tile[it];
@@ -231,20 +258,13 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
         const int bx = ti.bx0 + b;
         const bool valid = bx < ti.nbx;
         // expand the block's sparse entries into the zeroed workspace, dequantising on the way
-        const uint32_t* ep = ti.entries;
-        uint32_t n = 0;
-        int dc = 0;
+        const uint32_t* ep = ti.entries + s_first[it][b] + uint32_t(j);
+        const uint32_t n = s_count[it][b];
+        const int dc = s_dc[it][b];
         if (valid) {
-            const size_t blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
             int4* row = reinterpret_cast<int4*>(my + j * kRS);
             row[0] = make_int4(0, 0, 0, 0);
             row[1] = make_int4(0, 0, 0, 0);
-            const uint2 r = __ldg(reinterpret_cast<const uint2*>(ti.rec + blk));
-            uint32_t e0 = blk ? __ldg(&ti.rec[blk - 1].end) : 0u, e1 = r.x;
-            dc = int(int16_t(r.y & 0xFFFFu));
-            if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > ti.ent_cap) e1 = e0 = 0;   // never decoded
-            ep += e0 + uint32_t(j);
-            n = e1 - e0;
         }
         __syncwarp();
         const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(&s_tab[it][0]));
