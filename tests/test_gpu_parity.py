@@ -166,6 +166,43 @@ def test_crop_with_restart_markers_skips_entropy_work(dec, orc, css):
     assert cropped < dec.stats().subsequences
 
 
+@pytest.mark.parametrize("css", ["444", "422", "420", "400"])
+def test_encoder_optimised_huffman_tables(dec, orc, css):
+    """Per-picture optimised DHTs (libjpeg optimize_coding): different code lengths in every table, other
+    second-level sub-tables than the standard ones; a batch mixes them with standard-table pictures."""
+    import io
+
+    import torch
+    from PIL import Image
+
+    img = datagen.synth_image(321, 243, seed=31)
+    im = Image.fromarray(img if css != "400" else img[..., 1])
+    kw = dict(format="JPEG", quality=85, optimize=True)
+    if css != "400":
+        kw["subsampling"] = {"444": 0, "422": 1, "420": 2}[css]
+    bio = io.BytesIO()
+    im.save(bio, **kw)
+    opt = bio.getvalue()
+    std = datagen.make_jpeg(200, 120, "420" if css == "400" else css, seed=32)
+    st, got, want = gu.decode_one(dec, orc, opt, "rgb")
+    assert st == api.SUCCESS
+    gu.assert_same(got, want, f"optimised tables {css}")
+    # same tables object reused / replaced inside one batch
+    datas = [opt, std, opt, std]
+    streams, dests, keep = [], [], []
+    for d in datas:
+        s = api.JpegStream()
+        assert s.parse(d) == api.SUCCESS
+        rc, info = orc.parse(d)
+        dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "yuv_planar", (0, 0, 0, 0))
+        streams.append(s); dests.append(dest); keep.append((bufs, pitches, shapes))
+    assert dec.decode_batched(streams, api.make_params("yuv_planar"), dests) == api.SUCCESS
+    for k, d in enumerate(datas):
+        bufs, pitches, shapes = keep[k]
+        _, want = gu.oracle_outputs(orc, d, "yuv_planar", (0, 0, 0, 0), pitches)
+        gu.assert_same(gu.fetch(bufs, pitches, shapes), want, f"mixed tables batch {css} #{k}")
+
+
 def test_damaged_scans_do_not_break_the_decoder(dec, orc):
     """Random byte damage inside the entropy-coded data (and truncation): whatever comes out, the call
     must return, the device must stay healthy and the next clean decode must be bit-exact."""
