@@ -166,6 +166,32 @@ def test_crop_with_restart_markers_skips_entropy_work(dec, orc, css):
     assert cropped < dec.stats().subsequences
 
 
+@pytest.mark.parametrize("css", ["444", "440", "422", "420", "400"])
+def test_tiny_and_ragged_pictures(dec, orc, css):
+    """Pictures smaller than one MCU, one sample wide or high, and sizes one off a block / MCU multiple: the
+    partial MCUs, the floor-shifted chroma sizes and the exact-bounds stores at their extremes."""
+    for (w, h) in ((1, 1), (2, 3), (7, 5), (8, 8), (9, 8), (16, 17), (31, 33), (65, 15), (129, 1), (1, 129)):
+        data = datagen.make_jpeg(w, h, css, seed=40 + w + h)
+        for fmt in FORMATS:
+            st, got, want = gu.decode_one(dec, orc, data, fmt, pitch_pad=3, misalign=1)
+            assert st == api.SUCCESS, (w, h, css, fmt, st)
+            # a chroma plane of a one-row / one-column picture can have no samples at all (floor shift)
+            pairs = [(g, x) for g, x in zip(got, want) if x is not None and g.size]
+            gu.assert_same([g for g, _ in pairs], [x for _, x in pairs], f"{w}x{h} {css} {fmt}")
+
+
+@pytest.mark.parametrize("dims", [(20000, 24), (24, 20000), (65500, 8)])
+def test_extreme_aspect_ratios(dec, orc, dims):
+    """One MCU row of thousands of MCUs, and thousands of rows of one MCU (tile / CTA index arithmetic
+    at its extremes; 65500 is close to the 16-bit limit of a JPEG dimension)."""
+    w, h = dims
+    data = datagen.make_jpeg(w, h, "420", seed=77)
+    for fmt in ("rgb", "yuv_planar"):
+        st, got, want = gu.decode_one(dec, orc, data, fmt)
+        assert st == api.SUCCESS
+        gu.assert_same(got, want, f"{w}x{h} {fmt}")
+
+
 @pytest.mark.parametrize("css", ["444", "422", "420", "400"])
 def test_encoder_optimised_huffman_tables(dec, orc, css):
     """Per-picture optimised DHTs (libjpeg optimize_coding): different code lengths in every table, other
