@@ -523,6 +523,14 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     k1_.lut_smem_bytes = max_pairs * 2u * uint32_t(kFastSize) * 4u + max_sub * 4u;
     k1_.total_dc_tiles = dctile;
     k1_.sub_bytes = S;
+    {
+        uint32_t most = 0;
+        for (int i = 0; i < n; i++) most = std::max(most, h_img_cta0_[size_t(i) + 1] - h_img_cta0_[size_t(i)]);
+        k1_.inline_scan = (most <= 32u && EnvInt("ROCJPEG_B200_NO_INLINE_SCAN", 0) == 0) ? 1 : 0;
+        uint32_t most_mcus = 0;
+        for (int i = 0; i < n; i++) most_mcus = std::max(most_mcus, uint32_t(h_images_[size_t(i)].total_mcus));
+        k1_.dc_image = (most_mcus <= uint32_t(kDcImageMaxMcus) && EnvInt("ROCJPEG_B200_NO_DC_IMAGE", 0) == 0) ? 1 : 0;
+    }
     k2_ = K2Args{};
     k2_.nimages = n;
     k2_.total_tiles = k2tile;
@@ -674,7 +682,7 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(mark(6));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + 2 + 3 + 1 + 1 + 2;   // sync rounds, scan + write, 3 DC kernels, IDCT, output, + the two memsets
+    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + 1 + 1 + 2;   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, output, + the two memsets
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256;
     return kSuccess;

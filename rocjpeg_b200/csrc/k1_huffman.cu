@@ -611,10 +611,35 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     if (lane == 31) { wsum[warp] = v; wflag[warp] = f; wents[warp] = e; }
     // what enters this CTA from the previous CTAs of the image: k1_scan prepared it (a look-back here
     // would re-read every earlier partial of the image, quadratic for the 8192x8192 pictures)
-    if (tid == 0) {
-        const uint2 cin = a.cta_carry[cta];
-        carry_s[0] = cin.x;
-        carry_s[1] = cin.y;
+    if (!a.inline_scan) {
+        if (tid == 0) {
+            const uint2 cin = a.cta_carry[cta];
+            carry_s[0] = cin.x;
+            carry_s[1] = cin.y;
+        }
+    } else if (warp == 0) {
+        // at most 32 CTAs per image: one lane per earlier CTA of the image. Entries: plain sum. Blocks: the
+        // partials from the last CTA holding a restart-interval start on (its partial counts only the
+        // blocks after that start).
+        const uint32_t k = __ldg(a.img_cta0 + img) + uint32_t(lane);
+        uint2 part = make_uint2(0u, 0u);
+        uint32_t ents = 0;
+        if (k < cta) {
+            part = a.cta_partial[k];
+            ents = a.cta_entries[k];
+        }
+        const uint32_t starts = __ballot_sync(0xFFFFFFFFu, part.x != 0);
+        const int from = starts ? 31 - __clz(starts) : 0;
+        uint32_t cb = lane >= from ? part.y : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            cb += __shfl_xor_sync(0xFFFFFFFFu, cb, d);
+            ents += __shfl_xor_sync(0xFFFFFFFFu, ents, d);
+        }
+        if (lane == 0) {
+            carry_s[0] = cb;
+            carry_s[1] = ents;
+        }
     }
     __syncthreads();
     uint32_t add = 0, eadd = carry_s[1];
@@ -898,6 +923,72 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
     }
 }
 
+// Pictures of a few thousand MCUs (the 500x375 batches): the three launches above are three
+// latencies in a row for a few microseconds of work each. One CTA per picture does it all: chunks of
+// kDcImageThreads MCUs, a segmented scan per chunk, the chunk's last predictors carried to the next.
+constexpr int kDcImageThreads = 1024;
+
+__global__ void __launch_bounds__(kDcImageThreads) dc_image(K1Args a) {
+    PdlEntry();
+    __shared__ int wsum[kDcImageThreads / 32][3];
+    __shared__ int wflag[kDcImageThreads / 32];
+    __shared__ int carry_s[2][3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ImageDesc& im = a.images[blockIdx.x];
+    const int ri = im.restart_interval, bpm = im.bpm;
+    const int64_t total = int64_t(im.total_mcus);
+    if (tid < 3) carry_s[0][tid] = 0;
+    int it = 0;
+    for (int64_t base = 0; base < total; base += kDcImageThreads, it ^= 1) {
+        const int64_t m = base + tid;
+        const bool active = m < total;
+        const bool reset_here = active && (ri > 0 ? (m % ri) == 0 : m == 0);
+        int diffs[kMaxBlocksPerMcu];
+        int s[3] = {0, 0, 0};
+        BlockRec* rec = a.blk_rec + im.blk0 + m * bpm;
+        if (active) {
+            for (int k = 0; k < bpm; k++) {
+                diffs[k] = RecDc(rec[k]);
+                s[im.mcu_comp[k]] += diffs[k];
+            }
+        }
+        int v0 = s[0], v1 = s[1], v2 = s[2];
+        uint32_t f = reset_here ? 1u : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int p0 = __shfl_up_sync(0xFFFFFFFFu, v0, d);
+            const int p1 = __shfl_up_sync(0xFFFFFFFFu, v1, d);
+            const int p2 = __shfl_up_sync(0xFFFFFFFFu, v2, d);
+            const uint32_t pf = __shfl_up_sync(0xFFFFFFFFu, f, d);
+            if (lane >= d) {
+                if (!f) { v0 += p0; v1 += p1; v2 += p2; }
+                f |= pf;
+            }
+        }
+        __syncthreads();   // the previous chunk's readers are done
+        if (lane == 31) { wsum[warp][0] = v0; wsum[warp][1] = v1; wsum[warp][2] = v2; wflag[warp] = int(f); }
+        __syncthreads();
+        bool open = (f == 0);
+        int a0 = 0, a1 = 0, a2 = 0;
+        for (int w = warp - 1; w >= 0 && open; w--) {
+            a0 += wsum[w][0]; a1 += wsum[w][1]; a2 += wsum[w][2];
+            if (wflag[w]) open = false;
+        }
+        if (open) { a0 += carry_s[it][0]; a1 += carry_s[it][1]; a2 += carry_s[it][2]; }
+        // inclusive values = predictors after this MCU; the chunk's last thread hands them to the next chunk
+        if (tid == kDcImageThreads - 1) { carry_s[it ^ 1][0] = v0 + a0; carry_s[it ^ 1][1] = v1 + a1; carry_s[it ^ 1][2] = v2 + a2; }
+        if (active) {
+            int pred[3] = {v0 + a0 - s[0], v1 + a1 - s[1], v2 + a2 - s[2]};
+            if (reset_here) pred[0] = pred[1] = pred[2] = 0;
+            for (int k = 0; k < bpm; k++) {
+                const int comp = im.mcu_comp[k];
+                pred[comp] += diffs[k];
+                rec[k].dc = int16_t(pred[comp]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- gather
 
 constexpr int kGatherChunk = 16384;
@@ -951,7 +1042,7 @@ cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream, int ma
 
 cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream) {
     if (a.total_ctas == 0) return cudaSuccess;
-    {
+    if (!a.inline_scan) {
         const cudaError_t e = LaunchPdl(k1_scan, dim3(a.nimages), dim3(kScanThreads), 0, stream, a);
         if (e != cudaSuccess) return e;
     }
@@ -965,6 +1056,7 @@ cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream) {
 
 cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream) {
     if (a.total_dc_tiles == 0) return cudaSuccess;
+    if (a.dc_image) return LaunchPdl(dc_image, dim3(a.nimages), dim3(kDcImageThreads), 0, stream, a);
     cudaError_t e = LaunchPdl(dc_sums, dim3(a.total_dc_tiles), dim3(kDcTileMcus), 0, stream, a);
     if (e == cudaSuccess) e = LaunchPdl(dc_scan, dim3(a.nimages), dim3(kScanThreads), 0, stream, a);
     if (e == cudaSuccess) e = LaunchPdl(dc_apply, dim3(a.total_dc_tiles), dim3(kDcTileMcus), 0, stream, a);
@@ -991,6 +1083,7 @@ cudaError_t PreloadK1() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_sums);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_scan);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_apply);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_image);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, gather_scans);
     return e;
 }

@@ -99,7 +99,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     }
     const uint32_t nsub = uint32_t(subs.size());
     // T = subsequences a CTA owns; its kK1Halo leading threads re-decode the subsequences before them
-    const uint32_t H = 2;
+    const uint32_t H = 4;   // kK1Halo (stages.h)
     const uint32_t nctas = (nsub + T - 1) / T;
     std::vector<uint32_t> state(nsub, 0), used(nsub, 0), nnzv(nsub, 0);
     NullSink nsink;

@@ -125,6 +125,26 @@ def test_every_subsequence_size(dec, orc, S, monkeypatch):
         gu.assert_same(got, want, f"{name} S={S}")
 
 
+@pytest.mark.parametrize("knobs", [{}, {"ROCJPEG_B200_NO_INLINE_SCAN": "1"}, {"ROCJPEG_B200_NO_DC_IMAGE": "1"},
+                                   {"ROCJPEG_B200_NO_INLINE_SCAN": "1", "ROCJPEG_B200_NO_DC_IMAGE": "1"}])
+def test_small_and_large_picture_scan_paths_agree(dec, orc, knobs, monkeypatch):
+    """Batches of small pictures fold the CTA-offset scan into the write pass and integrate the DC
+    differences in one launch per picture; large pictures (and the knobs here) take the separate scan
+    kernels. Both must be exact, with and without restart intervals, and a picture above the one-launch
+    limits (2048x1536 4:4:4: 49 152 MCUs, > 32 K1 CTAs) must leave the small-picture paths by itself."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    for name in ("synth_420_500x375_dri7", "synth_444_500x375", "synth_422_500x375", "synth_400_333x211", "mug_422_crop_dri1"):
+        st, got, want = gu.decode_one(dec, orc, load(name), "yuv_planar")
+        assert st == api.SUCCESS
+        gu.assert_same(got, want, f"{name} {knobs}")
+    for rows in (0, 3):
+        data = datagen.make_jpeg(2048, 1536, "444", seed=77, restart_rows=rows)
+        st, got, want = gu.decode_one(dec, orc, data, "yuv_planar")
+        assert st == api.SUCCESS
+        gu.assert_same(got, want, f"large dri_rows={rows} {knobs}")
+
+
 @pytest.mark.parametrize("cap", ["0", "64"])
 def test_long_codes_through_the_canonical_search(dec, orc, cap, monkeypatch):
     """ROCJPEG_B200_SUBCAP shrinks the second-level table arena: long codes then take the canonical
