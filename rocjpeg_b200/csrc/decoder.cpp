@@ -347,6 +347,13 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     int S = EnvInt("ROCJPEG_B200_SUBSEQ", 0);
     if (S != 32 && S != 64 && S != 128) S = (total_clean >= (256u << 10)) ? 128 : (total_clean >= (48u << 10)) ? 64 : 32;
     stats_.sub_bytes = S;
+    // Halo: subsequences before a CTA's own that it re-decodes so that the state entering its first own
+    // one is already synchronised. Small pictures (one wave of CTAs, the kernel as slow as its slowest CTA):
+    // four, so that the verifying round has next to nothing to repair; large ones (many waves, throughput
+    // bound): two, every halo thread is 0.8 % more CTAs.
+    int halo = EnvInt("ROCJPEG_B200_HALO", 0);
+    if (halo < 1 || halo > 16) halo = (n > 0 && total_clean / uint64_t(n) >= (512u << 10)) ? 2 : 4;
+    const uint32_t owned = uint32_t(kK1Threads - halo);
 
     any_direct_ = false;
     needs_planes_ = false;
@@ -444,8 +451,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             sub += (sd.nbytes + uint32_t(S) - 1) / uint32_t(S);
         }
         im.nsub = sub - im.sub0;
-        sub = uint32_t(AlignUp(sub, kK1Owned));
-        h_img_cta0_[size_t(i)] = im.sub0 / kK1Owned;
+        sub = uint32_t(AlignUp(sub, owned));
+        h_img_cta0_[size_t(i)] = im.sub0 / owned;
         h_gather_[size_t(i)] = GatherItem{streams[i]->clean().data(), scan_off, uint32_t(p.clean_bytes), chunk};
         chunk += uint32_t((p.clean_bytes + 16383) / 16384);
         all_pinned_ = all_pinned_ && streams[i]->clean().pinned();
@@ -503,7 +510,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         k3tile += od.tiles_x * od.tiles_y;
         stats_.output_bytes += OutputBytes(p.css, od.fmt, od.w, od.h);
     }
-    h_img_cta0_[size_t(n)] = sub / kK1Owned;
+    h_img_cta0_[size_t(n)] = sub / owned;
     h_img_dctile0_[size_t(n)] = dctile;
     h_k2_tile0_[size_t(n)] = k2tile;
     h_k3_tile0_[size_t(n)] = k3tile;
@@ -519,7 +526,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
 
     k1_ = K1Args{};
     k1_.nimages = n;
-    k1_.total_ctas = sub / kK1Owned;
+    k1_.total_ctas = sub / owned;
+    k1_.halo = halo;
     k1_.lut_smem_bytes = max_pairs * 2u * uint32_t(kFastSize) * 4u + max_sub * 4u;
     k1_.total_dc_tiles = dctile;
     k1_.sub_bytes = S;

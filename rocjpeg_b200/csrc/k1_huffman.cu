@@ -9,8 +9,8 @@
 //   segment      = one restart interval (or the whole scan when DRI is absent):
 //                  byte-aligned start, known decoder state, known first block.
 //   subsequence  = S consecutive bytes of a segment (S = 32/64/128), one thread.
-//   CTA          = kK1Threads threads on ONE image: kK1Owned consecutive subsequences
-//                  it owns + the kK1Halo before them (re-decoded, never stored); the
+//   CTA          = kK1Threads threads on ONE image: kK1Threads - halo consecutive subsequences
+//                  it owns + the halo (2 or 4) before them (re-decoded, never stored); the
 //                  image's Huffman tables and the CTA's bytes are staged in shared memory.
 //
 // Schedule (self-synchronising parallel Huffman decoding)
@@ -50,8 +50,6 @@ namespace rjb {
 namespace {
 
 constexpr int T = kK1Threads;
-constexpr int H = kK1Halo;
-constexpr int TO = kK1Owned;
 constexpr uint32_t kNoState = 0xFFFFFFFFu;
 
 // largest i in [0, n) with a[i] <= v (a is non-decreasing, a[0] <= v)
@@ -389,6 +387,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters)
     const uint32_t cta = blockIdx.x;
     const uint32_t img = ImageOfCta<T * K1Smem<S>::kSlotStride>(a, sm.words, cta);
     const ImageDesc& im = a.images[img];
+    const int H = a.halo, TO = T - H;
     const int64_t gi = int64_t(cta) * TO + tid - H;
     const uint32_t g = uint32_t(gi);
     const bool owned = tid >= H;
@@ -578,6 +577,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const uint32_t cta = blockIdx.x;
     const uint32_t img = ImageOfCta<T * K1Smem<S>::kSlotStride>(a, sm.words, cta);
     const ImageDesc& im = a.images[img];
+    const int H = a.halo, TO = T - H;
     const int64_t gi = int64_t(cta) * TO + tid - H;
     const uint32_t g = uint32_t(gi);
     Sub me = Locate<S>(a, im, gi, true);

@@ -51,8 +51,8 @@ inline cudaError_t LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 
 constexpr int kK1Threads = 128;      // threads per CTA in K1, one subsequence each
 constexpr int kDcImageMaxMcus = 4096;   // pictures up to this many MCUs take the one-launch DC integration
-constexpr int kK1Halo = 4;           // leading threads that re-decode the previous CTA's last subsequences
-constexpr int kK1Owned = kK1Threads - kK1Halo;   // subsequences a K1 CTA owns
+// K1Args::halo leading threads of a CTA re-decode the previous CTA's last subsequences; the CTA owns the
+// kK1Threads - halo subsequences behind them (chosen per batch, decoder.cpp)
 constexpr int kDcTileMcus = 256;     // MCUs per DC-scan tile
 constexpr int kMaxSyncRounds = 8;    // counters kept per batch
 constexpr int kK3TileW = 256;        // output tile of the colour/layout stage, in luma samples
@@ -93,6 +93,7 @@ struct K1Args {
     uint32_t total_dc_tiles;
     int sub_bytes;                // subsequence size S in bytes: 32, 64 or 128
     uint32_t lut_smem_bytes;      // shared memory for the Huffman tables: 4 KiB per table pair + the second-level arena (batch maximum)
+    int halo;                     // threads of a CTA that re-decode the subsequences before the CTA's own
     int inline_scan;              // no image has more than 32 K1 CTAs: k1_write sums the partials of the image's earlier CTAs
                                   // itself (one warp, one load each) and k1_scan is not launched
     int dc_image;                 // no image has more than kDcImageMaxMcus MCUs: one CTA per image integrates its DC

@@ -98,8 +98,8 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         }
     }
     const uint32_t nsub = uint32_t(subs.size());
-    // T = subsequences a CTA owns; its kK1Halo leading threads re-decode the subsequences before them
-    const uint32_t H = 4;   // kK1Halo (stages.h)
+    // T = subsequences a CTA owns; its halo threads (K1Args::halo, 2 or 4) re-decode the subsequences before them
+    const uint32_t H = 4;
     const uint32_t nctas = (nsub + T - 1) / T;
     std::vector<uint32_t> state(nsub, 0), used(nsub, 0), nnzv(nsub, 0);
     NullSink nsink;

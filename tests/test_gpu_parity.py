@@ -125,6 +125,19 @@ def test_every_subsequence_size(dec, orc, S, monkeypatch):
         gu.assert_same(got, want, f"{name} S={S}")
 
 
+@pytest.mark.parametrize("halo", [1, 2, 4, 9])
+def test_every_halo_width(dec, orc, halo, monkeypatch):
+    """The number of subsequences a K1 CTA re-decodes ahead of its own is a per-batch choice (2 for large
+    pictures, 4 for small ones); any width must give the same coefficients - a short halo only means more
+    repairs in the verifying round."""
+    monkeypatch.setenv("ROCJPEG_B200_HALO", str(halo))
+    monkeypatch.setenv("ROCJPEG_B200_SUBSEQ", "32")   # many CTAs per picture
+    for name in ("synth_420_500x375_dri7", "synth_444_500x375", "mug_420_crop", "extreme_coefs_444"):
+        st, got, want = gu.decode_one(dec, orc, load(name), "rgb")
+        assert st == api.SUCCESS
+        gu.assert_same(got, want, f"{name} halo={halo}")
+
+
 @pytest.mark.parametrize("knobs", [{}, {"ROCJPEG_B200_NO_INLINE_SCAN": "1"}, {"ROCJPEG_B200_NO_DC_IMAGE": "1"},
                                    {"ROCJPEG_B200_NO_INLINE_SCAN": "1", "ROCJPEG_B200_NO_DC_IMAGE": "1"}])
 def test_small_and_large_picture_scan_paths_agree(dec, orc, knobs, monkeypatch):
