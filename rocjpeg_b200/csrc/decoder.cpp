@@ -528,6 +528,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     k1_.nimages = n;
     k1_.total_ctas = sub / owned;
     k1_.halo = halo;
+    k1_.rec_fill_vecs = uint32_t((blk * sizeof(BlockRec) + 15) / 16);   // the slab leaves 256 bytes behind every array
     k1_.lut_smem_bytes = max_pairs * 2u * uint32_t(kFastSize) * 4u + max_sub * 4u;
     k1_.total_dc_tiles = dctile;
     k1_.sub_bytes = S;
@@ -676,7 +677,9 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(mark(1));
     // Per-block records start as "never decoded" (8 bytes per block; the entry arena itself is
     // never cleared): blocks a damaged stream does not reach then decode as zero.
-    RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
+    // (round 0 of k1_sync writes the fill, spread over its CTAs - one launch less on the critical path;
+    // a batch without any subsequence to decode has no round 0)
+    if (k1_.total_ctas == 0) RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
     RJB_CUDA(cudaMemsetAsync(k1_.counters, 0, 256, stream_));
     RJB_CUDA(mark(2));
     for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
@@ -690,7 +693,7 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(mark(6));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + 1 + 1 + 2;   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, output, + the two memsets
+    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + 1 + 1 + 1;   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, output, + the counter memset
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256;
     return kSuccess;

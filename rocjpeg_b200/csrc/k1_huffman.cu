@@ -394,6 +394,14 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters)
     Sub me = Locate<S>(a, im, gi, round > 0);
     if (round > 0 && !owned) me.active = false;   // later rounds read the owner's state instead of a halo
     if (round == 0 && owned && me.active) a.sub_seg[g] = me.seg;
+    if (round == 0) {
+        // this CTA's share of the batch's block records starts as "never decoded": blocks a damaged stream
+        // does not reach, or a region of interest leaves out, then decode as zero
+        const uint32_t per = (a.rec_fill_vecs + gridDim.x - 1) / gridDim.x;
+        const uint32_t v0 = min(cta * per, a.rec_fill_vecs), v1 = min(v0 + per, a.rec_fill_vecs);
+        uint4* dst = reinterpret_cast<uint4*>(a.blk_rec);
+        for (uint32_t v = v0 + uint32_t(tid); v < v1; v += T) dst[v] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
 
     uint32_t my_used = 0, out = 0, old_out = kNoState;
     if (round > 0) {

@@ -93,6 +93,7 @@ struct K1Args {
     uint32_t total_dc_tiles;
     int sub_bytes;                // subsequence size S in bytes: 32, 64 or 128
     uint32_t lut_smem_bytes;      // shared memory for the Huffman tables: 4 KiB per table pair + the second-level arena (batch maximum)
+    uint32_t rec_fill_vecs;       // 16-byte vectors of blk_rec that round 0 of k1_sync fills with 0xFF ("never decoded")
     int halo;                     // threads of a CTA that re-decode the subsequences before the CTA's own
     int inline_scan;              // no image has more than 32 K1 CTAs: k1_write sums the partials of the image's earlier CTAs
                                   // itself (one warp, one load each) and k1_scan is not launched
