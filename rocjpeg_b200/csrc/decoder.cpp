@@ -166,6 +166,8 @@ int Lane::Create(int /*device_id*/, int sm_count) {
     // 384, two thirds of it arena, one third planes, split over the lanes; 0 = allocate on demand)
     if (!h_desc_.Reserve(1u << 20) || !h_counters_.Reserve(256)) return Fail(kOutOfMemory, "page-locked staging");
     const size_t per_lane = size_t(std::max(0, EnvInt("ROCJPEG_B200_PREALLOC_MB", 384))) * (1u << 20) / kMaxLanes;
+    RJB_CUDA(d_counters_.Reserve(512));
+    RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint8_t>(), 0, 512, stream_));
     if (per_lane) {
         RJB_CUDA(d_slab_.Reserve(per_lane * 2 / 3));
         RJB_CUDA(d_planes_.Reserve(per_lane / 3));
@@ -596,7 +598,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
                  o_used = carve(nsub_total_ * 4), o_subseg = carve(nsub_total_ * 4), o_cta_entries = carve(size_t(k1_.total_ctas) * 4),
                  o_cta_partial = carve(size_t(k1_.total_ctas) * 8), o_cta_carry = carve(size_t(k1_.total_ctas) * 8),
                  o_dc_partial = carve(size_t(k1_.total_dc_tiles) * 12), o_dc_carry = carve(size_t(k1_.total_dc_tiles) * 12),
-                 o_counters = carve(256);
+                 o_end = carve(0);
+    (void)o_end;
     RJB_CUDA(d_slab_.Reserve(off));
     if (needs_planes_) RJB_CUDA(d_planes_.Reserve(plane_bytes_ + 512));
     if (!h_counters_.Reserve(256)) return Fail(kOutOfMemory, "counter staging");
@@ -616,7 +619,7 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     k1_.dc_partial = reinterpret_cast<int3*>(base + o_dc_partial);
     k1_.dc_carry = reinterpret_cast<int3*>(base + o_dc_carry);
     k1_.cta_carry = reinterpret_cast<uint2*>(base + o_cta_carry);
-    k1_.counters = reinterpret_cast<uint32_t*>(base + o_counters);
+    // the batch's counter set is picked at launch time (LaunchAll): the sets alternate
     k1_.entries = reinterpret_cast<uint32_t*>(base + o_entries);
     k1_.blk_rec = reinterpret_cast<BlockRec*>(base + o_blkrec);
     k1_.nnz = reinterpret_cast<uint32_t*>(base + o_nnz);
@@ -679,8 +682,15 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     // never cleared): blocks a damaged stream does not reach then decode as zero.
     // (round 0 of k1_sync writes the fill, spread over its CTAs - one launch less on the critical path;
     // a batch without any subsequence to decode has no round 0)
-    if (k1_.total_ctas == 0) RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
-    RJB_CUDA(cudaMemsetAsync(k1_.counters, 0, 256, stream_));
+    // Counters: two sets; this batch's set was zeroed by the previous batch's write pass (or at creation),
+    // its own write pass zeroes the other one - no memset in front of the first kernel.
+    k1_.counters = d_counters_.as<uint32_t>() + 64 * counter_set_;
+    k1_.counters_next = d_counters_.as<uint32_t>() + 64 * (counter_set_ ^ 1);
+    counter_set_ ^= 1;
+    if (k1_.total_ctas == 0) {
+        RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
+        RJB_CUDA(cudaMemsetAsync(k1_.counters_next, 0, 256, stream_));
+    }
     RJB_CUDA(mark(2));
     for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
     stats_.sync_rounds = uint32_t(rounds);
@@ -693,7 +703,7 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(mark(6));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + 1 + 1 + 1;   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, output, + the counter memset
+    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + 1 + 1;   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, output
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256;
     return kSuccess;

@@ -56,7 +56,7 @@ class DeviceBuffer {
 
 enum StageId {
     kStageUpload = 0,   // descriptor block + entropy-coded bytes, host -> device
-    kStageClear,        // block records filled with "never decoded", counters reset
+    kStageClear,        // nothing in the common case (the record fill rides in k1_sync, the counters are zeroed a batch ahead)
     kStageSync,         // all k1_sync rounds
     kStageWrite,        // k1_scan + k1_write
     kStageDc,           // dc_sums + dc_scan + dc_apply
@@ -171,6 +171,8 @@ class Lane {
     StagingBuffer h_counters_;    // pinned read-back
     DeviceBuffer d_slab_;         // descriptors, scan bytes, K1 state, coefficient entries, block records: one allocation
     DeviceBuffer d_planes_;       // component planes, only when some image needs the output stage
+    DeviceBuffer d_counters_;     // two sets of K1 counters: a batch uses one, its write pass zeroes the other for the next
+    int counter_set_ = 0;
     BatchStats stats_;
 };
 

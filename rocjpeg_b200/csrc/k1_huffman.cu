@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const uint32_t g = uint32_t(gi);
     Sub me = Locate<S>(a, im, gi, true);
     if (tid < H) me.active = false;   // halo slots belong to the previous CTA
+    if (cta == 0 && tid < 64) a.counters_next[tid] = 0;   // the next batch's counters (this batch's are read back after K3)
     const LutView lv = StageCta<S>(sm, lut, a, im, me);
 
     const uint32_t st = me.active ? a.state[g] : 0;
