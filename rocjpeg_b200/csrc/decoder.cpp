@@ -347,14 +347,18 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     // 4:2:0 data a wrong start state needs about one MCU to re-synchronise); short ones only pay
     // off when the whole batch is too small to occupy the GPU otherwise.
     int S = EnvInt("ROCJPEG_B200_SUBSEQ", 0);
-    if (S != 32 && S != 64 && S != 128) S = (total_clean >= (256u << 10)) ? 128 : (total_clean >= (48u << 10)) ? 64 : 32;
+    // (measured: a lone 1920x1080 picture, 0.47 MB of scan, decodes 11 % faster with 64-byte subsequences
+    // - every pass of the latency-bound synchronisation is half as long; the 15 MB batch of 256 pictures,
+    // one full wave of CTAs at 128 bytes, is 20 % slower in that stage with 64)
+    if (S != 32 && S != 64 && S != 128) S = (total_clean >= (2u << 20)) ? 128 : (total_clean >= (48u << 10)) ? 64 : 32;
     stats_.sub_bytes = S;
     // Halo: subsequences before a CTA's own that it re-decodes so that the state entering its first own
-    // one is already synchronised. Small pictures (one wave of CTAs, the kernel as slow as its slowest CTA):
-    // four, so that the verifying round has next to nothing to repair; large ones (many waves, throughput
-    // bound): two, every halo thread is 0.8 % more CTAs.
+    // one is already synchronised. Small pictures (at most a wave of CTAs, the kernel as slow as its slowest
+    // CTA): 768 bytes' worth, after which the verifying round has nothing left to repair on the benchmark
+    // batches - a repair costs a staging and a chain of decodes, 15-20 us; large ones (many waves,
+    // throughput bound): two subsequences, every halo thread is 0.8 % more CTAs.
     int halo = EnvInt("ROCJPEG_B200_HALO", 0);
-    if (halo < 1 || halo > 16) halo = (n > 0 && total_clean / uint64_t(n) >= (512u << 10)) ? 2 : 4;
+    if (halo < 1 || halo > 16) halo = (n > 0 && total_clean / uint64_t(n) >= (512u << 10)) ? 2 : std::min(16, 768 / S);
     const uint32_t owned = uint32_t(kK1Threads - halo);
 
     any_direct_ = false;
