@@ -70,7 +70,7 @@ if rep and len(sys.argv) > 4:
     import os
 
     stage_of = {"k1_sync": "huffman_sync", "k1_scan": "huffman_write", "k1_write": "huffman_write", "dc_sums": "dc", "dc_scan": "dc",
-                "dc_apply": "dc", "k2_idct": "idct", "k3_output": "output"}
+                "dc_apply": "dc", "dc_image": "dc", "k2_idct": "idct", "k3_output": "output"}
     ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     per_stage, seen = {}, {}

@@ -399,6 +399,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
                 im.mcu_pair[k] = uint8_t(pair);
             }
             im.qt_index[c] = i * 3 + c;
+            im.comp_bits = 0;
+            for (int b = 0; b < k; b++) im.comp_bits |= uint32_t(im.mcu_comp[b]) << (2 * b);
             if (have) std::memcpy(&h_qtables_[(size_t(i) * 3 + c) * 64], p.qt_natural[p.tq[c]], 128);
         }
         // Huffman table set, de-duplicated across the batch
@@ -544,7 +546,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         k1_.inline_scan = (most <= 32u && EnvInt("ROCJPEG_B200_NO_INLINE_SCAN", 0) == 0) ? 1 : 0;
         uint32_t most_mcus = 0;
         for (int i = 0; i < n; i++) most_mcus = std::max(most_mcus, uint32_t(h_images_[size_t(i)].total_mcus));
-        k1_.dc_image = (most_mcus <= uint32_t(kDcImageMaxMcus) && EnvInt("ROCJPEG_B200_NO_DC_IMAGE", 0) == 0) ? 1 : 0;
+        const int dc_limit = EnvInt("ROCJPEG_B200_DC_IMAGE_MCUS", kDcImageMaxMcus);
+        k1_.dc_image = (most_mcus <= uint32_t(std::max(0, dc_limit)) && EnvInt("ROCJPEG_B200_NO_DC_IMAGE", 0) == 0) ? 1 : 0;
     }
     k2_ = K2Args{};
     k2_.nimages = n;

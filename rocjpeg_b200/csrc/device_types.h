@@ -65,7 +65,7 @@ struct ImageDesc {
     uint32_t ent_cap;                                 // entries reserved for this image (upper bound from the scan size)
     uint32_t nblocks;
     uint32_t dc_tile0;                                // first DC-scan tile of this image
-    uint32_t pad2_;
+    uint32_t comp_bits;                               // mcu_comp packed, two bits per block-in-MCU (the DC kernels unroll over it)
     // decoded component planes (MCU-padded), u8
     uint64_t plane_off[3];
     uint32_t plane_pitch[3];

@@ -772,6 +772,43 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
 // holds the 0xFF fill)
 __device__ __forceinline__ int RecDc(const BlockRec& r) { return r.end == kNoEntry ? 0 : int(r.dc); }
 
+// The DC differences of one MCU in registers (fully unrolled over the ten blocks an MCU can have, 8-byte
+// loads, selects by component instead of indexing: the scalar form kept its arrays in local memory) and
+// their sums per component. (A warp-cooperative variant - the 32 MCUs' records read and written as one
+// coalesced run and transposed through shared memory - was measured 10-15 % slower: these kernels are bound
+// by their instruction count, not by memory transactions.)
+struct McuDc {
+    int d[kMaxBlocksPerMcu];
+    int s0, s1, s2;
+    __device__ __forceinline__ void Load(const BlockRec* rec, int bpm, uint32_t comp_bits, bool active) {
+        s0 = s1 = s2 = 0;
+#pragma unroll
+        for (int k = 0; k < kMaxBlocksPerMcu; k++) {
+            d[k] = 0;
+            if (active && k < bpm) {
+                const uint2 r = *reinterpret_cast<const uint2*>(rec + k);
+                d[k] = r.x == kNoEntry ? 0 : int(int16_t(r.y & 0xFFFFu));   // a block no thread reached counts as 0
+            }
+            const uint32_t comp = (comp_bits >> (2 * k)) & 3u;
+            s0 += comp == 0u ? d[k] : 0;
+            s1 += comp == 1u ? d[k] : 0;
+            s2 += comp == 2u ? d[k] : 0;
+        }
+    }
+    // the integrated DC replaces the difference in every block's record; p0..p2 = predictors entering the MCU
+    __device__ __forceinline__ void Store(BlockRec* rec, int bpm, uint32_t comp_bits, int p0, int p1, int p2) const {
+#pragma unroll
+        for (int k = 0; k < kMaxBlocksPerMcu; k++) {
+            const uint32_t comp = (comp_bits >> (2 * k)) & 3u;
+            p0 += comp == 0u ? d[k] : 0;
+            p1 += comp == 1u ? d[k] : 0;
+            p2 += comp == 2u ? d[k] : 0;
+            if (k < bpm) rec[k].dc = int16_t(comp == 0u ? p0 : comp == 1u ? p1 : p2);
+        }
+    }
+};
+__device__ __forceinline__ bool ResetAt(uint32_t m, int ri) { return ri > 0 ? (m % uint32_t(ri)) == 0u : m == 0u; }
+
 // Does MCU range [m0, m1) of an image contain a predictor reset? Returns the last one, or -1.
 __device__ __forceinline__ int64_t LastReset(int64_t m0, int64_t m1, int ri) {
     if (m1 <= m0) return -1;
@@ -793,11 +830,9 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_sums(K1Args a) {
     const int64_t m = m0 + tid;
     if (tid < 3) red[tid] = 0;
     __syncthreads();
-    int s[3] = {0, 0, 0};
-    if (m < m1 && m >= reset) {
-        const BlockRec* d = a.blk_rec + im.blk0 + m * im.bpm;
-        for (int k = 0; k < im.bpm; k++) s[im.mcu_comp[k]] += RecDc(d[k]);
-    }
+    McuDc mcu;
+    mcu.Load(a.blk_rec + im.blk0 + m * im.bpm, im.bpm, im.comp_bits, m < m1 && m >= reset);
+    const int s[3] = {mcu.s0, mcu.s1, mcu.s2};
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         int v = s[c];
@@ -881,19 +916,13 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
     const int ri = im.restart_interval;
     const int64_t m = m0 + tid;
     const bool active = m < m1;
-    const bool reset_here = active && (ri > 0 ? (m % ri) == 0 : m == 0);
+    const bool reset_here = active && ResetAt(uint32_t(m), ri);
 
-    int diffs[kMaxBlocksPerMcu];
-    int s[3] = {0, 0, 0};
-    if (active) {
-        const BlockRec* d = a.blk_rec + im.blk0 + m * im.bpm;
-        for (int k = 0; k < im.bpm; k++) {
-            diffs[k] = RecDc(d[k]);
-            s[im.mcu_comp[k]] += diffs[k];
-        }
-    }
+    BlockRec* rec = a.blk_rec + im.blk0 + m * im.bpm;
+    McuDc mcu;
+    mcu.Load(rec, im.bpm, im.comp_bits, active);
     // inclusive segmented scan of the per-MCU sums
-    int v0 = s[0], v1 = s[1], v2 = s[2];
+    int v0 = mcu.s0, v1 = mcu.s1, v2 = mcu.s2;
     uint32_t f = reset_here ? 1u : 0u;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -919,49 +948,40 @@ __global__ void __launch_bounds__(kDcTileMcus) dc_apply(K1Args a) {
         if (wflag[w]) open = false;
     }
     if (open) { a0 += carry_s[0]; a1 += carry_s[1]; a2 += carry_s[2]; }
+    // exclusive prefix = predictor values entering this MCU; the absolute DC replaces the difference in the
+    // block's record (K2 reads end index and DC together)
     if (!active) return;
-    // exclusive prefix = predictor values entering this MCU
-    int pred[3] = {v0 + a0 - s[0], v1 + a1 - s[1], v2 + a2 - s[2]};
-    if (reset_here) pred[0] = pred[1] = pred[2] = 0;
-    // absolute DC replaces the difference in the block's record (K2 reads end index and DC together)
-    BlockRec* out = a.blk_rec + im.blk0 + m * im.bpm;
-    for (int k = 0; k < im.bpm; k++) {
-        const int comp = im.mcu_comp[k];
-        pred[comp] += diffs[k];
-        out[k].dc = int16_t(pred[comp]);
-    }
+    mcu.Store(rec, im.bpm, im.comp_bits, reset_here ? 0 : v0 + a0 - mcu.s0, reset_here ? 0 : v1 + a1 - mcu.s1,
+              reset_here ? 0 : v2 + a2 - mcu.s2);
 }
 
 // Pictures of a few thousand MCUs (the 500x375 batches): the three launches above are three
 // latencies in a row for a few microseconds of work each. One CTA per picture does it all: chunks of
 // kDcImageThreads MCUs, a segmented scan per chunk, the chunk's last predictors carried to the next.
-constexpr int kDcImageThreads = 1024;
+constexpr int kDcImageThreads = 512;   // 64 registers per thread (an MCU's ten differences live in registers): two CTAs per SM
 
 __global__ void __launch_bounds__(kDcImageThreads) dc_image(K1Args a) {
     PdlEntry();
-    __shared__ int wsum[kDcImageThreads / 32][3];
-    __shared__ int wflag[kDcImageThreads / 32];
-    __shared__ int carry_s[2][3];
+    constexpr int kWarps = kDcImageThreads / 32;
+    static_assert(kWarps <= 32, "the warp totals are scanned by one warp");
+    __shared__ int wsum[kWarps][3];    // per warp: value of its open segment at the warp's end
+    __shared__ int wflag[kWarps];      // the warp contains a predictor reset
+    __shared__ int wpre[kWarps][3];    // predictors entering the warp (from the chunk's earlier warps and the carry)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ImageDesc& im = a.images[blockIdx.x];
     const int ri = im.restart_interval, bpm = im.bpm;
+    const uint32_t comp_bits = im.comp_bits;
     const int64_t total = int64_t(im.total_mcus);
-    if (tid < 3) carry_s[0][tid] = 0;
-    int it = 0;
-    for (int64_t base = 0; base < total; base += kDcImageThreads, it ^= 1) {
+    int c0 = 0, c1 = 0, c2 = 0;   // warp 0: predictors entering the chunk
+    for (int64_t base = 0; base < total; base += kDcImageThreads) {
         const int64_t m = base + tid;
         const bool active = m < total;
-        const bool reset_here = active && (ri > 0 ? (m % ri) == 0 : m == 0);
-        int diffs[kMaxBlocksPerMcu];
-        int s[3] = {0, 0, 0};
+        const bool reset_here = active && ResetAt(uint32_t(m), ri);
         BlockRec* rec = a.blk_rec + im.blk0 + m * bpm;
-        if (active) {
-            for (int k = 0; k < bpm; k++) {
-                diffs[k] = RecDc(rec[k]);
-                s[im.mcu_comp[k]] += diffs[k];
-            }
-        }
-        int v0 = s[0], v1 = s[1], v2 = s[2];
+        McuDc mcu;
+        mcu.Load(rec, bpm, comp_bits, active);
+        // inclusive segmented scan of the per-MCU sums inside the warp
+        int v0 = mcu.s0, v1 = mcu.s1, v2 = mcu.s2;
         uint32_t f = reset_here ? 1u : 0u;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -977,23 +997,37 @@ __global__ void __launch_bounds__(kDcImageThreads) dc_image(K1Args a) {
         __syncthreads();   // the previous chunk's readers are done
         if (lane == 31) { wsum[warp][0] = v0; wsum[warp][1] = v1; wsum[warp][2] = v2; wflag[warp] = int(f); }
         __syncthreads();
-        bool open = (f == 0);
-        int a0 = 0, a1 = 0, a2 = 0;
-        for (int w = warp - 1; w >= 0 && open; w--) {
-            a0 += wsum[w][0]; a1 += wsum[w][1]; a2 += wsum[w][2];
-            if (wflag[w]) open = false;
-        }
-        if (open) { a0 += carry_s[it][0]; a1 += carry_s[it][1]; a2 += carry_s[it][2]; }
-        // inclusive values = predictors after this MCU; the chunk's last thread hands them to the next chunk
-        if (tid == kDcImageThreads - 1) { carry_s[it ^ 1][0] = v0 + a0; carry_s[it ^ 1][1] = v1 + a1; carry_s[it ^ 1][2] = v2 + a2; }
-        if (active) {
-            int pred[3] = {v0 + a0 - s[0], v1 + a1 - s[1], v2 + a2 - s[2]};
-            if (reset_here) pred[0] = pred[1] = pred[2] = 0;
-            for (int k = 0; k < bpm; k++) {
-                const int comp = im.mcu_comp[k];
-                pred[comp] += diffs[k];
-                rec[k].dc = int16_t(pred[comp]);
+        if (warp == 0) {
+            // the same scan over the 32 warp totals, with the chunk's carry in front
+            int t0 = 0, t1 = 0, t2 = 0;
+            uint32_t tf = 0;
+            if (lane < kWarps) { t0 = wsum[lane][0]; t1 = wsum[lane][1]; t2 = wsum[lane][2]; tf = uint32_t(wflag[lane]); }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int p0 = __shfl_up_sync(0xFFFFFFFFu, t0, d);
+                const int p1 = __shfl_up_sync(0xFFFFFFFFu, t1, d);
+                const int p2 = __shfl_up_sync(0xFFFFFFFFu, t2, d);
+                const uint32_t pf = __shfl_up_sync(0xFFFFFFFFu, tf, d);
+                if (lane >= d) {
+                    if (!tf) { t0 += p0; t1 += p1; t2 += p2; }
+                    tf |= pf;
+                }
             }
+            if (!tf) { t0 += c0; t1 += c1; t2 += c2; }
+            int x0 = __shfl_up_sync(0xFFFFFFFFu, t0, 1), x1 = __shfl_up_sync(0xFFFFFFFFu, t1, 1), x2 = __shfl_up_sync(0xFFFFFFFFu, t2, 1);
+            if (lane == 0) { x0 = c0; x1 = c1; x2 = c2; }
+            if (lane < kWarps) { wpre[lane][0] = x0; wpre[lane][1] = x1; wpre[lane][2] = x2; }
+            c0 = __shfl_sync(0xFFFFFFFFu, t0, 31);
+            c1 = __shfl_sync(0xFFFFFFFFu, t1, 31);
+            c2 = __shfl_sync(0xFFFFFFFFu, t2, 31);
+        }
+        __syncthreads();
+        if (active) {
+            // exclusive prefix = predictor values entering this MCU
+            const bool open = (f == 0);   // no reset at or before this MCU inside its warp
+            const int p0 = v0 - mcu.s0 + (open ? wpre[warp][0] : 0), p1 = v1 - mcu.s1 + (open ? wpre[warp][1] : 0),
+                      p2 = v2 - mcu.s2 + (open ? wpre[warp][2] : 0);
+            mcu.Store(rec, bpm, comp_bits, reset_here ? 0 : p0, reset_here ? 0 : p1, reset_here ? 0 : p2);
         }
     }
 }
