@@ -546,7 +546,9 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         k1_.inline_scan = (most <= 32u && EnvInt("ROCJPEG_B200_NO_INLINE_SCAN", 0) == 0) ? 1 : 0;
         uint32_t most_mcus = 0;
         for (int i = 0; i < n; i++) most_mcus = std::max(most_mcus, uint32_t(h_images_[size_t(i)].total_mcus));
-        const int dc_limit = EnvInt("ROCJPEG_B200_DC_IMAGE_MCUS", kDcImageMaxMcus);
+        // one CTA per picture: a lone picture of 8000 MCUs is faster through the tiled kernels (0.013 against 0.06 ms
+        // for 1920x1080), a lane full of such pictures keeps every SM busy either way and saves two launches
+        const int dc_limit = EnvInt("ROCJPEG_B200_DC_IMAGE_MCUS", n >= 16 ? 2 * kDcImageMaxMcus : kDcImageMaxMcus);
         k1_.dc_image = (most_mcus <= uint32_t(std::max(0, dc_limit)) && EnvInt("ROCJPEG_B200_NO_DC_IMAGE", 0) == 0) ? 1 : 0;
     }
     k2_ = K2Args{};

@@ -780,10 +780,13 @@ __device__ __forceinline__ int RecDc(const BlockRec& r) { return r.end == kNoEnt
 struct McuDc {
     int d[kMaxBlocksPerMcu];
     int s0, s1, s2;
-    __device__ __forceinline__ void Load(const BlockRec* rec, int bpm, uint32_t comp_bits, bool active) {
+    // N = unroll bound >= bpm (these kernels are bound by their instruction count: a grey picture, one block
+    // per MCU, must not pay for ten predicated steps)
+    template <int N>
+    __device__ __forceinline__ void LoadN(const BlockRec* rec, int bpm, uint32_t comp_bits, bool active) {
         s0 = s1 = s2 = 0;
 #pragma unroll
-        for (int k = 0; k < kMaxBlocksPerMcu; k++) {
+        for (int k = 0; k < N; k++) {
             d[k] = 0;
             if (active && k < bpm) {
                 const uint2 r = *reinterpret_cast<const uint2*>(rec + k);
@@ -795,16 +798,30 @@ struct McuDc {
             s2 += comp == 2u ? d[k] : 0;
         }
     }
-    // the integrated DC replaces the difference in every block's record; p0..p2 = predictors entering the MCU
-    __device__ __forceinline__ void Store(BlockRec* rec, int bpm, uint32_t comp_bits, int p0, int p1, int p2) const {
+    template <int N>
+    __device__ __forceinline__ void StoreN(BlockRec* rec, int bpm, uint32_t comp_bits, int p0, int p1, int p2) const {
 #pragma unroll
-        for (int k = 0; k < kMaxBlocksPerMcu; k++) {
+        for (int k = 0; k < N; k++) {
             const uint32_t comp = (comp_bits >> (2 * k)) & 3u;
             p0 += comp == 0u ? d[k] : 0;
             p1 += comp == 1u ? d[k] : 0;
             p2 += comp == 2u ? d[k] : 0;
             if (k < bpm) rec[k].dc = int16_t(comp == 0u ? p0 : comp == 1u ? p1 : p2);
         }
+    }
+    // bpm is uniform over the CTA (one picture): 1 grey, 3 4:4:4, 4 4:2:2 / 4:4:0, 6 4:2:0, up to 10 otherwise
+    __device__ __forceinline__ void Load(const BlockRec* rec, int bpm, uint32_t comp_bits, bool active) {
+        if (bpm == 1) LoadN<1>(rec, bpm, comp_bits, active);
+        else if (bpm <= 4) LoadN<4>(rec, bpm, comp_bits, active);
+        else if (bpm <= 6) LoadN<6>(rec, bpm, comp_bits, active);
+        else LoadN<kMaxBlocksPerMcu>(rec, bpm, comp_bits, active);
+    }
+    // the integrated DC replaces the difference in every block's record; p0..p2 = predictors entering the MCU
+    __device__ __forceinline__ void Store(BlockRec* rec, int bpm, uint32_t comp_bits, int p0, int p1, int p2) const {
+        if (bpm == 1) StoreN<1>(rec, bpm, comp_bits, p0, p1, p2);
+        else if (bpm <= 4) StoreN<4>(rec, bpm, comp_bits, p0, p1, p2);
+        else if (bpm <= 6) StoreN<6>(rec, bpm, comp_bits, p0, p1, p2);
+        else StoreN<kMaxBlocksPerMcu>(rec, bpm, comp_bits, p0, p1, p2);
     }
 };
 __device__ __forceinline__ bool ResetAt(uint32_t m, int ri) { return ri > 0 ? (m % uint32_t(ri)) == 0u : m == 0u; }
