@@ -58,8 +58,8 @@ enum StageId {
     kStageUpload = 0,   // descriptor block + entropy-coded bytes, host -> device
     kStageClear,        // nothing in the common case (the record fill rides in k1_sync, the counters are zeroed a batch ahead)
     kStageSync,         // all k1_sync rounds
-    kStageWrite,        // k1_scan + k1_write
-    kStageDc,           // dc_sums + dc_scan + dc_apply
+    kStageWrite,        // (k1_scan +) k1_write
+    kStageDc,           // dc_image, or dc_sums + dc_scan + dc_apply
     kStageIdct,         // k2_idct
     kStageOutput,       // k3_output
     kStageCount

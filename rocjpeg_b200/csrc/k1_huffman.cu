@@ -14,7 +14,8 @@
 //                  image's Huffman tables and the CTA's bytes are staged in shared memory.
 //
 // Schedule (self-synchronising parallel Huffman decoding)
-//   k1_sync round 0   every thread decodes its subsequence from a guessed state
+//   k1_sync round 0   (also fills the batch's block records with "never decoded")
+//                     every thread decodes its subsequence from a guessed state
 //                     (exact for the first subsequence of a segment) and records
 //                     its end state; then, inside the CTA, every thread whose
 //                     predecessor's end state differs from the state it started
@@ -29,15 +30,19 @@
 //                     last round; a non-zero value triggers more rounds
 //                     (correctness never depends on the stream synchronising).
 //   k1_scan           per image: exclusive prefix of the CTAs' block counts
-//                     (segmented at restart intervals) and entry counts.
+//                     (segmented at restart intervals) and entry counts. Not launched
+//                     when no picture has more than 32 CTAs: the write pass then sums
+//                     the picture's earlier partials itself.
 //   k1_write          the final decode: the image's sparse coefficient stream (one
 //                     32-bit (int16 value, zig-zag index) entry per symbol with
 //                     magnitude bits, eight per 256-bit store) and one 8-byte record
 //                     per block {where its entries end, DC difference}.
-//   dc_sums / dc_scan / dc_apply
-//                     per-component, per-restart-interval prefix sum of the DC
-//                     differences; the integrated DC replaces the difference in the
+//   dc_image          pictures up to a few thousand MCUs: per-component, per-restart-
+//                     interval prefix sum of the DC differences, one CTA per picture,
+//                     one launch; the integrated DC replaces the difference in the
 //                     block's record, where K2 reads it.
+//   dc_sums / dc_scan / dc_apply
+//                     the same for large pictures, tiles of 256 MCUs over all SMs.
 #include <cuda_runtime.h>
 
 #include <cstddef>

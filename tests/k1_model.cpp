@@ -10,6 +10,7 @@
 // CUDA kernels themselves are checked by the -m gpu tests.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -98,8 +99,10 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         }
     }
     const uint32_t nsub = uint32_t(subs.size());
-    // T = subsequences a CTA owns; its halo threads (K1Args::halo, 2 or 4) re-decode the subsequences before them
-    const uint32_t H = 4;
+    // T = subsequences a CTA owns; its halo threads (K1Args::halo: 2 for large pictures, 768 bytes' worth for small
+    // ones; K1_MODEL_HALO overrides) re-decode the subsequences before them
+    uint32_t H = uint32_t(768 / S);
+    if (const char* e = std::getenv("K1_MODEL_HALO")) H = uint32_t(std::atoi(e));
     const uint32_t nctas = (nsub + T - 1) / T;
     std::vector<uint32_t> state(nsub, 0), used(nsub, 0), nnzv(nsub, 0);
     NullSink nsink;

@@ -216,6 +216,22 @@ def test_k1_schedule_model_matches_oracle(k1_model, orc, name):
         assert st.rounds >= 2
 
 
+@pytest.mark.parametrize("halo", ["0", "1", "2", "16"])
+def test_k1_schedule_model_any_halo_width(k1_model, orc, halo, monkeypatch):
+    """The halo only moves work from the verifying rounds into round 0: every width, none included, must end
+    with the oracle's coefficients (the device picks 2 for large pictures, 768 bytes' worth for small ones)."""
+    monkeypatch.setenv("K1_MODEL_HALO", halo)
+    for name in ("synth_420_500x375_dri7", "synth_444_500x375", "mug_420_crop", "extreme_coefs_444"):
+        data = load(name)
+        rc, info = orc.parse(data)
+        want = np.concatenate([c.reshape(-1) for c in orc.coefficients(data, info)])
+        for S, T in [(32, 8), (128, 3)]:
+            out = np.zeros(want.size, dtype=np.int16)
+            st = _ModelStats()
+            assert k1_model.k1_model_decode(data, len(data), S, T, out.ctypes.data, out.size, C.byref(st)) == 0
+            assert np.array_equal(out, want), (name, S, T, halo)
+
+
 # ---------------------------------------------------------------- multi-device plan (host only)
 
 def test_shard_plan_is_lpt_and_balanced():
