@@ -85,6 +85,10 @@ RocJpegStatus rocJpegB200StreamGetInfo(RocJpegStreamHandle jpeg_stream_handle, R
 /* Copy the destuffed bytes of restart interval `segment` (returns its length via *nbytes). */
 RocJpegStatus rocJpegB200StreamGetSegment(RocJpegStreamHandle jpeg_stream_handle, uint32_t segment, uint8_t *out,
                                           size_t capacity, uint32_t *nbytes);
+/* Why the last rocJpegStreamParse on this handle failed (the text the library also prints to stderr, as the
+ * reference does through ERR - src/rocjpeg_commons.h); empty after a successful parse. NUL-terminated, truncated
+ * to `capacity`. */
+RocJpegStatus rocJpegB200StreamGetLastError(RocJpegStreamHandle jpeg_stream_handle, char *out, size_t capacity);
 /* Tables as the decoder sees them: quantiser steps in natural order; Huffman BITS/HUFFVAL. */
 RocJpegStatus rocJpegB200StreamGetQuantTable(RocJpegStreamHandle jpeg_stream_handle, int id, uint16_t out_natural[64]);
 RocJpegStatus rocJpegB200StreamGetHuffmanTable(RocJpegStreamHandle jpeg_stream_handle, int is_ac, int id, uint8_t bits[16],

@@ -82,7 +82,7 @@ EXPORTS = (
 EXT_EXPORTS = (
     "rocJpegB200SetProfiling", "rocJpegB200GetStats", "rocJpegB200Prepare", "rocJpegB200Run",
     "rocJpegB200GetCoefficients", "rocJpegB200GetPlanes", "rocJpegB200StreamGetInfo", "rocJpegB200StreamGetSegment",
-    "rocJpegB200StreamGetQuantTable", "rocJpegB200StreamGetHuffmanTable", "rocJpegB200Version",
+    "rocJpegB200StreamGetQuantTable", "rocJpegB200StreamGetHuffmanTable", "rocJpegB200Version", "rocJpegB200StreamGetLastError",
     "rocJpegB200PlanShards", "rocJpegB200GetDeviceCount",
 )
 
@@ -124,6 +124,7 @@ def load_library() -> C.CDLL:
     L.rocJpegB200GetPlanes.argtypes = [vp, i32, vp, C.c_size_t]
     L.rocJpegB200StreamGetInfo.argtypes = [vp, C.POINTER(StreamInfo)]
     L.rocJpegB200StreamGetSegment.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_uint32)]
+    L.rocJpegB200StreamGetLastError.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.rocJpegB200StreamGetQuantTable.argtypes = [vp, i32, vp]
     L.rocJpegB200StreamGetHuffmanTable.argtypes = [vp, i32, i32, vp, vp, C.POINTER(C.c_uint32)]
     L.rocJpegB200PlanShards.argtypes = [vp, i32, i32, vp]
@@ -180,6 +181,11 @@ class JpegStream:
         buf = C.create_string_buffer(max(n.value, 1))
         _check(self.lib.rocJpegB200StreamGetSegment(self.handle, k, buf, n.value, C.byref(n)), "segment")
         return buf.raw[:n.value]
+
+    def last_error(self) -> str:
+        buf = C.create_string_buffer(512)
+        _check(self.lib.rocJpegB200StreamGetLastError(self.handle, buf, len(buf)), "last error")
+        return buf.value.decode("utf-8", "replace")
 
     def quant_table(self, tid: int):
         import numpy as np

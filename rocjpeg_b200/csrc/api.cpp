@@ -83,6 +83,7 @@ RocJpegStatus ROCJPEGAPI rocJpegStreamParse(const unsigned char* data, size_t le
             ERR("Invalid JPEG! " + h->error);
             return ROCJPEG_STATUS_BAD_JPEG;
         }
+        h->error.clear();
     } catch (const std::exception& e) {
         h->error = e.what();
         ERR(e.what());
@@ -322,6 +323,15 @@ RocJpegStatus rocJpegB200StreamGetSegment(RocJpegStreamHandle jpeg_stream_handle
         if (capacity < s.nbytes) return ROCJPEG_STATUS_INVALID_PARAMETER;
         std::memcpy(out, h->parser->clean().data() + s.offset, s.nbytes);
     }
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200StreamGetLastError(RocJpegStreamHandle jpeg_stream_handle, char* out, size_t capacity) {
+    if (jpeg_stream_handle == nullptr || out == nullptr || capacity == 0) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    const std::string& e = static_cast<StreamHandle*>(jpeg_stream_handle)->error;
+    const size_t n = std::min(e.size(), capacity - 1);
+    std::memcpy(out, e.data(), n);
+    out[n] = 0;
     return ROCJPEG_STATUS_SUCCESS;
 }
 

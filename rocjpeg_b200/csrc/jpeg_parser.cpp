@@ -5,6 +5,8 @@
 
 #include <cuda_runtime_api.h>
 
+#include <string>
+
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
@@ -403,7 +405,8 @@ bool StreamParser::Parse(const uint8_t* d, size_t len) {
     if (!d || len < 4) return Fail("stream too short");
     if (d[0] != 0xFF || d[1] != 0xD8) return Fail("missing SOI");                   // parser.cpp:64
     size_t p = 2;
-    bool seen_dht = false, seen_dqt = false, seen_sos = false;
+    bool seen_dht = false, seen_dqt = false, seen_sos = false, seen_sof0 = false;
+    uint8_t other_sof = 0;   // a frame header this decoder (like the reference: parser.cpp:82, SOF = 0xC0 only) does not handle
     while (!seen_sos) {
         if (p + 4 > len) return Fail("truncated before SOS");
         while (p < len && d[p] == 0xFF) p++;                                        // parser.cpp:75
@@ -414,14 +417,32 @@ bool StreamParser::Parse(const uint8_t* d, size_t len) {
         if (seglen < 2 || next > len) return Fail("bad segment length");
         const uint8_t* s = d + p;
         switch (m) {
-            case 0xC0: if (!ParseSof(s, seglen)) return false; break;
+            case 0xC0: if (!ParseSof(s, seglen)) return false; seen_sof0 = true; break;
+            case 0xC1: case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD:
+            case 0xCE: case 0xCF:
+                other_sof = m;   // skipped by length as the reference does; the scan header then has no frame to refer to
+                break;
             case 0xC4: if (!ParseDht(s, seglen)) return false; seen_dht = true; break;
             case 0xDB: if (!ParseDqt(s, seglen)) return false; seen_dqt = true; break;
             case 0xDD:                                                              // parser.cpp:374-390
                 if (seglen != 4) return Fail("bad DRI length");
                 p_.restart_interval = int32_t(Rd16(s + 2));
                 break;
-            case 0xDA: if (!ParseSos(s, seglen)) return false; seen_sos = true; break;
+            case 0xDA:
+                // same verdict as the reference (its ParseSOS finds no matching frame components, parser.cpp:340-358),
+                // but say what the file is instead of reporting a component mismatch
+                if (!seen_sof0 && other_sof) {
+                    static const char* const kKind[16] = {"", "extended sequential", "progressive", "lossless", "", "differential sequential",
+                                                          "differential progressive", "differential lossless", "", "arithmetic-coded sequential",
+                                                          "arithmetic-coded progressive", "arithmetic-coded lossless", "", "arithmetic-coded differential",
+                                                          "arithmetic-coded differential", "arithmetic-coded differential"};
+                    const std::string why = std::string("not a baseline JPEG: ") + kKind[other_sof & 15] + " frame (SOF" +
+                                            std::to_string(other_sof & 15) + ") - only baseline sequential DCT (SOF0) is decoded";
+                    return Fail(why.c_str());   // Fail copies the text
+                }
+                if (!ParseSos(s, seglen)) return false;
+                seen_sos = true;
+                break;
             default: break;   // APPn, COM, SOF2 ... skipped by length (parser.cpp:105-108)
         }
         p = next;

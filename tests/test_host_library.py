@@ -160,6 +160,9 @@ def test_parser_reuse_and_unsupported(lib):
     i = bytes(base).index(b"\xFF\xC0")
     base[i + 1] = 0xC2
     assert s.parse(bytes(base)) == api.BAD_JPEG
+    assert "progressive frame (SOF2)" in s.last_error()   # same verdict, but the message names the file type
+    base[i + 1] = 0xC9
+    assert s.parse(bytes(base)) == api.BAD_JPEG and "arithmetic-coded sequential frame (SOF9)" in s.last_error()
     # 4:1:1 parses (ROCJPEG_CSS_411) but is not decodable, as in the reference (samples skip it)
     assert s.parse(make_411()) == api.SUCCESS
     assert s.info().chroma_subsampling == api.CSS_411 and s.info().decode_status == api.JPEG_NOT_SUPPORTED
