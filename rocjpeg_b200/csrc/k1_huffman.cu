@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters)
     uint32_t my_used = 0, out = 0, old_out = kNoState;
     if (round > 0) {
         // Does any owned subsequence start from a state that is not its predecessor's end state (the CTA
-        // boundary after a neighbour changed, or - behind k1_fix - a chain it could not finish)?
+        // boundary after a neighbour changed, or a chain an earlier round left unfinished)?
         int need0 = 0;
         if (me.active && !me.first) need0 = (StateKey(a.state[g - 1]) != a.used[g]);
         if (!__syncthreads_or(need0)) return;
