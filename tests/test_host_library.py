@@ -148,6 +148,52 @@ def test_parser_accept_reject_matches_oracle(lib, orc):
     assert s.info().scan_size == len(base[:sos + 200]) - s.info().scan_offset
 
 
+def test_parser_header_fuzz_matches_oracle_and_reference(lib, orc):
+    """Seeded single-byte and truncation mutations of the header region: the library's parser, the oracle's
+    and - where oracle/_ref is built - the reference's own RocJpegStreamParser must agree on accept / reject and,
+    when accepted, on the geometry; nothing may crash."""
+    import oracle
+
+    ref = oracle.RefParser() if oracle.ref_available() else None
+    rng = np.random.default_rng(1234)
+    checked = accepted = 0
+    for name in ("synth_420_123x77_dri", "synth_444_123x77", "custom_huffman_420_dri1", "synth_400_123x77"):
+        base = load(name)
+        sos = base.index(b"\xFF\xDA")
+        hdr_end = sos + 2 + int.from_bytes(base[sos + 2:sos + 4], "big")
+        s = api.JpegStream()
+        for _ in range(150):
+            m = bytearray(base)
+            kind = int(rng.integers(0, 4))
+            if kind == 0:      # one header byte replaced
+                m[int(rng.integers(2, hdr_end))] = int(rng.integers(0, 256))
+            elif kind == 1:    # one bit flipped
+                m[int(rng.integers(2, hdr_end))] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 2:    # truncated somewhere in the header
+                m = m[:int(rng.integers(2, hdr_end))]
+            else:              # two adjacent bytes (a length field, a marker) replaced
+                k = int(rng.integers(2, hdr_end - 1))
+                m[k], m[k + 1] = int(rng.integers(0, 256)), int(rng.integers(0, 256))
+            data = bytes(m)
+            st = s.parse(data)
+            rc, o = orc.parse(data)
+            assert (st == api.SUCCESS) == (rc == 0), (name, kind, data[:hdr_end].hex())
+            # the reference's parser has no bounds checks (a segment length that runs past the buffer is read out
+            # of bounds, src/rocjpeg_parser.cpp:75-108): its verdict is only defined when every segment fits
+            out_of_bounds = st != api.SUCCESS and any(w in s.last_error() for w in ("truncated", "segment length", "too short"))
+            if ref is not None and not out_of_bounds:
+                r = ref.parse(data)
+                assert (r.ok == 1) == (rc == 0), (name, kind, s.last_error(), data[:hdr_end].hex())
+            checked += 1
+            if st == api.SUCCESS:
+                accepted += 1
+                i = s.info()
+                assert (i.width, i.height, i.num_components, i.chroma_subsampling) == (o.width, o.height, o.ncomp, o.css)
+                assert (i.scan_offset, i.scan_size, i.restart_interval) == (o.scan_offset, o.scan_size, o.restart_interval)
+                assert i.decode_status == orc.supported(o)
+    assert checked == 600 and 50 < accepted < 550   # the mutations exercise both outcomes
+
+
 def test_parser_reuse_and_unsupported(lib):
     s = api.JpegStream()
     assert s.parse(load("synth_444_500x375")) == api.SUCCESS
