@@ -1084,7 +1084,7 @@ int Lane::CopyCoefficients(int image, int16_t* host_out, size_t count) {
     RJB_CUDA(cudaMemcpy(ents.data(), k1_.entries + im.ent0, ents.size() * 4, cudaMemcpyDeviceToHost));
     for (size_t b = 0; b < recs.size(); b++) {
         uint32_t e0 = b ? recs[b - 1].end : 0u, e1 = recs[b].end;   // a block's entries begin where its predecessor's end
-        if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > im.ent_cap) e0 = e1 = 0;
+        if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 0xFFFFu || e1 > im.ent_cap) e0 = e1 = 0;   // as K2
         for (uint32_t k = e0; k < e1; k++) tmp[b * 64 + kZz[CoefEntryPos(ents[k])]] = int16_t(ents[k] & 0xFFFFu);
         tmp[b * 64] = recs[b].dc;   // integrated DC lives in the block's record
     }

@@ -242,7 +242,10 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
             e0 = blk ? __ldg(&ti.rec[blk - 1].end) : 0u;
             uint32_t e1 = r.x;
             dc = int(int16_t(r.y & 0xFFFFu));
-            if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 128u || e1 > ti.ent_cap) e1 = e0 = 0;   // never decoded
+            // (a block of a valid stream has at most 64 entries + 7 pads per subsequence boundary inside it; after a DAMAGED
+            // restart interval the first block of the next one also owns the pad groups the counting pass reserved in vain,
+            // any number of them - they are skipped, not a reason to drop the block; s_count is 16 bits wide)
+            if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 0xFFFFu || e1 > ti.ent_cap) e1 = e0 = 0;   // never decoded
             n = e1 - e0;
         }
         s_first[t][bb] = e0;

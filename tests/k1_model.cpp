@@ -103,6 +103,8 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     // ones; K1_MODEL_HALO overrides) re-decode the subsequences before them
     uint32_t H = uint32_t(768 / S);
     if (const char* e = std::getenv("K1_MODEL_HALO")) H = uint32_t(std::atoi(e));
+    // K1_MODEL_TOLERANT=1: damaged streams are handled as the device handles them instead of failing the model's self-checks
+    const bool tolerant = std::getenv("K1_MODEL_TOLERANT") != nullptr && std::atoi(std::getenv("K1_MODEL_TOLERANT")) != 0;
     const uint32_t nctas = (nsub + T - 1) / T;
     std::vector<uint32_t> state(nsub, 0), used(nsub, 0), nnzv(nsub, 0);
     NullSink nsink;
@@ -216,7 +218,9 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
             DecodeSpan<true>(ld, &parser.lut(), sel, bpm, pb, subs[g].end_bit, c, z, cnt, nnz, blk, limit, sink);
             // counting pass and write pass must agree (the last thread of an interval may have counted padding)
             const uint32_t used_n = (sink.n - n0 + 7u) & ~7u;
-            if (subs[g].last ? used_n > nnzv[g] : used_n != nnzv[g]) return -7;
+            // (a damaged interval can hold more blocks than it should: the write pass stops at the interval's last block,
+            // the counting pass did not - fewer entries than reserved is then legitimate, more never is)
+            if (tolerant ? used_n > nnzv[g] : (subs[g].last ? used_n > nnzv[g] : used_n != nnzv[g])) return -7;
             // zero padding: the tail of the last group and the groups the counting pass reserved in vain
             for (uint32_t k2 = sink.n; k2 < n0 + nnzv[g] && k2 < cap; k2++) entries[k2] = kPadEntry;
         }
@@ -225,7 +229,11 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     std::vector<int16_t> coef(size_t(nblocks) * 64, 0);
     for (uint32_t b = 0; b < nblocks; b++) {
         uint32_t e0 = b ? blk_end[b - 1] : 0u, e1 = blk_end[b];   // a block begins where its predecessor ends
-        if (e0 == 0xFFFFFFFFu || e1 == 0xFFFFFFFFu || e1 < e0 || e1 - e0 > 128u || e1 > cap) return -8;
+        if (e0 == 0xFFFFFFFFu || e1 == 0xFFFFFFFFu || e1 < e0 || e1 - e0 > 0xFFFFu || e1 > cap) {
+            if (!tolerant) return -8;
+            if (e1 == 0xFFFFFFFFu) dcdiff[b] = 0;   // K2 / the DC kernels: a block no thread reached decodes as zero
+            continue;
+        }
         for (uint32_t k2 = e0; k2 < e1; k2++) coef[size_t(b) * 64 + kZig[CoefEntryPos(entries[k2])]] = int16_t(entries[k2] & 0xFFFFu);
     }
     // DC integration per component, reset at restart intervals

@@ -281,6 +281,41 @@ def test_k1_schedule_model_any_halo_width(k1_model, orc, halo, monkeypatch):
             assert np.array_equal(out, want), (name, S, T, halo)
 
 
+def test_k1_schedule_model_damaged_streams_do_not_depend_on_the_schedule(k1_model, orc, monkeypatch):
+    """Correctness never depends on the stream synchronising: on scans with random byte damage or cut short, every
+    subsequence size / CTA size must produce the SAME coefficients (the model handles what a damaged interval
+    leaves behind as the device does: a block no thread reached decodes as zero, pad groups are skipped)."""
+    monkeypatch.setenv("K1_MODEL_TOLERANT", "1")
+    rng = np.random.default_rng(5)
+    names = ["synth_420_500x375_dri7", "synth_444_500x375", "custom_huffman_420_dri1", "mug_422_crop_dri1", "synth_400_333x211"]
+    same_as_oracle = checked = 0
+    for trial in range(60):
+        data = bytearray(load(names[trial % len(names)]))
+        sos = data.rfind(b"\xff\xda")
+        lo, hi = sos + 14, len(data) - 2
+        if trial % 6 == 5:
+            data = data[:lo + int(rng.integers(1, hi - lo))] + b"\xff\xd9"
+        else:
+            for _ in range(int(rng.integers(1, 12))):
+                data[int(rng.integers(lo, hi))] = int(rng.integers(0, 256))
+        data = bytes(data)
+        rc, info = orc.parse(data)
+        if rc != 0:
+            continue
+        want = np.concatenate([c.reshape(-1) for c in orc.coefficients(data, info)])
+        outs = []
+        for S, T in [(32, 8), (64, 2), (128, 3), (128, 128)]:
+            out = np.zeros(want.size, dtype=np.int16)
+            st = _ModelStats()
+            assert k1_model.k1_model_decode(data, len(data), S, T, out.ctypes.data, out.size, C.byref(st)) == 0, (trial, S, T)
+            outs.append(out)
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0]), trial
+        checked += 1
+        same_as_oracle += int(np.array_equal(outs[0], want))
+    assert checked >= 50 and same_as_oracle >= checked // 3   # damage that keeps the block structure decodes like the oracle
+
+
 # ---------------------------------------------------------------- multi-device plan (host only)
 
 def test_shard_plan_is_lpt_and_balanced():
