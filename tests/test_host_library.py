@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 import oracle
-from rocjpeg_b200 import api
+from rocjpeg_b200 import api, datagen
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -279,6 +279,46 @@ def test_k1_schedule_model_any_halo_width(k1_model, orc, halo, monkeypatch):
             st = _ModelStats()
             assert k1_model.k1_model_decode(data, len(data), S, T, out.ctypes.data, out.size, C.byref(st)) == 0
             assert np.array_equal(out, want), (name, S, T, halo)
+
+
+def test_k1_schedule_model_random_streams(k1_model, orc):
+    """Seeded sweep over sizes (8..400), qualities (5..100), subsamplings, restart intervals, optimised Huffman tables
+    and white-noise pictures (long codes everywhere): the schedule model reproduces the oracle's coefficients."""
+    import io
+
+    from PIL import Image
+
+    rng = np.random.default_rng(99)
+    for trial in range(20):
+        w, h = int(rng.integers(8, 400)), int(rng.integers(8, 300))
+        css = ("444", "422", "420", "400", "440")[trial % 5]
+        q = int(rng.integers(5, 101))
+        img = datagen.synth_image(w, h, seed=1000 + trial)
+        if trial % 3 == 0:
+            img = rng.integers(0, 256, img.shape, dtype=np.uint8)
+        if css == "440":
+            data = datagen.encode_jpeg(img, css, q, restart_mcus=int(rng.integers(0, 9)))
+        else:
+            kw = dict(format="JPEG", quality=q, optimize=bool(trial % 2), progressive=False)
+            if css == "400":
+                im = Image.fromarray(img[..., 1], mode="L")
+            else:
+                im = Image.fromarray(img, mode="RGB")
+                kw["subsampling"] = {"444": 0, "422": 1, "420": 2}[css]
+            r = int(rng.integers(0, 9))
+            if r:
+                kw["restart_marker_blocks"] = r
+            b = io.BytesIO()
+            im.save(b, **kw)
+            data = b.getvalue()
+        rc, info = orc.parse(data)
+        assert rc == 0
+        want = np.concatenate([c.reshape(-1) for c in orc.coefficients(data, info)])
+        for S, T in [(32, 3), (128, 126)]:
+            out = np.zeros(want.size, dtype=np.int16)
+            st = _ModelStats()
+            assert k1_model.k1_model_decode(data, len(data), S, T, out.ctypes.data, out.size, C.byref(st)) == 0
+            assert np.array_equal(out, want), (trial, css, q, w, h, S, T)
 
 
 def test_k1_schedule_model_damaged_streams_do_not_depend_on_the_schedule(k1_model, orc, monkeypatch):
