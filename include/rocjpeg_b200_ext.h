@@ -26,14 +26,14 @@
 extern "C" {
 #endif
 
-#define ROCJPEG_B200_STAGE_COUNT 7 /* upload, clear, huffman-sync, huffman-write, dc, idct, output */
+#define ROCJPEG_B200_STAGE_COUNT 7 /* upload, destuff, huffman-sync, huffman-write, dc, idct, output */
 
 typedef struct {
     float stage_ms[ROCJPEG_B200_STAGE_COUNT]; /* CUDA-event time of each stage on the decoder's stream */
     float total_ms;                           /* first to last event */
     uint32_t sync_rounds;                     /* k1_sync launches (2 when the stream self-synchronises) */
     uint32_t decodes_per_round[8];            /* subsequence decodes performed in each round */
-    uint64_t scan_bytes;                      /* destuffed entropy-coded bytes in the batch */
+    uint64_t scan_bytes;                      /* entropy-coded bytes of the batch as uploaded (before destuffing) */
     uint64_t blocks;                          /* 8x8 blocks decoded */
     uint64_t subsequences;
     uint64_t plane_bytes;                     /* component-plane bytes written by the IDCT stage */
@@ -45,6 +45,7 @@ typedef struct {
     float host_submit_ms;                     /* host wall time of the last call spent describing the batch and enqueueing work */
     float host_wait_ms;                       /* host wall time of the last call spent waiting for the device */
     int32_t devices;                          /* GPUs the last call was sharded over (ROCJPEG_B200_DEVICES) */
+    uint64_t entries;                         /* 32-bit coefficient entries the entropy stage wrote (pad entries included) */
 } RocJpegB200Stats;
 
 /* CUDA-event timing on a decoder handle: 0 off (default), 1 an event after every stage (stage_ms and total_ms;
@@ -61,10 +62,34 @@ RocJpegStatus rocJpegB200Prepare(RocJpegHandle handle, RocJpegStreamHandle *jpeg
                                  const RocJpegDecodeParams *decode_params, RocJpegImage *destinations);
 RocJpegStatus rocJpegB200Run(RocJpegHandle handle);
 
+/* Timing-harness helper: exactly the caller's loop of the reference's batched sample - rocJpegStreamParse(datas[i],
+ * lengths[i], handles[i]) for every image, then one rocJpegDecodeBatched - issued from C. *parse_seconds (optional) = wall
+ * time of the parse loop. */
+RocJpegStatus rocJpegB200ParseAndDecodeBatched(RocJpegHandle handle, RocJpegStreamHandle *jpeg_stream_handles,
+                                               const unsigned char *const *datas, const size_t *lengths, int batch_size,
+                                               const RocJpegDecodeParams *decode_params, RocJpegImage *destinations,
+                                               double *parse_seconds);
+
 /* Stage taps for image `index` of the last decoded batch. Layout = the oracle's: component-major,
  * each component an MCU-padded raster of blocks (64 int16, natural order) / samples (u8). */
 RocJpegStatus rocJpegB200GetCoefficients(RocJpegHandle handle, int index, int16_t *host_out, size_t count);
 RocJpegStatus rocJpegB200GetPlanes(RocJpegHandle handle, int index, uint8_t *host_out, size_t count);
+
+/* Taps on the GPU destuffing pass (k0_destuff.cu) for image `index` of the last decoded batch: what it found in the
+ * raw bytes, and the destuffed bytes of one restart interval as they lie in device memory. */
+typedef struct {
+    uint32_t segments_seen;  /* restart intervals present in the bytes (restart markers + 1) */
+    uint32_t scan_size;      /* raw bytes up to the first FF D9 - what the reference's parser computes on the host
+                                (src/rocjpeg_parser.cpp:400-416) */
+    uint32_t flags;          /* ROCJPEG_B200_SCAN_* */
+    uint32_t reserved;
+} RocJpegB200ScanStatus;
+#define ROCJPEG_B200_SCAN_NO_EOI 1u          /* no FF D9: the slice ran to the end of the buffer */
+#define ROCJPEG_B200_SCAN_STRAY_MARKER 2u    /* a marker other than RSTn / EOI inside the entropy-coded data */
+#define ROCJPEG_B200_SCAN_EXTRA_RESTARTS 4u  /* more restart markers than the frame has restart intervals */
+RocJpegStatus rocJpegB200GetScanStatus(RocJpegHandle handle, int index, RocJpegB200ScanStatus *status);
+RocJpegStatus rocJpegB200GetDeviceSegment(RocJpegHandle handle, int index, uint32_t segment, uint8_t *host_out, size_t capacity,
+                                          uint32_t *nbytes);
 
 /* Parser taps (host only). */
 typedef struct {
@@ -72,17 +97,29 @@ typedef struct {
     int32_t h_sampling[3], v_sampling[3], quant_selector[3], dc_selector[3], ac_selector[3];
     int32_t restart_interval;
     uint32_t num_mcus;                /* as the reference computes it (src/rocjpeg_parser.cpp:197) */
-    uint32_t scan_offset, scan_size;  /* entropy-coded slice inside the caller's buffer */
+    uint32_t scan_offset;             /* first entropy-coded byte inside the caller's buffer */
+    uint32_t raw_bytes;               /* from there to the end of the buffer (the slice ends at the first FF D9: found on the GPU) */
     int32_t mcus_x, mcus_y, blocks_per_mcu;
     int32_t blocks_w[3], blocks_h[3];
-    uint32_t num_segments;            /* restart intervals */
-    uint32_t restart_markers_seen;
-    uint64_t clean_bytes;             /* destuffed stream incl. per-segment padding */
+    uint32_t num_segments;            /* restart intervals the frame needs, bounded by what the bytes can hold */
     int32_t decode_status;            /* RocJpegStatus rocJpegDecode would return for this stream */
-    int32_t staging_is_pinned;
+    int32_t source_is_device_visible; /* the entropy-coded bytes are in page-locked memory (the caller's or the staging pool's) */
+    int32_t source_is_zero_copy;      /* ... the caller's own page-locked buffer, used in place */
 } RocJpegB200StreamInfo;
 RocJpegStatus rocJpegB200StreamGetInfo(RocJpegStreamHandle jpeg_stream_handle, RocJpegB200StreamInfo *info);
-/* Copy the destuffed bytes of restart interval `segment` (returns its length via *nbytes). */
+/* The HOST restatement of the GPU destuffing pass (tests and taps only - rocJpegStreamParse does not touch the
+ * entropy-coded bytes and the decode path never runs this): slice size up to the first FF D9 as the reference's
+ * parser reports it (src/rocjpeg_parser.cpp:400-416), restart markers, destuffed restart intervals. Reads the
+ * caller's buffer given to the last rocJpegStreamParse, which must still be valid. */
+typedef struct {
+    uint32_t scan_size;
+    uint32_t restart_markers_seen;
+    uint32_t num_segments;
+    uint64_t clean_bytes;             /* destuffed stream incl. per-segment padding */
+} RocJpegB200HostScanInfo;
+RocJpegStatus rocJpegB200StreamHostScan(RocJpegStreamHandle jpeg_stream_handle, RocJpegB200HostScanInfo *info);
+/* Copy the destuffed bytes of restart interval `segment` as the host restatement produces them (returns its
+ * length via *nbytes). */
 RocJpegStatus rocJpegB200StreamGetSegment(RocJpegStreamHandle jpeg_stream_handle, uint32_t segment, uint8_t *out,
                                           size_t capacity, uint32_t *nbytes);
 /* Why the last rocJpegStreamParse on this handle failed (the text the library also prints to stderr, as the

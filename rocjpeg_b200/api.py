@@ -32,7 +32,7 @@ OUTPUT_NATIVE, OUTPUT_YUV_PLANAR, OUTPUT_Y, OUTPUT_RGB, OUTPUT_RGB_PLANAR = 0, 1
 FMT = {"native": 0, "yuv_planar": 1, "y": 2, "rgb": 3, "rgb_planar": 4}
 # RocJpegBackend (api/rocjpeg.h:176-179)
 BACKEND_HARDWARE, BACKEND_HYBRID = 0, 1
-STAGES = ("upload", "clear", "huffman_sync", "huffman_write", "dc", "idct", "output")
+STAGES = ("upload", "destuff", "huffman_sync", "huffman_write", "dc", "idct", "output")
 
 
 class RocJpegImage(C.Structure):
@@ -59,6 +59,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
         ("subsequence_bytes", C.c_int32), ("lanes", C.c_int32),
         ("host_submit_ms", C.c_float), ("host_wait_ms", C.c_float), ("devices", C.c_int32),
+        ("entries", C.c_uint64),
     ]
 
 
@@ -67,12 +68,23 @@ class StreamInfo(C.Structure):
         ("width", C.c_int32), ("height", C.c_int32), ("num_components", C.c_int32), ("chroma_subsampling", C.c_int32),
         ("h_sampling", C.c_int32 * 3), ("v_sampling", C.c_int32 * 3), ("quant_selector", C.c_int32 * 3),
         ("dc_selector", C.c_int32 * 3), ("ac_selector", C.c_int32 * 3), ("restart_interval", C.c_int32),
-        ("num_mcus", C.c_uint32), ("scan_offset", C.c_uint32), ("scan_size", C.c_uint32),
+        ("num_mcus", C.c_uint32), ("scan_offset", C.c_uint32), ("raw_bytes", C.c_uint32),
         ("mcus_x", C.c_int32), ("mcus_y", C.c_int32), ("blocks_per_mcu", C.c_int32),
         ("blocks_w", C.c_int32 * 3), ("blocks_h", C.c_int32 * 3), ("num_segments", C.c_uint32),
-        ("restart_markers_seen", C.c_uint32), ("clean_bytes", C.c_uint64), ("decode_status", C.c_int32),
-        ("staging_is_pinned", C.c_int32),
+        ("decode_status", C.c_int32), ("source_is_device_visible", C.c_int32), ("source_is_zero_copy", C.c_int32),
     ]
+
+
+class ScanStatus(C.Structure):
+    _fields_ = [("segments_seen", C.c_uint32), ("scan_size", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+SCAN_NO_EOI, SCAN_STRAY_MARKER, SCAN_EXTRA_RESTARTS = 1, 2, 4
+
+
+class HostScanInfo(C.Structure):
+    _fields_ = [("scan_size", C.c_uint32), ("restart_markers_seen", C.c_uint32), ("num_segments", C.c_uint32),
+                ("clean_bytes", C.c_uint64)]
 
 
 EXPORTS = (
@@ -83,7 +95,8 @@ EXT_EXPORTS = (
     "rocJpegB200SetProfiling", "rocJpegB200GetStats", "rocJpegB200Prepare", "rocJpegB200Run",
     "rocJpegB200GetCoefficients", "rocJpegB200GetPlanes", "rocJpegB200StreamGetInfo", "rocJpegB200StreamGetSegment",
     "rocJpegB200StreamGetQuantTable", "rocJpegB200StreamGetHuffmanTable", "rocJpegB200Version", "rocJpegB200StreamGetLastError",
-    "rocJpegB200PlanShards", "rocJpegB200GetDeviceCount",
+    "rocJpegB200PlanShards", "rocJpegB200GetDeviceCount", "rocJpegB200StreamHostScan",
+    "rocJpegB200GetScanStatus", "rocJpegB200GetDeviceSegment", "rocJpegB200ParseAndDecodeBatched",
 )
 
 _lib = None
@@ -123,6 +136,11 @@ def load_library() -> C.CDLL:
     L.rocJpegB200GetCoefficients.argtypes = [vp, i32, vp, C.c_size_t]
     L.rocJpegB200GetPlanes.argtypes = [vp, i32, vp, C.c_size_t]
     L.rocJpegB200StreamGetInfo.argtypes = [vp, C.POINTER(StreamInfo)]
+    L.rocJpegB200GetScanStatus.argtypes = [vp, i32, C.POINTER(ScanStatus)]
+    L.rocJpegB200GetDeviceSegment.argtypes = [vp, i32, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_uint32)]
+    L.rocJpegB200ParseAndDecodeBatched.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), i32, C.POINTER(RocJpegDecodeParams),
+                                                   C.POINTER(RocJpegImage), C.POINTER(C.c_double)]
+    L.rocJpegB200StreamHostScan.argtypes = [vp, C.POINTER(HostScanInfo)]
     L.rocJpegB200StreamGetSegment.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_uint32)]
     L.rocJpegB200StreamGetLastError.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.rocJpegB200StreamGetQuantTable.argtypes = [vp, i32, vp]
@@ -170,9 +188,20 @@ class JpegStream:
         self._data = data
         return self.lib.rocJpegStreamParse(data, len(data), self.handle)
 
+    def parse_ptr(self, address: int, length: int, keepalive=None) -> int:
+        """rocJpegStreamParse on a raw host address (e.g. a slice of a page-locked arena)."""
+        self._data = keepalive
+        return self.lib.rocJpegStreamParse(C.c_void_p(address), length, self.handle)
+
     def info(self) -> StreamInfo:
         s = StreamInfo()
         _check(self.lib.rocJpegB200StreamGetInfo(self.handle, C.byref(s)), "rocJpegB200StreamGetInfo")
+        return s
+
+    def host_scan(self) -> HostScanInfo:
+        """Host restatement of the GPU destuffing pass (tests only; needs the parsed bytes still alive)."""
+        s = HostScanInfo()
+        _check(self.lib.rocJpegB200StreamHostScan(self.handle, C.byref(s)), "rocJpegB200StreamHostScan")
         return s
 
     def segment(self, k: int) -> bytes:
@@ -283,6 +312,20 @@ class Decoder:
         hs, imgs, n, _ = streams if dests is None else self.make_batch(streams, dests)
         return self.lib.rocJpegDecodeBatched(self.handle, hs, n, C.byref(params), imgs)
 
+    def make_sources(self, addresses, lengths):
+        """Argument arrays (data pointers, lengths) for parse_and_decode_batched."""
+        n = len(addresses)
+        return ((C.c_void_p * n)(*addresses), (C.c_size_t * n)(*lengths))
+
+    def parse_and_decode_batched(self, batch, sources, params: RocJpegDecodeParams):
+        """rocJpegStreamParse per image + one rocJpegDecodeBatched, looped in C (the caller's loop of the reference's
+        batched sample). Returns (status, seconds spent in the parse loop)."""
+        hs, imgs, n, _ = batch
+        ptrs, lens = sources
+        sec = C.c_double()
+        st = self.lib.rocJpegB200ParseAndDecodeBatched(self.handle, hs, ptrs, lens, n, C.byref(params), imgs, C.byref(sec))
+        return st, sec.value
+
     # ---- extension taps -------------------------------------------------
     def prepare(self, streams, params, dests) -> int:
         hs = (C.c_void_p * len(streams))(*[s.handle for s in streams])
@@ -312,6 +355,19 @@ class Decoder:
         out = np.zeros(count, dtype=np.int16)
         _check(self.lib.rocJpegB200GetCoefficients(self.handle, index, out.ctypes.data, count), "rocJpegB200GetCoefficients")
         return out
+
+    def scan_status(self, index: int) -> ScanStatus:
+        s = ScanStatus()
+        _check(self.lib.rocJpegB200GetScanStatus(self.handle, index, C.byref(s)), "rocJpegB200GetScanStatus")
+        return s
+
+    def device_segment(self, index: int, k: int) -> bytes:
+        """Restart interval k of image `index` as the GPU destuffing pass left it in device memory."""
+        n = C.c_uint32()
+        _check(self.lib.rocJpegB200GetDeviceSegment(self.handle, index, k, None, 0, C.byref(n)), "device segment size")
+        buf = C.create_string_buffer(max(n.value, 1))
+        _check(self.lib.rocJpegB200GetDeviceSegment(self.handle, index, k, buf, n.value, C.byref(n)), "device segment")
+        return buf.raw[:n.value]
 
     def planes(self, index: int, count: int):
         import numpy as np

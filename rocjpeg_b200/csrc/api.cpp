@@ -8,6 +8,7 @@
 // wrappers mirror src/rocjpeg_api_decoder_handle.h / rocjpeg_api_stream_handle.h
 // (object + last-error string). The rocJpegB200* extension entry points are
 // declared in include/rocjpeg_b200_ext.h.
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <iostream>
@@ -231,6 +232,7 @@ RocJpegStatus rocJpegB200GetStats(RocJpegHandle handle, RocJpegB200Stats* stats)
     stats->host_submit_ms = s.host_submit_ms;
     stats->host_wait_ms = s.host_wait_ms;
     stats->devices = s.devices;
+    stats->entries = s.entries;
     return ROCJPEG_STATUS_SUCCESS;
 }
 
@@ -264,6 +266,23 @@ RocJpegStatus rocJpegB200Run(RocJpegHandle handle) {
     }
 }
 
+// The caller's loop of the reference's batched sample (samples/jpegDecodeBatched/jpegdecodebatched.cpp:106-160):
+// rocJpegStreamParse per image, then one rocJpegDecodeBatched - the public entry points, called from C so that
+// a timing harness written in Python measures the library and not its own interpreter.
+RocJpegStatus rocJpegB200ParseAndDecodeBatched(RocJpegHandle handle, RocJpegStreamHandle* jpeg_stream_handles, const unsigned char* const* datas,
+                                               const size_t* lengths, int batch_size, const RocJpegDecodeParams* decode_params,
+                                               RocJpegImage* destinations, double* parse_seconds) {
+    if (handle == nullptr || jpeg_stream_handles == nullptr || datas == nullptr || lengths == nullptr || batch_size < 0)
+        return ROCJPEG_STATUS_INVALID_PARAMETER;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < batch_size; i++) {
+        const RocJpegStatus st = rocJpegStreamParse(datas[i], lengths[i], jpeg_stream_handles[i]);
+        if (st != ROCJPEG_STATUS_SUCCESS) return st;
+    }
+    if (parse_seconds) *parse_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rocJpegDecodeBatched(handle, jpeg_stream_handles, batch_size, decode_params, destinations);
+}
+
 RocJpegStatus rocJpegB200PlanShards(const uint64_t* cost, int batch_size, int num_devices, int* out_device) {
     if (cost == nullptr || out_device == nullptr || batch_size < 0 || num_devices < 1) return ROCJPEG_STATUS_INVALID_PARAMETER;
     rjb::PlanShards(cost, batch_size, num_devices, out_device);
@@ -286,6 +305,23 @@ RocJpegStatus rocJpegB200GetPlanes(RocJpegHandle handle, int index, uint8_t* hos
     return RocJpegStatus(static_cast<DecoderHandle*>(handle)->decoder->CopyPlanes(index, host_out, count));
 }
 
+RocJpegStatus rocJpegB200GetDeviceSegment(RocJpegHandle handle, int index, uint32_t segment, uint8_t* host_out, size_t capacity, uint32_t* nbytes) {
+    if (handle == nullptr || nbytes == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    return RocJpegStatus(static_cast<DecoderHandle*>(handle)->decoder->CopySegment(index, segment, host_out, capacity, nbytes));
+}
+
+RocJpegStatus rocJpegB200GetScanStatus(RocJpegHandle handle, int index, RocJpegB200ScanStatus* status) {
+    if (handle == nullptr || status == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    rjb::ScanStatus st;
+    const int rc = static_cast<DecoderHandle*>(handle)->decoder->GetScanStatus(index, &st);
+    if (rc != 0) return RocJpegStatus(rc);
+    status->segments_seen = st.segments_seen;
+    status->scan_size = st.scan_size;
+    status->flags = st.flags;
+    status->reserved = st.reserved;
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
 RocJpegStatus rocJpegB200StreamGetInfo(RocJpegStreamHandle jpeg_stream_handle, RocJpegB200StreamInfo* info) {
     if (jpeg_stream_handle == nullptr || info == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
     auto h = static_cast<StreamHandle*>(jpeg_stream_handle);
@@ -300,13 +336,13 @@ RocJpegStatus rocJpegB200StreamGetInfo(RocJpegStreamHandle jpeg_stream_handle, R
     }
     info->restart_interval = p.restart_interval;
     info->num_mcus = p.num_mcus_ref;
-    info->scan_offset = p.scan_offset; info->scan_size = p.scan_size;
+    info->scan_offset = p.scan_offset;
+    info->raw_bytes = p.raw_bytes;
     info->mcus_x = p.mcus_x; info->mcus_y = p.mcus_y; info->blocks_per_mcu = p.bpm;
-    info->num_segments = uint32_t(p.segments.size());
-    info->restart_markers_seen = p.restart_markers_seen;
-    info->clean_bytes = p.clean_bytes;
+    info->num_segments = p.nseg;
     info->decode_status = p.support_status;
-    info->staging_is_pinned = h->parser->clean().pinned() ? 1 : 0;
+    info->source_is_device_visible = h->parser->raw().dev != nullptr ? 1 : 0;
+    info->source_is_zero_copy = h->parser->raw().zero_copy ? 1 : 0;
     return ROCJPEG_STATUS_SUCCESS;
 }
 
@@ -316,13 +352,27 @@ RocJpegStatus rocJpegB200StreamGetSegment(RocJpegStreamHandle jpeg_stream_handle
     auto h = static_cast<StreamHandle*>(jpeg_stream_handle);
     const rjb::ParsedJpeg& p = h->parser->parsed();
     if (!p.valid) return ROCJPEG_STATUS_BAD_JPEG;
-    if (segment >= p.segments.size()) return ROCJPEG_STATUS_INVALID_PARAMETER;
-    const rjb::Segment& s = p.segments[segment];
+    const rjb::HostScan& hs = h->parser->host_scan();
+    if (!hs.done || segment >= hs.segments.size()) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    const rjb::Segment& s = hs.segments[segment];
     *nbytes = s.nbytes;
     if (out != nullptr) {
         if (capacity < s.nbytes) return ROCJPEG_STATUS_INVALID_PARAMETER;
-        std::memcpy(out, h->parser->clean().data() + s.offset, s.nbytes);
+        std::memcpy(out, hs.clean.data() + s.offset, s.nbytes);
     }
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200StreamHostScan(RocJpegStreamHandle jpeg_stream_handle, RocJpegB200HostScanInfo* info) {
+    if (jpeg_stream_handle == nullptr || info == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    auto h = static_cast<StreamHandle*>(jpeg_stream_handle);
+    if (!h->parser->parsed().valid) return ROCJPEG_STATUS_BAD_JPEG;
+    const rjb::HostScan& hs = h->parser->host_scan();
+    if (!hs.done) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    info->scan_size = hs.scan_size;
+    info->restart_markers_seen = hs.restart_markers_seen;
+    info->num_segments = uint32_t(hs.segments.size());
+    info->clean_bytes = hs.clean_bytes;
     return ROCJPEG_STATUS_SUCCESS;
 }
 

@@ -164,7 +164,7 @@ int Lane::Create(int /*device_id*/, int sm_count) {
     // times every call, the first included; a cold cudaMalloc was measured at 1-26 ms): page-locked
     // staging and a starting size for the device arenas, ROCJPEG_B200_PREALLOC_MB per handle (default
     // 384, two thirds of it arena, one third planes, split over the lanes; 0 = allocate on demand)
-    if (!h_desc_.Reserve(1u << 20) || !h_counters_.Reserve(256)) return Fail(kOutOfMemory, "page-locked staging");
+    if (!h_desc_.Reserve(1u << 20) || !h_counters_.Reserve(256 + 4096 * sizeof(ScanStatus))) return Fail(kOutOfMemory, "page-locked staging");
     const size_t per_lane = size_t(std::max(0, EnvInt("ROCJPEG_B200_PREALLOC_MB", 384))) * (1u << 20) / kMaxLanes;
     RJB_CUDA(d_counters_.Reserve(512));
     RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint8_t>(), 0, 512, stream_));
@@ -221,6 +221,7 @@ int Decoder::Initialize() {
     RJB_CUDA(cudaStreamCreateWithPriority(&upload_stream_, cudaStreamNonBlocking, prio_hi));
     profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0);
     // everything a first decode would otherwise pay for: kernel modules, the lanes' streams and events
+    RJB_CUDA(PreloadK0());
     RJB_CUDA(PreloadK1());
     RJB_CUDA(PreloadK2());
     RJB_CUDA(PreloadK3());
@@ -320,7 +321,6 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         return Fail(kInvalidParameter, "unknown output format");
     h_images_.assign(size_t(n), ImageDesc{});
     h_outputs_.assign(size_t(n), OutputDesc{});
-    h_segments_.clear();
     h_img_cta0_.assign(size_t(n) + 1, 0);
     h_img_dctile0_.assign(size_t(n) + 1, 0);
     h_k2_tile0_.assign(size_t(n) + 1, 0);
@@ -332,7 +332,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     h_qtables_.assign(size_t(n) * 3 * 64, 1);
     stats_ = BatchStats();
 
-    uint64_t total_clean = 0;
+    uint64_t total_clean = 0;   // entropy-coded bytes as uploaded (destuffing removes well under 1 % of them)
     for (int i = 0; i < n; i++) {
         if (!streams[i]) return Fail(kInvalidParameter, "null stream handle in batch");
         const ParsedJpeg& p = streams[i]->parsed();
@@ -340,8 +340,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         if (p.support_status != kSuccess) {
             return Fail(p.support_status, "unsupported or inconsistent JPEG");
         }
-        if (!streams[i]->clean().data() || p.clean_bytes == 0) return Fail(kOutOfMemory, "no staging memory for the scan");
-        total_clean += p.clean_bytes;
+        if (!streams[i]->raw().host) return Fail(kOutOfMemory, "no staging memory for the scan");
+        total_clean += p.raw_bytes;
     }
     // Subsequence size. Long subsequences amortise the speculative re-decodes (with interleaved
     // 4:2:0 data a wrong start state needs about one MCU to re-synchronise); short ones only pay
@@ -364,9 +364,10 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     any_direct_ = false;
     needs_planes_ = false;
     const bool direct_ok = EnvInt("ROCJPEG_B200_NO_DIRECT", 0) == 0;
-    uint64_t scan_off = 0, blk = 0, plane_off = 0, ent = 0;
-    uint32_t sub = 0, dctile = 0, k2tile = 0, k3tile = 0, chunk = 0, max_pairs = 1, max_sub = 0;
+    uint64_t scan_off = 0, raw_off = 0, blk = 0, plane_off = 0, ent = 0, sub = 0;
+    uint32_t dctile = 0, k2tile = 0, k3tile = 0, chunk = 0, max_pairs = 1, max_sub = 0, k0tile = 0, nseg_total = 0;
     all_pinned_ = true;
+    h_k0_tile0_.assign(size_t(n) + 1, 0);
     for (int i = 0; i < n; i++) {
         const ParsedJpeg& p = streams[i]->parsed();
         ImageDesc& im = h_images_[size_t(i)];
@@ -422,49 +423,51 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         im.lut_set = set;
         max_pairs = std::max(max_pairs, uint32_t(im.npairs));
         max_sub = std::max(max_sub, (streams[i]->lut().sub_used + 3u) & ~3u);
-        // entropy-coded data
+        // entropy-coded data: uploaded raw (whole 16-byte vectors around it), destuffed on the device (k0_destuff.cu)
+        const RawScan& rs = streams[i]->raw();
+        const uint8_t* src = rs.dev ? rs.dev : rs.host;
+        im.raw_skip = uint32_t(reinterpret_cast<uintptr_t>(src) & 15u);
+        im.raw_len = rs.nbytes;
+        im.raw_off = raw_off;
+        const uint32_t up_bytes = uint32_t(AlignUp(size_t(im.raw_skip) + rs.nbytes, 16));
+        h_gather_[size_t(i)] = GatherItem{src - im.raw_skip, raw_off, up_bytes, chunk};
+        chunk += uint32_t((size_t(up_bytes) + 16383) / 16384);
+        all_pinned_ = all_pinned_ && rs.dev != nullptr;
+        raw_off += AlignUp(size_t(up_bytes) + 16, 128);
+        im.k0_tile0 = k0tile;
+        h_k0_tile0_[size_t(i)] = k0tile;
+        k0tile += std::max<uint32_t>(1u, uint32_t((size_t(im.raw_skip) + rs.nbytes + kK0TileBytes - 1) / kK0TileBytes));
         im.data_off = scan_off;
-        im.seg0 = uint32_t(h_segments_.size());
-        im.nseg = uint32_t(p.segments.size());
-        im.sub0 = sub;
-        const uint32_t ri = p.restart_interval > 0 ? uint32_t(p.restart_interval) : uint32_t(im.total_mcus);
+        im.seg0 = nseg_total;
+        im.nseg = p.nseg;
+        nseg_total += p.nseg;
+        const uint64_t clean_cap = CleanCapacity(rs.nbytes, p.nseg, uint32_t(S));
+        scan_off += clean_cap;
+        im.sub0 = uint32_t(sub);
+        im.nsub = uint32_t(clean_cap / uint32_t(S));
+        sub = AlignUp(sub + im.nsub, owned);
+        if (sub > 0x7FFFFFFFull || nseg_total > 0x7FFFFFFFu) return Fail(kNotSupported, "batch too large for one decode call");
+        h_img_cta0_[size_t(i)] = im.sub0 / owned;
         // Region of interest + restart markers: a restart interval is an independent unit (predictors
         // reset), so the intervals whose MCU rows lie wholly outside the crop rectangle are not entropy-
-        // decoded at all (same ROI rule as below: src/rocjpeg_decoder.cpp:126-131).
-        int64_t roi_row_lo = 0, roi_row_hi = INT64_MAX;
+        // decoded at all (same ROI rule as below: src/rocjpeg_decoder.cpp:126-131). The interval in front
+        // of the first wanted one is kept: the first block of an interval finds where its coefficient
+        // entries begin in the record of the block before it.
+        im.seg_keep_lo = 0;
+        im.seg_keep_hi = 0xFFFFFFFFu;
         {
             const uint32_t cw = uint32_t(int(params.crop_right) - int(params.crop_left));
             const uint32_t chh = uint32_t(int(params.crop_bottom) - int(params.crop_top));
             if (p.restart_interval > 0 && cw > 0 && chh > 0 && cw <= uint32_t(p.width) && chh <= uint32_t(p.height) &&
                 params.crop_top >= 0 && params.crop_bottom <= p.height && im.mcus_y > 0) {
                 const int mcu_h = 8 * std::max(1, p.ncomp == 1 ? 1 : p.vmax);
-                roi_row_lo = params.crop_top / mcu_h;
-                roi_row_hi = (params.crop_bottom - 1) / mcu_h;
+                const uint64_t row_lo = uint64_t(params.crop_top / mcu_h), row_hi = uint64_t((params.crop_bottom - 1) / mcu_h);
+                const uint64_t ri = uint64_t(p.restart_interval);
+                const uint64_t k_lo = row_lo * uint64_t(im.mcus_x) / ri, k_hi = ((row_hi + 1) * uint64_t(im.mcus_x) - 1) / ri;
+                im.seg_keep_lo = uint32_t(k_lo > 0 ? k_lo - 1 : 0);
+                im.seg_keep_hi = uint32_t(std::min<uint64_t>(k_hi, 0xFFFFFFFFull));
             }
         }
-        for (size_t sgi = 0; sgi < p.segments.size(); sgi++) {
-            const Segment& sg = p.segments[sgi];
-            SegmentDesc sd;
-            sd.data_off = scan_off + sg.offset;
-            sd.nbytes = sg.nbytes;
-            sd.sub0 = sub;
-            const uint64_t mcu_first = uint64_t(sgi) * ri;
-            const uint64_t mcu_cnt = mcu_first >= uint64_t(im.total_mcus) ? 0 : std::min<uint64_t>(ri, uint64_t(im.total_mcus) - mcu_first);
-            if (mcu_cnt > 0 && (int64_t((mcu_first + mcu_cnt - 1) / uint64_t(im.mcus_x)) < roi_row_lo ||
-                                int64_t(mcu_first / uint64_t(im.mcus_x)) > roi_row_hi))
-                sd.nbytes = 0;   // outside the region of interest: no subsequences, its blocks stay "never decoded"
-            sd.blk_first = uint32_t(mcu_first * uint64_t(p.bpm));
-            sd.blk_count = uint32_t(mcu_cnt * uint64_t(p.bpm));
-            h_segments_.push_back(sd);
-            sub += (sd.nbytes + uint32_t(S) - 1) / uint32_t(S);
-        }
-        im.nsub = sub - im.sub0;
-        sub = uint32_t(AlignUp(sub, owned));
-        h_img_cta0_[size_t(i)] = im.sub0 / owned;
-        h_gather_[size_t(i)] = GatherItem{streams[i]->clean().data(), scan_off, uint32_t(p.clean_bytes), chunk};
-        chunk += uint32_t((p.clean_bytes + 16383) / 16384);
-        all_pinned_ = all_pinned_ && streams[i]->clean().pinned();
-        scan_off += p.clean_bytes;
         // coefficients, DC tiles
         im.blk0 = blk;
         im.nblocks = uint32_t(im.total_mcus) * uint32_t(p.bpm);
@@ -472,7 +475,9 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         // entry arena: every entry consumes at least min_entry_bits of the scan, and a block holds at most 64
         im.ent0 = ent;
         // (+7 padding entries per subsequence: every thread's run is rounded up to whole 32-byte stores)
-        im.ent_cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 7 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
+        const uint64_t ent_cap = uint64_t(rs.nbytes) * 8 / p.min_entry_bits + 7 * (uint64_t(im.nsub) + 1) + 64;
+        if (ent_cap > 0xFFFFFF00ull) return Fail(kNotSupported, "scan too large for one picture");
+        im.ent_cap = uint32_t(ent_cap);
         ent += (uint64_t(im.ent_cap) + 63) & ~uint64_t(63);
         im.dc_tile0 = dctile;
         h_img_dctile0_[size_t(i)] = dctile;
@@ -518,24 +523,31 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         k3tile += od.tiles_x * od.tiles_y;
         stats_.output_bytes += OutputBytes(p.css, od.fmt, od.w, od.h);
     }
-    h_img_cta0_[size_t(n)] = sub / owned;
+    h_img_cta0_[size_t(n)] = uint32_t(sub / owned);
+    h_k0_tile0_[size_t(n)] = k0tile;
     h_img_dctile0_[size_t(n)] = dctile;
     h_k2_tile0_[size_t(n)] = k2tile;
     h_k3_tile0_[size_t(n)] = k3tile;
     gather_chunks_ = chunk;
     scan_bytes_ = scan_off;
+    raw_bytes_ = raw_off;
+    nseg_total_ = nseg_total;
     coef_blocks_ = blk;
     entry_count_ = ent;
     plane_bytes_ = plane_off;
     nsub_total_ = sub;
-    stats_.scan_bytes = scan_off;
+    stats_.scan_bytes = total_clean;
     stats_.blocks = blk;
     stats_.subsequences = sub;
 
     k1_ = K1Args{};
     k1_.nimages = n;
-    k1_.total_ctas = sub / owned;
+    k1_.total_ctas = uint32_t(sub / owned);
     k1_.halo = halo;
+    k0_ = K0Args{};
+    k0_.nimages = n;
+    k0_.total_tiles = k0tile;
+    k0_.sub_bytes = S;
     k1_.rec_fill_vecs = uint32_t((blk * sizeof(BlockRec) + 15) / 16);   // the slab leaves 256 bytes behind every array
     k1_.lut_smem_bytes = max_pairs * 2u * uint32_t(kFastSize) * 4u + max_sub * 4u;
     k1_.total_dc_tiles = dctile;
@@ -562,7 +574,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
 
 // Descriptor block: one pinned host buffer mirrored by one device buffer, one copy.
 struct Lane::Layout {
-    size_t images, outputs, segments, cta0, dctile0, k2tile0, k3tile0, gather, luts, qtables, total;
+    size_t images, outputs, cta0, k0tile0, dctile0, k2tile0, k3tile0, gather, luts, qtables, total;
 };
 
 int Lane::Upload(cudaStream_t up, UploadTurn turn) {
@@ -574,8 +586,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     auto place = [&](size_t bytes) { size_t at = o; o = AlignUp(o + bytes, 256); return at; };
     L.images = place(n * sizeof(ImageDesc));
     L.outputs = place(n * sizeof(OutputDesc));
-    L.segments = place(h_segments_.size() * sizeof(SegmentDesc));
     L.cta0 = place((n + 1) * 4);
+    L.k0tile0 = place((n + 1) * 4);
     L.dctile0 = place((n + 1) * 4);
     L.k2tile0 = place((n + 1) * 4);
     L.k3tile0 = place((n + 1) * 4);
@@ -587,8 +599,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     if (!h) return Fail(kOutOfMemory, "descriptor staging");
     std::memcpy(h + L.images, h_images_.data(), n * sizeof(ImageDesc));
     std::memcpy(h + L.outputs, h_outputs_.data(), n * sizeof(OutputDesc));
-    std::memcpy(h + L.segments, h_segments_.data(), h_segments_.size() * sizeof(SegmentDesc));
     std::memcpy(h + L.cta0, h_img_cta0_.data(), (n + 1) * 4);
+    std::memcpy(h + L.k0tile0, h_k0_tile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.dctile0, h_img_dctile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.k2tile0, h_k2_tile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.k3tile0, h_k3_tile0_.data(), (n + 1) * 4);
@@ -602,7 +614,9 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     // The plane arena is separate and only exists when some image needs the output stage.
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t at = off; off = AlignUp(off + bytes + 256, 256); return at; };
-    const size_t o_desc = carve(L.total), o_scan = carve(scan_bytes_ + 512), o_entries = carve(entry_count_ * 4),
+    const size_t o_desc = carve(L.total), o_raw = carve(raw_bytes_ + 512), o_scan = carve(scan_bytes_ + 512),
+                 o_segments = carve(size_t(nseg_total_) * sizeof(SegmentDesc)), o_tile_sum = carve(size_t(k0_.total_tiles) * 16),
+                 o_tile_carry = carve(size_t(k0_.total_tiles) * 16), o_status = carve(n * sizeof(ScanStatus)), o_entries = carve(entry_count_ * 4),
                  o_blkrec = carve(coef_blocks_ * sizeof(BlockRec)), o_nnz = carve(nsub_total_ * 4), o_state = carve(nsub_total_ * 4),
                  o_used = carve(nsub_total_ * 4), o_subseg = carve(nsub_total_ * 4), o_cta_entries = carve(size_t(k1_.total_ctas) * 4),
                  o_cta_partial = carve(size_t(k1_.total_ctas) * 8), o_cta_carry = carve(size_t(k1_.total_ctas) * 8),
@@ -611,12 +625,20 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     (void)o_end;
     RJB_CUDA(d_slab_.Reserve(off));
     if (needs_planes_) RJB_CUDA(d_planes_.Reserve(plane_bytes_ + 512));
-    if (!h_counters_.Reserve(256)) return Fail(kOutOfMemory, "counter staging");
+    if (!h_counters_.Reserve(256 + n * sizeof(ScanStatus))) return Fail(kOutOfMemory, "counter staging");
 
     uint8_t* base = d_slab_.as<uint8_t>();
     uint8_t* d = base + o_desc;
     k1_.images = reinterpret_cast<const ImageDesc*>(d + L.images);
-    k1_.segments = reinterpret_cast<const SegmentDesc*>(d + L.segments);
+    k1_.segments = reinterpret_cast<const SegmentDesc*>(base + o_segments);
+    k0_.images = k1_.images;
+    k0_.segments = reinterpret_cast<SegmentDesc*>(base + o_segments);
+    k0_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k0tile0);
+    k0_.raw = base + o_raw;
+    k0_.clean = base + o_scan;
+    k0_.tile_sum = reinterpret_cast<uint4*>(base + o_tile_sum);
+    k0_.tile_carry = reinterpret_cast<uint4*>(base + o_tile_carry);
+    k0_.status = reinterpret_cast<ScanStatus*>(base + o_status);
     k1_.img_cta0 = reinterpret_cast<const uint32_t*>(d + L.cta0);
     k1_.img_dctile0 = reinterpret_cast<const uint32_t*>(d + L.dctile0);
     k1_.scan = base + o_scan;
@@ -650,18 +672,19 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     // PCIe link and its kernels start while the next chunks are still in flight.
     guard.Acquire();
     RJB_CUDA(cudaMemcpyAsync(d, h, L.total, cudaMemcpyHostToDevice, up));
-    stats_.h2d_bytes = L.total + scan_bytes_;
+    stats_.h2d_bytes = L.total;
+    for (const GatherItem& g : h_gather_) stats_.h2d_bytes += g.nbytes;
     // Many small pictures: one gather kernel reading the parsers' mapped page-locked buffers (a copy call
     // per picture would cost the host more than the transfer). Few large ones: plain copies, which run on
     // the copy engine at full PCIe rate without occupying SMs.
-    const bool use_gather = all_pinned_ && h_images_.size() > 4 && scan_bytes_ / h_images_.size() < (256u << 10) &&
+    const bool use_gather = all_pinned_ && h_images_.size() > 4 && raw_bytes_ / h_images_.size() < (256u << 10) &&
                             EnvInt("ROCJPEG_B200_NO_GATHER", 0) == 0;
     if (use_gather) {
-        RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, const_cast<uint8_t*>(k1_.scan), up));
+        RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, const_cast<uint8_t*>(k0_.raw), up));
         stats_.kernel_launches++;
     } else {
         for (size_t i = 0; i < n; i++)
-            RJB_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(k1_.scan) + h_gather_[i].dst_off, h_gather_[i].src, h_gather_[i].nbytes,
+            RJB_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(k0_.raw) + h_gather_[i].dst_off, h_gather_[i].src, h_gather_[i].nbytes,
                                      cudaMemcpyHostToDevice, up));
     }
     if (up != stream_) {
@@ -700,6 +723,9 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
         RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
         RJB_CUDA(cudaMemsetAsync(k1_.counters_next, 0, 256, stream_));
     }
+    // K0: end of slice, destuffing, restart intervals -> clean stream + segment table, all on the device
+    RJB_CUDA(LaunchK0Destuff(k0_, stream_));
+    stats_.kernel_launches += 3;
     RJB_CUDA(mark(2));
     for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
     stats_.sync_rounds = uint32_t(rounds);
@@ -714,7 +740,8 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(mark(7));
     stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + 1 + 1;   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, output
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
-    stats_.d2h_bytes = 256;
+    RJB_CUDA(cudaMemcpyAsync(h_counters_.data() + 256, k0_.status, h_images_.size() * sizeof(ScanStatus), cudaMemcpyDeviceToHost, stream_));
+    stats_.d2h_bytes = 256 + h_images_.size() * sizeof(ScanStatus);
     return kSuccess;
 }
 
@@ -740,13 +767,16 @@ int Lane::Finish(int profiling_) {
             if (++guard > k1_.total_ctas + 2) return Fail(kExecutionFailed, "entropy decoder failed to converge");
         }
         RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
+        RJB_CUDA(cudaMemsetAsync(k1_.counters + 2 * kMaxSyncRounds, 0, 4, stream_));   // the first write pass counted its entries already
         RJB_CUDA(LaunchK1Write(k1_, stream_));
         RJB_CUDA(LaunchDcScan(k1_, stream_));
         RJB_CUDA(LaunchK2Idct(k2_, stream_));
         RJB_CUDA(LaunchK3Output(k3_, stream_));
+        RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
         RJB_CUDA(cudaStreamSynchronize(stream_));
         stats_.kernel_launches += 7;
     }
+    stats_.entries = cnt[2 * kMaxSyncRounds];
     for (int r = 0; r < kMaxSyncRounds; r++) stats_.decodes_per_round[r] = cnt[kMaxSyncRounds + r];
     if (profiling_) {
         for (int s = 0; s < kStageCount && profiling_ == 1; s++) {
@@ -763,7 +793,7 @@ int Lane::Finish(int profiling_) {
 // Contiguous split of the batch into chunks of similar entropy-coded size, one per lane.
 int Decoder::Split(const StreamParser* const* streams, int n) {
     uint64_t total = 0;
-    for (int i = 0; i < n; i++) total += streams[i] ? streams[i]->parsed().clean_bytes : 0;
+    for (int i = 0; i < n; i++) total += streams[i] ? streams[i]->parsed().raw_bytes : 0;
     int want = EnvInt("ROCJPEG_B200_LANES", 0);
     if (want <= 0) want = int(std::min<uint64_t>(kMaxLanes, total / (2u << 20)));   // about 2 MiB of scan per chunk at least
     want = std::max(1, std::min(std::min(want, kMaxLanes), n));
@@ -794,7 +824,7 @@ int Decoder::Split(const StreamParser* const* streams, int n) {
     int lane = 0;
     chunk_first_[0] = 0;
     for (int i = 0; i < n && lane + 1 < want; i++) {
-        acc += streams[i] ? streams[i]->parsed().clean_bytes : 0;
+        acc += streams[i] ? streams[i]->parsed().raw_bytes : 0;
         if (double(acc) >= double(total) * cum[lane + 1] && i + 1 < n) chunk_first_[++lane] = i + 1;
     }
     active_lanes_ = lane + 1;
@@ -884,6 +914,7 @@ void Decoder::Aggregate() {
         for (int r = 0; r < kMaxSyncRounds; r++) stats_.decodes_per_round[r] += s.decodes_per_round[r];
         stats_.scan_bytes += s.scan_bytes;
         stats_.blocks += s.blocks;
+        stats_.entries += s.entries;
         stats_.subsequences += s.subsequences;
         stats_.plane_bytes += s.plane_bytes;
         stats_.output_bytes += s.output_bytes;
@@ -947,7 +978,7 @@ int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const Deco
         const ParsedJpeg& p = streams[i]->parsed();
         if (!p.valid) return Fail(kBadJpeg, "stream handle holds no successfully parsed JPEG");
         if (p.support_status != kSuccess) return Fail(p.support_status, "unsupported or inconsistent JPEG");
-        cost[size_t(i)] = p.clean_bytes;
+        cost[size_t(i)] = p.raw_bytes;
     }
     shard_dev_.assign(size_t(n), 0);
     shard_local_.assign(size_t(n), 0);
@@ -991,6 +1022,7 @@ int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const Deco
         for (int r = 0; r < kMaxSyncRounds; r++) total.decodes_per_round[r] += s.decodes_per_round[r];
         total.scan_bytes += s.scan_bytes;
         total.blocks += s.blocks;
+        total.entries += s.entries;
         total.subsequences += s.subsequences;
         total.plane_bytes += s.plane_bytes;
         total.output_bytes += s.output_bytes;
@@ -1037,34 +1069,72 @@ int Decoder::Run() {
     return FinishAll();
 }
 
-int Decoder::CopyCoefficients(int image, int16_t* host_out, size_t count) {
-    std::lock_guard<std::mutex> lock(mutex_);
+Lane* Decoder::Locate(int image, int* local) {
     if (sharded_) {
-        if (image < 0 || size_t(image) >= shard_dev_.size()) return kInvalidParameter;
+        if (image < 0 || size_t(image) >= shard_dev_.size()) return nullptr;
         const int d = shard_dev_[size_t(image)];
-        if (d > 0) return peers_[size_t(d - 1)]->CopyCoefficients(shard_local_[size_t(image)], host_out, count);
+        if (d > 0) return peers_[size_t(d - 1)]->Locate(shard_local_[size_t(image)], local);
         image = shard_local_[size_t(image)];
     }
-    if (!prepared_ || image < 0 || image >= chunk_first_[active_lanes_] || !host_out) return kInvalidParameter;
-    DeviceGuard guard(device_id_);
+    if (!prepared_ || image < 0 || image >= chunk_first_[active_lanes_]) return nullptr;
     int l = 0;
     while (image >= chunk_first_[l + 1]) l++;
-    return lanes_[l].CopyCoefficients(image - chunk_first_[l], host_out, count);
+    *local = image - chunk_first_[l];
+    return &lanes_[l];
+}
+
+int Decoder::CopyCoefficients(int image, int16_t* host_out, size_t count) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    int local = 0;
+    Lane* lane = host_out ? Locate(image, &local) : nullptr;
+    if (!lane) return kInvalidParameter;
+    return lane->CopyCoefficients(local, host_out, count);
 }
 
 int Decoder::CopyPlanes(int image, uint8_t* host_out, size_t count) {
     std::lock_guard<std::mutex> lock(mutex_);
-    if (sharded_) {
-        if (image < 0 || size_t(image) >= shard_dev_.size()) return kInvalidParameter;
-        const int d = shard_dev_[size_t(image)];
-        if (d > 0) return peers_[size_t(d - 1)]->CopyPlanes(shard_local_[size_t(image)], host_out, count);
-        image = shard_local_[size_t(image)];
+    int local = 0;
+    Lane* lane = host_out ? Locate(image, &local) : nullptr;
+    if (!lane) return kInvalidParameter;
+    return lane->CopyPlanes(local, host_out, count);
+}
+
+int Decoder::CopySegment(int image, uint32_t segment, uint8_t* host_out, size_t capacity, uint32_t* nbytes) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    int local = 0;
+    Lane* lane = nbytes ? Locate(image, &local) : nullptr;
+    if (!lane) return kInvalidParameter;
+    return lane->CopySegment(local, segment, host_out, capacity, nbytes);
+}
+
+int Decoder::GetScanStatus(int image, ScanStatus* out) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    int local = 0;
+    Lane* lane = out ? Locate(image, &local) : nullptr;
+    if (!lane) return kInvalidParameter;
+    return lane->GetScanStatus(local, out);
+}
+
+int Lane::GetScanStatus(int image, ScanStatus* out) const {
+    if (image < 0 || size_t(image) >= h_images_.size()) return kInvalidParameter;
+    *out = reinterpret_cast<const ScanStatus*>(h_counters_.data() + 256)[image];   // read back with the counters at the end of the call
+    return kSuccess;
+}
+
+int Lane::CopySegment(int image, uint32_t segment, uint8_t* host_out, size_t capacity, uint32_t* nbytes) {
+    if (image < 0 || size_t(image) >= h_images_.size()) return kInvalidParameter;
+    const ImageDesc& im = h_images_[size_t(image)];
+    if (segment >= im.nseg) return kInvalidParameter;
+    SegmentDesc sd;
+    RJB_CUDA(cudaStreamSynchronize(stream_));
+    RJB_CUDA(cudaMemcpy(&sd, k1_.segments + im.seg0 + segment, sizeof(sd), cudaMemcpyDeviceToHost));
+    *nbytes = sd.nbytes;
+    if (host_out) {
+        if (capacity < sd.nbytes) return kInvalidParameter;
+        if (sd.data_off + sd.nbytes > scan_bytes_) return Fail(kExecutionFailed, "segment table entry outside the scan arena");
+        if (sd.nbytes) RJB_CUDA(cudaMemcpy(host_out, k1_.scan + sd.data_off, sd.nbytes, cudaMemcpyDeviceToHost));
     }
-    if (!prepared_ || image < 0 || image >= chunk_first_[active_lanes_] || !host_out) return kInvalidParameter;
-    DeviceGuard guard(device_id_);
-    int l = 0;
-    while (image >= chunk_first_[l + 1]) l++;
-    return lanes_[l].CopyPlanes(image - chunk_first_[l], host_out, count);
+    return kSuccess;
 }
 
 int Lane::CopyCoefficients(int image, int16_t* host_out, size_t count) {

@@ -56,7 +56,7 @@ class DeviceBuffer {
 
 enum StageId {
     kStageUpload = 0,   // descriptor block + entropy-coded bytes, host -> device
-    kStageClear,        // nothing in the common case (the record fill rides in k1_sync, the counters are zeroed a batch ahead)
+    kStageDestuff,      // K0: end of slice, destuffing, restart intervals, segment table (three launches)
     kStageSync,         // all k1_sync rounds
     kStageWrite,        // (k1_scan +) k1_write
     kStageDc,           // dc_image, or dc_sums + dc_scan + dc_apply
@@ -70,8 +70,9 @@ struct BatchStats {
     float total_ms = 0;                 // first event to last event
     uint32_t sync_rounds = 0;           // k1_sync launches that were needed
     uint32_t decodes_per_round[kMaxSyncRounds] = {};
-    uint64_t scan_bytes = 0;            // clean entropy-coded bytes
+    uint64_t scan_bytes = 0;            // entropy-coded bytes as uploaded
     uint64_t blocks = 0;                // 8x8 blocks decoded
+    uint64_t entries = 0;               // 32-bit coefficient entries K1 wrote (pad entries included)
     uint64_t subsequences = 0;
     uint64_t plane_bytes = 0;           // bytes of decoded component planes (K2 output)
     uint64_t output_bytes = 0;          // bytes K3 writes
@@ -132,6 +133,8 @@ class Lane {
     int Sync();
     int CopyCoefficients(int image, int16_t* host_out, size_t count);
     int CopyPlanes(int image, uint8_t* host_out, size_t count);
+    int CopySegment(int image, uint32_t segment, uint8_t* host_out, size_t capacity, uint32_t* nbytes);
+    int GetScanStatus(int image, ScanStatus* out) const;
     const BatchStats& stats() const { return stats_; }
     const std::string& last_error() const { return err_; }
     cudaEvent_t first_event() const { return ev_[0]; }
@@ -152,19 +155,20 @@ class Lane {
     // host-side batch description
     std::vector<ImageDesc> h_images_;
     std::vector<OutputDesc> h_outputs_;
-    std::vector<SegmentDesc> h_segments_;
-    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_;
+    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_, h_k0_tile0_;
     std::vector<GatherItem> h_gather_;
     std::vector<const HuffLutSet*> h_lut_ptrs_;
     std::vector<const ParsedJpeg*> h_lut_specs_;
     std::vector<uint64_t> h_lut_hashes_;
     std::vector<uint16_t> h_qtables_;
+    K0Args k0_ = {};
     K1Args k1_ = {};
     K2Args k2_ = {};
     K3Args k3_ = {};
     uint32_t gather_chunks_ = 0;
     bool all_pinned_ = false, any_direct_ = false, needs_planes_ = false;
-    size_t scan_bytes_ = 0, coef_blocks_ = 0, entry_count_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
+    size_t scan_bytes_ = 0, raw_bytes_ = 0, coef_blocks_ = 0, entry_count_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
+    uint32_t nseg_total_ = 0;
 
     StagingBuffer h_desc_;        // pinned descriptor block
     size_t desc_bytes_ = 0;
@@ -200,6 +204,8 @@ class Decoder {
     int Run();          // launch all stages for the prepared batch and synchronise
     int CopyCoefficients(int image, int16_t* host_out, size_t count);   // component-major raster layout
     int CopyPlanes(int image, uint8_t* host_out, size_t count);
+    int CopySegment(int image, uint32_t segment, uint8_t* host_out, size_t capacity, uint32_t* nbytes);   // destuffed by K0
+    int GetScanStatus(int image, ScanStatus* out);
     void SetProfiling(int level) { profiling_ = level; }   // 0 off, 1 per-stage events, 2 first/last event only
     const BatchStats& stats() const { return stats_; }
     const std::string& last_error() const { return err_; }
@@ -219,6 +225,8 @@ class Decoder {
     int BuildAll(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, bool launch);
     int FinishAll();
     void Aggregate();
+    // image index of the last call -> the decoder (this or a peer) and lane that holds it, index inside the lane
+    Lane* Locate(int image, int* local);
 
     int backend_, device_id_;
     bool initialized_ = false, prepared_ = false;

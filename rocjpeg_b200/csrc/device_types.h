@@ -8,6 +8,13 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef __CUDACC__
+#ifndef __host__
+#define __host__
+#define __device__
+#endif
+#endif
+
 namespace rjb {
 
 constexpr int kMaxBlocksPerMcu = 10;   // T.81 B.2.3
@@ -54,10 +61,16 @@ struct ImageDesc {
     uint8_t pad_[3];
     int32_t lut_set;                                  // index into the batch's HuffLutSet array
     int32_t qt_index[3];                              // index into the batch's quant-table array (natural order u16[64])
-    // entropy-coded data (destuffed, restart markers removed; see jpeg_parser.h)
-    uint64_t data_off;                                // byte offset of the image's clean stream in the scan arena
+    // entropy-coded data as uploaded (raw: byte stuffing, fill bytes and restart markers still in it)
+    uint64_t raw_off;                                 // byte offset of the image's raw bytes in the raw arena (16-byte aligned)
+    uint32_t raw_skip;                                // bytes in front of the first entropy-coded byte (0..15: whole 16-byte vectors are uploaded)
+    uint32_t raw_len;                                 // entropy-coded bytes present, up to the end of the caller's buffer (the slice ends at the first FF D9)
+    uint32_t k0_tile0;                                // first destuffing tile of this image
+    uint32_t seg_keep_lo, seg_keep_hi;                // restart intervals to decode, inclusive (region of interest; otherwise 0 .. nseg - 1)
+    // entropy-coded data destuffed by k0 (restart interval k starts at clean offset SegmentStart(r_k, k, S), see below)
+    uint64_t data_off;                                // byte offset of the image's clean stream in the scan arena (128-byte aligned)
     uint32_t seg0, nseg;                              // this image's slice of the batch segment table
-    uint32_t sub0, nsub;                              // first subsequence (multiple of the CTA size) and count
+    uint32_t sub0, nsub;                              // first subsequence (multiple of the CTA size) and count: clean capacity / S
     // coefficient store: a sparse stream of (int16 value, zig-zag index) entries in decode order
     // plus one record per block {where its entries end, DC} (stages.h: BlockRec)
     uint64_t blk0;                                    // first block of this image in the per-block arrays
@@ -71,8 +84,33 @@ struct ImageDesc {
     uint32_t plane_pitch[3];
 };
 
+// Where restart interval k of an image starts in the image's clean stream, as a function of where its
+// bytes start in the RAW stream (r = raw position just behind the k-th restart marker, 0 for k = 0) -
+// so that the destuffing pass can place every interval without knowing the lengths of the others.
+// Destuffing only removes bytes, an interval's clean length n_k is at most r_{k+1} - 2 - r_k, hence
+//   Start(k+1) - Start(k) >= (r_{k+1} - r_k) + S + 14 - (S - 1) >= n_k + 17:
+// intervals never overlap, start on a subsequence boundary (multiple of S) and leave room for the 16 zero
+// bytes the bit reader may look ahead into. Subsequence g of the image covers clean bytes [g S, (g+1) S).
+__host__ __device__ inline uint64_t SegmentStart(uint32_t r, uint32_t k, uint32_t S) {
+    return (uint64_t(r) + uint64_t(S + 14u) * k + (S - 1u)) / S * S;
+}
+// Clean-stream capacity of an image with `raw_len` raw bytes and at most `nseg` restart intervals.
+__host__ __device__ inline uint64_t CleanCapacity(uint32_t raw_len, uint32_t nseg, uint32_t S) {
+    return (SegmentStart(raw_len, nseg, S) + S + 127u) / 128u * 128u;
+}
+
+// Per-image outcome of the destuffing pass (device -> host with the status read-back).
+struct ScanStatus {
+    uint32_t segments_seen;   // restart intervals found in the bytes (restart markers + 1)
+    uint32_t scan_size;       // raw bytes up to the first FF D9 (= raw_len when there is none)
+    uint32_t flags;           // kScanNoEoi | kScanStrayMarker | kScanExtraRestarts
+    uint32_t reserved;
+};
+constexpr uint32_t kScanNoEoi = 1u, kScanStrayMarker = 2u, kScanExtraRestarts = 4u;
+
 // One restart interval ("segment") of one image: an independently decodable,
 // byte-aligned run of entropy-coded data with predictors reset (T.81 E.1.4).
+// Written by the destuffing pass (k0_destuff.cu), never by the host.
 struct SegmentDesc {
     uint64_t data_off;     // byte offset in the scan arena (16-byte aligned)
     uint32_t nbytes;       // entropy-coded bytes in the segment (excludes padding)

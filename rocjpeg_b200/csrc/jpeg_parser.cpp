@@ -5,6 +5,8 @@
 
 #include <cuda_runtime_api.h>
 
+#include <atomic>
+
 #include <string>
 
 #include <cstdlib>
@@ -65,6 +67,96 @@ uint8_t* StagingBuffer::Reserve(size_t bytes) {
     }
     ptr_ = static_cast<uint8_t*>(p);
     cap_ = want;
+    return ptr_;
+}
+
+// ------------------------------------------------------------ PinnedPool
+
+namespace {
+constexpr size_t kMinBlockLog2 = 12;               // 4 KiB
+constexpr size_t kFirstSlab = size_t(16) << 20;    // doubles up to kMaxSlab
+constexpr size_t kMaxSlab = size_t(256) << 20;
+inline int Log2Ceil(size_t v) {
+    int l = 0;
+    while ((size_t(1) << l) < v) l++;
+    return l;
+}
+}  // namespace
+
+PinnedPool& PinnedPool::Get() {
+    static PinnedPool* pool = new PinnedPool();   // never destroyed: handles may outlive static destructors
+    return *pool;
+}
+
+uint8_t* PinnedPool::Alloc(size_t bytes, size_t* cap, bool* pinned) {
+    const int cls = std::max<int>(Log2Ceil(bytes ? bytes : 1), int(kMinBlockLog2));
+    const size_t want = size_t(1) << cls;
+    std::lock_guard<std::mutex> lock(m_);
+    if (free_.size() <= size_t(cls)) free_.resize(size_t(cls) + 1);
+    *cap = want;
+    if (!free_[size_t(cls)].empty()) {
+        uint8_t* p = free_[size_t(cls)].back();
+        free_[size_t(cls)].pop_back();
+        *pinned = true;
+        return p;
+    }
+    if (!no_driver_ && slab_left_ < want) {
+        // the tail of the old slab is abandoned (at most half of it, the slabs double)
+        if (next_slab_ == 0) {
+            const char* mb = std::getenv("ROCJPEG_B200_PINNED_SLAB_MB");
+            next_slab_ = (mb && *mb) ? std::max<size_t>(1, size_t(std::atoi(mb))) << 20 : kFirstSlab;
+        }
+        const size_t slab = std::max(next_slab_, want);
+        void* p = nullptr;
+        cudaError_t e = cudaHostAlloc(&p, slab, cudaHostAllocPortable | cudaHostAllocMapped);
+        if (e == cudaSuccess && p) {
+            slab_ = static_cast<uint8_t*>(p);
+            slab_left_ = slab;
+            next_slab_ = std::min(kMaxSlab, slab * 2);
+        } else {
+            (void)cudaGetLastError();
+            if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNotSupported) no_driver_ = true;
+            slab_left_ = 0;
+        }
+    }
+    if (slab_left_ >= want) {
+        uint8_t* p = slab_;
+        slab_ += want;
+        slab_left_ -= want;
+        *pinned = true;
+        return p;
+    }
+    // no CUDA driver (host-only unit tests) or page-locking failed: pageable memory, decode still works from it
+    void* p = nullptr;
+    if (posix_memalign(&p, 4096, want) != 0) p = nullptr;
+    *pinned = false;
+    return static_cast<uint8_t*>(p);
+}
+
+void PinnedPool::Free(uint8_t* p, size_t cap, bool pinned) {
+    if (!p) return;
+    if (!pinned) {
+        std::free(p);
+        return;
+    }
+    const int cls = Log2Ceil(cap);
+    std::lock_guard<std::mutex> lock(m_);
+    if (free_.size() <= size_t(cls)) free_.resize(size_t(cls) + 1);
+    free_[size_t(cls)].push_back(p);
+}
+
+void PooledBuffer::Release() {
+    if (ptr_) PinnedPool::Get().Free(ptr_, cap_, pinned_);
+    ptr_ = nullptr;
+    cap_ = 0;
+    pinned_ = false;
+}
+
+uint8_t* PooledBuffer::Reserve(size_t bytes) {
+    if (bytes <= cap_ && ptr_) return ptr_;
+    Release();
+    ptr_ = PinnedPool::Get().Alloc(bytes, &cap_, &pinned_);
+    if (!ptr_) cap_ = 0;
     return ptr_;
 }
 
@@ -259,26 +351,25 @@ void StreamParser::DeriveGeometry() {
     }
 }
 
-// One pass over the entropy-coded bytes: finds the first FF D9 (the reference's
-// ParseEOI, parser.cpp:400-416), and on the way writes the destuffed,
-// marker-free bitstream, one 16-byte-aligned segment per restart interval.
-void StreamParser::ExtractEntropyData(const uint8_t* d, size_t begin, size_t length) {
-    p_.segments.clear();
-    p_.restart_markers_seen = 0;
-    const int64_t total_mcus = int64_t(p_.mcus_x) * p_.mcus_y;
-    const size_t expected =
-        (p_.restart_interval > 0 && total_mcus > 0) ? size_t((total_mcus + p_.restart_interval - 1) / p_.restart_interval) : 1;
-    const size_t cap = (length - begin) + (expected + 2) * 48 + 64;
-    uint8_t* out = clean_.Reserve(cap);
-    if (!out) {
-        p_.clean_bytes = 0;
-        p_.scan_size = 0;
-        return;
-    }
-    size_t o = 0, seg_start = 0, pos = begin;
+// Host restatement of the GPU destuffing pass (k0_destuff.cu) over the entropy-coded bytes `d[0, length)`:
+// finds the first FF D9 (the reference's ParseEOI, parser.cpp:400-416) and writes the destuffed,
+// marker-free bitstream, one 16-byte-aligned segment per restart interval. Rules (T.81 B.1.1.5, E.1.4;
+// the tolerant ones are this decoder's, shared with the GPU pass):
+//   FF 00 -> data byte FF;  FF FF -> the first FF is a fill byte;  FF D0..D7 -> ends the interval;
+//   FF D9 -> ends the slice;  FF xx (any other marker) -> the rest of the interval carries no data;
+//   a lone FF at the very end carries no data; intervals beyond ParsedJpeg::nseg are dropped, missing
+//   ones are empty.
+void StreamParser::ExtractEntropyData(const uint8_t* d, size_t length, HostScan* hs) const {
+    hs->segments.clear();
+    hs->restart_markers_seen = 0;
+    const size_t expected = p_.nseg;
+    const size_t cap = length + (expected + 2) * 48 + 64;
+    hs->clean.assign(cap, 0);
+    uint8_t* out = hs->clean.data();
+    size_t o = 0, seg_start = 0, pos = 0;
     bool dead = false;   // a non-restart marker was met: no more data until the next RSTn
     auto close_segment = [&]() {
-        if (p_.segments.size() < expected) p_.segments.push_back(Segment{uint32_t(seg_start), uint32_t(o - seg_start)});
+        if (hs->segments.size() < expected) hs->segments.push_back(Segment{uint32_t(seg_start), uint32_t(o - seg_start)});
         size_t padded = Align16(o) + 16;   // zero tail: the bit reader may look 16 bytes ahead
         std::memset(out + o, 0, padded - o);
         o = padded;
@@ -306,7 +397,7 @@ void StreamParser::ExtractEntropyData(const uint8_t* d, size_t begin, size_t len
             eoi = pos;
             break;
         } else if ((nx & 0xF8) == 0xD0) {
-            p_.restart_markers_seen++;
+            hs->restart_markers_seen++;
             if (o + 48 + 64 <= cap) close_segment();
             dead = false;
             pos += 2;
@@ -317,12 +408,57 @@ void StreamParser::ExtractEntropyData(const uint8_t* d, size_t begin, size_t len
             pos += 2;
         }
     }
-    if (eoi == length) eoi = length;   // no EOI: the slice runs to the end of the buffer
-    p_.scan_offset = uint32_t(begin);
-    p_.scan_size = uint32_t(eoi - begin);
+    hs->scan_size = uint32_t(eoi);   // no EOI: the slice runs to the end of the buffer
     close_segment();
-    while (p_.segments.size() < expected && o + 48 + 64 <= cap) close_segment();   // missing intervals: empty
-    p_.clean_bytes = o;
+    while (hs->segments.size() < expected && o + 48 + 64 <= cap) close_segment();   // missing intervals: empty
+    hs->clean_bytes = o;
+    hs->done = true;
+}
+
+const HostScan& StreamParser::host_scan() const {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!host_scan_.done && p_.valid && raw_.host) ExtractEntropyData(raw_.host, raw_.nbytes, &host_scan_);
+    return host_scan_;
+}
+
+namespace {
+// Is `p` page-locked host memory the device can read in place? Returns its device alias or nullptr.
+const uint8_t* DeviceAliasOf(const uint8_t* p) {
+    static std::atomic<int> no_driver{0};
+    static const bool enabled = [] {
+        const char* v = std::getenv("ROCJPEG_B200_ZERO_COPY");
+        return !(v && *v == '0');
+    }();
+    if (!enabled || no_driver.load(std::memory_order_relaxed)) return nullptr;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNotSupported) no_driver.store(1, std::memory_order_relaxed);
+        return nullptr;
+    }
+    if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) return static_cast<const uint8_t*>(at.devicePointer);
+    return nullptr;
+}
+}  // namespace
+
+// Makes the entropy-coded bytes reachable by the device: in place when the caller's buffer is page-locked,
+// otherwise through one copy into pooled page-locked staging (the only per-byte work of a parse).
+void StreamParser::AdoptSource(const uint8_t* scan, size_t nbytes) {
+    raw_ = RawScan();
+    raw_.nbytes = uint32_t(nbytes);
+    if (const uint8_t* dev = DeviceAliasOf(scan)) {
+        raw_.host = scan;
+        raw_.dev = dev;
+        raw_.zero_copy = true;
+        return;
+    }
+    uint8_t* st = staging_.Reserve(nbytes + 64);
+    if (!st) return;   // raw_.host stays null: the decode reports OUT_OF_MEMORY
+    std::memcpy(st, scan, nbytes);
+    std::memset(st + nbytes, 0xFF, 64 - (nbytes & 15));   // what the upload rounds up to
+    raw_.host = st;
+    raw_.dev = staging_.pinned() ? st : nullptr;
 }
 
 void StreamParser::BuildDecodeTables() {
@@ -335,6 +471,11 @@ void StreamParser::BuildDecodeTables() {
     else if (p_.css == CSS_UNKNOWN || p_.css == CSS_411) p_.support_status = kStatusNotSupported;
     else if (p_.bpm > kMaxBlocksPerMcu || p_.bpm < 1) p_.support_status = kStatusNotSupported;
     else if (p_.css == CSS_422 && p_.ncomp == 3 && p_.hs[1] == p_.hs[0]) p_.support_status = kStatusNotSupported;
+    // A block takes at least two bits (a DC code and an end-of-block): a frame header that announces far more
+    // blocks than the bytes present could ever hold (a 100-byte file "of" 65535 x 65535 samples) is not a
+    // truncated picture but a bad one - nothing is sized from such a header.
+    else if (uint64_t(p_.mcus_x) * uint64_t(p_.mcus_y) * uint64_t(p_.bpm) > 256ull * uint64_t(p_.raw_bytes) + 65536ull)
+        p_.support_status = kStatusBadJpeg;
     if (p_.support_status == kStatusSuccess) {
         for (int i = 0; i < p_.ncomp; i++) {
             if (!p_.qt_present[p_.tq[i]]) p_.support_status = kStatusBadJpeg;
@@ -396,11 +537,9 @@ void StreamParser::BuildDecodeTables() {
 bool StreamParser::Parse(const uint8_t* d, size_t len) {
     std::lock_guard<std::mutex> lock(mutex_);
     // the reference zeroes its parameters on every parse (parser.cpp:54)
-    std::vector<Segment> keep;
-    keep.swap(p_.segments);
     p_ = ParsedJpeg();
-    p_.segments.swap(keep);
-    p_.segments.clear();
+    raw_ = RawScan();
+    host_scan_.done = false;
     err_.clear();
     if (!d || len < 4) return Fail("stream too short");
     if (d[0] != 0xFF || d[1] != 0xD8) return Fail("missing SOI");                   // parser.cpp:64
@@ -450,8 +589,14 @@ bool StreamParser::Parse(const uint8_t* d, size_t len) {
     if (!seen_dht) return Fail("no Huffman table before SOS");                     // parser.cpp:111-118
     if (!seen_dqt) return Fail("no quantisation table before SOS");
     DeriveGeometry();
-    ExtractEntropyData(d, p, len);
+    p_.scan_offset = uint32_t(p);
+    p_.raw_bytes = uint32_t(len - p);
+    // restart intervals: what the frame needs, bounded by what the bytes can hold (a marker is two bytes)
+    const uint64_t total_mcus = uint64_t(p_.mcus_x) * uint64_t(p_.mcus_y);
+    const uint64_t by_header = (p_.restart_interval > 0 && total_mcus > 0) ? (total_mcus + uint64_t(p_.restart_interval) - 1) / uint64_t(p_.restart_interval) : 1;
+    p_.nseg = uint32_t(std::min<uint64_t>(by_header, uint64_t(p_.raw_bytes) / 2 + 1));
     BuildDecodeTables();
+    AdoptSource(d + p, len - p);
     p_.valid = true;
     return true;
 }

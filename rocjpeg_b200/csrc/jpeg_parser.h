@@ -7,15 +7,22 @@
 // and one DQT before SOS, entropy-coded slice = bytes up to the first FF D9),
 // plus bounds checks (the reference reads past the end of truncated input).
 //
-// Extended for the CUDA back end (BASELINE north star, item 2): while it makes
-// the one pass over the entropy-coded bytes that the reference already makes to
-// find FF D9 (src/rocjpeg_parser.cpp:400-416), it also
-//   * removes byte stuffing (FF 00 -> FF) and restart markers, writing a clean
-//     bitstream into page-locked memory owned by the stream handle;
-//   * records every restart interval as a 16-byte-aligned segment (offset,
-//     length) of that clean stream;
-//   * builds the decoder-form Huffman tables (first-level LUT + canonical slow
+// Extended for the CUDA back end (BASELINE north star, item 2). Parsing costs a
+// header walk, nothing proportional to the picture:
+//   * the entropy-coded bytes are NOT touched on the host. The reference makes one
+//     byte-serial pass over them to find FF D9 (src/rocjpeg_parser.cpp:400-416);
+//     here that pass - together with the removal of byte stuffing (FF 00 -> FF),
+//     fill bytes and restart markers and the discovery of the restart intervals -
+//     runs on the GPU (k0_destuff.cu), on the raw bytes as uploaded. The parser only
+//     makes the bytes reachable by the device: a caller buffer that is already
+//     page-locked (cudaHostAlloc / cudaHostRegister / hipHostMalloc through the
+//     shim) is used in place, anything else is copied once into page-locked
+//     staging taken from a process-wide pool;
+//   * it builds the decoder-form Huffman tables (two-level LUT + canonical slow
 //     path) and natural-order quantisation tables.
+// The host restatement of the same destuffing rules (HostScan) is kept for the
+// parser taps, the K1 schedule model and as the expected value of the GPU pass in
+// the tests; the decode path never calls it.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -47,6 +54,44 @@ class StagingBuffer {
     bool pinned_ = false;
 };
 
+// Process-wide pool of page-locked host memory (cudaHostAlloc, portable + mapped) handed out in
+// power-of-two blocks: stream handles that receive pageable input stage it here. One slab
+// allocation serves hundreds of handles (a cudaHostAlloc per handle was 32 ms for 256 handles).
+class PinnedPool {
+  public:
+    static PinnedPool& Get();
+    // Returns a block of at least `bytes` (capacity in *cap); pageable memory when no CUDA driver
+    // is present (*pinned = false; host-only unit tests).
+    uint8_t* Alloc(size_t bytes, size_t* cap, bool* pinned);
+    void Free(uint8_t* p, size_t cap, bool pinned);
+
+  private:
+    PinnedPool() = default;
+    std::mutex m_;
+    std::vector<std::vector<uint8_t*>> free_;   // by size class (log2)
+    uint8_t* slab_ = nullptr;
+    size_t slab_left_ = 0, next_slab_ = 0;
+    bool no_driver_ = false;
+};
+
+// Grow-only block from the pool.
+class PooledBuffer {
+  public:
+    PooledBuffer() = default;
+    ~PooledBuffer() { Release(); }
+    PooledBuffer(const PooledBuffer&) = delete;
+    PooledBuffer& operator=(const PooledBuffer&) = delete;
+    uint8_t* Reserve(size_t bytes);   // contents are NOT preserved across growth
+    void Release();
+    uint8_t* data() const { return ptr_; }
+    bool pinned() const { return pinned_; }
+
+  private:
+    uint8_t* ptr_ = nullptr;
+    size_t cap_ = 0;
+    bool pinned_ = false;
+};
+
 struct HuffSpec {
     uint8_t bits[16];
     uint8_t vals[256];
@@ -69,7 +114,9 @@ struct ParsedJpeg {
     int32_t scan_ncomp = 0, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
     int32_t restart_interval = 0;
     uint32_t num_mcus_ref = 0;                    // the reference's num_mcus (parser.cpp:197)
-    uint32_t scan_offset = 0, scan_size = 0;      // slice inside the caller's buffer (parser.cpp:400-416)
+    uint32_t scan_offset = 0;                     // first entropy-coded byte inside the caller's buffer (parser.cpp:400-416)
+    uint32_t raw_bytes = 0;                       // from there to the end of the caller's buffer (the slice ends at the first
+                                                  // FF D9, which the GPU pass finds; HostScan::scan_size on the host)
     uint8_t qt[4][64] = {};                       // zig-zag order, as in the stream
     bool qt_present[4] = {false, false, false, false};
     HuffSpec dc[2] = {}, ac[2] = {};
@@ -81,9 +128,25 @@ struct ParsedJpeg {
     uint16_t qt_natural[4][64] = {};              // de-zig-zagged quantiser steps
     uint64_t lut_hash = 0;                        // identity of the four Huffman tables (batch de-duplication)
     uint32_t min_entry_bits = 2;                  // fewest bits a symbol with magnitude bits can take (bounds the entry count)
-    std::vector<Segment> segments;                // one per restart interval (exactly ceil(mcus / Ri))
-    size_t clean_bytes = 0;                       // bytes used in `clean`
+    uint32_t nseg = 1;                            // restart intervals the scan can hold: ceil(mcus / Ri), bounded by the bytes present
+};
+
+// Where the entropy-coded bytes of the last parsed stream are, for the upload.
+struct RawScan {
+    const uint8_t* host = nullptr;   // first entropy-coded byte: inside the caller's buffer (zero-copy) or the handle's staging
+    const uint8_t* dev = nullptr;    // the same byte as the device sees it (page-locked memory); nullptr: pageable, copy with cudaMemcpy
+    uint32_t nbytes = 0;
+    bool zero_copy = false;          // `host` is the caller's own page-locked buffer
+};
+
+// Host restatement of the destuffing pass (tests, taps, schedule model - never the decode path).
+struct HostScan {
+    bool done = false;
+    uint32_t scan_size = 0;                       // bytes up to the first FF D9 (the reference's slice size)
     uint32_t restart_markers_seen = 0;
+    std::vector<Segment> segments;                // one per restart interval (exactly ParsedJpeg::nseg)
+    std::vector<uint8_t> clean;                   // destuffed bytes, 16-byte-aligned segments, zero padded
+    size_t clean_bytes = 0;
 };
 
 class StreamParser {
@@ -91,7 +154,10 @@ class StreamParser {
     // Returns false for streams the reference parser rejects (-> BAD_JPEG).
     bool Parse(const uint8_t* data, size_t length);
     const ParsedJpeg& parsed() const { return p_; }
-    const StagingBuffer& clean() const { return clean_; }
+    const RawScan& raw() const { return raw_; }
+    // Destuffed restart intervals computed on the host from the bytes Parse() was given (which must still
+    // be valid, as the reference requires until the decode returns).
+    const HostScan& host_scan() const;
     const HuffLutSet& lut() const { return lut_; }   // decoder-form tables of the last parsed stream
     const std::string& last_error() const { return err_; }
 
@@ -102,16 +168,19 @@ class StreamParser {
     bool ParseDqt(const uint8_t* s, uint32_t seglen);
     bool ParseSos(const uint8_t* s, uint32_t seglen);
     void DeriveGeometry();
-    void ExtractEntropyData(const uint8_t* d, size_t begin, size_t length);
+    void ExtractEntropyData(const uint8_t* d, size_t length, HostScan* out) const;
     void BuildDecodeTables();
+    void AdoptSource(const uint8_t* scan, size_t nbytes);
 
-    std::mutex mutex_;
+    mutable std::mutex mutex_;
     ParsedJpeg p_;
     HuffLutSet lut_ = {};             // kept across parses while the DHT content does not change
     HuffSpec lut_spec_dc_[2] = {}, lut_spec_ac_[2] = {};
     uint64_t lut_spec_hash_ = 0;
     bool lut_valid_ = false;
-    StagingBuffer clean_;
+    RawScan raw_;
+    PooledBuffer staging_;            // page-locked copy of pageable input
+    mutable HostScan host_scan_;
     std::string err_;
 };
 

@@ -238,8 +238,12 @@ __device__ __forceinline__ uint32_t DecodeCount(uint32_t slot_sa, const LutView&
     return PackState(acc & 63u, int((uint32_t(StateC(key)) + nb) % uint32_t(bpm)), int((acc >> 21) & 63u), nb > 0xFFFFu ? 0xFFFFu : nb);
 }
 
-// Per-thread description of its subsequence.
+// Per-thread description of its subsequence. Subsequence g of an image covers bytes [g S, (g+1) S) of the
+// image's clean stream; the destuffing pass starts every restart interval on a multiple of S
+// (device_types.h: SegmentStart), so a subsequence belongs to one interval, and the few that fall into the
+// gap between two intervals map to no data.
 struct Sub {
+    bool in_range;     // inside the image's subsequence range
     bool active;       // maps to real data
     bool first;        // first subsequence of its segment (state known exactly)
     bool last;         // last subsequence of its segment
@@ -251,7 +255,7 @@ struct Sub {
 template <int S>
 __device__ __forceinline__ Sub Locate(const K1Args& a, const ImageDesc& im, int64_t gi, bool use_cache) {
     Sub s;
-    s.active = gi >= int64_t(im.sub0) && gi < int64_t(im.sub0) + int64_t(im.nsub);
+    s.in_range = s.active = gi >= int64_t(im.sub0) && gi < int64_t(im.sub0) + int64_t(im.nsub);
     s.first = s.last = false;
     s.seg = 0;
     s.end_bit = 0;
@@ -274,6 +278,7 @@ __device__ __forceinline__ Sub Locate(const K1Args& a, const ImageDesc& im, int6
     const uint32_t j = g - sd.sub0;
     const uint32_t nchunks = (sd.nbytes + S - 1) / S;
     s.seg = k;
+    s.active = j < nchunks;   // behind the interval's last byte (or the interval is empty / not wanted): no data
     s.first = (j == 0);
     s.last = (j + 1 >= nchunks);
     const uint32_t off = j * S;
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters)
     const bool owned = tid >= H;
     Sub me = Locate<S>(a, im, gi, round > 0);
     if (round > 0 && !owned) me.active = false;   // later rounds read the owner's state instead of a halo
-    if (round == 0 && owned && me.active) a.sub_seg[g] = me.seg;
+    if (round == 0 && owned && me.in_range) a.sub_seg[g] = me.seg;
     if (round == 0) {
         // this CTA's share of the batch's block records starts as "never decoded": blocks a damaged stream
         // does not reach, or a region of interest leaves out, then decode as zero
@@ -656,6 +661,11 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
         }
     }
     __syncthreads();
+    if (tid == 0) {   // statistics: coefficient entries the batch writes (pads included), read back with the round counters
+        uint32_t t = 0;
+        for (int w = 0; w < kW; w++) t += wents[w];
+        if (t) atomicAdd(&a.counters[2 * kMaxSyncRounds], t);
+    }
     uint32_t add = 0, eadd = carry_s[1];
     bool open = (f == 0);   // no segment start at or before this thread inside its warp
     for (int w = warp - 1; w >= 0; w--) {

@@ -1,6 +1,9 @@
-// stages.h — host-callable launchers of the three CUDA stages.
+// stages.h — host-callable launchers of the CUDA stages.
 //
 // These replace, for a whole batch per launch:
+//   K0 (k0_destuff.cu)  the byte-serial FF D9 search of the reference's parser
+//                       (src/rocjpeg_parser.cpp:400-416) and the destuffing / restart-marker
+//                       handling VCN does on the slice it is given
 //   K1 (k1_huffman.cu)  the Huffman decode done by VCN fixed function in the
 //                       reference (src/rocjpeg_vaapi_decoder.cpp:677-689, 816-828)
 //   K2 (k2_idct.cu)     the dequantise + IDCT done by VCN fixed function (same call sites)
@@ -49,6 +52,7 @@ inline cudaError_t LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 }
 #endif
 
+constexpr int kK0TileBytes = 4096;   // raw bytes per destuffing tile (one CTA, 16 bytes per thread)
 constexpr int kK1Threads = 128;      // threads per CTA in K1, one subsequence each
 constexpr int kDcImageMaxMcus = 4096;   // pictures up to this many MCUs take the one-launch DC integration
 // K1Args::halo leading threads of a CTA re-decode the previous CTA's last subsequences; the CTA owns the
@@ -68,6 +72,23 @@ struct BlockRec {
     int16_t dc;
     int16_t pad_;
 };
+
+struct K0Args {
+    const ImageDesc* images;      // device
+    SegmentDesc* segments;        // device, written here: the batch's segment table
+    const uint32_t* img_tile0;    // device, nimages + 1 entries: first destuffing tile of each image
+    const uint8_t* raw;           // device raw arena (bytes as uploaded)
+    uint8_t* clean;               // device scan arena (destuffed)
+    uint4* tile_sum;              // per tile: prefix element of the tile
+    uint4* tile_carry;            // per tile: prefix element of everything before it in its image
+    ScanStatus* status;           // per image
+    int nimages;
+    uint32_t total_tiles;
+    int sub_bytes;                // S of the batch: intervals start on multiples of S
+};
+// Destuffing + restart-interval discovery + segment table for the whole batch (three launches).
+cudaError_t LaunchK0Destuff(const K0Args& a, cudaStream_t stream);
+cudaError_t PreloadK0();
 
 struct K1Args {
     const ImageDesc* images;      // device

@@ -1,0 +1,146 @@
+// k0_model.cpp — CPU model of the K0 (destuffing) schedule (TEST TOOL, not product, not oracle).
+//
+// Runs the product's own parser (csrc/jpeg_parser.cpp) for the header and the product's own per-piece
+// logic (csrc/k0_core.cuh, compiled for the host) through a serial emulation of what k0_destuff.cu does
+// in parallel: 16-byte pieces, tiles of 256 pieces, Kogge-Stone warp scans + warp totals inside a tile
+// (k0_reduce / k0_apply), a chunked scan over the tiles of the image (k0_scan), then the scatter walk of
+// every piece and the segment table. The no-GPU suite compares its result with the host restatement of
+// the same rules (StreamParser::host_scan); the CUDA kernels themselves - including their warp-level
+// fast path, which this model does not have - are checked by the -m gpu tests against the same.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "jpeg_parser.h"
+#include "k0_core.cuh"
+
+using namespace rjb;
+using namespace rjb::k0;
+
+namespace {
+constexpr int kThreads = 256, kTile = 4096;
+
+// the kernels' CtaScan: inclusive Kogge-Stone per warp of 32, then the warp totals
+void CtaScanModel(const std::vector<Elem>& e, std::vector<Elem>* excl, Elem* total) {
+    const size_t n = e.size();   // kThreads
+    std::vector<Elem> inc(e);
+    for (size_t w0 = 0; w0 < n; w0 += 32)
+        for (int d = 1; d < 32; d <<= 1) {
+            std::vector<Elem> prev(inc.begin() + long(w0), inc.begin() + long(w0) + 32);
+            for (int l = d; l < 32; l++) inc[w0 + size_t(l)] = Combine(prev[size_t(l - d)], prev[size_t(l)]);
+        }
+    excl->assign(n, Elem{0, 0, 0, 0});
+    Elem pre{0, 0, 0, 0};
+    for (size_t w0 = 0; w0 < n; w0 += 32) {
+        for (int l = 0; l < 32; l++) (*excl)[w0 + size_t(l)] = Combine(pre, l ? inc[w0 + size_t(l) - 1] : Elem{0, 0, 0, 0});
+        pre = Combine(pre, inc[w0 + 31]);
+    }
+    *total = pre;
+}
+
+struct HostMem {
+    std::vector<SegmentDesc>* segs;
+    uint8_t* clean;
+    ScanStatus* status;
+    uint32_t* fill_from;
+    SegmentDesc& Segment(uint32_t k) const { return (*segs)[k]; }
+    uint8_t* Clean() const { return clean; }
+    void Finish(const ScanStatus& st, uint32_t from) const {
+        *status = st;
+        *fill_from = from;
+    }
+};
+}  // namespace
+
+// Destuffs the scan of `data` as the device would with subsequence size S, the scan starting `skip` bytes into a
+// 16-byte vector, restart intervals [keep_lo, keep_hi] wanted. Outputs per restart interval: clean length, offset in
+// the clean stream, first subsequence; the clean stream itself (clean_cap bytes available, pre-filled by the caller);
+// status4 = {segments seen, scan size, flags, nseg}. Returns 0, or a negative RocJpegStatus.
+extern "C" int k0_model_destuff(const uint8_t* data, size_t len, int S, int skip, uint32_t keep_lo, uint32_t keep_hi, uint32_t* seg_nbytes,
+                                uint64_t* seg_off, uint32_t* seg_sub0, size_t seg_cap, uint8_t* clean, size_t clean_cap, uint32_t* status4) {
+    StreamParser parser;
+    if (!parser.Parse(data, len)) return -3;
+    const ParsedJpeg& p = parser.parsed();
+    if (p.support_status != 0) return p.support_status;
+    const RawScan& rs = parser.raw();
+    ImageDesc im = {};
+    im.restart_interval = p.restart_interval;
+    im.total_mcus = p.mcus_x * p.mcus_y;
+    im.bpm = p.bpm;
+    im.raw_skip = uint32_t(skip & 15);
+    im.raw_len = rs.nbytes;
+    im.nseg = p.nseg;
+    im.seg_keep_lo = keep_lo;
+    im.seg_keep_hi = keep_hi;
+    im.data_off = 0;
+    im.sub0 = 0;
+    const uint64_t cap = CleanCapacity(rs.nbytes, p.nseg, uint32_t(S));
+    im.nsub = uint32_t(cap / uint32_t(S));
+    if (cap > clean_cap || p.nseg > seg_cap) return -2;
+    // the uploaded bytes: junk in front (the 16-byte vector the scan starts in) and behind
+    const size_t up = (size_t(im.raw_skip) + rs.nbytes + 15) / 16 * 16;
+    std::vector<uint8_t> raw(up + 32, 0xFF);
+    for (size_t i = 0; i < im.raw_skip; i++) raw[i] = uint8_t(0xFF - (i & 1) * 0x27);   // FF D8 FF D8 ...: must be ignored
+    std::memcpy(raw.data() + im.raw_skip, rs.host, rs.nbytes);
+    for (size_t i = size_t(im.raw_skip) + rs.nbytes; i < raw.size(); i++) raw[i] = (i & 1) ? 0xD9 : 0x00;
+    const size_t ntiles = std::max<size_t>(1, (size_t(im.raw_skip) + rs.nbytes + kTile - 1) / kTile);
+    auto load = [&](size_t off) {
+        const int64_t pos0 = int64_t(off) - int64_t(im.raw_skip), L = int64_t(im.raw_len);
+        uint32_t w[4] = {0, 0, 0, 0}, prev = 0, next = 0xFF;
+        if (PieceOverlaps(pos0, L)) {
+            std::memcpy(w, raw.data() + off, 16);
+            if (pos0 > 0) prev = raw[off - 1];
+            if (pos0 + 16 < L) next = raw[off + 16];
+        }
+        return ClassifyPiece(w, prev, next, pos0, L);
+    };
+    // k0_reduce
+    std::vector<Elem> tile_sum(ntiles), tile_carry(ntiles);
+    std::vector<Elem> e(kThreads), ex;
+    for (size_t t = 0; t < ntiles; t++) {
+        for (int i = 0; i < kThreads; i++) e[size_t(i)] = PieceElem(load(t * kTile + size_t(i) * 16));
+        CtaScanModel(e, &ex, &tile_sum[t]);
+    }
+    // k0_scan
+    Elem carry{0, 0, 0, 0};
+    for (size_t base = 0; base < ntiles; base += kThreads) {
+        for (int i = 0; i < kThreads; i++) e[size_t(i)] = base + size_t(i) < ntiles ? tile_sum[base + size_t(i)] : Elem{0, 0, 0, 0};
+        Elem tot;
+        CtaScanModel(e, &ex, &tot);
+        for (int i = 0; i < kThreads && base + size_t(i) < ntiles; i++) tile_carry[base + size_t(i)] = Combine(carry, ex[size_t(i)]);
+        carry = Combine(carry, tot);
+    }
+    // k0_apply
+    std::vector<SegmentDesc> segs(p.nseg, SegmentDesc{0xDEADBEEFull, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    ScanStatus status = {0xFFFFFFFFu, 0, 0, 0};
+    uint32_t fill_from = 0xFFFFFFFFu;
+    HostMem mem{&segs, clean, &status, &fill_from};
+    const Placer<HostMem> pl{im, uint32_t(S), mem};
+    for (size_t t = 0; t < ntiles; t++) {
+        std::vector<Piece> pcs;
+        for (int i = 0; i < kThreads; i++) {
+            pcs.push_back(load(t * kTile + size_t(i) * 16));
+            e[size_t(i)] = PieceElem(pcs.back());
+        }
+        Elem tot;
+        CtaScanModel(e, &ex, &tot);
+        for (int i = 0; i < kThreads; i++) {
+            const Elem x = Combine(tile_carry[t], ex[size_t(i)]);
+            if (!(x.flags & kEnded) && pcs[size_t(i)].any) WalkPiece(pcs[size_t(i)], x, e[size_t(i)], pl);
+            FinishPiece(pcs[size_t(i)], x, e[size_t(i)], pl, t == 0 && i == 0);
+        }
+    }
+    if (fill_from == 0xFFFFFFFFu) return -8;   // nobody closed the slice: a bug in the schedule
+    for (uint32_t q = fill_from; q < im.nseg; q++) pl.Missing(q);
+    for (uint32_t k = 0; k < p.nseg; k++) {
+        seg_nbytes[k] = segs[k].nbytes;
+        seg_off[k] = segs[k].data_off;
+        seg_sub0[k] = segs[k].sub0;
+    }
+    status4[0] = status.segments_seen;
+    status4[1] = status.scan_size;
+    status4[2] = status.flags;
+    status4[3] = p.nseg;
+    return 0;
+}

@@ -66,7 +66,8 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     if (!parser.Parse(data, len)) return -3;
     const ParsedJpeg& p = parser.parsed();
     if (p.support_status != 0) return p.support_status;
-    const uint8_t* clean = parser.clean().data();
+    const HostScan& hscan = parser.host_scan();   // the host restatement of the destuffing pass (the device runs k0_destuff.cu)
+    const uint8_t* clean = hscan.clean.data();
     const int bpm = p.bpm;
     uint8_t mcu_comp[kMaxBlocksPerMcu], mcu_dc[kMaxBlocksPerMcu], mcu_ac[kMaxBlocksPerMcu];
     int comp_first[3] = {0, 0, 0};
@@ -86,8 +87,8 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     // subsequences
     std::vector<SubInfo> subs;
     std::vector<uint32_t> seg_blk_first, seg_blk_count;
-    for (size_t s = 0; s < p.segments.size(); s++) {
-        const Segment& sg = p.segments[s];
+    for (size_t s = 0; s < hscan.segments.size(); s++) {
+        const Segment& sg = hscan.segments[s];
         uint32_t n = (sg.nbytes + S - 1) / S;
         uint64_t mf = uint64_t(s) * ri;
         uint64_t mc = mf >= total_mcus ? 0 : std::min<uint64_t>(ri, total_mcus - mf);
@@ -191,7 +192,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
     const uint32_t nblocks = total_mcus * uint32_t(bpm);
     // the entry arena is NOT cleared on the device: start from garbage; per-block indices start
     // as "never decoded"
-    const uint32_t cap = uint32_t(uint64_t(p.clean_bytes) * 8 / p.min_entry_bits + 7 * (uint64_t(p.clean_bytes) / 32 + p.segments.size() + 1) + 64);
+    const uint32_t cap = uint32_t(uint64_t(hscan.clean_bytes) * 8 / p.min_entry_bits + 7 * (uint64_t(hscan.clean_bytes) / 32 + hscan.segments.size() + 1) + 64);
     std::vector<uint32_t> entries(cap, 0x77777777u), blk_end(size_t(nblocks), 0xFFFFFFFFu);
     std::vector<int16_t> dcdiff(nblocks, int16_t(0x7777));
     uint32_t ent_run = 0;

@@ -192,11 +192,28 @@ def test_crop_with_restart_markers_skips_entropy_work(dec, orc, css):
         st, got, want = gu.decode_one(dec, orc, data, fmt, crop=crop)
         assert st == api.SUCCESS
         gu.assert_same(got, want, f"dri crop {css} {fmt}")
-    cropped = dec.stats().subsequences
+    cropped = sum(dec.stats().decodes_per_round)
     st, got, want = gu.decode_one(dec, orc, data, "rgb")
     assert st == api.SUCCESS
     gu.assert_same(got, want, f"dri full {css}")
-    assert cropped < dec.stats().subsequences
+    assert cropped < sum(dec.stats().decodes_per_round)
+
+
+@pytest.mark.parametrize("css", ["420", "444", "400"])
+@pytest.mark.parametrize("dri", ["row", "one"])
+def test_crop_that_starts_at_the_first_column_of_a_restart_interval(dec, orc, css, dri):
+    """A crop whose first MCU row is the first row of a restart interval, at column 0: the first block of the first
+    wanted interval must keep its AC coefficients although the intervals above the crop are not decoded (its entries
+    begin where the block before it ends - the interval in front of the first wanted one is kept decoded)."""
+    w, h = 320, 240
+    mcu_h = 8 if css in ("444", "400") else 16
+    kw = dict(restart_rows=1) if dri == "row" else dict(restart_mcus=1)
+    data = datagen.make_jpeg(w, h, css, seed=23, **kw)
+    for crop in ((0, mcu_h, w, h), (0, 3 * mcu_h, 64, 5 * mcu_h), (2, 2 * mcu_h, 130, 2 * mcu_h + 9)):
+        for fmt in ("rgb", "yuv_planar"):
+            st, got, want = gu.decode_one(dec, orc, data, fmt, crop=crop)
+            assert st == api.SUCCESS
+            gu.assert_same(got, want, f"{css} dri={dri} crop={crop} {fmt}")
 
 
 @pytest.mark.parametrize("css", ["444", "440", "422", "420", "400"])
@@ -352,6 +369,118 @@ def test_prepare_run_matches_decode(dec, orc):
     assert st.total_ms > 0 and all(m >= 0 for m in st.stage_ms)
     _, want = gu.oracle_outputs(orc, data, "rgb", (0, 0, 0, 0), pitches)
     gu.assert_same(gu.fetch(bufs, pitches, shapes), want, "prepare/run")
+
+
+# ------------------------------------------------------------ K0: GPU destuffing / end of slice / restart intervals
+
+def _pinned_copies(datas, lead=0):
+    """The files in one page-locked arena, file i starting `lead + i` bytes (mod 16) off a 16-byte boundary."""
+    import torch
+
+    offs, total = [], 0
+    for i, d in enumerate(datas):
+        total = (total + 63) // 64 * 64 + ((lead + i) & 15)
+        offs.append(total)
+        total += len(d)
+    arena = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
+    a = arena.numpy()
+    a[:] = 0xFF
+    for o, d in zip(offs, datas):
+        a[o:o + len(d)] = np.frombuffer(d, np.uint8)
+    return arena, [arena.data_ptr() + o for o in offs]
+
+
+def _check_destuffed_batch(dec, datas, zero_copy, fmt="y"):
+    import torch
+
+    arena, addrs = _pinned_copies(datas, lead=3) if zero_copy else (None, None)
+    streams, dests, keep = [], [], []
+    for i, d in enumerate(datas):
+        s = api.JpegStream()
+        assert (s.parse_ptr(addrs[i], len(d), arena) if zero_copy else s.parse(d)) == api.SUCCESS
+        inf = s.info()
+        assert bool(inf.source_is_zero_copy) == zero_copy and inf.source_is_device_visible
+        buf = torch.zeros(inf.width * inf.height * 3 + 64, dtype=torch.uint8, device="cuda")
+        streams.append(s); keep.append(buf)
+        dests.append([(buf.data_ptr(), inf.width), (buf.data_ptr() + inf.width * inf.height, inf.width),
+                      (buf.data_ptr() + 2 * inf.width * inf.height, inf.width)])
+    st = dec.decode_batched(streams, api.make_params(fmt), dests)
+    assert st == api.SUCCESS, st
+    for i, (s, d) in enumerate(zip(streams, datas)):
+        hs, inf, ds = s.host_scan(), s.info(), dec.scan_status(i)
+        assert ds.scan_size == hs.scan_size, (i, ds.scan_size, hs.scan_size)
+        assert ds.segments_seen == hs.restart_markers_seen + 1
+        assert bool(ds.flags & api.SCAN_NO_EOI) == (hs.scan_size == inf.raw_bytes)
+        for k in range(inf.num_segments):
+            assert dec.device_segment(i, k) == s.segment(k), f"image {i} restart interval {k} of {inf.num_segments}"
+
+
+@pytest.mark.parametrize("zero_copy", [True, False])
+def test_gpu_destuffing_matches_the_host_restatement_on_every_fixture(dec, zero_copy):
+    _check_destuffed_batch(dec, [load(n) for n in CASES], zero_copy)
+
+
+@pytest.mark.parametrize("zero_copy", [True, False])
+@pytest.mark.parametrize("S", [32, 128])
+def test_gpu_destuffing_marker_patterns(dec, zero_copy, S, monkeypatch):
+    """The hand-made and random scans of the host-model tests (tests/test_host_library.py) through the kernels: stuffed
+    FF / fill bytes / restart markers / stray markers / early, missing and repeated EOI at every piece, warp and tile
+    boundary. Whatever such bytes decode to, the destuffed restart intervals must equal the host restatement."""
+    from test_host_library import _scan_with
+
+    monkeypatch.setenv("ROCJPEG_B200_SUBSEQ", str(S))
+    rng = np.random.default_rng(5)
+    body = lambda n: bytes(int(x) for x in rng.integers(0, 255, n))
+    scans = [
+        b"", b"\xFF", b"\xFF\xD9", b"\x12\xFF\x00\x34\xFF\xD9", b"\xFF\x00" * 40 + b"\xFF\xD9",
+        b"\xFF\xFF\xFF\x00\x55\xFF\xFF\xD0\x66\xFF\xFF\xFF\xD9",
+        body(15) + b"\xFF\x00" + body(14) + b"\xFF\x00" + body(100) + b"\xFF\xD9",
+        body(4095) + b"\xFF\x00" + body(5000) + b"\xFF\xD9",
+        body(4094) + b"\xFF\xD0" + body(3) + b"\xFF\xD1" + body(4090) + b"\xFF\xD2" + body(10),
+        body(510) + b"\xFF\xD3" + body(700) + b"\xFF\xD3" + body(9) + b"\xFF\xD9",
+        body(100) + b"\xFF\xE0" + body(50) + b"\xFF\xD0" + body(60) + b"\xFF\xC4" + body(5) + b"\xFF\x00" + body(5) + b"\xFF\xD9",
+        body(30) + b"\xFF\xD9" + body(40) + b"\xFF\xD0" + body(30) + b"\xFF\xD9",
+        b"".join(body(int(rng.integers(0, 40))) + b"\xFF" + bytes([0xD0 + (k & 7)]) for k in range(200)) + b"\xFF\xD9",
+        b"".join(body(int(rng.integers(0, 3))) + b"\xFF" + bytes([int(rng.choice([0, 0, 0xFF, 0xD0, 0xD5, 0xE1]))]) for k in range(3000)) + b"\xFF",
+        body(20000),
+    ]
+    alphabet = np.array([0xFF] * 6 + [0x00] * 3 + [0xD0, 0xD1, 0xD7, 0xD9, 0xC4, 0xDA] + list(range(1, 60)), np.uint8)
+    for n in (1, 15, 16, 17, 511, 512, 513, 4095, 4096, 4097, 12289, 70001):
+        scans.append(bytes(rng.choice(alphabet, n)))
+        scans.append(bytes(rng.choice(alphabet, n)).replace(b"\xFF\xD9", b"\xFF\x00"))
+    for base in ("synth_420_123x77_dri", "synth_444_123x77"):
+        _check_destuffed_batch(dec, [_scan_with(load(base), sc) for sc in scans], zero_copy)
+    # the decoder is still healthy
+    import oracle as _o
+
+    orc = _o.Oracle()
+    st, got, want = gu.decode_one(dec, orc, load("synth_420_500x375_dri7"), "rgb")
+    assert st == api.SUCCESS
+    gu.assert_same(got, want, "clean decode after the marker patterns")
+
+
+def test_zero_copy_and_staged_sources_decode_identically(dec, orc):
+    """JPEG files in the caller's page-locked memory are uploaded in place (any byte alignment), files in pageable memory
+    through the staging pool; trailing bytes behind the EOI, and a second picture behind the first, are ignored."""
+    names = ["synth_420_500x375_dri7", "synth_444_500x375", "mug_422_crop_dri1", "synth_400_333x211"]
+    datas = [load(n) for n in names]
+    datas.append(datas[1] + b"\x00" * 777 + datas[0])            # e.g. an MPO file: the first FF D9 ends the slice
+    datas.append(datas[2] + bytes(range(256)) * 3)
+    for lead in (0, 1, 7, 15):
+        arena, addrs = _pinned_copies(datas, lead)
+        for zero_copy in (True, False):
+            streams, dests, keep = [], [], []
+            for i, d in enumerate(datas):
+                s = api.JpegStream()
+                assert (s.parse_ptr(addrs[i], len(d), arena) if zero_copy else s.parse(d)) == api.SUCCESS
+                rc, info = orc.parse(d)
+                dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "rgb", (0, 0, 0, 0))
+                streams.append(s); dests.append(dest); keep.append((bufs, pitches, shapes))
+            assert dec.decode_batched(streams, api.make_params("rgb"), dests) == api.SUCCESS
+            for i, d in enumerate(datas):
+                bufs, pitches, shapes = keep[i]
+                _, want = gu.oracle_outputs(orc, d, "rgb", (0, 0, 0, 0), pitches)
+                gu.assert_same(gu.fetch(bufs, pitches, shapes), want, f"lead={lead} zero_copy={zero_copy} image {i}")
 
 
 # ------------------------------------------------------------ BASELINE.json shapes

@@ -90,7 +90,9 @@ def test_parser_matches_oracle(lib, orc, name):
     rc, o = orc.parse(data)
     assert rc == 0
     assert (i.width, i.height, i.num_components, i.chroma_subsampling) == (o.width, o.height, o.ncomp, o.css)
-    assert (i.scan_offset, i.scan_size, i.restart_interval, i.num_mcus) == (o.scan_offset, o.scan_size, o.restart_interval, o.num_mcus_ref)
+    hs = s.host_scan()   # rocJpegStreamParse itself never touches the entropy-coded bytes: the GPU finds the end of the slice
+    assert (i.scan_offset, hs.scan_size, i.restart_interval, i.num_mcus) == (o.scan_offset, o.scan_size, o.restart_interval, o.num_mcus_ref)
+    assert i.raw_bytes == len(data) - o.scan_offset
     assert (i.mcus_x, i.mcus_y, i.blocks_per_mcu) == (o.mcus_x, o.mcus_y, o.blocks_per_mcu)
     for c in range(o.ncomp):
         assert (i.h_sampling[c], i.v_sampling[c], i.quant_selector[c], i.dc_selector[c], i.ac_selector[c]) == (
@@ -106,7 +108,7 @@ def test_parser_matches_oracle(lib, orc, name):
             bits, vals = s.huffman_table(1, t)
             assert bits == bytes(o.ac_bits[t]) and vals == bytes(o.ac_vals[t])[:len(vals)]
     assert i.decode_status == orc.supported(o)
-    assert i.restart_markers_seen == o.n_restart_markers
+    assert hs.restart_markers_seen == o.n_restart_markers
     # destuffed segments == an independent restatement of T.81 B.1.1.5 / E.1.4
     scan = data[o.scan_offset:o.scan_offset + o.scan_size]
     segs, cur, k = [], bytearray(), 0
@@ -124,7 +126,7 @@ def test_parser_matches_oracle(lib, orc, name):
     segs.append(bytes(cur))
     total = o.mcus_x * o.mcus_y
     expected = (total + o.restart_interval - 1) // o.restart_interval if o.restart_interval else 1
-    assert i.num_segments == expected == len(segs)
+    assert i.num_segments == hs.num_segments == expected == len(segs)
     assert [s.segment(j) for j in range(i.num_segments)] == segs
 
 
@@ -145,7 +147,7 @@ def test_parser_accept_reject_matches_oracle(lib, orc):
     # a scan cut short still parses (slice runs to the end of the buffer), as in the reference
     s = api.JpegStream()
     assert s.parse(base[:sos + 200]) == api.SUCCESS
-    assert s.info().scan_size == len(base[:sos + 200]) - s.info().scan_offset
+    assert s.host_scan().scan_size == len(base[:sos + 200]) - s.info().scan_offset
 
 
 def test_parser_header_fuzz_matches_oracle_and_reference(lib, orc):
@@ -189,7 +191,7 @@ def test_parser_header_fuzz_matches_oracle_and_reference(lib, orc):
                 accepted += 1
                 i = s.info()
                 assert (i.width, i.height, i.num_components, i.chroma_subsampling) == (o.width, o.height, o.ncomp, o.css)
-                assert (i.scan_offset, i.scan_size, i.restart_interval) == (o.scan_offset, o.scan_size, o.restart_interval)
+                assert (i.scan_offset, s.host_scan().scan_size, i.restart_interval) == (o.scan_offset, o.scan_size, o.restart_interval)
                 assert i.decode_status == orc.supported(o)
     assert checked == 600 and 50 < accepted < 550   # the mutations exercise both outcomes
 
@@ -197,9 +199,9 @@ def test_parser_header_fuzz_matches_oracle_and_reference(lib, orc):
 def test_parser_reuse_and_unsupported(lib):
     s = api.JpegStream()
     assert s.parse(load("synth_444_500x375")) == api.SUCCESS
-    big = s.info().clean_bytes
+    big = s.host_scan().clean_bytes
     assert s.parse(load("synth_420_64x64")) == api.SUCCESS
-    assert s.info().clean_bytes < big and s.info().width == 64
+    assert s.host_scan().clean_bytes < big and s.info().width == 64
     # progressive (SOF2): the frame header is skipped like any unknown marker, so the scan
     # header cannot match it -> BAD_JPEG, exactly as the reference parser decides
     base = bytearray(load("synth_420_123x77"))
@@ -241,15 +243,124 @@ class _ModelStats(C.Structure):
 @pytest.fixture(scope="session")
 def k1_model():
     out = os.path.join(HERE, "_build", "libk1model.so")
-    src = [os.path.join(HERE, "k1_model.cpp"), os.path.join(ROOT, "rocjpeg_b200", "csrc", "jpeg_parser.cpp")]
-    deps = src + [os.path.join(ROOT, "rocjpeg_b200", "csrc", f) for f in ("huff_core.cuh", "jpeg_parser.h", "device_types.h")]
+    src = [os.path.join(HERE, "k1_model.cpp"), os.path.join(HERE, "k0_model.cpp"), os.path.join(ROOT, "rocjpeg_b200", "csrc", "jpeg_parser.cpp")]
+    deps = src + [os.path.join(ROOT, "rocjpeg_b200", "csrc", f) for f in ("huff_core.cuh", "k0_core.cuh", "jpeg_parser.h", "device_types.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "rocjpeg_b200", "csrc"),
                         "-I", "/usr/local/cuda/include", *src, "-L/usr/local/cuda/lib64", "-lcudart", "-o", out], check=True)
     L = C.CDLL(out)
     L.k1_model_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(_ModelStats)]
+    L.k0_model_destuff.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
     return L
+
+
+# ---------------------------------------------------------------- K0 (GPU destuffing) schedule on the CPU
+
+def _scan_with(base: bytes, scan: bytes) -> bytes:
+    """The header of `base` (up to the end of its SOS segment) followed by arbitrary scan bytes."""
+    sos = base.index(b"\xFF\xDA")
+    end = sos + 2 + int.from_bytes(base[sos + 2:sos + 4], "big")
+    return base[:end] + scan
+
+
+def _k0_model_segments(k1_model, data, S, skip, keep=(0, 0xFFFFFFFF)):
+    s = api.JpegStream()
+    assert s.parse(data) == api.SUCCESS
+    nseg = s.info().num_segments
+    cap = len(data) + (S + 14) * (nseg + 2) + 1024
+    clean = np.full(cap, 0xA5, np.uint8)
+    nbytes, off, sub0 = np.zeros(nseg, np.uint32), np.zeros(nseg, np.uint64), np.zeros(nseg, np.uint32)
+    st = np.zeros(4, np.uint32)
+    rc = k1_model.k0_model_destuff(data, len(data), S, skip, keep[0], keep[1], nbytes.ctypes.data, off.ctypes.data, sub0.ctypes.data,
+                                   nseg, clean.ctypes.data, cap, st.ctypes.data)
+    assert rc == 0, rc
+    return s, nbytes, off, sub0, clean, st
+
+
+def _check_k0_against_host_scan(k1_model, data, S, skip):
+    s, nbytes, off, sub0, clean, st = _k0_model_segments(k1_model, data, S, skip)
+    hs = s.host_scan()
+    nseg = s.info().num_segments
+    assert hs.num_segments == nseg
+    want = [s.segment(j) for j in range(nseg)]
+    got = [bytes(clean[int(off[j]):int(off[j]) + int(nbytes[j])]) for j in range(nseg)]
+    assert got == want, (S, skip)
+    assert st[1] == hs.scan_size and st[3] == nseg
+    assert st[0] == hs.restart_markers_seen + 1
+    prev_end = 0
+    for j in range(nseg):
+        if nbytes[j] == 0 and j >= st[0]:
+            continue
+        assert off[j] % S == 0 and sub0[j] == off[j] // S           # every interval starts on a subsequence boundary
+        assert off[j] >= prev_end                                    # ... behind the previous one's 16 zero bytes
+        assert not clean[int(off[j]) + int(nbytes[j]):int(off[j]) + int(nbytes[j]) + 16].any()
+        prev_end = int(off[j]) + int(nbytes[j]) + 16
+    assert all(sub0[j] <= sub0[j + 1] for j in range(nseg - 1))      # K1 finds a subsequence's interval by bisection
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_k0_schedule_model_matches_host_scan(k1_model, name):
+    data = load(name)
+    for S, skip in ((128, 0), (64, 5), (32, 15)):
+        _check_k0_against_host_scan(k1_model, data, S, skip)
+
+
+def test_k0_schedule_model_marker_patterns(k1_model):
+    """Hand-made scans around every rule of the destuffing pass and every boundary of its schedule (16-byte pieces,
+    32-piece warps, 4096-byte tiles): stuffed FF, fill bytes, restart markers out of sequence / too many / too few,
+    stray markers (the interval carries no more data), FF D9 early / missing / twice, a lone FF at the end."""
+    dri = load("synth_420_123x77_dri")      # DRI present: several restart intervals expected
+    plain = load("synth_444_123x77")        # no DRI: one interval
+    rng = np.random.default_rng(5)
+    body = lambda n: bytes(int(x) for x in rng.integers(0, 255, n))   # no FF inside
+    scans = [
+        b"",                                                          # no entropy-coded bytes at all
+        b"\xFF",                                                      # lone FF
+        b"\xFF\xD9",
+        b"\x12\xFF\x00\x34\xFF\xD9",
+        b"\xFF\x00" * 40 + b"\xFF\xD9",
+        b"\xFF\xFF\xFF\x00\x55\xFF\xFF\xD0\x66\xFF\xFF\xFF\xD9",          # fill bytes before a stuffed FF, a RST and the EOI
+        body(15) + b"\xFF\x00" + body(14) + b"\xFF\x00" + body(100) + b"\xFF\xD9",   # FF as last byte of a piece, 00 as first of the next
+        body(4095) + b"\xFF\x00" + body(5000) + b"\xFF\xD9",              # ... of a tile
+        body(4094) + b"\xFF\xD0" + body(3) + b"\xFF\xD1" + body(4090) + b"\xFF\xD2" + body(10),   # RST at a tile edge; no EOI
+        body(510) + b"\xFF\xD3" + body(700) + b"\xFF\xD3" + body(9) + b"\xFF\xD9",      # RST out of sequence, at a warp edge
+        body(100) + b"\xFF\xE0" + body(50) + b"\xFF\xD0" + body(60) + b"\xFF\xC4" + body(5) + b"\xFF\x00" + body(5) + b"\xFF\xD9",   # stray markers
+        body(30) + b"\xFF\xD9" + body(40) + b"\xFF\xD0" + body(30) + b"\xFF\xD9",       # bytes (and a RST) behind the first EOI
+        b"".join(body(int(rng.integers(0, 40))) + b"\xFF" + bytes([0xD0 + (k & 7)]) for k in range(200)) + b"\xFF\xD9",   # far more RSTs than the frame has intervals
+        b"".join(body(int(rng.integers(0, 3))) + b"\xFF" + bytes([int(rng.choice([0, 0, 0xFF, 0xD0, 0xD5, 0xE1]))]) for k in range(3000)) + b"\xFF",   # dense
+        body(20000),                                                  # no marker at all
+    ]
+    for base in (dri, plain):
+        for scan in scans:
+            data = _scan_with(base, scan)
+            for S, skip in ((128, 0), (32, 7), (64, 15)):
+                _check_k0_against_host_scan(k1_model, data, S, skip)
+
+
+def test_k0_schedule_model_random_byte_soup(k1_model):
+    """Seeded random scans with a marker-rich byte distribution, lengths around the piece / warp / tile sizes."""
+    rng = np.random.default_rng(77)
+    base = load("synth_420_123x77_dri")
+    alphabet = np.array([0xFF] * 6 + [0x00] * 3 + [0xD0, 0xD1, 0xD7, 0xD9, 0xC4, 0xDA] + list(range(1, 60)), np.uint8)
+    for n in (1, 2, 15, 16, 17, 31, 33, 511, 512, 513, 4095, 4096, 4097, 8191, 12289, 70001):
+        for rep in range(3):
+            scan = bytes(rng.choice(alphabet, n))
+            if rep == 2:
+                scan = scan.replace(b"\xFF\xD9", b"\xFF\x00")   # a long one without EOI
+            _check_k0_against_host_scan(k1_model, _scan_with(base, scan), int(rng.choice([32, 64, 128])), int(rng.integers(0, 16)))
+
+
+def test_k0_region_of_interest_keeps_only_wanted_intervals(k1_model):
+    data = load("synth_420_500x375_dri7")
+    s, nbytes, off, sub0, clean, st = _k0_model_segments(k1_model, data, 64, 3, keep=(2, 4))
+    want = [s.segment(j) for j in range(s.info().num_segments)]
+    for j in range(len(want)):
+        if 2 <= j <= 4:
+            assert bytes(clean[int(off[j]):int(off[j]) + int(nbytes[j])]) == want[j]
+        else:
+            assert nbytes[j] == 0
 
 
 @pytest.mark.parametrize("name", CASES)
