@@ -292,6 +292,28 @@ def main():
         streams.append(s)
     first_parse_s = time.perf_counter() - t0
     assert all(s.info().source_is_zero_copy for s in streams), "the pinned arena was not recognised as page-locked memory"
+    dests, keep = [], []
+    for (w, h, css) in dims:
+        chans = api.output_channel_shapes(css, fmt, w, h)
+        pitches = [rb for (_, rb) in chans]
+        if fmt == "yuv_planar" and css in ("422", "420"):
+            pitches[2] = pitches[1]
+        bufs = [torch.empty(rows * p + 64, dtype=torch.uint8, device="cuda") for (rows, _), p in zip(chans, pitches)]
+        keep.append(bufs)
+        dests.append([(b.data_ptr(), p) for b, p in zip(bufs, pitches)])
+    params = api.make_params(fmt)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def l2_flush():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            rdist.barrier()
+            torch.cuda.synchronize()
+
     # ---- device-resident arm (value) -------------------------------------------------
     lanes_env = os.environ.get("ROCJPEG_B200_LANES")
     dec.set_profiling(2)   # first/last event only: the stages overlap as they do in production

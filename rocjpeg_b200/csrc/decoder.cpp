@@ -365,7 +365,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     needs_planes_ = false;
     const bool direct_ok = EnvInt("ROCJPEG_B200_NO_DIRECT", 0) == 0;
     uint64_t scan_off = 0, raw_off = 0, blk = 0, plane_off = 0, ent = 0, sub = 0;
-    uint32_t dctile = 0, k2tile = 0, k3tile = 0, chunk = 0, max_pairs = 1, max_sub = 0, k0tile = 0, nseg_total = 0;
+    uint32_t dctile = 0, k2tile = 0, k3tile = 0, max_pairs = 1, max_sub = 0, k0tile = 0, nseg_total = 0;
     all_pinned_ = true;
     h_k0_tile0_.assign(size_t(n) + 1, 0);
     for (int i = 0; i < n; i++) {
@@ -430,8 +430,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         im.raw_len = rs.nbytes;
         im.raw_off = raw_off;
         const uint32_t up_bytes = uint32_t(AlignUp(size_t(im.raw_skip) + rs.nbytes, 16));
-        h_gather_[size_t(i)] = GatherItem{src - im.raw_skip, raw_off, up_bytes, chunk};
-        chunk += uint32_t((size_t(up_bytes) + 16383) / 16384);
+        h_gather_[size_t(i)] = GatherItem{src - im.raw_skip, raw_off, up_bytes, 0u};
         all_pinned_ = all_pinned_ && rs.dev != nullptr;
         raw_off += AlignUp(size_t(up_bytes) + 16, 128);
         im.k0_tile0 = k0tile;
@@ -528,7 +527,6 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     h_img_dctile0_[size_t(n)] = dctile;
     h_k2_tile0_[size_t(n)] = k2tile;
     h_k3_tile0_[size_t(n)] = k3tile;
-    gather_chunks_ = chunk;
     scan_bytes_ = scan_off;
     raw_bytes_ = raw_off;
     nseg_total_ = nseg_total;
@@ -679,8 +677,9 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     // the copy engine at full PCIe rate without occupying SMs.
     const bool use_gather = all_pinned_ && h_images_.size() > 4 && raw_bytes_ / h_images_.size() < (256u << 10) &&
                             EnvInt("ROCJPEG_B200_NO_GATHER", 0) == 0;
-    if (use_gather) {
-        RJB_CUDA(LaunchGather(reinterpret_cast<const GatherItem*>(d + L.gather), int(n), gather_chunks_, const_cast<uint8_t*>(k0_.raw), up));
+    tiles_reduced_ = use_gather;
+    if (use_gather) {   // ... which also leaves the per-tile prefix elements of the destuffing pass
+        RJB_CUDA(LaunchGatherReduce(k0_, reinterpret_cast<const GatherItem*>(d + L.gather), up));
         stats_.kernel_launches++;
     } else {
         for (size_t i = 0; i < n; i++)
@@ -724,8 +723,12 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
         RJB_CUDA(cudaMemsetAsync(k1_.counters_next, 0, 256, stream_));
     }
     // K0: end of slice, destuffing, restart intervals -> clean stream + segment table, all on the device
+    if (!(include_upload && tiles_reduced_)) {   // cudaMemcpy upload, or a resident batch run again: the reduction is its own launch
+        RJB_CUDA(LaunchK0Reduce(k0_, stream_));
+        stats_.kernel_launches++;
+    }
     RJB_CUDA(LaunchK0Destuff(k0_, stream_));
-    stats_.kernel_launches += 3;
+    stats_.kernel_launches += 2;
     RJB_CUDA(mark(2));
     for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
     stats_.sync_rounds = uint32_t(rounds);

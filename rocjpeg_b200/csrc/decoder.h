@@ -165,7 +165,7 @@ class Lane {
     K1Args k1_ = {};
     K2Args k2_ = {};
     K3Args k3_ = {};
-    uint32_t gather_chunks_ = 0;
+    bool tiles_reduced_ = false;   // the upload kernel left the destuffing pass's per-tile prefix elements
     bool all_pinned_ = false, any_direct_ = false, needs_planes_ = false;
     size_t scan_bytes_ = 0, raw_bytes_ = 0, coef_blocks_ = 0, entry_count_ = 0, plane_bytes_ = 0, nsub_total_ = 0;
     uint32_t nseg_total_ = 0;

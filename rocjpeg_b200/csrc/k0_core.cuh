@@ -63,16 +63,19 @@ RJB_K0_HD Elem Combine(const Elem& a, const Elem& b) {
     return r;
 }
 
-// bit i of the result = byte i of the 16 (little-endian words) equals `pattern` under `and_mask`
+// bit i of the result = byte i of the 16 (little-endian words) equals the byte `pattern` repeats, under `and_mask`.
+// Exact per-byte zero test of x = (w & and_mask) ^ pattern (no carries across bytes), then the four top bits
+// gathered by one multiply.
 RJB_K0_HD uint32_t EqMask16(const uint32_t (&w)[4], uint32_t and_mask, uint32_t pattern) {
     uint32_t m = 0;
-#ifdef __CUDA_ARCH__
+#ifdef __CUDACC__
 #pragma unroll
-    for (int q = 0; q < 4; q++) m |= (((__vcmpeq4(w[q] & and_mask, pattern) & 0x80808080u) * 0x00204081u) >> 28) << (4 * q);
-#else
-    for (int i = 0; i < 16; i++)
-        if ((((w[i >> 2] & and_mask) >> (8 * (i & 3))) & 0xFFu) == (pattern & 0xFFu)) m |= 1u << i;
 #endif
+    for (int q = 0; q < 4; q++) {
+        const uint32_t x = (w[q] & and_mask) ^ pattern;
+        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;   // 0x80 in every zero byte of x
+        m |= ((z * 0x00204081u) >> 28) << (4 * q);
+    }
     return m;
 }
 
@@ -88,6 +91,17 @@ struct Piece {
 };
 
 RJB_K0_HD uint32_t ByteOf(const Piece& pc, uint32_t i) { return (pc.w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
+
+// The piece's kept bytes, in order, to dst (any alignment); returns their number. Unrolled: the words stay in registers.
+RJB_K0_HD uint32_t CompactPiece(const Piece& pc, uint8_t* dst) {
+    uint32_t n = 0;
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+    for (int i = 0; i < 16; i++)
+        if ((pc.keep >> i) & 1u) dst[n++] = uint8_t(pc.w[i >> 2] >> (8 * (i & 3)));
+    return n;
+}
 
 // Does the piece at scan position pos0 overlap the scan [0, len)?
 RJB_K0_HD bool PieceOverlaps(int64_t pos0, int64_t len) { return pos0 + 16 > 0 && pos0 < len; }
@@ -112,8 +126,12 @@ RJB_K0_HD Piece ClassifyPiece(const uint32_t (&w_in)[4], uint32_t prev, uint32_t
         }
     }
     const uint32_t valid = BitsBelow(uint32_t(hi)) & ~BitsBelow(uint32_t(lo)) & 0xFFFFu;
-    const uint32_t F = EqMask16(pc.w, 0xFFFFFFFFu, 0xFFFFFFFFu), Z = EqMask16(pc.w, 0xFFFFFFFFu, 0u),
-                   D = EqMask16(pc.w, 0xF8F8F8F8u, 0xD0D0D0D0u), E = EqMask16(pc.w, 0xFFFFFFFFu, 0xD9D9D9D9u);
+    const uint32_t F = EqMask16(pc.w, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    if (F == 0u && prev != 0xFFu) {   // no FF in or right before the piece (94 % of them): every byte is data
+        pc.keep = valid;
+        return pc;
+    }
+    const uint32_t Z = EqMask16(pc.w, 0xFFFFFFFFu, 0u), D = EqMask16(pc.w, 0xF8F8F8F8u, 0xD0D0D0D0u), E = EqMask16(pc.w, 0xFFFFFFFFu, 0xD9D9D9D9u);
     const uint32_t Fn = (F >> 1) | (next == 0xFFu ? 0x8000u : 0u), Zn = (Z >> 1) | (next == 0x00u ? 0x8000u : 0u),
                    Dn = (D >> 1) | ((next & 0xF8u) == 0xD0u ? 0x8000u : 0u), En = (E >> 1) | (next == 0xD9u ? 0x8000u : 0u);
     const uint32_t prevF = ((F << 1) | (prev == 0xFFu ? 1u : 0u)) & 0xFFFFu;
@@ -227,12 +245,14 @@ RJB_K0_HD void WalkPiece(const Piece& pc, const Elem& ex, const Elem& mine, cons
         if (dead || !m) return;
         if (pl.Wanted(k)) {
             uint8_t* dst = pl.Dst(r, k) + cnt;
-            while (m) {
-                const uint32_t i = LowestBit(m);
-                m &= m - 1u;
-                *dst++ = uint8_t(ByteOf(pc, i));
-                cnt++;
-            }
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+            for (int i = 0; i < 16; i++)
+                if ((m >> i) & 1u) {
+                    *dst++ = uint8_t(pc.w[i >> 2] >> (8 * (i & 3)));
+                    cnt++;
+                }
         } else {
             cnt += Popc(m);
         }

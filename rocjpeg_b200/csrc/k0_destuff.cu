@@ -20,9 +20,14 @@
 //   (restart markers so far, kept bytes since the last one, position behind the last one,
 //    interval dead, slice ended)
 // which composes associatively (Combine below), so three launches do it: per-tile reduction,
-// one scan over the tiles of each image, per-tile scan + scatter. A tile is 4 KiB of one image,
-// one 16-byte vector per thread. The bytes are read twice from L2 (the batch's raw bytes were
-// written there a moment ago by the upload) and written once: HBM-bound, ~3 bytes moved per byte.
+// one scan over the tiles of each image, per-tile scan + scatter. A tile is 16 KiB of one image,
+// four 16-byte pieces (64 consecutive bytes) per thread. When the upload is the gather kernel
+// (many small pictures read in place from page-locked host memory), the per-tile reduction rides
+// in it: the bytes pass through the SMs anyway while the PCIe link is the limit. The kernels are
+// issue-bound, not bandwidth-bound (the batch's raw bytes sit in L2), hence: a thread whose 64
+// bytes hold no FF - four out of five - is recognised with two instructions per word and does no
+// classification at all; a warp without markers scans one integer instead of the four-word
+// element; kept bytes leave through shared memory as 128-bit stores, one run per restart interval.
 #include <cuda_runtime.h>
 
 #include "k0_core.cuh"
@@ -34,8 +39,11 @@ namespace {
 using namespace k0;
 
 constexpr int kThreads = 256;
+constexpr int kPieces = 4;                      // 16-byte pieces per thread
+constexpr int kChunk = 16 * kPieces;            // bytes per thread
 constexpr int kTileBytes = kK0TileBytes;
-static_assert(kTileBytes == kThreads * 16, "one 16-byte vector per thread");
+static_assert(kTileBytes == kThreads * kChunk, "64 bytes per thread");
+constexpr int kStageBytes = 32 * kChunk + 48;   // a warp's kept bytes at the run's 16-byte phase
 
 __device__ __forceinline__ Elem ShflUp(const Elem& e, int d) {
     Elem r;
@@ -46,18 +54,66 @@ __device__ __forceinline__ Elem ShflUp(const Elem& e, int d) {
     return r;
 }
 
-// Loads and classifies the piece at byte offset `off` of the image's uploaded bytes (off = multiple of 16).
-__device__ __forceinline__ Piece LoadPiece(const uint8_t* raw, const ImageDesc& im, uint64_t off) {
-    const int64_t len = int64_t(im.raw_len), pos0 = int64_t(off) - int64_t(im.raw_skip);
-    uint32_t w[4] = {0u, 0u, 0u, 0u}, prev = 0u, next = 0xFFu;
-    if (PieceOverlaps(pos0, len)) {
-        const uint8_t* base = raw + im.raw_off + off;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base));
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        if (pos0 > 0) prev = __ldg(base - 1);
-        if (pos0 + 16 < len) next = __ldg(base + 16);
+// A thread's 64 bytes of an image's uploaded data.
+struct Chunk {
+    uint32_t w[4 * kPieces];
+    uint32_t prev, next;   // the bytes around it (only meaningful inside the scan)
+    int64_t pos0;          // scan position of byte 0
+    bool overlaps;         // some byte lies inside the scan
+    bool fast;             // wholly inside the scan, no FF in or right before it: 64 data bytes and nothing else
+};
+
+__device__ __forceinline__ void FinishChunk(Chunk& c, int64_t len) {
+    c.overlaps = c.pos0 + kChunk > 0 && c.pos0 < len;
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < 4 * kPieces; i++) any |= (~c.w[i] - 0x01010101u) & c.w[i];   // top bit of a byte set <=> some byte of the word is FF
+    c.fast = c.pos0 >= 0 && c.pos0 + kChunk <= len && (any & 0x80808080u) == 0u && c.prev != 0xFFu;
+}
+
+// `off` = byte offset of the chunk in the image's uploaded bytes (multiple of 64).
+__device__ __forceinline__ Chunk LoadChunk(const uint8_t* raw, const ImageDesc& im, uint64_t off) {
+    Chunk c;
+    const int64_t len = int64_t(im.raw_len);
+    c.pos0 = int64_t(off) - int64_t(im.raw_skip);
+    c.prev = 0u;
+    c.next = 0xFFu;
+    const uint8_t* base = raw + im.raw_off + off;
+#pragma unroll
+    for (int j = 0; j < kPieces; j++) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (PieceOverlaps(c.pos0 + 16 * j, len)) v = __ldg(reinterpret_cast<const uint4*>(base) + j);
+        c.w[4 * j] = v.x; c.w[4 * j + 1] = v.y; c.w[4 * j + 2] = v.z; c.w[4 * j + 3] = v.w;
     }
-    return ClassifyPiece(w, prev, next, pos0, len);
+    if (c.pos0 > 0 && c.pos0 <= len) c.prev = __ldg(base - 1);
+    if (c.pos0 + kChunk < len && c.pos0 + kChunk >= 0) c.next = __ldg(base + kChunk);
+    FinishChunk(c, len);
+    return c;
+}
+
+__device__ __forceinline__ Piece PieceOf(const Chunk& c, int j, int64_t len) {
+    const uint32_t prev = j ? (c.w[4 * j - 1] >> 24) : c.prev;
+    const uint32_t next = j < kPieces - 1 ? (c.w[4 * j + 4] & 0xFFu) : c.next;
+    return ClassifyPiece(*reinterpret_cast<const uint32_t(*)[4]>(&c.w[4 * j]), prev, next, c.pos0 + 16 * j, len);
+}
+
+// The chunk's prefix element; *plain = it holds no marker (the element is just a byte count).
+__device__ __forceinline__ Elem ChunkElem(const Chunk& c, int64_t len, bool* plain) {
+    Elem e{0u, 0u, 0u, 0u};
+    *plain = true;
+    if (c.fast) {
+        e.tail = kChunk;
+        return e;
+    }
+    if (!c.overlaps) return e;
+#pragma unroll
+    for (int j = 0; j < kPieces; j++) {
+        const Piece pc = PieceOf(c, j, len);
+        if (!pc.any) continue;
+        e = Combine(e, PieceElem(pc));
+        if (pc.rst | pc.oth | pc.eoi) *plain = false;
+    }
+    return e;
 }
 
 // largest i in [0, n) with a[i] <= v
@@ -71,20 +127,45 @@ __device__ __forceinline__ uint32_t UpperIndexK0(const uint32_t* a, uint32_t n, 
 }
 
 // Scan of `e` over the CTA: *excl = exclusive value of the thread, *total = CTA total (when asked for).
-__device__ __forceinline__ void CtaScan(const Elem& e, Elem* warp_tot /* shared [kThreads / 32] */, Elem* excl, Elem* total) {
+// `plain` = the thread's chunk holds no marker: a warp (a CTA) of plain chunks - nearly all of them when the
+// picture has no restart markers - scans one integer instead of four words through Combine.
+__device__ __forceinline__ void CtaScan(const Elem& e, bool plain, Elem* warp_tot /* shared [kThreads / 32] */, Elem* excl, Elem* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Elem inc = e;
+    const bool warp_plain = __all_sync(0xFFFFFFFFu, plain);
+    if (warp_plain) {
+        uint32_t t = e.tail;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const Elem p = ShflUp(inc, d);
-        if (lane >= d) inc = Combine(p, inc);
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t p = __shfl_up_sync(0xFFFFFFFFu, t, d);
+            if (lane >= d) t += p;
+        }
+        inc.tail = t;
+    } else {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Elem p = ShflUp(inc, d);
+            if (lane >= d) inc = Combine(p, inc);
+        }
     }
     if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    Elem pre{0u, 0u, 0u, 0u};
-    for (int w = 0; w < warp; w++) pre = Combine(pre, warp_tot[w]);
     Elem ex = ShflUp(inc, 1);
     if (lane == 0) ex = Elem{0u, 0u, 0u, 0u};
+    if (__syncthreads_and(warp_plain)) {
+        uint32_t pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) {
+            const uint32_t t = warp_tot[w].tail;
+            if (w < warp) pre += t;
+            tot += t;
+        }
+        ex.tail += pre;
+        *excl = ex;
+        if (total) *total = Elem{0u, tot, 0u, 0u};
+        return;
+    }
+    Elem pre{0u, 0u, 0u, 0u};
+    for (int w = 0; w < warp; w++) pre = Combine(pre, warp_tot[w]);
     *excl = Combine(pre, ex);
     if (total) {
         Elem t = pre;
@@ -101,11 +182,71 @@ __global__ void __launch_bounds__(kThreads) k0_reduce(K0Args a) {
     const uint32_t tile = blockIdx.x;
     const uint32_t img = UpperIndexK0(a.img_tile0, uint32_t(a.nimages), tile);
     const ImageDesc& im = a.images[img];
-    const uint64_t off = uint64_t(tile - im.k0_tile0) * kTileBytes + uint64_t(threadIdx.x) * 16u;
-    const Piece pc = LoadPiece(a.raw, im, off);
+    const uint64_t off = uint64_t(tile - im.k0_tile0) * kTileBytes + uint64_t(threadIdx.x) * kChunk;
+    const Chunk c = LoadChunk(a.raw, im, off);
+    bool plain;
+    const Elem e = ChunkElem(c, int64_t(im.raw_len), &plain);
     Elem ex, tot;
-    CtaScan(PieceElem(pc), s_warp, &ex, &tot);
+    CtaScan(e, plain, s_warp, &ex, &tot);
     if (threadIdx.x == 0) a.tile_sum[tile] = make_uint4(tot.nrst, tot.tail, tot.last_r, tot.flags);
+}
+
+// ---------------------------------------------------------------- gather_reduce: upload + k0_reduce in one
+//
+// Many small pictures in page-locked host memory: a few CTAs copy them, 16 KiB at a time, straight from the
+// caller's buffers into the raw arena (a copy call per picture would cost the host more than the transfer).
+// The link is the limit, so the tile's prefix element is computed on the way, from the copy kept in shared
+// memory - the separate reduction launch (and its read of the bytes) is not needed then.
+
+constexpr int kGatherCtas = 64;   // PCIe-bound: a few CTAs saturate the link; the rest of the GPU stays free
+                                  // for the kernels of the other pipeline lanes
+
+__global__ void __launch_bounds__(kThreads) gather_reduce(K0Args a, const GatherItem* items, uint8_t* raw_out) {
+    PdlEntry();
+    __shared__ Elem s_warp[kThreads / 32];
+    __shared__ __align__(16) uint4 s_tile[kTileBytes / 16];
+    __shared__ uint32_t s_edge[2];
+    const int tid = threadIdx.x;
+    for (uint32_t tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const uint32_t img = UpperIndexK0(a.img_tile0, uint32_t(a.nimages), tile);
+        const ImageDesc& im = a.images[img];
+        const GatherItem it = items[img];
+        const uint32_t off = (tile - im.k0_tile0) * uint32_t(kTileBytes);
+        const uint32_t n = it.nbytes > off ? min(uint32_t(kTileBytes), it.nbytes - off) : 0u;   // multiple of 16
+        const int64_t len = int64_t(im.raw_len), tpos0 = int64_t(off) - int64_t(im.raw_skip);
+        __syncthreads();   // the previous tile's readers of s_tile / s_edge / s_warp are done
+        // the bytes around the tile, read from the source (the neighbouring tiles are other CTAs' work)
+        if (tid == 0) s_edge[0] = (tpos0 > 0 && tpos0 <= len) ? uint32_t(it.src[off - 1]) : 0u;
+        if (tid == 32) s_edge[1] = (tpos0 + kTileBytes < len) ? uint32_t(it.src[off + kTileBytes]) : 0xFFu;
+        const uint4* src = reinterpret_cast<const uint4*>(it.src + off);
+        uint4* dst = reinterpret_cast<uint4*>(raw_out + it.dst_off + off);
+        for (uint32_t i = uint32_t(tid); i < uint32_t(kTileBytes / 16); i += kThreads) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (i < n / 16) {
+                v = src[i];
+                dst[i] = v;
+            }
+            s_tile[i] = v;
+        }
+        __syncthreads();
+        Chunk c;
+        c.pos0 = tpos0 + int64_t(tid) * kChunk;
+#pragma unroll
+        for (int j = 0; j < kPieces; j++) {
+            const uint4 v = s_tile[tid * kPieces + j];
+            c.w[4 * j] = v.x; c.w[4 * j + 1] = v.y; c.w[4 * j + 2] = v.z; c.w[4 * j + 3] = v.w;
+        }
+        c.prev = tid ? (reinterpret_cast<const uint32_t*>(s_tile)[tid * (kChunk / 4) - 1] >> 24) : s_edge[0];
+        c.next = tid < kThreads - 1 ? (reinterpret_cast<const uint32_t*>(s_tile)[(tid + 1) * (kChunk / 4)] & 0xFFu) : s_edge[1];
+        if (c.pos0 <= 0) c.prev = 0u;
+        if (c.pos0 + kChunk >= len) c.next = 0xFFu;
+        FinishChunk(c, len);
+        bool plain;
+        const Elem e = ChunkElem(c, len, &plain);
+        Elem ex, tot;
+        CtaScan(e, plain, s_warp, &ex, &tot);
+        if (tid == 0) a.tile_sum[tile] = make_uint4(tot.nrst, tot.tail, tot.last_r, tot.flags);
+    }
 }
 
 // ---------------------------------------------------------------- k0_scan: exclusive scan over an image's tiles
@@ -125,7 +266,7 @@ __global__ void __launch_bounds__(kThreads) k0_scan(K0Args a) {
         }
         Elem ex, tot;
         __syncthreads();   // the previous chunk's readers of s_warp are done
-        CtaScan(e, s_warp, &ex, &tot);
+        CtaScan(e, false, s_warp, &ex, &tot);
         ex = Combine(carry, ex);
         if (k < t1) a.tile_carry[k] = make_uint4(ex.nrst, ex.tail, ex.last_r, ex.flags);
         carry = Combine(carry, tot);
@@ -147,22 +288,48 @@ struct DevMem {
     }
 };
 
+// NW little-endian words (4 NW bytes) to shared memory at byte address `at`, any alignment: word stores of the
+// funnel-shifted stream, byte stores only for the partial words at both ends (a neighbouring lane owns their
+// other bytes).
+template <int NW>
+__device__ __forceinline__ void StoreShifted(uint8_t* at, const uint32_t* w) {
+    const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(at)) & 3u;
+    uint32_t* p = reinterpret_cast<uint32_t*>(at - a);
+    if (a == 0u) {
+#pragma unroll
+        for (int i = 0; i < NW; i++) p[i] = w[i];
+        return;
+    }
+    const uint32_t down = 32u - 8u * a;
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+        if (uint32_t(b) < 4u - a) at[b] = uint8_t(w[0] >> (8 * b));
+#pragma unroll
+    for (int i = 1; i < NW; i++) p[i] = __funnelshift_r(w[i - 1], w[i], down);
+    uint8_t* tail = at + 4 * NW - a;
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+        if (uint32_t(b) < a) tail[b] = uint8_t(w[NW - 1] >> (down + 8 * b));
+}
+
 template <int S>
 __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
     PdlEntry();
     __shared__ Elem s_warp[kThreads / 32];
-    __shared__ __align__(16) uint8_t s_stage[kThreads / 32][512 + 32];
+    __shared__ __align__(16) uint8_t s_stage[kThreads / 32][kStageBytes];
     __shared__ uint32_t s_fill_from;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
     const uint32_t img = UpperIndexK0(a.img_tile0, uint32_t(a.nimages), tile);
     const ImageDesc& im = a.images[img];
-    const uint64_t off = uint64_t(tile - im.k0_tile0) * kTileBytes + uint64_t(tid) * 16u;
-    const Piece pc = LoadPiece(a.raw, im, off);
-    const Elem mine = PieceElem(pc);
+    const int64_t len = int64_t(im.raw_len);
+    const uint64_t off = uint64_t(tile - im.k0_tile0) * kTileBytes + uint64_t(tid) * kChunk;
+    const Chunk c = LoadChunk(a.raw, im, off);
+    bool plain;
+    const Elem mine = ChunkElem(c, len, &plain);
     Elem ex;
     if (tid == 0) s_fill_from = 0xFFFFFFFFu;
-    CtaScan(mine, s_warp, &ex, nullptr);
+    CtaScan(mine, plain, s_warp, &ex, nullptr);
     {
         const uint4 q = a.tile_carry[tile];
         ex = Combine(Elem{q.x, q.y, q.z, q.w}, ex);
@@ -171,53 +338,68 @@ __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
     const Placer<DevMem> pl{im, uint32_t(S), mem};
     const bool ended_before = (ex.flags & kEnded) != 0;
 
-    // Fast path, decided per warp: no marker of any kind in the warp's 512 bytes and the slice has not ended -
-    // every lane's kept bytes go to one contiguous run. They are gathered in shared memory at the run's 16-byte
-    // phase and leave as 128-bit stores (a byte store per kept byte otherwise).
-    const bool simple = !ended_before && (pc.rst | pc.oth | pc.eoi) == 0u;
-    if (__all_sync(0xFFFFFFFFu, simple)) {
-        const uint32_t n = Popc(pc.keep);
-        const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, ex.nrst, 0), r0 = __shfl_sync(0xFFFFFFFFu, ex.last_r, 0),
-                       c0 = __shfl_sync(0xFFFFFFFFu, ex.tail, 0), f0 = __shfl_sync(0xFFFFFFFFu, ex.flags, 0);
-        uint32_t incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t p = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += p;
-        }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if (!(f0 & kDead) && pl.Wanted(k0) && total) {
-            uint8_t* dst = pl.Dst(r0, k0) + c0;
-            const uint32_t phase = uint32_t(reinterpret_cast<uintptr_t>(dst) & 15u);
-            uint8_t* st = s_stage[warp] + phase + (incl - n);
-            uint32_t keep = pc.keep;
-            if (keep == 0xFFFFu && ((phase + incl - n) & 3u) == 0u) {
-                reinterpret_cast<uint32_t*>(st)[0] = pc.w[0];
-                reinterpret_cast<uint32_t*>(st)[1] = pc.w[1];
-                reinterpret_cast<uint32_t*>(st)[2] = pc.w[2];
-                reinterpret_cast<uint32_t*>(st)[3] = pc.w[3];
+    // Chunks without a marker: their kept bytes form one contiguous piece of their restart interval, at the offset
+    // the prefix gives (kept bytes since the interval began). The lanes of a warp that belong to the same
+    // interval - all of them, unless a restart marker lies in the warp's 2 KiB - gather their bytes in shared
+    // memory at the run's 16-byte phase and write them out as 128-bit stores.
+    const uint32_t n = mine.tail;
+    const bool staged = plain && c.overlaps && !ended_before && !(ex.flags & kDead) && n != 0u && pl.Wanted(ex.nrst);
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, staged);
+    while (todo) {
+        const int leader = __ffs(int(todo)) - 1;
+        const uint32_t kL = __shfl_sync(0xFFFFFFFFu, ex.nrst, leader), rL = __shfl_sync(0xFFFFFFFFu, ex.last_r, leader),
+                       cL = __shfl_sync(0xFFFFFFFFu, ex.tail, leader);
+        const bool member = staged && ex.nrst == kL;
+        const uint32_t members = __ballot_sync(0xFFFFFFFFu, member);
+        uint8_t* dst = pl.Dst(rL, kL) + cL;
+        const uint32_t phase = uint32_t(reinterpret_cast<uintptr_t>(dst) & 15u);
+        if (member) {
+            uint8_t* at = s_stage[warp] + phase + (ex.tail - cL);
+            if (c.fast) {
+                StoreShifted<4 * kPieces>(at, c.w);
             } else {
-                while (keep) {
-                    const uint32_t i = LowestBit(keep);
-                    keep &= keep - 1u;
-                    *st++ = uint8_t(ByteOf(pc, i));
+#pragma unroll
+                for (int j = 0; j < kPieces; j++) {
+                    const Piece pc = PieceOf(c, j, len);
+                    if (pc.keep == 0xFFFFu) {
+                        StoreShifted<4>(at, &c.w[4 * j]);
+                        at += 16;
+                    } else {
+                        at += CompactPiece(pc, at);
+                    }
                 }
             }
-            __syncwarp();
-            const uint8_t* buf = s_stage[warp] + phase;
-            uint32_t head = (16u - phase) & 15u;
-            if (head > total) head = total;
-            if (uint32_t(lane) < head) dst[lane] = buf[lane];
-            const uint32_t nvec = (total - head) >> 4;
-            for (uint32_t v = uint32_t(lane); v < nvec; v += 32)
-                reinterpret_cast<uint4*>(dst + head)[v] = reinterpret_cast<const uint4*>(buf + head)[v];
-            const uint32_t done = head + (nvec << 4);
-            if (done + uint32_t(lane) < total) dst[done + lane] = buf[done + lane];
         }
-    } else if (!ended_before && pc.any) {
-        WalkPiece(pc, ex, mine, pl);
+        __syncwarp();
+        const int last = 31 - __clz(int(members));
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, ex.tail + n, last) - cL;
+        const uint8_t* buf = s_stage[warp] + phase;
+        uint32_t head = (16u - phase) & 15u;
+        if (head > total) head = total;
+        if (uint32_t(lane) < head) dst[lane] = buf[lane];
+        const uint32_t nvec = (total - head) >> 4;
+        for (uint32_t v = uint32_t(lane); v < nvec; v += 32)
+            reinterpret_cast<uint4*>(dst + head)[v] = reinterpret_cast<const uint4*>(buf + head)[v];
+        const uint32_t done = head + (nvec << 4);
+        if (done + uint32_t(lane) < total) dst[done + lane] = buf[done + lane];
+        __syncwarp();
+        todo &= ~members;
     }
-    FinishPiece(pc, ex, mine, pl, tile == im.k0_tile0 && tid == 0);
+    // Chunks with a marker walk their pieces (bytes stored one by one, restart intervals opened and closed); the first
+    // chunk of the image opens interval 0; the chunk holding the last byte closes the last interval when there is no FF D9.
+    const bool first = tile == im.k0_tile0 && tid == 0;
+    const bool walk = !plain && c.overlaps && !ended_before;
+    if (walk || first || (c.overlaps && c.pos0 + kChunk >= len) || len == 0) {
+        Elem x = ex;
+#pragma unroll 1
+        for (int j = 0; j < kPieces; j++) {
+            const Piece pc = PieceOf(c, j, len);
+            const Elem pe = PieceElem(pc);
+            if (walk && pc.any && !(x.flags & kEnded)) WalkPiece(pc, x, pe, pl);
+            FinishPiece(pc, x, pe, pl, first && j == 0);
+            x = Combine(x, pe);
+        }
+    }
     __syncthreads();
     const uint32_t from = s_fill_from;
     if (from != 0xFFFFFFFFu)
@@ -226,10 +408,19 @@ __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
 
 }  // namespace
 
+cudaError_t LaunchK0Reduce(const K0Args& a, cudaStream_t stream) {
+    if (a.total_tiles == 0) return cudaSuccess;
+    return LaunchPdl(k0_reduce, dim3(a.total_tiles), dim3(kThreads), 0, stream, a);
+}
+
+cudaError_t LaunchGatherReduce(const K0Args& a, const GatherItem* items, cudaStream_t stream) {
+    if (a.total_tiles == 0) return cudaSuccess;
+    return LaunchPdl(gather_reduce, dim3(min(a.total_tiles, uint32_t(kGatherCtas))), dim3(kThreads), 0, stream, a, items, const_cast<uint8_t*>(a.raw));
+}
+
 cudaError_t LaunchK0Destuff(const K0Args& a, cudaStream_t stream) {
     if (a.total_tiles == 0) return cudaSuccess;
-    cudaError_t e = LaunchPdl(k0_reduce, dim3(a.total_tiles), dim3(kThreads), 0, stream, a);
-    if (e == cudaSuccess) e = LaunchPdl(k0_scan, dim3(a.nimages), dim3(kThreads), 0, stream, a);
+    cudaError_t e = LaunchPdl(k0_scan, dim3(a.nimages), dim3(kThreads), 0, stream, a);
     if (e != cudaSuccess) return e;
     switch (a.sub_bytes) {
         case 32: return LaunchPdl(k0_apply<32>, dim3(a.total_tiles), dim3(kThreads), 0, stream, a);
@@ -242,6 +433,7 @@ cudaError_t LaunchK0Destuff(const K0Args& a, cudaStream_t stream) {
 cudaError_t PreloadK0() {
     cudaFuncAttributes at;
     cudaError_t e = cudaFuncGetAttributes(&at, k0_reduce);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, gather_reduce);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k0_scan);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k0_apply<32>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k0_apply<64>);

@@ -1064,35 +1064,6 @@ __global__ void __launch_bounds__(kDcImageThreads) dc_image(K1Args a) {
     }
 }
 
-// ---------------------------------------------------------------- gather
-
-constexpr int kGatherChunk = 16384;
-constexpr int kGatherCtas = 64;   // PCIe-bound: a few CTAs saturate the link; the rest of the GPU stays free
-                                  // for the kernels of the other pipeline lanes
-
-__global__ void __launch_bounds__(256) gather_scans(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena) {
-    PdlEntry();
-    __shared__ int s_item;
-    for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int lo = 0, hi = nitems;
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (items[mid].chunk0 <= chunk) lo = mid; else hi = mid;
-            }
-            s_item = lo;
-        }
-        __syncthreads();
-        const GatherItem it = items[s_item];
-        const uint32_t off = (chunk - it.chunk0) * kGatherChunk;
-        const uint32_t n = min(uint32_t(kGatherChunk), it.nbytes - off);
-        const uint4* src = reinterpret_cast<const uint4*>(it.src + off);
-        uint4* dst = reinterpret_cast<uint4*>(arena + it.dst_off + off);
-        for (uint32_t i = threadIdx.x; i < n / 16; i += blockDim.x) dst[i] = src[i];
-    }
-}
-
 template <int S>
 cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream, int max_iters = T + 1) {
     static_assert(S <= 128, "the packed decoder state holds bit positions below 2048");
@@ -1138,11 +1109,6 @@ cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream) {
     return e;
 }
 
-cudaError_t LaunchGather(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena, cudaStream_t stream) {
-    if (total_chunks == 0) return cudaSuccess;
-    return LaunchPdl(gather_scans, dim3(min(total_chunks, uint32_t(kGatherCtas))), dim3(256), 0, stream, items, nitems, total_chunks, arena);
-}
-
 // Forces the module holding this stage's kernels onto the device (CUDA loads lazily: the first launch
 // of every kernel would otherwise pay for it inside the first decode call).
 cudaError_t PreloadK1() {
@@ -1159,7 +1125,6 @@ cudaError_t PreloadK1() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_scan);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_apply);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_image);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, gather_scans);
     return e;
 }
 

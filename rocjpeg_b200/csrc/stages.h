@@ -52,7 +52,7 @@ inline cudaError_t LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 }
 #endif
 
-constexpr int kK0TileBytes = 4096;   // raw bytes per destuffing tile (one CTA, 16 bytes per thread)
+constexpr int kK0TileBytes = 16384;  // raw bytes per destuffing tile (one CTA, 64 bytes per thread) = bytes per gather step
 constexpr int kK1Threads = 128;      // threads per CTA in K1, one subsequence each
 constexpr int kDcImageMaxMcus = 4096;   // pictures up to this many MCUs take the one-launch DC integration
 // K1Args::halo leading threads of a CTA re-decode the previous CTA's last subsequences; the CTA owns the
@@ -86,7 +86,18 @@ struct K0Args {
     uint32_t total_tiles;
     int sub_bytes;                // S of the batch: intervals start on multiples of S
 };
-// Destuffing + restart-interval discovery + segment table for the whole batch (three launches).
+// Gather per-image raw bytes from mapped page-locked host memory into the raw arena.
+struct GatherItem {
+    const uint8_t* src;   // device-visible address of the 16-byte vector the image's first entropy-coded byte lies in
+    uint64_t dst_off;     // byte offset in the raw arena
+    uint32_t nbytes;      // multiple of 16
+    uint32_t pad_;
+};
+// Per-tile prefix elements of the raw bytes already in the arena (cudaMemcpy uploads, resident re-runs) ...
+cudaError_t LaunchK0Reduce(const K0Args& a, cudaStream_t stream);
+// ... or computed on the way by the kernel that uploads them (items: device array, one per image).
+cudaError_t LaunchGatherReduce(const K0Args& a, const GatherItem* items, cudaStream_t stream);
+// Scan over the tiles + scatter: destuffed bytes, restart intervals, segment table (two launches).
 cudaError_t LaunchK0Destuff(const K0Args& a, cudaStream_t stream);
 cudaError_t PreloadK0();
 
@@ -155,18 +166,9 @@ struct K3Args {
 };
 cudaError_t LaunchK3Output(const K3Args& a, cudaStream_t stream);
 
-// Gather per-image clean streams from mapped page-locked host memory into the scan arena.
-struct GatherItem {
-    const uint8_t* src;   // device-visible address of the image's clean stream
-    uint64_t dst_off;     // byte offset in the scan arena
-    uint32_t nbytes;      // multiple of 16
-    uint32_t chunk0;      // first 16 KiB gather chunk of this image
-};
 // Load the stages' kernels now instead of at their first launch.
 cudaError_t PreloadK1();
 cudaError_t PreloadK2();
 cudaError_t PreloadK3();
-
-cudaError_t LaunchGather(const GatherItem* items, int nitems, uint32_t total_chunks, uint8_t* arena, cudaStream_t stream);
 
 }  // namespace rjb

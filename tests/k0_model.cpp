@@ -2,7 +2,8 @@
 //
 // Runs the product's own parser (csrc/jpeg_parser.cpp) for the header and the product's own per-piece
 // logic (csrc/k0_core.cuh, compiled for the host) through a serial emulation of what k0_destuff.cu does
-// in parallel: 16-byte pieces, tiles of 256 pieces, Kogge-Stone warp scans + warp totals inside a tile
+// in parallel: 16-byte pieces, tiles of 16 KiB, Kogge-Stone warp scans + warp totals inside a tile (the kernels
+// fold four pieces per thread first: another bracketing of the same associative composition)
 // (k0_reduce / k0_apply), a chunked scan over the tiles of the image (k0_scan), then the scatter walk of
 // every piece and the segment table. The no-GPU suite compares its result with the host restatement of
 // the same rules (StreamParser::host_scan); the CUDA kernels themselves - including their warp-level
@@ -19,7 +20,7 @@ using namespace rjb;
 using namespace rjb::k0;
 
 namespace {
-constexpr int kThreads = 256, kTile = 4096;
+constexpr int kThreads = 1024, kTile = 16384;   // the kernels' tile: 256 threads x four 16-byte pieces
 
 // the kernels' CtaScan: inclusive Kogge-Stone per warp of 32, then the warp totals
 void CtaScanModel(const std::vector<Elem>& e, std::vector<Elem>* excl, Elem* total) {
