@@ -12,7 +12,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "librocjpeg.so")
+LIB_PATH = os.environ.get("ROCJPEG_B200_LIB") or os.path.join(HERE, "lib", "librocjpeg.so")   # the override serves debugging builds
 
 # RocJpegStatus (include/rocjpeg.h, api/rocjpeg.h:53-67)
 STATUS = {

@@ -698,7 +698,17 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     const int rounds = std::min(std::max(EnvInt("ROCJPEG_B200_SYNC_ROUNDS", 2), 1), kMaxSyncRounds);
     // profiling 1: an event after every stage (they sit between the kernels, so neighbouring stages no longer
     // overlap through programmatic dependent launch); 2: only the first and the last event (total time)
+    // ROCJPEG_B200_DEBUG_SYNC=1: synchronise after every stage and say which one failed
+    static const bool debug_sync = EnvInt("ROCJPEG_B200_DEBUG_SYNC", 0) != 0;
     auto mark = [&](int i) -> cudaError_t {
+        if (debug_sync) {
+            const cudaError_t e = cudaStreamSynchronize(stream_);
+            if (e != cudaSuccess) {
+                static const char* const kNames[] = {"(before)", "upload", "destuff", "huffman sync", "huffman write", "dc", "idct", "output"};
+                std::cerr << "[rocjpeg_b200] stage '" << kNames[i] << "' failed: " << cudaGetErrorName(e) << std::endl;
+                return e;
+            }
+        }
         const bool want = profiling_ == 1 || (profiling_ == 2 && (i == 0 || i == kStageCount));
         return want ? cudaEventRecord(ev_[i], stream_) : cudaSuccess;
     };

@@ -30,6 +30,9 @@
 // element; kept bytes leave through shared memory as 128-bit stores, one run per restart interval.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "k0_core.cuh"
 #include "stages.h"
 
@@ -351,6 +354,8 @@ __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
                        cL = __shfl_sync(0xFFFFFFFFu, ex.tail, leader);
         const bool member = staged && ex.nrst == kL;
         const uint32_t members = __ballot_sync(0xFFFFFFFFu, member);
+        // bytes of the run (every warp-wide exchange of an iteration happens here, before the lanes go separate ways)
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, ex.tail + n, 31 - __clz(int(members))) - cL;
         uint8_t* dst = pl.Dst(rL, kL) + cL;
         const uint32_t phase = uint32_t(reinterpret_cast<uintptr_t>(dst) & 15u);
         if (member) {
@@ -358,21 +363,14 @@ __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
             if (c.fast) {
                 StoreShifted<4 * kPieces>(at, c.w);
             } else {
+                // a chunk with an FF in it (one in five): piece by piece, byte stores. (Word stores for its all-kept pieces,
+                // mixed with the byte-wise compaction of the others, lost the piece behind a compacted one in the generated
+                // code - found by the restart-marker pictures of tests/test_gpu_parity.py; not worth a fifth of the chunks.)
 #pragma unroll
-                for (int j = 0; j < kPieces; j++) {
-                    const Piece pc = PieceOf(c, j, len);
-                    if (pc.keep == 0xFFFFu) {
-                        StoreShifted<4>(at, &c.w[4 * j]);
-                        at += 16;
-                    } else {
-                        at += CompactPiece(pc, at);
-                    }
-                }
+                for (int j = 0; j < kPieces; j++) at += CompactPiece(PieceOf(c, j, len), at);
             }
         }
         __syncwarp();
-        const int last = 31 - __clz(int(members));
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, ex.tail + n, last) - cL;
         const uint8_t* buf = s_stage[warp] + phase;
         uint32_t head = (16u - phase) & 15u;
         if (head > total) head = total;
@@ -422,6 +420,11 @@ cudaError_t LaunchK0Destuff(const K0Args& a, cudaStream_t stream) {
     if (a.total_tiles == 0) return cudaSuccess;
     cudaError_t e = LaunchPdl(k0_scan, dim3(a.nimages), dim3(kThreads), 0, stream, a);
     if (e != cudaSuccess) return e;
+    if (getenv("ROCJPEG_B200_DEBUG_SYNC")) {
+        e = cudaStreamSynchronize(stream);
+        fprintf(stderr, "[rocjpeg_b200] k0_reduce + k0_scan: %s\n", cudaGetErrorName(e));
+        if (e != cudaSuccess) return e;
+    }
     switch (a.sub_bytes) {
         case 32: return LaunchPdl(k0_apply<32>, dim3(a.total_tiles), dim3(kThreads), 0, stream, a);
         case 64: return LaunchPdl(k0_apply<64>, dim3(a.total_tiles), dim3(kThreads), 0, stream, a);
