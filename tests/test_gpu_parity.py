@@ -459,6 +459,15 @@ def test_gpu_destuffing_marker_patterns(dec, zero_copy, S, monkeypatch):
     gu.assert_same(got, want, "clean decode after the marker patterns")
 
 
+@pytest.mark.parametrize("shape", [(3840, 2048, "400"), (512, 4096, "400"), (3840, 2160, "422"), (2048, 1536, "444")])
+def test_gpu_destuffing_large_pictures_with_a_restart_marker_per_mcu_row(dec, shape):
+    """Hundreds of restart intervals of a few KiB each over many 16 KiB tiles: runs of several intervals inside one warp,
+    chunks with stuffed bytes between them (the sizes that exposed a lost 16-byte piece in the staging of k0_apply)."""
+    w, h, css = shape
+    _check_destuffed_batch(dec, [datagen.make_jpeg(w, h, css, seed=400, restart_rows=1)], False)
+    _check_destuffed_batch(dec, [datagen.make_jpeg(w, h, css, seed=401, restart_rows=1), datagen.make_jpeg(w // 2, h // 2, css, seed=402, restart_rows=2)], True)
+
+
 def test_zero_copy_and_staged_sources_decode_identically(dec, orc):
     """JPEG files in the caller's page-locked memory are uploaded in place (any byte alignment), files in pageable memory
     through the staging pool; trailing bytes behind the EOI, and a second picture behind the first, are ignored."""
