@@ -238,6 +238,14 @@ void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out, uint32_t sub_
 
 // ------------------------------------------------------------ StreamParser
 
+bool StreamParser::TablesFailed() {
+    dht_cache_.key.clear();
+    dqt_cache_.key.clear();
+    lut_valid_ = false;
+    p_.valid = false;
+    return false;
+}
+
 bool StreamParser::Fail(const char* why) {
     err_ = why;
     p_.valid = false;
@@ -267,9 +275,9 @@ bool StreamParser::ParseSof(const uint8_t* s, uint32_t seglen) {
 }
 
 // src/rocjpeg_parser.cpp:256-313
-bool StreamParser::ParseDht(const uint8_t* s, uint32_t seglen) {
-    int32_t rem = int32_t(seglen) - 2;
-    const uint8_t* q = s + 2;
+bool StreamParser::ParseDht(const uint8_t* payload, uint32_t n) {
+    int32_t rem = int32_t(n);
+    const uint8_t* q = payload;
     while (rem > 0) {
         if (rem < 17) return Fail("truncated DHT");
         uint8_t idx = *q++;
@@ -293,8 +301,8 @@ bool StreamParser::ParseDht(const uint8_t* s, uint32_t seglen) {
 }
 
 // src/rocjpeg_parser.cpp:217-246
-bool StreamParser::ParseDqt(const uint8_t* s, uint32_t seglen) {
-    const uint8_t *q = s + 2, *end = s + seglen;
+bool StreamParser::ParseDqt(const uint8_t* payload, uint32_t n) {
+    const uint8_t *q = payload, *end = payload + n;
     while (q < end) {
         uint8_t idx = *q++;
         if (idx >> 4) return Fail("16-bit quantisation tables are not supported");   // :230
@@ -304,6 +312,55 @@ bool StreamParser::ParseDqt(const uint8_t* s, uint32_t seglen) {
         p_.qt_present[idx] = true;
         q += 64;
     }
+    return true;
+}
+
+// One DHT / DQT segment of the stream being parsed. While it repeats the previous stream's bytes nothing happens;
+// at the first difference the tables are cleared and every segment seen so far is parsed for real.
+template <class ParseFn, class ClearFn>
+bool StreamParser::TakeTableSegment(TableCache& c, const uint8_t* payload, uint32_t n, ParseFn parse, ClearFn clear) {
+    if (c.nseg < 8) {
+        c.seg[c.nseg] = payload;
+        c.seglen[c.nseg] = n;
+    }
+    c.nseg++;
+    if (c.matching) {
+        if (c.nseg <= 8 && c.cursor + n <= c.key.size() && std::memcmp(c.key.data() + c.cursor, payload, n) == 0) {
+            c.cursor += n;
+            return true;
+        }
+        c.matching = false;   // diverged: what matched so far belongs to tables that no longer apply
+        c.changed = true;
+        c.key.clear();
+        clear();
+        for (int i = 0; i + 1 < c.nseg && i < 8; i++)
+            if (!parse(c.seg[i], c.seglen[i])) return false;
+    } else if (!c.changed) {
+        c.changed = true;
+        c.key.clear();
+        clear();
+    }
+    return parse(payload, n);
+}
+
+// All table segments of the stream have been seen: a stream that only repeated a prefix of the previous one's
+// is re-parsed; the key of the next comparison is this stream's.
+template <class ParseFn, class ClearFn>
+bool StreamParser::FinishTableSegments(TableCache& c, ParseFn parse, ClearFn clear) {
+    if (c.matching && c.cursor == c.key.size()) return true;   // identical tables: everything derived from them stands
+    if (c.matching) {
+        c.matching = false;
+        c.changed = true;
+        clear();
+        for (int i = 0; i < c.nseg && i < 8; i++)
+            if (!parse(c.seg[i], c.seglen[i])) {
+                c.key.clear();
+                return false;
+            }
+    }
+    c.key.clear();
+    if (c.nseg <= 8)
+        for (int i = 0; i < c.nseg; i++) c.key.insert(c.key.end(), c.seg[i], c.seg[i] + c.seglen[i]);
     return true;
 }
 
@@ -483,10 +540,11 @@ void StreamParser::BuildDecodeTables() {
             else if (!p_.dc[p_.td[i]].present || !p_.ac[p_.ta[i]].present) p_.support_status = kStatusBadJpeg;
         }
     }
-    for (int t = 0; t < 4; t++)
-        for (int k = 0; k < 64; k++) p_.qt_natural[t][kZigzag[k]] = p_.qt[t][k];
-    // Identity of the four Huffman tables. Streams parsed through the same handle very often
-    // repeat the previous tables (the standard ones): the decoder-form LUTs are then kept.
+    if (dqt_cache_.changed)
+        for (int t = 0; t < 4; t++)
+            for (int k = 0; k < 64; k++) p_.qt_natural[t][kZigzag[k]] = p_.qt[t][k];
+    if (!dht_cache_.changed && lut_valid_) return;   // same DHT bytes as the previous stream: hash, bounds and LUTs stand
+    // Identity of the four Huffman tables (batch de-duplication in the decoder).
     uint64_t h = 1469598103934665603ull;
     auto mix = [&](const void* ptr, size_t n) {
         const uint8_t* b = static_cast<const uint8_t*>(ptr);
@@ -516,35 +574,55 @@ void StreamParser::BuildDecodeTables() {
                 }
         }
     p_.min_entry_bits = min_bits < 2 ? 2 : (min_bits > 31 ? 2 : min_bits);
-    const bool same = lut_valid_ && h == lut_spec_hash_ && std::memcmp(lut_spec_dc_, p_.dc, sizeof(p_.dc)) == 0 &&
-                      std::memcmp(lut_spec_ac_, p_.ac, sizeof(p_.ac)) == 0;
-    if (!same) {
-        std::memset(&lut_, 0, sizeof(lut_));
-        // debug knob: a smaller second-level arena forces long codes onto the canonical search
-        const char* cap_env = std::getenv("ROCJPEG_B200_SUBCAP");
-        const uint32_t cap = (cap_env && *cap_env) ? uint32_t(std::atoi(cap_env)) : uint32_t(kSubCap);
-        for (int t = 0; t < 2; t++) {
-            if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &lut_, cap);
-            if (p_.ac[t].present) BuildHuffLut(p_.ac[t], 2 + t, &lut_, cap);
-        }
-        std::memcpy(lut_spec_dc_, p_.dc, sizeof(p_.dc));
-        std::memcpy(lut_spec_ac_, p_.ac, sizeof(p_.ac));
-        lut_spec_hash_ = h;
-        lut_valid_ = true;
+    std::memset(&lut_, 0, sizeof(lut_));
+    // debug knob: a smaller second-level arena forces long codes onto the canonical search
+    const char* cap_env = std::getenv("ROCJPEG_B200_SUBCAP");
+    const uint32_t cap = (cap_env && *cap_env) ? uint32_t(std::atoi(cap_env)) : uint32_t(kSubCap);
+    for (int t = 0; t < 2; t++) {
+        if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &lut_, cap);
+        if (p_.ac[t].present) BuildHuffLut(p_.ac[t], 2 + t, &lut_, cap);
     }
+    lut_cap_ = cap;
+    lut_valid_ = true;
+}
+
+// Everything of the previous stream except its tables (the reference zeroes its parameters on every parse,
+// parser.cpp:54; the tables are compared segment by segment instead, see TableCache).
+void StreamParser::ResetFrame() {
+    p_.valid = false;
+    p_.width = p_.height = p_.ncomp = 0;
+    p_.css = CSS_UNKNOWN;
+    for (int i = 0; i < 3; i++) p_.comp_id[i] = p_.hs[i] = p_.vs[i] = p_.tq[i] = p_.td[i] = p_.ta[i] = p_.blocks_w[i] = p_.blocks_h[i] = 0;
+    p_.scan_ncomp = p_.restart_interval = 0;
+    p_.num_mcus_ref = p_.scan_offset = p_.raw_bytes = 0;
+    p_.hmax = p_.vmax = 1;
+    p_.mcus_x = p_.mcus_y = p_.bpm = 0;
+    p_.support_status = 0;
+    p_.nseg = 1;
+    raw_ = RawScan();
+    host_scan_.done = false;
+    err_.clear();
+    dht_cache_.Begin();
+    dqt_cache_.Begin();
 }
 
 bool StreamParser::Parse(const uint8_t* d, size_t len) {
     std::lock_guard<std::mutex> lock(mutex_);
-    // the reference zeroes its parameters on every parse (parser.cpp:54)
-    p_ = ParsedJpeg();
-    raw_ = RawScan();
-    host_scan_.done = false;
-    err_.clear();
+    ResetFrame();
     if (!d || len < 4) return Fail("stream too short");
     if (d[0] != 0xFF || d[1] != 0xD8) return Fail("missing SOI");                   // parser.cpp:64
     size_t p = 2;
     bool seen_dht = false, seen_dqt = false, seen_sos = false, seen_sof0 = false;
+    auto parse_dht = [this](const uint8_t* q, uint32_t n) { return ParseDht(q, n); };
+    auto parse_dqt = [this](const uint8_t* q, uint32_t n) { return ParseDqt(q, n); };
+    auto clear_dht = [this]() {
+        for (int t = 0; t < 2; t++) p_.dc[t].present = p_.ac[t].present = false;
+        lut_valid_ = false;
+    };
+    auto clear_dqt = [this]() {
+        for (int t = 0; t < 4; t++) p_.qt_present[t] = false;
+        std::memset(p_.qt, 0, sizeof(p_.qt));
+    };
     uint8_t other_sof = 0;   // a frame header this decoder (like the reference: parser.cpp:82, SOF = 0xC0 only) does not handle
     while (!seen_sos) {
         if (p + 4 > len) return Fail("truncated before SOS");
@@ -561,8 +639,14 @@ bool StreamParser::Parse(const uint8_t* d, size_t len) {
             case 0xCE: case 0xCF:
                 other_sof = m;   // skipped by length as the reference does; the scan header then has no frame to refer to
                 break;
-            case 0xC4: if (!ParseDht(s, seglen)) return false; seen_dht = true; break;
-            case 0xDB: if (!ParseDqt(s, seglen)) return false; seen_dqt = true; break;
+            case 0xC4:
+                if (!TakeTableSegment(dht_cache_, s + 2, seglen - 2, parse_dht, clear_dht)) return TablesFailed();
+                seen_dht = true;
+                break;
+            case 0xDB:
+                if (!TakeTableSegment(dqt_cache_, s + 2, seglen - 2, parse_dqt, clear_dqt)) return TablesFailed();
+                seen_dqt = true;
+                break;
             case 0xDD:                                                              // parser.cpp:374-390
                 if (seglen != 4) return Fail("bad DRI length");
                 p_.restart_interval = int32_t(Rd16(s + 2));
@@ -588,6 +672,7 @@ bool StreamParser::Parse(const uint8_t* d, size_t len) {
     }
     if (!seen_dht) return Fail("no Huffman table before SOS");                     // parser.cpp:111-118
     if (!seen_dqt) return Fail("no quantisation table before SOS");
+    if (!FinishTableSegments(dht_cache_, parse_dht, clear_dht) || !FinishTableSegments(dqt_cache_, parse_dqt, clear_dqt)) return TablesFailed();
     DeriveGeometry();
     p_.scan_offset = uint32_t(p);
     p_.raw_bytes = uint32_t(len - p);

@@ -164,20 +164,36 @@ class StreamParser {
   private:
     bool Fail(const char* why);
     bool ParseSof(const uint8_t* s, uint32_t seglen);
-    bool ParseDht(const uint8_t* s, uint32_t seglen);
-    bool ParseDqt(const uint8_t* s, uint32_t seglen);
+    bool ParseDht(const uint8_t* payload, uint32_t n);   // payload = the segment behind its two length bytes
+    bool ParseDqt(const uint8_t* payload, uint32_t n);
     bool ParseSos(const uint8_t* s, uint32_t seglen);
     void DeriveGeometry();
     void ExtractEntropyData(const uint8_t* d, size_t length, HostScan* out) const;
     void BuildDecodeTables();
     void AdoptSource(const uint8_t* scan, size_t nbytes);
+    void ResetFrame();
+    // Table segments (DHT / DQT) of the stream being parsed against the previous stream's: while the payload bytes
+    // repeat - the normal case, the same encoder wrote the files - nothing is re-parsed, re-hashed or rebuilt.
+    struct TableCache {
+        std::vector<uint8_t> key;                           // payloads of the previous stream's segments, concatenated
+        size_t cursor = 0;                                  // bytes of `key` matched so far
+        bool matching = false;                              // every segment so far repeated the previous stream's
+        bool changed = false;                               // the tables were re-parsed during this Parse()
+        const uint8_t* seg[8] = {};                         // this stream's segments (payload pointers / lengths) ...
+        uint32_t seglen[8] = {};
+        int nseg = 0;                                       // ... more than 8: no caching
+        void Begin() { cursor = 0; matching = !key.empty(); changed = false; nseg = 0; }
+    };
+    template <class ParseFn, class ClearFn> bool TakeTableSegment(TableCache& c, const uint8_t* payload, uint32_t n, ParseFn parse, ClearFn clear);
+    template <class ParseFn, class ClearFn> bool FinishTableSegments(TableCache& c, ParseFn parse, ClearFn clear);
+    TableCache dht_cache_, dqt_cache_;
 
     mutable std::mutex mutex_;
     ParsedJpeg p_;
     HuffLutSet lut_ = {};             // kept across parses while the DHT content does not change
-    HuffSpec lut_spec_dc_[2] = {}, lut_spec_ac_[2] = {};
-    uint64_t lut_spec_hash_ = 0;
+    uint32_t lut_cap_ = 0;
     bool lut_valid_ = false;
+    bool TablesFailed();              // a table segment was rejected: nothing of it may be reused by the next parse
     RawScan raw_;
     PooledBuffer staging_;            // page-locked copy of pageable input
     mutable HostScan host_scan_;

@@ -279,6 +279,31 @@ def test_encoder_optimised_huffman_tables(dec, orc, css):
         gu.assert_same(gu.fetch(bufs, pitches, shapes), want, f"mixed tables batch {css} #{k}")
 
 
+def test_one_stream_handle_reused_across_pictures_with_different_tables(dec, orc):
+    """The parser keeps the previous stream's decoder-form tables while the DHT / DQT bytes repeat; a handle that sees
+    standard tables, optimised tables, other quantisers and standard tables again must decode each picture exactly."""
+    import io
+
+    import torch
+    from PIL import Image
+
+    img = datagen.synth_image(200, 136, seed=8)
+    files = [load("synth_420_500x375_dri7"), load("custom_huffman_420_dri1")]
+    for q, ss, opt in ((85, 0, True), (60, 2, True), (97, 1, False), (85, 0, True)):
+        bio = io.BytesIO()
+        Image.fromarray(img).save(bio, format="JPEG", quality=q, subsampling=ss, optimize=opt)
+        files.append(bio.getvalue())
+    files += [files[0], files[2], files[1]]
+    s = api.JpegStream()
+    for k, data in enumerate(files):
+        assert s.parse(data) == api.SUCCESS
+        rc, info = orc.parse(data)
+        dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "rgb", (0, 0, 0, 0))
+        assert dec.decode(s, api.make_params("rgb"), dest) == api.SUCCESS
+        _, want = gu.oracle_outputs(orc, data, "rgb", (0, 0, 0, 0), pitches)
+        gu.assert_same(gu.fetch(bufs, pitches, shapes), want, f"reused handle, picture {k}")
+
+
 def test_damaged_scans_do_not_break_the_decoder(dec, orc):
     """Random byte damage inside the entropy-coded data (and truncation): whatever comes out, the call
     must return, the device must stay healthy and the next clean decode must be bit-exact."""
