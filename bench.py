@@ -203,6 +203,94 @@ def run_cpu_baseline(datas, fmt, budget_s=12.0, threads=None):
     return mp * passes / el / 1e6, len(datas) * passes / el, threads, sample
 
 
+def measure_inlib(api, torch, workload, args, ndev, dev0, ready):
+    """One parse + rocJpegDecodeBatched per step, sharded by the library over `ndev` GPUs (ROCJPEG_B200_DEVICES); see main().
+    `ready` = the already built single-GPU objects of the same workload (or None: build them, incl. the 1-GPU time)."""
+    import numpy as np
+
+    import oracle
+
+    if ready is None:
+        datas, fmt = build_workload(workload, args.batch or None)
+        _, dims = pixels_of(datas)
+        offs, total = [], 0
+        for d in datas:
+            offs.append(total)
+            total += (len(d) + 63) // 64 * 64
+        arena = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
+        an = arena.numpy()
+        for o, d in zip(offs, datas):
+            an[o:o + len(d)] = memoryview(d)
+        addrs, lens, dests0, single_ms = [arena.data_ptr() + o for o in offs], [len(d) for d in datas], None, None
+    else:
+        datas, fmt, dims, addrs, lens, arena, dests0, single_ms = ready
+    total_px = sum(w * h for (w, h, _) in dims)
+    params = api.make_params(fmt)
+
+    def alloc(devices):
+        dests, keep = [], []
+        for (w, h, css), dv in zip(dims, devices):
+            chans = api.output_channel_shapes(css, fmt, w, h)
+            pitches = [rb for (_, rb) in chans]
+            if fmt == "yuv_planar" and css in ("422", "420"):
+                pitches[2] = pitches[1]
+            bufs = [torch.zeros(rows * p + 64, dtype=torch.uint8, device=f"cuda:{dv}") for (rows, _), p in zip(chans, pitches)]
+            keep.append((bufs, pitches, chans))
+            dests.append([(b.data_ptr(), p) for b, p in zip(bufs, pitches)])
+        return dests, keep
+
+    def timed(dec, streams, dests):
+        batch, sources = dec.make_batch(streams, dests), dec.make_sources(addrs, lens)
+        for _ in range(args.warmup + 2):
+            st, _ = dec.parse_and_decode_batched(batch, sources, params)
+            assert st == api.SUCCESS, st
+        ts = []
+        for _ in range(args.steps):
+            for dv in range(torch.cuda.device_count()):
+                torch.cuda.synchronize(dv)
+            t0 = time.perf_counter()
+            st, _ = dec.parse_and_decode_batched(batch, sources, params)
+            ts.append(time.perf_counter() - t0)
+            assert st == api.SUCCESS, st
+        return 1e3 * sum(ts) / len(ts), dec.stats()
+
+    streams = []
+    for a, n in zip(addrs, lens):
+        s = api.JpegStream()
+        assert s.parse_ptr(a, n, arena) == api.SUCCESS
+        streams.append(s)
+    if single_ms is None:      # 1-GPU time of this workload through the same calls
+        dec1 = api.Decoder(api.BACKEND_HARDWARE, dev0)
+        dests0, keep0 = alloc([dev0] * len(datas))
+        single_ms, _ = timed(dec1, streams, dests0)
+        dec1.close()
+    os.environ["ROCJPEG_B200_DEVICES"] = str(ndev)
+    decn = api.Decoder(api.BACKEND_HARDWARE, dev0)
+    del os.environ["ROCJPEG_B200_DEVICES"]
+    used = decn.num_devices()
+    out = {"devices_used": used, "single_gpu_ms": round(single_ms, 4)}
+    orc = oracle.Oracle()
+    ncount = torch.cuda.device_count()
+    plan = api.plan_shards([s.info().raw_bytes for s in streams], used)
+    for mode, devices in (("all_destinations_on_gpu0", [dev0] * len(datas)), ("destinations_colocated", [(dev0 + int(k)) % ncount for k in plan])):
+        dests, keep = alloc(devices)
+        ms, stn = timed(decn, streams, dests)
+        ok = True
+        for i in sorted(set([0, len(datas) // 3, len(datas) - 1])):   # a sample of the outputs against the oracle
+            bufs, pitches, chans = keep[i]
+            _, want = orc.decode(datas[i], fmt, pitches=pitches)
+            for b, p, (rows, rb), wnt in zip(bufs, pitches, chans, want):
+                got = b.cpu().numpy()[:rows * p].reshape(rows, p)[:, :rb]
+                ok = ok and bool(np.array_equal(got, wnt[:rows, :rb]))
+        out[mode] = {"ms_per_step": round(ms, 4), "value": round(total_px / 1e6 / (ms / 1e3), 1), "unit": UNIT,
+                     "speedup_vs_1gpu": round(single_ms / ms, 3), "efficiency": round(single_ms / ms / used, 3),
+                     "host_submit_ms": round(stn.host_submit_ms, 4), "host_wait_ms": round(stn.host_wait_ms, 4),
+                     "devices": int(stn.devices), "verified_against_oracle": ok}
+        del dests, keep
+    decn.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,8 +302,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inlib-devices", type=int, default=0,
-                    help="single process: shard each rocJpegDecodeBatched call over this many GPUs inside the library "
-                         "(ROCJPEG_B200_DEVICES), every destination on GPU 0; reported under e2e_inlib")
+                    help="single process: also shard each rocJpegDecodeBatched call over this many GPUs inside the library "
+                         "(ROCJPEG_B200_DEVICES); reported under `inlib` (under torchrun rank 0 does this with all N GPUs)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank decodes a full batch; strong: one batch sharded over the ranks by scan bytes")
     args = ap.parse_args()
@@ -416,26 +504,22 @@ def main():
         assert rc == api.SUCCESS
     clocks = sampler.stop()
     dec.set_profiling(False)
-    # optional: one process, the library shards the same call over several GPUs (destinations stay on this GPU)
+    # ---- one call sharded inside the library over N GPUs (north star item 6) -----------------
+    # Rank 0 alone, while the other ranks wait at a CPU barrier with idle GPUs: one rocJpegStreamParse x batch +
+    # rocJpegDecodeBatched through a handle created with ROCJPEG_B200_DEVICES=N, (i) every destination on GPU 0
+    # (the reference samples' layout: pixels of the peers' shares cross NVLink), (ii) destinations co-located with
+    # the device the library's own plan gives each image (no pixel crosses a link).
     inlib = None
-    if args.inlib_devices > 1 and world == 1:
-        os.environ["ROCJPEG_B200_DEVICES"] = str(args.inlib_devices)
-        decn = api.Decoder(api.BACKEND_HARDWARE, local_rank)
-        del os.environ["ROCJPEG_B200_DEVICES"]
-        for _ in range(args.warmup + 2):
-            assert decn.decode_batched(batch, params) == api.SUCCESS
-        ts = []
-        for _ in range(args.steps):
-            l2_flush()
-            t0 = time.perf_counter()
-            assert decn.decode_batched(batch, params) == api.SUCCESS
-            ts.append(time.perf_counter() - t0)
-        sn = decn.stats()
-        ms = 1e3 * sum(ts) / len(ts)
-        inlib = {"devices_requested": args.inlib_devices, "devices_used": int(sn.devices), "value": round(total_px / 1e6 / (ms / 1e3), 1),
-                 "unit": UNIT, "ms_per_step": round(ms, 4), "host_submit_ms": round(sn.host_submit_ms, 4),
-                 "host_wait_ms": round(sn.host_wait_ms, 4), "note": "one rocJpegDecodeBatched call sharded by the library, all destinations on GPU 0"}
-        decn.close()
+    ndev_inlib = world if world > 1 else args.inlib_devices
+    if world > 1:
+        rdist.cpu_barrier()
+    if ndev_inlib > 1 and rank == 0 and torch.cuda.device_count() >= ndev_inlib:
+        inlib = {"devices_requested": ndev_inlib, "single_gpu_e2e_ms": round(e2e_ms, 4), "workloads": {}}
+        for wl in ([args.workload] if world == 1 else [args.workload, "c4_dri"]):
+            inlib["workloads"][wl] = measure_inlib(api, torch, wl, args, ndev_inlib, local_rank,
+                                                   (datas, fmt, dims, addrs, lens, arena, dests, e2e_ms) if wl == args.workload else None)
+    if world > 1:
+        rdist.cpu_barrier()
 
     # max over ranks
     pre_ms, pg_ms = 1e3 * sum(pre_s) / len(pre_s), 1e3 * sum(pg_s) / len(pg_s)
@@ -518,7 +602,7 @@ def main():
         "e2e_host": {"submit_ms": round(e2e_stats.host_submit_ms, 4), "wait_ms": round(e2e_stats.host_wait_ms, 4)},
     }
     if inlib:
-        line["e2e_inlib"] = inlib
+        line["inlib"] = inlib
     if not args.no_cpu_baseline:
         mps, ips, threads, sample = run_cpu_baseline(datas, fmt, args.cpu_budget)
         line["cpu_baseline"] = {"value": round(mps, 2), "unit": UNIT, "images_per_s": round(ips, 1), "cores": threads, "kind": "port",

@@ -131,14 +131,19 @@ RocJpegStatus rocJpegB200StreamGetQuantTable(RocJpegStreamHandle jpeg_stream_han
 RocJpegStatus rocJpegB200StreamGetHuffmanTable(RocJpegStreamHandle jpeg_stream_handle, int is_ac, int id, uint8_t bits[16],
                                                uint8_t vals[256], uint32_t *count);
 
-/* Multi-GPU sharding of rocJpegDecodeBatched (images are independent: no collective). With the
- * environment variable ROCJPEG_B200_DEVICES=N (N > 1) set when rocJpegCreate runs, the handle also
- * drives the N-1 devices after device_id; each batch is then split by the longest-processing-time
- * rule over the devices, every device decodes its share concurrently and stores its pixels straight
- * into the caller's buffers (peer access over NVLink), which must live on the handle's device.
- * rocJpegB200PlanShards exposes the assignment rule (host only): cost[i] = entropy-coded bytes of
- * image i, out_device[i] in [0, num_devices). rocJpegB200GetDeviceCount = devices the handle drives. */
+/* Multi-GPU sharding of rocJpegDecodeBatched (images are independent: no collective). With the environment variable
+ * ROCJPEG_B200_DEVICES=N (N > 1) set when rocJpegCreate runs, the handle also drives the N-1 devices after device_id.
+ * Each batch is then split over the devices: an image whose destination buffer lives on one of those peer devices is
+ * decoded there (nothing of it crosses a link); the others - destinations on the handle's own device, the layout of the
+ * reference's samples - are dealt by the longest-processing-time rule on entropy-coded bytes, and the shares of the
+ * peers are delivered into the handle's device over NVLink (row-wise stores of the output stage through peer access).
+ * Every device decodes its share concurrently; the join is one stream sync per device. A destination on a device the
+ * handle does not drive is rejected (INVALID_PARAMETER).
+ * rocJpegB200PlanShards / ...Pinned expose the assignment rule (host only): cost[i] = entropy-coded bytes of image i,
+ * fixed[i] >= 0 pins image i to that device (fixed may be NULL), out_device[i] in [0, num_devices) = index among the
+ * devices the handle drives (0 = device_id). rocJpegB200GetDeviceCount = devices the handle drives. */
 RocJpegStatus rocJpegB200PlanShards(const uint64_t *cost, int batch_size, int num_devices, int *out_device);
+RocJpegStatus rocJpegB200PlanShardsPinned(const uint64_t *cost, const int *fixed, int batch_size, int num_devices, int *out_device);
 RocJpegStatus rocJpegB200GetDeviceCount(RocJpegHandle handle, int *num_devices);
 
 const char *rocJpegB200Version(void);

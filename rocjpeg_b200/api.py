@@ -97,6 +97,7 @@ EXT_EXPORTS = (
     "rocJpegB200StreamGetQuantTable", "rocJpegB200StreamGetHuffmanTable", "rocJpegB200Version", "rocJpegB200StreamGetLastError",
     "rocJpegB200PlanShards", "rocJpegB200GetDeviceCount", "rocJpegB200StreamHostScan",
     "rocJpegB200GetScanStatus", "rocJpegB200GetDeviceSegment", "rocJpegB200ParseAndDecodeBatched",
+    "rocJpegB200PlanShardsPinned",
 )
 
 _lib = None
@@ -146,6 +147,7 @@ def load_library() -> C.CDLL:
     L.rocJpegB200StreamGetQuantTable.argtypes = [vp, i32, vp]
     L.rocJpegB200StreamGetHuffmanTable.argtypes = [vp, i32, i32, vp, vp, C.POINTER(C.c_uint32)]
     L.rocJpegB200PlanShards.argtypes = [vp, i32, i32, vp]
+    L.rocJpegB200PlanShardsPinned.argtypes = [vp, vp, i32, i32, vp]
     L.rocJpegB200GetDeviceCount.argtypes = [vp, C.POINTER(i32)]
     L.rocJpegB200Version.restype = C.c_char_p
     for name in EXPORTS + EXT_EXPORTS:
@@ -162,6 +164,18 @@ def plan_shards(costs, num_devices: int):
     c = np.ascontiguousarray(costs, dtype=np.uint64)
     out = np.zeros(len(c), dtype=np.int32)
     _check(load_library().rocJpegB200PlanShards(c.ctypes.data, len(c), num_devices, out.ctypes.data), "rocJpegB200PlanShards")
+    return out
+
+
+def plan_shards_pinned(costs, fixed, num_devices: int):
+    """plan_shards with some images pinned to a device (fixed[i] >= 0): what the library does with destination buffers
+    that already live on a peer device."""
+    import numpy as np
+
+    c = np.ascontiguousarray(costs, dtype=np.uint64)
+    f = np.ascontiguousarray(fixed, dtype=np.int32)
+    out = np.zeros(len(c), dtype=np.int32)
+    _check(load_library().rocJpegB200PlanShardsPinned(c.ctypes.data, f.ctypes.data, len(c), num_devices, out.ctypes.data), "rocJpegB200PlanShardsPinned")
     return out
 
 

@@ -289,6 +289,12 @@ RocJpegStatus rocJpegB200PlanShards(const uint64_t* cost, int batch_size, int nu
     return ROCJPEG_STATUS_SUCCESS;
 }
 
+RocJpegStatus rocJpegB200PlanShardsPinned(const uint64_t* cost, const int* fixed, int batch_size, int num_devices, int* out_device) {
+    if (cost == nullptr || out_device == nullptr || batch_size < 0 || num_devices < 1) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    rjb::PlanShardsPinned(cost, fixed, batch_size, num_devices, out_device);
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
 RocJpegStatus rocJpegB200GetDeviceCount(RocJpegHandle handle, int* num_devices) {
     if (handle == nullptr || num_devices == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
     *num_devices = static_cast<DecoderHandle*>(handle)->decoder->num_devices();

@@ -260,12 +260,35 @@ int Decoder::Initialize() {
     return kSuccess;
 }
 
-void PlanShards(const uint64_t* cost, int n, int ndev, int* out_device) {
+namespace {
+// Device that owns a device pointer; -1 for anything else (host memory, null, unknown).
+int DeviceOfPointer(const void* p) {
+    if (!p) return -1;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    return at.type == cudaMemoryTypeDevice ? at.device : -1;
+}
+}  // namespace
+
+void PlanShards(const uint64_t* cost, int n, int ndev, int* out_device) { PlanShardsPinned(cost, nullptr, n, ndev, out_device); }
+
+void PlanShardsPinned(const uint64_t* cost, const int* fixed, int n, int ndev, int* out_device) {
     if (ndev < 1) ndev = 1;
-    std::vector<int> order(size_t(std::max(n, 0)));
-    for (int i = 0; i < n; i++) order[size_t(i)] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<int> order;
+    order.reserve(size_t(std::max(n, 0)));
     std::vector<uint64_t> load(size_t(ndev), 0);
+    for (int i = 0; i < n; i++) {
+        if (fixed && fixed[i] >= 0 && fixed[i] < ndev) {
+            out_device[i] = fixed[i];
+            load[size_t(fixed[i])] += cost[i] + 1;
+        } else {
+            order.push_back(i);
+        }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     for (int i : order) {
         int best = 0;
         for (int d = 1; d < ndev; d++)
@@ -316,7 +339,7 @@ static uint64_t OutputBytes(int css, int fmt, int W, int H) {
     }
 }
 
-int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
+int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, const uint8_t* remote) {
     if (params.output_format < FMT_NATIVE || params.output_format > FMT_RGB_PLANAR)
         return Fail(kInvalidParameter, "unknown output format");
     h_images_.assign(size_t(n), ImageDesc{});
@@ -512,7 +535,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         const bool whole = od.x0 == 0 && od.y0 == 0 && od.w == p.width && od.h == p.height;
         const bool planar = od.fmt == FMT_Y || od.fmt == FMT_YUV_PLANAR ||
                             (od.fmt == FMT_NATIVE && (p.css == CSS_444 || p.css == CSS_440 || p.css == CSS_400));
-        od.direct = (whole && planar && direct_ok) ? 1 : 0;
+        od.direct = (whole && planar && direct_ok && !(remote && remote[i])) ? 1 : 0;
         od.tiles_x = od.direct ? 0u : uint32_t((od.w + kK3TileW - 1) / kK3TileW);
         od.tiles_y = od.direct ? 0u : uint32_t((od.h + kK3TileH - 1) / kK3TileH);
         any_direct_ = any_direct_ || od.direct || !whole;   // the plane arena is then incomplete: the tap re-runs the IDCT
@@ -845,7 +868,7 @@ int Decoder::Split(const StreamParser* const* streams, int n) {
     return active_lanes_;
 }
 
-int Decoder::BuildAll(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, bool launch) {
+int Decoder::BuildAll(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, bool launch, const uint8_t* remote) {
     // validate the whole batch before anything is launched: an error leaves every destination untouched
     for (int i = 0; i < n; i++) {
         if (!streams[i]) return Fail(kInvalidParameter, "null stream handle in batch");
@@ -883,7 +906,7 @@ int Decoder::BuildAll(const StreamParser* const* streams, int n, const DecodePar
         UploadTurn ut;
         ut.turn = threaded ? &turn : nullptr;
         ut.mine = l;
-        int st = lane.Build(streams + first, cnt, params, dsts + first);
+        int st = lane.Build(streams + first, cnt, params, dsts + first, remote ? remote + first : nullptr);
         if (st == kSuccess) st = launch ? lane.LaunchAll(true, profiling_, upload_stream_, ut) : lane.Upload(upload_stream_, ut);
         else TurnGuard pass(ut);   // never reached the upload: pass the turn on
         status[l] = st;
@@ -968,10 +991,10 @@ int Decoder::Decode(const StreamParser* const* streams, int n, const DecodeParam
     return st;
 }
 
-int Decoder::Submit(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts) {
+int Decoder::Submit(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, const uint8_t* remote) {
     DeviceGuard guard(device_id_);
     prepared_ = false;
-    return BuildAll(streams, n, params, dsts, true);
+    return BuildAll(streams, n, params, dsts, true, remote);
 }
 
 int Decoder::Wait() {
@@ -993,16 +1016,31 @@ int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const Deco
         if (p.support_status != kSuccess) return Fail(p.support_status, "unsupported or inconsistent JPEG");
         cost[size_t(i)] = p.raw_bytes;
     }
+    // Where does each destination live? An image whose buffer is on one of the peer devices this handle drives is
+    // decoded there (its pixels never cross a link); the others - buffers on the handle's own device, the reference
+    // samples' case - are dealt by the longest-processing-time rule over all devices, and those that land on a peer
+    // are delivered over NVLink.
+    std::vector<int> fixed(static_cast<size_t>(n), -1), owner(static_cast<size_t>(n), 0);
+    for (int i = 0; i < n; i++) {
+        const int dev = DeviceOfPointer(dsts[i].channel[0]);
+        for (int d = 1; d < ndev; d++)
+            if (dev == peers_[size_t(d - 1)]->device_id()) fixed[size_t(i)] = d;
+        if (dev >= 0 && dev != device_id_ && fixed[size_t(i)] < 0)
+            return Fail(kInvalidParameter, "destination buffer on a device this handle does not drive");
+        owner[size_t(i)] = fixed[size_t(i)] >= 0 ? fixed[size_t(i)] : 0;
+    }
     shard_dev_.assign(size_t(n), 0);
     shard_local_.assign(size_t(n), 0);
-    PlanShards(cost.data(), n, ndev, shard_dev_.data());
+    PlanShardsPinned(cost.data(), fixed.data(), n, ndev, shard_dev_.data());
     std::vector<std::vector<const StreamParser*>> sub_streams(static_cast<size_t>(ndev));
     std::vector<std::vector<DestImage>> sub_dsts(static_cast<size_t>(ndev));
+    std::vector<std::vector<uint8_t>> sub_remote(static_cast<size_t>(ndev));
     for (int i = 0; i < n; i++) {
         const size_t d = size_t(shard_dev_[size_t(i)]);
         shard_local_[size_t(i)] = int(sub_streams[d].size());
         sub_streams[d].push_back(streams[i]);
         sub_dsts[d].push_back(dsts[i]);
+        sub_remote[d].push_back(uint8_t(int(d) != owner[size_t(i)] ? 1 : 0));
     }
     // enqueue everything on every device - one submitter thread per device, the caller's thread taking
     // this handle's device - then join: the devices run concurrently
@@ -1012,7 +1050,8 @@ int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const Deco
     auto submit = [&](int d) {
         if (sub_streams[size_t(d)].empty()) return;
         Decoder* dec = d == 0 ? this : peers_[size_t(d - 1)].get();
-        sub_status[size_t(d)] = dec->Submit(sub_streams[size_t(d)].data(), int(sub_streams[size_t(d)].size()), params, sub_dsts[size_t(d)].data());
+        sub_status[size_t(d)] = dec->Submit(sub_streams[size_t(d)].data(), int(sub_streams[size_t(d)].size()), params, sub_dsts[size_t(d)].data(),
+                                             sub_remote[size_t(d)].data());
         submitted[size_t(d)] = sub_status[size_t(d)] == kSuccess ? 1 : 0;
     };
     if (!shard_pool_) shard_pool_.reset(new SubmitPool(ndev - 1));

@@ -126,7 +126,9 @@ class Lane {
     Lane(const Lane&) = delete;
     Lane& operator=(const Lane&) = delete;
     int Create(int device_id, int sm_count);
-    int Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
+    // remote[i] != 0: image i's destination lives on another GPU (stores go over NVLink: rows through the output stage, not the
+    // IDCT stage's scattered block stores); nullptr: all local
+    int Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, const uint8_t* remote = nullptr);
     int Upload(cudaStream_t upload_stream, UploadTurn turn = UploadTurn());   // nullptr: use the lane's own stream
     int LaunchAll(bool include_upload, int profiling, cudaStream_t upload_stream, UploadTurn turn = UploadTurn());
     int Finish(int profiling);
@@ -190,6 +192,9 @@ constexpr int kMaxDevices = 16;
 // independent units (no exchange step), so this is the whole "parallelism
 // plan" of a sharded rocJpegDecodeBatched. out_device[i] in [0, ndev).
 void PlanShards(const uint64_t* cost, int n, int ndev, int* out_device);
+// The same with some images already placed: fixed[i] >= 0 pins image i to that device (its destination buffer lives
+// there), fixed[i] < 0 leaves it to the rule; the pinned images' costs count as load before the others are dealt.
+void PlanShardsPinned(const uint64_t* cost, const int* fixed, int n, int ndev, int* out_device);
 
 class Decoder {
   public:
@@ -218,11 +223,11 @@ class Decoder {
     // writes its pixels straight into the caller's buffers (peer stores over NVLink when the
     // buffer lives on another GPU). No collective: the join is one stream sync per device.
     int DecodeSharded(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);
-    int Submit(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts);   // async part
+    int Submit(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, const uint8_t* remote);   // async part
     int Wait();
     int Fail(int status, const std::string& why);
     int Split(const StreamParser* const* streams, int n);
-    int BuildAll(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, bool launch);
+    int BuildAll(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, bool launch, const uint8_t* remote = nullptr);
     int FinishAll();
     void Aggregate();
     // image index of the last call -> the decoder (this or a peer) and lane that holds it, index inside the lane

@@ -23,6 +23,22 @@ def init(backend: str, device=None):
     return rank, world
 
 
+_cpu_group = None
+
+
+def cpu_barrier():
+    """A barrier that keeps the GPUs idle while ranks wait (gloo over the loopback): an NCCL barrier parks a spinning
+    kernel on every waiting rank's GPU, which would disturb a measurement another rank makes on those GPUs."""
+    global _cpu_group
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    if _cpu_group is None:
+        _cpu_group = dist.new_group(backend="gloo")
+    dist.barrier(group=_cpu_group)
+
+
 def barrier():
     import torch.distributed as dist
 

@@ -616,9 +616,12 @@ def test_reference_samples_batched_and_perf(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-def test_batched_decode_sharded_over_two_devices(orc, monkeypatch):
-    """ROCJPEG_B200_DEVICES=2: one rocJpegDecodeBatched call split over two GPUs (no collective), every
-    destination on device 0, peers store through peer access. Bit-exact like the single-device path."""
+@pytest.mark.parametrize("layout", ["all_on_device0", "colocated", "mixed"])
+def test_batched_decode_sharded_over_two_devices(orc, monkeypatch, layout):
+    """ROCJPEG_B200_DEVICES=2: one rocJpegDecodeBatched call split over two GPUs (no collective). Destinations all on
+    device 0 (the peer's share is delivered through peer access), co-located with the library's own plan (nothing crosses a
+    link), or scattered at random over both devices (an image follows its buffer to the peer). Bit-exact like the
+    single-device path."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -631,25 +634,43 @@ def test_batched_decode_sharded_over_two_devices(orc, monkeypatch):
             pytest.skip("no peer access between device 0 and 1")
         names = [n for n in CASES] * 2
         datas = [load(n) for n in names]
-        for fmt in ("rgb", "yuv_planar"):
-            streams, dests, keep = [], [], []
+        rng = np.random.default_rng(3)
+        for fmt in ("rgb", "yuv_planar", "native"):
+            streams = []
             for d in datas:
                 s = api.JpegStream()
                 assert s.parse(d) == api.SUCCESS
+                streams.append(s)
+            if layout == "all_on_device0":
+                where = [0] * len(datas)
+            elif layout == "colocated":
+                where = [int(x) for x in api.plan_shards([s.info().raw_bytes for s in streams], 2)]
+            else:
+                where = [int(x) for x in rng.integers(0, 2, len(datas))]
+            dests, keep = [], []
+            for d, dv in zip(datas, where):
                 rc, info = orc.parse(d)
-                dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, fmt, (0, 0, 0, 0))
-                streams.append(s); dests.append(dest); keep.append((bufs, pitches, shapes))
+                with torch.cuda.device(dv):
+                    dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, fmt, (0, 0, 0, 0), pitch_pad=3, misalign=1)
+                dests.append(dest); keep.append((bufs, pitches, shapes))
             assert d2.decode_batched(streams, api.make_params(fmt), dests) == api.SUCCESS
             st = d2.stats()
             assert st.devices == 2
             for k, d in enumerate(datas):
                 bufs, pitches, shapes = keep[k]
-                got = gu.fetch(bufs, pitches, shapes)
+                got = gu.fetch(bufs, pitches, shapes, 1)
                 _, want = gu.oracle_outputs(orc, d, fmt, (0, 0, 0, 0), pitches)
-                gu.assert_same(got, want, f"sharded {names[k]} {fmt}")
-                rc, info = orc.parse(d)
-                n = sum(info.blocks_w[c] * info.blocks_h[c] * 64 for c in range(info.ncomp))
-                coefs = np.concatenate([c.reshape(-1) for c in orc.coefficients(d, info)])
-                assert np.array_equal(d2.coefficients(k, n), coefs), f"sharded {names[k]}: coefficients"
+                gu.assert_same(got, want, f"sharded {layout} {names[k]} {fmt}")
+                if fmt == "rgb":
+                    rc, info = orc.parse(d)
+                    n = sum(info.blocks_w[c] * info.blocks_h[c] * 64 for c in range(info.ncomp))
+                    coefs = np.concatenate([c.reshape(-1) for c in orc.coefficients(d, info)])
+                    assert np.array_equal(d2.coefficients(k, n), coefs), f"sharded {names[k]}: coefficients"
+        # a destination on a device the handle does not drive is refused, nothing is written
+        if torch.cuda.device_count() >= 3:
+            with torch.cuda.device(2):
+                rc, info = orc.parse(datas[0])
+                dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "rgb", (0, 0, 0, 0))
+            assert d2.decode_batched(streams[:2], api.make_params("rgb"), [dest, dests[1]]) == api.INVALID_PARAMETER
     finally:
         d2.close()

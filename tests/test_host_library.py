@@ -552,6 +552,22 @@ def test_shard_plan_is_lpt_and_balanced():
         assert dev.tolist() == want
     assert api.plan_shards([], 4).size == 0
     assert api.plan_shards([5, 5, 5, 5], 2).tolist() == [0, 1, 0, 1]
+    # images whose destination already lives on a peer device stay there; the rest fill up the least loaded devices
+    rng = np.random.default_rng(4)
+    for ndev in (2, 4, 8):
+        costs = rng.integers(1000, 90000, 200)
+        fixed = np.where(rng.random(200) < 0.4, rng.integers(0, ndev, 200), -1)
+        dev = api.plan_shards_pinned(costs, fixed, ndev)
+        assert all(dev[i] == fixed[i] for i in range(200) if fixed[i] >= 0)
+        loads = np.array([costs[dev == d].sum() for d in range(ndev)])
+        pinned = np.array([costs[(fixed == d)].sum() for d in range(ndev)])
+        if pinned.max() <= costs.sum() / ndev:      # pinning did not overload anyone: the free images level the devices
+            assert loads.max() - loads.min() <= costs.max() + 200
+    # a plan made with everything free, then replayed with the peers' images pinned (co-located destinations), is kept
+    costs = rng.integers(1000, 90000, 256)
+    plan = api.plan_shards(costs, 4)
+    again = api.plan_shards_pinned(costs, np.where(plan > 0, plan, -1), 4)
+    assert (again == plan).mean() > 0.9 and all(again[i] == plan[i] for i in range(256) if plan[i] > 0)
 
 
 @pytest.mark.parametrize("cap", ["0", "64"])
