@@ -46,6 +46,8 @@ typedef struct {
     float host_wait_ms;                       /* host wall time of the last call spent waiting for the device */
     int32_t devices;                          /* GPUs the last call was sharded over (ROCJPEG_B200_DEVICES) */
     uint64_t entries;                         /* 32-bit coefficient entries the entropy stage wrote (pad entries included) */
+    uint32_t truncated_images;                /* pictures of the last call whose scan ended before their last block */
+    uint32_t pad_;
 } RocJpegB200Stats;
 
 /* CUDA-event timing on a decoder handle: 0 off (default), 1 an event after every stage (stage_ms and total_ms;
@@ -84,10 +86,22 @@ typedef struct {
     uint32_t flags;          /* ROCJPEG_B200_SCAN_* */
     uint32_t reserved;
 } RocJpegB200ScanStatus;
-#define ROCJPEG_B200_SCAN_NO_EOI 1u          /* no FF D9: the slice ran to the end of the buffer */
-#define ROCJPEG_B200_SCAN_STRAY_MARKER 2u    /* a marker other than RSTn / EOI inside the entropy-coded data */
-#define ROCJPEG_B200_SCAN_EXTRA_RESTARTS 4u  /* more restart markers than the frame has restart intervals */
+#define ROCJPEG_B200_SCAN_NO_EOI 1u            /* no FF D9: the slice ran to the end of the buffer */
+#define ROCJPEG_B200_SCAN_STRAY_MARKER 2u      /* a marker other than RSTn / EOI inside the entropy-coded data */
+#define ROCJPEG_B200_SCAN_EXTRA_RESTARTS 4u    /* more restart markers than the frame has restart intervals */
+#define ROCJPEG_B200_SCAN_MISSING_INTERVALS 8u /* fewer restart intervals in the bytes than the frame needs */
+#define ROCJPEG_B200_SCAN_EMPTY_INTERVAL 16u   /* a restart interval that must hold blocks holds no bytes */
+#define ROCJPEG_B200_DECODE_SHORT 32u          /* a restart interval ran out of bytes before its last block */
+#define ROCJPEG_B200_DECODE_LEFTOVER 64u       /* a restart interval holds a byte or more behind its last block */
+#define ROCJPEG_B200_TRUNCATED_MASK (8u | 16u | 32u)
 RocJpegStatus rocJpegB200GetScanStatus(RocJpegHandle handle, int index, RocJpegB200ScanStatus *status);
+/* Per-image outcome of the last rocJpegDecode / rocJpegDecodeBatched: ROCJPEG_B200_SCAN_* | ROCJPEG_B200_DECODE_* flags.
+ * Every picture of a batch is decoded as far as its bytes go (blocks a truncated or damaged scan does not reach are
+ * zero: mid grey). When any picture has a ROCJPEG_B200_TRUNCATED_MASK flag the decode call returns
+ * ROCJPEG_STATUS_BAD_JPEG (the reference's VCN path reports a failed surface as an error too,
+ * src/rocjpeg_vaapi_decoder.cpp:846-868, and stops its batch there); this tells which pictures and why. Environment
+ * ROCJPEG_B200_STRICT=0 keeps the return code at SUCCESS. */
+RocJpegStatus rocJpegB200GetImageStatus(RocJpegHandle handle, int index, uint32_t *flags);
 RocJpegStatus rocJpegB200GetDeviceSegment(RocJpegHandle handle, int index, uint32_t segment, uint8_t *host_out, size_t capacity,
                                           uint32_t *nbytes);
 

@@ -59,7 +59,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
         ("subsequence_bytes", C.c_int32), ("lanes", C.c_int32),
         ("host_submit_ms", C.c_float), ("host_wait_ms", C.c_float), ("devices", C.c_int32),
-        ("entries", C.c_uint64),
+        ("entries", C.c_uint64), ("truncated_images", C.c_uint32), ("pad_", C.c_uint32),
     ]
 
 
@@ -79,7 +79,8 @@ class ScanStatus(C.Structure):
     _fields_ = [("segments_seen", C.c_uint32), ("scan_size", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
-SCAN_NO_EOI, SCAN_STRAY_MARKER, SCAN_EXTRA_RESTARTS = 1, 2, 4
+SCAN_NO_EOI, SCAN_STRAY_MARKER, SCAN_EXTRA_RESTARTS, SCAN_MISSING_INTERVALS, SCAN_EMPTY_INTERVAL = 1, 2, 4, 8, 16
+DECODE_SHORT, DECODE_LEFTOVER, TRUNCATED_MASK = 32, 64, 8 | 16 | 32
 
 
 class HostScanInfo(C.Structure):
@@ -97,7 +98,7 @@ EXT_EXPORTS = (
     "rocJpegB200StreamGetQuantTable", "rocJpegB200StreamGetHuffmanTable", "rocJpegB200Version", "rocJpegB200StreamGetLastError",
     "rocJpegB200PlanShards", "rocJpegB200GetDeviceCount", "rocJpegB200StreamHostScan",
     "rocJpegB200GetScanStatus", "rocJpegB200GetDeviceSegment", "rocJpegB200ParseAndDecodeBatched",
-    "rocJpegB200PlanShardsPinned",
+    "rocJpegB200PlanShardsPinned", "rocJpegB200GetImageStatus",
 )
 
 _lib = None
@@ -137,6 +138,7 @@ def load_library() -> C.CDLL:
     L.rocJpegB200GetCoefficients.argtypes = [vp, i32, vp, C.c_size_t]
     L.rocJpegB200GetPlanes.argtypes = [vp, i32, vp, C.c_size_t]
     L.rocJpegB200StreamGetInfo.argtypes = [vp, C.POINTER(StreamInfo)]
+    L.rocJpegB200GetImageStatus.argtypes = [vp, i32, C.POINTER(C.c_uint32)]
     L.rocJpegB200GetScanStatus.argtypes = [vp, i32, C.POINTER(ScanStatus)]
     L.rocJpegB200GetDeviceSegment.argtypes = [vp, i32, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_uint32)]
     L.rocJpegB200ParseAndDecodeBatched.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), i32, C.POINTER(RocJpegDecodeParams),
@@ -374,6 +376,12 @@ class Decoder:
         s = ScanStatus()
         _check(self.lib.rocJpegB200GetScanStatus(self.handle, index, C.byref(s)), "rocJpegB200GetScanStatus")
         return s
+
+    def image_status(self, index: int) -> int:
+        """SCAN_* | DECODE_* flags of image `index` of the last decode call."""
+        f = C.c_uint32()
+        _check(self.lib.rocJpegB200GetImageStatus(self.handle, index, C.byref(f)), "rocJpegB200GetImageStatus")
+        return f.value
 
     def device_segment(self, index: int, k: int) -> bytes:
         """Restart interval k of image `index` as the GPU destuffing pass left it in device memory."""

@@ -233,6 +233,7 @@ RocJpegStatus rocJpegB200GetStats(RocJpegHandle handle, RocJpegB200Stats* stats)
     stats->host_wait_ms = s.host_wait_ms;
     stats->devices = s.devices;
     stats->entries = s.entries;
+    stats->truncated_images = s.truncated_images;
     return ROCJPEG_STATUS_SUCCESS;
 }
 
@@ -325,6 +326,15 @@ RocJpegStatus rocJpegB200GetScanStatus(RocJpegHandle handle, int index, RocJpegB
     status->scan_size = st.scan_size;
     status->flags = st.flags;
     status->reserved = st.reserved;
+    return ROCJPEG_STATUS_SUCCESS;
+}
+
+RocJpegStatus rocJpegB200GetImageStatus(RocJpegHandle handle, int index, uint32_t* flags) {
+    if (handle == nullptr || flags == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    rjb::ScanStatus st;
+    const int rc = static_cast<DecoderHandle*>(handle)->decoder->GetScanStatus(index, &st);
+    if (rc != 0) return RocJpegStatus(rc);
+    *flags = st.flags;
     return ROCJPEG_STATUS_SUCCESS;
 }
 

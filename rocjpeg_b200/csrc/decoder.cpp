@@ -220,6 +220,7 @@ int Decoder::Initialize() {
     RJB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     RJB_CUDA(cudaStreamCreateWithPriority(&upload_stream_, cudaStreamNonBlocking, prio_hi));
     profiling_ = EnvInt("ROCJPEG_B200_PROFILE", 0);
+    strict_status_ = EnvInt("ROCJPEG_B200_STRICT", 1) != 0;
     // everything a first decode would otherwise pay for: kernel modules, the lanes' streams and events
     RJB_CUDA(PreloadK0());
     RJB_CUDA(PreloadK1());
@@ -391,6 +392,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     uint32_t dctile = 0, k2tile = 0, k3tile = 0, max_pairs = 1, max_sub = 0, k0tile = 0, nseg_total = 0;
     all_pinned_ = true;
     h_k0_tile0_.assign(size_t(n) + 1, 0);
+    h_needed_segments_.assign(size_t(n), 1);
     for (int i = 0; i < n; i++) {
         const ParsedJpeg& p = streams[i]->parsed();
         ImageDesc& im = h_images_[size_t(i)];
@@ -462,6 +464,10 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         im.data_off = scan_off;
         im.seg0 = nseg_total;
         im.nseg = p.nseg;
+        {   // restart intervals the frame needs (p.nseg is bounded by what the bytes can hold)
+            const uint64_t mcus = uint64_t(im.total_mcus);
+            h_needed_segments_[size_t(i)] = p.restart_interval > 0 ? uint32_t((mcus + uint32_t(p.restart_interval) - 1) / uint32_t(p.restart_interval)) : 1u;
+        }
         nseg_total += p.nseg;
         const uint64_t clean_cap = CleanCapacity(rs.nbytes, p.nseg, uint32_t(S));
         scan_off += clean_cap;
@@ -660,6 +666,7 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     k0_.tile_sum = reinterpret_cast<uint4*>(base + o_tile_sum);
     k0_.tile_carry = reinterpret_cast<uint4*>(base + o_tile_carry);
     k0_.status = reinterpret_cast<ScanStatus*>(base + o_status);
+    k1_.status = k0_.status;
     k1_.img_cta0 = reinterpret_cast<const uint32_t*>(d + L.cta0);
     k1_.img_dctile0 = reinterpret_cast<const uint32_t*>(d + L.dctile0);
     k1_.scan = base + o_scan;
@@ -813,6 +820,13 @@ int Lane::Finish(int profiling_) {
         stats_.kernel_launches += 7;
     }
     stats_.entries = cnt[2 * kMaxSyncRounds];
+    // per-image outcome: what the destuffing pass and the entropy stage found in the bytes
+    ScanStatus* st = reinterpret_cast<ScanStatus*>(h_counters_.data() + 256);
+    truncated_images_ = 0;
+    for (size_t i = 0; i < h_images_.size(); i++) {
+        if (st[i].segments_seen < h_needed_segments_[i]) st[i].flags |= kScanMissingIntervals;
+        if (st[i].flags & kStatusTruncatedMask) truncated_images_++;
+    }
     for (int r = 0; r < kMaxSyncRounds; r++) stats_.decodes_per_round[r] = cnt[kMaxSyncRounds + r];
     if (profiling_) {
         for (int s = 0; s < kStageCount && profiling_ == 1; s++) {
@@ -932,11 +946,19 @@ int Decoder::BuildAll(const StreamParser* const* streams, int n, const DecodePar
 
 int Decoder::FinishAll() {
     int status = kSuccess;
+    uint32_t truncated = 0;
     for (int l = 0; l < active_lanes_; l++) {
         int st = lanes_[l].Finish(profiling_);
         if (st != kSuccess && status == kSuccess) status = Fail(st, lanes_[l].last_error());
+        truncated += lanes_[l].truncated_images();
     }
     Aggregate();
+    stats_.truncated_images = truncated;
+    // Every picture of the batch has been decoded as far as its bytes go (missing blocks are zero: grey); a scan that
+    // ended before its last block makes the call report BAD_JPEG - the VCN path reports a failed surface as an error
+    // too (src/rocjpeg_vaapi_decoder.cpp:846-868) - and rocJpegB200GetImageStatus tells which pictures and why.
+    if (status == kSuccess && truncated != 0 && strict_status_)
+        status = Fail(kBadJpeg, std::to_string(truncated) + " picture(s) of the batch ended before their last block (truncated or damaged scan)");
     return status;
 }
 
@@ -987,7 +1009,7 @@ int Decoder::Decode(const StreamParser* const* streams, int n, const DecodeParam
     if (EnvInt("ROCJPEG_B200_TRACE", 0))
         std::cerr << "[rocjpeg_b200] decode n=" << n << " lanes=" << active_lanes_ << " submit_ms=" << stats_.host_submit_ms
                   << " wait_ms=" << stats_.host_wait_ms << std::endl;
-    prepared_ = (st == kSuccess);
+    prepared_ = (st == kSuccess) || (st == kBadJpeg && stats_.truncated_images != 0);   // a truncated picture still leaves a decoded batch behind
     return st;
 }
 
@@ -1000,7 +1022,7 @@ int Decoder::Submit(const StreamParser* const* streams, int n, const DecodeParam
 int Decoder::Wait() {
     DeviceGuard guard(device_id_);
     int st = FinishAll();
-    prepared_ = (st == kSuccess);
+    prepared_ = (st == kSuccess) || (st == kBadJpeg && stats_.truncated_images != 0);
     return st;
 }
 
@@ -1075,6 +1097,7 @@ int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const Deco
         total.scan_bytes += s.scan_bytes;
         total.blocks += s.blocks;
         total.entries += s.entries;
+        total.truncated_images += s.truncated_images;
         total.subsequences += s.subsequences;
         total.plane_bytes += s.plane_bytes;
         total.output_bytes += s.output_bytes;
@@ -1089,7 +1112,7 @@ int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const Deco
     stats_ = total;
     stats_.host_submit_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
     stats_.host_wait_ms = std::chrono::duration<float, std::milli>(t2 - t1).count();
-    sharded_ = (status == kSuccess);
+    sharded_ = (status == kSuccess) || (status == kBadJpeg && total.truncated_images != 0);
     if (status != kSuccess) prepared_ = false;
     return status;
 }

@@ -82,6 +82,7 @@ struct BatchStats {
     int lanes = 0;                      // pipeline lanes (chunks) the batch was split over
     float host_submit_ms = 0, host_wait_ms = 0;   // host wall time: describing + enqueueing / waiting for the device
     int devices = 1;                    // GPUs the call was sharded over
+    uint32_t truncated_images = 0;      // pictures whose scan ended before their last block
 };
 
 // Helper threads of one decoder: the lanes of a call are described and enqueued in parallel (kernel
@@ -142,6 +143,7 @@ class Lane {
     cudaEvent_t first_event() const { return ev_[0]; }
     cudaEvent_t last_event() const { return ev_[kStageCount]; }
     int num_images() const { return int(h_images_.size()); }
+    uint32_t truncated_images() const { return truncated_images_; }
 
   private:
     struct Layout;   // byte layout of the descriptor block
@@ -157,7 +159,8 @@ class Lane {
     // host-side batch description
     std::vector<ImageDesc> h_images_;
     std::vector<OutputDesc> h_outputs_;
-    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_, h_k0_tile0_;
+    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_, h_k0_tile0_, h_needed_segments_;
+    uint32_t truncated_images_ = 0;
     std::vector<GatherItem> h_gather_;
     std::vector<const HuffLutSet*> h_lut_ptrs_;
     std::vector<const ParsedJpeg*> h_lut_specs_;
@@ -235,6 +238,7 @@ class Decoder {
 
     int backend_, device_id_;
     bool initialized_ = false, prepared_ = false;
+    bool strict_status_ = true;   // ROCJPEG_B200_STRICT=0: truncated scans do not change the return code
     int profiling_ = 0;
     std::mutex mutex_;
     std::string err_;

@@ -103,10 +103,17 @@ __host__ __device__ inline uint64_t CleanCapacity(uint32_t raw_len, uint32_t nse
 struct ScanStatus {
     uint32_t segments_seen;   // restart intervals found in the bytes (restart markers + 1)
     uint32_t scan_size;       // raw bytes up to the first FF D9 (= raw_len when there is none)
-    uint32_t flags;           // kScanNoEoi | kScanStrayMarker | kScanExtraRestarts
+    uint32_t flags;           // kScan* (destuffing pass) | kDecode* (entropy stage); OR-ed in by many threads, zeroed by the tile reduction
     uint32_t reserved;
 };
-constexpr uint32_t kScanNoEoi = 1u, kScanStrayMarker = 2u, kScanExtraRestarts = 4u;
+constexpr uint32_t kScanNoEoi = 1u,            // no FF D9: the slice ran to the end of the buffer
+                   kScanStrayMarker = 2u,      // a marker other than RSTn / EOI inside the entropy-coded data
+                   kScanExtraRestarts = 4u,    // more restart markers than the frame has restart intervals
+                   kScanMissingIntervals = 8u, // fewer restart intervals in the bytes than the frame needs (set on the host)
+                   kScanEmptyInterval = 16u,   // a restart interval that must hold blocks holds no bytes
+                   kDecodeShort = 32u,         // a restart interval ran out of bytes before its last block
+                   kDecodeLeftover = 64u;      // a restart interval holds a byte or more behind its last block
+constexpr uint32_t kStatusTruncatedMask = kScanMissingIntervals | kScanEmptyInterval | kDecodeShort;   // -> BAD_JPEG
 
 // One restart interval ("segment") of one image: an independently decodable,
 // byte-aligned run of entropy-coded data with predictors reset (T.81 E.1.4).

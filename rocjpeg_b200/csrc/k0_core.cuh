@@ -179,7 +179,8 @@ RJB_K0_HD Elem PieceElem(const Piece& pc) {
 }
 
 // Placement of one image's restart intervals. `Mem` provides Segment(k) -> SegmentDesc&, Clean() -> uint8_t*
-// (the image's clean stream) and Finish(ScanStatus, first missing interval).
+// (the image's clean stream), Flag(bits) (OR into the image's status flags) and Finish(segments seen, scan size,
+// first missing interval).
 template <class Mem>
 struct Placer {
     const ImageDesc& im;
@@ -206,6 +207,10 @@ struct Placer {
         if (k >= im.nseg) return;
         const bool w = Wanted(k);
         mem.Segment(k).nbytes = w ? n : 0u;   // outside the region of interest: no subsequences, its blocks stay "never decoded"
+        if (w && n == 0u) {
+            const uint32_t ri = im.restart_interval > 0 ? uint32_t(im.restart_interval) : uint32_t(im.total_mcus);
+            if (uint64_t(k) * ri < uint64_t(im.total_mcus)) mem.Flag(kScanEmptyInterval);
+        }
         if (w) {
             uint8_t* z = Dst(r, k) + n;
             for (int i = 0; i < 16; i++) z[i] = 0;   // the bit reader may look 16 bytes ahead
@@ -214,12 +219,8 @@ struct Placer {
     // the slice ended (FF D9 at raw position `scan_size`, or the end of the buffer) inside interval k
     RJB_K0_HD void End(uint32_t r, uint32_t k, uint32_t n, uint32_t scan_size, uint32_t flags) const {
         Close(r, k, n);
-        ScanStatus st;
-        st.segments_seen = k + 1u;
-        st.scan_size = scan_size;
-        st.flags = flags | (k >= im.nseg ? kScanExtraRestarts : 0u);
-        st.reserved = 0;
-        mem.Finish(st, k + 1u);
+        mem.Flag(flags | (k >= im.nseg ? kScanExtraRestarts : 0u));
+        mem.Finish(k + 1u, scan_size, k + 1u);
     }
     // intervals the bytes do not contain (truncated file): empty, sorted behind every real subsequence
     RJB_K0_HD void Missing(uint32_t k) const {

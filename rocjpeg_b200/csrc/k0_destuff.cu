@@ -191,7 +191,10 @@ __global__ void __launch_bounds__(kThreads) k0_reduce(K0Args a) {
     const Elem e = ChunkElem(c, int64_t(im.raw_len), &plain);
     Elem ex, tot;
     CtaScan(e, plain, s_warp, &ex, &tot);
-    if (threadIdx.x == 0) a.tile_sum[tile] = make_uint4(tot.nrst, tot.tail, tot.last_r, tot.flags);
+    if (threadIdx.x == 0) {
+        a.tile_sum[tile] = make_uint4(tot.nrst, tot.tail, tot.last_r, tot.flags);
+        if (tile == im.k0_tile0) a.status[img] = ScanStatus{0u, 0u, 0u, 0u};   // the later passes OR their findings into it
+    }
 }
 
 // ---------------------------------------------------------------- gather_reduce: upload + k0_reduce in one
@@ -248,7 +251,10 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(K0Args a, const Gather
         const Elem e = ChunkElem(c, len, &plain);
         Elem ex, tot;
         CtaScan(e, plain, s_warp, &ex, &tot);
-        if (tid == 0) a.tile_sum[tile] = make_uint4(tot.nrst, tot.tail, tot.last_r, tot.flags);
+        if (tid == 0) {
+            a.tile_sum[tile] = make_uint4(tot.nrst, tot.tail, tot.last_r, tot.flags);
+            if (tile == im.k0_tile0) a.status[img] = ScanStatus{0u, 0u, 0u, 0u};
+        }
     }
 }
 
@@ -285,8 +291,12 @@ struct DevMem {
     uint32_t* fill_from;   // shared: first restart interval the bytes do not contain
     __device__ __forceinline__ SegmentDesc& Segment(uint32_t k) const { return a.segments[im.seg0 + k]; }
     __device__ __forceinline__ uint8_t* Clean() const { return a.clean + im.data_off; }
-    __device__ __forceinline__ void Finish(const ScanStatus& st, uint32_t from) const {
-        a.status[img] = st;
+    __device__ __forceinline__ void Flag(uint32_t bits) const {
+        if (bits) atomicOr(&a.status[img].flags, bits);
+    }
+    __device__ __forceinline__ void Finish(uint32_t segments_seen, uint32_t scan_size, uint32_t from) const {
+        a.status[img].segments_seen = segments_seen;
+        a.status[img].scan_size = scan_size;
         *fill_from = from;
     }
 };

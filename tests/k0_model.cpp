@@ -47,8 +47,10 @@ struct HostMem {
     uint32_t* fill_from;
     SegmentDesc& Segment(uint32_t k) const { return (*segs)[k]; }
     uint8_t* Clean() const { return clean; }
-    void Finish(const ScanStatus& st, uint32_t from) const {
-        *status = st;
+    void Flag(uint32_t bits) const { status->flags |= bits; }
+    void Finish(uint32_t segments_seen, uint32_t scan_size, uint32_t from) const {
+        status->segments_seen = segments_seen;
+        status->scan_size = scan_size;
         *fill_from = from;
     }
 };
@@ -114,7 +116,7 @@ extern "C" int k0_model_destuff(const uint8_t* data, size_t len, int S, int skip
     }
     // k0_apply
     std::vector<SegmentDesc> segs(p.nseg, SegmentDesc{0xDEADBEEFull, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
-    ScanStatus status = {0xFFFFFFFFu, 0, 0, 0};
+    ScanStatus status = {0xFFFFFFFFu, 0, 0, 0};   // flags start at zero as the tile reduction leaves them
     uint32_t fill_from = 0xFFFFFFFFu;
     HostMem mem{&segs, clean, &status, &fill_from};
     const Placer<HostMem> pl{im, uint32_t(S), mem};
