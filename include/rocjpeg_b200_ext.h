@@ -92,7 +92,6 @@ typedef struct {
 #define ROCJPEG_B200_SCAN_MISSING_INTERVALS 8u /* fewer restart intervals in the bytes than the frame needs */
 #define ROCJPEG_B200_SCAN_EMPTY_INTERVAL 16u   /* a restart interval that must hold blocks holds no bytes */
 #define ROCJPEG_B200_DECODE_SHORT 32u          /* a restart interval ran out of bytes before its last block */
-#define ROCJPEG_B200_DECODE_LEFTOVER 64u       /* a restart interval holds a byte or more behind its last block */
 #define ROCJPEG_B200_TRUNCATED_MASK (8u | 16u | 32u)
 RocJpegStatus rocJpegB200GetScanStatus(RocJpegHandle handle, int index, RocJpegB200ScanStatus *status);
 /* Per-image outcome of the last rocJpegDecode / rocJpegDecodeBatched: ROCJPEG_B200_SCAN_* | ROCJPEG_B200_DECODE_* flags.

@@ -80,7 +80,7 @@ class ScanStatus(C.Structure):
 
 
 SCAN_NO_EOI, SCAN_STRAY_MARKER, SCAN_EXTRA_RESTARTS, SCAN_MISSING_INTERVALS, SCAN_EMPTY_INTERVAL = 1, 2, 4, 8, 16
-DECODE_SHORT, DECODE_LEFTOVER, TRUNCATED_MASK = 32, 64, 8 | 16 | 32
+DECODE_SHORT, TRUNCATED_MASK = 32, 8 | 16 | 32
 
 
 class HostScanInfo(C.Structure):

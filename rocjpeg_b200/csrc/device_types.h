@@ -111,8 +111,7 @@ constexpr uint32_t kScanNoEoi = 1u,            // no FF D9: the slice ran to the
                    kScanExtraRestarts = 4u,    // more restart markers than the frame has restart intervals
                    kScanMissingIntervals = 8u, // fewer restart intervals in the bytes than the frame needs (set on the host)
                    kScanEmptyInterval = 16u,   // a restart interval that must hold blocks holds no bytes
-                   kDecodeShort = 32u,         // a restart interval ran out of bytes before its last block
-                   kDecodeLeftover = 64u;      // a restart interval holds a byte or more behind its last block
+                   kDecodeShort = 32u;         // a restart interval ran out of bytes before its last block
 constexpr uint32_t kStatusTruncatedMask = kScanMissingIntervals | kScanEmptyInterval | kDecodeShort;   // -> BAD_JPEG
 
 // One restart interval ("segment") of one image: an independently decodable,

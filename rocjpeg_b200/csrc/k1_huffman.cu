@@ -761,9 +761,8 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
         }
     }
     // per-image status (read back by the host with the round counters): the interval ran out of bytes before its last
-    // block (truncated or damaged scan) / bytes are left behind its last block
+    // block (truncated or damaged scan)
     if (me.last && blk0 < limit && uint32_t(rp - recs) < limit) atomicOr(&a.status[img].flags, kDecodeShort);
-    if (blk0 >= limit && me.end_bit > StateOverflow(key) + 7u) atomicOr(&a.status[img].flags, kDecodeLeftover);
     // a block still in progress whose DC symbol was ours: the thread that ends it stores only the end index
     if (has_dc && (ln.acc & kAccZMask) != 0 && blk0 < limit && me.end_bit != 0) rp->dc = int16_t(dcv);
     if (n & 7u) {   // last, partial group: padded with entries for position 0, which K2 overwrites with the DC anyway

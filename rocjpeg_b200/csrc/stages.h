@@ -119,7 +119,7 @@ struct K1Args {
     int3* dc_carry;               // per DC tile: predictors entering it (dc_scan)
     uint32_t* counters;           // [kMaxSyncRounds] boundary changes per round, then [kMaxSyncRounds] decodes per round
     uint32_t* counters_next;      // the next batch's set (64 words): k1_write zeroes it
-    ScanStatus* status;           // per image: the write pass ORs kDecodeShort / kDecodeLeftover into the flags
+    ScanStatus* status;           // per image: the write pass ORs kDecodeShort into the flags
     uint32_t* entries;            // coefficient entry arena (huff_core.cuh: MakeCoefEntry), decode order
     BlockRec* blk_rec;            // per block, decode order
     int nimages;

@@ -496,7 +496,7 @@ def _pinned_copies(datas, lead=0):
     return arena, [arena.data_ptr() + o for o in offs]
 
 
-def _check_destuffed_batch(dec, datas, zero_copy, fmt="y"):
+def _check_destuffed_batch(dec, datas, zero_copy, fmt="y", valid_pictures=True):
     import torch
 
     arena, addrs = _pinned_copies(datas, lead=3) if zero_copy else (None, None)
@@ -511,7 +511,7 @@ def _check_destuffed_batch(dec, datas, zero_copy, fmt="y"):
         dests.append([(buf.data_ptr(), inf.width), (buf.data_ptr() + inf.width * inf.height, inf.width),
                       (buf.data_ptr() + 2 * inf.width * inf.height, inf.width)])
     st = dec.decode_batched(streams, api.make_params(fmt), dests)
-    assert st == api.SUCCESS, st
+    assert st == api.SUCCESS or (not valid_pictures and st == api.BAD_JPEG), st   # hand-made scans are short of blocks, of course
     for i, (s, d) in enumerate(zip(streams, datas)):
         hs, inf, ds = s.host_scan(), s.info(), dec.scan_status(i)
         assert ds.scan_size == hs.scan_size, (i, ds.scan_size, hs.scan_size)
@@ -555,7 +555,7 @@ def test_gpu_destuffing_marker_patterns(dec, zero_copy, S, monkeypatch):
         scans.append(bytes(rng.choice(alphabet, n)))
         scans.append(bytes(rng.choice(alphabet, n)).replace(b"\xFF\xD9", b"\xFF\x00"))
     for base in ("synth_420_123x77_dri", "synth_444_123x77"):
-        _check_destuffed_batch(dec, [_scan_with(load(base), sc) for sc in scans], zero_copy)
+        _check_destuffed_batch(dec, [_scan_with(load(base), sc) for sc in scans], zero_copy, valid_pictures=False)
     # the decoder is still healthy
     import oracle as _o
 
