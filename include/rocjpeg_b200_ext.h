@@ -72,6 +72,16 @@ RocJpegStatus rocJpegB200ParseAndDecodeBatched(RocJpegHandle handle, RocJpegStre
                                                const RocJpegDecodeParams *decode_params, RocJpegImage *destinations,
                                                double *parse_seconds);
 
+/* File -> device ingestion (opt-in; the callers' I/O in the reference's samples is one ifstream read per image into a
+ * pageable vector on the decode thread, samples/rocjpeg_samples_utils.h:213-234 and
+ * samples/jpegDecodeBatched/jpegdecodebatched.cpp:106-121): `io_threads` threads (<= 0: 8) read paths[i] straight into
+ * stream handle i's pooled page-locked staging and parse it there, equivalent to rocJpegStreamParse on the file's bytes
+ * but without the intermediate copy - rocJpegDecodeBatched then uploads from that memory in place. per_file_status
+ * (optional) receives one status per file: SUCCESS, INVALID_PARAMETER (cannot open / read), BAD_JPEG. Returns the first
+ * failure, or SUCCESS. */
+RocJpegStatus rocJpegB200StreamLoadFiles(RocJpegStreamHandle *jpeg_stream_handles, const char *const *paths, int count,
+                                         int io_threads, RocJpegStatus *per_file_status);
+
 /* Stage taps for image `index` of the last decoded batch. Layout = the oracle's: component-major,
  * each component an MCU-padded raster of blocks (64 int16, natural order) / samples (u8). */
 RocJpegStatus rocJpegB200GetCoefficients(RocJpegHandle handle, int index, int16_t *host_out, size_t count);

@@ -98,7 +98,7 @@ EXT_EXPORTS = (
     "rocJpegB200StreamGetQuantTable", "rocJpegB200StreamGetHuffmanTable", "rocJpegB200Version", "rocJpegB200StreamGetLastError",
     "rocJpegB200PlanShards", "rocJpegB200GetDeviceCount", "rocJpegB200StreamHostScan",
     "rocJpegB200GetScanStatus", "rocJpegB200GetDeviceSegment", "rocJpegB200ParseAndDecodeBatched",
-    "rocJpegB200PlanShardsPinned", "rocJpegB200GetImageStatus",
+    "rocJpegB200PlanShardsPinned", "rocJpegB200GetImageStatus", "rocJpegB200StreamLoadFiles",
 )
 
 _lib = None
@@ -138,6 +138,7 @@ def load_library() -> C.CDLL:
     L.rocJpegB200GetCoefficients.argtypes = [vp, i32, vp, C.c_size_t]
     L.rocJpegB200GetPlanes.argtypes = [vp, i32, vp, C.c_size_t]
     L.rocJpegB200StreamGetInfo.argtypes = [vp, C.POINTER(StreamInfo)]
+    L.rocJpegB200StreamLoadFiles.argtypes = [C.POINTER(vp), C.POINTER(C.c_char_p), i32, i32, C.POINTER(i32)]
     L.rocJpegB200GetImageStatus.argtypes = [vp, i32, C.POINTER(C.c_uint32)]
     L.rocJpegB200GetScanStatus.argtypes = [vp, i32, C.POINTER(ScanStatus)]
     L.rocJpegB200GetDeviceSegment.argtypes = [vp, i32, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_uint32)]
@@ -179,6 +180,16 @@ def plan_shards_pinned(costs, fixed, num_devices: int):
     out = np.zeros(len(c), dtype=np.int32)
     _check(load_library().rocJpegB200PlanShardsPinned(c.ctypes.data, f.ctypes.data, len(c), num_devices, out.ctypes.data), "rocJpegB200PlanShardsPinned")
     return out
+
+
+def load_files(streams, paths, io_threads: int = 0):
+    """rocJpegB200StreamLoadFiles: read + parse paths[i] into streams[i] with I/O threads. Returns (status, per-file statuses)."""
+    n = len(streams)
+    hs = (C.c_void_p * n)(*[s.handle for s in streams])
+    ps = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    per = (C.c_int * n)()
+    st = load_library().rocJpegB200StreamLoadFiles(hs, ps, n, io_threads, per)
+    return st, list(per)
 
 
 def error_name(status: int) -> str:

@@ -8,7 +8,10 @@
 // wrappers mirror src/rocjpeg_api_decoder_handle.h / rocjpeg_api_stream_handle.h
 // (object + last-error string). The rocJpegB200* extension entry points are
 // declared in include/rocjpeg_b200_ext.h.
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstring>
 #include <exception>
 #include <iostream>
@@ -282,6 +285,43 @@ RocJpegStatus rocJpegB200ParseAndDecodeBatched(RocJpegHandle handle, RocJpegStre
     }
     if (parse_seconds) *parse_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return rocJpegDecodeBatched(handle, jpeg_stream_handles, batch_size, decode_params, destinations);
+}
+
+// File -> device ingestion: `io_threads` threads read the files straight into the stream handles' pooled page-locked
+// staging and parse them there (rjb::StreamParser::ParseFile).
+RocJpegStatus rocJpegB200StreamLoadFiles(RocJpegStreamHandle* jpeg_stream_handles, const char* const* paths, int count, int io_threads,
+                                         RocJpegStatus* per_file_status) {
+    if (jpeg_stream_handles == nullptr || paths == nullptr || count < 0) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    for (int i = 0; i < count; i++)
+        if (jpeg_stream_handles[i] == nullptr || paths[i] == nullptr) return ROCJPEG_STATUS_INVALID_PARAMETER;
+    const int nthreads = std::max(1, std::min(io_threads <= 0 ? 8 : io_threads, std::max(count, 1)));
+    std::vector<RocJpegStatus> status(size_t(count), ROCJPEG_STATUS_SUCCESS);
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= count) return;
+            auto h = static_cast<StreamHandle*>(jpeg_stream_handles[i]);
+            try {
+                const int rc = h->parser->ParseFile(paths[i]);
+                h->error = rc == 0 ? std::string() : h->parser->last_error();
+                status[size_t(i)] = rc == 0 ? ROCJPEG_STATUS_SUCCESS : rc == -2 ? ROCJPEG_STATUS_INVALID_PARAMETER : ROCJPEG_STATUS_BAD_JPEG;
+            } catch (const std::exception& e) {
+                h->error = e.what();
+                status[size_t(i)] = ROCJPEG_STATUS_RUNTIME_ERROR;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    RocJpegStatus first = ROCJPEG_STATUS_SUCCESS;
+    for (int i = 0; i < count; i++) {
+        if (per_file_status) per_file_status[i] = status[size_t(i)];
+        if (status[size_t(i)] != ROCJPEG_STATUS_SUCCESS && first == ROCJPEG_STATUS_SUCCESS) first = status[size_t(i)];
+    }
+    return first;
 }
 
 RocJpegStatus rocJpegB200PlanShards(const uint64_t* cost, int batch_size, int num_devices, int* out_device) {

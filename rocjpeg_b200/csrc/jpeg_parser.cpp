@@ -9,6 +9,7 @@
 
 #include <string>
 
+#include <cstdio>
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
@@ -608,6 +609,32 @@ void StreamParser::ResetFrame() {
 
 bool StreamParser::Parse(const uint8_t* d, size_t len) {
     std::lock_guard<std::mutex> lock(mutex_);
+    return ParseLocked(d, len, false);
+}
+
+int StreamParser::ParseFile(const char* path) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    ResetFrame();
+    FILE* f = path ? std::fopen(path, "rb") : nullptr;
+    if (!f) {
+        Fail("cannot open the file");
+        return -2;
+    }
+    std::fseek(f, 0, SEEK_END);
+    const long size = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    uint8_t* buf = size > 0 ? file_.Reserve(size_t(size) + 64) : nullptr;
+    const size_t got = buf ? std::fread(buf, 1, size_t(size), f) : 0;
+    std::fclose(f);
+    if (!buf || got != size_t(size)) {
+        Fail(size <= 0 ? "empty file" : "cannot read the file");
+        return -2;
+    }
+    std::memset(buf + size, 0xFF, 64 - (size_t(size) & 15));   // what the upload rounds up to
+    return ParseLocked(buf, size_t(size), true) ? 0 : -3;
+}
+
+bool StreamParser::ParseLocked(const uint8_t* d, size_t len, bool data_is_file_buffer) {
     ResetFrame();
     if (!d || len < 4) return Fail("stream too short");
     if (d[0] != 0xFF || d[1] != 0xD8) return Fail("missing SOI");                   // parser.cpp:64
@@ -681,7 +708,14 @@ bool StreamParser::Parse(const uint8_t* d, size_t len) {
     const uint64_t by_header = (p_.restart_interval > 0 && total_mcus > 0) ? (total_mcus + uint64_t(p_.restart_interval) - 1) / uint64_t(p_.restart_interval) : 1;
     p_.nseg = uint32_t(std::min<uint64_t>(by_header, uint64_t(p_.raw_bytes) / 2 + 1));
     BuildDecodeTables();
-    AdoptSource(d + p, len - p);
+    if (data_is_file_buffer) {   // already in this handle's page-locked memory: used in place
+        raw_ = RawScan();
+        raw_.nbytes = uint32_t(len - p);
+        raw_.host = d + p;
+        raw_.dev = file_.pinned() ? d + p : nullptr;
+    } else {
+        AdoptSource(d + p, len - p);
+    }
     p_.valid = true;
     return true;
 }

@@ -153,6 +153,11 @@ class StreamParser {
   public:
     // Returns false for streams the reference parser rejects (-> BAD_JPEG).
     bool Parse(const uint8_t* data, size_t length);
+    // File -> device ingestion (the step before the path in the reference's samples: an ifstream read per image on the
+    // decode thread, samples/rocjpeg_samples_utils.h:213-234): the file is read straight into this handle's pooled
+    // page-locked staging and parsed there - no intermediate copy, the upload reads the staging in place.
+    // Returns 0, -2 (cannot open / read: see last_error), -3 (not a JPEG this parser accepts).
+    int ParseFile(const char* path);
     const ParsedJpeg& parsed() const { return p_; }
     const RawScan& raw() const { return raw_; }
     // Destuffed restart intervals computed on the host from the bytes Parse() was given (which must still
@@ -171,6 +176,7 @@ class StreamParser {
     void ExtractEntropyData(const uint8_t* d, size_t length, HostScan* out) const;
     void BuildDecodeTables();
     void AdoptSource(const uint8_t* scan, size_t nbytes);
+    bool ParseLocked(const uint8_t* data, size_t length, bool data_is_file_buffer);
     void ResetFrame();
     // Table segments (DHT / DQT) of the stream being parsed against the previous stream's: while the payload bytes
     // repeat - the normal case, the same encoder wrote the files - nothing is re-parsed, re-hashed or rebuilt.
@@ -196,6 +202,7 @@ class StreamParser {
     bool TablesFailed();              // a table segment was rejected: nothing of it may be reused by the next parse
     RawScan raw_;
     PooledBuffer staging_;            // page-locked copy of pageable input
+    PooledBuffer file_;               // a whole file read by ParseFile (page-locked)
     mutable HostScan host_scan_;
     std::string err_;
 };

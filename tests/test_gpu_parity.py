@@ -696,6 +696,50 @@ def test_reference_sample_jpegdecode(tmp_path, fmt, crop):
                             f"{next((k for k in range(min(len(got), len(want))) if got[k] != want[k]), None)}"
 
 
+def test_file_ingestion_decodes_like_parsed_bytes(dec, orc, tmp_path):
+    """Files read by the library's I/O threads straight into pooled page-locked memory (rocJpegB200StreamLoadFiles) decode
+    bit-exactly, and the handles can be reloaded with other files."""
+    names = [n for n in CASES if _G["cases"][n]["width"] >= 16]
+    paths = []
+    for n in names:
+        p = tmp_path / (n + ".jpg")
+        p.write_bytes(load(n))
+        paths.append(str(p))
+    streams = [api.JpegStream() for _ in paths]
+    for order in (list(range(len(paths))), list(reversed(range(len(paths))))):
+        st, per = api.load_files(streams, [paths[k] for k in order], 4)
+        assert st == api.SUCCESS and all(x == api.SUCCESS for x in per)
+        assert all(s.info().source_is_device_visible for s in streams)
+        dests, keep = [], []
+        for k in order:
+            rc, info = orc.parse(load(names[k]))
+            dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "rgb", (0, 0, 0, 0))
+            dests.append(dest); keep.append((bufs, pitches, shapes))
+        assert dec.decode_batched(streams, api.make_params("rgb"), dests) == api.SUCCESS
+        for j, k in enumerate(order):
+            _, want = gu.oracle_outputs(orc, load(names[k]), "rgb", (0, 0, 0, 0), keep[j][1])
+            gu.assert_same(gu.fetch(*keep[j]), want, f"file ingestion {names[k]}")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(SAMPLES, "jpegdecode_files")), reason="samples not built")
+@pytest.mark.parametrize("fmt", ["rgb", "yuv_planar", "native"])
+def test_file_ingestion_sample(tmp_path, fmt):
+    import shutil
+
+    src = tmp_path / "in"
+    src.mkdir()
+    n = 0
+    for name in CASES:
+        shutil.copy(os.path.join(GOLDEN, name + ".jpg"), src / (name + ".jpg"))
+        n += 1
+    (src / "zz_not_a_jpeg.jpg").write_bytes(b"hello")
+    r = subprocess.run([os.path.join(SAMPLES, "jpegdecode_files"), "-i", str(src), "-fmt", fmt, "-b", "8", "-t", "3", "-n", "2"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"Total decoded images: {2 * n}" in r.stdout, r.stdout
+    assert "Skipped (unreadable / unsupported) files: 2" in r.stdout, r.stdout
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(SAMPLES, "jpegdecodebatched")), reason="samples not built")
 def test_reference_samples_batched_and_perf(tmp_path):
     import shutil

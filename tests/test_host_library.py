@@ -296,6 +296,44 @@ def test_stream_handle_reuse_keeps_nothing_of_the_previous_stream(lib, k1_model,
         assert np.array_equal(out, np.concatenate([c.reshape(-1) for c in orc.coefficients(data, info)]))
 
 
+def test_file_ingestion_equals_parsing_the_bytes(lib, tmp_path):
+    """rocJpegB200StreamLoadFiles (I/O threads -> pooled page-locked memory -> parse in place) leaves every stream handle
+    exactly as rocJpegStreamParse on the file's bytes does; unreadable files and non-JPEG files get their own status
+    and do not disturb the others."""
+    names = list(CASES)
+    paths = []
+    for n in names:
+        p = tmp_path / (n + ".jpg")
+        p.write_bytes(load(n))
+        paths.append(str(p))
+    (tmp_path / "text.jpg").write_bytes(b"not a jpeg at all, just text\n" * 10)
+    (tmp_path / "empty.jpg").write_bytes(b"")
+    paths += [str(tmp_path / "text.jpg"), str(tmp_path / "missing.jpg"), str(tmp_path / "empty.jpg")]
+    for threads in (1, 4, 0):
+        streams = [api.JpegStream() for _ in paths]
+        st, per = api.load_files(streams, paths, threads)
+        assert per[:len(names)] == [api.SUCCESS] * len(names)
+        assert per[len(names):] == [api.BAD_JPEG, api.INVALID_PARAMETER, api.INVALID_PARAMETER] and st == api.BAD_JPEG
+        for n, s in zip(names, streams):
+            ref = api.JpegStream()
+            assert ref.parse(load(n)) == api.SUCCESS
+            assert _tables_of(s) == _tables_of(ref), n
+            a, b = s.host_scan(), ref.host_scan()
+            assert (a.scan_size, a.restart_markers_seen, a.num_segments, a.clean_bytes) == (b.scan_size, b.restart_markers_seen, b.num_segments, b.clean_bytes)
+            assert [s.segment(k) for k in range(a.num_segments)] == [ref.segment(k) for k in range(b.num_segments)]
+            assert s.info().raw_bytes == ref.info().raw_bytes and s.info().scan_offset == ref.info().scan_offset
+        assert "cannot open" in streams[len(names) + 1].last_error()
+        # a handle that held a file can parse bytes again, and the other way round
+        assert streams[0].parse(load(names[1])) == api.SUCCESS and streams[0].info().width == api_info_width(load(names[1]))
+    assert lib.rocJpegB200StreamLoadFiles(None, None, 1, 1, None) == api.INVALID_PARAMETER
+
+
+def api_info_width(data):
+    s = api.JpegStream()
+    assert s.parse(data) == api.SUCCESS
+    return s.info().width
+
+
 # ---------------------------------------------------------------- K1 schedule on the CPU
 
 class _ModelStats(C.Structure):
