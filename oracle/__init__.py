@@ -191,6 +191,8 @@ def output_shapes(info, fmt: str, crop=(0, 0, 0, 0), oracle: Oracle | None = Non
             return [(H, 2 * W)]
         if css == "420":
             return [(H, W), (H >> 1, W)]
+        if css == "411":
+            return [(H, W), (H, W >> 2), (H, W >> 2)]
     if fmt == "yuv_planar":
         if css == "444":
             return [(H, W)] * 3
@@ -200,6 +202,8 @@ def output_shapes(info, fmt: str, crop=(0, 0, 0, 0), oracle: Oracle | None = Non
             return [(H, W), (H, W >> 1), (H, W >> 1)]
         if css == "420":
             return [(H, W), (H >> 1, W >> 1), (H >> 1, W >> 1)]
+        if css == "411":
+            return [(H, W), (H, W >> 2), (H, W >> 2)]
     raise ValueError((fmt, css))
 
 

@@ -256,7 +256,7 @@ int orc_supported(const OrcInfo *o) {
     if (o->width <= 0 || o->height <= 0) return ORC_NOT_SUPPORTED;
     if (o->ncomp != 1 && o->ncomp != 3) return ORC_NOT_SUPPORTED;
     if (o->scan_ncomp != o->ncomp) return ORC_NOT_SUPPORTED;
-    if (o->css == CSS_UNKNOWN || o->css == CSS_411) return ORC_NOT_SUPPORTED;
+    if (o->css == CSS_UNKNOWN) return ORC_NOT_SUPPORTED;   /* 4:1:1 (api/rocjpeg.h:91, rejected by the reference's decoder) is decoded: section 8 f4 */
     if (o->blocks_per_mcu > 10) return ORC_NOT_SUPPORTED;
     if (o->css == CSS_422 && o->ncomp == 3 && o->hs[1] == o->hs[0]) return ORC_NOT_SUPPORTED; /* (2,2,2|2,1,1) */
     for (int i = 0; i < o->ncomp; i++) {
@@ -589,7 +589,7 @@ int orc_convert(const OrcInfo *o, const uint8_t *planes, int fmt, const int16_t 
     int roi = orc_roi(o, crop, &x0, &y0, &W, &H);
     if (roi < 0) return ORC_INVALID;
     int css = o->css;
-    int sx = (css == CSS_422 || css == CSS_420) ? 1 : 0;   /* chroma shift, horizontal */
+    int sx = (css == CSS_411) ? 2 : (css == CSS_422 || css == CSS_420) ? 1 : 0;   /* chroma shift, horizontal */
     int sy = (css == CSS_440 || css == CSS_420) ? 1 : 0;   /* chroma shift, vertical */
 #define CH_OK(c) (dst[c] != NULL && dst_pitch[c] != 0)
     switch (fmt) {
@@ -605,14 +605,15 @@ int orc_convert(const OrcInfo *o, const uint8_t *planes, int fmt, const int16_t 
         if (CH_OK(0))
             for (int y = 0; y < H; y++)
                 for (int x = 0; x < W; x++) dst[0][(size_t)y * dst_pitch[0] + x] = pl_at(&s, 0, x0 + x, y0 + y);
-        if (css == CSS_444 || css == CSS_440) {
-            /* decoder.cpp:157-158 with CopyChannel's roi rule :376-389 */
-            int ch = H >> sy, cy0 = y0 >> sy;
+        if (css == CSS_444 || css == CSS_440 || css == CSS_411) {
+            /* decoder.cpp:157-158 with CopyChannel's roi rule :376-389. 4:1:1 has no VCN surface in the reference
+             * (it is rejected there): its native layout here is three planes, chroma (W>>2) x H, like 4:4:4 / 4:4:0 */
+            int ch = H >> sy, cy0 = y0 >> sy, cw = W >> sx, cx0 = x0 >> sx;
             for (int c = 1; c < 3; c++)
                 if (CH_OK(c))
                     for (int y = 0; y < ch; y++)
-                        for (int x = 0; x < W; x++)
-                            dst[c][(size_t)y * dst_pitch[c] + x] = pl_at(&s, c, x0 + x, cy0 + y);
+                        for (int x = 0; x < cw; x++)
+                            dst[c][(size_t)y * dst_pitch[c] + x] = pl_at(&s, c, cx0 + x, cy0 + y);
         } else if (css == CSS_420) {
             /* interleaved UV rows, byte offset (top>>1)*pitch + left (decoder.cpp:380-388) */
             if (CH_OK(1))

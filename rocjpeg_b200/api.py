@@ -287,10 +287,11 @@ def output_channel_shapes(css: str, fmt: str, width: int, height: int):
         return [(H, W)]
     if fmt == "native":
         return {"444": [(H, W)] * 3, "440": [(H, W), (H >> 1, W), (H >> 1, W)], "422": [(H, 2 * W)],
-                "420": [(H, W), (H >> 1, W)]}[css]
+                "420": [(H, W), (H >> 1, W)], "411": [(H, W), (H, W >> 2), (H, W >> 2)]}[css]
     if fmt == "yuv_planar":
         return {"444": [(H, W)] * 3, "440": [(H, W), (H >> 1, W), (H >> 1, W)],
-                "422": [(H, W), (H, W >> 1), (H, W >> 1)], "420": [(H, W), (H >> 1, W >> 1), (H >> 1, W >> 1)]}[css]
+                "422": [(H, W), (H, W >> 1), (H, W >> 1)], "420": [(H, W), (H >> 1, W >> 1), (H >> 1, W >> 1)],
+                "411": [(H, W), (H, W >> 2), (H, W >> 2)]}[css]
     raise ValueError((css, fmt))
 
 

@@ -324,7 +324,7 @@ int Decoder::GetImageInfo(const StreamParser* s, uint8_t* ncomp, int32_t* css, u
 // Bytes the output stage writes for one image (valid bytes only), mirroring the
 // sizing rules of samples/rocjpeg_samples_utils.h:318-399.
 static uint64_t OutputBytes(int css, int fmt, int W, int H) {
-    const int sx = (css == CSS_422 || css == CSS_420) ? 1 : 0, sy = (css == CSS_440 || css == CSS_420) ? 1 : 0;
+    const int sx = css == CSS_411 ? 2 : (css == CSS_422 || css == CSS_420) ? 1 : 0, sy = (css == CSS_440 || css == CSS_420) ? 1 : 0;
     const uint64_t luma = uint64_t(W) * H;
     switch (fmt) {
         case FMT_RGB:
@@ -335,7 +335,7 @@ static uint64_t OutputBytes(int css, int fmt, int W, int H) {
             if (css == CSS_400) return luma;
             if (css == CSS_422) return 2 * luma;
             if (css == CSS_420) return luma + uint64_t(W) * uint64_t(H >> 1);
-            return luma + 2ull * uint64_t(W) * uint64_t(H >> sy);
+            return luma + 2ull * uint64_t(W >> sx) * uint64_t(H >> sy);
         default: return 0;
     }
 }
@@ -540,7 +540,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         // into the caller's channels (4:2:2 / 4:2:0 NATIVE are interleaved surfaces and keep their tiles).
         const bool whole = od.x0 == 0 && od.y0 == 0 && od.w == p.width && od.h == p.height;
         const bool planar = od.fmt == FMT_Y || od.fmt == FMT_YUV_PLANAR ||
-                            (od.fmt == FMT_NATIVE && (p.css == CSS_444 || p.css == CSS_440 || p.css == CSS_400));
+                            (od.fmt == FMT_NATIVE && (p.css == CSS_444 || p.css == CSS_440 || p.css == CSS_411 || p.css == CSS_400));
         od.direct = (whole && planar && direct_ok && !(remote && remote[i])) ? 1 : 0;
         od.tiles_x = od.direct ? 0u : uint32_t((od.w + kK3TileW - 1) / kK3TileW);
         od.tiles_y = od.direct ? 0u : uint32_t((od.h + kK3TileH - 1) / kK3TileH);

@@ -521,12 +521,12 @@ void StreamParser::AdoptSource(const uint8_t* scan, size_t nbytes) {
 
 void StreamParser::BuildDecodeTables() {
     // support check: what the CUDA path decodes (baseline, one interleaved scan
-    // over all components, css in {444, 440, 422, 420, 400})
+    // over all components, css in {444, 440, 422, 420, 411, 400})
     p_.support_status = kStatusSuccess;
     if (p_.width <= 0 || p_.height <= 0) p_.support_status = kStatusNotSupported;
     else if (p_.ncomp != 1 && p_.ncomp != 3) p_.support_status = kStatusNotSupported;
     else if (p_.scan_ncomp != p_.ncomp) p_.support_status = kStatusNotSupported;
-    else if (p_.css == CSS_UNKNOWN || p_.css == CSS_411) p_.support_status = kStatusNotSupported;
+    else if (p_.css == CSS_UNKNOWN) p_.support_status = kStatusNotSupported;
     else if (p_.bpm > kMaxBlocksPerMcu || p_.bpm < 1) p_.support_status = kStatusNotSupported;
     else if (p_.css == CSS_422 && p_.ncomp == 3 && p_.hs[1] == p_.hs[0]) p_.support_status = kStatusNotSupported;
     // A block takes at least two bits (a DC code and an end-of-block): a frame header that announces far more

@@ -139,7 +139,7 @@ __device__ __forceinline__ TileInfo ResolveTile(const K2Args& a, const uint32_t*
             if (!od.direct && !a.force_planes && (od.x0 != 0 || od.y0 != 0 || od.w != im.width || od.h != im.height)) {
                 // Region of interest (src/rocjpeg_decoder.cpp:120-141): the output stage only reads the
                 // samples under the crop rectangle, so blocks outside it are not transformed at all.
-                const int sx = (comp != 0 && (im.css == CSS_422 || im.css == CSS_420)) ? 1 : 0;
+                const int sx = comp == 0 ? 0 : im.css == CSS_411 ? 2 : (im.css == CSS_422 || im.css == CSS_420) ? 1 : 0;
                 const int sy = (comp != 0 && (im.css == CSS_440 || im.css == CSS_420)) ? 1 : 0;
                 const int bx_lo = (od.x0 >> sx) >> 3, bx_hi = ((od.x0 + od.w - 1) >> sx) >> 3;
                 const int by_lo = (od.y0 >> sy) >> 3, by_hi = ((od.y0 + od.h - 1) >> sy) >> 3;
@@ -149,7 +149,7 @@ __device__ __forceinline__ TileInfo ResolveTile(const K2Args& a, const uint32_t*
                 // channel, pitch and visible size of this component in the caller's layout
                 // (src/rocjpeg_decoder.cpp:576-636: planar chroma at the subsampled size, floor shifts;
                 // 4:2:2 / 4:2:0 use pitch[1] for both chroma planes, 4:4:4 / 4:4:0 each channel's own)
-                const int sx = (im.css == CSS_422 || im.css == CSS_420) ? 1 : 0;
+                const int sx = im.css == CSS_411 ? 2 : (im.css == CSS_422 || im.css == CSS_420) ? 1 : 0;
                 const int sy = (im.css == CSS_440 || im.css == CSS_420) ? 1 : 0;
                 const uint32_t dpitch = comp == 0 ? od.dst_pitch[0] : (sx == 0 ? od.dst_pitch[comp] : od.dst_pitch[1]);
                 const int cw = comp == 0 ? im.width : (im.width >> sx), chh = comp == 0 ? im.height : (im.height >> sy);

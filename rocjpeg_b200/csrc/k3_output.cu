@@ -169,8 +169,8 @@ __device__ __forceinline__ void RowRgb(const K3Job& j, int sx, int sy, bool gray
                 uint32_t ub[8], vb[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    ub[i] = __ldg(urow + ((X + i) >> 1));
-                    vb[i] = __ldg(vrow + ((X + i) >> 1));
+                    ub[i] = __ldg(urow + ((X + i) >> sx));
+                    vb[i] = __ldg(vrow + ((X + i) >> sx));
                 }
                 uu = make_uint2(Pack4(ub[0], ub[1], ub[2], ub[3]), Pack4(ub[4], ub[5], ub[6], ub[7]));
                 vv = make_uint2(Pack4(vb[0], vb[1], vb[2], vb[3]), Pack4(vb[4], vb[5], vb[6], vb[7]));
@@ -273,11 +273,17 @@ __device__ __forceinline__ Rgb8 Convert8(uint2 yy, uint2 uu, uint2 vv) {
             fv[i] = ByteToFloat(vv.x, 0x7650 + i, kC);
             fv[4 + i] = ByteToFloat(vv.y, 0x7650 + i, kC);
         }
-    } else {
+    } else if (SX == 1) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {   // chroma byte i serves pixels 2i and 2i+1
             fu[2 * i] = fu[2 * i + 1] = ByteToFloat(uu.x, 0x7650 + i, kC);
             fv[2 * i] = fv[2 * i + 1] = ByteToFloat(vv.x, 0x7650 + i, kC);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {   // 4:1:1: chroma byte i serves pixels 4i .. 4i+3
+            fu[i] = ByteToFloat(uu.x, 0x7650 + (i >> 2), kC);
+            fv[i] = ByteToFloat(vv.x, 0x7650 + (i >> 2), kC);
         }
     }
     uint32_t r[8], g[8], b[8];
@@ -329,9 +335,12 @@ __device__ __forceinline__ void RowRgbFast(const K3Job& j, int sy, bool gray, in
         if (SX == 0) {
             uu = __ldg(reinterpret_cast<const uint2*>(urow + X));
             vv = __ldg(reinterpret_cast<const uint2*>(vrow + X));
-        } else {
+        } else if (SX == 1) {
             uu = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(urow + (X >> 1))), 0u);
             vv = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(vrow + (X >> 1))), 0u);
+        } else {
+            uu = make_uint2(__ldg(reinterpret_cast<const uint16_t*>(urow + (X >> 2))), 0u);
+            vv = make_uint2(__ldg(reinterpret_cast<const uint16_t*>(vrow + (X >> 2))), 0u);
         }
         o = Convert8<SX>(yy, uu, vv);
     }
@@ -406,7 +415,7 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
     __syncthreads();
     const K3Job& j = s_job;
     const int W = j.W, H = j.H, x0 = j.x0, y0 = j.y0, css = j.css, fmt = j.fmt;
-    const int sx = (css == CSS_422 || css == CSS_420) ? 1 : 0;
+    const int sx = css == CSS_411 ? 2 : (css == CSS_422 || css == CSS_420) ? 1 : 0;   // chroma shift: 4:1:1 has one chroma sample per four pixels
     const int sy = (css == CSS_440 || css == CSS_420) ? 1 : 0;
     const bool gray = (css == CSS_400);
     uint8_t* buf = s_buf[warp];
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(kThreads) k3_output(K3Args a) {
             if (y >= H) break;
             const bool dst_ok = ((bases | (size_t(y) * j.dpitch[0])) & 3) == 0;
             if (src_ok && dst_ok) {
-                if (sx) RowRgbFast<1>(j, sy, gray, y, lane); else RowRgbFast<0>(j, sy, gray, y, lane);
+                if (sx == 2) RowRgbFast<2>(j, sy, gray, y, lane); else if (sx) RowRgbFast<1>(j, sy, gray, y, lane); else RowRgbFast<0>(j, sy, gray, y, lane);
             } else {
                 RowRgb(j, sx, sy, gray, buf, y, lane);
             }

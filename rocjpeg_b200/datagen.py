@@ -12,7 +12,7 @@ from __future__ import annotations
 import io
 import numpy as np
 
-CSS_NAMES = ("444", "440", "422", "420", "400")
+CSS_NAMES = ("444", "440", "422", "420", "411", "400")
 
 
 def synth_image(width: int, height: int, seed: int = 0) -> np.ndarray:
@@ -46,13 +46,13 @@ def encode_jpeg(img: np.ndarray, css: str = "420", quality: int = 90, restart_mc
                 restart_rows: int = 0) -> bytes:
     """Baseline JPEG bytes. `restart_mcus` = DRI in MCUs; `restart_rows` = DRI in MCU rows."""
     assert css in CSS_NAMES
-    if css == "440":
+    if css in ("440", "411"):   # Pillow offers 4:4:4 / 4:2:2 / 4:2:0 only: OpenCV's libjpeg-turbo writes these two
         import cv2
 
         params = [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
-                  cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440]
+                  cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440 if css == "440" else cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]
         if restart_rows and not restart_mcus:
-            restart_mcus = restart_rows * ((img.shape[1] + 7) // 8)
+            restart_mcus = restart_rows * ((img.shape[1] + (7 if css == "440" else 31)) // (8 if css == "440" else 32))
         if restart_mcus:
             params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(restart_mcus)]
         ok, buf = cv2.imencode(".jpg", img[..., ::-1], params)

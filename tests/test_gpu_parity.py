@@ -216,7 +216,33 @@ def test_crop_that_starts_at_the_first_column_of_a_restart_interval(dec, orc, cs
             gu.assert_same(got, want, f"{css} dri={dri} crop={crop} {fmt}")
 
 
-@pytest.mark.parametrize("css", ["444", "440", "422", "420", "400"])
+@pytest.mark.parametrize("dri", [0, 1])
+def test_411_pictures_every_format_and_crop(dec, orc, dri):
+    """4:1:1 (one chroma sample per four pixels; ROCJPEG_CSS_411 exists in the API but the reference refuses to decode
+    it): coefficients and planes like every other subsampling, chroma planes (W>>2) x H for NATIVE / YUV_PLANAR, nearest-
+    neighbour chroma for RGB, crops at any offset."""
+    info0 = None
+    for (w, h) in ((500, 375), (131, 67), (33, 9), (640, 48)):
+        data = datagen.make_jpeg(w, h, "411", seed=60 + w, restart_rows=dri)
+        rc, info = orc.parse(data)
+        assert rc == 0 and oracle.CSS[info.css] == "411"
+        s = api.JpegStream()
+        assert s.parse(data) == api.SUCCESS
+        assert dec.image_info(s) == (3, api.CSS_411, [w, w >> 2, w >> 2, 0], [h, h, h, 0])
+        crops = [(0, 0, 0, 0)] + ([(16, 8, 80, 56), (17, 9, 82, 59), (3, 1, 40, 33)] if w >= 96 and h >= 64 else [])
+        for fmt in FORMATS:
+            for crop in crops:
+                for pad, mis in ((0, 0), (13, 3)):
+                    st, got, want = gu.decode_one(dec, orc, data, fmt, crop, pad, mis)
+                    assert st == api.SUCCESS, (fmt, crop, st)
+                    gu.assert_same(got, want, f"411 {w}x{h} {fmt} {crop} pad={pad} mis={mis}")
+        n = sum(info.blocks_w[c] * info.blocks_h[c] * 64 for c in range(info.ncomp))
+        st, got, want = gu.decode_one(dec, orc, data, "y")
+        assert np.array_equal(dec.coefficients(0, n), np.concatenate([c.reshape(-1) for c in orc.coefficients(data, info)]))
+        assert np.array_equal(dec.planes(0, n), np.concatenate([p.reshape(-1) for p in orc.planes(data, info)]))
+
+
+@pytest.mark.parametrize("css", ["444", "440", "422", "420", "411", "400"])
 def test_tiny_and_ragged_pictures(dec, orc, css):
     """Pictures smaller than one MCU, one sample wide or high, and sizes one off a block / MCU multiple: the
     partial MCUs, the floor-shifted chroma sizes and the exact-bounds stores at their extremes."""
@@ -432,10 +458,10 @@ def test_image_info_and_errors(dec, orc):
     assert dec.decode(s, api.make_params("y", (100, 50, 150, 70)), dest) == api.INVALID_PARAMETER
     # oversize crop is ignored (whole picture), as in the reference (src/rocjpeg_decoder.cpp:126-131)
     assert dec.decode(s, api.make_params("y", (0, 0, 500, 500)), dest) == api.SUCCESS
-    # 4:1:1 stream: parses, cannot be decoded
-    from test_host_library import make_411
+    # sampling factors the API has no name for: parses, cannot be decoded
+    from test_host_library import make_unknown_css
 
-    assert s.parse(make_411()) == api.SUCCESS
+    assert s.parse(make_unknown_css()) == api.SUCCESS
     assert dec.decode(s, api.make_params("y"), dest) == api.JPEG_NOT_SUPPORTED
     # unparsed stream handle
     assert dec.decode(api.JpegStream(), api.make_params("y"), dest) == api.BAD_JPEG

@@ -211,9 +211,12 @@ def test_parser_reuse_and_unsupported(lib):
     assert "progressive frame (SOF2)" in s.last_error()   # same verdict, but the message names the file type
     base[i + 1] = 0xC9
     assert s.parse(bytes(base)) == api.BAD_JPEG and "arithmetic-coded sequential frame (SOF9)" in s.last_error()
-    # 4:1:1 parses (ROCJPEG_CSS_411) but is not decodable, as in the reference (samples skip it)
+    # 4:1:1 (ROCJPEG_CSS_411, api/rocjpeg.h:91): the reference parses it and refuses to decode it; here it decodes
+    # (SURVEY.md section 8 f4). Sampling factors the API has no name for stay unsupported.
     assert s.parse(make_411()) == api.SUCCESS
-    assert s.info().chroma_subsampling == api.CSS_411 and s.info().decode_status == api.JPEG_NOT_SUPPORTED
+    assert s.info().chroma_subsampling == api.CSS_411 and s.info().decode_status == api.SUCCESS
+    assert s.parse(make_unknown_css()) == api.SUCCESS
+    assert s.info().chroma_subsampling == api.CSS_UNKNOWN and s.info().decode_status == api.JPEG_NOT_SUPPORTED
 
 
 def make_411():
@@ -221,6 +224,13 @@ def make_411():
 
     coefs = [np.zeros((1, 4, 64), np.int16), np.zeros((1, 1, 64), np.int16), np.zeros((1, 1, 64), np.int16)]
     return jw.write_jpeg(32, 8, coefs, [4, 1, 1], [1, 1, 1], [0, 0, 0], {0: bytes([1] * 64)})
+
+
+def make_unknown_css():
+    import jpeg_writer as jw
+
+    coefs = [np.zeros((1, 2, 64), np.int16), np.zeros((1, 2, 64), np.int16), np.zeros((1, 1, 64), np.int16)]
+    return jw.write_jpeg(16, 8, coefs, [2, 2, 1], [1, 1, 1], [0, 0, 0], {0: bytes([1] * 64)})
 
 
 def test_decoder_creation_without_gpu_fails_loudly(lib):

@@ -157,7 +157,7 @@ def test_parser_rejects_truncated(orc):
 
 
 @pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref (reference build) not present")
-@pytest.mark.parametrize("css", datagen.CSS_NAMES)
+@pytest.mark.parametrize("css", [c for c in datagen.CSS_NAMES if c != "411"])   # the reference has no 4:1:1 kernels: see the test below
 def test_oracle_output_matches_reference_kernels(orc, css):
     """Live (not golden) run of the reference's kernels over fresh pictures incl. odd sizes."""
     from ref_assembly import reference_output
@@ -176,6 +176,40 @@ def test_oracle_output_matches_reference_kernels(orc, css):
                 shapes = oracle.output_shapes(info, fmt, crop, orc)
                 for d, r, (rows, rb) in zip(dst, ref, shapes):
                     assert np.array_equal(d[:rows, :rb], r), (css, w, h, fmt, crop)
+
+
+def test_oracle_411_pinned(orc, ljt):
+    """4:1:1 (the reference parses it and refuses to decode it). Coefficients and planes are pinned
+    against libjpeg-turbo like every other subsampling; RGB is pinned against the reference's own 4:4:4 kernels fed with the
+    chroma planes replicated four times horizontally - nearest-neighbour chroma, the rule of all its subsampled kernels
+    (src/rocjpeg_hip_kernels.cpp:947-954, 1389-1429)."""
+    for (w, h, rows) in ((200, 120, 0), (131, 67, 1), (33, 9, 0)):
+        data = datagen.make_jpeg(w, h, "411", seed=70 + w, restart_rows=rows)
+        rc, info = orc.parse(data)
+        assert rc == 0 and oracle.CSS[info.css] == "411" and orc.supported(info) == 0 and info.blocks_per_mcu == 6
+        coefs, lc = orc.coefficients(data, info), ljt.coefficients(data, info)
+        planes, lp = orc.planes(data, info), ljt.raw_planes(data, info)
+        li = ljt.info(data)
+        for c in range(3):
+            assert np.array_equal(coefs[c], lc[c]), f"component {c} coefficients"
+            hh, ww = li.hib[c] * 8, li.wib[c] * 8
+            assert np.array_equal(planes[c][:hh, :ww], lp[c][:hh, :ww]), f"component {c} plane"
+        _, yuv = orc.decode(data, "yuv_planar")
+        assert np.array_equal(yuv[0][:h, :w], planes[0][:h, :w])
+        for c in (1, 2):
+            assert np.array_equal(yuv[c][:h, :w >> 2], planes[c][:h, :w >> 2])
+        if oracle.ref_available():
+            from ref_assembly import reference_output
+
+            rk = oracle.RefKernels()
+            rc, info444 = orc.parse(datagen.make_jpeg(w, h, "444", seed=1))
+            ph, pw = info444.blocks_h[0] * 8, info444.blocks_w[0] * 8
+            fake = [np.ascontiguousarray(planes[0][:ph, :pw])] + [np.ascontiguousarray(np.repeat(planes[c], 4, axis=1)[:ph, :pw]) for c in (1, 2)]
+            for fmt in ("rgb", "rgb_planar"):
+                _, dst = orc.decode(data, fmt)
+                ref = reference_output(rk, info444, fake, fmt, (0, 0, 0, 0))
+                for d, r, (rows_, rb) in zip(dst, ref, oracle.output_shapes(info, fmt)):
+                    assert np.array_equal(d[:rows_, :rb], r), (w, h, fmt)
 
 
 def test_rgb_vs_libjpeg_default_decode_is_reported_not_gated(orc, ljt):
