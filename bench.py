@@ -536,14 +536,16 @@ def main():
     # Algorithmic bytes per stage, from what the stages actually move:
     # entries = 32-bit coefficient entries K1 really wrote (counted on the device), 8-byte record per block.
     blocks, scan, entries = stats.blocks, stats.scan_bytes, stats.entries
-    k3_read = stats.plane_bytes if stage_ms[6] > 0 else 0
+    fused = stats.fused_blocks / blocks if blocks else 0.0      # share of the blocks the fused IDCT + output kernel handles
+    k3_read = stats.plane_bytes * (1.0 - fused) if stage_ms[6] > 0 else 0
+    coef_read = entries * 4 + blocks * 8                        # sparse entries + one record per block
     stage_bytes = {
         "destuff": scan * 2,                                    # raw bytes read, destuffed bytes written (re-read from L2 by the scatter pass)
         "huffman_sync": scan,                                   # count-only passes: the scan is read, a few words per subsequence written
         "huffman_write": scan + entries * 4 + blocks * 8,       # scan read; sparse entries + one record per block written
         "dc": blocks * 8 * 2,                                   # records read and rewritten
-        "idct": entries * 4 + blocks * 8 + blocks * 64,         # entries + records read, 64 samples per block written
-        "output": k3_read + stats.output_bytes,                 # planes read at coded resolution + pixels written
+        "idct": (coef_read + blocks * 64) * (1.0 - fused),      # entries + records read, 64 samples per block written (un-fused pictures)
+        "output": coef_read * fused + k3_read + stats.output_bytes,   # fused pictures: coefficients in, pixels out; others: planes read + pixels written
     }
     stages = {}
     for i, name in enumerate(api.STAGES):
@@ -554,11 +556,13 @@ def main():
                         "frac_of_hbm_peak": round(b / ms / 1e6 / peak, 4) if b and ms > 0 else None,
                         "traffic": measured_traffic(args.workload, name)}
     # dense-equivalent figure SURVEY.md section 8d quotes for the IDCT (128 B int16 block read + 64 B written)
-    if stage_ms[5] > 0:
-        stages["idct"]["dense_equiv_GB_s"] = round(blocks * 192 / stage_ms[5] / 1e6, 1)
+    if stage_ms[5] > 0 and fused < 1.0:
+        stages["idct"]["dense_equiv_GB_s"] = round(blocks * (1.0 - fused) * 192 / stage_ms[5] / 1e6, 1)
+    if fused > 0:
+        stages["output"]["note"] = f"{fused:.0%} of the blocks through the fused IDCT + output kernel (k23_fused: coefficient entries in, pixels out)"
     # `roofline`: the slower of the two HBM-bound stages the north star asks an HBM fraction for (IDCT, colour/output);
     # the entropy stage is latency/issue bound and reported as compressed GB/s + issue utilisation in `roofline_k1`
-    hbm = [n for n in ("idct", "output") if stages[n]["ms"] > 0]
+    hbm = [n for n in ("idct", "output") if stages[n]["ms"] > 0 and stage_bytes[n] > 0]
     dom = max(hbm, key=lambda n: stages[n]["ms"])
     dom_ms = stages[dom]["ms"]
     achieved = stage_bytes[dom] / dom_ms / 1e6 if dom_ms > 0 else 0.0

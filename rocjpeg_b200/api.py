@@ -59,7 +59,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
         ("subsequence_bytes", C.c_int32), ("lanes", C.c_int32),
         ("host_submit_ms", C.c_float), ("host_wait_ms", C.c_float), ("devices", C.c_int32),
-        ("entries", C.c_uint64), ("truncated_images", C.c_uint32), ("pad_", C.c_uint32),
+        ("entries", C.c_uint64), ("truncated_images", C.c_uint32), ("pad_", C.c_uint32), ("fused_blocks", C.c_uint64),
     ]
 
 

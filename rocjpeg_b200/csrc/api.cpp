@@ -237,6 +237,7 @@ RocJpegStatus rocJpegB200GetStats(RocJpegHandle handle, RocJpegB200Stats* stats)
     stats->devices = s.devices;
     stats->entries = s.entries;
     stats->truncated_images = s.truncated_images;
+    stats->fused_blocks = s.fused_blocks;
     return ROCJPEG_STATUS_SUCCESS;
 }
 

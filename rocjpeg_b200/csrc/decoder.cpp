@@ -226,6 +226,7 @@ int Decoder::Initialize() {
     RJB_CUDA(PreloadK1());
     RJB_CUDA(PreloadK2());
     RJB_CUDA(PreloadK3());
+    RJB_CUDA(PreloadK23());
     for (int l = 1; l < kMaxLanes; l++) {
         st = lanes_[l].Create(device_id_, sm_count_);
         if (st != kSuccess) return Fail(st, lanes_[l].last_error());
@@ -349,6 +350,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     h_img_dctile0_.assign(size_t(n) + 1, 0);
     h_k2_tile0_.assign(size_t(n) + 1, 0);
     h_k3_tile0_.assign(size_t(n) + 1, 0);
+    h_k23_tile0_.assign(size_t(n) + 1, 0);
     h_gather_.assign(size_t(n), GatherItem{});
     h_lut_ptrs_.clear();
     h_lut_specs_.clear();
@@ -388,6 +390,9 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     any_direct_ = false;
     needs_planes_ = false;
     const bool direct_ok = EnvInt("ROCJPEG_B200_NO_DIRECT", 0) == 0;
+    const bool fuse_ok = EnvInt("ROCJPEG_B200_NO_FUSE", 0) == 0;
+    uint32_t k23tile = 0;
+    k2_needed_ = false;
     uint64_t scan_off = 0, raw_off = 0, blk = 0, plane_off = 0, ent = 0, sub = 0;
     uint32_t dctile = 0, k2tile = 0, k3tile = 0, max_pairs = 1, max_sub = 0, k0tile = 0, nseg_total = 0;
     all_pinned_ = true;
@@ -542,10 +547,19 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         const bool planar = od.fmt == FMT_Y || od.fmt == FMT_YUV_PLANAR ||
                             (od.fmt == FMT_NATIVE && (p.css == CSS_444 || p.css == CSS_440 || p.css == CSS_411 || p.css == CSS_400));
         od.direct = (whole && planar && direct_ok && !(remote && remote[i])) ? 1 : 0;
-        od.tiles_x = od.direct ? 0u : uint32_t((od.w + kK3TileW - 1) / kK3TileW);
-        od.tiles_y = od.direct ? 0u : uint32_t((od.h + kK3TileH - 1) / kK3TileH);
-        any_direct_ = any_direct_ || od.direct || !whole;   // the plane arena is then incomplete: the tap re-runs the IDCT
-        needs_planes_ = needs_planes_ || !od.direct;
+        // Whole-picture RGB / RGB_PLANAR: IDCT and colour conversion in one kernel, the planes never leave shared memory
+        od.fused = (whole && fuse_ok && (od.fmt == FMT_RGB || od.fmt == FMT_RGB_PLANAR)) ? 1 : 0;
+        const bool tiles = !od.direct && !od.fused;
+        od.tiles_x = tiles ? uint32_t((od.w + kK3TileW - 1) / kK3TileW) : 0u;
+        od.tiles_y = tiles ? uint32_t((od.h + kK3TileH - 1) / kK3TileH) : 0u;
+        any_direct_ = any_direct_ || od.direct || od.fused || !whole;   // the plane arena is then incomplete: the tap re-runs the IDCT
+        needs_planes_ = needs_planes_ || tiles;
+        k2_needed_ = k2_needed_ || !od.fused;
+        h_k23_tile0_[size_t(i)] = k23tile;
+        if (od.fused) {
+            k23tile += uint32_t((p.width + kK3TileW - 1) / kK3TileW) * uint32_t(p.mcus_y);
+            stats_.fused_blocks += im.nblocks;
+        }
         od.tile0 = k3tile;
         h_k3_tile0_[size_t(i)] = k3tile;
         k3tile += od.tiles_x * od.tiles_y;
@@ -556,6 +570,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     h_img_dctile0_[size_t(n)] = dctile;
     h_k2_tile0_[size_t(n)] = k2tile;
     h_k3_tile0_[size_t(n)] = k3tile;
+    h_k23_tile0_[size_t(n)] = k23tile;
     scan_bytes_ = scan_off;
     raw_bytes_ = raw_off;
     nseg_total_ = nseg_total;
@@ -596,12 +611,15 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     k3_ = K3Args{};
     k3_.nimages = n;
     k3_.total_tiles = k3tile;
+    k23_ = K23Args{};
+    k23_.nimages = n;
+    k23_.total_tiles = k23tile;
     return kSuccess;
 }
 
 // Descriptor block: one pinned host buffer mirrored by one device buffer, one copy.
 struct Lane::Layout {
-    size_t images, outputs, cta0, k0tile0, dctile0, k2tile0, k3tile0, gather, luts, qtables, total;
+    size_t images, outputs, cta0, k0tile0, dctile0, k2tile0, k3tile0, k23tile0, gather, luts, qtables, total;
 };
 
 int Lane::Upload(cudaStream_t up, UploadTurn turn) {
@@ -618,6 +636,7 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     L.dctile0 = place((n + 1) * 4);
     L.k2tile0 = place((n + 1) * 4);
     L.k3tile0 = place((n + 1) * 4);
+    L.k23tile0 = place((n + 1) * 4);
     L.gather = place(n * sizeof(GatherItem));
     L.luts = place(h_lut_ptrs_.size() * sizeof(HuffLutSet));
     L.qtables = place(h_qtables_.size() * 2);
@@ -631,6 +650,7 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     std::memcpy(h + L.dctile0, h_img_dctile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.k2tile0, h_k2_tile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.k3tile0, h_k3_tile0_.data(), (n + 1) * 4);
+    std::memcpy(h + L.k23tile0, h_k23_tile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.gather, h_gather_.data(), n * sizeof(GatherItem));
     for (size_t s = 0; s < h_lut_ptrs_.size(); s++) std::memcpy(h + L.luts + s * sizeof(HuffLutSet), h_lut_ptrs_[s], sizeof(HuffLutSet));
     std::memcpy(h + L.qtables, h_qtables_.data(), h_qtables_.size() * 2);
@@ -695,6 +715,12 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     k3_.outputs = reinterpret_cast<const OutputDesc*>(d + L.outputs);
     k3_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k3tile0);
     k3_.planes = k2_.planes;
+    k23_.images = k1_.images;
+    k23_.outputs = k2_.outputs;
+    k23_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k23tile0);
+    k23_.qtables = k2_.qtables;
+    k23_.entries = k1_.entries;
+    k23_.blk_rec = k1_.blk_rec;
 
     // Uploads of all lanes go through ONE stream, in lane order: the first chunk gets the whole
     // PCIe link and its kernels start while the next chunks are still in flight.
@@ -777,11 +803,13 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(mark(4));
     RJB_CUDA(LaunchDcScan(k1_, stream_));
     RJB_CUDA(mark(5));
-    RJB_CUDA(LaunchK2Idct(k2_, stream_));
+    if (k2_needed_) RJB_CUDA(LaunchK2Idct(k2_, stream_));
     RJB_CUDA(mark(6));
+    RJB_CUDA(LaunchK23Fused(k23_, stream_));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + 1 + 1;   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, output
+    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + (k2_needed_ ? 1 : 0) + (k23_.total_tiles ? 1 : 0) +
+                              (k3_.total_tiles ? 1 : 0);   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, fused IDCT + output, output
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data() + 256, k0_.status, h_images_.size() * sizeof(ScanStatus), cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256 + h_images_.size() * sizeof(ScanStatus);
@@ -813,7 +841,8 @@ int Lane::Finish(int profiling_) {
         RJB_CUDA(cudaMemsetAsync(k1_.counters + 2 * kMaxSyncRounds, 0, 4, stream_));   // the first write pass counted its entries already
         RJB_CUDA(LaunchK1Write(k1_, stream_));
         RJB_CUDA(LaunchDcScan(k1_, stream_));
-        RJB_CUDA(LaunchK2Idct(k2_, stream_));
+        if (k2_needed_) RJB_CUDA(LaunchK2Idct(k2_, stream_));
+        RJB_CUDA(LaunchK23Fused(k23_, stream_));
         RJB_CUDA(LaunchK3Output(k3_, stream_));
         RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
         RJB_CUDA(cudaStreamSynchronize(stream_));
@@ -975,6 +1004,7 @@ void Decoder::Aggregate() {
         stats_.entries += s.entries;
         stats_.subsequences += s.subsequences;
         stats_.plane_bytes += s.plane_bytes;
+        stats_.fused_blocks += s.fused_blocks;
         stats_.output_bytes += s.output_bytes;
         stats_.h2d_bytes += s.h2d_bytes;
         stats_.d2h_bytes += s.d2h_bytes;
@@ -1100,6 +1130,7 @@ int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const Deco
         total.truncated_images += s.truncated_images;
         total.subsequences += s.subsequences;
         total.plane_bytes += s.plane_bytes;
+        total.fused_blocks += s.fused_blocks;
         total.output_bytes += s.output_bytes;
         total.h2d_bytes += s.h2d_bytes;
         total.d2h_bytes += s.d2h_bytes;

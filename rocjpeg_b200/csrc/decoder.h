@@ -75,6 +75,7 @@ struct BatchStats {
     uint64_t entries = 0;               // 32-bit coefficient entries K1 wrote (pad entries included)
     uint64_t subsequences = 0;
     uint64_t plane_bytes = 0;           // bytes of decoded component planes (K2 output)
+    uint64_t fused_blocks = 0;          // blocks the fused IDCT + output kernel transformed (their planes never reach memory)
     uint64_t output_bytes = 0;          // bytes K3 writes
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
     uint32_t kernel_launches = 0;
@@ -159,7 +160,7 @@ class Lane {
     // host-side batch description
     std::vector<ImageDesc> h_images_;
     std::vector<OutputDesc> h_outputs_;
-    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_, h_k0_tile0_, h_needed_segments_;
+    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_, h_k0_tile0_, h_k23_tile0_, h_needed_segments_;
     uint32_t truncated_images_ = 0;
     std::vector<GatherItem> h_gather_;
     std::vector<const HuffLutSet*> h_lut_ptrs_;
@@ -170,6 +171,8 @@ class Lane {
     K1Args k1_ = {};
     K2Args k2_ = {};
     K3Args k3_ = {};
+    K23Args k23_ = {};
+    bool k2_needed_ = true;       // some image of the lane is not served by the fused kernel
     bool tiles_reduced_ = false;   // the upload kernel left the destuffing pass's per-tile prefix elements
     bool all_pinned_ = false, any_direct_ = false, needs_planes_ = false;
     size_t scan_bytes_ = 0, raw_bytes_ = 0, coef_blocks_ = 0, entry_count_ = 0, plane_bytes_ = 0, nsub_total_ = 0;

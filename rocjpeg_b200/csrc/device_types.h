@@ -134,7 +134,7 @@ struct OutputDesc {
     uint32_t tile0;          // first output tile of this image
     uint32_t tiles_x, tiles_y;
     int32_t direct;          // the IDCT stage stores this image's planes straight into dst (planar formats, no crop): no output tiles
-    int32_t pad_;
+    int32_t fused;           // whole-picture RGB / RGB_PLANAR: the fused IDCT + output kernel serves it (no IDCT tiles' output, no output tiles)
 };
 
 }  // namespace rjb

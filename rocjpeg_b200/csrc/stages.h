@@ -157,6 +157,20 @@ struct K2Args {
 };
 cudaError_t LaunchK2Idct(const K2Args& a, cudaStream_t stream);
 
+// K2 + K3 in one kernel for whole-picture RGB / RGB_PLANAR outputs (OutputDesc::fused): coefficients in, pixels out.
+struct K23Args {
+    const ImageDesc* images;
+    const OutputDesc* outputs;
+    const uint32_t* img_tile0;    // nimages + 1: first strip of each image (fused images only have strips)
+    const uint16_t* qtables;
+    const uint32_t* entries;
+    const BlockRec* blk_rec;
+    int nimages;
+    uint32_t total_tiles;
+};
+cudaError_t LaunchK23Fused(const K23Args& a, cudaStream_t stream);
+cudaError_t PreloadK23();
+
 struct K3Args {
     const ImageDesc* images;
     const OutputDesc* outputs;
