@@ -350,7 +350,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     h_img_dctile0_.assign(size_t(n) + 1, 0);
     h_k2_tile0_.assign(size_t(n) + 1, 0);
     h_k3_tile0_.assign(size_t(n) + 1, 0);
-    h_k23_tile0_.assign(size_t(n) + 1, 0);
+    h_fused_.clear();
+    h_tile_img_.clear();
     h_gather_.assign(size_t(n), GatherItem{});
     h_lut_ptrs_.clear();
     h_lut_specs_.clear();
@@ -548,16 +549,41 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
                             (od.fmt == FMT_NATIVE && (p.css == CSS_444 || p.css == CSS_440 || p.css == CSS_411 || p.css == CSS_400));
         od.direct = (whole && planar && direct_ok && !(remote && remote[i])) ? 1 : 0;
         // Whole-picture RGB / RGB_PLANAR: IDCT and colour conversion in one kernel, the planes never leave shared memory
-        od.fused = (whole && fuse_ok && (od.fmt == FMT_RGB || od.fmt == FMT_RGB_PLANAR)) ? 1 : 0;
+        od.fused = (whole && fuse_ok && (od.fmt == FMT_RGB || od.fmt == FMT_RGB_PLANAR) && h_fused_.size() < 65535) ? 1 : 0;
         const bool tiles = !od.direct && !od.fused;
         od.tiles_x = tiles ? uint32_t((od.w + kK3TileW - 1) / kK3TileW) : 0u;
         od.tiles_y = tiles ? uint32_t((od.h + kK3TileH - 1) / kK3TileH) : 0u;
         any_direct_ = any_direct_ || od.direct || od.fused || !whole;   // the plane arena is then incomplete: the tap re-runs the IDCT
         needs_planes_ = needs_planes_ || tiles;
         k2_needed_ = k2_needed_ || !od.fused;
-        h_k23_tile0_[size_t(i)] = k23tile;
         if (od.fused) {
-            k23tile += uint32_t((p.width + kK3TileW - 1) / kK3TileW) * uint32_t(p.mcus_y);
+            FusedImage fi = {};
+            fi.ent0 = im.ent0; fi.blk0 = im.blk0; fi.ent_cap = im.ent_cap;
+            for (int c = 0; c < 3; c++) fi.dst[c] = od.dst[c];
+            fi.dpitch = od.dst_pitch[0];
+            fi.width = p.width; fi.height = p.height; fi.css = p.css; fi.fmt = od.fmt;
+            fi.ncomp = p.ncomp; fi.bpm = p.bpm; fi.mcus_x = p.mcus_x;
+            int hmax = 1, vmax = 1;
+            for (int c = 0; c < p.ncomp; c++) { hmax = std::max(hmax, im.hs[c]); vmax = std::max(vmax, im.vs[c]); }
+            fi.vmax = vmax;
+            fi.mpt = kK3TileW / (8 * hmax);
+            fi.tiles_x = uint32_t((p.width + kK3TileW - 1) / kK3TileW);
+            fi.tile0 = k23tile;
+            fi.sx = p.css == CSS_411 ? 2 : (p.css == CSS_422 || p.css == CSS_420) ? 1 : 0;
+            fi.sy = (p.css == CSS_440 || p.css == CSS_420) ? 1 : 0;
+            uint32_t off = 0;
+            for (int c = 0; c < p.ncomp; c++) {
+                fi.H[c] = uint8_t(im.hs[c]); fi.V[c] = uint8_t(im.vs[c]); fi.first_blk[c] = uint8_t(im.comp_first_blk[c]);
+                fi.hshift[c] = uint8_t(im.hs[c] == 4 ? 2 : im.hs[c] == 2 ? 1 : 0);
+                fi.qidx[c] = uint32_t(im.qt_index[c]);
+                fi.pitch[c] = uint32_t(8 * fi.mpt * im.hs[c]);
+                fi.base[c] = off;
+                off += c == 0 ? 16u * kK3TileW : 8u * kK3TileW;   // plane capacities in the kernel's shared memory
+            }
+            const uint32_t ntiles = fi.tiles_x * uint32_t(p.mcus_y);
+            h_tile_img_.insert(h_tile_img_.end(), ntiles, uint16_t(h_fused_.size()));
+            h_fused_.push_back(fi);
+            k23tile += ntiles;
             stats_.fused_blocks += im.nblocks;
         }
         od.tile0 = k3tile;
@@ -570,7 +596,6 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     h_img_dctile0_[size_t(n)] = dctile;
     h_k2_tile0_[size_t(n)] = k2tile;
     h_k3_tile0_[size_t(n)] = k3tile;
-    h_k23_tile0_[size_t(n)] = k23tile;
     scan_bytes_ = scan_off;
     raw_bytes_ = raw_off;
     nseg_total_ = nseg_total;
@@ -619,7 +644,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
 
 // Descriptor block: one pinned host buffer mirrored by one device buffer, one copy.
 struct Lane::Layout {
-    size_t images, outputs, cta0, k0tile0, dctile0, k2tile0, k3tile0, k23tile0, gather, luts, qtables, total;
+    size_t images, outputs, cta0, k0tile0, dctile0, k2tile0, k3tile0, fused, tile_img, gather, luts, qtables, total;
 };
 
 int Lane::Upload(cudaStream_t up, UploadTurn turn) {
@@ -636,7 +661,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     L.dctile0 = place((n + 1) * 4);
     L.k2tile0 = place((n + 1) * 4);
     L.k3tile0 = place((n + 1) * 4);
-    L.k23tile0 = place((n + 1) * 4);
+    L.fused = place(h_fused_.size() * sizeof(FusedImage));
+    L.tile_img = place(h_tile_img_.size() * 2);
     L.gather = place(n * sizeof(GatherItem));
     L.luts = place(h_lut_ptrs_.size() * sizeof(HuffLutSet));
     L.qtables = place(h_qtables_.size() * 2);
@@ -650,7 +676,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     std::memcpy(h + L.dctile0, h_img_dctile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.k2tile0, h_k2_tile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.k3tile0, h_k3_tile0_.data(), (n + 1) * 4);
-    std::memcpy(h + L.k23tile0, h_k23_tile0_.data(), (n + 1) * 4);
+    std::memcpy(h + L.fused, h_fused_.data(), h_fused_.size() * sizeof(FusedImage));
+    std::memcpy(h + L.tile_img, h_tile_img_.data(), h_tile_img_.size() * 2);
     std::memcpy(h + L.gather, h_gather_.data(), n * sizeof(GatherItem));
     for (size_t s = 0; s < h_lut_ptrs_.size(); s++) std::memcpy(h + L.luts + s * sizeof(HuffLutSet), h_lut_ptrs_[s], sizeof(HuffLutSet));
     std::memcpy(h + L.qtables, h_qtables_.data(), h_qtables_.size() * 2);
@@ -715,9 +742,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     k3_.outputs = reinterpret_cast<const OutputDesc*>(d + L.outputs);
     k3_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k3tile0);
     k3_.planes = k2_.planes;
-    k23_.images = k1_.images;
-    k23_.outputs = k2_.outputs;
-    k23_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k23tile0);
+    k23_.fused = reinterpret_cast<const FusedImage*>(d + L.fused);
+    k23_.tile_img = reinterpret_cast<const uint16_t*>(d + L.tile_img);
     k23_.qtables = k2_.qtables;
     k23_.entries = k1_.entries;
     k23_.blk_rec = k1_.blk_rec;

@@ -160,9 +160,11 @@ class Lane {
     // host-side batch description
     std::vector<ImageDesc> h_images_;
     std::vector<OutputDesc> h_outputs_;
-    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_, h_k0_tile0_, h_k23_tile0_, h_needed_segments_;
+    std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_, h_k0_tile0_, h_needed_segments_;
     uint32_t truncated_images_ = 0;
     std::vector<GatherItem> h_gather_;
+    std::vector<FusedImage> h_fused_;      // pictures served by the fused IDCT + output kernel
+    std::vector<uint16_t> h_tile_img_;     // per strip of that kernel: index into h_fused_
     std::vector<const HuffLutSet*> h_lut_ptrs_;
     std::vector<const ParsedJpeg*> h_lut_specs_;
     std::vector<uint64_t> h_lut_hashes_;

@@ -137,4 +137,22 @@ struct OutputDesc {
     int32_t fused;           // whole-picture RGB / RGB_PLANAR: the fused IDCT + output kernel serves it (no IDCT tiles' output, no output tiles)
 };
 
+// Everything the fused IDCT + output kernel (k23_fused.cu) needs about one picture, prepared on the host so that a CTA
+// starts from one record instead of deriving it (a quarter of the kernel's time when thread 0 did: profiles/r02_*).
+struct FusedImage {
+    uint64_t ent0, blk0;          // the picture's coefficient entries / block records
+    uint8_t* dst[3];
+    uint32_t dpitch;              // pitch[0]: RGB rows, and all three RGB_PLANAR planes (src/rocjpeg_decoder.cpp:526-544)
+    uint32_t ent_cap;
+    int32_t width, height, css, fmt;
+    int32_t ncomp, bpm, mcus_x, vmax;
+    int32_t mpt;                  // MCUs per 256-sample strip
+    uint32_t tiles_x;             // strips per MCU row
+    uint32_t tile0;               // first strip of the picture
+    int32_t sx, sy;               // chroma shifts
+    uint8_t H[3], V[3], first_blk[3], hshift[3];
+    uint32_t qidx[3];             // quantiser table per component
+    uint32_t pitch[3], base[3];   // shared-memory plane pitch / offset per component
+};
+
 }  // namespace rjb

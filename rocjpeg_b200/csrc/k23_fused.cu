@@ -35,21 +35,7 @@ __device__ __forceinline__ uint32_t UpperIndexF(const uint32_t* a, uint32_t n, u
     return lo;
 }
 
-struct Strip {
-    const uint32_t* entries;
-    const BlockRec* rec;
-    uint32_t ent_cap;
-    int32_t ncomp, bpm, mcus_x, hmax, vmax;
-    int32_t H[3], V[3], first_blk[3];
-    int32_t m0, nm;              // first MCU of the strip in its MCU row, MCUs present
-    int32_t my;                  // MCU row
-    int32_t nblocks;             // blocks of the strip
-    int32_t cnt[3], nbw[3];      // blocks / blocks per block row, per component
-    uint32_t pitch[3], base[3];  // shared-memory plane pitch and offset per component
-    uint32_t qidx[3];            // quantiser table of each component
-};
-
-__global__ void __launch_bounds__(kFThreads, 4) k23_fused(K23Args a) {
+__global__ void __launch_bounds__(kFThreads, 6) k23_fused(K23Args a) {
     PdlEntry();
     constexpr int kRS = 12, kBS = 104;   // workspace strides as in k2_idct.cu (bank-conflict free column / row access)
     __shared__ __align__(16) int ws[32 * kBS];
@@ -60,89 +46,60 @@ __global__ void __launch_bounds__(kFThreads, 4) k23_fused(K23Args a) {
     __shared__ uint16_t s_count[kMaxBlocks], s_off[kMaxBlocks];
     __shared__ int16_t s_dc[kMaxBlocks];
     __shared__ uint8_t s_comp[kMaxBlocks];
-    __shared__ Strip s_strip;
     __shared__ K3Job s_job;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // every thread reads the picture's record itself (uniform loads, one cache line): no thread-0 prologue
+    const FusedImage& fi = a.fused[__ldg(a.tile_img + blockIdx.x)];
+    const uint32_t t = blockIdx.x - fi.tile0;
+    const int mrow = int(t / fi.tiles_x), tx = int(t - uint32_t(mrow) * fi.tiles_x);
+    const int m0 = tx * fi.mpt, nm = min(fi.mpt, fi.mcus_x - m0);
+    const int ncomp = fi.ncomp;
+    const int nbw0 = nm * fi.H[0], nbw1 = ncomp > 1 ? nm * fi.H[1] : 0, nbw2 = ncomp > 2 ? nm * fi.H[2] : 0;
+    const int cnt0 = nbw0 * fi.V[0], cnt1 = nbw1 * (ncomp > 1 ? fi.V[1] : 0), cnt2 = nbw2 * (ncomp > 2 ? fi.V[2] : 0);
+    const int nblocks = cnt0 + cnt1 + cnt2;
+    const uint32_t* entries = a.entries + fi.ent0;
+    const BlockRec* rec = a.blk_rec + fi.blk0;
+    const int xt = tx * kStripW, rows = 8 * fi.vmax, y0t = mrow * rows;
     if (tid == 0) {
-        const uint32_t img = UpperIndexF(a.img_tile0, uint32_t(a.nimages), blockIdx.x);
-        const ImageDesc& im = a.images[img];
-        const OutputDesc& od = a.outputs[img];
-        const uint32_t t = blockIdx.x - a.img_tile0[img];
-        const uint32_t tiles_x = uint32_t(im.width + kStripW - 1) / kStripW;
-        Strip st;
-        st.entries = a.entries + im.ent0;
-        st.rec = a.blk_rec + im.blk0;
-        st.ent_cap = im.ent_cap;
-        st.ncomp = im.ncomp;
-        st.bpm = im.bpm;
-        st.mcus_x = im.mcus_x;
-        st.hmax = st.vmax = 1;
-        for (int c = 0; c < im.ncomp; c++) {
-            st.H[c] = im.hs[c]; st.V[c] = im.vs[c]; st.first_blk[c] = im.comp_first_blk[c];
-            st.qidx[c] = uint32_t(im.qt_index[c]);
-            st.hmax = max(st.hmax, im.hs[c]);
-            st.vmax = max(st.vmax, im.vs[c]);
-        }
-        const int mpt = kStripW / (8 * st.hmax);            // MCUs per full strip
-        st.my = int(t / tiles_x);
-        st.m0 = int(t % tiles_x) * mpt;
-        st.nm = min(mpt, im.mcus_x - st.m0);
-        st.nblocks = 0;
-        uint32_t off = 0;
-        for (int c = 0; c < 3; c++) {
-            const bool have = c < im.ncomp;
-            st.nbw[c] = have ? st.nm * st.H[c] : 0;
-            st.cnt[c] = have ? st.nbw[c] * st.V[c] : 0;
-            st.nblocks += st.cnt[c];
-            st.pitch[c] = have ? uint32_t(8 * mpt * st.H[c]) : 0u;
-            st.base[c] = off;
-            off += c == 0 ? uint32_t(kLumaBytes) : uint32_t(kChromaBytes);
-        }
-        s_strip = st;
         // the row routines see the strip's shared-memory planes through pointers whose origin is the picture's (0, 0)
-        const int sx = im.css == CSS_411 ? 2 : (im.css == CSS_422 || im.css == CSS_420) ? 1 : 0;
-        const int sy = (im.css == CSS_440 || im.css == CSS_420) ? 1 : 0;
         K3Job j;
-        const int xt = int(t % tiles_x) * kStripW, y0t = st.my * 8 * st.vmax;
         for (int c = 0; c < 3; c++) {
-            const int cc = c < im.ncomp ? c : 0;
-            const int shx = cc ? sx : 0, shy = cc ? sy : 0;
-            j.pitch[c] = st.pitch[cc];
-            j.p[c] = s_pl + st.base[cc] - (size_t(y0t >> shy) * st.pitch[cc] + size_t(xt >> shx));
+            const int cc = c < ncomp ? c : 0;
+            const int shx = cc ? fi.sx : 0, shy = cc ? fi.sy : 0;
+            j.pitch[c] = fi.pitch[cc];
+            j.p[c] = s_pl + fi.base[cc] - (size_t(y0t >> shy) * fi.pitch[cc] + size_t(xt >> shx));
+            j.dst[c] = fi.dst[c];
+            j.dpitch[c] = fi.dpitch;
         }
-        for (int c = 0; c < 4; c++) {
-            j.dst[c] = od.dst[c];
-            j.dpitch[c] = od.dst_pitch[c];
-        }
-        j.W = im.width; j.H = im.height; j.x0 = 0; j.y0 = 0; j.css = im.css; j.fmt = od.fmt;
+        j.dst[3] = nullptr;
+        j.dpitch[3] = 0;
+        j.W = fi.width; j.H = fi.height; j.x0 = 0; j.y0 = 0; j.css = fi.css; j.fmt = fi.fmt;
         j.xt = xt;
-        j.ty = st.my;
-        j.nx = min(kStripW, im.width - xt);
+        j.ty = mrow;
+        j.nx = min(kStripW, fi.width - xt);
         s_job = j;
     }
-    __syncthreads();
-    const Strip& st = s_strip;
     // quantiser / offset tables per component
-    for (int idx = tid; idx < st.ncomp * 64; idx += kFThreads) {
+    for (int idx = tid; idx < ncomp * 64; idx += kFThreads) {
         const int c = idx >> 6, code = idx & 63;   // entries carry position + 1 (huff_core.cuh)
         const int nat = kZigzag[(code + 63) & 63];
-        s_tab[c][code] = uint32_t(((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(a.qtables + size_t(st.qidx[c]) * 64 + nat)) << 16);
+        s_tab[c][code] = uint32_t(((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(a.qtables + size_t(fi.qidx[c]) * 64 + nat)) << 16);
     }
     // per block of the strip: its record (where its entries lie, integrated DC) and where its samples go
-    if (tid < st.nblocks) {
-        int g = tid, c = 0;
-        while (c < 2 && g >= st.cnt[c]) g -= st.cnt[c++];
-        const int v = g / st.nbw[c], bx = g - v * st.nbw[c];
-        const int hs = __ffs(st.H[c]) - 1;
-        const size_t blk = size_t(st.my * st.mcus_x + st.m0 + (bx >> hs)) * size_t(st.bpm) + size_t(st.first_blk[c] + v * st.H[c] + (bx & (st.H[c] - 1)));
-        const uint2 r = __ldg(reinterpret_cast<const uint2*>(st.rec + blk));
-        uint32_t e0 = blk ? __ldg(&st.rec[blk - 1].end) : 0u, e1 = r.x;
-        if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 0xFFFFu || e1 > st.ent_cap) e1 = e0 = 0;   // never decoded (as k2_idct.cu)
+    if (tid < nblocks) {
+        int g = tid, c = 0, nbw = nbw0;
+        if (g >= cnt0) { g -= cnt0; c = 1; nbw = nbw1; if (g >= cnt1) { g -= cnt1; c = 2; nbw = nbw2; } }
+        const int v = g / nbw, bx = g - v * nbw;
+        const int H = fi.H[c];
+        const size_t blk = size_t(mrow * fi.mcus_x + m0 + (bx >> fi.hshift[c])) * size_t(fi.bpm) + size_t(fi.first_blk[c] + v * H + (bx & (H - 1)));
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(rec + blk));
+        uint32_t e0 = blk ? __ldg(&rec[blk - 1].end) : 0u, e1 = r.x;
+        if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 0xFFFFu || e1 > fi.ent_cap) e1 = e0 = 0;   // never decoded (as k2_idct.cu)
         s_first[tid] = e0;
         s_count[tid] = uint16_t(e1 - e0);
         s_dc[tid] = int16_t(r.y & 0xFFFFu);
         s_comp[tid] = uint8_t(c);
-        s_off[tid] = uint16_t(st.base[c] + uint32_t(v * 8) * st.pitch[c] + uint32_t(bx * 8));
+        s_off[tid] = uint16_t(fi.base[c] + uint32_t(v * 8) * fi.pitch[c] + uint32_t(bx * 8));
     }
     __syncthreads();
     // ---- IDCT: 32 blocks at a time, 8 threads per block (k2_idct.cu's inner loop, samples to shared memory) ----
@@ -150,12 +107,12 @@ __global__ void __launch_bounds__(kFThreads, 4) k23_fused(K23Args a) {
     int* my = ws + b * kBS;
     const uint32_t my_sa = uint32_t(__cvta_generic_to_shared(my));
 #pragma unroll 1
-    for (int g0 = 0; g0 < st.nblocks; g0 += 32) {
+    for (int g0 = 0; g0 < nblocks; g0 += 32) {
         const int g = g0 + b;
-        const bool valid = g < st.nblocks;
+        const bool valid = g < nblocks;
         const int c = valid ? s_comp[g] : 0;
         const uint32_t n = valid ? s_count[g] : 0u;
-        const uint32_t* ep = st.entries + (valid ? s_first[g] : 0u) + uint32_t(jj);
+        const uint32_t* ep = entries + (valid ? s_first[g] : 0u) + uint32_t(jj);
         if (valid) {
             int4* row = reinterpret_cast<int4*>(my + jj * kRS);
             row[0] = make_int4(0, 0, 0, 0);
@@ -195,7 +152,7 @@ __global__ void __launch_bounds__(kFThreads, 4) k23_fused(K23Args a) {
             const int4 lo = *reinterpret_cast<const int4*>(my + jj * kRS), hi = *reinterpret_cast<const int4*>(my + jj * kRS + 4);   // row jj
             in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
             Islow8<18>(in, out, (1 << 17) + (128 << 18));
-            *reinterpret_cast<uint2*>(s_pl + s_off[g] + uint32_t(jj) * st.pitch[c]) =
+            *reinterpret_cast<uint2*>(s_pl + s_off[g] + uint32_t(jj) * fi.pitch[c]) =
                 make_uint2(PackSat4(out[0], out[1], out[2], out[3]), PackSat4(out[4], out[5], out[6], out[7]));
         }
         __syncwarp();
@@ -213,7 +170,6 @@ __global__ void __launch_bounds__(kFThreads, 4) k23_fused(K23Args a) {
     const uintptr_t bases = fmt == FMT_RGB ? reinterpret_cast<uintptr_t>(j.dst[0]) + size_t(j.xt) * 3
                                            : (reinterpret_cast<uintptr_t>(j.dst[0]) | reinterpret_cast<uintptr_t>(j.dst[1]) |
                                               reinterpret_cast<uintptr_t>(j.dst[2])) + size_t(j.xt);
-    const int rows = 8 * st.vmax, y0t = st.my * rows;
     uint8_t* buf = s_buf[warp];
     for (int r = warp; r < rows; r += kFThreads / 32) {
         const int y = y0t + r;

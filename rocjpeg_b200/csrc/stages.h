@@ -159,9 +159,8 @@ cudaError_t LaunchK2Idct(const K2Args& a, cudaStream_t stream);
 
 // K2 + K3 in one kernel for whole-picture RGB / RGB_PLANAR outputs (OutputDesc::fused): coefficients in, pixels out.
 struct K23Args {
-    const ImageDesc* images;
-    const OutputDesc* outputs;
-    const uint32_t* img_tile0;    // nimages + 1: first strip of each image (fused images only have strips)
+    const FusedImage* fused;      // one per image served by this kernel
+    const uint16_t* tile_img;     // per strip: index into `fused`
     const uint16_t* qtables;
     const uint32_t* entries;
     const BlockRec* blk_rec;
