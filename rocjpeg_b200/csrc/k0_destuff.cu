@@ -58,20 +58,59 @@ __device__ __forceinline__ Elem ShflUp(const Elem& e, int d) {
 }
 
 // A thread's 64 bytes of an image's uploaded data.
+//   kind kGeneral  anything else: a marker of any kind (FF not followed by 00), two stuffed bytes in one word, or a chunk
+//                  that reaches over an end of the scan - the per-piece code of k0_core.cuh handles it;
+//   kind kData     wholly inside the scan, no FF in it, the byte before it is not FF: 64 data bytes;
+//   kind kStuffed  wholly inside the scan, every FF in it is followed by 00 (byte stuffing only): the data bytes are the
+//                  chunk minus the bytes that follow an FF. `drop[i]` flags those (0x80 in the byte's lane), at most one per word.
+// Four chunks out of five are kData, nearly all others kStuffed; both are recognised and counted without a branch per byte.
+enum ChunkKind : int { kGeneral = 0, kData = 1, kStuffed = 2 };
 struct Chunk {
     uint32_t w[4 * kPieces];
+    uint32_t drop[4 * kPieces];
     uint32_t prev, next;   // the bytes around it (only meaningful inside the scan)
     int64_t pos0;          // scan position of byte 0
     bool overlaps;         // some byte lies inside the scan
-    bool fast;             // wholly inside the scan, no FF in or right before it: 64 data bytes and nothing else
+    int kind;
+    uint32_t nkeep;        // data bytes of a kData / kStuffed chunk
 };
 
+// 0x80 in every byte of x that is zero (exact per byte: no carries between bytes)
+__device__ __forceinline__ uint32_t ZeroBytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+
 __device__ __forceinline__ void FinishChunk(Chunk& c, int64_t len) {
+    constexpr int NW = 4 * kPieces;
     c.overlaps = c.pos0 + kChunk > 0 && c.pos0 < len;
-    uint32_t any = 0;
+    c.kind = kGeneral;
+    c.nkeep = 0;
+    if (!(c.pos0 >= 0 && c.pos0 + kChunk <= len)) return;
+    uint32_t f[NW], any = 0, ev = 0, two = 0, holes = 0;
 #pragma unroll
-    for (int i = 0; i < 4 * kPieces; i++) any |= (~c.w[i] - 0x01010101u) & c.w[i];   // top bit of a byte set <=> some byte of the word is FF
-    c.fast = c.pos0 >= 0 && c.pos0 + kChunk <= len && (any & 0x80808080u) == 0u && c.prev != 0xFFu;
+    for (int i = 0; i < NW; i++) {
+        f[i] = ZeroBytes(~c.w[i]);   // FF bytes
+        any |= f[i];
+    }
+    if (any == 0u && c.prev != 0xFFu) {
+        c.kind = kData;
+        c.nkeep = kChunk;
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        // the byte that follows each byte of word i, lane for lane
+        const uint32_t nb = i + 1 < NW ? __funnelshift_r(c.w[i], c.w[i + 1], 8) : ((c.w[i] >> 8) | (c.next << 24));
+        ev |= f[i] & ~ZeroBytes(nb);                                                             // FF followed by something else than 00
+        const uint32_t d = (i ? __funnelshift_l(f[i - 1], f[i], 8) : ((f[0] << 8) | (c.prev == 0xFFu ? 0x80u : 0u))) & ~f[i];   // bytes behind an FF (an FF there is judged on its own)
+        c.drop[i] = d;
+        two |= d & (d - 1u);
+        holes += uint32_t(__popc(d));
+    }
+    // (the byte behind an FF in front of the chunk is dropped whatever it is - stuffing or the second byte of a marker
+    // that belongs to the previous chunk - unless it is FF itself, which `ev` then reports)
+    if ((ev | two) == 0u) {
+        c.kind = kStuffed;
+        c.nkeep = uint32_t(kChunk) - holes;
+    }
 }
 
 // `off` = byte offset of the chunk in the image's uploaded bytes (multiple of 64).
@@ -104,8 +143,8 @@ __device__ __forceinline__ Piece PieceOf(const Chunk& c, int j, int64_t len) {
 __device__ __forceinline__ Elem ChunkElem(const Chunk& c, int64_t len, bool* plain) {
     Elem e{0u, 0u, 0u, 0u};
     *plain = true;
-    if (c.fast) {
-        e.tail = kChunk;
+    if (c.kind != kGeneral) {
+        e.tail = c.nkeep;
         return e;
     }
     if (!c.overlaps) return e;
@@ -301,28 +340,46 @@ struct DevMem {
     }
 };
 
-// NW little-endian words (4 NW bytes) to shared memory at byte address `at`, any alignment: word stores of the
-// funnel-shifted stream, byte stores only for the partial words at both ends (a neighbouring lane owns their
-// other bytes).
+// Removes the dropped bytes of a kStuffed chunk in registers: from the top word down (a deletion only moves what lies
+// above it, which has been dealt with), the bytes above a hole slide down by one. Afterwards the first c.nkeep bytes of
+// w[] are the chunk's data bytes in order.
+__device__ __forceinline__ void DeleteHoles(Chunk& c) {
+    constexpr int NW = 4 * kPieces;
+#pragma unroll
+    for (int i = NW - 1; i >= 0; i--) {
+        const uint32_t d = c.drop[i];
+        if (d) {
+            const uint32_t below = (d >> 7) - 1u;                                   // the bytes of word i below the hole (d = 0x80 << 8b)
+            const uint32_t up = i + 1 < NW ? c.w[i + 1] : 0u;
+            c.w[i] = (c.w[i] & below) | (__funnelshift_r(c.w[i], up, 8) & ~below);   // hole closed, the next word's first byte enters
+#pragma unroll
+            for (int k = i + 1; k < NW; k++) c.w[k] = __funnelshift_r(c.w[k], k + 1 < NW ? c.w[k + 1] : 0u, 8);
+        }
+    }
+}
+
+// The first n bytes of the NW little-endian words w[] to shared memory at byte address `at` (any alignment), exactly:
+// whole words of the stream as seen from the destination's word grid (funnel-shifted), byte stores only for the words
+// the run covers partly at its two ends - a neighbouring lane owns their other bytes.
 template <int NW>
-__device__ __forceinline__ void StoreShifted(uint8_t* at, const uint32_t* w) {
+__device__ __forceinline__ void StoreBytesShifted(uint8_t* at, const uint32_t (&w)[NW], uint32_t n) {
     const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(at)) & 3u;
     uint32_t* p = reinterpret_cast<uint32_t*>(at - a);
-    if (a == 0u) {
+    const uint32_t sh = 32u - 8u * a;   // (funnel shifts take their count mod 32: a == 0 passes w[k] through)
 #pragma unroll
-        for (int i = 0; i < NW; i++) p[i] = w[i];
-        return;
+    for (int k = 0; k <= NW; k++) {
+        // destination word k holds stream bytes [4k - a, 4k - a + 4)
+        const uint32_t lo_w = k ? w[k - 1] : 0u, hi_w = k < NW ? w[k] : 0u;
+        const uint32_t v = a ? __funnelshift_r(lo_w, hi_w, sh) : hi_w;
+        const int lo = 4 * k - int(a), hi = lo + 4;
+        if (lo >= 0 && hi <= int(n)) {
+            if (k < NW || a) p[k] = v;
+        } else if (hi > 0 && lo < int(n)) {
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (lo + b >= 0 && lo + b < int(n)) reinterpret_cast<uint8_t*>(p + k)[b] = uint8_t(v >> (8 * b));
+        }
     }
-    const uint32_t down = 32u - 8u * a;
-#pragma unroll
-    for (int b = 0; b < 3; b++)
-        if (uint32_t(b) < 4u - a) at[b] = uint8_t(w[0] >> (8 * b));
-#pragma unroll
-    for (int i = 1; i < NW; i++) p[i] = __funnelshift_r(w[i - 1], w[i], down);
-    uint8_t* tail = at + 4 * NW - a;
-#pragma unroll
-    for (int b = 0; b < 3; b++)
-        if (uint32_t(b) < a) tail[b] = uint8_t(w[NW - 1] >> (down + 8 * b));
 }
 
 template <int S>
@@ -337,9 +394,10 @@ __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
     const ImageDesc& im = a.images[img];
     const int64_t len = int64_t(im.raw_len);
     const uint64_t off = uint64_t(tile - im.k0_tile0) * kTileBytes + uint64_t(tid) * kChunk;
-    const Chunk c = LoadChunk(a.raw, im, off);
+    Chunk c = LoadChunk(a.raw, im, off);
     bool plain;
     const Elem mine = ChunkElem(c, len, &plain);
+    if (c.kind == kStuffed) DeleteHoles(c);
     Elem ex;
     if (tid == 0) s_fill_from = 0xFFFFFFFFu;
     CtaScan(mine, plain, s_warp, &ex, nullptr);
@@ -370,12 +428,10 @@ __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
         const uint32_t phase = uint32_t(reinterpret_cast<uintptr_t>(dst) & 15u);
         if (member) {
             uint8_t* at = s_stage[warp] + phase + (ex.tail - cL);
-            if (c.fast) {
-                StoreShifted<4 * kPieces>(at, c.w);
+            if (c.kind != kGeneral) {
+                StoreBytesShifted<4 * kPieces>(at, c.w, n);   // (the holes of a kStuffed chunk were deleted above)
             } else {
-                // a chunk with an FF in it (one in five): piece by piece, byte stores. (Word stores for its all-kept pieces,
-                // mixed with the byte-wise compaction of the others, lost the piece behind a compacted one in the generated
-                // code - found by the restart-marker pictures of tests/test_gpu_parity.py; not worth a fifth of the chunks.)
+                // a chunk at an end of the scan, or with two stuffed bytes in one word: piece by piece, byte stores
 #pragma unroll
                 for (int j = 0; j < kPieces; j++) at += CompactPiece(PieceOf(c, j, len), at);
             }
