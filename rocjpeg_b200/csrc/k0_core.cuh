@@ -286,7 +286,7 @@ RJB_K0_HD void WalkPiece(const Piece& pc, const Elem& ex, const Elem& mine, cons
 // last interval.
 template <class Mem>
 RJB_K0_HD void FinishPiece(const Piece& pc, const Elem& ex, const Elem& mine, const Placer<Mem>& pl, bool first_piece) {
-    if (first_piece) pl.Open(0u, 0u);
+    if (first_piece) pl.Open(0u, 0u);   // (the kernel opens interval 0 itself and passes false)
     if (pl.im.raw_len == 0u) {
         if (first_piece) pl.End(0u, 0u, 0u, 0u, kScanNoEoi);
         return;

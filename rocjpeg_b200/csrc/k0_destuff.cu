@@ -451,18 +451,32 @@ __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
     }
     // Chunks with a marker walk their pieces (bytes stored one by one, restart intervals opened and closed); the first
     // chunk of the image opens interval 0; the chunk holding the last byte closes the last interval when there is no FF D9.
+    // (The walk indexes the chunk's words by a run-time piece number: it reads them from the warp's staging buffer, free
+    // by now, so that the register copy is only ever indexed statically and stays in registers.)
     const bool first = tile == im.k0_tile0 && tid == 0;
     const bool walk = !plain && c.overlaps && !ended_before;
-    if (walk || first || (c.overlaps && c.pos0 + kChunk >= len) || len == 0) {
+    if (first) pl.Open(0u, 0u);
+    if (len == 0) {
+        if (first) pl.End(0u, 0u, 0u, 0u, kScanNoEoi);
+    } else if (walk) {
+        uint32_t* sw = reinterpret_cast<uint32_t*>(s_stage[warp]) + lane * (kChunk / 4);
+#pragma unroll
+        for (int k = 0; k < 4 * kPieces; k++) sw[k] = c.w[k];
         Elem x = ex;
 #pragma unroll 1
         for (int j = 0; j < kPieces; j++) {
-            const Piece pc = PieceOf(c, j, len);
+            const uint32_t prev = j ? (sw[4 * j - 1] >> 24) : c.prev;
+            const uint32_t next = j < kPieces - 1 ? (sw[4 * j + 4] & 0xFFu) : c.next;
+            const uint32_t pw[4] = {sw[4 * j], sw[4 * j + 1], sw[4 * j + 2], sw[4 * j + 3]};
+            const Piece pc = ClassifyPiece(pw, prev, next, c.pos0 + 16 * j, len);
             const Elem pe = PieceElem(pc);
-            if (walk && pc.any && !(x.flags & kEnded)) WalkPiece(pc, x, pe, pl);
-            FinishPiece(pc, x, pe, pl, first && j == 0);
+            if (pc.any && !(x.flags & kEnded)) WalkPiece(pc, x, pe, pl);
+            FinishPiece(pc, x, pe, pl, false);
             x = Combine(x, pe);
         }
+    } else if (plain && c.overlaps && !ended_before && c.pos0 + kChunk >= len) {
+        const Elem inc = Combine(ex, mine);   // no marker in the chunk that holds the last byte: the slice ends with the buffer
+        pl.End(inc.last_r, inc.nrst, inc.tail, im.raw_len, kScanNoEoi | ((inc.flags & kStray) ? kScanStrayMarker : 0u));
     }
     __syncthreads();
     const uint32_t from = s_fill_from;
