@@ -130,7 +130,14 @@ typedef struct {
     int32_t decode_status;            /* RocJpegStatus rocJpegDecode would return for this stream */
     int32_t source_is_device_visible; /* the entropy-coded bytes are in page-locked memory (the caller's or the staging pool's) */
     int32_t source_is_zero_copy;      /* ... the caller's own page-locked buffer, used in place */
+    int32_t features;                 /* ROCJPEG_B200_FEAT_*: what the stream uses beyond what the reference's parser accepts */
 } RocJpegB200StreamInfo;
+/* Accepted here, rejected by the reference's parser: an SOF1 frame header with 8-bit samples (the
+ * sequential Huffman process is the same decode; libjpeg-turbo writes SOF1 as soon as a quantiser step exceeds 255),
+ * quantiser tables with 16-bit steps (src/rocjpeg_parser.cpp:230) and Huffman table ids 2 and 3 (:274). */
+#define ROCJPEG_B200_FEAT_SOF1 1
+#define ROCJPEG_B200_FEAT_DQT16 2
+#define ROCJPEG_B200_FEAT_HUFF_ID23 4
 RocJpegStatus rocJpegB200StreamGetInfo(RocJpegStreamHandle jpeg_stream_handle, RocJpegB200StreamInfo *info);
 /* The HOST restatement of the GPU destuffing pass (tests and taps only - rocJpegStreamParse does not touch the
  * entropy-coded bytes and the decode path never runs this): slice size up to the first FF D9 as the reference's

@@ -43,10 +43,11 @@ class OrcInfo(C.Structure):
         ("restart_interval", C.c_int32),
         ("num_mcus_ref", C.c_uint32), ("scan_offset", C.c_uint32), ("scan_size", C.c_uint32),
         ("qt", (C.c_uint8 * 64) * 4), ("qt_present", C.c_uint8 * 4),
-        ("dc_bits", (C.c_uint8 * 16) * 2), ("dc_vals", (C.c_uint8 * 12) * 2),
-        ("ac_bits", (C.c_uint8 * 16) * 2), ("ac_vals", (C.c_uint8 * 162) * 2),
-        ("dc_present", C.c_uint8 * 2), ("ac_present", C.c_uint8 * 2),
+        ("dc_bits", (C.c_uint8 * 16) * 4), ("dc_vals", (C.c_uint8 * 12) * 4),
+        ("ac_bits", (C.c_uint8 * 16) * 4), ("ac_vals", (C.c_uint8 * 162) * 4),
+        ("dc_present", C.c_uint8 * 4), ("ac_present", C.c_uint8 * 4),
         ("n_restart_markers", C.c_uint32),
+        ("qt16", (C.c_uint16 * 64) * 4), ("features", C.c_int32),
     ]
 
 

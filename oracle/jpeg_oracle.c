@@ -55,13 +55,23 @@ typedef struct {
     int32_t restart_interval;
     uint32_t num_mcus_ref;                /* the reference's num_mcus (parser.cpp:197) */
     uint32_t scan_offset, scan_size;      /* entropy-coded slice: [offset, offset+size) */
-    uint8_t qt[4][64];                    /* zig-zag order, as stored in the stream */
+    uint8_t qt[4][64];                    /* zig-zag order, as stored in the stream (low byte of a 16-bit table) */
     uint8_t qt_present[4];
-    uint8_t dc_bits[2][16], dc_vals[2][12];
-    uint8_t ac_bits[2][16], ac_vals[2][162];
-    uint8_t dc_present[2], ac_present[2];
+    uint8_t dc_bits[4][16], dc_vals[4][12];
+    uint8_t ac_bits[4][16], ac_vals[4][162];
+    uint8_t dc_present[4], ac_present[4];
     uint32_t n_restart_markers;           /* RSTn markers found inside the slice */
+    uint16_t qt16[4][64];                 /* the quantiser steps at full width, zig-zag order */
+    int32_t features;                     /* ORC_FEAT_*: what the stream uses beyond what the reference's parser accepts */
 } OrcInfo;
+
+/* Widening beyond the reference's parser: the sequential Huffman process with 8-bit samples
+ * is the same decode whether the frame header says SOF0 or SOF1 (T.81 Table B.1, F.1.1: "extended" only permits what
+ * follows); quantiser tables with 16-bit steps (the reference rejects them, parser.cpp:230) and Huffman table ids 2 and 3
+ * (rejected at parser.cpp:274) only change table storage. libjpeg-turbo writes SOF1 as soon as a quantiser step exceeds 255. */
+#define ORC_FEAT_SOF1 1
+#define ORC_FEAT_DQT16 2
+#define ORC_FEAT_HUFF_ID23 4
 
 static const uint8_t kZigzag[64] = {
     0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48,
@@ -110,6 +120,10 @@ int orc_parse(const uint8_t *d, size_t len, OrcInfo *o) {
         if (seglen < 2 || next > len) return ORC_BAD_JPEG;
         const uint8_t *s = d + p;
         switch (m) {
+        case 0xC1:   /* SOF1: extended sequential, Huffman - the same decode when the samples have 8 bits */
+            if (seglen < 8 || s[2] != 8) return ORC_BAD_JPEG;
+            o->features |= ORC_FEAT_SOF1;
+            /* fall through */
         case 0xC0: { /* SOF0, parser.cpp:160-207 */
             if (seglen < 8) return ORC_BAD_JPEG;
             o->height = (int)RD16(s + 3);
@@ -140,7 +154,8 @@ int orc_parse(const uint8_t *d, size_t len, OrcInfo *o) {
                 if (rem < 17) return ORC_BAD_JPEG;
                 uint8_t idx = *q++;
                 int is_ac = idx & 0xF0, id = idx & 0x0F;
-                if (id >= 2) return ORC_BAD_JPEG;                /* parser.cpp:274 */
+                if (id >= 4) return ORC_BAD_JPEG;                /* T.81 B.2.4.2: Th 0..3 (the reference stops at 1, parser.cpp:274) */
+                if (id >= 2) o->features |= ORC_FEAT_HUFF_ID23;
                 uint32_t count = 0;
                 for (int i = 0; i < 16; i++) count += q[i];
                 if (is_ac) {
@@ -168,12 +183,18 @@ int orc_parse(const uint8_t *d, size_t len, OrcInfo *o) {
             const uint8_t *q = s + 2, *end = s + seglen;
             while (q < end) {
                 uint8_t idx = *q++;
-                if (idx >> 4) return ORC_BAD_JPEG;               /* 16-bit tables, parser.cpp:230 */
+                int wide = idx >> 4;                             /* Pq: 0 = 8-bit steps, 1 = 16-bit (rejected by the reference, parser.cpp:230) */
+                idx &= 15;
+                if (wide > 1) return ORC_BAD_JPEG;
                 if (idx >= 4) return ORC_BAD_JPEG;               /* parser.cpp:234 */
-                if (q + 64 > end) return ORC_BAD_JPEG;
-                memcpy(o->qt[idx], q, 64);
+                if (q + (wide ? 128 : 64) > end) return ORC_BAD_JPEG;
+                for (int k = 0; k < 64; k++) {
+                    o->qt16[idx][k] = wide ? (uint16_t)RD16(q + 2 * k) : q[k];
+                    o->qt[idx][k] = (uint8_t)o->qt16[idx][k];
+                }
+                if (wide) o->features |= ORC_FEAT_DQT16;
                 o->qt_present[idx] = 1;
-                q += 64;
+                q += wide ? 128 : 64;
             }
             seen_dqt = 1;
             break;
@@ -261,7 +282,6 @@ int orc_supported(const OrcInfo *o) {
     if (o->css == CSS_422 && o->ncomp == 3 && o->hs[1] == o->hs[0]) return ORC_NOT_SUPPORTED; /* (2,2,2|2,1,1) */
     for (int i = 0; i < o->ncomp; i++) {
         if (!o->qt_present[o->tq[i]]) return ORC_BAD_JPEG;
-        if (o->td[i] >= 2 || o->ta[i] >= 2) return ORC_BAD_JPEG;
         if (!o->dc_present[o->td[i]] || !o->ac_present[o->ta[i]]) return ORC_BAD_JPEG;
     }
     return ORC_OK;
@@ -364,8 +384,8 @@ int orc_decode_coefficients(const uint8_t *data, size_t len, const OrcInfo *o, i
     int rc = orc_supported(o);
     if (rc != ORC_OK) return rc;
     if ((size_t)o->scan_offset + o->scan_size > len) return ORC_BAD_JPEG;
-    HuffTab dc[2], ac[2];
-    for (int i = 0; i < 2; i++) {
+    HuffTab dc[4], ac[4];
+    for (int i = 0; i < 4; i++) {
         if (o->dc_present[i]) build_hufftab(o->dc_bits[i], o->dc_vals[i], &dc[i]);
         if (o->ac_present[i]) build_hufftab(o->ac_bits[i], o->ac_vals[i], &ac[i]);
     }
@@ -489,7 +509,7 @@ int orc_idct_planes(const OrcInfo *o, const int16_t *coefs, uint8_t *planes) {
     size_t cb = 0;
     for (int c = 0; c < o->ncomp; c++) {
         uint16_t qn[64];
-        for (int k = 0; k < 64; k++) qn[kZigzag[k]] = o->qt[o->tq[c]][k];
+        for (int k = 0; k < 64; k++) qn[kZigzag[k]] = o->qt16[o->tq[c]][k];
         int pitch = o->blocks_w[c] * 8;
         for (int by = 0; by < o->blocks_h[c]; by++)
             for (int bx = 0; bx < o->blocks_w[c]; bx++) {

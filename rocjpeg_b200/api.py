@@ -72,6 +72,7 @@ class StreamInfo(C.Structure):
         ("mcus_x", C.c_int32), ("mcus_y", C.c_int32), ("blocks_per_mcu", C.c_int32),
         ("blocks_w", C.c_int32 * 3), ("blocks_h", C.c_int32 * 3), ("num_segments", C.c_uint32),
         ("decode_status", C.c_int32), ("source_is_device_visible", C.c_int32), ("source_is_zero_copy", C.c_int32),
+        ("features", C.c_int32),
     ]
 
 
@@ -79,6 +80,7 @@ class ScanStatus(C.Structure):
     _fields_ = [("segments_seen", C.c_uint32), ("scan_size", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+FEAT_SOF1, FEAT_DQT16, FEAT_HUFF_ID23 = 1, 2, 4
 SCAN_NO_EOI, SCAN_STRAY_MARKER, SCAN_EXTRA_RESTARTS, SCAN_MISSING_INTERVALS, SCAN_EMPTY_INTERVAL = 1, 2, 4, 8, 16
 DECODE_SHORT, TRUNCATED_MASK = 32, 8 | 16 | 32
 

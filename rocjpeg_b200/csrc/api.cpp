@@ -400,6 +400,7 @@ RocJpegStatus rocJpegB200StreamGetInfo(RocJpegStreamHandle jpeg_stream_handle, R
     info->decode_status = p.support_status;
     info->source_is_device_visible = h->parser->raw().dev != nullptr ? 1 : 0;
     info->source_is_zero_copy = h->parser->raw().zero_copy ? 1 : 0;
+    info->features = p.features;
     return ROCJPEG_STATUS_SUCCESS;
 }
 
@@ -452,7 +453,7 @@ RocJpegStatus rocJpegB200StreamGetQuantTable(RocJpegStreamHandle jpeg_stream_han
 
 RocJpegStatus rocJpegB200StreamGetHuffmanTable(RocJpegStreamHandle jpeg_stream_handle, int is_ac, int id, uint8_t bits[16],
                                                uint8_t vals[256], uint32_t* count) {
-    if (jpeg_stream_handle == nullptr || bits == nullptr || vals == nullptr || count == nullptr || id < 0 || id >= 2)
+    if (jpeg_stream_handle == nullptr || bits == nullptr || vals == nullptr || count == nullptr || id < 0 || id >= rjb::kHuffIds)
         return ROCJPEG_STATUS_INVALID_PARAMETER;
     const rjb::ParsedJpeg& p = static_cast<StreamHandle*>(jpeg_stream_handle)->parser->parsed();
     if (!p.valid) return ROCJPEG_STATUS_BAD_JPEG;

@@ -417,17 +417,17 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             int pair = -1;
             if (have) {
                 for (int q = 0; q < im.npairs; q++)
-                    if (im.pair_dc[q] == p.td[c] && im.pair_ac[q] == 2 + p.ta[c]) pair = q;
+                    if (im.pair_dc[q] == p.td[c] && im.pair_ac[q] == kHuffIds + p.ta[c]) pair = q;
                 if (pair < 0) {
                     pair = im.npairs++;
                     im.pair_dc[pair] = uint8_t(p.td[c]);
-                    im.pair_ac[pair] = uint8_t(2 + p.ta[c]);
+                    im.pair_ac[pair] = uint8_t(kHuffIds + p.ta[c]);
                 }
             }
             for (int b = 0; b < H * V && k < kMaxBlocksPerMcu; b++, k++) {
                 im.mcu_comp[k] = uint8_t(c);
                 im.mcu_dc[k] = uint8_t(p.td[c]);
-                im.mcu_ac[k] = uint8_t(2 + p.ta[c]);
+                im.mcu_ac[k] = uint8_t(kHuffIds + p.ta[c]);
                 im.mcu_pair[k] = uint8_t(pair);
             }
             im.qt_index[c] = i * 3 + c;

@@ -25,7 +25,10 @@ constexpr int kSubCap = 1024;          // second-level entries shared by the fou
 enum Css : int32_t { CSS_444 = 0, CSS_440 = 1, CSS_422 = 2, CSS_420 = 3, CSS_411 = 4, CSS_400 = 5, CSS_UNKNOWN = -1 };
 enum Fmt : int32_t { FMT_NATIVE = 0, FMT_YUV_PLANAR = 1, FMT_Y = 2, FMT_RGB = 3, FMT_RGB_PLANAR = 4 };
 
-// One set of four Huffman tables (0 = DC0, 1 = DC1, 2 = AC0, 3 = AC1), decoder form: a two-level
+constexpr int kHuffIds = 4;            // Huffman table ids per class (T.81 B.2.4.2: Th 0..3; baseline files use 0 and 1)
+constexpr int kHuffTabs = 2 * kHuffIds;   // slots of a set: 0..3 = DC tables 0..3, 4..7 = AC tables 0..3
+
+// One set of Huffman tables (slot t < kHuffIds = DC table t, slot kHuffIds + t = AC table t), decoder form: a two-level
 // lookup over 32-bit entries (huff_core.cuh: MakeEntry / MakeLink).
 //   fast[t][next 9 bits]  symbol entry when the code is at most kFastBits long, else a link to a
 //                         sub-table in `sub` indexed by the following x bits (x = longest code under
@@ -35,13 +38,13 @@ enum Fmt : int32_t { FMT_NATIVE = 0, FMT_YUV_PLANAR = 1, FMT_Y = 2, FMT_RGB = 3,
 //   peek16 < upper[t][l] has length l and symbol vals[t][(peek16 >> (16-l)) + valoff[t][l]].
 // K1 stages fast + the used part of sub in shared memory; upper/valoff/vals stay in global memory.
 struct HuffLutSet {
-    uint32_t fast[4][kFastSize];
+    uint32_t fast[kHuffTabs][kFastSize];
     uint32_t sub[kSubCap];
     uint32_t sub_used;       // entries of `sub` in use
     uint32_t pad_[3];
-    uint32_t upper[4][17];   // exclusive upper bound of codes of length l, left-aligned to 16 bits
-    int32_t valoff[4][17];   // valptr[l] - mincode[l]
-    uint8_t vals[4][256];
+    uint32_t upper[kHuffTabs][17];   // exclusive upper bound of codes of length l, left-aligned to 16 bits
+    int32_t valoff[kHuffTabs][17];   // valptr[l] - mincode[l]
+    uint8_t vals[kHuffTabs][256];
 };
 
 // Geometry + bookkeeping of one image inside a batch (device-resident array).
@@ -53,11 +56,11 @@ struct ImageDesc {
     int32_t blocks_w[3], blocks_h[3];                 // MCU-padded block grid per component
     int32_t comp_first_blk[3];                        // index of a component's first block inside the MCU
     uint8_t mcu_comp[kMaxBlocksPerMcu];               // block-in-MCU -> component
-    uint8_t mcu_dc[kMaxBlocksPerMcu];                 // block-in-MCU -> DC table (0/1)
-    uint8_t mcu_ac[kMaxBlocksPerMcu];                 // block-in-MCU -> AC table (2/3 = AC0/AC1 slot in HuffLutSet)
+    uint8_t mcu_dc[kMaxBlocksPerMcu];                 // block-in-MCU -> DC table slot in HuffLutSet
+    uint8_t mcu_ac[kMaxBlocksPerMcu];                 // block-in-MCU -> AC table slot in HuffLutSet (kHuffIds + id)
     uint8_t mcu_pair[kMaxBlocksPerMcu];               // block-in-MCU -> table pair (index into pair_dc / pair_ac)
     uint8_t npairs;                                   // distinct (DC table, AC table) pairs the scan uses: 1..3
-    uint8_t pair_dc[3], pair_ac[3];                   // HuffLutSet table index (0..3) of each pair's DC / AC table
+    uint8_t pair_dc[3], pair_ac[3];                   // HuffLutSet slot of each pair's DC / AC table
     uint8_t pad_[3];
     int32_t lut_set;                                  // index into the batch's HuffLutSet array
     int32_t qt_index[3];                              // index into the batch's quant-table array (natural order u16[64])

@@ -101,9 +101,9 @@ RJB_HD uint32_t LinkFirst(uint32_t e) { return e >> 16; }
 RJB_HD uint32_t SlowEntry(const HuffLutSet* lut, uint32_t tab, uint32_t v16) {
     for (int l = kFastBits + 1; l <= 16; l++) {
         if (v16 < lut->upper[tab][l])
-            return MakeEntry(uint32_t(l), lut->vals[tab][(int32_t(v16 >> (16 - l)) + lut->valoff[tab][l]) & 255], tab >= 2);
+            return MakeEntry(uint32_t(l), lut->vals[tab][(int32_t(v16 >> (16 - l)) + lut->valoff[tab][l]) & 255], tab >= uint32_t(kHuffIds));
     }
-    return MakeEntry(16, 0, tab >= 2);
+    return MakeEntry(16, 0, tab >= uint32_t(kHuffIds));
 }
 
 RJB_HD uint32_t FunnelLeft(uint32_t hi, uint32_t lo, uint32_t k) {
@@ -115,17 +115,17 @@ RJB_HD uint32_t FunnelLeft(uint32_t hi, uint32_t lo, uint32_t k) {
 #endif
 }
 
-// Which Huffman tables block c of the MCU uses, as two bit masks (bit c = table id 0/1).
+// Which Huffman tables (HuffLutSet slots) block c of the MCU uses.
 struct TableSel {
-    uint32_t dc_mask, ac_mask;
+    uint8_t dc[kMaxBlocksPerMcu], ac[kMaxBlocksPerMcu];
 };
-RJB_HD uint32_t DcTab(TableSel t, int c) { return (t.dc_mask >> c) & 1u; }
-RJB_HD uint32_t AcTab(TableSel t, int c) { return 2u + ((t.ac_mask >> c) & 1u); }
+RJB_HD uint32_t DcTab(const TableSel& t, int c) { return t.dc[c]; }
+RJB_HD uint32_t AcTab(const TableSel& t, int c) { return t.ac[c]; }
 RJB_HD TableSel MakeTableSel(const uint8_t* mcu_dc, const uint8_t* mcu_ac, int bpm) {
-    TableSel t{0u, 0u};
+    TableSel t = {};
     for (int c = 0; c < bpm; c++) {
-        t.dc_mask |= uint32_t(mcu_dc[c] & 1u) << c;
-        t.ac_mask |= uint32_t(mcu_ac[c] & 1u) << c;   // slots 2/3 -> bit 0
+        t.dc[c] = mcu_dc[c];
+        t.ac[c] = mcu_ac[c];
     }
     return t;
 }

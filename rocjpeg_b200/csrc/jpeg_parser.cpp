@@ -180,12 +180,12 @@ int ClassifyChromaSubsampling(const int32_t h[3], const int32_t v[3]) {
 // ------------------------------------------------------------ Huffman tables
 
 // T.81 Annex C (code assignment) + F.2.2.3 (decoder tables), restated as a two-level lookup over
-// a left-aligned peek (device_types.h: HuffLutSet). slot: 0 = DC0, 1 = DC1, 2 = AC0, 3 = AC1.
+// a left-aligned peek (device_types.h: HuffLutSet). slot: t = DC table t, kHuffIds + t = AC table t.
 // Sub-tables are appended to out->sub (the caller zeroes the set before building its tables).
 void BuildHuffLut(const HuffSpec& spec, int slot, HuffLutSet* out, uint32_t sub_cap) {
     uint32_t* fast = out->fast[slot];
     if (sub_cap > uint32_t(kSubCap)) sub_cap = uint32_t(kSubCap);
-    const bool is_ac = slot >= 2;
+    const bool is_ac = slot >= kHuffIds;
     const uint32_t invalid = MakeEntry(16, 0, is_ac);   // unassigned code: 16 bits consumed, symbol 0
     for (int i = 0; i < kFastSize; i++) fast[i] = invalid;
     std::memcpy(out->vals[slot], spec.vals, 256);
@@ -254,8 +254,12 @@ bool StreamParser::Fail(const char* why) {
 }
 
 // src/rocjpeg_parser.cpp:160-207
-bool StreamParser::ParseSof(const uint8_t* s, uint32_t seglen) {
+bool StreamParser::ParseSof(const uint8_t* s, uint32_t seglen, bool extended) {
     if (seglen < 8) return Fail("truncated SOF");
+    if (extended) {   // SOF1: the sequential Huffman process; the same decode as SOF0 when the samples have 8 bits
+        if (s[2] != 8) return Fail("not a baseline JPEG: extended sequential frame (SOF1) with 12-bit samples - only 8-bit samples are decoded");
+        p_.features |= kFeatSof1;
+    }
     p_.height = int32_t(Rd16(s + 3));
     p_.width = int32_t(Rd16(s + 5));
     p_.ncomp = s[7];
@@ -284,7 +288,8 @@ bool StreamParser::ParseDht(const uint8_t* payload, uint32_t n) {
         uint8_t idx = *q++;
         bool is_ac = (idx & 0xF0) != 0;
         int id = idx & 0x0F;
-        if (id >= 2) return Fail("Huffman table id out of range");            // :274
+        if (id >= kHuffIds) return Fail("Huffman table id out of range");     // T.81 B.2.4.2: Th 0..3 (the reference stops at 1, :274)
+        if (id >= 2) p_.features |= kFeatHuffId23;
         uint32_t count = 0;
         for (int i = 0; i < 16; i++) count += q[i];
         if (is_ac ? count > 162 : count > 12) return Fail("too many Huffman values");   // :291, :298
@@ -306,12 +311,15 @@ bool StreamParser::ParseDqt(const uint8_t* payload, uint32_t n) {
     const uint8_t *q = payload, *end = payload + n;
     while (q < end) {
         uint8_t idx = *q++;
-        if (idx >> 4) return Fail("16-bit quantisation tables are not supported");   // :230
+        const int wide = idx >> 4;   // Pq: 0 = 8-bit steps, 1 = 16-bit (the reference rejects those, :230)
+        idx &= 15;
+        if (wide > 1) return Fail("quantisation table precision out of range");
         if (idx >= 4) return Fail("quantisation table id out of range");             // :234
-        if (q + 64 > end) return Fail("truncated DQT");
-        std::memcpy(p_.qt[idx], q, 64);
+        if (q + (wide ? 128 : 64) > end) return Fail("truncated DQT");
+        for (int k = 0; k < 64; k++) p_.qt[idx][k] = wide ? uint16_t(Rd16(q + 2 * k)) : uint16_t(q[k]);
+        if (wide) p_.features |= kFeatDqt16;
         p_.qt_present[idx] = true;
-        q += 64;
+        q += wide ? 128 : 64;
     }
     return true;
 }
@@ -537,8 +545,7 @@ void StreamParser::BuildDecodeTables() {
     if (p_.support_status == kStatusSuccess) {
         for (int i = 0; i < p_.ncomp; i++) {
             if (!p_.qt_present[p_.tq[i]]) p_.support_status = kStatusBadJpeg;
-            if (p_.td[i] >= 2 || p_.ta[i] >= 2) p_.support_status = kStatusBadJpeg;
-            else if (!p_.dc[p_.td[i]].present || !p_.ac[p_.ta[i]].present) p_.support_status = kStatusBadJpeg;
+            if (!p_.dc[p_.td[i]].present || !p_.ac[p_.ta[i]].present) p_.support_status = kStatusBadJpeg;
         }
     }
     if (dqt_cache_.changed)
@@ -551,7 +558,7 @@ void StreamParser::BuildDecodeTables() {
         const uint8_t* b = static_cast<const uint8_t*>(ptr);
         for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
     };
-    for (int t = 0; t < 2; t++) {
+    for (int t = 0; t < kHuffIds; t++) {
         uint8_t present[2] = {uint8_t(p_.dc[t].present), uint8_t(p_.ac[t].present)};
         mix(present, 2);
         mix(p_.dc[t].bits, 16);
@@ -563,7 +570,7 @@ void StreamParser::BuildDecodeTables() {
     // Shortest symbol that carries magnitude bits: code length + SSSS. Bounds how many
     // coefficient entries a scan of a given size can produce.
     uint32_t min_bits = 32;
-    for (int t = 0; t < 2; t++)
+    for (int t = 0; t < kHuffIds; t++)
         for (int is_ac = 0; is_ac < 2; is_ac++) {
             const HuffSpec& sp = is_ac ? p_.ac[t] : p_.dc[t];
             if (!sp.present) continue;
@@ -579,9 +586,9 @@ void StreamParser::BuildDecodeTables() {
     // debug knob: a smaller second-level arena forces long codes onto the canonical search
     const char* cap_env = std::getenv("ROCJPEG_B200_SUBCAP");
     const uint32_t cap = (cap_env && *cap_env) ? uint32_t(std::atoi(cap_env)) : uint32_t(kSubCap);
-    for (int t = 0; t < 2; t++) {
+    for (int t = 0; t < kHuffIds; t++) {
         if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &lut_, cap);
-        if (p_.ac[t].present) BuildHuffLut(p_.ac[t], 2 + t, &lut_, cap);
+        if (p_.ac[t].present) BuildHuffLut(p_.ac[t], kHuffIds + t, &lut_, cap);
     }
     lut_cap_ = cap;
     lut_valid_ = true;
@@ -600,6 +607,7 @@ void StreamParser::ResetFrame() {
     p_.mcus_x = p_.mcus_y = p_.bpm = 0;
     p_.support_status = 0;
     p_.nseg = 1;
+    p_.features &= (kFeatDqt16 | kFeatHuffId23);   // what the kept tables use stays with them; the frame's part is per stream
     raw_ = RawScan();
     host_scan_.done = false;
     err_.clear();
@@ -643,12 +651,14 @@ bool StreamParser::ParseLocked(const uint8_t* d, size_t len, bool data_is_file_b
     auto parse_dht = [this](const uint8_t* q, uint32_t n) { return ParseDht(q, n); };
     auto parse_dqt = [this](const uint8_t* q, uint32_t n) { return ParseDqt(q, n); };
     auto clear_dht = [this]() {
-        for (int t = 0; t < 2; t++) p_.dc[t].present = p_.ac[t].present = false;
+        for (int t = 0; t < kHuffIds; t++) p_.dc[t].present = p_.ac[t].present = false;
         lut_valid_ = false;
+        p_.features &= ~kFeatHuffId23;
     };
     auto clear_dqt = [this]() {
         for (int t = 0; t < 4; t++) p_.qt_present[t] = false;
         std::memset(p_.qt, 0, sizeof(p_.qt));
+        p_.features &= ~kFeatDqt16;
     };
     uint8_t other_sof = 0;   // a frame header this decoder (like the reference: parser.cpp:82, SOF = 0xC0 only) does not handle
     while (!seen_sos) {
@@ -661,8 +671,9 @@ bool StreamParser::ParseLocked(const uint8_t* d, size_t len, bool data_is_file_b
         if (seglen < 2 || next > len) return Fail("bad segment length");
         const uint8_t* s = d + p;
         switch (m) {
-            case 0xC0: if (!ParseSof(s, seglen)) return false; seen_sof0 = true; break;
-            case 0xC1: case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD:
+            case 0xC0: if (!ParseSof(s, seglen, false)) return false; seen_sof0 = true; break;
+            case 0xC1: if (!ParseSof(s, seglen, true)) return false; seen_sof0 = true; break;
+            case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD:
             case 0xCE: case 0xCF:
                 other_sof = m;   // skipped by length as the reference does; the scan header then has no frame to refer to
                 break;

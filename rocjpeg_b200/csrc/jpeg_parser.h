@@ -92,6 +92,11 @@ class PooledBuffer {
     bool pinned_ = false;
 };
 
+// What a stream may use beyond the reference's parser: SOF1 with 8-bit samples (the same decode
+// process as SOF0; libjpeg-turbo writes it as soon as a quantiser step exceeds 255), 16-bit quantiser steps (rejected at
+// src/rocjpeg_parser.cpp:230) and Huffman table ids 2 and 3 (rejected at :274).
+constexpr int32_t kFeatSof1 = 1, kFeatDqt16 = 2, kFeatHuffId23 = 4;
+
 struct HuffSpec {
     uint8_t bits[16];
     uint8_t vals[256];
@@ -117,9 +122,10 @@ struct ParsedJpeg {
     uint32_t scan_offset = 0;                     // first entropy-coded byte inside the caller's buffer (parser.cpp:400-416)
     uint32_t raw_bytes = 0;                       // from there to the end of the caller's buffer (the slice ends at the first
                                                   // FF D9, which the GPU pass finds; HostScan::scan_size on the host)
-    uint8_t qt[4][64] = {};                       // zig-zag order, as in the stream
+    uint16_t qt[4][64] = {};                      // zig-zag order, as in the stream (8- or 16-bit steps)
     bool qt_present[4] = {false, false, false, false};
-    HuffSpec dc[2] = {}, ac[2] = {};
+    HuffSpec dc[kHuffIds] = {}, ac[kHuffIds] = {};
+    int32_t features = 0;                         // kFeat*: what the stream uses beyond what the reference's parser accepts
     // derived geometry (T.81 A.1.1, A.2)
     int32_t hmax = 1, vmax = 1, mcus_x = 0, mcus_y = 0, bpm = 0;
     int32_t blocks_w[3] = {0, 0, 0}, blocks_h[3] = {0, 0, 0};
@@ -168,7 +174,7 @@ class StreamParser {
 
   private:
     bool Fail(const char* why);
-    bool ParseSof(const uint8_t* s, uint32_t seglen);
+    bool ParseSof(const uint8_t* s, uint32_t seglen, bool extended);
     bool ParseDht(const uint8_t* payload, uint32_t n);   // payload = the segment behind its two length bytes
     bool ParseDqt(const uint8_t* payload, uint32_t n);
     bool ParseSos(const uint8_t* s, uint32_t seglen);

@@ -156,9 +156,10 @@ def _seg(marker, payload):
 
 
 def write_jpeg(width, height, coefs, hs, vs, tq, qts_zigzag, dc_tabs=None, ac_tabs=None, td=None, ta=None,
-               restart_interval=0, extra_segments=b"", comp_ids=None, eoi=True):
-    """Assemble a complete baseline JPEG.
-    qts_zigzag: dict id -> 64 u8 in zig-zag (stream) order. dc_tabs/ac_tabs: dict id -> (bits, vals)."""
+               restart_interval=0, extra_segments=b"", comp_ids=None, eoi=True, sof_marker=0xC0):
+    """Assemble a complete sequential Huffman JPEG (SOF0, or SOF1 with sof_marker=0xC1).
+    qts_zigzag: dict id -> 64 quantiser steps in zig-zag (stream) order; a table with a step above 255 is written with
+    16-bit precision. dc_tabs/ac_tabs: dict id (0..3) -> (bits, vals)."""
     ncomp = len(coefs)
     dc_tabs = dc_tabs or {0: STD_DC_LUMA, 1: STD_DC_CHROMA}
     ac_tabs = ac_tabs or {0: STD_AC_LUMA, 1: STD_AC_CHROMA}
@@ -173,11 +174,15 @@ def write_jpeg(width, height, coefs, hs, vs, tq, qts_zigzag, dc_tabs=None, ac_ta
     out = bytearray(b"\xFF\xD8")
     out += extra_segments
     for tid, q in sorted(qts_zigzag.items()):
-        out += _seg(0xDB, bytes([tid]) + bytes(int(x) for x in q))
+        q = [int(x) for x in q]
+        if max(q) > 255:
+            out += _seg(0xDB, bytes([0x10 | tid]) + b"".join(struct.pack(">H", x) for x in q))
+        else:
+            out += _seg(0xDB, bytes([tid]) + bytes(q))
     sof = struct.pack(">BHHB", 8, height, width, ncomp)
     for c in range(ncomp):
         sof += bytes([comp_ids[c], (hs[c] << 4) | vs[c], tq[c]])
-    out += _seg(0xC0, sof)
+    out += _seg(sof_marker, sof)
     used_dc = sorted(set(td))
     used_ac = sorted(set(ta))
     dht = b""

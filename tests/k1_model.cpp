@@ -78,7 +78,7 @@ extern "C" int k1_model_decode(const uint8_t* data, size_t len, int S, int T, in
         for (int b = 0; b < H * V; b++, k++) {
             mcu_comp[k] = uint8_t(c);
             mcu_dc[k] = uint8_t(p.td[c]);
-            mcu_ac[k] = uint8_t(2 + p.ta[c]);
+            mcu_ac[k] = uint8_t(kHuffIds + p.ta[c]);
         }
     }
     const TableSel sel = MakeTableSel(mcu_dc, mcu_ac, bpm);

@@ -216,6 +216,29 @@ def test_crop_that_starts_at_the_first_column_of_a_restart_interval(dec, orc, cs
             gu.assert_same(got, want, f"{css} dri={dri} crop={crop} {fmt}")
 
 
+def test_widened_streams_decode_exactly(dec, orc):
+    """16-bit quantiser tables, Huffman table ids 2-3, SOF1 frame headers with 8-bit samples (what libjpeg-turbo writes for
+    coarse quantisers): rejected by the reference's parser, decoded here - coefficients, planes and every output format
+    against the oracle (itself pinned against libjpeg-turbo on the same streams), alone and mixed into one batch."""
+    from test_oracle_pinning import widened_streams
+
+    streams_ = widened_streams(orc)
+    for name, data in streams_.items():
+        rc, info = orc.parse(data)
+        for fmt in FORMATS:
+            for crop in ((0, 0, 0, 0), (8, 8, 72, 56)):
+                st, got, want = gu.decode_one(dec, orc, data, fmt, crop, 5, 1)
+                assert st == api.SUCCESS, (name, fmt, st)
+                gu.assert_same(got, want, f"{name} {fmt} {crop}")
+        n = sum(info.blocks_w[c] * info.blocks_h[c] * 64 for c in range(info.ncomp))
+        st, got, want = gu.decode_one(dec, orc, data, "y")
+        assert np.array_equal(dec.coefficients(0, n), np.concatenate([c.reshape(-1) for c in orc.coefficients(data, info)])), name
+        assert np.array_equal(dec.planes(0, n), np.concatenate([p.reshape(-1) for p in orc.planes(data, info)])), name
+    datas = list(streams_.values()) + [load("synth_420_500x375_dri7"), load("custom_huffman_420_dri1")]
+    _check_batch(dec, orc, datas, "rgb_planar")
+    _check_batch(dec, orc, datas, "yuv_planar")
+
+
 @pytest.mark.parametrize("dri", [0, 1])
 def test_411_pictures_every_format_and_crop(dec, orc, dri):
     """4:1:1 (one chroma sample per four pixels; ROCJPEG_CSS_411 exists in the API but the reference refuses to decode

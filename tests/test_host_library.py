@@ -183,9 +183,15 @@ def test_parser_header_fuzz_matches_oracle_and_reference(lib, orc):
             # the reference's parser has no bounds checks (a segment length that runs past the buffer is read out
             # of bounds, src/rocjpeg_parser.cpp:75-108): its verdict is only defined when every segment fits
             out_of_bounds = st != api.SUCCESS and any(w in s.last_error() for w in ("truncated", "segment length", "too short"))
+            # what this decoder accepts beyond the reference's parser (SOF1 with 8-bit samples, 16-bit quantiser steps, Huffman
+            # table ids 2-3: SURVEY.md section 8 f4) is flagged by the parser; the reference's verdict on such a stream is "reject"
+            widened = st == api.SUCCESS and s.info().features != 0
             if ref is not None and not out_of_bounds:
                 r = ref.parse(data)
-                assert (r.ok == 1) == (rc == 0), (name, kind, s.last_error(), data[:hdr_end].hex())
+                if widened:
+                    assert r.ok == 0 and o.features == s.info().features, (name, kind, data[:hdr_end].hex())
+                else:
+                    assert (r.ok == 1) == (rc == 0), (name, kind, s.last_error(), data[:hdr_end].hex())
             checked += 1
             if st == api.SUCCESS:
                 accepted += 1
@@ -365,6 +371,40 @@ def k1_model():
     L.k0_model_destuff.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
     return L
+
+
+def test_widened_streams_parse_and_decode_in_the_k1_model(lib, k1_model, orc):
+    """SOF1 (8-bit samples), 16-bit quantiser steps, Huffman table ids 2-3: the library's parser agrees with the oracle's
+    (fields, tables, feature flags) and its decoder-form tables decode them (K1 schedule model) like the oracle."""
+    from test_oracle_pinning import widened_streams
+
+    for name, data in widened_streams(orc).items():
+        s = api.JpegStream()
+        assert s.parse(data) == api.SUCCESS, name
+        i = s.info()
+        rc, o = orc.parse(data)
+        assert rc == 0 and i.features == o.features and i.decode_status == api.SUCCESS, name
+        for c in range(o.ncomp):
+            q = s.quant_table(o.tq[c])
+            assert np.array_equal(q[orc.zigzag], np.frombuffer(bytes(o.qt16[o.tq[c]]), dtype=np.uint16)), name
+        for t in range(4):
+            if o.dc_present[t]:
+                bits, vals = s.huffman_table(0, t)
+                assert bits == bytes(o.dc_bits[t]) and vals == bytes(o.dc_vals[t])[:len(vals)]
+            if o.ac_present[t]:
+                bits, vals = s.huffman_table(1, t)
+                assert bits == bytes(o.ac_bits[t]) and vals == bytes(o.ac_vals[t])[:len(vals)]
+        n = sum(o.blocks_w[c] * o.blocks_h[c] * 64 for c in range(o.ncomp))
+        out = np.zeros(n, np.int16)
+        for S, T in ((32, 16), (128, 64)):
+            assert k1_model.k1_model_decode(data, len(data), S, T, out.ctypes.data, out.size, None) == 0, name
+            assert np.array_equal(out, np.concatenate([c.reshape(-1) for c in orc.coefficients(data, o)])), name
+    # SOF1 with 12-bit samples stays rejected, and says why
+    data = bytearray(widened_streams(orc)["huff_ids_2_3_sof1_dri"])
+    k = bytes(data).index(b"\xFF\xC1")
+    data[k + 4] = 12
+    s = api.JpegStream()
+    assert s.parse(bytes(data)) == api.BAD_JPEG and "12-bit" in s.last_error()
 
 
 # ---------------------------------------------------------------- K0 (GPU destuffing) schedule on the CPU

@@ -143,6 +143,9 @@ def test_oracle_parser_accept_reject_matches_reference(orc):
     for name, data in _mutations(base).items():
         rc, o = orc.parse(data)
         r = rp.parse(data)
+        if rc == 0 and o.features:   # accepted here on purpose, rejected by the reference: 16-bit DQT, Huffman ids 2-3, SOF1
+            assert not r.ok and name in ("dqt_16bit", "dht_id2"), name
+            continue
         assert (rc == 0) == bool(r.ok), f"{name}: oracle rc={rc}, reference ok={r.ok}"
         if r.ok:
             assert (r.width, r.height, r.css) == (o.width, o.height, o.css), name
@@ -210,6 +213,56 @@ def test_oracle_411_pinned(orc, ljt):
                 ref = reference_output(rk, info444, fake, fmt, (0, 0, 0, 0))
                 for d, r, (rows_, rb) in zip(dst, ref, oracle.output_shapes(info, fmt)):
                     assert np.array_equal(d[:rows_, :rb], r), (w, h, fmt)
+
+
+def widened_streams(orc):
+    """Streams that use what this decoder accepts beyond the reference's parser: name -> bytes."""
+    import io
+
+    from PIL import Image
+
+    import jpeg_writer as jw
+
+    out = {}
+    img = datagen.synth_image(120, 88, seed=9)
+    # libjpeg-turbo itself: quantiser steps above 255 -> 16-bit DQT and an SOF1 frame header
+    for name, ss in (("pil_dqt16_sof1_444", 0), ("pil_dqt16_sof1_420", 2)):
+        bio = io.BytesIO()
+        Image.fromarray(img).save(bio, format="JPEG", subsampling=ss, qtables=[[min(16 + 40 * k, 700) for k in range(64)], [min(20 + 55 * k, 900) for k in range(64)]])
+        out[name] = bio.getvalue()
+    # hand-assembled: Huffman table ids 2 and 3 (all four DC and AC tables in use), with and without the SOF1 label and DRI
+    base = datagen.make_jpeg(96, 72, "420", seed=12)
+    rc, info = orc.parse(base)
+    coefs = orc.coefficients(base, info)
+    qts = {t: bytes(info.qt[t]) for t in range(4) if info.qt_present[t]}
+    dc = {0: jw.STD_DC_LUMA, 1: jw.STD_DC_CHROMA, 2: jw.STD_DC_CHROMA, 3: jw.STD_DC_LUMA}
+    ac = {0: jw.STD_AC_LUMA, 1: jw.STD_AC_CHROMA, 2: jw.STD_AC_CHROMA, 3: jw.STD_AC_LUMA}
+    out["huff_ids_2_3"] = jw.write_jpeg(96, 72, coefs, [2, 1, 1], [2, 1, 1], [info.tq[c] for c in range(3)], qts, dc, ac, [3, 2, 1], [0, 3, 2])
+    out["huff_ids_2_3_sof1_dri"] = jw.write_jpeg(96, 72, coefs, [2, 1, 1], [2, 1, 1], [info.tq[c] for c in range(3)], qts, dc, ac, [2, 3, 2], [2, 1, 3],
+                                               restart_interval=2, sof_marker=0xC1)
+    q16 = {0: [min(3 + 9 * k, 400) for k in range(64)], 1: [min(5 + 11 * k, 600) for k in range(64)]}
+    small = [np.clip(c.astype(np.int32) // 6, -40, 40).astype(np.int16) for c in coefs]   # keeps coef * step inside the islow domain
+    out["dqt16_sof0_label"] = jw.write_jpeg(96, 72, small, [2, 1, 1], [2, 1, 1], [0, 1, 1], q16)
+    return out
+
+
+def test_oracle_widened_streams_pinned(orc, ljt):
+    """16-bit quantiser tables, Huffman table ids 2-3 and SOF1 frame headers (8-bit samples): accepted here, rejected by the
+    reference's parser. The oracle's coefficients and planes are pinned against libjpeg-turbo, which decodes all of them."""
+    feats = {"pil_dqt16_sof1_444": 3, "pil_dqt16_sof1_420": 3, "huff_ids_2_3": 4, "huff_ids_2_3_sof1_dri": 5, "dqt16_sof0_label": 2}
+    for name, data in widened_streams(orc).items():
+        rc, info = orc.parse(data)
+        assert rc == 0 and orc.supported(info) == 0, name
+        assert info.features == feats[name], (name, info.features)
+        if oracle.ref_available():
+            assert not oracle.RefParser().parse(data).ok, name   # the reference refuses every one of them
+        coefs, lc = orc.coefficients(data, info), ljt.coefficients(data, info)
+        planes, lp = orc.planes(data, info), ljt.raw_planes(data, info)
+        li = ljt.info(data)
+        for c in range(info.ncomp):
+            assert np.array_equal(coefs[c], lc[c]), f"{name}: component {c} coefficients"
+            hh, ww = li.hib[c] * 8, li.wib[c] * 8
+            assert np.array_equal(planes[c][:hh, :ww], lp[c][:hh, :ww]), f"{name}: component {c} plane"
 
 
 def test_rgb_vs_libjpeg_default_decode_is_reported_not_gated(orc, ljt):
