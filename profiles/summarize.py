@@ -69,8 +69,9 @@ if rep and len(sys.argv) > 4:
     import json
     import os
 
-    stage_of = {"k1_sync": "huffman_sync", "k1_scan": "huffman_write", "k1_write": "huffman_write", "dc_sums": "dc", "dc_scan": "dc",
-                "dc_apply": "dc", "dc_image": "dc", "k2_idct": "idct", "k3_output": "output"}
+    stage_of = {"k0_reduce": "destuff", "k0_scan": "destuff", "k0_apply": "destuff", "k1_sync": "huffman_sync", "k1_scan": "huffman_write",
+                "k1_write": "huffman_write", "dc_sums": "dc", "dc_scan": "dc", "dc_apply": "dc", "dc_image": "dc", "k2_idct": "idct",
+                "k23_fused": "output", "k3_output": "output"}
     ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     per_stage, seen = {}, {}
@@ -88,6 +89,16 @@ if rep and len(sys.argv) > 4:
     path = "profiles/traffic.json"
     t = json.load(open(path)) if os.path.exists(path) else {}
     t[sys.argv[4]] = {k: int(v) for k, v in per_stage.items()}
+    # issue-slot utilisation of the entropy stage (what bench.py reports as roofline_k1.issue_utilisation)
+    ii = h.index("smsp__issue_active.avg.pct_of_peak_sustained_active") if "smsp__issue_active.avg.pct_of_peak_sustained_active" in h else None
+    if ii is not None:
+        iss = {}
+        for r in d:
+            name = r[ki].split("(")[0].split("<")[0].replace("void ", "").split("::")[-1]
+            if name in ("k1_sync", "k1_write") and name not in iss:
+                iss[name] = round(float(r[ii].replace(",", "")) / 100.0, 3)
+        if iss:
+            t[sys.argv[4]]["k1_issue"] = iss
     t.setdefault("_note", "dram__bytes_read.sum + dram__bytes_write.sum per stage of ONE step, from the ncu --set full capture named by "
                           "the tag in profiles/<tag>_kernels.md (cold cache, one pipeline lane)")
     json.dump(t, open(path, "w"), indent=1, sort_keys=True)

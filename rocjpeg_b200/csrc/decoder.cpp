@@ -795,8 +795,19 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
         return want ? cudaEventRecord(ev_[i], stream_) : cudaSuccess;
     };
     stats_.kernel_launches = 0;
+    // whatever happens below, the lanes queued behind this one on the upload stream get their turn (the guard passes it on
+    // when this function leaves before Upload() did), and a failure leaves both counter sets clean for the next call
+    struct ExitGuard {
+        Lane* lane;
+        TurnGuard turn;
+        bool ok = false;
+        ~ExitGuard() {
+            if (!ok && lane->d_counters_.capacity() >= 512) cudaMemsetAsync(lane->d_counters_.as<uint8_t>(), 0, 512, lane->stream_);
+        }
+    } exit_guard{this, TurnGuard(include_upload ? turn : UploadTurn())};
     RJB_CUDA(mark(0));
     if (include_upload) {
+        exit_guard.turn.passed = true;   // Upload() owns the turn from here on (its own guard passes it on)
         int st = Upload(up, turn);
         if (st != kSuccess) return st;
     }
@@ -839,6 +850,7 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data() + 256, k0_.status, h_images_.size() * sizeof(ScanStatus), cudaMemcpyDeviceToHost, stream_));
     stats_.d2h_bytes = 256 + h_images_.size() * sizeof(ScanStatus);
+    exit_guard.ok = true;
     return kSuccess;
 }
 
@@ -991,8 +1003,7 @@ int Decoder::BuildAll(const StreamParser* const* streams, int n, const DecodePar
     }
     for (int l = 0; l < active_lanes_; l++) {
         if (status[l] != kSuccess) {
-            for (int k = 0; k < active_lanes_; k++)
-                if (k != l && status[k] == kSuccess) lanes_[k].Sync();   // do not leave work in flight behind an error
+            for (int k = 0; k < active_lanes_; k++) lanes_[k].Sync();   // do not leave work in flight behind an error (the failed lane's included)
             return Fail(status[l], lanes_[l].last_error());
         }
     }
