@@ -145,6 +145,10 @@ class Lane {
     cudaEvent_t last_event() const { return ev_[kStageCount]; }
     int num_images() const { return int(h_images_.size()); }
     uint32_t truncated_images() const { return truncated_images_; }
+    // ROCJPEG_B200_TRACE=2: one line per lane, device times relative to `origin` (the first lane's upload-begin event)
+    void PrintTimeline(int index, cudaEvent_t origin, double host_origin_ms) const;
+    cudaEvent_t trace_origin() const { return ev_trace_[0]; }
+    void set_host_mark(int i, double ms) { host_ms_[i] = ms; }
 
   private:
     struct Layout;   // byte layout of the descriptor block
@@ -155,6 +159,8 @@ class Lane {
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev_[kStageCount + 1] = {};
     cudaEvent_t ev_uploaded_ = nullptr;
+    cudaEvent_t ev_trace_[3] = {};   // ROCJPEG_B200_TRACE=2: upload begins / upload done / last kernel done, on the device's clock
+    double host_ms_[3] = {};         // ... and when the host began describing the lane, began enqueueing, was done with it
     int sm_count_ = 0;
 
     // host-side batch description
@@ -163,6 +169,12 @@ class Lane {
     std::vector<uint32_t> h_img_cta0_, h_img_dctile0_, h_k2_tile0_, h_k3_tile0_, h_k0_tile0_, h_needed_segments_;
     uint32_t truncated_images_ = 0;
     std::vector<GatherItem> h_gather_;
+    struct CopyRun {
+        const uint8_t* src;   // host address (page-locked), 16-byte aligned
+        uint64_t dst_off;     // offset in the raw arena
+        size_t nbytes;
+    };
+    std::vector<CopyRun> h_runs_;          // upload plan: neighbouring streams of one page-locked allocation move with one copy
     std::vector<FusedImage> h_fused_;      // pictures served by the fused IDCT + output kernel
     std::vector<uint16_t> h_tile_img_;     // per strip of that kernel: index into h_fused_
     std::vector<const HuffLutSet*> h_lut_ptrs_;

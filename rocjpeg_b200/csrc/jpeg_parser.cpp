@@ -488,14 +488,54 @@ const HostScan& StreamParser::host_scan() const {
 }
 
 namespace {
-// Is `p` page-locked host memory the device can read in place? Returns its device alias or nullptr.
-const uint8_t* DeviceAliasOf(const uint8_t* p) {
+// cuPointerGetAttributes of the driver, reached through the runtime (no link dependency on libcuda): one call
+// answers "page-locked? device alias? which allocation?" and does not fail on ordinary host pointers.
+typedef int (*PointerAttributesFn)(unsigned int, int*, void**, unsigned long long);
+PointerAttributesFn DriverPointerAttributes() {
+    static const PointerAttributesFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttributes", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<PointerAttributesFn>(f);
+    }();
+    return fn;
+}
+
+// Is `p` page-locked host memory the device can read in place? Returns its device alias or nullptr, and the
+// allocation it belongs to.
+const uint8_t* DeviceAliasOf(const uint8_t* p, uintptr_t* range_base, size_t* range_size) {
     static std::atomic<int> no_driver{0};
     static const bool enabled = [] {
         const char* v = std::getenv("ROCJPEG_B200_ZERO_COPY");
         return !(v && *v == '0');
     }();
+    *range_base = 0;
+    *range_size = 0;
     if (!enabled || no_driver.load(std::memory_order_relaxed)) return nullptr;
+    if (PointerAttributesFn fn = DriverPointerAttributes()) {
+        // CU_POINTER_ATTRIBUTE_MEMORY_TYPE = 2, DEVICE_POINTER = 3, RANGE_START_ADDR = 11, RANGE_SIZE = 12, IS_MANAGED = 8
+        int which[5] = {2, 3, 11, 12, 8};
+        unsigned int mem_type = 0;
+        unsigned long long dev_ptr = 0, start = 0;
+        size_t size = 0;
+        unsigned int managed = 0;
+        void* out[5] = {&mem_type, &dev_ptr, &start, &size, &managed};
+        if (fn(5, which, out, static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(p))) == 0) {
+            if (mem_type == 1u /* CU_MEMORYTYPE_HOST */ && dev_ptr != 0 && !managed) {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+                if (start != 0 && size != 0 && a >= uintptr_t(start) && a < uintptr_t(start) + size) {
+                    *range_base = uintptr_t(start);
+                    *range_size = size;
+                }
+                return reinterpret_cast<const uint8_t*>(uintptr_t(dev_ptr));
+            }
+            if (mem_type == 0u) return nullptr;   // an ordinary host pointer
+        }
+        // anything else (driver not initialised yet, managed memory ...): ask the runtime, which initialises itself
+    }
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, p);
     if (e != cudaSuccess) {
@@ -513,7 +553,7 @@ const uint8_t* DeviceAliasOf(const uint8_t* p) {
 void StreamParser::AdoptSource(const uint8_t* scan, size_t nbytes) {
     raw_ = RawScan();
     raw_.nbytes = uint32_t(nbytes);
-    if (const uint8_t* dev = DeviceAliasOf(scan)) {
+    if (const uint8_t* dev = DeviceAliasOf(scan, &raw_.range_base, &raw_.range_size)) {
         raw_.host = scan;
         raw_.dev = dev;
         raw_.zero_copy = true;
@@ -525,6 +565,7 @@ void StreamParser::AdoptSource(const uint8_t* scan, size_t nbytes) {
     std::memset(st + nbytes, 0xFF, 64 - (nbytes & 15));   // what the upload rounds up to
     raw_.host = st;
     raw_.dev = staging_.pinned() ? st : nullptr;
+    if (raw_.dev) (void)DeviceAliasOf(st, &raw_.range_base, &raw_.range_size);   // the pool's slab
 }
 
 void StreamParser::BuildDecodeTables() {
@@ -724,6 +765,7 @@ bool StreamParser::ParseLocked(const uint8_t* d, size_t len, bool data_is_file_b
         raw_.nbytes = uint32_t(len - p);
         raw_.host = d + p;
         raw_.dev = file_.pinned() ? d + p : nullptr;
+        if (raw_.dev) (void)DeviceAliasOf(d + p, &raw_.range_base, &raw_.range_size);
     } else {
         AdoptSource(d + p, len - p);
     }

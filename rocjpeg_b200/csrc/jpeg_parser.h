@@ -143,6 +143,10 @@ struct RawScan {
     const uint8_t* dev = nullptr;    // the same byte as the device sees it (page-locked memory); nullptr: pageable, copy with cudaMemcpy
     uint32_t nbytes = 0;
     bool zero_copy = false;          // `host` is the caller's own page-locked buffer
+    // the page-locked allocation `host` lies in (0, 0: unknown): streams of one allocation that lie close together
+    // are uploaded with one copy (decoder.cpp: Lane::Build)
+    uintptr_t range_base = 0;
+    size_t range_size = 0;
 };
 
 // Host restatement of the destuffing pass (tests, taps, schedule model - never the decode path).

@@ -26,13 +26,27 @@ constexpr int kMaxBlocks = 128;       // blocks of one strip: 32 MCUs x 4 (4:4:0
 constexpr int kLumaBytes = 16 * kStripW, kChromaBytes = 8 * kStripW;   // plane capacities: 16 rows of luma; 8 x 256 or 16 x 128 of chroma
 static_assert(kStripW == kTileW, "the row routines assume 8 samples per lane over the strip");
 
-__device__ __forceinline__ uint32_t UpperIndexF(const uint32_t* a, uint32_t n, uint32_t v) {
-    uint32_t lo = 0, hi = n;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(a + mid) <= v) lo = mid; else hi = mid;
-    }
-    return lo;
+// shared memory through 32-bit window addresses (computed once: the generic-pointer forms made the compiler rebuild
+// the window base in every iteration of the issue-bound IDCT loop)
+__device__ __forceinline__ uint32_t SharedU32(const void* p) {
+    uint32_t a = uint32_t(__cvta_generic_to_shared(p));
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));   // opaque: keeps the address in a register instead of re-deriving the window base
+    return a;
+}
+__device__ __forceinline__ uint32_t Lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 Lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void Sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void Sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void Sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __global__ void __launch_bounds__(kFThreads, 6) k23_fused(K23Args a) {
@@ -42,10 +56,8 @@ __global__ void __launch_bounds__(kFThreads, 6) k23_fused(K23Args a) {
     __shared__ __align__(16) uint8_t s_pl[kLumaBytes + 2 * kChromaBytes];
     __shared__ __align__(16) uint8_t s_buf[kFThreads / 32][kRowBuf];
     __shared__ uint32_t s_tab[3][64];            // per component and zig-zag code: workspace byte offset | quantiser step << 16
-    __shared__ uint32_t s_first[kMaxBlocks];
-    __shared__ uint16_t s_count[kMaxBlocks], s_off[kMaxBlocks];
-    __shared__ int16_t s_dc[kMaxBlocks];
-    __shared__ uint8_t s_comp[kMaxBlocks];
+    // per block of the strip: {first entry, entries | component << 16 | valid << 24, dequantised DC, plane offset | pitch << 16}
+    __shared__ __align__(16) uint4 s_meta[kMaxBlocks];
     __shared__ K3Job s_job;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // every thread reads the picture's record itself (uniform loads, one cache line): no thread-0 prologue
@@ -83,77 +95,76 @@ __global__ void __launch_bounds__(kFThreads, 6) k23_fused(K23Args a) {
     for (int idx = tid; idx < ncomp * 64; idx += kFThreads) {
         const int c = idx >> 6, code = idx & 63;   // entries carry position + 1 (huff_core.cuh)
         const int nat = kZigzag[(code + 63) & 63];
-        s_tab[c][code] = uint32_t(((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(a.qtables + size_t(fi.qidx[c]) * 64 + nat)) << 16);
+        // (code 1 = position 0: DC-difference and pad entries; the block's integrated DC is stored with the zero fill, so these
+        // are parked in a padding word of the workspace's first row)
+        s_tab[c][code] = uint32_t(code == 1 ? 8 * 4 : ((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(a.qtables + size_t(fi.qidx[c]) * 64 + nat)) << 16);
     }
     // per block of the strip: its record (where its entries lie, integrated DC) and where its samples go
-    if (tid < nblocks) {
-        int g = tid, c = 0, nbw = nbw0;
-        if (g >= cnt0) { g -= cnt0; c = 1; nbw = nbw1; if (g >= cnt1) { g -= cnt1; c = 2; nbw = nbw2; } }
-        const int v = g / nbw, bx = g - v * nbw;
-        const int H = fi.H[c];
-        const size_t blk = size_t(mrow * fi.mcus_x + m0 + (bx >> fi.hshift[c])) * size_t(fi.bpm) + size_t(fi.first_blk[c] + v * H + (bx & (H - 1)));
-        const uint2 r = __ldg(reinterpret_cast<const uint2*>(rec + blk));
-        uint32_t e0 = blk ? __ldg(&rec[blk - 1].end) : 0u, e1 = r.x;
-        if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 0xFFFFu || e1 > fi.ent_cap) e1 = e0 = 0;   // never decoded (as k2_idct.cu)
-        s_first[tid] = e0;
-        s_count[tid] = uint16_t(e1 - e0);
-        s_dc[tid] = int16_t(r.y & 0xFFFFu);
-        s_comp[tid] = uint8_t(c);
-        s_off[tid] = uint16_t(fi.base[c] + uint32_t(v * 8) * fi.pitch[c] + uint32_t(bx * 8));
+    if (tid < kMaxBlocks) {
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < nblocks) {
+            int g = tid, c = 0, nbw = nbw0;
+            if (g >= cnt0) { g -= cnt0; c = 1; nbw = nbw1; if (g >= cnt1) { g -= cnt1; c = 2; nbw = nbw2; } }
+            const int v = g / nbw, bx = g - v * nbw;
+            const int H = fi.H[c];
+            const size_t blk = size_t(mrow * fi.mcus_x + m0 + (bx >> fi.hshift[c])) * size_t(fi.bpm) + size_t(fi.first_blk[c] + v * H + (bx & (H - 1)));
+            const uint2 r = __ldg(reinterpret_cast<const uint2*>(rec + blk));
+            uint32_t e0 = blk ? __ldg(&rec[blk - 1].end) : 0u, e1 = r.x;
+            if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 0xFFFFu || e1 > fi.ent_cap) e1 = e0 = 0;   // never decoded (as k2_idct.cu)
+            m.x = e0;
+            m.y = (e1 - e0) | (uint32_t(c) << 16) | (1u << 24);
+            m.z = uint32_t(int(int16_t(r.y & 0xFFFFu)) * int(__ldg(a.qtables + size_t(fi.qidx[c]) * 64)));   // integrated DC, dequantised
+            m.w = (fi.base[c] + uint32_t(v * 8) * fi.pitch[c] + uint32_t(bx * 8)) | (fi.pitch[c] << 16);
+        }
+        s_meta[tid] = m;
     }
     __syncthreads();
-    // ---- IDCT: 32 blocks at a time, 8 threads per block (k2_idct.cu's inner loop, samples to shared memory) ----
+    // ---- IDCT: 32 blocks at a time, 8 threads per block (k2_idct.cu's arithmetic, samples to shared memory). The loop is
+    // issue bound: everything it touches is addressed through 32-bit shared-window addresses computed once, a block's
+    // description is one 128-bit load, and the trip count is the same for every warp.
     const int b = tid >> 3, jj = tid & 7;
-    int* my = ws + b * kBS;
-    const uint32_t my_sa = uint32_t(__cvta_generic_to_shared(my));
+    const uint32_t my_sa = SharedU32(ws) + uint32_t(b * kBS * 4);
+    const uint32_t row_sa = my_sa + uint32_t(jj * kRS * 4), col_sa = my_sa + uint32_t(jj * 4);
+    const uint32_t tab_sa0 = SharedU32(&s_tab[0][0]), pl_sa = SharedU32(s_pl);
+    uint32_t meta_sa = SharedU32(s_meta) + uint32_t(b * 16);
+    const uint32_t* const ent_j = entries + jj;
+    const uint32_t meta_end = SharedU32(s_meta) + uint32_t(nblocks * 16);
 #pragma unroll 1
-    for (int g0 = 0; g0 < nblocks; g0 += 32) {
-        const int g = g0 + b;
-        const bool valid = g < nblocks;
-        const int c = valid ? s_comp[g] : 0;
-        const uint32_t n = valid ? s_count[g] : 0u;
-        const uint32_t* ep = entries + (valid ? s_first[g] : 0u) + uint32_t(jj);
-        if (valid) {
-            int4* row = reinterpret_cast<int4*>(my + jj * kRS);
-            row[0] = make_int4(0, 0, 0, 0);
-            row[1] = make_int4(0, 0, 0, 0);
-        }
+    for (; meta_sa < meta_end + uint32_t(b * 16); meta_sa += 32 * 16) {   // (same trip count for the 32 block slots: slot b's g runs b, b + 32, ...)
+        const uint4 m = Lds128(meta_sa);
+        const uint32_t n = m.y & 0xFFFFu;
+        const uint32_t* ep = ent_j + m.x;
+        // four loads in flight per thread (32 entries per block) before the first is used
+        const uint32_t k = uint32_t(jj);
+        uint32_t e[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) e[u] = (k + 8u * u < n) ? __ldg(ep + 8 * u) : 0u;
+        Sts128(row_sa, make_uint4(jj == 0 ? m.z : 0u, 0u, 0u, 0u));   // zero fill; the integrated DC goes in with it
+        Sts128(row_sa + 16, make_uint4(0u, 0u, 0u, 0u));
         __syncwarp();
-        const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(&s_tab[c][0]));
+        const uint32_t tab_sa = tab_sa0 + ((m.y >> 8) & 0x300u);
         auto put = [&](uint32_t en) {
-            uint32_t t;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(tab_sa + ((en >> 14) & 0xFCu)));
-            const int v = int(int16_t(en & 0xFFFFu)) * int(t >> 16);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_sa + (t & 0xFFFFu)), "r"(v) : "memory");
+            const uint32_t t = Lds32(tab_sa + ((en >> 14) & 0xFCu));
+            Sts32(my_sa + (t & 0xFFFFu), uint32_t(int(int16_t(en & 0xFFFFu)) * int(t >> 16)));
         };
-        {
-            const uint32_t k = uint32_t(jj);
-            uint32_t e[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) e[u] = (k + 8u * u < n) ? __ldg(ep + 8 * u) : 0u;
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (k + 8u * u < n) put(e[u]);
-        }
-        for (uint32_t k = uint32_t(jj) + 32u; k < n; k += 8) put(__ldg(ep + (k - uint32_t(jj))));
-        __syncwarp();
-        if (valid && jj == 0) my[0] = int(s_dc[g]) * int(s_tab[c][1] >> 16);   // integrated DC replaces any DC-difference entry
+        for (int u = 0; u < 4; u++)
+            if (k + 8u * u < n) put(e[u]);
+        for (uint32_t kk = k + 32u; kk < n; kk += 8) put(__ldg(ep + (kk - k)));
         __syncwarp();
         int in[8], out[8];
-        if (valid) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) in[r] = my[r * kRS + jj];   // column jj
-            Islow8<11>(in, out, 1 << 10);
+        for (int r = 0; r < 8; r++) in[r] = int(Lds32(col_sa + uint32_t(r * kRS * 4)));   // column jj
+        Islow8<11>(in, out, 1 << 10);
 #pragma unroll
-            for (int r = 0; r < 8; r++) my[r * kRS + jj] = out[r];
-        }
+        for (int r = 0; r < 8; r++) Sts32(col_sa + uint32_t(r * kRS * 4), uint32_t(out[r]));
         __syncwarp();
-        if (valid) {
-            const int4 lo = *reinterpret_cast<const int4*>(my + jj * kRS), hi = *reinterpret_cast<const int4*>(my + jj * kRS + 4);   // row jj
-            in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
+        {
+            const uint4 lo = Lds128(row_sa), hi = Lds128(row_sa + 16);   // row jj
+            in[0] = int(lo.x); in[1] = int(lo.y); in[2] = int(lo.z); in[3] = int(lo.w);
+            in[4] = int(hi.x); in[5] = int(hi.y); in[6] = int(hi.z); in[7] = int(hi.w);
             Islow8<18>(in, out, (1 << 17) + (128 << 18));
-            *reinterpret_cast<uint2*>(s_pl + s_off[g] + uint32_t(jj) * fi.pitch[c]) =
-                make_uint2(PackSat4(out[0], out[1], out[2], out[3]), PackSat4(out[4], out[5], out[6], out[7]));
+            if (m.y >> 24) Sts64(pl_sa + (m.w & 0xFFFFu) + uint32_t(jj) * (m.w >> 16), PackSat4(out[0], out[1], out[2], out[3]), PackSat4(out[4], out[5], out[6], out[7]));
         }
         __syncwarp();
     }
