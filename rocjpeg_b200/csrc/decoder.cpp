@@ -165,7 +165,7 @@ int Lane::Fail(int status, const std::string& why) {
     return status;
 }
 
-int Lane::Create(int /*device_id*/, int sm_count) {
+int Lane::Create(int /*device_id*/, int sm_count, bool prealloc) {
     if (created_) return kSuccess;
     sm_count_ = sm_count;
     RJB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
@@ -178,10 +178,10 @@ int Lane::Create(int /*device_id*/, int sm_count) {
     // staging and a starting size for the device arenas, ROCJPEG_B200_PREALLOC_MB per handle (default
     // 384, two thirds of it arena, one third planes, split over the lanes; 0 = allocate on demand)
     if (!h_desc_.Reserve(1u << 20) || !h_counters_.Reserve(256 + 4096 * sizeof(ScanStatus))) return Fail(kOutOfMemory, "page-locked staging");
-    const size_t per_lane = size_t(std::max(0, EnvInt("ROCJPEG_B200_PREALLOC_MB", 384))) * (1u << 20) / kMaxLanes;
+    const size_t per_lane = size_t(std::max(0, EnvInt("ROCJPEG_B200_PREALLOC_MB", 384))) * (1u << 20) / 4;   // (the lanes a call uses by default)
     RJB_CUDA(d_counters_.Reserve(512));
     RJB_CUDA(cudaMemsetAsync(d_counters_.as<uint8_t>(), 0, 512, stream_));
-    if (per_lane) {
+    if (per_lane && prealloc) {
         RJB_CUDA(d_slab_.Reserve(per_lane * 2 / 3));
         RJB_CUDA(d_planes_.Reserve(per_lane / 3));
     }
@@ -240,7 +240,7 @@ int Decoder::Initialize() {
     RJB_CUDA(PreloadK2());
     RJB_CUDA(PreloadK3());
     RJB_CUDA(PreloadK23());
-    for (int l = 1; l < kMaxLanes; l++) {
+    for (int l = 1; l < 4; l++) {   // the lanes a call uses by default; the others (ROCJPEG_B200_LANES > 4) are created on demand
         st = lanes_[l].Create(device_id_, sm_count_);
         if (st != kSuccess) return Fail(st, lanes_[l].last_error());
     }
@@ -365,6 +365,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     h_k3_tile0_.assign(size_t(n) + 1, 0);
     h_fused_.clear();
     h_tile_img_.clear();
+    h_tile_img_w_.clear();
     h_gather_.assign(size_t(n), GatherItem{});
     h_lut_ptrs_.clear();
     h_lut_specs_.clear();
@@ -405,7 +406,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     needs_planes_ = false;
     const bool direct_ok = EnvInt("ROCJPEG_B200_NO_DIRECT", 0) == 0;
     const bool fuse_ok = EnvInt("ROCJPEG_B200_NO_FUSE", 0) == 0;
-    uint32_t k23tile = 0;
+    uint32_t k23tile = 0, k23tile_w = 0;
+    const bool warp_ok = EnvInt("ROCJPEG_B200_NO_WARP_FUSE", 0) == 0;
     k2_needed_ = false;
     uint64_t scan_off = 0, raw_off = 0, blk = 0, plane_off = 0, ent = 0, sub = 0;
     uint32_t dctile = 0, k2tile = 0, k3tile = 0, max_pairs = 1, max_sub = 0, k0tile = 0, nseg_total = 0;
@@ -628,7 +630,11 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             fi.vmax = vmax;
             fi.mpt = kK3TileW / (8 * hmax);
             fi.tiles_x = uint32_t((p.width + kK3TileW - 1) / kK3TileW);
-            fi.tile0 = k23tile;
+            // destination rows all 4-byte aligned (every row takes the register path): the warp-per-column kernel
+            bool aligned = (od.dst_pitch[0] & 3u) == 0;
+            for (int c = 0; c < (od.fmt == FMT_RGB ? 1 : 3); c++) aligned = aligned && (reinterpret_cast<uintptr_t>(od.dst[c]) & 3u) == 0;
+            aligned = aligned && warp_ok && (fi.mpt / 8) * p.bpm <= 16;   // a warp's MCUs hold at most 16 blocks (k23_fused.cu)
+            fi.tile0 = aligned ? k23tile_w : k23tile;
             fi.sx = p.css == CSS_411 ? 2 : (p.css == CSS_422 || p.css == CSS_420) ? 1 : 0;
             fi.sy = (p.css == CSS_440 || p.css == CSS_420) ? 1 : 0;
             uint32_t off = 0;
@@ -638,12 +644,14 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
                 fi.qidx[c] = uint32_t(im.qt_index[c]);
                 fi.pitch[c] = uint32_t(8 * fi.mpt * im.hs[c]);
                 fi.base[c] = off;
+                fi.comp_info[c] = uint32_t(fi.H[c]) | (uint32_t(fi.V[c]) << 8) | (uint32_t(fi.first_blk[c]) << 16) | (uint32_t(fi.hshift[c]) << 24);
                 off += c == 0 ? 16u * kK3TileW : 8u * kK3TileW;   // plane capacities in the kernel's shared memory
             }
             const uint32_t ntiles = fi.tiles_x * uint32_t(p.mcus_y);
-            h_tile_img_.insert(h_tile_img_.end(), ntiles, uint16_t(h_fused_.size()));
+            std::vector<uint32_t>& list = aligned ? h_tile_img_w_ : h_tile_img_;
+            for (uint32_t r = 0; r < uint32_t(p.mcus_y); r++) list.insert(list.end(), fi.tiles_x, uint32_t(h_fused_.size()) | (r << 16));   // picture | MCU row << 16
             h_fused_.push_back(fi);
-            k23tile += ntiles;
+            (aligned ? k23tile_w : k23tile) += ntiles;
             stats_.fused_blocks += im.nblocks;
         }
         od.tile0 = k3tile;
@@ -700,12 +708,13 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     k23_ = K23Args{};
     k23_.nimages = n;
     k23_.total_tiles = k23tile;
+    k23_.total_tiles_w = k23tile_w;
     return kSuccess;
 }
 
 // Descriptor block: one pinned host buffer mirrored by one device buffer, one copy.
 struct Lane::Layout {
-    size_t images, outputs, cta0, k0tile0, dctile0, k2tile0, k3tile0, fused, tile_img, gather, luts, qtables, total;
+    size_t images, outputs, cta0, k0tile0, dctile0, k2tile0, k3tile0, fused, tile_img, tile_img_w, gather, luts, qtables, total;
 };
 
 int Lane::Upload(cudaStream_t up, UploadTurn turn) {
@@ -723,7 +732,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     L.k2tile0 = place((n + 1) * 4);
     L.k3tile0 = place((n + 1) * 4);
     L.fused = place(h_fused_.size() * sizeof(FusedImage));
-    L.tile_img = place(h_tile_img_.size() * 2);
+    L.tile_img = place(h_tile_img_.size() * 4);
+    L.tile_img_w = place(h_tile_img_w_.size() * 4);
     L.gather = place(n * sizeof(GatherItem));
     L.luts = place(h_lut_ptrs_.size() * sizeof(HuffLutSet));
     L.qtables = place(h_qtables_.size() * 2);
@@ -738,7 +748,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     std::memcpy(h + L.k2tile0, h_k2_tile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.k3tile0, h_k3_tile0_.data(), (n + 1) * 4);
     std::memcpy(h + L.fused, h_fused_.data(), h_fused_.size() * sizeof(FusedImage));
-    std::memcpy(h + L.tile_img, h_tile_img_.data(), h_tile_img_.size() * 2);
+    std::memcpy(h + L.tile_img, h_tile_img_.data(), h_tile_img_.size() * 4);
+    std::memcpy(h + L.tile_img_w, h_tile_img_w_.data(), h_tile_img_w_.size() * 4);
     std::memcpy(h + L.gather, h_gather_.data(), n * sizeof(GatherItem));
     for (size_t s = 0; s < h_lut_ptrs_.size(); s++) std::memcpy(h + L.luts + s * sizeof(HuffLutSet), h_lut_ptrs_[s], sizeof(HuffLutSet));
     std::memcpy(h + L.qtables, h_qtables_.data(), h_qtables_.size() * 2);
@@ -804,7 +815,8 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     k3_.img_tile0 = reinterpret_cast<const uint32_t*>(d + L.k3tile0);
     k3_.planes = k2_.planes;
     k23_.fused = reinterpret_cast<const FusedImage*>(d + L.fused);
-    k23_.tile_img = reinterpret_cast<const uint16_t*>(d + L.tile_img);
+    k23_.tile_img = reinterpret_cast<const uint32_t*>(d + L.tile_img);
+    k23_.tile_img_w = reinterpret_cast<const uint32_t*>(d + L.tile_img_w);
     k23_.qtables = k2_.qtables;
     k23_.entries = k1_.entries;
     k23_.blk_rec = k1_.blk_rec;
@@ -916,7 +928,7 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(LaunchK23Fused(k23_, stream_));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + (k2_needed_ ? 1 : 0) + (k23_.total_tiles ? 1 : 0) +
+    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + (k2_needed_ ? 1 : 0) + (k23_.total_tiles ? 1 : 0) + (k23_.total_tiles_w ? 1 : 0) +
                               (k3_.total_tiles ? 1 : 0);   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, fused IDCT + output, output
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data() + 256, k0_.status, h_images_.size() * sizeof(ScanStatus), cudaMemcpyDeviceToHost, stream_));
@@ -993,16 +1005,19 @@ int Decoder::Split(const StreamParser* const* streams, int n) {
     uint64_t total = 0;
     for (int i = 0; i < n; i++) total += streams[i] ? streams[i]->parsed().raw_bytes : 0;
     int want = EnvInt("ROCJPEG_B200_LANES", 0);
-    if (want <= 0) want = int(std::min<uint64_t>(kMaxLanes, total / (2u << 20)));   // about 2 MiB of scan per chunk at least
+    // about 2 MiB of scan per chunk at least, four chunks at most (every kernel of a chunk is a smaller, less efficient grid:
+    // eight chunks cost the 256-picture batch 30 % of its resident throughput) - ROCJPEG_B200_LANES overrides, up to kMaxLanes
+    if (want <= 0) want = int(std::min<uint64_t>(4, total / (2u << 20)));
     want = std::max(1, std::min(std::min(want, kMaxLanes), n));
     // Chunk sizes as cumulative shares of the scan bytes; ROCJPEG_B200_SPLIT ("30,40,20,10": percentages,
-    // one per lane) overrides. Many small pictures (compute-bound call): decreasing shares, so that the
-    // tail behind the final upload is short (c3 / c3j: 3-4 % faster end to end than equal shares). Few
-    // large ones (upload-bound call): equal shares keep the PCIe link and the SMs evenly busy.
+    // one per lane) overrides. Many small pictures: a smaller first and last chunk - the first so that the kernels
+    // start early, the last so that the tail behind the final upload is short (c3: 0.82 ms end to end with 20/30/30/20,
+    // 0.86 with 30/40/20/10, 0.85 with equal shares; profiles/r03_e2e.md). Few large ones (upload and kernels take
+    // about as long): equal shares.
     double cum[kMaxLanes + 1] = {0};
     for (int l = 1; l <= want; l++) cum[l] = double(l) / want;
     if (want == 4 && n > 0 && total / uint64_t(n) < (256u << 10)) {
-        cum[1] = 0.30; cum[2] = 0.70; cum[3] = 0.90; cum[4] = 1.0;
+        cum[1] = 0.20; cum[2] = 0.50; cum[3] = 0.80; cum[4] = 1.0;
     }
     if (const char* sp = std::getenv("ROCJPEG_B200_SPLIT")) {
         double w[kMaxLanes] = {0}, sum = 0;
@@ -1051,7 +1066,7 @@ int Decoder::BuildAll(const StreamParser* const* streams, int n, const DecodePar
         return Fail(kInvalidParameter, "unknown output format");
     Split(streams, n);
     for (int l = 0; l < active_lanes_; l++) {
-        const int st = lanes_[l].Create(device_id_, sm_count_);
+        const int st = lanes_[l].Create(device_id_, sm_count_, l < 4);
         if (st != kSuccess) return Fail(st, lanes_[l].last_error());
     }
     // Optionally one submitter per lane (ROCJPEG_B200_SUBMIT_THREADS=1): the caller's thread takes lane 0,

@@ -127,7 +127,7 @@ class Lane {
     ~Lane();
     Lane(const Lane&) = delete;
     Lane& operator=(const Lane&) = delete;
-    int Create(int device_id, int sm_count);
+    int Create(int device_id, int sm_count, bool prealloc = true);
     // remote[i] != 0: image i's destination lives on another GPU (stores go over NVLink: rows through the output stage, not the
     // IDCT stage's scattered block stores); nullptr: all local
     int Build(const StreamParser* const* streams, int n, const DecodeParams& params, const DestImage* dsts, const uint8_t* remote = nullptr);
@@ -176,7 +176,8 @@ class Lane {
     };
     std::vector<CopyRun> h_runs_;          // upload plan: neighbouring streams of one page-locked allocation move with one copy
     std::vector<FusedImage> h_fused_;      // pictures served by the fused IDCT + output kernel
-    std::vector<uint16_t> h_tile_img_;     // per strip of that kernel: index into h_fused_
+    std::vector<uint32_t> h_tile_img_;     // per strip of the strip kernel (k23_fused): index into h_fused_
+    std::vector<uint32_t> h_tile_img_w_;   // ... of the warp-per-column kernel (k23_warp: aligned destinations)
     std::vector<const HuffLutSet*> h_lut_ptrs_;
     std::vector<const ParsedJpeg*> h_lut_specs_;
     std::vector<uint64_t> h_lut_hashes_;
@@ -202,7 +203,7 @@ class Lane {
     BatchStats stats_;
 };
 
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = 8;      // lanes a handle owns; how many a call uses: Decoder::Split
 constexpr int kMaxDevices = 16;
 
 

@@ -156,6 +156,7 @@ struct FusedImage {
     uint8_t H[3], V[3], first_blk[3], hshift[3];
     uint32_t qidx[3];             // quantiser table per component
     uint32_t pitch[3], base[3];   // shared-memory plane pitch / offset per component
+    uint32_t comp_info[3];        // H | V << 8 | first_blk << 16 | hshift << 24: one load per component in k23_warp
 };
 
 }  // namespace rjb

@@ -29,6 +29,28 @@ namespace {
 
 using namespace idct;
 
+// shared memory through 32-bit window addresses kept in registers (the generic-pointer forms made the compiler re-derive
+// the window base inside the issue-bound tile loop)
+__device__ __forceinline__ uint32_t SharedU32(const void* p) {
+    uint32_t a = uint32_t(__cvta_generic_to_shared(p));
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ uint32_t Lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 Lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void Sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void Sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 constexpr int kBlocksPerTile = 32;
 constexpr int kThreads = kBlocksPerTile * 8;
 constexpr int kTilesPerCta = 8;
@@ -170,9 +192,8 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
     // row/column split and the quantiser load
     __shared__ uint32_t s_tab[kTilesPerCta][64];
     __shared__ uint32_t s_tile0[kSearchCache];
-    __shared__ uint32_t s_first[kTilesPerCta][kBlocksPerTile];   // first entry of every block of every tile
-    __shared__ uint16_t s_count[kTilesPerCta][kBlocksPerTile];   // its number of entries
-    __shared__ int16_t s_dc[kTilesPerCta][kBlocksPerTile];       // its integrated DC
+    // per tile and block: {first entry, entries | valid << 24, dequantised integrated DC, -}
+    __shared__ __align__(16) uint4 s_meta[kTilesPerCta][kBlocksPerTile];
     static_assert(kTilesPerCta * kBlocksPerTile == kThreads, "one record fetch per thread");
     const int tid = threadIdx.x;
     const bool cached = a.nimages <= kSearchCache;
@@ -187,91 +208,80 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
         const TileInfo& ti = s_tile[t];
         if (ti.nbx >= 0) {
             const int nat = kZigzag[(code + 63) & 63];
-            s_tab[t][code] = uint32_t(((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(ti.qt + nat)) << 16);
+            // (code 1 = position 0: DC-difference and pad entries - the integrated DC goes in with the zero fill - are parked in
+            // a padding word of the workspace's first row)
+            s_tab[t][code] = uint32_t(code == 1 ? 8 * 4 : ((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(ti.qt + nat)) << 16);
         }
     }
     __syncthreads();
     const int b = tid >> 3, j = tid & 7;
-    int* my = ws + b * kBS;
     // Records of ALL the CTA's tiles first: every thread fetches the record pair of one (tile, block) -
     // eight tiles x 32 blocks = 256 - so the tile loop below starts from shared memory instead of
     // waiting for a dependent global load at the top of every tile (profiles/r01g_*).
     {
         const int t = tid >> 5, bb = tid & 31;
         const TileInfo& ti = s_tile[t];
-        uint32_t e0 = 0, n = 0;
-        int dc = 0;
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
         if (ti.nbx >= 0 && ti.direct != 2 && ti.bx0 + bb < ti.nbx) {
             const int bx = ti.bx0 + bb;
             const size_t blk = size_t(ti.row_mcu + uint32_t(bx >> ti.hshift)) * uint32_t(ti.bpm) + ti.k_row + uint32_t(bx & ti.hmask);
             const uint2 r = __ldg(reinterpret_cast<const uint2*>(ti.rec + blk));
-            e0 = blk ? __ldg(&ti.rec[blk - 1].end) : 0u;
-            uint32_t e1 = r.x;
-            dc = int(int16_t(r.y & 0xFFFFu));
+            uint32_t e0 = blk ? __ldg(&ti.rec[blk - 1].end) : 0u, e1 = r.x;
             // (a block of a valid stream has at most 64 entries + 7 pads per subsequence boundary inside it; after a DAMAGED
             // restart interval the first block of the next one also owns the pad groups the counting pass reserved in vain,
-            // any number of them - they are skipped, not a reason to drop the block; s_count is 16 bits wide)
+            // any number of them - they are skipped, not a reason to drop the block; the count is 16 bits wide)
             if (e0 == kNoEntry || e1 == kNoEntry || e1 < e0 || e1 - e0 > 0xFFFFu || e1 > ti.ent_cap) e1 = e0 = 0;   // never decoded
-            n = e1 - e0;
+            m.x = e0;
+            m.y = (e1 - e0) | (1u << 24);
+            m.z = uint32_t(int(int16_t(r.y & 0xFFFFu)) * int(__ldg(ti.qt)));   // integrated DC, dequantised
         }
-        s_first[t][bb] = e0;
-        s_count[t][bb] = uint16_t(n);
-        s_dc[t][bb] = int16_t(dc);
+        s_meta[t][bb] = m;
     }
     __syncthreads();
+    const uint32_t my_sa = SharedU32(ws) + uint32_t(b * kBS * 4);
+    const uint32_t row_sa = my_sa + uint32_t(j * kRS * 4), col_sa = my_sa + uint32_t(j * 4);
+    const uint32_t tab_sa0 = SharedU32(&s_tab[0][0]);
+    const uint32_t meta_sa0 = SharedU32(&s_meta[0][0]) + uint32_t(b * 16);
 #pragma unroll 1
     for (int it = 0; it < kTilesPerCta; it++) {
         const TileInfo& ti = s_tile[it];
         if (ti.nbx < 0) break;
         if (ti.direct == 2) continue;   // e.g. chroma of a colour picture decoded to ROCJPEG_OUTPUT_Y
-        const int bx = ti.bx0 + b;
-        const bool valid = bx < ti.nbx;
-        // expand the block's sparse entries into the zeroed workspace, dequantising on the way
-        const uint32_t* ep = ti.entries + s_first[it][b] + uint32_t(j);
-        const uint32_t n = s_count[it][b];
-        const int dc = s_dc[it][b];
-        if (valid) {
-            int4* row = reinterpret_cast<int4*>(my + j * kRS);
-            row[0] = make_int4(0, 0, 0, 0);
-            row[1] = make_int4(0, 0, 0, 0);
-        }
+        const uint4 m = Lds128(meta_sa0 + uint32_t(it * kBlocksPerTile * 16));
+        const uint32_t n = m.y & 0xFFFFu;
+        // expand the block's sparse entries into the zeroed workspace, dequantising on the way; four loads in flight
+        // per thread (32 entries per block) before the first is used
+        const uint32_t* ep = ti.entries + m.x + uint32_t(j);
+        const uint32_t k = uint32_t(j);
+        uint32_t e[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) e[u] = (k + 8u * u < n) ? __ldg(ep + 8 * u) : 0u;
+        Sts128(row_sa, make_uint4(j == 0 ? m.z : 0u, 0u, 0u, 0u));   // zero fill; the integrated DC goes in with it
+        Sts128(row_sa + 16, make_uint4(0u, 0u, 0u, 0u));
         __syncwarp();
-        const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(&s_tab[it][0]));
-        const uint32_t my_sa = uint32_t(__cvta_generic_to_shared(my));
+        const uint32_t tab_sa = tab_sa0 + uint32_t(it * 256);
         auto put = [&](uint32_t en) {
-            uint32_t t;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(tab_sa + ((en >> 14) & 0xFCu)));
-            const int v = int(int16_t(en & 0xFFFFu)) * int(t >> 16);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_sa + (t & 0xFFFFu)), "r"(v) : "memory");
+            const uint32_t t = Lds32(tab_sa + ((en >> 14) & 0xFCu));
+            Sts32(my_sa + (t & 0xFFFFu), uint32_t(int(int16_t(en & 0xFFFFu)) * int(t >> 16)));
         };
-        // four loads in flight per thread (32 entries per block) before the first is used: the loop was
-        // waiting on one global load after the other
-        {
-            const uint32_t k = uint32_t(j);
-            uint32_t e[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) e[u] = (k + 8u * u < n) ? __ldg(ep + 8 * u) : 0u;
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (k + 8u * u < n) put(e[u]);
-        }
-        for (uint32_t k = uint32_t(j) + 32u; k < n; k += 8) put(__ldg(ep + (k - uint32_t(j))));
-        __syncwarp();
-        if (valid && j == 0) my[0] = dc * int(s_tab[it][1] >> 16);   // integrated DC replaces any DC-difference entry
+        for (int u = 0; u < 4; u++)
+            if (k + 8u * u < n) put(e[u]);
+        for (uint32_t kk = k + 32u; kk < n; kk += 8) put(__ldg(ep + (kk - k)));
         __syncwarp();
         int in[8], out[8];
-        if (valid) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) in[r] = my[r * kRS + j];   // column j
-            Islow8<11>(in, out, 1 << 10);
+        for (int r = 0; r < 8; r++) in[r] = int(Lds32(col_sa + uint32_t(r * kRS * 4)));   // column j
+        Islow8<11>(in, out, 1 << 10);
 #pragma unroll
-            for (int r = 0; r < 8; r++) my[r * kRS + j] = out[r];
-        }
+        for (int r = 0; r < 8; r++) Sts32(col_sa + uint32_t(r * kRS * 4), uint32_t(out[r]));
         __syncwarp();
-        if (valid) {
-            const int4 lo = *reinterpret_cast<const int4*>(my + j * kRS), hi = *reinterpret_cast<const int4*>(my + j * kRS + 4);   // row j
-            in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
+        if (m.y >> 24) {
+            const uint4 lo = Lds128(row_sa), hi = Lds128(row_sa + 16);   // row j
+            in[0] = int(lo.x); in[1] = int(lo.y); in[2] = int(lo.z); in[3] = int(lo.w);
+            in[4] = int(hi.x); in[5] = int(hi.y); in[6] = int(hi.z); in[7] = int(hi.w);
             Islow8<18>(in, out, (1 << 17) + (128 << 18));
+            const int bx = ti.bx0 + b;
             uint8_t* dst = ti.out + size_t(j) * ti.pitch + size_t(bx) * 8;
             const uint2 v = make_uint2(PackSat4(out[0], out[1], out[2], out[3]), PackSat4(out[4], out[5], out[6], out[7]));
             if (!ti.direct) {

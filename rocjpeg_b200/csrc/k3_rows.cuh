@@ -294,6 +294,51 @@ __device__ __forceinline__ void Store8(uint8_t* d, uint2 v, bool al8) {   // d i
     }
 }
 
+// 8 converted pixels (the first n of them) of output row y from column x on; destination rows 4-byte aligned at least.
+__device__ __forceinline__ void StoreRgb8(int fmt, uint8_t* dst0, uint8_t* dst1, uint8_t* dst2, uint32_t dpitch, int y, int x, int n, const Rgb8& o) {
+    if (fmt == FMT_RGB) {
+        uint8_t* d = dst0 + size_t(y) * dpitch + size_t(x) * 3;
+        // interleave R,G,B bytes: 8 pixels -> 6 words
+        uint32_t w[6];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t r = h ? o.r.y : o.r.x, g = h ? o.g.y : o.g.x, b = h ? o.b.y : o.b.x;
+            w[3 * h + 0] = __byte_perm(__byte_perm(r, g, 0x1040), b, 0x3410);   // r0 g0 b0 r1
+            w[3 * h + 1] = __byte_perm(__byte_perm(g, b, 0x2051), r, 0x3610);   // g1 b1 r2 g2
+            w[3 * h + 2] = __byte_perm(__byte_perm(b, r, 0x3702), g, 0x3720);   // b2 r3 g3 b3
+        }
+        if (n >= 8) {
+            if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) reinterpret_cast<uint2*>(d)[k] = make_uint2(w[2 * k], w[2 * k + 1]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) reinterpret_cast<uint32_t*>(d)[k] = w[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 24; k++)
+                if (k < 3 * n) d[k] = uint8_t((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+        }
+    } else {
+        // all three planes use pitch[0] (src/rocjpeg_decoder.cpp:526-544)
+        const size_t off = size_t(y) * dpitch + size_t(x);
+        uint8_t* d0 = dst0 + off;
+        uint8_t* d1 = dst1 + off;
+        uint8_t* d2 = dst2 + off;
+        if (n >= 8) {
+            const bool al8 = ((reinterpret_cast<uintptr_t>(d0) | reinterpret_cast<uintptr_t>(d1) | reinterpret_cast<uintptr_t>(d2)) & 7) == 0;
+            Store8(d0, o.r, al8);
+            Store8(d1, o.g, al8);
+            Store8(d2, o.b, al8);
+        } else {
+            StoreBytes(d0, o.r, n);
+            StoreBytes(d1, o.g, n);
+            StoreBytes(d2, o.b, n);
+        }
+    }
+}
+
 // One output row segment (nx pixels from column xt of output row y), RGB or RGB_PLANAR.
 // Preconditions (checked by the caller, warp-uniform): (x0 + xt) % 8 == 0, destination row(s) 4-byte aligned.
 template <int SX, bool SM = false>
@@ -323,47 +368,7 @@ __device__ __forceinline__ void RowRgbFast(const K3Job& j, int sy, bool gray, in
         }
         o = Convert8<SX>(yy, uu, vv);
     }
-    if (j.fmt == FMT_RGB) {
-        uint8_t* d = j.dst[0] + size_t(y) * j.dpitch[0] + size_t(xt + lane * 8) * 3;
-        // interleave R,G,B bytes: 8 pixels -> 6 words
-        uint32_t w[6];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const uint32_t r = h ? o.r.y : o.r.x, g = h ? o.g.y : o.g.x, b = h ? o.b.y : o.b.x;
-            w[3 * h + 0] = __byte_perm(__byte_perm(r, g, 0x1040), b, 0x3410);   // r0 g0 b0 r1
-            w[3 * h + 1] = __byte_perm(__byte_perm(g, b, 0x2051), r, 0x3610);   // g1 b1 r2 g2
-            w[3 * h + 2] = __byte_perm(__byte_perm(b, r, 0x3702), g, 0x3720);   // b2 r3 g3 b3
-        }
-        if (n >= 8) {
-            if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) reinterpret_cast<uint2*>(d)[k] = make_uint2(w[2 * k], w[2 * k + 1]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 6; k++) reinterpret_cast<uint32_t*>(d)[k] = w[k];
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 24; k++)
-                if (k < 3 * n) d[k] = uint8_t((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
-        }
-    } else {
-        // all three planes use pitch[0] (src/rocjpeg_decoder.cpp:526-544)
-        const size_t off = size_t(y) * j.dpitch[0] + size_t(xt + lane * 8);
-        uint8_t* d0 = j.dst[0] + off;
-        uint8_t* d1 = j.dst[1] + off;
-        uint8_t* d2 = j.dst[2] + off;
-        if (n >= 8) {
-            const bool al8 = ((reinterpret_cast<uintptr_t>(d0) | reinterpret_cast<uintptr_t>(d1) | reinterpret_cast<uintptr_t>(d2)) & 7) == 0;
-            Store8(d0, o.r, al8);
-            Store8(d1, o.g, al8);
-            Store8(d2, o.b, al8);
-        } else {
-            StoreBytes(d0, o.r, n);
-            StoreBytes(d1, o.g, n);
-            StoreBytes(d2, o.b, n);
-        }
-    }
+    StoreRgb8(j.fmt, j.dst[0], j.dst[1], j.dst[2], j.dpitch[0], y, xt + lane * 8, n, o);
 }
 
 

@@ -160,12 +160,13 @@ cudaError_t LaunchK2Idct(const K2Args& a, cudaStream_t stream);
 // K2 + K3 in one kernel for whole-picture RGB / RGB_PLANAR outputs (OutputDesc::fused): coefficients in, pixels out.
 struct K23Args {
     const FusedImage* fused;      // one per image served by this kernel
-    const uint16_t* tile_img;     // per strip: index into `fused`
+    const uint32_t* tile_img;     // per strip of k23_fused (pictures with unaligned destination rows): index into `fused` | MCU row << 16
+    const uint32_t* tile_img_w;   // per strip of k23_warp (destination rows 4-byte aligned), same encoding
     const uint16_t* qtables;
     const uint32_t* entries;
     const BlockRec* blk_rec;
     int nimages;
-    uint32_t total_tiles;
+    uint32_t total_tiles, total_tiles_w;
 };
 cudaError_t LaunchK23Fused(const K23Args& a, cudaStream_t stream);
 cudaError_t PreloadK23();

@@ -100,9 +100,11 @@ def main():
         ("lanes4_20_35_30_15", {"ROCJPEG_B200_LANES": "4", "ROCJPEG_B200_SPLIT": "20,35,30,15"}, steps),
         ("nofuse", {"ROCJPEG_B200_NO_FUSE": "1"}, steps),
     ]
+    for sp in filter(None, os.environ.get("E2E_SPLITS", "").split(";")):
+        configs.append(("split_" + sp.replace(",", "_"), {"ROCJPEG_B200_LANES": str(len(sp.split(","))), "ROCJPEG_B200_SPLIT": sp}, steps))
     extra = os.environ.get("E2E_CONFIGS")
     for name, env, n in configs:
-        if extra and name not in extra.split(","):
+        if extra and name not in extra.split(",") and not name.startswith("split_"):
             continue
         e = dict(os.environ)
         e.update(env)
