@@ -6,6 +6,9 @@
 #include <cuda_runtime_api.h>
 
 #include <atomic>
+#include <memory>
+#include <mutex>
+#include <vector>
 
 #include <string>
 
@@ -623,16 +626,48 @@ void StreamParser::BuildDecodeTables() {
                 }
         }
     p_.min_entry_bits = min_bits < 2 ? 2 : (min_bits > 31 ? 2 : min_bits);
-    std::memset(&lut_, 0, sizeof(lut_));
     // debug knob: a smaller second-level arena forces long codes onto the canonical search
     const char* cap_env = std::getenv("ROCJPEG_B200_SUBCAP");
     const uint32_t cap = (cap_env && *cap_env) ? uint32_t(std::atoi(cap_env)) : uint32_t(kSubCap);
+    // Decoder-form tables are a pure function of the DHT content: a process-wide cache lets the first parse of a new
+    // handle copy them (14 KiB) instead of building them (the reference's perf sample creates one handle per image; 256
+    // first parses took 4.2 ms, most of it here).
+    struct Cached {
+        uint64_t hash;
+        uint32_t cap;
+        HuffSpec dc[kHuffIds], ac[kHuffIds];
+        HuffLutSet lut;
+    };
+    static std::mutex cache_mutex;
+    static std::vector<std::unique_ptr<Cached>> cache;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        for (const auto& c : cache)
+            if (c->hash == h && c->cap == cap && std::memcmp(c->dc, p_.dc, sizeof(p_.dc)) == 0 && std::memcmp(c->ac, p_.ac, sizeof(p_.ac)) == 0) {
+                std::memcpy(&lut_, &c->lut, sizeof(lut_));
+                lut_cap_ = cap;
+                lut_valid_ = true;
+                return;
+            }
+    }
+    std::memset(&lut_, 0, sizeof(lut_));
     for (int t = 0; t < kHuffIds; t++) {
         if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &lut_, cap);
         if (p_.ac[t].present) BuildHuffLut(p_.ac[t], kHuffIds + t, &lut_, cap);
     }
     lut_cap_ = cap;
     lut_valid_ = true;
+    {
+        std::unique_ptr<Cached> c(new Cached);
+        c->hash = h;
+        c->cap = cap;
+        std::memcpy(c->dc, p_.dc, sizeof(p_.dc));
+        std::memcpy(c->ac, p_.ac, sizeof(p_.ac));
+        std::memcpy(&c->lut, &lut_, sizeof(lut_));
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        if (cache.size() >= 16) cache.erase(cache.begin());   // oldest out
+        cache.push_back(std::move(c));
+    }
 }
 
 // Everything of the previous stream except its tables (the reference zeroes its parameters on every parse,
