@@ -53,7 +53,7 @@ __device__ __forceinline__ void Sts128(uint32_t a, uint4 v) {
 
 constexpr int kBlocksPerTile = 32;
 constexpr int kThreads = kBlocksPerTile * 8;
-constexpr int kTilesPerCta = 8;
+constexpr int kTilesPerCta = 16;   // (8: a fifth of the warp time went to the barriers of the per-CTA set-up, profiles/r03l_*)
 constexpr int kSearchCache = 1024;   // image tile prefix entries searched in shared memory
 
 // Everything the 256 threads of a CTA need about one tile (32 adjacent blocks of one block row
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
     __shared__ uint32_t s_tile0[kSearchCache];
     // per tile and block: {first entry, entries | valid << 24, dequantised integrated DC, -}
     __shared__ __align__(16) uint4 s_meta[kTilesPerCta][kBlocksPerTile];
-    static_assert(kTilesPerCta * kBlocksPerTile == kThreads, "one record fetch per thread");
+    static_assert((kTilesPerCta * kBlocksPerTile) % kThreads == 0, "whole record fetches per thread");
     const int tid = threadIdx.x;
     const bool cached = a.nimages <= kSearchCache;
     if (cached) {
@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(kThreads, 8) k2_idct(K2Args a) {
     // Records of ALL the CTA's tiles first: every thread fetches the record pair of one (tile, block) -
     // eight tiles x 32 blocks = 256 - so the tile loop below starts from shared memory instead of
     // waiting for a dependent global load at the top of every tile (profiles/r01g_*).
-    {
-        const int t = tid >> 5, bb = tid & 31;
+#pragma unroll
+    for (int rep = 0; rep < kTilesPerCta * kBlocksPerTile / kThreads; rep++) {
+        const int t = (tid >> 5) + rep * (kThreads / 32), bb = tid & 31;
         const TileInfo& ti = s_tile[t];
         uint4 m = make_uint4(0u, 0u, 0u, 0u);
         if (ti.nbx >= 0 && ti.direct != 2 && ti.bx0 + bb < ti.nbx) {
