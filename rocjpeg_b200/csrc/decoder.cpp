@@ -634,6 +634,8 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
             bool aligned = (od.dst_pitch[0] & 3u) == 0;
             for (int c = 0; c < (od.fmt == FMT_RGB ? 1 : 3); c++) aligned = aligned && (reinterpret_cast<uintptr_t>(od.dst[c]) & 3u) == 0;
             aligned = aligned && warp_ok && (fi.mpt / 8) * p.bpm <= 16;   // a warp's MCUs hold at most 16 blocks (k23_fused.cu)
+            // a destination on another GPU: the strip kernel's rows cross NVLink as 256-pixel segments, the warp kernel's as 32-byte ones
+            if (remote && remote[i]) aligned = false;
             fi.tile0 = aligned ? k23tile_w : k23tile;
             fi.sx = p.css == CSS_411 ? 2 : (p.css == CSS_422 || p.css == CSS_420) ? 1 : 0;
             fi.sy = (p.css == CSS_440 || p.css == CSS_420) ? 1 : 0;
