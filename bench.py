@@ -594,7 +594,9 @@ def main():
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(stage_bytes[dom]), "launch_ms": dom_ms,
-                     "note": "slower of the two HBM-bound stages (IDCT, output); every stage's own fraction is in `stages`"},
+                     "issue_utilisation": (measured_traffic(args.workload, "issue") or {}).get("k2_idct" if dom == "idct" else "k23_warp"),
+                     "note": "slower of the two stages the north star names HBM-bound (IDCT, output); both are in fact bound by issue slots "
+                             "(issue_utilisation: committed ncu capture); every stage's own fraction is in `stages`"},
         "roofline_k1": {"bound": "latency/issue", "compressed_GB_s": round(scan / (k1_ms or 1e-9) / 1e6, 2), "ms": round(k1_ms, 4),
                         "sync_ms": round(stage_ms[2], 4), "write_ms": round(stage_ms[3], 4),
                         "entries_written_GB_s": round((entries * 4 + blocks * 8) / (stage_ms[3] or 1e-9) / 1e6, 1),

@@ -265,6 +265,65 @@ def test_411_pictures_every_format_and_crop(dec, orc, dri):
         assert np.array_equal(dec.planes(0, n), np.concatenate([p.reshape(-1) for p in orc.planes(data, info)]))
 
 
+def _aligned_rgb(dec, orc, data, what):
+    """RGB / RGB_PLANAR into buffers whose base and pitch are multiples of 16: every row takes the register path, the fused
+    IDCT + output kernel with one warp per 32-sample column (k23_warp) serves the picture."""
+    import torch
+
+    rc, info = orc.parse(data)
+    assert rc == 0
+    for fmt in ("rgb", "rgb_planar"):
+        shapes = oracle.output_shapes(info, fmt, (0, 0, 0, 0), orc)
+        pitches = [(rb + 15) // 16 * 16 + 16 for (_, rb) in shapes]
+        if fmt == "rgb_planar":
+            pitches[1] = pitches[2] = pitches[0]
+        bufs = [torch.full((rows * p + 64,), gu.FILL, dtype=torch.uint8, device="cuda") for (rows, _), p in zip(shapes, pitches)]
+        assert all(b.data_ptr() % 16 == 0 for b in bufs)
+        s = api.JpegStream()
+        assert s.parse(data) == api.SUCCESS
+        assert dec.decode(s, api.make_params(fmt), [(b.data_ptr(), p) for b, p in zip(bufs, pitches)]) == api.SUCCESS, (what, fmt)
+        assert dec.stats().fused_blocks > 0
+        got = gu.fetch(bufs, pitches, shapes)
+        _, want = gu.oracle_outputs(orc, data, fmt, (0, 0, 0, 0), pitches)
+        gu.assert_same(got, want, f"{what} {fmt} aligned rows")
+
+
+@pytest.mark.parametrize("css", ["444", "440", "422", "420", "411", "400"])
+def test_fused_rgb_with_aligned_rows(dec, orc, css):
+    """Every subsampling through the warp-per-column fused kernel: whole and ragged strips (widths around multiples of 32 and
+    256), pictures smaller than one MCU, with and without restart markers."""
+    for (w, h), dri in (((500, 375), 0), ((123, 77), 1), ((257, 40), 0), ((255, 17), 0), ((33, 9), 0), ((8, 8), 0), ((1, 1), 0), ((640, 48), 1),
+                        ((31, 33), 0), ((288, 16), 0)):
+        _aligned_rgb(dec, orc, datagen.make_jpeg(w, h, css, seed=90 + w + h, restart_rows=dri), f"{css} {w}x{h} dri={dri}")
+
+
+def test_fused_rgb_422_with_full_height_chroma_blocks(dec, orc):
+    """Sampling factors (2x2, 1x2, 1x2) - classified 4:2:2 like (2x1, 1x1, 1x1), but a 16x16 MCU of eight blocks: sixteen
+    blocks under a warp's 32 samples, the most the fused kernel's per-warp tables hold. No encoder here writes it: the
+    stream is assembled from coefficients."""
+    import jpeg_writer as jw
+
+    rng = np.random.default_rng(17)
+    for (w, h) in ((70, 50), (300, 40), (32, 16)):
+        hs, vs = [2, 1, 1], [2, 2, 2]
+        mx, my = (w + 15) // 16, (h + 15) // 16
+        coefs = []
+        for c in range(3):
+            a = np.zeros((my * vs[c], mx * hs[c], 64), np.int16)
+            a[..., 0] = rng.integers(-40, 40, a.shape[:2])
+            for k in range(1, 14):
+                a[..., k] = rng.integers(-6, 7, a.shape[:2]) * (rng.random(a.shape[:2]) < 0.5)
+            coefs.append(a)
+        data = jw.write_jpeg(w, h, coefs, hs, vs, [0, 1, 1], {0: bytes([2] * 64), 1: bytes([3] * 64)})
+        rc, info = orc.parse(data)
+        assert rc == 0 and orc.supported(info) == 0 and oracle.CSS[info.css] == "422"
+        _aligned_rgb(dec, orc, data, f"(2x2,1x2,1x2) {w}x{h}")
+        for fmt in ("rgb", "yuv_planar", "native"):
+            st, got, want = gu.decode_one(dec, orc, data, fmt, pitch_pad=5, misalign=1)
+            assert st == api.SUCCESS
+            gu.assert_same(got, want, f"(2x2,1x2,1x2) {w}x{h} {fmt}")
+
+
 @pytest.mark.parametrize("css", ["444", "440", "422", "420", "411", "400"])
 def test_tiny_and_ragged_pictures(dec, orc, css):
     """Pictures smaller than one MCU, one sample wide or high, and sizes one off a block / MCU multiple: the
@@ -568,6 +627,51 @@ def _check_destuffed_batch(dec, datas, zero_copy, fmt="y", valid_pictures=True):
         assert bool(ds.flags & api.SCAN_NO_EOI) == (hs.scan_size == inf.raw_bytes)
         for k in range(inf.num_segments):
             assert dec.device_segment(i, k) == s.segment(k), f"image {i} restart interval {k} of {inf.num_segments}"
+
+
+@pytest.mark.parametrize("layout", ["packed", "gaps", "reversed", "duplicates", "no_merge"])
+def test_upload_plan_over_page_locked_arenas(orc, layout, monkeypatch):
+    """Streams of one page-locked allocation are uploaded by one copy per run of neighbours (Lane::Build): packed files (one run),
+    files 40 KB apart (a run each), descending addresses (no merging), the same file twice in a batch (overlapping sources), and
+    the per-picture path (ROCJPEG_B200_NO_MERGE=1) - pixels must not depend on the plan."""
+    import torch
+
+    if layout == "no_merge":
+        monkeypatch.setenv("ROCJPEG_B200_NO_MERGE", "1")
+    names = [n for n in CASES if "extreme" not in n][:12]
+    datas = [load(n) for n in names]
+    gap = 40960 if layout == "gaps" else 0
+    offs, total = [], 0
+    for i, d in enumerate(datas):
+        total = (total + 63) // 64 * 64 + (i & 15) + gap
+        offs.append(total)
+        total += len(d)
+    arena = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
+    a = arena.numpy()
+    a[:] = 0xFF
+    for o, d in zip(offs, datas):
+        a[o:o + len(d)] = np.frombuffer(d, np.uint8)
+    order = list(range(len(datas)))
+    if layout == "reversed":
+        order.reverse()
+    if layout == "duplicates":
+        order = order + order[:4] + [order[0]]
+    d2 = api.Decoder(api.BACKEND_HARDWARE, 0)
+    try:
+        streams, dests, keep = [], [], []
+        for k in order:
+            s = api.JpegStream()
+            assert s.parse_ptr(arena.data_ptr() + offs[k], len(datas[k]), arena) == api.SUCCESS
+            assert s.info().source_is_zero_copy
+            rc, info = orc.parse(datas[k])
+            dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "rgb", (0, 0, 0, 0), pitch_pad=1)
+            streams.append(s); dests.append(dest); keep.append((bufs, pitches, shapes))
+        assert d2.decode_batched(streams, api.make_params("rgb"), dests) == api.SUCCESS
+        for k, (bufs, pitches, shapes) in zip(order, keep):
+            _, want = gu.oracle_outputs(orc, datas[k], "rgb", (0, 0, 0, 0), pitches)
+            gu.assert_same(gu.fetch(bufs, pitches, shapes), want, f"{layout} {names[k]}")
+    finally:
+        d2.close()
 
 
 @pytest.mark.parametrize("zero_copy", [True, False])
