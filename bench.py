@@ -547,6 +547,8 @@ def main():
         "idct": (coef_read + blocks * 64) * (1.0 - fused),      # entries + records read, 64 samples per block written (un-fused pictures)
         "output": coef_read * fused + k3_read + stats.output_bytes,   # fused pictures: coefficients in, pixels out; others: planes read + pixels written
     }
+    if stage_ms[3] <= 0.005:   # counting and write pass ran as one kernel (k1_fused): its time is under huffman_sync
+        stage_bytes["huffman_sync"] = stage_bytes["huffman_write"]
     stages = {}
     for i, name in enumerate(api.STAGES):
         ms = stage_ms[i]

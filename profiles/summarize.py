@@ -69,7 +69,7 @@ if rep and len(sys.argv) > 4:
     import json
     import os
 
-    stage_of = {"k0_reduce": "destuff", "k0_scan": "destuff", "k0_apply": "destuff", "k1_sync": "huffman_sync", "k1_scan": "huffman_write",
+    stage_of = {"k0_reduce": "destuff", "k0_scan": "destuff", "k0_apply": "destuff", "k1_sync": "huffman_sync", "k1_fused": "huffman_sync", "k1_scan": "huffman_write",
                 "k1_write": "huffman_write", "dc_sums": "dc", "dc_scan": "dc", "dc_apply": "dc", "dc_image": "dc", "k2_idct": "idct",
                 "k23_fused": "output", "k23_warp": "output", "k3_output": "output"}
     ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
@@ -95,7 +95,7 @@ if rep and len(sys.argv) > 4:
         iss = {}
         for r in d:
             name = r[ki].split("(")[0].split("<")[0].replace("void ", "").split("::")[-1]
-            if name in ("k1_sync", "k1_write", "k2_idct", "k23_warp", "k23_fused", "k3_output", "k0_apply") and name not in iss:
+            if name in ("k1_sync", "k1_write", "k1_fused", "k2_idct", "k23_warp", "k23_fused", "k3_output", "k0_apply") and name not in iss:
                 iss[name] = round(float(r[ii].replace(",", "")) / 100.0, 3)
         if iss:
             t[sys.argv[4]]["k1_issue"] = {k: v for k, v in iss.items() if k.startswith("k1_")}

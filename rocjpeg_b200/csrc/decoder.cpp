@@ -767,7 +767,7 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
                  o_tile_carry = carve(size_t(k0_.total_tiles) * 16), o_status = carve(n * sizeof(ScanStatus)), o_entries = carve(entry_count_ * 4),
                  o_blkrec = carve(coef_blocks_ * sizeof(BlockRec)), o_nnz = carve(nsub_total_ * 4), o_state = carve(nsub_total_ * 4),
                  o_used = carve(nsub_total_ * 4), o_subseg = carve(nsub_total_ * 4), o_cta_entries = carve(size_t(k1_.total_ctas) * 4),
-                 o_cta_partial = carve(size_t(k1_.total_ctas) * 8), o_cta_carry = carve(size_t(k1_.total_ctas) * 8),
+                 o_cta_partial = carve(size_t(k1_.total_ctas) * 8), o_cta_carry = carve(size_t(k1_.total_ctas) * 8), o_cta_flag = carve(size_t(k1_.total_ctas) * 4),
                  o_dc_partial = carve(size_t(k1_.total_dc_tiles) * 12), o_dc_carry = carve(size_t(k1_.total_dc_tiles) * 12),
                  o_end = carve(0);
     (void)o_end;
@@ -799,6 +799,7 @@ int Lane::Upload(cudaStream_t up, UploadTurn turn) {
     k1_.dc_partial = reinterpret_cast<int3*>(base + o_dc_partial);
     k1_.dc_carry = reinterpret_cast<int3*>(base + o_dc_carry);
     k1_.cta_carry = reinterpret_cast<uint2*>(base + o_cta_carry);
+    k1_.cta_flag = reinterpret_cast<uint32_t*>(base + o_cta_flag);
     // the batch's counter set is picked at launch time (LaunchAll): the sets alternate
     k1_.entries = reinterpret_cast<uint32_t*>(base + o_entries);
     k1_.blk_rec = reinterpret_cast<BlockRec*>(base + o_blkrec);
@@ -910,6 +911,11 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
         RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
         RJB_CUDA(cudaMemsetAsync(k1_.counters_next, 0, 256, stream_));
     }
+    // Counting and write pass of the entropy stage in one kernel when no picture has more than 32 K1 CTAs (k1_huffman.cu:
+    // k1_fused); ROCJPEG_B200_NO_K1_FUSE=1 or an explicit ROCJPEG_B200_SYNC_ROUNDS keep the separate kernels.
+    const bool k1_fuse_ok = EnvInt("ROCJPEG_B200_NO_K1_FUSE", 0) == 0 && std::getenv("ROCJPEG_B200_SYNC_ROUNDS") == nullptr;
+    const bool k1_fused = k1_fuse_ok && k1_.inline_scan && k1_.total_ctas != 0;
+    if (k1_fused) RJB_CUDA(cudaMemsetAsync(k1_.cta_flag, 0, size_t(k1_.total_ctas) * 4, stream_));   // "published" flags of the CTAs
     // K0: end of slice, destuffing, restart intervals -> clean stream + segment table, all on the device
     if (!(include_upload && tiles_reduced_)) {   // cudaMemcpy upload, or a resident batch run again: the reduction is its own launch
         RJB_CUDA(LaunchK0Reduce(k0_, stream_));
@@ -918,10 +924,16 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(LaunchK0Destuff(k0_, stream_));
     stats_.kernel_launches += 2;
     RJB_CUDA(mark(2));
-    for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
-    stats_.sync_rounds = uint32_t(rounds);
-    RJB_CUDA(mark(3));
-    RJB_CUDA(LaunchK1Write(k1_, stream_));
+    if (k1_fused) {
+        RJB_CUDA(LaunchK1Fused(k1_, stream_));
+        stats_.sync_rounds = 1;   // counters[0] = CTA boundaries that did not hold: Finish() then runs the separate kernels
+        RJB_CUDA(mark(3));
+    } else {
+        for (int r = 0; r < rounds; r++) RJB_CUDA(LaunchK1Sync(k1_, r, stream_));
+        stats_.sync_rounds = uint32_t(rounds);
+        RJB_CUDA(mark(3));
+        RJB_CUDA(LaunchK1Write(k1_, stream_));
+    }
     RJB_CUDA(mark(4));
     RJB_CUDA(LaunchDcScan(k1_, stream_));
     RJB_CUDA(mark(5));
@@ -930,7 +942,7 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
     RJB_CUDA(LaunchK23Fused(k23_, stream_));
     RJB_CUDA(LaunchK3Output(k3_, stream_));
     RJB_CUDA(mark(7));
-    stats_.kernel_launches += uint32_t(rounds) + (k1_.inline_scan ? 1 : 2) + (k1_.dc_image ? 1 : 3) + (k2_needed_ ? 1 : 0) + (k23_.total_tiles ? 1 : 0) + (k23_.total_tiles_w ? 1 : 0) +
+    stats_.kernel_launches += (k1_fused ? 1u : uint32_t(rounds) + (k1_.inline_scan ? 1u : 2u)) + (k1_.dc_image ? 1 : 3) + (k2_needed_ ? 1 : 0) + (k23_.total_tiles ? 1 : 0) + (k23_.total_tiles_w ? 1 : 0) +
                               (k3_.total_tiles ? 1 : 0);   // sync rounds, (scan +) write, 1 or 3 DC kernels, IDCT, fused IDCT + output, output
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
     RJB_CUDA(cudaMemcpyAsync(h_counters_.data() + 256, k0_.status, h_images_.size() * sizeof(ScanStatus), cudaMemcpyDeviceToHost, stream_));
@@ -964,14 +976,16 @@ int Lane::Finish(int profiling_) {
         }
         RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
         RJB_CUDA(cudaMemsetAsync(k1_.counters + 2 * kMaxSyncRounds, 0, 4, stream_));   // the first write pass counted its entries already
+        RJB_CUDA(LaunchK1ClearShort(k1_, stream_));   // ... and may have reported pictures short that are not
         RJB_CUDA(LaunchK1Write(k1_, stream_));
         RJB_CUDA(LaunchDcScan(k1_, stream_));
         if (k2_needed_) RJB_CUDA(LaunchK2Idct(k2_, stream_));
         RJB_CUDA(LaunchK23Fused(k23_, stream_));
         RJB_CUDA(LaunchK3Output(k3_, stream_));
         RJB_CUDA(cudaMemcpyAsync(h_counters_.data(), k1_.counters, 256, cudaMemcpyDeviceToHost, stream_));
+        RJB_CUDA(cudaMemcpyAsync(h_counters_.data() + 256, k0_.status, h_images_.size() * sizeof(ScanStatus), cudaMemcpyDeviceToHost, stream_));
         RJB_CUDA(cudaStreamSynchronize(stream_));
-        stats_.kernel_launches += 7;
+        stats_.kernel_launches += 8;
     }
     stats_.entries = cnt[2 * kMaxSyncRounds];
     // per-image outcome: what the destuffing pass and the entropy stage found in the bytes

@@ -387,12 +387,22 @@ __device__ __forceinline__ LutView StageCta(K1Smem<S>& sm, uint32_t* lut, const 
 // halo threads compute is stored; round >= 1 verifies every CTA boundary against the owner's
 // result and repairs the few that differ.
 
-template <int S>
-__global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters) {
-    PdlEntry();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
-    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
+// What a thread of the synchronisation pass hands to the write pass when both run in one kernel (k1_fused).
+struct SyncOut {
+    Sub me;             // the thread's subsequence (halo slots: as decoded, not owned)
+    LutView lv;
+    uint32_t img;
+    uint32_t state;     // end state + block count of the subsequence
+    uint32_t used;      // key of the state it was decoded from (= the predecessor's end state once synchronised)
+    uint32_t nnz;       // coefficient entries it produces (padded)
+    bool live;          // false: the CTA left early (round > 0, nothing to repair)
+};
+
+// FUSED: round 0 inside k1_fused - the per-round counter counts nothing here (k1_fused counts boundary mismatches itself).
+template <int S, bool FUSED>
+__device__ __forceinline__ SyncOut SyncBody(const K1Args& a, K1Smem<S>& sm, uint32_t* lut, int round, int max_iters) {
+    SyncOut so;
+    so.live = false;
     const int tid = threadIdx.x;
     const uint32_t cta = blockIdx.x;
     const uint32_t img = ImageOfCta<T * K1Smem<S>::kSlotStride>(a, sm.words, cta);
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters)
         // boundary after a neighbour changed, or a chain an earlier round left unfinished)?
         int need0 = 0;
         if (me.active && !me.first) need0 = (StateKey(a.state[g - 1]) != a.used[g]);
-        if (!__syncthreads_or(need0)) return;
+        if (!__syncthreads_or(need0)) return so;
         if (me.active) {
             my_used = a.used[g];
             out = a.state[g];
@@ -500,7 +510,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters)
     }
     // A change of the state handed to the next CTA means that CTA must look again.
     const bool hands_over = mine && !me.last && (tid == T - 1);
-    if (hands_over && (old_out == kNoState || StateKey(old_out) != StateKey(out))) atomicAdd(&a.counters[round], 1u);
+    if (!FUSED && hands_over && (old_out == kNoState || StateKey(old_out) != StateKey(out))) atomicAdd(&a.counters[round], 1u);
     if (ndecodes) atomicAdd(&a.counters[kMaxSyncRounds + round], ndecodes);
 
     // CTA partial for the block-position scan: (contains a segment start, blocks after the last start)
@@ -519,6 +529,23 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters)
     if (mine && my_nnz) atomicAdd(&red[2], my_nnz);
     __syncthreads();
     if (tid == 0) a.cta_entries[cta] = red[2];
+    so.me = me;
+    so.lv = lv;
+    so.img = img;
+    so.state = out;
+    so.used = my_used;
+    so.nnz = my_nnz;
+    so.live = true;
+    return so;
+}
+
+template <int S>
+__global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters) {
+    PdlEntry();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
+    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
+    (void)SyncBody<S, false>(a, sm, lut, round, max_iters);
 }
 
 // ---------------------------------------------------------------- k1_scan
@@ -585,27 +612,17 @@ __global__ void __launch_bounds__(kScanThreads) k1_scan(K1Args a) {
 
 // ---------------------------------------------------------------- k1_write
 
-template <int S>
-__global__ void __launch_bounds__(T) k1_write(K1Args a) {
-    PdlEntry();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
-    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
+// The write pass behind the staging: `st`, `my_nnz`, `key` = the thread's synchronised end state, entry count and start
+// state. FUSED (k1_fused): the same CTA has just synchronised - what enters it from the picture's earlier CTAs is read
+// from their partials as soon as each has published them (`cta_flag`), and the state handed over at the CTA boundary is
+// checked against the owner's.
+template <int S, bool FUSED>
+__device__ __forceinline__ void WriteBody(const K1Args& a, K1Smem<S>& sm, const LutView& lv, uint32_t img, const ImageDesc& im, const Sub& me,
+                                          uint32_t st, uint32_t my_nnz, uint32_t key) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t cta = blockIdx.x;
-    const uint32_t img = ImageOfCta<T * K1Smem<S>::kSlotStride>(a, sm.words, cta);
-    const ImageDesc& im = a.images[img];
-    const int H = a.halo, TO = T - H;
-    const int64_t gi = int64_t(cta) * TO + tid - H;
-    const uint32_t g = uint32_t(gi);
-    Sub me = Locate<S>(a, im, gi, true);
-    if (tid < H) me.active = false;   // halo slots belong to the previous CTA
     if (cta == 0 && tid < 64) a.counters_next[tid] = 0;   // the next batch's counters (this batch's are read back after K3)
-    const LutView lv = StageCta<S>(sm, lut, a, im, me);
-
-    const uint32_t st = me.active ? a.state[g] : 0;
     const uint32_t nb = StateBlocks(st);
-    const uint32_t my_nnz = me.active ? a.nnz[g] : 0;
     // Two scans over the CTA: block positions (segmented: a segment start resets the count) and
     // entry offsets (plain, they run through the whole image).
     uint32_t v = nb, e = my_nnz;
@@ -644,8 +661,17 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
         uint2 part = make_uint2(0u, 0u);
         uint32_t ents = 0;
         if (k < cta) {
-            part = a.cta_partial[k];
-            ents = a.cta_entries[k];
+            if (FUSED) {   // an earlier CTA (lower index: dispatched before this one, it never waits for a later one)
+                uint32_t f;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.cta_flag + k) : "memory");
+                } while (f == 0u);
+                part = __ldcg(a.cta_partial + k);
+                ents = __ldcg(a.cta_entries + k);
+            } else {
+                part = a.cta_partial[k];
+                ents = a.cta_entries[k];
+            }
         }
         const uint32_t starts = __ballot_sync(0xFFFFFFFFu, part.x != 0);
         const int from = starts ? 31 - __clz(starts) : 0;
@@ -689,8 +715,6 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     // with the DC). No clearing, no read-modify-write, no ownership hand-over: a thread decodes
     // exactly the symbols that start inside its subsequence, as in the counting passes.
     const SegmentDesc sd = a.segments[me.seg];
-    uint32_t key = 0;
-    if (!me.first) key = StateKey(a.state[g - 1]);
     const uint32_t blk0 = sd.blk_first + excl, limit = sd.blk_first + sd.blk_count;
     // running pointers: the current block's record {end-of-entries index, DC} and the next 32-byte
     // entry group of this thread's run; the run never leaves its reservation [n, n_end), the
@@ -782,6 +806,68 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
         reinterpret_cast<uint4*>(ep)[0] = make_uint4(kPadEntry, kPadEntry, kPadEntry, kPadEntry);
         reinterpret_cast<uint4*>(ep)[1] = make_uint4(kPadEntry, kPadEntry, kPadEntry, kPadEntry);
     }
+}
+
+template <int S>
+__global__ void __launch_bounds__(T) k1_write(K1Args a) {
+    PdlEntry();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
+    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
+    const int tid = threadIdx.x;
+    const uint32_t cta = blockIdx.x;
+    const uint32_t img = ImageOfCta<T * K1Smem<S>::kSlotStride>(a, sm.words, cta);
+    const ImageDesc& im = a.images[img];
+    const int H = a.halo, TO = T - H;
+    const int64_t gi = int64_t(cta) * TO + tid - H;
+    const uint32_t g = uint32_t(gi);
+    Sub me = Locate<S>(a, im, gi, true);
+    if (tid < H) me.active = false;   // halo slots belong to the previous CTA
+    const LutView lv = StageCta<S>(sm, lut, a, im, me);
+    const uint32_t st = me.active ? a.state[g] : 0;
+    const uint32_t my_nnz = me.active ? a.nnz[g] : 0;
+    uint32_t key = 0;
+    if (me.active && !me.first) key = StateKey(a.state[g - 1]);
+    WriteBody<S, false>(a, sm, lv, img, im, me, st, my_nnz, key);
+}
+
+// ---------------------------------------------------------------- k1_fused
+//
+// Counting and write pass in ONE kernel for batches of small pictures (no picture has more than 32 K1 CTAs): a CTA
+// synchronises its subsequences exactly as round 0 of k1_sync does, publishes its block / entry counts and the state
+// it hands over, and goes straight on to write - the bytes and the tables are still in shared memory (the second
+// staging, a launch and its tail are saved), and while one picture's CTAs walk their chains the others' already
+// write. What the verifying round of k1_sync checks is checked here by the CTA itself: the state its halo threads
+// derived for its first subsequence must be the one the owner (the CTA before it) ended on; every mismatch is counted
+// in counters[0], and the host then falls back to the separate kernels for the batch (none on the benchmark batches,
+// forced in tests with ROCJPEG_B200_HALO=1).
+template <int S>
+__global__ void __launch_bounds__(T) k1_fused(K1Args a, int max_iters) {
+    PdlEntry();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
+    K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
+    const int tid = threadIdx.x;
+    const uint32_t cta = blockIdx.x;
+    SyncOut so = SyncBody<S, true>(a, sm, lut, 0, max_iters);
+    // this CTA's counts and states are in global memory: let the picture's later CTAs see them
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.cta_flag + cta), "r"(1u) : "memory");
+    const int H = a.halo;
+    const ImageDesc& im = a.images[so.img];
+    // the state entering the CTA's first own subsequence came from the halo: is it what the owner ended on?
+    if (tid == H && so.me.active && !so.me.first && cta > 0) {
+        uint32_t f;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.cta_flag + cta - 1) : "memory");
+        } while (f == 0u);
+        const uint32_t g = uint32_t(int64_t(cta) * (T - H));
+        if (StateKey(__ldcg(a.state + g - 1)) != so.used) atomicAdd(&a.counters[0], 1u);
+    }
+    Sub me = so.me;
+    if (tid < H) me.active = false;   // halo slots belong to the previous CTA
+    WriteBody<S, true>(a, sm, so.lv, so.img, im, me, me.active ? so.state : 0u, me.active ? so.nnz : 0u, so.used);
 }
 
 // ---------------------------------------------------------------- DC prediction
@@ -1067,6 +1153,13 @@ __global__ void __launch_bounds__(kDcImageThreads) dc_image(K1Args a) {
     }
 }
 
+// Before the separate kernels redo a batch the fused kernel mis-speculated on: what its write pass reported per picture
+// ("ran out of bytes") came from wrong start states.
+__global__ void k1_clear_short(K1Args a) {
+    const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i < a.nimages) a.status[i].flags &= ~kDecodeShort;
+}
+
 template <int S>
 cudaError_t SyncImpl(const K1Args& a, int round, cudaStream_t stream, int max_iters = T + 1) {
     static_assert(S <= 128, "the packed decoder state holds bit positions below 2048");
@@ -1085,6 +1178,26 @@ cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream, int ma
         case 32: return SyncImpl<32>(a, round, stream, max_iters);
         case 64: return SyncImpl<64>(a, round, stream, max_iters);
         case 128: return SyncImpl<128>(a, round, stream, max_iters);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t LaunchK1ClearShort(const K1Args& a, cudaStream_t stream) {
+    if (a.nimages <= 0) return cudaSuccess;
+    k1_clear_short<<<dim3((a.nimages + 255) / 256), dim3(256), 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t LaunchK1Fused(const K1Args& a, cudaStream_t stream) {
+    if (a.total_ctas == 0) return cudaSuccess;
+    const int max_iters = T + 1;
+    switch (a.sub_bytes) {
+        case 32: { const size_t smem = sizeof(K1Smem<32>) + a.lut_smem_bytes; if (smem > 48 * 1024) return cudaErrorInvalidValue;
+                   return LaunchPdl(k1_fused<32>, dim3(a.total_ctas), dim3(T), smem, stream, a, max_iters); }
+        case 64: { const size_t smem = sizeof(K1Smem<64>) + a.lut_smem_bytes; if (smem > 48 * 1024) return cudaErrorInvalidValue;
+                   return LaunchPdl(k1_fused<64>, dim3(a.total_ctas), dim3(T), smem, stream, a, max_iters); }
+        case 128: { const size_t smem = sizeof(K1Smem<128>) + a.lut_smem_bytes; if (smem > 48 * 1024) return cudaErrorInvalidValue;
+                    return LaunchPdl(k1_fused<128>, dim3(a.total_ctas), dim3(T), smem, stream, a, max_iters); }
         default: return cudaErrorInvalidValue;
     }
 }
@@ -1123,6 +1236,9 @@ cudaError_t PreloadK1() {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_write<128>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_write<64>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_write<32>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_fused<128>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_fused<64>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_fused<32>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k1_scan);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_sums);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, dc_scan);

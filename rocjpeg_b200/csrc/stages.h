@@ -115,6 +115,7 @@ struct K1Args {
     uint2* cta_partial;           // per K1 CTA: (has segment start, blocks after the last start)
     uint32_t* cta_entries;        // per K1 CTA: coefficient entries of the CTA's subsequences
     uint2* cta_carry;             // per K1 CTA: (blocks, entries) entering it from the image's earlier CTAs (k1_scan)
+    uint32_t* cta_flag;           // per K1 CTA: k1_fused has published the CTA's counts and states (zeroed before the launch)
     int3* dc_partial;             // per DC tile: per-component DC sum after the tile's last reset
     int3* dc_carry;               // per DC tile: predictors entering it (dc_scan)
     uint32_t* counters;           // [kMaxSyncRounds] boundary changes per round, then [kMaxSyncRounds] decodes per round
@@ -140,6 +141,10 @@ struct K1Args {
 cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream, int max_iters = 0);
 // Final pass: positions from the block counts, coefficients and DC differences written.
 cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream);
+// Both in one kernel (batches whose pictures have at most 32 K1 CTAs, K1Args::inline_scan); counters[0] = CTA boundaries whose
+// handed-over state was not the owner's: non-zero -> run LaunchK1Sync rounds >= 1 and LaunchK1Write.
+cudaError_t LaunchK1Fused(const K1Args& a, cudaStream_t stream);
+cudaError_t LaunchK1ClearShort(const K1Args& a, cudaStream_t stream);   // before that fallback's LaunchK1Write
 // DC prediction: per-tile sums, then prefix; absolute DC written over the per-block differences.
 cudaError_t LaunchDcScan(const K1Args& a, cudaStream_t stream);
 

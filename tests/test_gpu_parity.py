@@ -115,6 +115,27 @@ def test_batched_mixed_everything(dec, orc):
     assert st.blocks > 0 and st.kernel_launches > 0
 
 
+def test_fused_entropy_kernel_falls_back_when_a_cta_boundary_does_not_hold(orc, monkeypatch):
+    """k1_fused (counting + write pass in one kernel) trusts the state its halo threads derive for the CTA's first subsequence
+    and checks it against the owner's: with a one-subsequence halo of 32 bytes a third of the boundaries fail, the host must
+    notice (counters[0]) and redo the batch with the separate kernels - pixels exact either way."""
+    monkeypatch.setenv("ROCJPEG_B200_HALO", "1")
+    monkeypatch.setenv("ROCJPEG_B200_SUBSEQ", "32")
+    datas = [datagen.make_jpeg(500, 375, css, seed=700 + i) for i, css in enumerate(("444", "422", "420", "444"))]
+    d2 = api.Decoder(api.BACKEND_HARDWARE, 0)
+    try:
+        _check_batch(d2, orc, datas, "rgb_planar")
+        assert d2.stats().sync_rounds > 1, "the fused kernel's boundary check never failed: the fallback was not exercised"
+        monkeypatch.setenv("ROCJPEG_B200_HALO", "16")
+        _check_batch(d2, orc, datas, "rgb_planar")
+        assert d2.stats().sync_rounds == 1   # the fused kernel alone
+        monkeypatch.setenv("ROCJPEG_B200_NO_K1_FUSE", "1")
+        _check_batch(d2, orc, datas, "yuv_planar")
+        assert d2.stats().sync_rounds == 2   # counting round + verifying round, then the write pass
+    finally:
+        d2.close()
+
+
 @pytest.mark.parametrize("S", [32, 64, 128])
 def test_every_subsequence_size(dec, orc, S, monkeypatch):
     monkeypatch.setenv("ROCJPEG_B200_SUBSEQ", str(S))
