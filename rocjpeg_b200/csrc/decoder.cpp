@@ -694,6 +694,7 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
         uint32_t most = 0;
         for (int i = 0; i < n; i++) most = std::max(most, h_img_cta0_[size_t(i) + 1] - h_img_cta0_[size_t(i)]);
         k1_.inline_scan = (most <= 32u && EnvInt("ROCJPEG_B200_NO_INLINE_SCAN", 0) == 0) ? 1 : 0;
+        k1_.fusable = most <= uint32_t(std::max(0, EnvInt("ROCJPEG_B200_K1_FUSE_CTAS", 256))) ? 1 : 0;
         uint32_t most_mcus = 0;
         for (int i = 0; i < n; i++) most_mcus = std::max(most_mcus, uint32_t(h_images_[size_t(i)].total_mcus));
         // one CTA per picture: a lone picture of 8000 MCUs is faster through the tiled kernels (0.013 against 0.06 ms
@@ -911,10 +912,10 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
         RJB_CUDA(cudaMemsetAsync(k1_.blk_rec, 0xFF, coef_blocks_ * sizeof(BlockRec), stream_));
         RJB_CUDA(cudaMemsetAsync(k1_.counters_next, 0, 256, stream_));
     }
-    // Counting and write pass of the entropy stage in one kernel when no picture has more than 32 K1 CTAs (k1_huffman.cu:
+    // Counting and write pass of the entropy stage in one kernel when no picture has more than 256 K1 CTAs (k1_huffman.cu:
     // k1_fused); ROCJPEG_B200_NO_K1_FUSE=1 or an explicit ROCJPEG_B200_SYNC_ROUNDS keep the separate kernels.
     const bool k1_fuse_ok = EnvInt("ROCJPEG_B200_NO_K1_FUSE", 0) == 0 && std::getenv("ROCJPEG_B200_SYNC_ROUNDS") == nullptr;
-    const bool k1_fused = k1_fuse_ok && k1_.inline_scan && k1_.total_ctas != 0;
+    const bool k1_fused = k1_fuse_ok && k1_.fusable && k1_.total_ctas != 0;
     if (k1_fused) RJB_CUDA(cudaMemsetAsync(k1_.cta_flag, 0, size_t(k1_.total_ctas) * 4, stream_));   // "published" flags of the CTAs
     // K0: end of slice, destuffing, restart intervals -> clean stream + segment table, all on the device
     if (!(include_upload && tiles_reduced_)) {   // cudaMemcpy upload, or a resident batch run again: the reduction is its own launch

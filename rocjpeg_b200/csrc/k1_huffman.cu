@@ -647,7 +647,44 @@ __device__ __forceinline__ void WriteBody(const K1Args& a, K1Smem<S>& sm, const 
     if (lane == 31) { wsum[warp] = v; wflag[warp] = f; wents[warp] = e; }
     // what enters this CTA from the previous CTAs of the image: k1_scan prepared it (a look-back here
     // would re-read every earlier partial of the image, quadratic for the 8192x8192 pictures)
-    if (!a.inline_scan) {
+    if (FUSED) {
+        // One lane per earlier CTA of the picture, 32 at a time from the nearest backwards, each read as soon as its owner has
+        // published it (a lower CTA index: dispatched before this one, and it never waits for a later one). Entries: plain sum.
+        // Blocks: the partials from the last CTA holding a restart-interval start on (its partial counts only the blocks
+        // after that start).
+        if (warp == 0) {
+            const int64_t first = int64_t(__ldg(a.img_cta0 + img));
+            uint32_t cb = 0, ents = 0;
+            bool open = true;
+            for (int64_t hi = int64_t(cta); hi > first; hi -= 32) {
+                const int64_t k = hi - 32 + lane;   // lane 31: the CTA just before the ones already summed
+                uint2 part = make_uint2(0u, 0u);
+                if (k >= first) {
+                    uint32_t f;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.cta_flag + k) : "memory");
+                    } while (f == 0u);
+                    part = __ldcg(a.cta_partial + k);
+                    ents += __ldcg(a.cta_entries + k);
+                }
+                if (open) {
+                    const uint32_t starts = __ballot_sync(0xFFFFFFFFu, part.x != 0);
+                    const int from = starts ? 31 - __clz(starts) : 0;
+                    if (lane >= from) cb += part.y;
+                    open = starts == 0u;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                cb += __shfl_xor_sync(0xFFFFFFFFu, cb, d);
+                ents += __shfl_xor_sync(0xFFFFFFFFu, ents, d);
+            }
+            if (lane == 0) {
+                carry_s[0] = cb;
+                carry_s[1] = ents;
+            }
+        }
+    } else if (!a.inline_scan) {
         if (tid == 0) {
             const uint2 cin = a.cta_carry[cta];
             carry_s[0] = cin.x;
@@ -661,17 +698,8 @@ __device__ __forceinline__ void WriteBody(const K1Args& a, K1Smem<S>& sm, const 
         uint2 part = make_uint2(0u, 0u);
         uint32_t ents = 0;
         if (k < cta) {
-            if (FUSED) {   // an earlier CTA (lower index: dispatched before this one, it never waits for a later one)
-                uint32_t f;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.cta_flag + k) : "memory");
-                } while (f == 0u);
-                part = __ldcg(a.cta_partial + k);
-                ents = __ldcg(a.cta_entries + k);
-            } else {
-                part = a.cta_partial[k];
-                ents = a.cta_entries[k];
-            }
+            part = a.cta_partial[k];
+            ents = a.cta_entries[k];
         }
         const uint32_t starts = __ballot_sync(0xFFFFFFFFu, part.x != 0);
         const int from = starts ? 31 - __clz(starts) : 0;
@@ -833,7 +861,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
 
 // ---------------------------------------------------------------- k1_fused
 //
-// Counting and write pass in ONE kernel for batches of small pictures (no picture has more than 32 K1 CTAs): a CTA
+// Counting and write pass in ONE kernel for pictures of up to 256 K1 CTAs (4 MB of scan at 128-byte subsequences): a CTA
 // synchronises its subsequences exactly as round 0 of k1_sync does, publishes its block / entry counts and the state
 // it hands over, and goes straight on to write - the bytes and the tables are still in shared memory (the second
 // staging, a launch and its tail are saved), and while one picture's CTAs walk their chains the others' already

@@ -132,6 +132,7 @@ struct K1Args {
     int halo;                     // threads of a CTA that re-decode the subsequences before the CTA's own
     int inline_scan;              // no image has more than 32 K1 CTAs: k1_write sums the partials of the image's earlier CTAs
                                   // itself (one warp, one load each) and k1_scan is not launched
+    int fusable;                  // no image has more than 256 K1 CTAs: counting and write pass may run as one kernel (k1_fused)
     int dc_image;                 // no image has more than kDcImageMaxMcus MCUs: one CTA per image integrates its DC
                                   // differences in ONE launch (dc_image) instead of sums / scan / apply
 };
@@ -141,7 +142,7 @@ struct K1Args {
 cudaError_t LaunchK1Sync(const K1Args& a, int round, cudaStream_t stream, int max_iters = 0);
 // Final pass: positions from the block counts, coefficients and DC differences written.
 cudaError_t LaunchK1Write(const K1Args& a, cudaStream_t stream);
-// Both in one kernel (batches whose pictures have at most 32 K1 CTAs, K1Args::inline_scan); counters[0] = CTA boundaries whose
+// Both in one kernel (batches whose pictures have at most 256 K1 CTAs, K1Args::fusable); counters[0] = CTA boundaries whose
 // handed-over state was not the owner's: non-zero -> run LaunchK1Sync rounds >= 1 and LaunchK1Write.
 cudaError_t LaunchK1Fused(const K1Args& a, cudaStream_t stream);
 cudaError_t LaunchK1ClearShort(const K1Args& a, cudaStream_t stream);   // before that fallback's LaunchK1Write
