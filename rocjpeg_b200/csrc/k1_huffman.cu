@@ -400,11 +400,10 @@ struct SyncOut {
 
 // FUSED: round 0 inside k1_fused - the per-round counter counts nothing here (k1_fused counts boundary mismatches itself).
 template <int S, bool FUSED>
-__device__ __forceinline__ SyncOut SyncBody(const K1Args& a, K1Smem<S>& sm, uint32_t* lut, int round, int max_iters) {
+__device__ __forceinline__ SyncOut SyncBody(const K1Args& a, K1Smem<S>& sm, uint32_t* lut, int round, int max_iters, const uint32_t cta) {
     SyncOut so;
     so.live = false;
     const int tid = threadIdx.x;
-    const uint32_t cta = blockIdx.x;
     const uint32_t img = ImageOfCta<T * K1Smem<S>::kSlotStride>(a, sm.words, cta);
     const ImageDesc& im = a.images[img];
     const int H = a.halo, TO = T - H;
@@ -545,7 +544,7 @@ __global__ void __launch_bounds__(T) k1_sync(K1Args a, int round, int max_iters)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
     K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
-    (void)SyncBody<S, false>(a, sm, lut, round, max_iters);
+    (void)SyncBody<S, false>(a, sm, lut, round, max_iters, blockIdx.x);
 }
 
 // ---------------------------------------------------------------- k1_scan
@@ -618,9 +617,8 @@ __global__ void __launch_bounds__(kScanThreads) k1_scan(K1Args a) {
 // checked against the owner's.
 template <int S, bool FUSED>
 __device__ __forceinline__ void WriteBody(const K1Args& a, K1Smem<S>& sm, const LutView& lv, uint32_t img, const ImageDesc& im, const Sub& me,
-                                          uint32_t st, uint32_t my_nnz, uint32_t key) {
+                                          uint32_t st, uint32_t my_nnz, uint32_t key, const uint32_t cta) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t cta = blockIdx.x;
     if (cta == 0 && tid < 64) a.counters_next[tid] = 0;   // the next batch's counters (this batch's are read back after K3)
     const uint32_t nb = StateBlocks(st);
     // Two scans over the CTA: block positions (segmented: a segment start resets the count) and
@@ -856,7 +854,7 @@ __global__ void __launch_bounds__(T) k1_write(K1Args a) {
     const uint32_t my_nnz = me.active ? a.nnz[g] : 0;
     uint32_t key = 0;
     if (me.active && !me.first) key = StateKey(a.state[g - 1]);
-    WriteBody<S, false>(a, sm, lv, img, im, me, st, my_nnz, key);
+    WriteBody<S, false>(a, sm, lv, img, im, me, st, my_nnz, key, cta);
 }
 
 // ---------------------------------------------------------------- k1_fused
@@ -876,8 +874,13 @@ __global__ void __launch_bounds__(T) k1_fused(K1Args a, int max_iters) {
     uint32_t* const lut = reinterpret_cast<uint32_t*>(smem_raw);
     K1Smem<S>& sm = *reinterpret_cast<K1Smem<S>*>(smem_raw + a.lut_smem_bytes);
     const int tid = threadIdx.x;
-    const uint32_t cta = blockIdx.x;
-    SyncOut so = SyncBody<S, true>(a, sm, lut, 0, max_iters);
+    // Which CTA's work this is: a ticket, not blockIdx - the waits below are for lower indices, and a ticket holder
+    // knows that every lower ticket has been drawn by a CTA that is running (whatever order the grid is dispatched in).
+    __shared__ uint32_t s_ticket;
+    if (tid == 0) s_ticket = atomicAdd(a.cta_flag + a.total_ctas, 1u);
+    __syncthreads();
+    const uint32_t cta = s_ticket;
+    SyncOut so = SyncBody<S, true>(a, sm, lut, 0, max_iters, cta);
     // this CTA's counts and states are in global memory: let the picture's later CTAs see them
     __threadfence();
     __syncthreads();
@@ -895,7 +898,7 @@ __global__ void __launch_bounds__(T) k1_fused(K1Args a, int max_iters) {
     }
     Sub me = so.me;
     if (tid < H) me.active = false;   // halo slots belong to the previous CTA
-    WriteBody<S, true>(a, sm, so.lv, so.img, im, me, me.active ? so.state : 0u, me.active ? so.nnz : 0u, so.used);
+    WriteBody<S, true>(a, sm, so.lv, so.img, im, me, me.active ? so.state : 0u, me.active ? so.nnz : 0u, so.used, cta);
 }
 
 // ---------------------------------------------------------------- DC prediction

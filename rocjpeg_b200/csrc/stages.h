@@ -115,7 +115,7 @@ struct K1Args {
     uint2* cta_partial;           // per K1 CTA: (has segment start, blocks after the last start)
     uint32_t* cta_entries;        // per K1 CTA: coefficient entries of the CTA's subsequences
     uint2* cta_carry;             // per K1 CTA: (blocks, entries) entering it from the image's earlier CTAs (k1_scan)
-    uint32_t* cta_flag;           // per K1 CTA: k1_fused has published the CTA's counts and states (zeroed before the launch)
+    uint32_t* cta_flag;           // per K1 CTA: k1_fused has published the CTA's counts and states; [total_ctas] = its ticket counter (all zeroed before the launch)
     int3* dc_partial;             // per DC tile: per-component DC sum after the tile's last reset
     int3* dc_carry;               // per DC tile: predictors entering it (dc_scan)
     uint32_t* counters;           // [kMaxSyncRounds] boundary changes per round, then [kMaxSyncRounds] decodes per round
