@@ -276,9 +276,42 @@ int Decoder::Initialize() {
 }
 
 namespace {
-// Device that owns a device pointer; -1 for anything else (host memory, null, unknown).
-int DeviceOfPointer(const void* p) {
+// Device that owns a device pointer; -1 for anything else (host memory, null, unknown). *base / *size (optional) = the
+// allocation the pointer lies in: destinations carved from one allocation (a framework's caching allocator) cost one
+// driver query, not one per picture.
+typedef int (*PointerAttributesFn)(unsigned int, int*, void**, unsigned long long);
+PointerAttributesFn DriverPointerAttributes() {
+    static const PointerAttributesFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttributes", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<PointerAttributesFn>(f);
+    }();
+    return fn;
+}
+
+int DeviceOfPointer(const void* p, uintptr_t* base = nullptr, size_t* size = nullptr) {
+    if (base) *base = 0;
+    if (size) *size = 0;
     if (!p) return -1;
+    if (PointerAttributesFn fn = DriverPointerAttributes()) {
+        // CU_POINTER_ATTRIBUTE_MEMORY_TYPE = 2, DEVICE_ORDINAL = 9, RANGE_START_ADDR = 11, RANGE_SIZE = 12
+        int which[4] = {2, 9, 11, 12};
+        unsigned int mem_type = 0;
+        int ordinal = -1;
+        unsigned long long start = 0;
+        size_t bytes = 0;
+        void* out[4] = {&mem_type, &ordinal, &start, &bytes};
+        if (fn(4, which, out, static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(p))) == 0) {
+            if (mem_type != 2u /* CU_MEMORYTYPE_DEVICE */) return -1;
+            if (base) *base = uintptr_t(start);
+            if (size) *size = bytes;
+            return ordinal;
+        }
+    }
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -1233,8 +1266,14 @@ int Decoder::DecodeSharded(const StreamParser* const* streams, int n, const Deco
     // samples' case - are dealt by the longest-processing-time rule over all devices, and those that land on a peer
     // are delivered over NVLink.
     std::vector<int> fixed(static_cast<size_t>(n), -1), owner(static_cast<size_t>(n), 0);
+    uintptr_t range_base = 0;
+    size_t range_size = 0;
+    int range_dev = -1;
     for (int i = 0; i < n; i++) {
-        const int dev = DeviceOfPointer(dsts[i].channel[0]);
+        const uintptr_t ptr = reinterpret_cast<uintptr_t>(dsts[i].channel[0]);
+        if (!(range_size != 0 && ptr >= range_base && ptr - range_base < range_size))   // not in the allocation asked about last
+            range_dev = DeviceOfPointer(dsts[i].channel[0], &range_base, &range_size);
+        const int dev = range_dev;
         for (int d = 1; d < ndev; d++)
             if (dev == peers_[size_t(d - 1)]->device_id()) fixed[size_t(i)] = d;
         if (dev >= 0 && dev != device_id_ && fixed[size_t(i)] < 0)
