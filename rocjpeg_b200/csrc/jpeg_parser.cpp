@@ -486,6 +486,7 @@ void StreamParser::ExtractEntropyData(const uint8_t* d, size_t length, HostScan*
 
 const HostScan& StreamParser::host_scan() const {
     std::lock_guard<std::mutex> lock(mutex_);
+    EnsureStagedLocked();
     if (!host_scan_.done && p_.valid && raw_.host) ExtractEntropyData(raw_.host, raw_.nbytes, &host_scan_);
     return host_scan_;
 }
@@ -555,6 +556,8 @@ const uint8_t* DeviceAliasOf(const uint8_t* p, uintptr_t* range_base, size_t* ra
 // otherwise through one copy into pooled page-locked staging (the only per-byte work of a parse).
 void StreamParser::AdoptSource(const uint8_t* scan, size_t nbytes) {
     raw_ = RawScan();
+    pending_src_ = nullptr;
+    pending_len_ = 0;
     raw_.nbytes = uint32_t(nbytes);
     if (const uint8_t* dev = DeviceAliasOf(scan, &raw_.range_base, &raw_.range_size)) {
         raw_.host = scan;
@@ -564,11 +567,30 @@ void StreamParser::AdoptSource(const uint8_t* scan, size_t nbytes) {
     }
     uint8_t* st = staging_.Reserve(nbytes + 64);
     if (!st) return;   // raw_.host stays null: the decode reports OUT_OF_MEMORY
-    std::memcpy(st, scan, nbytes);
     std::memset(st + nbytes, 0xFF, 64 - (nbytes & 15));   // what the upload rounds up to
     raw_.host = st;
     raw_.dev = staging_.pinned() ? st : nullptr;
     if (raw_.dev) (void)DeviceAliasOf(st, &raw_.range_base, &raw_.range_size);   // the pool's slab
+    // the copy itself waits for the decode call (EnsureStaged) - unless asked not to, or there is no driver (host-only tests)
+    static const bool eager = [] {
+        const char* v = std::getenv("ROCJPEG_B200_EAGER_COPY");
+        return v && *v == '1';
+    }();
+    pending_src_ = scan;
+    pending_len_ = nbytes;
+    if (eager || !raw_.dev) EnsureStagedLocked();
+}
+
+void StreamParser::EnsureStagedLocked() const {
+    if (!pending_src_) return;
+    std::memcpy(const_cast<uint8_t*>(raw_.host), pending_src_, pending_len_);
+    pending_src_ = nullptr;
+    pending_len_ = 0;
+}
+
+void StreamParser::EnsureStaged() const {
+    std::lock_guard<std::mutex> lock(mutex_);   // (the same handle may sit in a batch twice: two helper threads)
+    EnsureStagedLocked();
 }
 
 void StreamParser::BuildDecodeTables() {
@@ -685,6 +707,8 @@ void StreamParser::ResetFrame() {
     p_.nseg = 1;
     p_.features &= (kFeatDqt16 | kFeatHuffId23);   // what the kept tables use stays with them; the frame's part is per stream
     raw_ = RawScan();
+    pending_src_ = nullptr;
+    pending_len_ = 0;
     host_scan_.done = false;
     err_.clear();
     dht_cache_.Begin();

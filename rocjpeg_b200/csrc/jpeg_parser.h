@@ -170,6 +170,12 @@ class StreamParser {
     int ParseFile(const char* path);
     const ParsedJpeg& parsed() const { return p_; }
     const RawScan& raw() const { return raw_; }
+    // Pageable input is staged in page-locked memory lazily: Parse() only reserves the block, the bytes are copied when the
+    // decode call needs them (by its helper threads, several streams at a time, chunk by chunk alongside the uploads) - the
+    // caller's buffer is borrowed from rocJpegStreamParse until the decode returns, as the reference requires
+    // (src/rocjpeg_parser.cpp:413 keeps a pointer into it). Idempotent; a second decode of the handle finds the copy.
+    bool staging_pending() const { return pending_src_ != nullptr; }
+    void EnsureStaged() const;
     // Destuffed restart intervals computed on the host from the bytes Parse() was given (which must still
     // be valid, as the reference requires until the decode returns).
     const HostScan& host_scan() const;
@@ -186,6 +192,7 @@ class StreamParser {
     void ExtractEntropyData(const uint8_t* d, size_t length, HostScan* out) const;
     void BuildDecodeTables();
     void AdoptSource(const uint8_t* scan, size_t nbytes);
+    void EnsureStagedLocked() const;
     bool ParseLocked(const uint8_t* data, size_t length, bool data_is_file_buffer);
     void ResetFrame();
     // Table segments (DHT / DQT) of the stream being parsed against the previous stream's: while the payload bytes
@@ -211,6 +218,8 @@ class StreamParser {
     bool lut_valid_ = false;
     bool TablesFailed();              // a table segment was rejected: nothing of it may be reused by the next parse
     RawScan raw_;
+    mutable const uint8_t* pending_src_ = nullptr;   // pageable source not yet copied into staging_ (EnsureStaged)
+    mutable size_t pending_len_ = 0;
     PooledBuffer staging_;            // page-locked copy of pageable input
     PooledBuffer file_;               // a whole file read by ParseFile (page-locked)
     mutable HostScan host_scan_;

@@ -650,6 +650,36 @@ def _check_destuffed_batch(dec, datas, zero_copy, fmt="y", valid_pictures=True):
             assert dec.device_segment(i, k) == s.segment(k), f"image {i} restart interval {k} of {inf.num_segments}"
 
 
+def test_pageable_sources_are_staged_by_the_decode_call(dec, orc):
+    """Ordinary (pageable) buffers: rocJpegStreamParse reserves page-locked staging, the decode call copies the bytes (helper
+    threads, chunk by chunk). The buffer is borrowed until the first decode returns - as the reference requires - and not
+    needed afterwards: a second decode of the same handles finds the staged copy even if the buffer has been overwritten."""
+    import ctypes as C
+
+    names = [n for n in CASES if "extreme" not in n][:10]
+    datas = [load(n) for n in names] * 3          # 30 streams: several per helper thread
+    bufs_host = [C.create_string_buffer(d, len(d)) for d in datas]
+    streams, dests, keep = [], [], []
+    for d, hb in zip(datas, bufs_host):
+        s = api.JpegStream()
+        assert s.parse_ptr(C.addressof(hb), len(d), hb) == api.SUCCESS
+        inf = s.info()
+        assert not inf.source_is_zero_copy and inf.source_is_device_visible
+        rc, info = orc.parse(d)
+        dest, bufs, pitches, shapes = gu.alloc_outputs(orc, info, "rgb", (0, 0, 0, 0), pitch_pad=2)
+        streams.append(s); dests.append(dest); keep.append((bufs, pitches, shapes))
+    for rep in range(2):
+        assert dec.decode_batched(streams, api.make_params("rgb"), dests) == api.SUCCESS
+        for d, (bufs, pitches, shapes), name in zip(datas, keep, names * 3):
+            _, want = gu.oracle_outputs(orc, d, "rgb", (0, 0, 0, 0), pitches)
+            gu.assert_same(gu.fetch(bufs, pitches, shapes), want, f"pageable {name} pass {rep}")
+        for hb in bufs_host:                        # the caller's buffers are free to go after the first decode
+            C.memset(hb, 0x5A, len(hb))
+        for (bufs, _, _) in keep:
+            for t in bufs:
+                t.fill_(gu.FILL)
+
+
 @pytest.mark.parametrize("layout", ["packed", "gaps", "reversed", "duplicates", "no_merge"])
 def test_upload_plan_over_page_locked_arenas(orc, layout, monkeypatch):
     """Streams of one page-locked allocation are uploaded by one copy per run of neighbours (Lane::Build): packed files (one run),
