@@ -221,15 +221,24 @@ __global__ void __launch_bounds__(kFThreads, 6) k23_warp(K23Args a) {
     __shared__ uint32_t s_tab[3][64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = __ldg(a.tile_img_w + blockIdx.x);
-    const FusedImage& fi = a.fused[tile & 0xFFFFu];
-    const int mrow = int(tile >> 16), tx = int(blockIdx.x - fi.tile0) - mrow * int(fi.tiles_x);
-    const int ncomp = fi.ncomp;
-    for (int idx = tid; idx < ncomp * 64; idx += kFThreads) {
-        const int c = idx >> 6, code = idx & 63;
-        const int nat = kZigzag[(code + 63) & 63];
-        s_tab[c][code] = uint32_t(code == 1 ? 8 * 4 : ((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(a.qtables + size_t(fi.qidx[c]) * 64 + nat)) << 16);
+    const FusedImage& gfi = a.fused[tile & 0xFFFFu];
+    // the picture's record into shared memory: every warp reads a dozen of its fields, each a dependent global load otherwise
+    // (a quarter of the kernel's stall samples sat in the per-warp set-up, profiles/r03z_c3_hot.md)
+    __shared__ __align__(16) FusedImage s_fi;
+    static_assert(sizeof(FusedImage) % 16 == 0, "copied as 16-byte vectors");
+    if (tid < int(sizeof(FusedImage) / 16)) reinterpret_cast<uint4*>(&s_fi)[tid] = __ldg(reinterpret_cast<const uint4*>(&gfi) + tid);
+    {
+        const int ncomp_g = gfi.ncomp;
+        for (int idx = tid; idx < ncomp_g * 64; idx += kFThreads) {
+            const int c = idx >> 6, code = idx & 63;
+            const int nat = kZigzag[(code + 63) & 63];
+            s_tab[c][code] = uint32_t(code == 1 ? 8 * 4 : ((nat >> 3) * kRS + (nat & 7)) * 4) | (uint32_t(__ldg(a.qtables + size_t(gfi.qidx[c]) * 64 + nat)) << 16);
+        }
     }
     __syncthreads();
+    const FusedImage& fi = s_fi;
+    const int mrow = int(tile >> 16), tx = int(blockIdx.x - fi.tile0) - mrow * int(fi.tiles_x);
+    const int ncomp = fi.ncomp;
     const int mpt = fi.mpt, mcus_x = fi.mcus_x;
     const int mpw = mpt >> 3;                          // MCUs per warp: 4 (8-sample MCUs), 2 or 1
     const int m0 = tx * mpt + warp * mpw, nm = min(mpw, mcus_x - m0);
