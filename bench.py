@@ -602,10 +602,12 @@ def main():
                              "(issue_utilisation: committed ncu capture); every stage's own fraction is in `stages`"},
         "roofline_k1": {"bound": "latency/issue", "compressed_GB_s": round(scan / (k1_ms or 1e-9) / 1e6, 2), "ms": round(k1_ms, 4),
                         "sync_ms": round(stage_ms[2], 4), "write_ms": round(stage_ms[3], 4),
-                        "entries_written_GB_s": round((entries * 4 + blocks * 8) / (stage_ms[3] or 1e-9) / 1e6, 1),
+                        "entries_written_GB_s": round((entries * 4 + blocks * 8) / ((stage_ms[3] if stage_ms[3] > 0.005 else k1_ms) or 1e-9) / 1e6, 1),
+                        "fused": stage_ms[3] <= 0.005,
                         "issue_utilisation": measured_traffic(args.workload, "k1_issue"),
-                        "note": "entropy stage: compressed bitstream GB/s over k1_sync + k1_write; issue-slot utilisation from the "
-                                "committed ncu capture (profiles/)"},
+                        "note": "entropy stage: compressed bitstream GB/s over k1_sync + k1_write (fused: one kernel, k1_fused, its time under "
+                                "sync_ms; entries_written_GB_s then over the whole kernel); issue-slot utilisation from the committed "
+                                "ncu capture (profiles/)"},
         "stages": stages, "stages_note": "CUDA-event time per stage of the same resident batch on one pipeline lane "
                                          f"(stages serialised; that step takes {round(one_lane_ms, 4)} ms)",
         "k1": {"lanes": stats.lanes, "subsequence_bytes": stats.subsequence_bytes, "subsequences": int(stats.subsequences), "sync_rounds": stats.sync_rounds,
