@@ -719,6 +719,11 @@ int Lane::Build(const StreamParser* const* streams, int n, const DecodeParams& p
     k0_.nimages = n;
     k0_.total_tiles = k0tile;
     k0_.sub_bytes = S;
+    {
+        uint32_t most_tiles = 0;
+        for (int i = 0; i < n; i++) most_tiles = std::max(most_tiles, h_k0_tile0_[size_t(i) + 1] - h_k0_tile0_[size_t(i)]);
+        k0_.inline_scan = (most_tiles <= 32u && EnvInt("ROCJPEG_B200_NO_INLINE_SCAN", 0) == 0) ? 1 : 0;
+    }
     k1_.rec_fill_vecs = uint32_t((blk * sizeof(BlockRec) + 15) / 16);   // the slab leaves 256 bytes behind every array
     k1_.lut_smem_bytes = max_pairs * 2u * uint32_t(kFastSize) * 4u + max_sub * 4u;
     k1_.total_dc_tiles = dctile;
@@ -956,7 +961,7 @@ int Lane::LaunchAll(bool include_upload, int profiling_, cudaStream_t up, Upload
         stats_.kernel_launches++;
     }
     RJB_CUDA(LaunchK0Destuff(k0_, stream_));
-    stats_.kernel_launches += 2;
+    stats_.kernel_launches += k0_.inline_scan ? 1 : 2;
     RJB_CUDA(mark(2));
     if (k1_fused) {
         RJB_CUDA(LaunchK1Fused(k1_, stream_));

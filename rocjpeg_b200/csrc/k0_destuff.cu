@@ -57,6 +57,15 @@ __device__ __forceinline__ Elem ShflUp(const Elem& e, int d) {
     return r;
 }
 
+__device__ __forceinline__ Elem ShflDown(const Elem& e, int d) {
+    Elem r;
+    r.nrst = __shfl_down_sync(0xFFFFFFFFu, e.nrst, d);
+    r.tail = __shfl_down_sync(0xFFFFFFFFu, e.tail, d);
+    r.last_r = __shfl_down_sync(0xFFFFFFFFu, e.last_r, d);
+    r.flags = __shfl_down_sync(0xFFFFFFFFu, e.flags, d);
+    return r;
+}
+
 // A thread's 64 bytes of an image's uploaded data.
 //   kind kGeneral  anything else: a marker of any kind (FF not followed by 00), two stuffed bytes in one word, or a chunk
 //                  that reaches over an end of the scan - the per-piece code of k0_core.cuh handles it;
@@ -386,6 +395,7 @@ template <int S>
 __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
     PdlEntry();
     __shared__ Elem s_warp[kThreads / 32];
+    __shared__ Elem s_carry;
     __shared__ __align__(16) uint8_t s_stage[kThreads / 32][kStageBytes];
     __shared__ uint32_t s_fill_from;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -400,8 +410,28 @@ __global__ void __launch_bounds__(kThreads) k0_apply(K0Args a) {
     if (c.kind == kStuffed) DeleteHoles(c);
     Elem ex;
     if (tid == 0) s_fill_from = 0xFFFFFFFFu;
-    CtaScan(mine, plain, s_warp, &ex, nullptr);
-    {
+    if (a.inline_scan) {
+        // no picture has more than 32 tiles: the tile combines the prefix elements of the picture's earlier tiles itself (one lane
+        // each, in order) - k0_scan is not launched
+        if (warp == 0) {
+            const uint32_t k = im.k0_tile0 + uint32_t(lane);
+            Elem e{0u, 0u, 0u, 0u};
+            if (k < tile) {
+                const uint4 q = a.tile_sum[k];
+                e = Elem{q.x, q.y, q.z, q.w};
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {   // lane i ends up with e_i o e_{i+1} o ... (the empty element is neutral)
+                const Elem p = ShflDown(e, d);
+                if (lane + d < 32) e = Combine(e, p);
+            }
+            if (lane == 0) s_carry = e;
+        }
+    }
+    CtaScan(mine, plain, s_warp, &ex, nullptr);   // (ends with a CTA barrier: s_carry is visible behind it)
+    if (a.inline_scan) {
+        ex = Combine(s_carry, ex);
+    } else {
         const uint4 q = a.tile_carry[tile];
         ex = Combine(Elem{q.x, q.y, q.z, q.w}, ex);
     }
@@ -498,7 +528,8 @@ cudaError_t LaunchGatherReduce(const K0Args& a, const GatherItem* items, cudaStr
 
 cudaError_t LaunchK0Destuff(const K0Args& a, cudaStream_t stream) {
     if (a.total_tiles == 0) return cudaSuccess;
-    cudaError_t e = LaunchPdl(k0_scan, dim3(a.nimages), dim3(kThreads), 0, stream, a);
+    cudaError_t e = cudaSuccess;
+    if (!a.inline_scan) e = LaunchPdl(k0_scan, dim3(a.nimages), dim3(kThreads), 0, stream, a);
     if (e != cudaSuccess) return e;
     if (getenv("ROCJPEG_B200_DEBUG_SYNC")) {
         e = cudaStreamSynchronize(stream);

@@ -85,6 +85,7 @@ struct K0Args {
     int nimages;
     uint32_t total_tiles;
     int sub_bytes;                // S of the batch: intervals start on multiples of S
+    int inline_scan;              // no image has more than 32 tiles: k0_apply combines the earlier tiles' elements itself, no k0_scan
 };
 // Gather per-image raw bytes from mapped page-locked host memory into the raw arena.
 struct GatherItem {
