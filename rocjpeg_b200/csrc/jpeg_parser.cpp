@@ -651,14 +651,14 @@ void StreamParser::BuildDecodeTables() {
     // debug knob: a smaller second-level arena forces long codes onto the canonical search
     const char* cap_env = std::getenv("ROCJPEG_B200_SUBCAP");
     const uint32_t cap = (cap_env && *cap_env) ? uint32_t(std::atoi(cap_env)) : uint32_t(kSubCap);
-    // Decoder-form tables are a pure function of the DHT content: a process-wide cache lets the first parse of a new
-    // handle copy them (14 KiB) instead of building them (the reference's perf sample creates one handle per image; 256
-    // first parses took 4.2 ms, most of it here).
+    // Decoder-form tables are a pure function of the DHT content: a process-wide cache lets every handle that meets the
+    // same tables share ONE copy (the reference's perf sample creates one handle per image; 256 first parses took 4.2 ms,
+    // most of it building the tables and faulting in the 22 KiB each handle used to keep of its own).
     struct Cached {
         uint64_t hash;
         uint32_t cap;
         HuffSpec dc[kHuffIds], ac[kHuffIds];
-        HuffLutSet lut;
+        std::shared_ptr<const HuffLutSet> lut;
     };
     static std::mutex cache_mutex;
     static std::vector<std::unique_ptr<Cached>> cache;
@@ -666,17 +666,19 @@ void StreamParser::BuildDecodeTables() {
         std::lock_guard<std::mutex> lock(cache_mutex);
         for (const auto& c : cache)
             if (c->hash == h && c->cap == cap && std::memcmp(c->dc, p_.dc, sizeof(p_.dc)) == 0 && std::memcmp(c->ac, p_.ac, sizeof(p_.ac)) == 0) {
-                std::memcpy(&lut_, &c->lut, sizeof(lut_));
+                lut_ = c->lut;
                 lut_cap_ = cap;
                 lut_valid_ = true;
                 return;
             }
     }
-    std::memset(&lut_, 0, sizeof(lut_));
+    std::shared_ptr<HuffLutSet> built(new HuffLutSet());
+    std::memset(built.get(), 0, sizeof(HuffLutSet));
     for (int t = 0; t < kHuffIds; t++) {
-        if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, &lut_, cap);
-        if (p_.ac[t].present) BuildHuffLut(p_.ac[t], kHuffIds + t, &lut_, cap);
+        if (p_.dc[t].present) BuildHuffLut(p_.dc[t], t, built.get(), cap);
+        if (p_.ac[t].present) BuildHuffLut(p_.ac[t], kHuffIds + t, built.get(), cap);
     }
+    lut_ = built;
     lut_cap_ = cap;
     lut_valid_ = true;
     {
@@ -685,11 +687,20 @@ void StreamParser::BuildDecodeTables() {
         c->cap = cap;
         std::memcpy(c->dc, p_.dc, sizeof(p_.dc));
         std::memcpy(c->ac, p_.ac, sizeof(p_.ac));
-        std::memcpy(&c->lut, &lut_, sizeof(lut_));
+        c->lut = lut_;
         std::lock_guard<std::mutex> lock(cache_mutex);
-        if (cache.size() >= 16) cache.erase(cache.begin());   // oldest out
+        if (cache.size() >= 16) cache.erase(cache.begin());   // oldest out (handles that use it keep their reference)
         cache.push_back(std::move(c));
     }
+}
+
+const HuffLutSet& StreamParser::EmptyLut() {
+    static const HuffLutSet* empty = [] {
+        HuffLutSet* e = new HuffLutSet();
+        std::memset(e, 0, sizeof(HuffLutSet));
+        return e;
+    }();
+    return *empty;
 }
 
 // Everything of the previous stream except its tables (the reference zeroes its parameters on every parse,

@@ -26,6 +26,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -179,7 +180,7 @@ class StreamParser {
     // Destuffed restart intervals computed on the host from the bytes Parse() was given (which must still
     // be valid, as the reference requires until the decode returns).
     const HostScan& host_scan() const;
-    const HuffLutSet& lut() const { return lut_; }   // decoder-form tables of the last parsed stream
+    const HuffLutSet& lut() const { return lut_ ? *lut_ : EmptyLut(); }   // decoder-form tables of the last parsed stream
     const std::string& last_error() const { return err_; }
 
   private:
@@ -213,7 +214,10 @@ class StreamParser {
 
     mutable std::mutex mutex_;
     ParsedJpeg p_;
-    HuffLutSet lut_ = {};             // kept across parses while the DHT content does not change
+    // Decoder-form tables: shared with the process-wide cache (jpeg_parser.cpp: BuildDecodeTables) - a handle holds a
+    // reference, not 22 KiB of its own (creating 256 handles spent 3 ms faulting those pages in).
+    std::shared_ptr<const HuffLutSet> lut_;
+    static const HuffLutSet& EmptyLut();
     uint32_t lut_cap_ = 0;
     bool lut_valid_ = false;
     bool TablesFailed();              // a table segment was rejected: nothing of it may be reused by the next parse
