@@ -571,14 +571,15 @@ void StreamParser::AdoptSource(const uint8_t* scan, size_t nbytes) {
     raw_.host = st;
     raw_.dev = staging_.pinned() ? st : nullptr;
     if (raw_.dev) (void)DeviceAliasOf(st, &raw_.range_base, &raw_.range_size);   // the pool's slab
-    // the copy itself waits for the decode call (EnsureStaged) - unless asked not to, or there is no driver (host-only tests)
-    static const bool eager = [] {
-        const char* v = std::getenv("ROCJPEG_B200_EAGER_COPY");
-        return v && *v == '1';
-    }();
+    // The copy: here, on the caller's thread (default: callers that want it parallel parse from several threads, one handle
+    // each, as the reference's perf sample does) - or, with ROCJPEG_B200_DEFERRED_COPY=1, inside the decode call, by its helper
+    // threads, chunk by chunk ahead of each chunk's upload (a single-threaded caller with a large pageable batch: c3 1.9 -> 1.1 ms
+    // per batch, c4 26.6 -> 7.2 ms; but helper threads of several handles decoding at once oversubscribe a small host, and the
+    // caller's buffer must then stay valid until the decode returns, which is all the reference promises anyway).
+    const char* dv = std::getenv("ROCJPEG_B200_DEFERRED_COPY");
     pending_src_ = scan;
     pending_len_ = nbytes;
-    if (eager || !raw_.dev) EnsureStagedLocked();
+    if (!(dv && *dv == '1') || !raw_.dev) EnsureStagedLocked();
 }
 
 void StreamParser::EnsureStagedLocked() const {

@@ -171,10 +171,10 @@ class StreamParser {
     int ParseFile(const char* path);
     const ParsedJpeg& parsed() const { return p_; }
     const RawScan& raw() const { return raw_; }
-    // Pageable input is staged in page-locked memory lazily: Parse() only reserves the block, the bytes are copied when the
-    // decode call needs them (by its helper threads, several streams at a time, chunk by chunk alongside the uploads) - the
-    // caller's buffer is borrowed from rocJpegStreamParse until the decode returns, as the reference requires
-    // (src/rocjpeg_parser.cpp:413 keeps a pointer into it). Idempotent; a second decode of the handle finds the copy.
+    // Pageable input is copied into page-locked staging by Parse() - or, with ROCJPEG_B200_DEFERRED_COPY=1, when the decode
+    // call needs the bytes (by its helper threads, several streams at a time, chunk by chunk alongside the uploads; the
+    // caller's buffer is then borrowed from rocJpegStreamParse until the decode returns, as the reference requires:
+    // src/rocjpeg_parser.cpp:413 keeps a pointer into it). EnsureStaged is idempotent; a second decode finds the copy.
     bool staging_pending() const { return pending_src_ != nullptr; }
     void EnsureStaged() const;
     // Destuffed restart intervals computed on the host from the bytes Parse() was given (which must still

@@ -650,11 +650,16 @@ def _check_destuffed_batch(dec, datas, zero_copy, fmt="y", valid_pictures=True):
             assert dec.device_segment(i, k) == s.segment(k), f"image {i} restart interval {k} of {inf.num_segments}"
 
 
-def test_pageable_sources_are_staged_by_the_decode_call(dec, orc):
-    """Ordinary (pageable) buffers: rocJpegStreamParse reserves page-locked staging, the decode call copies the bytes (helper
-    threads, chunk by chunk). The buffer is borrowed until the first decode returns - as the reference requires - and not
-    needed afterwards: a second decode of the same handles finds the staged copy even if the buffer has been overwritten."""
+@pytest.mark.parametrize("deferred", [False, True])
+def test_pageable_sources_are_staged_by_the_decode_call(dec, orc, deferred, monkeypatch):
+    """Ordinary (pageable) buffers are copied into page-locked staging by rocJpegStreamParse - or, with
+    ROCJPEG_B200_DEFERRED_COPY=1, by the decode call (helper threads, chunk by chunk); the buffer is then borrowed until the
+    first decode returns, as the reference requires. Either way it is not needed afterwards: a second decode of the same
+    handles finds the staged copy even if the buffer has been overwritten."""
     import ctypes as C
+
+    if deferred:
+        monkeypatch.setenv("ROCJPEG_B200_DEFERRED_COPY", "1")
 
     names = [n for n in CASES if "extreme" not in n][:10]
     datas = [load(n) for n in names] * 3          # 30 streams: several per helper thread
