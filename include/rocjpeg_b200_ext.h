@@ -26,12 +26,14 @@
 extern "C" {
 #endif
 
-#define ROCJPEG_B200_STAGE_COUNT 7 /* upload, destuff, huffman-sync, huffman-write, dc, idct, output */
+#define ROCJPEG_B200_STAGE_COUNT 7 /* upload, destuff, huffman-sync (the whole entropy stage when it runs as one kernel), huffman-write, dc, idct,
+                                      output (the fused IDCT + output kernels included) */
 
 typedef struct {
     float stage_ms[ROCJPEG_B200_STAGE_COUNT]; /* CUDA-event time of each stage on the decoder's stream */
     float total_ms;                           /* first to last event */
-    uint32_t sync_rounds;                     /* k1_sync launches (2 when the stream self-synchronises) */
+    uint32_t sync_rounds;                     /* 1: the fused entropy kernel alone (k1_fused, its CTA-boundary check held); else k1_sync
+                                                 launches (2 when the stream self-synchronises within the counting + verifying round) */
     uint32_t decodes_per_round[8];            /* subsequence decodes performed in each round */
     uint64_t scan_bytes;                      /* entropy-coded bytes of the batch as uploaded (before destuffing) */
     uint64_t blocks;                          /* 8x8 blocks decoded */
